@@ -1,0 +1,100 @@
+"""Loader for the UNMODIFIED reference modules (test infrastructure only).
+
+Only tests/, ``__graft_entry__.smoke()``, ``oracle/make_golden.py`` and bench.py's
+``cpu_baseline`` / ``--impl reference`` leg may import this file.  The product package
+``hcunet_b200`` never does.
+
+The reference (`/root/reference/hcat/unet.py`, `/root/reference/hcat/loss.py`) cannot be
+imported with a plain ``import hcat`` in this image: ``hcat/__init__.py:1-5`` eagerly imports
+``segment``/``main`` (skimage, GPy, matplotlib ... absent) and ``hcat/unet.py:6-9`` imports
+``hcat.utils.pad_image_with_reflections``.  We register an empty ``hcat`` package and a stub
+``hcat.utils`` in ``sys.modules`` and then execute the two reference source files unmodified
+from where they lie.  ``/root/reference`` only exists in the build
+container, never on the GPU box, so everything here is gated on ``reference_available()``.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("HCUNET_REFERENCE_ROOT", "/root/reference")
+
+_cache = {}
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "hcat", "unet.py"))
+
+
+def _load(name: str, filename: str):
+    key = (name, filename)
+    if key in _cache:
+        return _cache[key]
+    # private names so a real ``hcat`` shim package (repo root) is never shadowed
+    pkg_name = "_hcat_reference"
+    if pkg_name not in sys.modules:
+        pkg = types.ModuleType(pkg_name)
+        pkg.__path__ = []  # mark as package
+        sys.modules[pkg_name] = pkg
+    saved = {k: sys.modules.get(k) for k in ("hcat", "hcat.utils")}
+    stub_pkg = types.ModuleType("hcat")
+    stub_pkg.__path__ = []
+    stub_utils = types.ModuleType("hcat.utils")
+
+    def pad_image_with_reflections(*a, **k):  # only used by the unfinished ``evaluate``
+        raise NotImplementedError("stub: hcat.utils is outside the hot path")
+
+    stub_utils.pad_image_with_reflections = pad_image_with_reflections
+    sys.modules["hcat"] = stub_pkg
+    sys.modules["hcat.utils"] = stub_utils
+    try:
+        spec = importlib.util.spec_from_file_location(f"{pkg_name}.{name}", filename)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cache[key] = mod
+    return mod
+
+
+def load_reference_unet():
+    """Return the reference ``hcat.unet`` module (unmodified source)."""
+    if not reference_available():
+        raise FileNotFoundError(f"reference not mounted at {REFERENCE_ROOT}")
+    return _load("unet", os.path.join(REFERENCE_ROOT, "hcat", "unet.py"))
+
+
+def load_reference_loss():
+    """Return the reference ``hcat.loss`` module (unmodified source)."""
+    if not reference_available():
+        raise FileNotFoundError(f"reference not mounted at {REFERENCE_ROOT}")
+    return _load("loss", os.path.join(REFERENCE_ROOT, "hcat", "loss.py"))
+
+
+def build_reference_unet(**kwargs):
+    """Construct the reference Unet_Constructor.
+
+    2D models cannot be constructed by the reference as shipped (`hcat/unet.py:293-303`
+    raises).  For ``image_dimensions == 2`` we alias ``torch.nn.modules.conv.ConvTranspose3d``
+    to ``ConvTranspose2d`` DURING CONSTRUCTION ONLY so the gate at `unet.py:293` passes
+    (SURVEY.md section 8c "2D oracle").  This deviation is disclosed wherever 2D parity is
+    reported.
+    """
+    import torch
+
+    ref = load_reference_unet()
+    if kwargs.get("image_dimensions", 2) == 2:
+        conv_mod = torch.nn.modules.conv
+        saved = conv_mod.ConvTranspose3d
+        conv_mod.ConvTranspose3d = torch.nn.ConvTranspose2d
+        try:
+            return ref.Unet_Constructor(**kwargs)
+        finally:
+            conv_mod.ConvTranspose3d = saved
+    return ref.Unet_Constructor(**kwargs)

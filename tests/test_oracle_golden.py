@@ -1,0 +1,117 @@
+"""Pins the oracle restatement (oracle/unet_oracle.py) to the reference.
+
+(a) against the committed golden vectors minted by executing the unmodified reference
+    (tests/golden/*.pt, oracle/make_golden.py), and
+(b) when /root/reference is mounted (build container only), against the live reference modules.
+"""
+import pytest
+import torch
+
+from conftest import MODEL_CASES, load_golden
+from oracle import unet_oracle as O
+from oracle.ref_loader import build_reference_unet, load_reference_loss, reference_available
+
+
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_oracle_matches_golden_model(name):
+    fx = load_golden(name)
+    loss, logits, grads, newbuf = O.train_step_grads(fx["state_dict"], fx["kwargs"], fx["x"], fx["mask"], fx["pwl"])
+    # same torch build, same primitive ops in the same order => bit-exact
+    assert torch.equal(logits, fx["logits_train"])
+    assert torch.equal(loss, fx["loss"])
+    for k, g in fx["grads"].items():
+        assert torch.equal(grads[k], g), k
+    for k, v in fx["buffers_after"].items():
+        assert torch.equal(newbuf[k], v), k
+    sd = dict(fx["state_dict"])
+    sd.update(newbuf)
+    with torch.no_grad():
+        ev, _ = O.unet_forward(sd, fx["kwargs"], fx["x"], training=False)
+    assert torch.equal(ev, fx["logits_eval"])
+
+
+def test_oracle_matches_golden_losses():
+    fx = torch.load(__import__("os").path.join(__import__("conftest").GOLDEN, "loss_cases.pt"), weights_only=False)
+    assert len(fx["cases"]) >= 20
+    for c in fx["cases"]:
+        p = c["pred"].clone().requires_grad_(True)
+        if c["fn"] == "cross_entropy":
+            if c["method"] == "random":
+                torch.manual_seed(5)
+                v = O.cross_entropy(p, c["mask"], c["pwl"], c["method"], c["num_random_pixels"])
+            else:
+                v = O.cross_entropy(p, c["mask"], c["pwl"], c["method"])
+        else:
+            v = getattr(O, c["fn"])(p, c["mask"])
+        v.backward()
+        assert torch.equal(v.detach(), c["value"]), (c["fn"], c.get("method"), c.get("variant"))
+        assert torch.equal(p.grad, c["grad"]), (c["fn"], c.get("method"), c.get("variant"))
+
+
+def test_loss_error_behaviour():
+    p = torch.zeros(1, 1, 4, 4, 2)
+    with pytest.raises(ValueError):
+        O.cross_entropy(p, p, p, method="nope")
+    with pytest.raises(ValueError):
+        O.cross_entropy(p, p, p, method="random")
+    with pytest.raises(ValueError):
+        O.cross_entropy(p, p, p, method="random", num_random_pixels=1)
+    with pytest.raises(IndexError):
+        O.cross_entropy(torch.zeros(4, 4, 4), torch.zeros(4, 4, 4), None)
+    # pwl=None => weight 2 (loss.py:46-48)
+    a = O.cross_entropy(p + 0.3, torch.ones_like(p), None)
+    b = O.cross_entropy(p + 0.3, torch.ones_like(p), torch.ones_like(p))
+    assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted")
+def test_oracle_matches_live_reference_and_quirks():
+    torch.manual_seed(3)
+    kwargs = dict(O.README_3D, feature_sizes=[4, 8, 16])
+    ref = build_reference_unet(**kwargs)
+    ref.train()
+    x = torch.randn(1, 4, 44, 46, 7)
+    out_ref = ref(x)
+    sd = {k: v.detach().clone() for k, v in ref.state_dict().items()}
+    # state_dict was read AFTER the train forward: rewind buffers is not possible, so compare eval
+    ref.eval()
+    with torch.no_grad():
+        ev_ref = ref(x)
+        ev, _ = O.unet_forward(sd, kwargs, x, training=False)
+    assert torch.equal(ev, ev_ref)
+    assert out_ref.shape == ev.shape
+    # the skip connection is dead -- Up(x, skip) ignores skip's values
+    up = ref.up_steps[0]
+    xx = torch.randn(1, 16, 5, 5, 3)
+    up.eval()
+    with torch.no_grad():
+        a = up(xx, torch.randn(1, 8, 12, 12, 6))
+        b = up(xx, torch.zeros(1, 8, 12, 12, 6))
+    assert torch.equal(a, b)
+    # 128x128 is too small for the 5-level README model
+    big = build_reference_unet(**O.README_3D)
+    with pytest.raises(RuntimeError):
+        big(torch.randn(1, 4, 128, 128, 32))
+    sd5 = {k: v.detach() for k, v in big.state_dict().items()}
+    with pytest.raises(RuntimeError):
+        O.unet_forward(sd5, O.README_3D, torch.randn(1, 4, 128, 128, 32))
+    # the reference cannot construct 2D models as shipped
+    from oracle.ref_loader import load_reference_unet
+    with pytest.raises(RuntimeError):
+        load_reference_unet().Unet_Constructor()
+    # README spelling raises TypeError
+    with pytest.raises(TypeError):
+        load_reference_unet().Unet_Constructor(image_dimmensions=3)
+    # loss module parity on a fresh random case
+    L = load_reference_loss()
+    p = torch.randn(2, 1, 5, 6, 3)
+    m = (torch.rand(2, 1, 7, 7, 4) > 0.5).float()
+    w = torch.rand(2, 1, 7, 7, 4)
+    for method in ("pixel", "sigmoid", "worst_z"):
+        assert torch.equal(L.cross_entropy(p, m, w, method), O.cross_entropy(p, m, w, method))
+    assert torch.equal(L.dice(p, m), O.dice(p, m))
