@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- the headline metric of BASELINE.json on B200: 3D U-Net training voxels/s.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                 # our arm (one JSON line on stdout)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                     # N ranks, data-parallel over patches
+    python bench.py --impl reference --steps 2 --warmup 1          # the reference's CPU path (oracle port)
+
+Workload (`config.workload`): BASELINE.json configs[1] with the shape correction of SURVEY.md section 0.4 --
+README 3D Unet_Constructor (in=4, out=1, features [8,16,32,64,128], kernels (3,3,2)/(3,3,1)), one training step
+= forward + pixel-weighted cross_entropy + backward + Adam, batch 4 of 4x256x256x32 patches per GPU, synthetic
+seeded data, reference-default random-init weights.  A voxel is one input spatial site (B*X*Y*Z).
+
+`value`   : device-timed (CUDA events, max over ranks) with the step's inputs already resident in HBM.
+`e2e`     : the same step through the public API with HOST inputs -- pinned fp16 image / mask / pwl tensors like
+            the reference dataloader yields (`transforms.py:133`), H2D copies (double-buffered on a copy stream)
+            and the D2H read of the loss inside the timed region.
+`roofline`: the kernel family with the largest share of the step, algorithmic bytes / CUDA-event time.
+`cpu_baseline`: the oracle port (reference algorithm, torch CPU fp32) on this box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "3d_unet_train_voxels_per_s"
+UNIT = "voxel/s"
+SHAPE = (4, 256, 256, 32)   # C, X, Y, Z of one patch
+WORKLOAD = "README 3D Unet_Constructor [8,16,32,64,128] k(3,3,2)/(3,3,1): train step (fwd + pixel-weighted BCE + bwd + Adam)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("HCUNET_BENCH_PRECISION", "mixed"), choices=["fp32", "mixed"])
+    ap.add_argument("--batch", type=int, default=4, help="patches per GPU per step")
+    ap.add_argument("--z", type=int, default=SHAPE[3])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port (reference algorithm on torch CPU fp32)
+# ----------------------------------------------------------------------------------------------------
+def cpu_step_fn(z):
+    import torch
+
+    import hcunet_b200 as H
+    from oracle import unet_oracle as O
+
+    torch.manual_seed(0)
+    m = H.Unet_Constructor(**O.README_3D)  # parameter container only: identical init to the reference
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    x, mask, pwl = O.golden_inputs(O.README_3D, (1, SHAPE[0], SHAPE[1], SHAPE[2], z), 0)
+
+    def step():
+        # forward (train-mode BN) + pixel-weighted loss + backward, exactly the reference's op sequence
+        loss, _, grads, newbuf = O.train_step_grads(sd, O.README_3D, x, mask, pwl)
+        with torch.no_grad():  # plain Adam-free SGD-like touch of every parameter so the step has an update
+            for k, g in grads.items():
+                sd[k] = sd[k] - 1e-3 * g
+            sd.update(newbuf)
+        return float(loss)
+
+    return step, SHAPE[1] * SHAPE[2] * z
+
+
+def run_cpu(steps, warmup, z):
+    import torch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, vox = cpu_step_fn(z)
+    for _ in range(warmup):
+        step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        ts.append(time.perf_counter() - t0)
+    t = sum(ts) / len(ts)
+    return {"value": vox / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of batch 1 x {SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]}x{z} (the GPU step is batch 4 of the same "
+                      f"patch), oracle/unet_oracle.py on torch {torch.__version__} CPU fp32, {cores} threads",
+            "ms_per_step": t * 1e3}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = run_cpu(max(1, args.steps), max(0, args.warmup), args.z)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic (seeded), random-init weights",
+            "config": {"workload": WORKLOAD, "patch": [SHAPE[0], SHAPE[1], SHAPE[2], args.z], "batch_per_step": 1,
+                       "note": "reference CPU path = oracle port of hcat/unet.py + hcat/loss.py (the reference is pure "
+                               "Python on torch; it cannot travel to the GPU box), bounded sample of the GPU workload"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import hcunet_b200 as H
+    from hcunet_b200 import _lib
+    from hcunet_b200.parallel import GradSync
+    from oracle import unet_oracle as O  # cpu_baseline leg + workload kwargs only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, (C, X, Y), Z = args.batch, SHAPE[:3], args.z
+
+    torch.manual_seed(0)
+    model = H.Unet_Constructor(**O.README_3D)
+    model.precision = args.precision
+    model = model.to(dev).train()
+    sync = GradSync(model, world)          # broadcast params from rank 0; fp32 mean all-reduce of the gradients
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
+
+    # synthetic patches: NBUF distinct batches so consecutive steps never reuse a cached input
+    NBUF = 3
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = []
+    for _ in range(NBUF):
+        img = torch.randn((B, C, X, Y, Z), generator=g).half().pin_memory()
+        msk = (torch.rand((B, 1, X, Y, Z), generator=g) > 0.7).half().pin_memory()
+        pwl = (torch.rand((B, 1, X, Y, Z), generator=g) * 3).half().pin_memory()
+        host.append((img, msk, pwl))
+    resident = [tuple(t.to(dev) for t in h) for h in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def step(img, msk, pwl):
+        opt.zero_grad(set_to_none=True)
+        logits = model(img)
+        loss = H.cross_entropy(logits, msk, pwl, "pixel")
+        loss.backward()
+        sync.allreduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """EXACTLY `steps` steps between barrier+synchronize, CUDA events, max over ranks -> seconds."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- resident-input throughput (`value`) ----------------------------------------------------
+    def res_step(i):
+        flush.zero_()  # L2 flush between iterations (256 MB write); inside the region, ~40 us
+        step(*resident[i % NBUF])
+
+    for i in range(args.warmup):
+        res_step(i)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launch_count()
+    t_res = timed(res_step, args.steps)
+    launches = _lib.launch_count() - l0
+    # the flush is not part of the workload: time it alone and subtract
+    t_flush = timed(lambda i: flush.zero_(), args.steps)
+    t_step = max(1e-9, (t_res - t_flush) / args.steps)
+    vox_per_step = B * X * Y * Z * world
+
+    # ---- end to end (`e2e`): pinned host inputs, H2D on a copy stream one step ahead, loss read back ----
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    losses = []
+
+    def prefetch(i):
+        s = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[s])
+            for d, h in zip(slots[s], host[i % NBUF]):
+                d.copy_(h, non_blocking=True)
+            ready[s].record(copy_stream)
+
+    def e2e_run(steps):
+        for s in range(2):
+            freed[s].record()
+        prefetch(0)
+        for i in range(steps):
+            if i + 1 < steps:
+                prefetch(i + 1)
+            s = i % 2
+            torch.cuda.current_stream().wait_event(ready[s])
+            loss = step(*slots[s])
+            freed[s].record()
+            losses.append(loss.item())  # D2H read of the step's result (4 bytes) -- a host sync every step
+
+    e2e_run(max(2, args.warmup))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_run(args.steps)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_e2e = float(t) / args.steps
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- per-kernel CUDA-event profile of the same step -> roofline of the dominant kernel ------------
+    roof = None
+    if rank == 0 and not args.no_profile:
+        from hcunet_b200 import profiler
+
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        prof = profiler.KernelProfile()
+        with prof:
+            for i in range(min(args.steps, 5)):
+                step(*resident[i % NBUF])
+        roof = prof.roofline(peaks, t_step * min(args.steps, 5))
+
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC, "value": vox_per_step / t_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp16 storage, fp32 accumulate" if args.precision == "mixed" else "fp32",
+                "data": "synthetic (seeded), random-init weights",
+                "config": {"workload": WORKLOAD, "patch": [C, X, Y, Z], "batch_per_gpu": B, "global_batch": B * world,
+                           "precision": args.precision, "parallelism": f"dp{world}", "optimizer": "Adam(fused) lr 1e-3",
+                           "l2": "256 MB buffer zeroed between iterations, its time measured alone and subtracted",
+                           "output_voxels_per_step": B * world * 68 * 68 * (Z - 5)},
+                "e2e": {"value": vox_per_step / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": 4, "ms_per_step": t_e2e * 1e3,
+                        "note": "pinned fp16 image/mask/pwl -> H2D on a copy stream one step ahead; loss.item() each step"},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
+                "loss_first_last": [losses[0], losses[-1]] if losses else None}
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if not args.no_cpu_baseline and world == 1:
+            cb = run_cpu(2, 1, Z)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_ours(a)

@@ -1,0 +1,153 @@
+"""ctypes binding of the C ABI declared in ``include/hcunet_b200.h``.
+
+There is NO fallback: if ``libhcunet_b200.so`` is missing or was built for another ABI version the
+import of any compute path raises.  ``hcunet_b200.build.build()`` (or ``python __graft_entry__.py``)
+produces the library in-tree.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
+ABI_VERSION = 4
+
+F32, BF16, F16 = 0, 1, 2
+
+
+class HcuConvDesc(C.Structure):
+    _fields_ = [
+        ("dtype_in", C.c_int32), ("dtype_out", C.c_int32), ("batch", C.c_int32),
+        ("in_size", C.c_int32 * 3), ("in_cpitch", C.c_int32), ("in_c_off", C.c_int32),
+        ("in_c_gstep", C.c_int32), ("cin", C.c_int32),
+        ("out_size", C.c_int32 * 3), ("out_tsize", C.c_int32 * 3), ("out_cpitch", C.c_int32),
+        ("out_c_off", C.c_int32), ("cout", C.c_int32), ("groups", C.c_int32),
+        ("taps", C.c_int32 * 3), ("dil", C.c_int32 * 3), ("pad", C.c_int32 * 3),
+        ("istep", C.c_int32 * 3), ("ostep", C.c_int32 * 3), ("ooff", C.c_int32 * 3),
+        ("in_relu", C.c_int32), ("out_relu", C.c_int32), ("reserved", C.c_int32 * 4),
+    ]
+
+
+class HcuWeightMap(C.Structure):
+    _fields_ = [
+        ("groups", C.c_int32), ("j", C.c_int32 * 3), ("na", C.c_int32), ("nb", C.c_int32),
+        ("base", C.c_int64), ("sg", C.c_int64), ("sa", C.c_int64), ("sb", C.c_int64), ("st", C.c_int64 * 3),
+        ("t0", C.c_int32 * 3), ("tstep", C.c_int32 * 3), ("fold", C.c_int32), ("fold_stride", C.c_int64),
+    ]
+
+
+class HcuLossDesc(C.Structure):
+    _fields_ = [
+        ("b", C.c_int32), ("c", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("z", C.c_int32),
+        ("mx", C.c_int32), ("my", C.c_int32), ("mz", C.c_int32),
+        ("dtype_mask", C.c_int32), ("dtype_pwl", C.c_int32), ("mode", C.c_int32), ("reserved", C.c_int32 * 3),
+    ]
+
+
+P = C.c_void_p
+I32, I64, F, D = C.c_int32, C.c_int64, C.c_float, C.c_double
+
+# name -> argtypes; every function returns int (0 == ok) unless listed in _RESTYPES
+SIGNATURES = {
+    "hcu_abi_version": [],
+    "hcu_last_error": [],
+    "hcu_launch_count": [],
+    "hcu_zero": [P, C.c_size_t, P],
+    "hcu_conv_fwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
+    "hcu_conv_wgrad_partial": [C.POINTER(HcuConvDesc), P, P, P, P, P, I32, P],
+    "hcu_weight_gather": [C.POINTER(HcuWeightMap), P, P, P],
+    "hcu_weight_scatter": [C.POINTER(HcuWeightMap), P, I32, I64, F, P, I32, P, P],
+    "hcu_nc_to_cl": [P, I32, P, I32, I64, I32, I64, I32, P, P],
+    "hcu_cl_to_nc": [P, I32, P, I32, I64, I32, I64, I32, P, P],
+    "hcu_grad_scale": [P, I64, F, P, P, P],
+    "hcu_bn_finalize": [P, I32, D, P, P, F, F, P, P, P, P, P, P, P],
+    "hcu_bn_eval_affine": [I32, P, P, P, P, F, P, P, P, P],
+    "hcu_bn_relu_apply": [P, I32, P, I32, I64, I32, P, P, I32, P],
+    "hcu_bn_relu_maxpool": [P, I32, P, I32, P, I32, I32, I32, I32, I32, I32, I32, I32, P, P, I32, P],
+    "hcu_maxpool_bwd": [P, I32, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
+    "hcu_bn_bwd_stats": [P, I32, P, I32, I64, I32, P, P, P, P, I32, P, P],
+    "hcu_bn_bwd_finalize": [P, I32, D, P, P, P, I32, F, P, P, P, P, P, P],
+    "hcu_bn_bwd_apply": [P, I32, P, I32, P, I32, I64, I32, P, P, I32, P, P],
+    "hcu_colsum": [P, I32, I64, I32, I32, I32, F, P, P, P, P],
+    "hcu_wbce_fwd": [C.POINTER(HcuLossDesc), P, P, P, P, P, P],
+    "hcu_wbce_bwd": [C.POINTER(HcuLossDesc), P, P, P, P, F, P, P, P],
+    "hcu_pair_reduce": [C.POINTER(HcuLossDesc), I32, P, P, P, P],
+    "hcu_pair_bwd": [C.POINTER(HcuLossDesc), I32, P, P, P, P, P],
+}
+_RESTYPES = {"hcu_last_error": C.c_char_p, "hcu_launch_count": C.c_longlong}
+
+_lib = None
+
+
+class _ProfState:
+    profiler = None   # hcunet_b200.profiler.KernelProfile while one is active
+    note = None       # (layer, algorithmic bytes, flops) for the next call, set by the engine
+
+
+def note(layer=None, nbytes=0, flops=0):
+    """Annotate the next C-ABI call (only looked at while a KernelProfile is active)."""
+    if _ProfState.profiler is not None:
+        _ProfState.note = (layer, nbytes, flops)
+
+
+def _wrap(name, fn):
+    def call(*args):
+        prof = _ProfState.profiler
+        if prof is None:
+            return fn(*args)
+        import torch
+
+        n, _ProfState.note = _ProfState.note, None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        prof.records.append((name, n, e0, e1))
+        return rc
+
+    call.__name__ = name
+    return call
+
+
+class _Lib:
+    """Attribute access returns the (profiling-aware) C entry points."""
+
+
+def load():
+    """Load (once) and return the ctypes library; raises RuntimeError when it is unusable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"hcunet_b200: CUDA library not built ({LIB_PATH} missing). There is no CPU / PyTorch fallback: "
+            "run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc) first.")
+    lib = C.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise RuntimeError(f"hcunet_b200: {LIB_PATH} does not export {name}; rebuild it") from e
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, C.c_int)
+    ver = lib.hcu_abi_version()
+    if ver != ABI_VERSION:
+        raise RuntimeError(f"hcunet_b200: library ABI {ver} != binding ABI {ABI_VERSION}; rebuild it")
+    out = _Lib()
+    out._cdll = lib
+    for name in SIGNATURES:
+        raw = getattr(lib, name)
+        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count") else _wrap(name, raw))
+    _lib = out
+    return out
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().hcu_last_error()
+        raise RuntimeError(f"hcunet_b200 {what} failed ({rc}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(load().hcu_launch_count())

@@ -1,0 +1,123 @@
+// Shared helpers for the hcunet_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/hcunet_b200.h"
+
+namespace hcu {
+
+// ---- error plumbing -------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define HCU_CHECK_ARG(cond, ...)          \
+  do {                                    \
+    if (!(cond)) {                        \
+      hcu::set_error(__VA_ARGS__);        \
+      return HCU_ERR_INVALID;             \
+    }                                     \
+  } while (0)
+
+// to be used right after a kernel launch
+#define HCU_CHECK_LAUNCH(name)                                                   \
+  do {                                                                           \
+    cudaError_t e__ = cudaPeekAtLastError();                                     \
+    if (e__ != cudaSuccess) {                                                    \
+      cudaGetLastError();                                                        \
+      hcu::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+      return HCU_ERR_CUDA;                                                       \
+    }                                                                            \
+    hcu::count_launch();                                                         \
+  } while (0)
+
+// ---- dtype helpers --------------------------------------------------------------------------
+template <typename T> struct DT;
+template <> struct DT<float> { static constexpr int id = HCU_F32; };
+template <> struct DT<__nv_bfloat16> { static constexpr int id = HCU_BF16; };
+template <> struct DT<__half> { static constexpr int id = HCU_F16; };
+
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+// 4 consecutive elements <-> float4 (pointer must be 4-element aligned)
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+  float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ float4 load4(const __half* p) {
+  uint2 r = *reinterpret_cast<const uint2*>(p);
+  __half2 a = *reinterpret_cast<__half2*>(&r.x);
+  __half2 b = *reinterpret_cast<__half2*>(&r.y);
+  float2 fa = __half22float2(a), fb = __half22float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void store4(__nv_bfloat16* p, float4 v) {
+  __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+  __nv_bfloat162 b = __floats2bfloat162_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+__device__ __forceinline__ void store4(__half* p, float4 v) {
+  __half2 a = __floats2half2_rn(v.x, v.y);
+  __half2 b = __floats2half2_rn(v.z, v.w);
+  uint2 r;
+  r.x = *reinterpret_cast<uint32_t*>(&a);
+  r.y = *reinterpret_cast<uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// dispatch helpers on HcuDType
+#define HCU_DISPATCH_DTYPE(dt, T, ...)                         \
+  switch (dt) {                                                \
+    case HCU_F32: { using T = float; __VA_ARGS__; } break;     \
+    case HCU_BF16: { using T = __nv_bfloat16; __VA_ARGS__; } break; \
+    case HCU_F16: { using T = __half; __VA_ARGS__; } break;    \
+    default: hcu::set_error("bad dtype %d", (int)(dt)); return HCU_ERR_INVALID; \
+  }
+#define HCU_DISPATCH_ACT(dt, T, ...)                           \
+  switch (dt) {                                                \
+    case HCU_F32: { using T = float; __VA_ARGS__; } break;     \
+    case HCU_F16: { using T = __half; __VA_ARGS__; } break;    \
+    default: hcu::set_error("activation dtype must be f32 or f16, got %d", (int)(dt)); return HCU_ERR_INVALID; \
+  }
+
+}  // namespace hcu

@@ -1,0 +1,652 @@
+// Memory-bound kernels of the hot path: boundary layout transforms, weight gathers, BatchNorm
+// finalize / apply / backward, fused BN+ReLU+MaxPool, max-pool backward, column sums.
+// All are grid-stride kernels sized to a multiple of the SM count, 128-bit accesses where the
+// channel pitch allows it, fp32 math with fp64 cross-CTA accumulation.
+#include <stdarg.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+namespace hcu {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
+  long long blocks = (work_items + threads - 1) / threads;
+  long long cap = (long long)num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// launch geometry whose total thread count is a multiple of c, so each thread keeps ONE channel
+static inline void channel_fixed_geometry(long long total, int c, int& threads, int& grid) {
+  threads = 256;
+  if (c <= 256 && 256 % c != 0) threads = (256 / c) * c;
+  if (threads < 32) threads = 256;
+  grid = grid_for(total, threads * 8, 4);
+  if (c > 256 && c % 256 == 0) {
+    const int q = c / 256;
+    grid = (grid + q - 1) / q * q;
+  }
+}
+
+// ---- layout ---------------------------------------------------------------------------------
+// [N][C][S] -> [N][S][cpitch]; 32x32 smem transpose tiles over (c, s) so both sides coalesce.
+template <typename TS, typename TD>
+__global__ void nc_to_cl_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n, int c, long long s,
+                                int cpitch, const float* __restrict__ dscale) {
+  __shared__ float tile[32][33];
+  const float mul = dscale != nullptr ? dscale[0] : 1.f;
+  const long long s_tiles = (s + 31) / 32;
+  const int c_tiles = (cpitch + 31) / 32;
+  const long long total = n * s_tiles * c_tiles;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int ct = (int)(t % c_tiles);
+    long long r = t / c_tiles;
+    const long long stile = r % s_tiles;
+    const long long b = r / s_tiles;
+    const long long s0 = stile * 32;
+    const int c0 = ct * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int cc = c0 + j;
+      const long long ss = s0 + threadIdx.x;
+      float v = 0.f;
+      if (cc < c && ss < s) v = to_f(src[(b * c + cc) * s + ss]) * mul;
+      tile[j][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const long long ss = s0 + j;
+      const int cc = c0 + threadIdx.x;
+      if (ss < s && cc < cpitch) dst[(b * s + ss) * cpitch + cc] = from_f<TD>(tile[threadIdx.x][j]);
+    }
+    __syncthreads();
+  }
+}
+
+template <typename TS, typename TD>
+__global__ void cl_to_nc_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n, int c, long long s,
+                                int cpitch, const float* __restrict__ dscale) {
+  __shared__ float tile[32][33];
+  const float mul = dscale != nullptr ? dscale[0] : 1.f;
+  const long long s_tiles = (s + 31) / 32;
+  const int c_tiles = (c + 31) / 32;
+  const long long total = n * s_tiles * c_tiles;
+  for (long long t = blockIdx.x; t < total; t += gridDim.x) {
+    const int ct = (int)(t % c_tiles);
+    long long r = t / c_tiles;
+    const long long stile = r % s_tiles;
+    const long long b = r / s_tiles;
+    const long long s0 = stile * 32;
+    const int c0 = ct * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const long long ss = s0 + j;
+      const int cc = c0 + threadIdx.x;
+      float v = 0.f;
+      if (ss < s && cc < c) v = to_f(src[(b * s + ss) * cpitch + cc]) * mul;
+      tile[j][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+      const int cc = c0 + j;
+      const long long ss = s0 + threadIdx.x;
+      if (cc < c && ss < s) dst[(b * c + cc) * s + ss] = from_f<TD>(tile[threadIdx.x][j]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- weights --------------------------------------------------------------------------------
+__device__ __forceinline__ long long wm_index(const HcuWeightMap& m, long long e) {
+  const int b = (int)(e % m.nb); e /= m.nb;
+  const int a = (int)(e % m.na); e /= m.na;
+  const int jz = (int)(e % m.j[2]); e /= m.j[2];
+  const int jy = (int)(e % m.j[1]); e /= m.j[1];
+  const int jx = (int)(e % m.j[0]);
+  const int g = (int)(e / m.j[0]);
+  return m.base + g * m.sg + a * m.sa + b * m.sb + (long long)(m.t0[0] + jx * m.tstep[0]) * m.st[0] +
+         (long long)(m.t0[1] + jy * m.tstep[1]) * m.st[1] + (long long)(m.t0[2] + jz * m.tstep[2]) * m.st[2];
+}
+
+__global__ void weight_gather_kernel(HcuWeightMap m, const float* __restrict__ ref, float* __restrict__ packed,
+                                     long long total) {
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const long long idx = wm_index(m, e);
+    float v = ref[idx];
+    if (m.fold) v += ref[idx + m.fold_stride];
+    packed[e] = v;
+  }
+}
+
+__global__ void weight_scatter_kernel(HcuWeightMap m, const float* __restrict__ partial, int nsplit,
+                                      long long split_stride, float scale, const float* __restrict__ dscale,
+                                      int accumulate, float* __restrict__ ref, long long total) {
+  if (dscale != nullptr) scale *= dscale[0];
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int i = 0; i < nsplit; ++i) s += partial[(long long)i * split_stride + e];
+    s *= scale;
+    const long long idx = wm_index(m, e);
+    if (accumulate) {
+      ref[idx] += s;
+      if (m.fold) ref[idx + m.fold_stride] += s;
+    } else {
+      ref[idx] = s;
+      if (m.fold) ref[idx + m.fold_stride] = s;
+    }
+  }
+}
+
+// ---- BatchNorm --------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int c, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* mean,
+                                   float* invstd, float* scale, float* shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const double mu = stats[i] / count;
+  double var = stats[c + i] / count - mu * mu;
+  if (var < 0.0) var = 0.0;
+  const float is = (float)(1.0 / sqrt(var + (double)eps));
+  const float muf = (float)mu;
+  mean[i] = muf;
+  invstd[i] = is;
+  const float sc = gamma[i] * is;
+  scale[i] = sc;
+  shift[i] = beta[i] - muf * sc;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[i] = (1.f - momentum) * running_mean[i] + momentum * muf;
+    running_var[i] = (1.f - momentum) * running_var[i] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_affine_kernel(int c, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                      const float* __restrict__ conv_bias, float* scale, float* shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  const float is = 1.f / sqrtf(rv[i] + eps);
+  const float sc = gamma[i] * is;
+  scale[i] = sc;
+  const float b = conv_bias != nullptr ? conv_bias[i] : 0.f;
+  shift[i] = beta[i] + (b - rm[i]) * sc;
+}
+
+template <typename TY, typename TA, bool VEC>
+__global__ void bn_relu_apply_kernel(const TY* __restrict__ y, TA* __restrict__ a, long long total, int c,
+                                     const float* __restrict__ scale, const float* __restrict__ shift, int relu) {
+  if (VEC) {
+    const long long nv = total >> 2;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nv;
+         e += (long long)gridDim.x * blockDim.x) {
+      const int ch = (int)((e << 2) % c);
+      float4 v = load4(y + (e << 2));
+      const float4 sc = *reinterpret_cast<const float4*>(scale + ch);
+      const float4 sh = *reinterpret_cast<const float4*>(shift + ch);
+      v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+      v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+      if (relu) { v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y; v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w; }
+      store4(a + (e << 2), v);
+    }
+  } else {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+      const int ch = (int)(e % c);
+      float v = fmaf(to_f(y[e]), scale[ch], shift[ch]);
+      if (relu) v = v < 0.f ? 0.f : v;
+      a[e] = from_f<TA>(v);
+    }
+  }
+}
+
+// one thread per (pooled voxel, channel); channels fastest => coalesced on both sides
+template <typename TY, typename TP>
+__global__ void bn_relu_maxpool_kernel(const TY* __restrict__ y, TP* __restrict__ pooled,
+                                       uint8_t* __restrict__ argmax, int n, int ix, int iy, int iz, int c, int px,
+                                       int py, int pz, const float* __restrict__ scale,
+                                       const float* __restrict__ shift, int relu) {
+  const int ox = ix / px, oy = iy / py, oz = iz / pz;
+  const long long total = (long long)n * ox * oy * oz * c;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % c);
+    long long r = e / c;
+    const int z = (int)(r % oz); r /= oz;
+    const int yy = (int)(r % oy); r /= oy;
+    const int x = (int)(r % ox);
+    const int b = (int)(r / ox);
+    const float sc = scale != nullptr ? scale[ch] : 1.f;
+    const float sh = scale != nullptr ? shift[ch] : 0.f;
+    float best = -INFINITY;
+    int bi = 0;
+    for (int wx = 0; wx < px; ++wx)
+      for (int wy = 0; wy < py; ++wy)
+        for (int wz = 0; wz < pz; ++wz) {
+          const long long src = ((((long long)b * ix + (x * px + wx)) * iy + (yy * py + wy)) * iz + (z * pz + wz)) * c + ch;
+          float v = to_f(y[src]);
+          if (scale != nullptr) v = fmaf(v, sc, sh);
+          if (relu) v = v < 0.f ? 0.f : v;  // NaN stays NaN, like ATen's relu
+          // ATen max_pool3d_with_indices: take if (val > max) || isnan(val); ties keep the first
+          if (v > best || v != v) {
+            best = v;
+            bi = (wx * py + wy) * pz + wz;
+          }
+        }
+    pooled[e] = from_f<TP>(best);
+    argmax[e] = (uint8_t)bi;
+  }
+}
+
+template <typename TDP, typename TDF>
+__global__ void maxpool_bwd_kernel(const TDP* __restrict__ dpooled, const uint8_t* __restrict__ argmax,
+                                   TDF* __restrict__ dfull, int n, int ix, int iy, int iz, int c, int px, int py,
+                                   int pz) {
+  const int ox = ix / px, oy = iy / py, oz = iz / pz;
+  const long long total = (long long)n * ix * iy * iz * c;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(e % c);
+    long long r = e / c;
+    const int z = (int)(r % iz); r /= iz;
+    const int yy = (int)(r % iy); r /= iy;
+    const int x = (int)(r % ix);
+    const int b = (int)(r / ix);
+    const int qx = x / px, qy = yy / py, qz = z / pz;
+    float v = 0.f;
+    if (qx < ox && qy < oy && qz < oz) {
+      const long long pe = ((((long long)b * ox + qx) * oy + qy) * oz + qz) * c + ch;
+      const int w = ((x - qx * px) * py + (yy - qy * py)) * pz + (z - qz * pz);
+      if ((int)argmax[pe] == w) v = to_f(dpooled[pe]);
+    }
+    dfull[e] = from_f<TDF>(v);
+  }
+}
+
+// pass 1 of BN(+ReLU) backward: per-channel sums of g and g*xhat.
+// Each thread walks pixels for a fixed channel group so per-thread partials stay in registers.
+template <typename TD, typename TY>
+__global__ void bn_bwd_stats_kernel(const TD* __restrict__ da, const TY* __restrict__ y, long long npix, int c,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                    double* __restrict__ sums) {
+  // thread -> channel (tid % c) when c <= blockDim; generic: loop channels
+  extern __shared__ float sh[];  // [2][c]
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const long long total = npix * c;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // make the per-thread channel constant across iterations when stride % c == 0
+  const bool fixed = (stride % c) == 0;
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (fixed) {
+    const int ch = (int)(e % c);
+    const float sc = scale[ch], sf = shift[ch], mu = mean[ch], is = invstd[ch];
+    float s1 = 0.f, s2 = 0.f;
+    for (; e < total; e += stride) {
+      const float yv = to_f(y[e]);
+      float g = to_f(da[e]);
+      if (relu && fmaf(yv, sc, sf) <= 0.f) g = 0.f;
+      s1 += g;
+      s2 = fmaf(g, (yv - mu) * is, s2);
+    }
+    atomicAdd(&sh[ch], s1);
+    atomicAdd(&sh[c + ch], s2);
+  } else {
+    for (; e < total; e += stride) {
+      const int ch = (int)(e % c);
+      const float yv = to_f(y[e]);
+      float g = to_f(da[e]);
+      if (relu && fmaf(yv, scale[ch], shift[ch]) <= 0.f) g = 0.f;
+      atomicAdd(&sh[ch], g);
+      atomicAdd(&sh[c + ch], g * (yv - mean[ch]) * invstd[ch]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) atomicAdd(&sums[i], (double)sh[i]);
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int c, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, int training, float grad_scale,
+                                       const float* __restrict__ dscale, float* dgamma, float* dbeta, float* dbias,
+                                       float* coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  if (dscale != nullptr) grad_scale *= dscale[0];
+  const double sg = sums[i], sgx = sums[c + i];
+  if (dgamma != nullptr) dgamma[i] = (float)(sgx * grad_scale);
+  if (dbeta != nullptr) dbeta[i] = (float)(sg * grad_scale);
+  const double s = (double)gamma[i] * (double)invstd[i];
+  double c1, c2, c3;
+  if (training) {
+    const double mg = sg / count, mgx = sgx / count;
+    c1 = s;
+    c2 = -s * (double)invstd[i] * mgx;
+    c3 = s * (double)invstd[i] * mgx * (double)mean[i] - s * mg;
+    // conv bias feeds a batch-stat BN: its gradient sum(dy) is analytically zero
+    if (dbias != nullptr) dbias[i] = (float)((c1 * sg + c2 * count * (double)mean[i] + c3 * count) * grad_scale);
+  } else {
+    c1 = s; c2 = 0.0; c3 = 0.0;
+    if (dbias != nullptr) dbias[i] = (float)(s * sg * grad_scale);
+  }
+  coef[i] = (float)c1;
+  coef[c + i] = (float)c2;
+  coef[2 * c + i] = (float)c3;
+}
+
+template <typename TD, typename TY, typename TO, bool VEC>
+__global__ void bn_bwd_apply_kernel(const TD* __restrict__ da, const TY* __restrict__ y, TO* __restrict__ dy,
+                                    long long total, int c, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int relu, const float* __restrict__ coef) {
+  if (VEC) {
+    const long long nv = total >> 2;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < nv;
+         e += (long long)gridDim.x * blockDim.x) {
+      const int ch = (int)((e << 2) % c);
+      const float4 yv = load4(y + (e << 2));
+      float4 g = load4(da + (e << 2));
+      const float4 sc = *reinterpret_cast<const float4*>(scale + ch);
+      const float4 sf = *reinterpret_cast<const float4*>(shift + ch);
+      const float4 c1 = *reinterpret_cast<const float4*>(coef + ch);
+      const float4 c2 = *reinterpret_cast<const float4*>(coef + c + ch);
+      const float4 c3 = *reinterpret_cast<const float4*>(coef + 2 * c + ch);
+      if (relu) {
+        if (fmaf(yv.x, sc.x, sf.x) <= 0.f) g.x = 0.f;
+        if (fmaf(yv.y, sc.y, sf.y) <= 0.f) g.y = 0.f;
+        if (fmaf(yv.z, sc.z, sf.z) <= 0.f) g.z = 0.f;
+        if (fmaf(yv.w, sc.w, sf.w) <= 0.f) g.w = 0.f;
+      }
+      float4 o;
+      o.x = fmaf(c1.x, g.x, fmaf(c2.x, yv.x, c3.x));
+      o.y = fmaf(c1.y, g.y, fmaf(c2.y, yv.y, c3.y));
+      o.z = fmaf(c1.z, g.z, fmaf(c2.z, yv.z, c3.z));
+      o.w = fmaf(c1.w, g.w, fmaf(c2.w, yv.w, c3.w));
+      store4(dy + (e << 2), o);
+    }
+  } else {
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+      const int ch = (int)(e % c);
+      const float yv = to_f(y[e]);
+      float g = to_f(da[e]);
+      if (relu && fmaf(yv, scale[ch], shift[ch]) <= 0.f) g = 0.f;
+      dy[e] = from_f<TO>(fmaf(coef[ch], g, fmaf(coef[c + ch], yv, coef[2 * c + ch])));
+    }
+  }
+}
+
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, long long npix, int cpitch, int c_off, int c,
+                              double* __restrict__ scratch) {
+  extern __shared__ float sh[];  // [c]
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const long long total = npix * c;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (stride % c == 0) {
+    const int ch = (int)(e % c);
+    float s = 0.f;
+    for (; e < total; e += stride) s += to_f(x[(e / c) * cpitch + c_off + ch]);
+    atomicAdd(&sh[ch], s);
+  } else {
+    for (; e < total; e += stride) atomicAdd(&sh[(int)(e % c)], to_f(x[(e / c) * cpitch + c_off + (int)(e % c)]));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&scratch[i], (double)sh[i]);
+}
+
+__global__ void colsum_finish_kernel(const double* __restrict__ scratch, int c, float scale,
+                                     const float* __restrict__ dscale, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (dscale != nullptr) scale *= dscale[0];
+  if (i < c) out[i] = (float)(scratch[i] * scale);
+}
+
+// loss scaling for the fp16 backward: scales[0] = S = 2^k with max|g| * S ~ target, scales[1] = 1/S
+__global__ void absmax_kernel(const float* __restrict__ g, long long n, unsigned int* __restrict__ amax_bits) {
+  float m = 0.f;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float v = fabsf(g[e]);
+    if (v > m && v <= 3.0e38f) m = v;  // ignore inf / NaN: they propagate on their own
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(amax_bits, __float_as_uint(m));  // non-negative floats order as uints
+}
+__global__ void grad_scale_finish_kernel(const unsigned int* __restrict__ amax_bits, float target, float* scales) {
+  const float amax = __uint_as_float(amax_bits[0]);
+  float s = 1.f;
+  if (amax > 0.f) {
+    int e;
+    frexpf(target / amax, &e);          // target/amax = f * 2^e, f in [0.5, 1)
+    e = max(-60, min(60, e - 1));
+    s = ldexpf(1.f, e);
+  }
+  scales[0] = s;
+  scales[1] = 1.f / s;
+}
+
+}  // namespace hcu
+
+using namespace hcu;
+
+extern "C" int hcu_grad_scale(const float* g, int64_t n, float target, unsigned int* scratch, float* scales,
+                              void* stream) {
+  HCU_CHECK_ARG(g && scratch && scales && n > 0 && target > 0.f, "grad_scale: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(unsigned int), st);
+  if (e != cudaSuccess) { set_error("grad_scale: memset: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
+  absmax_kernel<<<grid_for(n, 256 * 4), 256, 0, st>>>(g, n, scratch);
+  HCU_CHECK_LAUNCH("absmax");
+  grad_scale_finish_kernel<<<1, 1, 0, st>>>(scratch, target, scales);
+  HCU_CHECK_LAUNCH("grad_scale_finish");
+  return 0;
+}
+
+extern "C" int hcu_abi_version(void) { return HCU_ABI_VERSION; }
+extern "C" const char* hcu_last_error(void) { return g_err; }
+extern "C" long long hcu_launch_count(void) { return g_launches.load(); }
+
+extern "C" int hcu_zero(void* ptr, size_t bytes, void* stream) {
+  cudaError_t e = cudaMemsetAsync(ptr, 0, bytes, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("hcu_zero: %s", cudaGetErrorString(e));
+    return HCU_ERR_CUDA;
+  }
+  return 0;
+}
+
+extern "C" int hcu_nc_to_cl(const void* src, int32_t dtype_src, void* dst, int32_t dtype_dst, int64_t n, int32_t c,
+                            int64_t s, int32_t cpitch, const float* dscale, void* stream) {
+  HCU_CHECK_ARG(src && dst && n > 0 && c > 0 && s > 0 && cpitch >= c, "nc_to_cl: bad arguments");
+  long long tiles = n * ((s + 31) / 32) * ((cpitch + 31) / 32);
+  int grid = (int)(tiles < (long long)num_sms() * 16 ? tiles : (long long)num_sms() * 16);
+  dim3 block(32, 8);
+  HCU_DISPATCH_DTYPE(dtype_src, TS, HCU_DISPATCH_ACT(dtype_dst, TD,
+      nc_to_cl_kernel<TS, TD><<<grid, block, 0, (cudaStream_t)stream>>>((const TS*)src, (TD*)dst, n, c, s, cpitch, dscale)));
+  HCU_CHECK_LAUNCH("nc_to_cl");
+  return 0;
+}
+
+extern "C" int hcu_cl_to_nc(const void* src, int32_t dtype_src, void* dst, int32_t dtype_dst, int64_t n, int32_t c,
+                            int64_t s, int32_t cpitch, const float* dscale, void* stream) {
+  HCU_CHECK_ARG(src && dst && n > 0 && c > 0 && s > 0 && cpitch >= c, "cl_to_nc: bad arguments");
+  long long tiles = n * ((s + 31) / 32) * ((c + 31) / 32);
+  int grid = (int)(tiles < (long long)num_sms() * 16 ? tiles : (long long)num_sms() * 16);
+  dim3 block(32, 8);
+  HCU_DISPATCH_ACT(dtype_src, TS, HCU_DISPATCH_DTYPE(dtype_dst, TD,
+      cl_to_nc_kernel<TS, TD><<<grid, block, 0, (cudaStream_t)stream>>>((const TS*)src, (TD*)dst, n, c, s, cpitch, dscale)));
+  HCU_CHECK_LAUNCH("cl_to_nc");
+  return 0;
+}
+
+static long long wm_total(const HcuWeightMap* m) {
+  return (long long)m->groups * m->j[0] * m->j[1] * m->j[2] * m->na * m->nb;
+}
+
+extern "C" int hcu_weight_gather(const HcuWeightMap* m, const float* ref, float* packed, void* stream) {
+  HCU_CHECK_ARG(m && ref && packed, "weight_gather: null pointer");
+  const long long total = wm_total(m);
+  HCU_CHECK_ARG(total > 0, "weight_gather: empty map");
+  weight_gather_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*m, ref, packed, total);
+  HCU_CHECK_LAUNCH("weight_gather");
+  return 0;
+}
+
+extern "C" int hcu_weight_scatter(const HcuWeightMap* m, const float* partial, int32_t nsplit, int64_t split_stride,
+                                  float scale, const float* dscale, int32_t accumulate, float* ref, void* stream) {
+  HCU_CHECK_ARG(m && ref && partial && nsplit > 0, "weight_scatter: bad arguments");
+  const long long total = wm_total(m);
+  HCU_CHECK_ARG(total > 0 && split_stride >= total, "weight_scatter: bad sizes");
+  weight_scatter_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*m, partial, nsplit, split_stride,
+                                                                                scale, dscale, accumulate, ref, total);
+  HCU_CHECK_LAUNCH("weight_scatter");
+  return 0;
+}
+
+extern "C" int hcu_bn_finalize(const double* stats, int32_t c, double count, const float* gamma, const float* beta,
+                               float eps, float momentum, float* running_mean, float* running_var, float* mean,
+                               float* invstd, float* scale, float* shift, void* stream) {
+  HCU_CHECK_ARG(stats && gamma && beta && mean && invstd && scale && shift && c > 0 && count > 0,
+                "bn_finalize: bad arguments");
+  HCU_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running stats come together");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, c, count, gamma, beta, eps, momentum,
+                                                                       running_mean, running_var, mean, invstd,
+                                                                       scale, shift);
+  HCU_CHECK_LAUNCH("bn_finalize");
+  return 0;
+}
+
+extern "C" int hcu_bn_eval_affine(int32_t c, const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float eps, const float* conv_bias, float* scale,
+                                  float* shift, void* stream) {
+  HCU_CHECK_ARG(gamma && beta && running_mean && running_var && scale && shift && c > 0, "bn_eval_affine: bad args");
+  bn_eval_affine_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(c, gamma, beta, running_mean,
+                                                                          running_var, eps, conv_bias, scale, shift);
+  HCU_CHECK_LAUNCH("bn_eval_affine");
+  return 0;
+}
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int hcu_bn_relu_apply(const void* y, int32_t dtype_y, void* a, int32_t dtype_a, int64_t npix, int32_t c,
+                                 const float* scale, const float* shift, int32_t relu, void* stream) {
+  HCU_CHECK_ARG(y && a && scale && shift && npix > 0 && c > 0, "bn_relu_apply: bad arguments");
+  const long long total = npix * c;
+  const bool vec = (c % 4 == 0) && aligned16(y) && aligned16(a) && aligned16(scale) && aligned16(shift);
+  const int grid = grid_for(vec ? total / 4 : total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  HCU_DISPATCH_ACT(dtype_y, TY, HCU_DISPATCH_ACT(dtype_a, TA, {
+    if (vec) bn_relu_apply_kernel<TY, TA, true><<<grid, 256, 0, st>>>((const TY*)y, (TA*)a, total, c, scale, shift, relu);
+    else bn_relu_apply_kernel<TY, TA, false><<<grid, 256, 0, st>>>((const TY*)y, (TA*)a, total, c, scale, shift, relu);
+  }));
+  HCU_CHECK_LAUNCH("bn_relu_apply");
+  return 0;
+}
+
+extern "C" int hcu_bn_relu_maxpool(const void* y, int32_t dtype_y, void* pooled, int32_t dtype_p, uint8_t* argmax,
+                                   int32_t n, int32_t ix, int32_t iy, int32_t iz, int32_t c, int32_t px, int32_t py,
+                                   int32_t pz, const float* scale, const float* shift, int32_t relu, void* stream) {
+  HCU_CHECK_ARG(y && pooled && argmax && n > 0 && c > 0 && px > 0 && py > 0 && pz > 0, "maxpool: bad arguments");
+  HCU_CHECK_ARG(ix / px > 0 && iy / py > 0 && iz / pz > 0, "maxpool: input smaller than the pooling window");
+  HCU_CHECK_ARG(px * py * pz <= 255, "maxpool: window too large for uint8 argmax");
+  HCU_CHECK_ARG((scale == nullptr) == (shift == nullptr), "maxpool: scale/shift come together");
+  const long long total = (long long)n * (ix / px) * (iy / py) * (iz / pz) * c;
+  cudaStream_t st = (cudaStream_t)stream;
+  HCU_DISPATCH_ACT(dtype_y, TY, HCU_DISPATCH_ACT(dtype_p, TP,
+      bn_relu_maxpool_kernel<TY, TP><<<grid_for(total, 256), 256, 0, st>>>((const TY*)y, (TP*)pooled, argmax, n, ix,
+                                                                           iy, iz, c, px, py, pz, scale, shift,
+                                                                           relu)));
+  HCU_CHECK_LAUNCH("bn_relu_maxpool");
+  return 0;
+}
+
+extern "C" int hcu_maxpool_bwd(const void* dpooled, int32_t dtype_dp, const uint8_t* argmax, void* dfull,
+                               int32_t dtype_df, int32_t n, int32_t ix, int32_t iy, int32_t iz, int32_t c, int32_t px,
+                               int32_t py, int32_t pz, void* stream) {
+  HCU_CHECK_ARG(dpooled && argmax && dfull && n > 0 && c > 0 && px > 0 && py > 0 && pz > 0, "maxpool_bwd: bad args");
+  const long long total = (long long)n * ix * iy * iz * c;
+  cudaStream_t st = (cudaStream_t)stream;
+  HCU_DISPATCH_ACT(dtype_dp, TDP, HCU_DISPATCH_ACT(dtype_df, TDF,
+      maxpool_bwd_kernel<TDP, TDF><<<grid_for(total, 256), 256, 0, st>>>((const TDP*)dpooled, argmax, (TDF*)dfull, n,
+                                                                         ix, iy, iz, c, px, py, pz)));
+  HCU_CHECK_LAUNCH("maxpool_bwd");
+  return 0;
+}
+
+extern "C" int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix,
+                                int32_t c, const float* scale, const float* shift, const float* mean,
+                                const float* invstd, int32_t relu, double* sums, void* stream) {
+  HCU_CHECK_ARG(da && y && scale && shift && mean && invstd && sums && npix > 0 && c > 0, "bn_bwd_stats: bad args");
+  HCU_CHECK_ARG(c <= 4096, "bn_bwd_stats: too many channels");
+  const long long total = npix * c;
+  int threads, grid;
+  channel_fixed_geometry(total, c, threads, grid);
+  cudaStream_t st = (cudaStream_t)stream;
+  HCU_DISPATCH_ACT(dtype_da, TD, HCU_DISPATCH_ACT(dtype_y, TY,
+      bn_bwd_stats_kernel<TD, TY><<<grid, threads, 2 * c * sizeof(float), st>>>((const TD*)da, (const TY*)y, npix, c,
+                                                                                 scale, shift, mean, invstd, relu,
+                                                                                 sums)));
+  HCU_CHECK_LAUNCH("bn_bwd_stats");
+  return 0;
+}
+
+extern "C" int hcu_bn_bwd_finalize(const double* sums, int32_t c, double count, const float* gamma, const float* mean,
+                                   const float* invstd, int32_t training, float grad_scale, const float* dscale,
+                                   float* dgamma, float* dbeta, float* dbias, float* coef, void* stream) {
+  HCU_CHECK_ARG(sums && gamma && mean && invstd && coef && c > 0 && count > 0, "bn_bwd_finalize: bad args");
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, c, count, gamma, mean, invstd,
+                                                                           training, grad_scale, dscale, dgamma, dbeta,
+                                                                           dbias, coef);
+  HCU_CHECK_LAUNCH("bn_bwd_finalize");
+  return 0;
+}
+
+extern "C" int hcu_bn_bwd_apply(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, void* dy,
+                                int32_t dtype_dy, int64_t npix, int32_t c, const float* scale, const float* shift,
+                                int32_t relu, const float* coef, void* stream) {
+  HCU_CHECK_ARG(da && y && dy && scale && shift && coef && npix > 0 && c > 0, "bn_bwd_apply: bad args");
+  const long long total = npix * c;
+  const bool vec = (c % 4 == 0) && aligned16(da) && aligned16(y) && aligned16(dy) && aligned16(scale) &&
+                   aligned16(shift) && aligned16(coef);
+  const int grid = grid_for(vec ? total / 4 : total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  HCU_DISPATCH_ACT(dtype_da, TD, HCU_DISPATCH_ACT(dtype_y, TY, HCU_DISPATCH_ACT(dtype_dy, TO, {
+    if (vec) bn_bwd_apply_kernel<TD, TY, TO, true><<<grid, 256, 0, st>>>((const TD*)da, (const TY*)y, (TO*)dy, total, c, scale, shift, relu, coef);
+    else bn_bwd_apply_kernel<TD, TY, TO, false><<<grid, 256, 0, st>>>((const TD*)da, (const TY*)y, (TO*)dy, total, c, scale, shift, relu, coef);
+  })));
+  HCU_CHECK_LAUNCH("bn_bwd_apply");
+  return 0;
+}
+
+extern "C" int hcu_colsum(const void* x, int32_t dtype_x, int64_t npix, int32_t cpitch, int32_t c_off, int32_t c,
+                          float scale, const float* dscale, double* scratch, float* out, void* stream) {
+  HCU_CHECK_ARG(x && scratch && out && npix > 0 && c > 0 && c_off >= 0 && c_off + c <= cpitch && c <= 4096,
+                "colsum: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * c, st);
+  if (e != cudaSuccess) { set_error("colsum: memset: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
+  int threads, grid;
+  channel_fixed_geometry(npix * c, c, threads, grid);
+  HCU_DISPATCH_ACT(dtype_x, T,
+      colsum_kernel<T><<<grid, threads, c * sizeof(float), st>>>((const T*)x, npix, cpitch, c_off, c, scratch));
+  HCU_CHECK_LAUNCH("colsum");
+  colsum_finish_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, c, scale, dscale, out);
+  HCU_CHECK_LAUNCH("colsum_finish");
+  return 0;
+}

@@ -1,0 +1,546 @@
+"""Planner + executor for the U-Net hot path on the C ABI (``include/hcunet_b200.h``).
+
+``plan_unet`` turns the reference's constructor kwargs (`hcat/unet.py:16-27`) plus an input shape into
+a static list of layer geometries, raising the same ``RuntimeError`` the reference raises for inputs
+that are too small (`unet.py:246-257` via ATen's "Kernel size can't be greater than actual input
+size", and the ``torch.cat`` size mismatch at `unet.py:312`).  ``UnetEngine`` executes that plan:
+every arithmetic step is one of the library's hand-written kernels, enqueued on the current CUDA
+stream.  Activations are channels-last ``[N][X][Y][Z][C]``; the reference layout only exists at the
+boundary.  The dead skip connection (`unet.py:309-312`: ``conv1(cat(x_up, x_up))``) is reproduced by
+folding the two K-halves of ``Up.conv1``'s weight, so no concatenated tensor is ever built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import HcuConvDesc, HcuWeightMap
+
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}
+_ACT_DTYPE = {"fp32": torch.float32, "mixed": torch.float16}
+GRAD_SCALE_TARGET = 64.0  # fp16 backward: max|dlogits| * S lands in (32, 64]
+
+
+def _t3(v, dims: int, fill: int = 1) -> Tuple[int, int, int]:
+    """int / tuple of len dims -> 3-tuple (2D gets a trailing Z entry of ``fill``)."""
+    if isinstance(v, int):
+        v = (v,) * dims
+    v = tuple(int(e) for e in v)
+    if len(v) != dims:
+        raise RuntimeError(f"expected {dims} values, got {v}")
+    return v + (fill,) * (3 - dims)
+
+
+@dataclass
+class ConvGeom:
+    name: str            # e.g. down_steps.0.conv1
+    bn: Optional[str]    # e.g. down_steps.0.batch1 (None for out_conv)
+    cin_t: int           # channels of the tensor this conv reads
+    cout_t: int
+    groups: int          # groups as launched (after the cat(x,x) rewrite)
+    cin_g: int
+    cout_g: int
+    ref_cin_g: int       # second dim of the reference weight tensor
+    fold: bool           # Up.conv1 with groups == 1: W_eff = W[:, :C] + W[:, C:]
+    taps: Tuple[int, int, int]
+    dil: Tuple[int, int, int]
+    in_sz: Tuple[int, int, int]
+    out_sz: Tuple[int, int, int]
+    pool: Optional[Tuple[int, int, int]] = None      # max-pool applied to this block's output
+    pool_sz: Optional[Tuple[int, int, int]] = None
+    first: bool = False
+
+
+@dataclass
+class UpGeom:
+    name: str            # up_steps.i.up_conv
+    cin: int
+    cout: int
+    k: Tuple[int, int, int]
+    s: Tuple[int, int, int]
+    in_sz: Tuple[int, int, int]
+    out_sz: Tuple[int, int, int]
+
+
+@dataclass
+class Plan:
+    dims: int
+    batch: int
+    in_channels: int
+    out_channels: int
+    in_sz: Tuple[int, int, int]
+    steps: List[object] = field(default_factory=list)   # ConvGeom / UpGeom in execution order
+    out_sz: Tuple[int, int, int] = (0, 0, 0)
+
+
+def _conv_out(sz, taps, dil, what):
+    out = []
+    for i in range(3):
+        eff = (taps[i] - 1) * dil[i] + 1
+        if sz[i] < eff:
+            raise RuntimeError(
+                f"Calculated padded input size per channel: {tuple(sz)}. Kernel size: "
+                f"{tuple((t - 1) * d + 1 for t, d in zip(taps, dil))}. Kernel size can't be greater than actual "
+                f"input size ({what})")
+        out.append(sz[i] - eff + 1)
+    return tuple(out)
+
+
+def plan_unet(spec: dict, xshape) -> Plan:
+    dims = spec["image_dimensions"]
+    if len(xshape) != dims + 2:
+        raise RuntimeError(f"Expected {dims + 2}D input to a {dims}D U-Net, but got input of size: {list(xshape)}")
+    feats = list(spec["feature_sizes"])
+    if xshape[1] != spec["in_channels"]:
+        raise RuntimeError(f"Given groups={spec['groups']['conv1']}, expected input{list(xshape)} to have "
+                           f"{spec['in_channels']} channels, but got {xshape[1]} channels instead")
+    sz = tuple(int(v) for v in xshape[2:]) + (1,) * (3 - dims)
+    plan = Plan(dims=dims, batch=int(xshape[0]), in_channels=spec["in_channels"],
+                out_channels=spec["out_channels"], in_sz=sz)
+    taps = {k: _t3(spec["kernel"][k], dims) for k in ("conv1", "conv2")}
+    dil = {k: _t3(spec["dilation"][k], dims) for k in ("conv1", "conv2")}
+    grp = {k: int(spec["groups"][k]) for k in ("conv1", "conv2")}
+    pool = _t3(spec["max_pool_kernel"], dims)
+    up_k = _t3(spec["upsample_kernel"], dims)
+    up_s = _t3(spec["upsample_stride"], dims)
+
+    def block(prefix, cin, cout, sz, up):
+        for idx in ("1", "2"):
+            key = "conv" + idx
+            c_in = cin if idx == "1" else cout
+            g = grp[key]
+            ref_cin = (2 * c_in if (up and idx == "1") else c_in)
+            if ref_cin % g or cout % g:
+                raise ValueError("in_channels and out_channels must be divisible by groups")
+            fold = False
+            groups, cin_g, cout_g = g, c_in // g, cout // g
+            if up and idx == "1":
+                # conv1(cat(x, x)) -- unet.py:311-312.  g == 1: fold the K halves.  g == 2: group j sees
+                # cat channels [j*C, (j+1)*C) == all of x, i.e. a dense conv with the weight as stored.
+                if g == 1:
+                    fold, groups, cin_g, cout_g = True, 1, c_in, cout
+                elif g == 2:
+                    groups, cin_g, cout_g = 1, c_in, cout
+                else:
+                    raise NotImplementedError("groups > 2 on Up.conv1 (cat(x, x) slices wrap) is not supported yet")
+            osz = _conv_out(sz, taps[key], dil[key], f"{prefix}.{key}")
+            plan.steps.append(ConvGeom(name=f"{prefix}.{key}", bn=f"{prefix}.batch{idx}", cin_t=c_in, cout_t=cout,
+                                       groups=groups, cin_g=cin_g, cout_g=cout_g, ref_cin_g=ref_cin // g, fold=fold,
+                                       taps=taps[key], dil=dil[key], in_sz=sz, out_sz=osz))
+            sz = osz
+        return sz
+
+    skips = []
+    cin = spec["in_channels"]
+    for i, f in enumerate(feats):
+        sz = block(f"down_steps.{i}", cin, f, sz, up=False)
+        cin = f
+        if i < len(feats) - 1:
+            skips.append(sz)
+            psz = tuple(sz[d] // pool[d] for d in range(3))
+            if min(psz) < 1:
+                raise RuntimeError(f"Given input size: ({f}x{'x'.join(map(str, sz[:dims]))}). Calculated output size: "
+                                   f"({f}x{'x'.join(map(str, psz[:dims]))}). Output size is too small")
+            last = plan.steps[-1]
+            last.pool, last.pool_sz = pool, psz
+            sz = psz
+    plan.steps[0].first = True
+    for i in range(len(feats) - 1):
+        f_in, f_out = feats[-1 - i], feats[-2 - i]
+        for d in range(3):
+            if up_k[d] < up_s[d]:
+                raise NotImplementedError("upsample_kernel smaller than upsample_stride is not supported")
+        osz = tuple((sz[d] - 1) * up_s[d] + up_k[d] for d in range(3))
+        plan.steps.append(UpGeom(name=f"up_steps.{i}.up_conv", cin=f_in, cout=f_out, k=up_k, s=up_s, in_sz=sz,
+                                 out_sz=osz))
+        skip = skips.pop()
+        # crop(x_up, skip) then cat((x_up, cropped)) -- unet.py:311-312: fails when the skip is smaller anywhere
+        for d in range(dims):
+            if skip[d] < osz[d]:
+                raise RuntimeError(f"Sizes of tensors must match except in dimension 1. Expected size {osz[d]} but got "
+                                   f"size {skip[d]} for tensor number 1 in the list.")
+        sz = block(f"up_steps.{i}", f_out, f_out, osz, up=True)
+    plan.steps.append(ConvGeom(name="out_conv", bn=None, cin_t=feats[0], cout_t=spec["out_channels"], groups=1,
+                               cin_g=feats[0], cout_g=spec["out_channels"], ref_cin_g=feats[0], fold=False,
+                               taps=(1, 1, 1), dil=(1, 1, 1), in_sz=sz, out_sz=sz))
+    plan.out_sz = sz
+    return plan
+
+
+# ---------------------------------------------------------------------------------------------
+# descriptor helpers
+# ---------------------------------------------------------------------------------------------
+
+def _i3(v):
+    return (C.c_int32 * 3)(*[int(e) for e in v])
+
+
+def conv_desc(dt_in, dt_out, batch, in_size, in_cpitch, in_c_off, in_c_gstep, cin, out_size, out_tsize, out_cpitch,
+              out_c_off, cout, groups, taps, dil=(1, 1, 1), pad=(0, 0, 0), istep=(1, 1, 1), ostep=(1, 1, 1),
+              ooff=(0, 0, 0), in_relu=0, out_relu=0) -> HcuConvDesc:
+    d = HcuConvDesc()
+    d.dtype_in, d.dtype_out, d.batch = dt_in, dt_out, batch
+    d.in_size, d.in_cpitch, d.in_c_off, d.in_c_gstep, d.cin = _i3(in_size), in_cpitch, in_c_off, in_c_gstep, cin
+    d.out_size, d.out_tsize, d.out_cpitch, d.out_c_off = _i3(out_size), _i3(out_tsize), out_cpitch, out_c_off
+    d.cout, d.groups = cout, groups
+    d.taps, d.dil, d.pad, d.istep, d.ostep, d.ooff = _i3(taps), _i3(dil), _i3(pad), _i3(istep), _i3(ostep), _i3(ooff)
+    d.in_relu, d.out_relu = in_relu, out_relu
+    return d
+
+
+def weight_map(groups, j, na, nb, sg, sa, sb, st, t0=(0, 0, 0), tstep=(1, 1, 1), base=0, fold=0,
+               fold_stride=0) -> HcuWeightMap:
+    m = HcuWeightMap()
+    m.groups, m.j, m.na, m.nb = groups, _i3(j), na, nb
+    m.base, m.sg, m.sa, m.sb = base, sg, sa, sb
+    m.st = (C.c_int64 * 3)(*[int(e) for e in st])
+    m.t0, m.tstep, m.fold, m.fold_stride = _i3(t0), _i3(tstep), fold, fold_stride
+    return m
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _nsplit(m: int, roles: int) -> int:
+    """How many CTAs rows split the pixel reduction of a weight gradient."""
+    target = 148 * 8 * 3
+    n = max(1, -(-target // max(1, roles)))
+    n = min(n, max(1, m // 256))
+    return int(min(n, 2048))
+
+
+class UnetEngine:
+    """Executes forward / backward of one ``Plan`` on the CUDA library."""
+
+    def __init__(self, spec: dict):
+        self.spec = spec
+        self._plans: Dict[tuple, Plan] = {}
+        self._inv = None
+
+    @property
+    def lib(self):
+        """The ctypes library, loaded on first use (raises when it is missing: no fallback)."""
+        return _lib.load()
+
+    def plan(self, xshape) -> Plan:
+        key = tuple(xshape)
+        p = self._plans.get(key)
+        if p is None:
+            p = plan_unet(self.spec, xshape)
+            self._plans[key] = p
+        return p
+
+    # ---- small wrappers -----------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _gather_w(self, wm: HcuWeightMap, ref: torch.Tensor, n: int) -> torch.Tensor:
+        out = torch.empty(n, dtype=torch.float32, device=ref.device)
+        _lib.check(self.lib.hcu_weight_gather(C.byref(wm), _ptr(ref), _ptr(out), self._stream()), "weight_gather")
+        return out
+
+    def _conv(self, d, x, w, bias=None, out=None, stats=None, in_scale=None, in_shift=None, out_scale=None,
+              out_shift=None):
+        _lib.check(self.lib.hcu_conv_fwd(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
+                                         _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), self._stream()),
+                   "conv_fwd")
+
+    # ---- weight maps (reference layouts: Conv [Cout, Cin/g, kx, ky, kz]; ConvT [Cin, Cout, kx, ky, kz]) ----
+    @staticmethod
+    def _wm_conv_fwd(g: ConvGeom) -> HcuWeightMap:
+        T = g.taps[0] * g.taps[1] * g.taps[2]
+        rc = g.ref_cin_g
+        return weight_map(g.groups, g.taps, g.cin_g, g.cout_g, sg=g.cout_g * rc * T, sa=T, sb=rc * T,
+                          st=(g.taps[1] * g.taps[2], g.taps[2], 1), fold=int(g.fold), fold_stride=g.cin_g * T)
+
+    @staticmethod
+    def _wm_conv_dgrad(g: ConvGeom) -> HcuWeightMap:
+        T = g.taps[0] * g.taps[1] * g.taps[2]
+        rc = g.ref_cin_g
+        return weight_map(g.groups, g.taps, g.cout_g, g.cin_g, sg=g.cout_g * rc * T, sa=rc * T, sb=T,
+                          st=(g.taps[1] * g.taps[2], g.taps[2], 1), t0=tuple(t - 1 for t in g.taps),
+                          tstep=(-1, -1, -1), fold=int(g.fold), fold_stride=g.cin_g * T)
+
+    @staticmethod
+    def _wm_up_phase(u: UpGeom, phi, J) -> HcuWeightMap:
+        T = u.k[0] * u.k[1] * u.k[2]
+        return weight_map(1, J, u.cin, u.cout, sg=0, sa=u.cout * T, sb=T, st=(u.k[1] * u.k[2], u.k[2], 1),
+                          t0=tuple(phi[d] + u.s[d] * (J[d] - 1) for d in range(3)),
+                          tstep=tuple(-u.s[d] for d in range(3)))
+
+    @staticmethod
+    def _wm_up_dgrad(u: UpGeom) -> HcuWeightMap:
+        T = u.k[0] * u.k[1] * u.k[2]
+        return weight_map(1, u.k, u.cout, u.cin, sg=0, sa=T, sb=u.cout * T, st=(u.k[1] * u.k[2], u.k[2], 1))
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor], x: torch.Tensor,
+                training: bool, save: bool, precision: str = "fp32"):
+        """Returns (logits [B, Cout, *spatial] fp32, saved-state or None)."""
+        lib, st = self.lib, self._stream()
+        plan = self.plan(x.shape)
+        dev = x.device
+        act_dtype = _ACT_DTYPE[precision]
+        adt = _DT[act_dtype]
+        B = plan.batch
+        x = x.contiguous()
+        if x.dtype not in _DT:
+            x = x.float()
+        S = plan.in_sz[0] * plan.in_sz[1] * plan.in_sz[2]
+        cur = torch.empty((B, S, plan.in_channels), dtype=act_dtype, device=dev)
+        _lib.check(lib.hcu_nc_to_cl(_ptr(x), _DT[x.dtype], _ptr(cur), adt, B, plan.in_channels, S, plan.in_channels,
+                                    None, st), "nc_to_cl")
+        saved = [] if save else None
+        use_batch_stats = training
+        for g in plan.steps:
+            if isinstance(g, UpGeom):
+                out = self._up_forward(g, params, cur, B, act_dtype)
+                if save:
+                    saved.append(("up", g, cur))
+                cur = out
+                continue
+            npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
+            w = self._gather_w(self._wm_conv_fwd(g), params[g.name + ".weight"],
+                               g.groups * g.taps[0] * g.taps[1] * g.taps[2] * g.cin_g * g.cout_g)
+            bias = params[g.name + ".bias"]
+            if g.bn is None:  # out_conv: logits, fp32
+                y = torch.empty((B, npix // B, g.cout_t), dtype=torch.float32, device=dev)
+                d = conv_desc(adt, _lib.F32, B, g.in_sz, g.cin_t, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0,
+                              g.cout_g, g.groups, g.taps, g.dil)
+                self._conv(d, cur, w, bias, y)
+                if save:
+                    saved.append(("out", g, cur))
+                if g.cout_t == 1:
+                    logits = y.view((B, 1) + tuple(g.out_sz[:plan.dims]))
+                else:
+                    logits = torch.empty((B, g.cout_t) + tuple(g.out_sz[:plan.dims]), dtype=torch.float32, device=dev)
+                    _lib.check(lib.hcu_cl_to_nc(_ptr(y), _lib.F32, _ptr(logits), _lib.F32, B, g.cout_t, npix // B,
+                                                g.cout_t, None, st), "cl_to_nc")
+                cur = None
+                break
+            gamma, beta = params[g.bn + ".weight"], params[g.bn + ".bias"]
+            rm, rv = buffers[g.bn + ".running_mean"], buffers[g.bn + ".running_var"]
+            d = conv_desc(adt, adt, B, g.in_sz, g.cin_t, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0,
+                          g.cout_g, g.groups, g.taps, g.dil)
+            vec = torch.empty((4, g.cout_t), dtype=torch.float32, device=dev)  # mean, invstd, scale, shift
+            if not save and not use_batch_stats:
+                # inference: BN folded into the conv epilogue, activation written once
+                _lib.check(lib.hcu_bn_eval_affine(g.cout_t, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), BN_EPS,
+                                                  _ptr(bias), _ptr(vec[2]), _ptr(vec[3]), st), "bn_eval_affine")
+                d.out_relu = 1
+                a = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
+                self._conv(d, cur, w, None, a, out_scale=vec[2], out_shift=vec[3])
+                if g.pool is not None:
+                    pooled, _ = self._pool(a, g, B, act_dtype, None, None, 0)
+                    a = pooled
+                cur = a
+                continue
+            y = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
+            if use_batch_stats:
+                stats = torch.zeros((2, g.cout_t), dtype=torch.float64, device=dev)
+                self._conv(d, cur, w, bias, y, stats=stats)
+                _lib.check(lib.hcu_bn_finalize(_ptr(stats), g.cout_t, float(npix), _ptr(gamma), _ptr(beta), BN_EPS,
+                                               BN_MOMENTUM, _ptr(rm), _ptr(rv), _ptr(vec[0]), _ptr(vec[1]),
+                                               _ptr(vec[2]), _ptr(vec[3]), st), "bn_finalize")
+            else:
+                # eval-mode forward that must be differentiable: running statistics, unfused
+                self._conv(d, cur, w, bias, y)
+                _lib.check(lib.hcu_bn_eval_affine(g.cout_t, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), BN_EPS, None,
+                                                  _ptr(vec[2]), _ptr(vec[3]), st), "bn_eval_affine")
+                vec[0].copy_(rm)
+                vec[1].copy_(torch.rsqrt(rv + BN_EPS))
+            argmax = None
+            if g.pool is not None:
+                a, argmax = self._pool(y, g, B, act_dtype, vec[2], vec[3], 1)
+            else:
+                a = torch.empty_like(y)
+                _lib.check(lib.hcu_bn_relu_apply(_ptr(y), adt, _ptr(a), adt, npix, g.cout_t, _ptr(vec[2]),
+                                                 _ptr(vec[3]), 1, st), "bn_relu_apply")
+            if save:
+                saved.append(("conv", g, cur, y, vec, argmax))
+            cur = a
+        if training:
+            nbt = [buffers[g.bn + ".num_batches_tracked"] for g in plan.steps
+                   if isinstance(g, ConvGeom) and g.bn is not None]
+            torch._foreach_add_(nbt, 1)
+        return logits, (plan, saved, act_dtype, training)
+
+    def _pool(self, y, g: ConvGeom, B, act_dtype, scale, shift, relu):
+        adt = _DT[act_dtype]
+        ps = g.pool_sz
+        pooled = torch.empty((B, ps[0] * ps[1] * ps[2], g.cout_t), dtype=act_dtype, device=y.device)
+        argmax = torch.empty((B, ps[0] * ps[1] * ps[2], g.cout_t), dtype=torch.uint8, device=y.device)
+        _lib.check(self.lib.hcu_bn_relu_maxpool(_ptr(y), adt, _ptr(pooled), adt, _ptr(argmax), B, g.out_sz[0],
+                                                g.out_sz[1], g.out_sz[2], g.cout_t, g.pool[0], g.pool[1], g.pool[2],
+                                                _ptr(scale), _ptr(shift), relu, self._stream()), "bn_relu_maxpool")
+        return pooled, argmax
+
+    @staticmethod
+    def _phases(u: UpGeom):
+        for px in range(u.s[0]):
+            for py in range(u.s[1]):
+                for pz in range(u.s[2]):
+                    phi = (px, py, pz)
+                    J = tuple(-(-(u.k[d] - phi[d]) // u.s[d]) for d in range(3))
+                    Q = tuple(-(-(u.out_sz[d] - phi[d]) // u.s[d]) for d in range(3))
+                    yield phi, J, Q
+
+    def _up_forward(self, u: UpGeom, params, cur, B, act_dtype):
+        """ConvTranspose (`unet.py:294-298,310`) as prod(stride) stride-1 sub-convolutions, one per output phase."""
+        adt = _DT[act_dtype]
+        wt, bias = params[u.name + ".weight"], params[u.name + ".bias"]
+        out = torch.empty((B, u.out_sz[0] * u.out_sz[1] * u.out_sz[2], u.cout), dtype=act_dtype, device=cur.device)
+        for phi, J, Q in self._phases(u):
+            w = self._gather_w(self._wm_up_phase(u, phi, J), wt, J[0] * J[1] * J[2] * u.cin * u.cout)
+            d = conv_desc(adt, adt, B, u.in_sz, u.cin, 0, u.cin, u.cin, Q, u.out_sz, u.cout, 0, u.cout, 1, J,
+                          pad=tuple(j - 1 for j in J), ostep=u.s, ooff=phi)
+            self._conv(d, cur, w, bias, out)
+        return out
+
+    # ---- backward -----------------------------------------------------------------------------
+    def backward(self, params: Dict[str, torch.Tensor], state, dlogits: torch.Tensor, need_dx: bool):
+        """Returns ({param name: grad}, dx or None)."""
+        lib, st = self.lib, self._stream()
+        plan, saved, act_dtype, training = state
+        adt = _DT[act_dtype]
+        dev = dlogits.device
+        B = plan.batch
+        grads: Dict[str, torch.Tensor] = {}
+        scratch = torch.empty(4096, dtype=torch.float64, device=dev)
+        dlogits = dlogits.contiguous().float()
+        So = plan.out_sz[0] * plan.out_sz[1] * plan.out_sz[2]
+        co = plan.out_channels
+        # fp16 backward: scale dlogits by a device-computed power of two S (no host sync); every parameter
+        # gradient is multiplied by 1/S where it is written (inv), so nothing downstream sees S
+        scl = inv = None
+        if act_dtype == torch.float16:
+            scales = torch.empty(2, dtype=torch.float32, device=dev)
+            _lib.check(lib.hcu_grad_scale(_ptr(dlogits), dlogits.numel(), GRAD_SCALE_TARGET,
+                                          _ptr(scratch.view(torch.int32)), _ptr(scales), st), "grad_scale")
+            scl, inv = scales[0:1], scales[1:2]
+        if co == 1 and scl is None:
+            dcur = dlogits.view(B, So, 1)
+            dcur_dt = _lib.F32
+        else:
+            dcur = torch.empty((B, So, co), dtype=act_dtype, device=dev)
+            _lib.check(lib.hcu_nc_to_cl(_ptr(dlogits), _lib.F32, _ptr(dcur), adt, B, co, So, co, _ptr(scl), st),
+                       "nc_to_cl")
+            dcur_dt = adt
+        self._inv = inv
+        dx = None
+        for item in reversed(saved):
+            kind = item[0]
+            if kind == "out":
+                _, g, a_in = item
+                npix = B * So
+                grads[g.name + ".bias"] = self._colsum(dcur, dcur_dt, npix, co, scratch)
+                grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, adt, dcur, dcur_dt, B, params[g.name + ".weight"])
+                dcur = self._dgrad_conv(g, dcur, dcur_dt, B, params[g.name + ".weight"], act_dtype)
+                dcur_dt = adt
+            elif kind == "conv":
+                _, g, a_in, y, vec, argmax = item
+                npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
+                if argmax is not None:
+                    dfull = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
+                    _lib.check(lib.hcu_maxpool_bwd(_ptr(dcur), dcur_dt, _ptr(argmax), _ptr(dfull), adt, B, g.out_sz[0],
+                                                   g.out_sz[1], g.out_sz[2], g.cout_t, g.pool[0], g.pool[1],
+                                                   g.pool[2], st), "maxpool_bwd")
+                    dcur, dcur_dt = dfull, adt
+                sums = torch.zeros((2, g.cout_t), dtype=torch.float64, device=dev)
+                _lib.check(lib.hcu_bn_bwd_stats(_ptr(dcur), dcur_dt, _ptr(y), adt, npix, g.cout_t, _ptr(vec[2]),
+                                                _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(sums), st),
+                           "bn_bwd_stats")
+                dgamma = torch.empty(g.cout_t, dtype=torch.float32, device=dev)
+                dbeta = torch.empty_like(dgamma)
+                dbias = torch.empty_like(dgamma)
+                coef = torch.empty((3, g.cout_t), dtype=torch.float32, device=dev)
+                _lib.check(lib.hcu_bn_bwd_finalize(_ptr(sums), g.cout_t, float(npix), _ptr(params[g.bn + ".weight"]),
+                                                   _ptr(vec[0]), _ptr(vec[1]), 1 if training else 0, 1.0, _ptr(inv),
+                                                   _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(coef), st),
+                           "bn_bwd_finalize")
+                dy = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
+                _lib.check(lib.hcu_bn_bwd_apply(_ptr(dcur), dcur_dt, _ptr(y), adt, _ptr(dy), adt, npix, g.cout_t,
+                                                _ptr(vec[2]), _ptr(vec[3]), 1, _ptr(coef), st), "bn_bwd_apply")
+                grads[g.bn + ".weight"], grads[g.bn + ".bias"], grads[g.name + ".bias"] = dgamma, dbeta, dbias
+                grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, adt, dy, adt, B, params[g.name + ".weight"])
+                if g.first and not need_dx:
+                    dcur = None
+                else:
+                    dcur = self._dgrad_conv(g, dy, adt, B, params[g.name + ".weight"], act_dtype)
+                    dcur_dt = adt
+                if g.first and need_dx:
+                    S = plan.in_sz[0] * plan.in_sz[1] * plan.in_sz[2]
+                    dx = torch.empty((B, plan.in_channels) + tuple(plan.in_sz[:plan.dims]), dtype=torch.float32,
+                                     device=dev)
+                    _lib.check(lib.hcu_cl_to_nc(_ptr(dcur), adt, _ptr(dx), _lib.F32, B, plan.in_channels, S,
+                                                plan.in_channels, _ptr(inv), st), "cl_to_nc")
+            else:  # "up"
+                _, u, a_in = item
+                npix_out = B * u.out_sz[0] * u.out_sz[1] * u.out_sz[2]
+                grads[u.name + ".bias"] = self._colsum(dcur, dcur_dt, npix_out, u.cout, scratch)
+                # weight gradient: R[t][co][ci] = sum_i dOut[i*s + t][co] * In[i][ci]
+                T = u.k[0] * u.k[1] * u.k[2]
+                d = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin, 1,
+                              u.k, istep=u.s)
+                m = B * u.in_sz[0] * u.in_sz[1] * u.in_sz[2]
+                roles = T * (-(-u.cout // 8)) * (-(-u.cin // 8))
+                ns = _nsplit(m, roles)
+                total = T * u.cout * u.cin
+                partial = torch.empty((ns, total), dtype=torch.float32, device=dev)
+                _lib.check(lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(dcur), None, None, _ptr(a_in), _ptr(partial), ns,
+                                                      st), "wgrad(up)")
+                gw = torch.empty_like(params[u.name + ".weight"])
+                wm = self._wm_up_dgrad(u)
+                _lib.check(lib.hcu_weight_scatter(C.byref(wm), _ptr(partial), ns, total, 1.0, _ptr(inv), 0, _ptr(gw),
+                                                  st), "weight_scatter(up)")
+                grads[u.name + ".weight"] = gw
+                # data gradient: strided gather convolution over dOut
+                w = self._gather_w(wm, params[u.name + ".weight"], total)
+                dprev = torch.empty((B, u.in_sz[0] * u.in_sz[1] * u.in_sz[2], u.cin), dtype=act_dtype, device=dev)
+                d2 = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin,
+                               1, u.k, istep=u.s)
+                self._conv(d2, dcur, w, None, dprev)
+                dcur, dcur_dt = dprev, adt
+        return grads, dx
+
+    def _colsum(self, x, dt, npix, c, scratch):
+        out = torch.empty(c, dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.hcu_colsum(_ptr(x), dt, npix, c, 0, c, 1.0, _ptr(self._inv), _ptr(scratch), _ptr(out),
+                                       self._stream()), "colsum")
+        return out
+
+    def _wgrad_conv(self, g: ConvGeom, a_in, a_dt, dy, dy_dt, B, wref):
+        T = g.taps[0] * g.taps[1] * g.taps[2]
+        d = conv_desc(a_dt, dy_dt, B, g.in_sz, g.cin_t, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0, g.cout_g,
+                      g.groups, g.taps, g.dil)
+        m = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
+        roles = g.groups * T * (-(-g.cin_g // 8)) * (-(-g.cout_g // 8))
+        ns = _nsplit(m, roles)
+        total = g.groups * T * g.cin_g * g.cout_g
+        partial = torch.empty((ns, total), dtype=torch.float32, device=dy.device)
+        _lib.check(self.lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(a_in), None, None, _ptr(dy), _ptr(partial), ns,
+                                                   self._stream()), "wgrad")
+        gw = torch.empty_like(wref)
+        wm = self._wm_conv_fwd(g)
+        _lib.check(self.lib.hcu_weight_scatter(C.byref(wm), _ptr(partial), ns, total, 1.0, _ptr(self._inv), 0, _ptr(gw),
+                                               self._stream()), "weight_scatter")
+        return gw
+
+    def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype):
+        adt = _DT[act_dtype]
+        T = g.taps[0] * g.taps[1] * g.taps[2]
+        w = self._gather_w(self._wm_conv_dgrad(g), wref, g.groups * T * g.cin_g * g.cout_g)
+        dprev = torch.empty((B, g.in_sz[0] * g.in_sz[1] * g.in_sz[2], g.cin_t), dtype=act_dtype, device=dy.device)
+        pad = tuple((g.taps[i] - 1) * g.dil[i] for i in range(3))
+        d = conv_desc(dy_dt, adt, B, g.out_sz, g.cout_t, 0, g.cout_g, g.cout_g, g.in_sz, g.in_sz, g.cin_t, 0, g.cin_g,
+                      g.groups, g.taps, g.dil, pad=pad)
+        self._conv(d, dy, w, None, dprev)
+        return dprev

@@ -1,0 +1,213 @@
+/*
+ * hcunet_b200.h -- C ABI of libhcunet_b200.so (hand-written sm_100a kernels for the HcUnet hot path).
+ *
+ * The reference (wisamreid/HcUnet) is pure Python with NO FFI: every arithmetic call on its hot
+ * path is a torch.nn module (hcat/unet.py:49-51) or torch.nn.functional (hcat/loss.py:65).  The
+ * entry points below are therefore what a maintainer binds *instead of* those ATen/cuDNN calls;
+ * each one names the reference call site it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  All pointers are DEVICE pointers unless
+ *     the name says host.  The caller owns every buffer (PyTorch caching allocator); the library
+ *     allocates nothing persistent.
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     immediately: no implicit synchronisation, no default-stream use, CUDA-graph capturable.
+ *   - return value: 0 on success, negative HcuStatus on failure; hcu_last_error() gives a
+ *     thread-local message.  Nothing throws, nothing exits.
+ *   - activations are CHANNELS-LAST: [N][X][Y][Z][C] (2D: Z == 1), element type HcuDType.
+ *     The reference layout [N][C][X][Y][Z] only exists at the boundary (hcu_nc_to_cl /
+ *     hcu_cl_to_nc).  Parameters stay in the reference (PyTorch) layout in fp32 and are
+ *     gathered into GEMM-B layouts by hcu_weight_gather.
+ */
+#ifndef HCUNET_B200_H
+#define HCUNET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCU_ABI_VERSION 4
+
+typedef enum HcuStatus {
+  HCU_OK = 0,
+  HCU_ERR_INVALID = -1,   /* bad descriptor / unsupported combination */
+  HCU_ERR_CUDA = -2,      /* a CUDA runtime call failed (message has the CUDA string) */
+  HCU_ERR_UNSUPPORTED = -3
+} HcuStatus;
+
+/* activations / gradients are HCU_F32 or HCU_F16; HCU_BF16 is accepted for loss masks / weights only */
+typedef enum HcuDType { HCU_F32 = 0, HCU_BF16 = 1, HCU_F16 = 2 } HcuDType;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int hcu_abi_version(void);
+const char* hcu_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long hcu_launch_count(void);
+int hcu_zero(void* ptr, size_t bytes, void* stream);
+
+/* ---- generic gather-convolution descriptor -------------------------------------------------
+ * One launch computes, for every output position o = (n, ox, oy, oz) of an OX*OY*OZ grid and
+ * every group g:
+ *   out[n, o*ostep + ooff, out_c_off + g*cout + co] =
+ *       epilogue( sum_{t, ci} A(in[n, o*istep - pad + t*dil, in_c_off + g*in_c_gstep + ci]) * W[g][t][ci][co] )
+ * with zero fill outside the input.  With the right (istep, pad, ostep, ooff, W) this one engine is
+ *   - Conv{2,3}d forward, any kernel/dilation/groups, padding 0       (hcat/unet.py:246-257,281-292,120)
+ *   - its data gradient (pad = (k-1)*dil, flipped W)                  (autograd of the same calls)
+ *   - ConvTranspose{2,3}d forward as stride-phase sub-convolutions    (hcat/unet.py:294-298,310)
+ *   - ConvTranspose data gradient (istep = stride)
+ * A() is an optional per-input-channel affine+ReLU applied on load (fuses the producer's
+ * BatchNorm+ReLU, hcat/unet.py:264-265); the epilogue optionally adds bias, applies a per-channel
+ * affine (+ReLU) (eval-mode BN folded in) and accumulates per-channel sum / sum-of-squares in
+ * fp64 for training-mode BatchNorm (hcat/unet.py:259-260).
+ */
+typedef struct HcuConvDesc {
+  int32_t dtype_in;        /* HcuDType of `in`  */
+  int32_t dtype_out;       /* HcuDType of `out` */
+  int32_t batch;
+  int32_t in_size[3];      /* IX, IY, IZ */
+  int32_t in_cpitch;       /* channels per input voxel in memory */
+  int32_t in_c_off;        /* first input channel of group 0 */
+  int32_t in_c_gstep;      /* input-channel offset between consecutive groups */
+  int32_t cin;             /* input channels reduced over, per group */
+  int32_t out_size[3];     /* OX, OY, OZ: output positions computed by this launch */
+  int32_t out_tsize[3];    /* TX, TY, TZ: spatial size of the output TENSOR */
+  int32_t out_cpitch;
+  int32_t out_c_off;
+  int32_t cout;            /* output channels per group */
+  int32_t groups;
+  int32_t taps[3];
+  int32_t dil[3];
+  int32_t pad[3];          /* low-side zero padding (in input voxels) */
+  int32_t istep[3];        /* input step per output position (conv stride) */
+  int32_t ostep[3];        /* output step per output position (transposed-conv stride) */
+  int32_t ooff[3];         /* output offset (transposed-conv phase) */
+  int32_t in_relu;         /* apply ReLU after the input affine */
+  int32_t out_relu;        /* apply ReLU in the epilogue */
+  int32_t reserved[4];
+} HcuConvDesc;
+
+/* W: fp32 [groups][taps][cin][cout].  bias/out_scale/out_shift: fp32 [groups*cout] or NULL.
+ * in_scale/in_shift: fp32 [in_cpitch] or NULL.  stats: fp64 [2][out_cpitch] (sum, sumsq) or NULL;
+ * stats see the value after bias, before out_scale/out_shift/ReLU.
+ * Replaces: nn.Conv3d/Conv2d.forward (unet.py:246-257), conv backward-data, ConvTranspose3d (unet.py:294). */
+int hcu_conv_fwd(const HcuConvDesc* d, const void* in, const float* W, const float* bias,
+                 const float* in_scale, const float* in_shift, const float* out_scale,
+                 const float* out_shift, void* out, double* stats, void* stream);
+
+/* Weight gradient of the same gather-convolution:
+ *   R[g][t][ca][cb] = sum_{n,o} A(a[n, o*istep - pad + t*dil, a_c_off + g*a_c_gstep + ca]) * b[n, o, b_c_off + g*cb_n + cb]
+ * `d` describes the gather side exactly like hcu_conv_fwd (in_* = a, cin = ca count, cout = cb count,
+ * out_size = the o grid, out_cpitch/out_c_off/dtype_out describe `b`, ostep/ooff must be 1/0).
+ * The reduction over (n,o) is split over `nsplit` CTAs rows; partial[nsplit][groups*taps*cin*cout] fp32.
+ * Replaces: convolution_backward's weight gradient (autograd of unet.py:246-257,294-298). */
+int hcu_conv_wgrad_partial(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
+                           const void* b, float* partial, int32_t nsplit, void* stream);
+
+/* ---- weight layout transforms -------------------------------------------------------------
+ * Generic strided gather between a reference-layout parameter and a packed GEMM-B tensor
+ * P[g][jx][jy][jz][a][b]:
+ *   ref_index = base + g*sg + a*sa + b*sb + sum_d (t0[d] + j_d*tstep[d]) * st[d]   (+ fold_stride if fold)
+ * gather : P = ref[idx] (+ ref[idx+fold_stride] when fold)      -- forward / dgrad / phase weights
+ * scatter: ref[idx] (and ref[idx+fold_stride]) = scale * sum_{s<nsplit} P_s   -- wgrad results
+ * `dscale` (every function that has it): optional DEVICE fp32 scalar multiplied into `scale`; it carries
+ * the 1/S of the fp16 backward's loss scaling (hcu_grad_scale) without a host round trip.
+ */
+typedef struct HcuWeightMap {
+  int32_t groups, j[3], na, nb;
+  int64_t base, sg, sa, sb, st[3];
+  int32_t t0[3], tstep[3];
+  int32_t fold;            /* 0/1 */
+  int64_t fold_stride;
+} HcuWeightMap;
+int hcu_weight_gather(const HcuWeightMap* m, const float* ref, float* packed, void* stream);
+int hcu_weight_scatter(const HcuWeightMap* m, const float* partial, int32_t nsplit, int64_t split_stride,
+                       float scale, const float* dscale, int32_t accumulate, float* ref, void* stream);
+
+/* ---- boundary layout ------------------------------------------------------------------------
+ * [N][C][S] (reference, S = X*Y*Z) <-> [N][S][cpitch] channels-last.  Extra channels are zero.
+ * Replaces nothing in the reference; it is the cost of keeping its NCDHW API (unet.py:125). */
+int hcu_nc_to_cl(const void* src, int32_t dtype_src, void* dst, int32_t dtype_dst, int64_t n, int32_t c,
+                 int64_t s, int32_t cpitch, const float* dscale, void* stream);
+int hcu_cl_to_nc(const void* src, int32_t dtype_src, void* dst, int32_t dtype_dst, int64_t n, int32_t c,
+                 int64_t s, int32_t cpitch, const float* dscale, void* stream);
+/* Loss scaling of the fp16 backward: scales[0] = S = 2^k such that max|g| * S is in (target/2, target],
+ * scales[1] = 1/S; g: fp32 [n]; scratch: one uint32.  No host synchronisation. */
+int hcu_grad_scale(const float* g, int64_t n, float target, unsigned int* scratch, float* scales, void* stream);
+
+/* ---- BatchNorm (+ReLU, +MaxPool) --------------------------------------------------------------
+ * Training statistics come from hcu_conv_fwd's fp64 `stats`.  hcu_bn_finalize turns them into
+ * mean / invstd / (scale, shift) and updates running stats exactly like nn.BatchNorm3d
+ * (momentum, unbiased running var, eps) -- unet.py:259-260,305-306.
+ * hcu_bn_eval_affine builds (scale, shift) from running stats for eval(). */
+int hcu_bn_finalize(const double* stats, int32_t c, double count, const float* gamma, const float* beta,
+                    float eps, float momentum, float* running_mean, float* running_var,
+                    float* mean, float* invstd, float* scale, float* shift, void* stream);
+int hcu_bn_eval_affine(int32_t c, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, const float* conv_bias, float* scale, float* shift,
+                       void* stream);
+/* a = relu?(y*scale[c] + shift[c]) elementwise over [npix][c].  Replaces batchN + relu_ (unet.py:264-265). */
+int hcu_bn_relu_apply(const void* y, int32_t dtype_y, void* a, int32_t dtype_a, int64_t npix, int32_t c,
+                      const float* scale, const float* shift, int32_t relu, void* stream);
+/* Fused (optional affine+ReLU) + MaxPool with kernel == stride, floor mode (unet.py:123,131).
+ * in [n][ix][iy][iz][c] -> pooled [n][ix/px][iy/py][iz/pz][c]; argmax: uint8 window index
+ * ((wx*py + wy)*pz + wz) of the FIRST maximum in PyTorch scan order, NaN propagates. */
+int hcu_bn_relu_maxpool(const void* y, int32_t dtype_y, void* pooled, int32_t dtype_p, uint8_t* argmax,
+                        int32_t n, int32_t ix, int32_t iy, int32_t iz, int32_t c, int32_t px, int32_t py,
+                        int32_t pz, const float* scale, const float* shift, int32_t relu, void* stream);
+/* dfull[n][ix][iy][iz][c] = dpooled routed to the argmax voxel, zero elsewhere (max_pool backward). */
+int hcu_maxpool_bwd(const void* dpooled, int32_t dtype_dp, const uint8_t* argmax, void* dfull, int32_t dtype_df,
+                    int32_t n, int32_t ix, int32_t iy, int32_t iz, int32_t c, int32_t px, int32_t py, int32_t pz,
+                    void* stream);
+/* BatchNorm+ReLU backward, pass 1: g = da * [y*scale+shift > 0 or !relu];
+ * sums[0][c] += sum g, sums[1][c] += sum g*(y-mean)*invstd   (fp64). */
+int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix, int32_t c,
+                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                     int32_t relu, double* sums, void* stream);
+/* pass 2 (tiny): dgamma, dbeta, conv-bias grad and the coefficients of dy = c1*g + c2*y + c3.
+ * training != 0: batch-stat backward; training == 0: running-stat (eval) backward. */
+int hcu_bn_bwd_finalize(const double* sums, int32_t c, double count, const float* gamma, const float* mean,
+                        const float* invstd, int32_t training, float grad_scale, const float* dscale, float* dgamma,
+                        float* dbeta, float* dbias, float* coef, void* stream);
+/* pass 3: dy = c1[c]*g + c2[c]*y + c3[c]. */
+int hcu_bn_bwd_apply(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, void* dy, int32_t dtype_dy,
+                     int64_t npix, int32_t c, const float* scale, const float* shift, int32_t relu,
+                     const float* coef, void* stream);
+/* out[c] (+)= scale * sum over pixels of x[pix][c_off + c]  (bias gradients of convT / out_conv). */
+int hcu_colsum(const void* x, int32_t dtype_x, int64_t npix, int32_t cpitch, int32_t c_off, int32_t c,
+               float scale, const float* dscale, double* scratch, float* out, void* stream);
+
+/* ---- losses (hcat/loss.py) ----------------------------------------------------------------------
+ * pred: fp32 contiguous [B][C][x][y][z] (2D: z == 1).  mask / pwl: any HcuDType, [B][C][X][Y][Z]
+ * with X>=x..., cropped from the origin (loss.py:51-56); pwl may be NULL (weight 2, loss.py:46-48).
+ * mode 0 'pixel' (loss.py:70-72); mode 1 'sigmoid' (loss.py:38-40,97-99: BCE-with-logits of sigmoid(pred)).
+ * out_sum: fp64 scalar accumulator (caller zeroes it); if zsums != NULL also per-z sums fp64 [z]
+ * (the 'worst_z' reduction, loss.py:74-80). */
+typedef struct HcuLossDesc {
+  int32_t b, c, x, y, z;      /* pred shape */
+  int32_t mx, my, mz;         /* mask / pwl spatial shape (>= pred's) */
+  int32_t dtype_mask, dtype_pwl;
+  int32_t mode;
+  int32_t reserved[3];
+} HcuLossDesc;
+int hcu_wbce_fwd(const HcuLossDesc* d, const float* pred, const void* mask, const void* pwl, double* out_sum,
+                 double* zsums, void* stream);
+/* dpred = gout[0] * mult * zscale[z] * dBCE/dpred * (pwl+1); gout is a DEVICE fp32 scalar (the upstream
+ * gradient), mult a host scalar (1/N for the mean), zscale: DEVICE fp32 [z] or NULL. */
+int hcu_wbce_bwd(const HcuLossDesc* d, const float* pred, const void* mask, const void* pwl, const float* gout,
+                 float mult, const float* zscale, float* dpred, void* stream);
+/* dice / L1 / MSE reductions (loss.py:104-177): sums[0..2] fp64 =
+ *   kind 0 (dice): sum sigmoid(p)*m, sum sigmoid(p), sum m;  kind 1 (L1): sum |p-m|;  kind 2 (MSE): sum (p-m)^2 */
+int hcu_pair_reduce(const HcuLossDesc* d, int32_t kind, const float* pred, const void* mask, double* sums,
+                    void* stream);
+/* dpred for the same three; coef: DEVICE fp32 [2]:
+ *   dice: dpred = s(1-s) * (coef[0]*m + coef[1]);  L1: coef[0]*sign(p-m);  MSE: coef[0]*(p-m) */
+int hcu_pair_bwd(const HcuLossDesc* d, int32_t kind, const float* pred, const void* mask, const float* coef,
+                 float* dpred, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCUNET_B200_H */

@@ -1,0 +1,267 @@
+"""GPU parity tests proper: the CUDA path (through the public API -> C ABI -> sm_100a kernels) against
+(a) the committed golden vectors minted from the unmodified reference and (b) the CPU oracle on fresh
+seeded inputs.  Tolerances are the ones BASELINE.json's north_star states:
+
+    fp32 path  : rel-L2 <= 1e-5 on outputs (logits, loss); gradients rel-L2 <= 1e-4 per tensor
+    mixed path : rel-L2 <= 2e-3 on outputs; gradients rel-L2 <= 2e-2 per tensor (fp16 storage of the
+                 activation gradients, fp32 accumulate); >= 99.9 % thresholded-mask agreement
+
+Conv biases that feed a training-mode BatchNorm have an analytically-zero gradient (the reference's values are
+rounding noise ~1e-9), so those are compared with an absolute tolerance.
+"""
+import os
+
+import pytest
+import torch
+
+from conftest import GOLDEN, MODEL_CASES, load_golden
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": dict(out=1e-5, grad=1e-4, buf=1e-5), "mixed": dict(out=2e-3, grad=2e-2, buf=2e-3)}
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def build(fx, precision):
+    import hcunet_b200 as H
+
+    m = H.Unet_Constructor(**fx["kwargs"])
+    m.load_state_dict(fx["state_dict"])
+    m.precision = precision
+    return m.cuda()
+
+
+def is_dead_bias(name):
+    # conv bias directly followed by train-mode BN: d/dbias == 0 analytically
+    return name.endswith(".bias") and (".conv1." in name or ".conv2." in name)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "mixed"])
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_train_step_matches_golden(name, precision):
+    import hcunet_b200 as H
+
+    tol = TOL[precision]
+    fx = load_golden(name)
+    m = build(fx, precision)
+    m.train()
+    x, mask, pwl = fx["x"].cuda(), fx["mask"].cuda(), fx["pwl"].cuda()
+    before = H._lib.launch_count()
+    logits = m(x)
+    assert logits.shape == fx["logits_train"].shape
+    assert logits.dtype == torch.float32 and logits.is_cuda
+    assert rel_l2(logits, fx["logits_train"]) <= tol["out"], rel_l2(logits, fx["logits_train"])
+    loss = H.cross_entropy(logits, mask, pwl, "pixel")
+    assert abs(float(loss) - float(fx["loss"])) <= tol["out"] * abs(float(fx["loss"]))
+    loss.backward()
+    torch.cuda.synchronize()
+    assert H._lib.launch_count() - before > 20, "the CUDA library did not run"
+    worst = 0.0
+    gmax = max(float(g.abs().max()) for g in fx["grads"].values())
+    for k, g in fx["grads"].items():
+        mine = dict(m.named_parameters())[k].grad
+        assert mine is not None, k
+        if is_dead_bias(k):
+            assert float((mine.cpu() - g).abs().max()) <= 1e-4 * gmax + 1e-7, k
+            continue
+        r = rel_l2(mine, g)
+        worst = max(worst, r)
+        assert r <= tol["grad"], (k, r)
+    sd = m.state_dict()
+    for k, v in fx["buffers_after"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        else:
+            assert rel_l2(sd[k], v) <= tol["buf"], (k, rel_l2(sd[k], v))
+    # eval-mode forward with the updated running statistics (BN folded into the conv epilogue)
+    m.eval()
+    with torch.no_grad():
+        ev = m(x)
+    assert rel_l2(ev, fx["logits_eval"]) <= tol["out"], rel_l2(ev, fx["logits_eval"])
+    agree = ((ev.cpu() > 0) == (fx["logits_eval"] > 0)).float().mean()
+    assert float(agree) >= 0.999
+    print(f"{name}/{precision}: logits {rel_l2(logits, fx['logits_train']):.2e} eval {rel_l2(ev, fx['logits_eval']):.2e} "
+          f"worst grad {worst:.2e}")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "mixed"])
+def test_fresh_input_matches_oracle(precision):
+    """Not a fixture: new seed, ragged sizes (odd pooling remainders), eval-mode backward, input gradient."""
+    import hcunet_b200 as H
+
+    tol = TOL[precision]
+    kwargs = dict(O.README_3D, feature_sizes=[4, 8, 16])
+    torch.manual_seed(21)
+    m = H.Unet_Constructor(**kwargs)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((1, 4, 47, 45, 7), generator=g)
+    mask = (torch.rand((1, 1, 47, 45, 7), generator=g) > 0.5).float()
+    pwl = torch.rand((1, 1, 47, 45, 7), generator=g)
+    loss_o, logits_o, grads_o, newbuf = O.train_step_grads(sd, kwargs, x, mask, pwl)
+    m.precision = precision
+    m = m.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    logits = m(xg)
+    loss = H.cross_entropy(logits, mask.cuda().half(), pwl.cuda(), "pixel")  # fp16 mask like the dataloader
+    loss.backward()
+    assert rel_l2(logits, logits_o) <= tol["out"]
+    assert abs(float(loss) - float(loss_o)) <= tol["out"] * abs(float(loss_o))
+    for k, gr in grads_o.items():
+        if is_dead_bias(k):
+            continue
+        assert rel_l2(dict(m.named_parameters())[k].grad, gr) <= tol["grad"], k
+    # input gradient against autograd through the oracle
+    xo = x.clone().requires_grad_(True)
+    lo, _ = O.unet_forward(sd, kwargs, xo, training=True)
+    O.cross_entropy(lo, mask, pwl).backward()
+    assert rel_l2(xg.grad, xo.grad) <= tol["grad"]
+
+
+def test_too_small_and_bad_inputs_raise():
+    import hcunet_b200 as H
+
+    m = H.Unet_Constructor(**O.README_3D).cuda()
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 4, 128, 128, 32, device="cuda"))  # bottom level smaller than the kernel
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 3, 256, 256, 8, device="cuda"))   # wrong channel count
+    with pytest.raises(RuntimeError):
+        m(torch.randn(1, 4, 192, 192, 8))                  # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        H.cross_entropy(torch.zeros(1, 1, 4, 4, 2), torch.zeros(1, 1, 4, 4, 2), None)  # CPU: no fallback
+
+
+def test_loss_cases_match_golden():
+    import hcunet_b200 as H
+
+    fx = torch.load(os.path.join(GOLDEN, "loss_cases.pt"), weights_only=False)
+    n = 0
+    for c in fx["cases"]:
+        p = c["pred"].cuda().requires_grad_(True)
+        m = c["mask"].cuda()
+        if c["fn"] == "cross_entropy":
+            w = c["pwl"].cuda() if c["pwl"] is not None else None
+            if c["method"] == "random":
+                torch.manual_seed(5)
+                v = H.cross_entropy(p, m, w, "random", c["num_random_pixels"])
+            else:
+                v = H.cross_entropy(p, m, w, c["method"])
+        else:
+            v = getattr(H, c["fn"])(p, m)
+        v.backward()
+        tag = (c["fn"], c.get("method"), c.get("variant"))
+        assert v.dtype == torch.float32
+        assert abs(float(v) - float(c["value"])) <= 2e-6 * max(1.0, abs(float(c["value"]))), tag
+        assert rel_l2(p.grad, c["grad"]) <= 5e-6, (tag, rel_l2(p.grad, c["grad"]))
+        n += 1
+    assert n >= 20
+
+
+def test_loss_errors_and_pwl_none():
+    import hcunet_b200 as H
+
+    p = torch.zeros(1, 1, 4, 4, 2, device="cuda")
+    with pytest.raises(ValueError):
+        H.cross_entropy(p, p, p, method="nope")
+    with pytest.raises(ValueError):
+        H.cross_entropy(p, p, p, method="random")
+    with pytest.raises(ValueError):
+        H.cross_entropy(p, p, p, method="random", num_random_pixels=1)
+    with pytest.raises(IndexError):
+        H.cross_entropy(torch.zeros(4, 4, 4, device="cuda"), torch.zeros(4, 4, 4, device="cuda"), None)
+    a = H.cross_entropy(p + 0.3, torch.ones_like(p), None)
+    b = H.cross_entropy(p + 0.3, torch.ones_like(p), torch.ones_like(p))
+    assert float(a) == float(b)  # pwl=None => weight 2 (loss.py:46-48)
+
+
+def test_maxpool_ties_and_nan_follow_aten():
+    """Post-ReLU zeros make ties common: the first maximum in scan order wins, NaN propagates (ATen)."""
+    import ctypes as C
+
+    from hcunet_b200 import _lib
+
+    lib = _lib.load()
+    torch.manual_seed(0)
+    n, c, ix, iy, iz = 2, 8, 9, 7, 5
+    x = torch.randint(0, 3, (n, c, ix, iy, iz)).float()
+    x[0, 1, 2, 2, 1] = float("nan")
+    xr = x.clone().requires_grad_(True)
+    ref, idx = torch.nn.functional.max_pool3d(xr, (2, 2, 1), return_indices=True)
+    go = torch.randn_like(ref)
+    ref.backward(go)
+    cl = x.permute(0, 2, 3, 4, 1).contiguous().cuda()
+    ox, oy, oz = ix // 2, iy // 2, iz
+    pooled = torch.empty((n, ox, oy, oz, c), device="cuda")
+    arg = torch.empty((n, ox, oy, oz, c), dtype=torch.uint8, device="cuda")
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(lib.hcu_bn_relu_maxpool(P(cl), _lib.F32, P(pooled), _lib.F32, P(arg), n, ix, iy, iz, c, 2, 2, 1, None,
+                                       None, 0, st))
+    got = pooled.permute(0, 4, 1, 2, 3).cpu()
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(ref.detach(), nan=-7.0))
+    dfull = torch.empty((n, ix, iy, iz, c), device="cuda")
+    gcl = go.permute(0, 2, 3, 4, 1).contiguous().cuda()
+    _lib.check(lib.hcu_maxpool_bwd(P(gcl), _lib.F32, P(arg), P(dfull), _lib.F32, n, ix, iy, iz, c, 2, 2, 1, st))
+    assert torch.equal(dfull.permute(0, 4, 1, 2, 3).cpu(), xr.grad)
+
+
+def test_save_load_roundtrip(tmp_path):
+    import hcunet_b200 as H
+
+    fx = load_golden("g3d_small")
+    m = build(fx, "fp32")
+    f = str(tmp_path / "m.unet")
+    cwd = os.getcwd()
+    os.chdir(tmp_path)  # save() snapshots ./**/*.py like the reference (unet.py:150-160)
+    try:
+        assert m.save(f, hyperparameters={"lr": 1e-3}) is None
+    finally:
+        os.chdir(cwd)
+    blob = torch.load(f, weights_only=False)
+    assert set(blob) == {"state_dict", "model_specifications", "hyperparameters", "python_files", "tree_structure"}
+    m2 = H.Unet_Constructor(image_dimensions=3, in_channels=1, out_channels=1, feature_sizes=[2, 4],
+                            kernel=(3, 3, 1), upsample_kernel=(2, 2, 1), max_pool_kernel=(2, 2, 1),
+                            upsample_stride=(2, 2, 1))
+    hp = m2.load(f)
+    assert hp == {"lr": 1e-3}
+    assert not m2.training and m2.model_specification == m.model_specification
+    for k, v in m.state_dict().items():
+        assert torch.equal(v.cpu(), m2.state_dict()[k].cpu()), k
+    # the loaded module is on the CPU like the reference's (unet.py:177 re-runs __init__); moved, it computes
+    x = fx["x"].cuda()
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m2.cuda()(x), m(x))
+    # a state_dict in the file drives the oracle restatement of the reference: same logits
+    sd = {k: v.cpu() for k, v in blob["state_dict"].items()}
+    with torch.no_grad():
+        ref, _ = O.unet_forward(sd, blob["model_specifications"], fx["x"], training=False)
+    assert rel_l2(m(x), ref) <= 1e-5
+
+
+def test_skip_connection_is_dead_like_the_reference():
+    """Up.forward computes conv1(cat(x_up, x_up)); the skip tensor's values never matter.  Our
+    engine never reads it -- check the consequence: the folded weight equals the reference arithmetic."""
+    import hcunet_b200 as H
+
+    fx = load_golden("g3d_small")
+    m = build(fx, "fp32").eval()
+    sd = {k: v.clone() for k, v in fx["state_dict"].items()}
+    # swapping the two K-halves of every Up.conv1 weight must not change the output (W[:, :C] + W[:, C:])
+    for k in list(sd):
+        if k.startswith("up_steps") and k.endswith("conv1.weight"):
+            w = sd[k]
+            h = w.shape[1] // 2
+            sd[k] = torch.cat([w[:, h:], w[:, :h]], 1)
+    m2 = H.Unet_Constructor(**fx["kwargs"])
+    m2.load_state_dict(sd)
+    m2 = m2.cuda().eval()
+    with torch.no_grad():
+        a, b = m(fx["x"].cuda()), m2(fx["x"].cuda())
+    assert rel_l2(a, b) <= 1e-6

@@ -1,0 +1,123 @@
+"""CPU-side tests (no GPU): the drop-in surface, the planner's geometry / error behaviour, and that the
+C-ABI library loads and exports every symbol ``include/hcunet_b200.h`` declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import MODEL_CASES, ROOT, load_golden
+from oracle import unet_oracle as O
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from hcunet_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "hcunet_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(hcu_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    assert os.path.exists(_lib.LIB_PATH), "run `python -c 'import __graft_entry__ as g; g.build()'` first"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    loaded = _lib.load()
+    assert loaded.hcu_abi_version() == _lib.ABI_VERSION
+    m = re.search(r"#define HCU_ABI_VERSION (\d+)", header)
+    assert int(m.group(1)) == _lib.ABI_VERSION
+    # struct sizes agree with the header's layout (all int32 / int64 fields, natural alignment)
+    assert ctypes.sizeof(_lib.HcuConvDesc) == 4 * (3 + 3 + 4 + 3 + 3 + 4 + 3 * 6 + 2 + 4)
+    assert ctypes.sizeof(_lib.HcuLossDesc) == 4 * 14
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_surface_matches_reference_state_dict_and_plan(name):
+    import hcunet_b200 as H
+    from hcunet_b200.engine import plan_unet
+
+    fx = load_golden(name)
+    torch.manual_seed(fx["seed"])
+    m = H.Unet_Constructor(**fx["kwargs"])
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(fx["state_dict"].keys())
+    for k, v in fx["state_dict"].items():
+        assert sd[k].shape == v.shape and sd[k].dtype == v.dtype, k
+        # same construction order => same RNG stream => same initial conv weights as the reference
+        if "conv" in k:
+            assert torch.equal(sd[k], v), k
+    m.load_state_dict(fx["state_dict"])
+    plan = plan_unet(m.model_specification, fx["xshape"])
+    dims = fx["kwargs"]["image_dimensions"]
+    assert tuple(plan.out_sz[:dims]) == tuple(fx["logits_train"].shape[2:])
+    assert m.model_specification == O.normalise_spec(fx["kwargs"])
+
+
+def test_constructor_errors_and_spelling():
+    import hcunet_b200 as H
+
+    with pytest.raises(ValueError):
+        H.Unet_Constructor(image_dimensions=4)
+    with pytest.raises(ValueError):
+        H.Unet_Constructor(feature_sizes=[8])
+    with pytest.raises(AssertionError):
+        H.Unet_Constructor(feature_sizes=[8, 12])
+    with pytest.raises(TypeError):
+        H.Unet_Constructor(image_dimmensions=3)  # README.md:17 spelling raises in the reference too
+    m = H.Unet_Constructor(**O.README_3D)
+    assert sum(p.numel() for p in m.parameters()) == 727009 and len(m.state_dict()) == 136
+
+
+def test_planner_raises_like_the_reference():
+    from hcunet_b200.engine import plan_unet
+
+    spec = O.normalise_spec(O.README_3D)
+    with pytest.raises(RuntimeError):
+        plan_unet(spec, (1, 4, 128, 128, 32))
+    with pytest.raises(RuntimeError):
+        plan_unet(spec, (1, 3, 256, 256, 32))   # channels
+    with pytest.raises(RuntimeError):
+        plan_unet(spec, (1, 4, 256, 256))       # rank
+    p = plan_unet(spec, (1, 4, 256, 256, 32))
+    assert p.out_sz == (68, 68, 27)
+    p = plan_unet(spec, (1, 4, 256, 256, 64))
+    assert p.out_sz == (68, 68, 59)
+    # geometry table of SURVEY 8a (cfg4)
+    convs = {g.name: g for g in p.steps if hasattr(g, "taps")}
+    assert convs["down_steps.0.conv1"].out_sz == (254, 254, 63)
+    assert convs["down_steps.4.conv2"].out_sz == (8, 8, 59)
+    assert convs["up_steps.3.conv2"].out_sz == (68, 68, 59)
+    assert convs["up_steps.0.conv1"].fold and convs["up_steps.0.conv1"].cin_g == 64
+    # 2D classic: 572 -> 388 in the textbook; the reference's valid convs + dead skips give 196
+    spec2 = O.normalise_spec({})
+    assert plan_unet(spec2, (16, 3, 572, 572)).out_sz[:2] == (196, 196)
+    # a skip smaller than the upsampled tensor makes torch.cat raise in the reference (unet.py:312)
+    spec3 = O.normalise_spec(dict(O.README_3D, feature_sizes=[4, 8], upsample_kernel=(12, 12, 2)))
+    with pytest.raises(RuntimeError):
+        plan_unet(spec3, (1, 4, 20, 20, 4))
+
+
+def test_no_cpu_fallback_and_shim():
+    import hcat
+    import hcunet_b200 as H
+
+    assert hcat.unet.Unet_Constructor is H.Unet_Constructor and hcat.loss.cross_entropy is H.cross_entropy
+    m = H.Unet_Constructor(**dict(O.README_3D, feature_sizes=[4, 8]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 4, 20, 20, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        H.cross_entropy(torch.zeros(1, 1, 4, 4, 2), torch.zeros(1, 1, 4, 4, 2), None)
+    # argument validation happens before the device check, like the reference's ordering (loss.py:25-36)
+    with pytest.raises(ValueError):
+        H.cross_entropy(torch.zeros(1, 1, 4, 4, 2), torch.zeros(1, 1, 4, 4, 2), None, method="nope")
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "hcunet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle|oracle/", src, flags=re.M), \
+                    f"{f} reaches into oracle/"
