@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 F32, BF16, F16 = 0, 1, 2
 
@@ -55,6 +55,10 @@ SIGNATURES = {
     "hcu_launch_count": [],
     "hcu_zero": [P, C.c_size_t, P],
     "hcu_conv_fwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
+    "hcu_conv_tc_supported": [C.POINTER(HcuConvDesc)],
+    "hcu_conv_tc_packed_bytes": [C.POINTER(HcuConvDesc)],
+    "hcu_conv_tc_pack": [C.POINTER(HcuConvDesc), P, P, P],
+    "hcu_conv_tc_fwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
     "hcu_conv_wgrad_partial": [C.POINTER(HcuConvDesc), P, P, P, P, P, I32, P],
     "hcu_weight_gather": [C.POINTER(HcuWeightMap), P, P, P],
     "hcu_weight_scatter": [C.POINTER(HcuWeightMap), P, I32, I64, F, P, I32, P, P],
@@ -75,7 +79,7 @@ SIGNATURES = {
     "hcu_pair_reduce": [C.POINTER(HcuLossDesc), I32, P, P, P, P],
     "hcu_pair_bwd": [C.POINTER(HcuLossDesc), I32, P, P, P, P, P],
 }
-_RESTYPES = {"hcu_last_error": C.c_char_p, "hcu_launch_count": C.c_longlong}
+_RESTYPES = {"hcu_last_error": C.c_char_p, "hcu_launch_count": C.c_longlong, "hcu_conv_tc_packed_bytes": C.c_longlong}
 
 _lib = None
 
@@ -138,7 +142,8 @@ def load():
     out._cdll = lib
     for name in SIGNATURES:
         raw = getattr(lib, name)
-        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count") else _wrap(name, raw))
+        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_conv_tc_supported",
+                                         "hcu_conv_tc_packed_bytes") else _wrap(name, raw))
     _lib = out
     return out
 

@@ -1,0 +1,604 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM).
+//
+// Formulation ("flat shift"): with channels-last fp16 activations [n][x][y][z][C], one x-plane is a flat
+// array of Yv*Zv pixels of C channels.  For a stride-1 convolution the output at flat position q of plane
+// ox is   out[ox][q] = sum_{tx,ty,tz} in[ox + tx*dx][q + ty*dy*Zv + tz*dz] . W[tx,ty,tz]
+// i.e. every filter tap is the SAME [pixels x C] matrix shifted by a constant number of pixels.  Positions
+// whose (y, z) wrap around the row / plane end are computed and discarded (<= 5 % waste on the big layers).
+// So the A operand of the GEMM is never expanded (no im2col, not even in shared memory): a CTA keeps a ring
+// of R input x-planes for a run of M + halo flat positions in shared memory, laid out as
+// [channel-plane of 8][pixel][8 x fp16] = the canonical no-swizzle K-major UMMA core-matrix layout, and the
+// MMA issuer just points shared-memory descriptors at (pixel offset of the tap, channel plane).  Each input
+// element is read from L2/HBM ~(1 + halo/M)(1 + 2/Lx) times instead of prod(kernel) times.
+//
+// The CTA marches along x: producer warps load plane x+KX-1 (applying the previous layer's BatchNorm scale /
+// shift + ReLU on the fly, so the normalised activation never exists in HBM) while the single MMA thread
+// issues the taps of plane x into one of two TMEM accumulator buffers and the epilogue warps drain the other
+// (bias, per-channel sum / sum-of-squares for train-mode BN, optional affine + ReLU, fp16/fp32 store).
+//
+// Roles (288 threads): warps 0-3 epilogue (thread = accumulator row / TMEM lane), warps 4-7 producers,
+// warp 8 = TMEM allocation + barrier init + weight bulk copy (cp.async.bulk) + MMA issue (lane 0).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace hcu {
+
+namespace tc {
+
+constexpr int kThreads = 288;
+constexpr int kMaxPairs = 64;   // (ty, tz, channel-plane) K16 steps per tx
+constexpr int kMaxRing = 8;
+constexpr int kSmemLimit = 227 * 1024;
+
+struct Params {
+  const __half* in;
+  const __half* wp;  // packed weights [nsplit][E][Nc][8] fp16
+  void* out;
+  const float* bias;
+  const float* in_scale;
+  const float* in_shift;
+  const float* out_scale;
+  const float* out_shift;
+  double* stats;
+  int stats_pitch;
+  int N, IX, IY, IZ, Cp, P;
+  int OX, OY, OZ;
+  int KX, KY, KZ, dx, dy, dz, px, py, pz;
+  int Yv, Zv;
+  int M, MB, RUN, PS, SLOT, R;
+  int Nc, nsplit, cout, E_tx, npairs, E;
+  int n_runs, Lx, n_xseg;
+  long long out_sn, out_sx, out_sy, out_sz, out_base;
+  int out_c_off, out_f32, in_relu, out_relu;
+  // shared memory carve-up (bytes from the 128-aligned base)
+  int off_w, off_a, off_bar, off_tab, off_stat, smem_bytes;
+  int tmem_cols;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (unsigned long long it = 0; !ok; ++it) {
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (it > (1ull << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], fp16 inputs, fp32 accumulate, M=128, K=16
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, no swizzle: rows of one 8x(16 B) core matrix are 16 B apart; SBO = next 8 rows, LBO = next 8 K
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint4 ldg_nc16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// sum over the 32 lanes of 16 per-lane values; lane l ends up with channel (l >> 1) & 15 (both lanes of a pair)
+__device__ __forceinline__ float reduce16(float* v, int lane) {
+#pragma unroll
+  for (int h = 8, off = 16; h >= 1; h >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = up ? v[i + h] : v[i];
+      const float send = up ? v[i] : v[i + h];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  // barrier map: full[R], empty[R], tfull[2], tempty[2], wbar
+  const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * p.R, bar_tfull = bar_empty + 8 * p.R,
+                 bar_tempty = bar_tfull + 16, bar_w = bar_tempty + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (2 * p.R + 5));
+  int2* tab = reinterpret_cast<int2*>(smem + p.off_tab);      // per pair: (A byte offset, LBO bytes)
+  float* sstat = reinterpret_cast<float*>(smem + p.off_stat);  // [2][Nc]
+  const uint32_t a_base = smem_u32(smem + p.off_a), w_base = smem_u32(smem + p.off_w);
+
+  // ---- work item ---------------------------------------------------------------------------------
+  int item = blockIdx.x;
+  const int ns = item % p.nsplit; item /= p.nsplit;
+  const int run = item % p.n_runs; item /= p.n_runs;
+  const int xs = item % p.n_xseg;
+  const int n = item / p.n_xseg;
+  const int x0 = xs * p.Lx;
+  const int nout = min(p.Lx, p.OX - x0);
+  const int nplanes = nout + (p.KX - 1) * p.dx;
+  const int q0 = run * p.M;
+
+  // ---- one-time setup --------------------------------------------------------------------------------
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < p.R; ++i) {
+        mbar_init(bar_full + 8 * i, 4);   // one arrive per producer warp
+        mbar_init(bar_empty + 8 * i, 1);  // tcgen05.commit
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(bar_tfull + 8 * i, 1);   // tcgen05.commit
+        mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
+      }
+      mbar_init(bar_w, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+    // per-pair table: K16 step e -> entries 2e, 2e+1 of the (ty, tz, plane) list of one tx group
+    const int per_tx = p.KY * p.KZ * p.P;
+    for (int e = lane; e < p.npairs; e += 32) {
+      const int e0 = 2 * e, e1 = 2 * e + 1;
+      const int t0 = e0 / p.P, c0 = e0 % p.P;
+      const int off0 = ((t0 / p.KZ) * p.dy * p.Zv + (t0 % p.KZ) * p.dz) * 16 + c0 * p.PS;
+      int off1 = off0;  // odd tail: second K8 half re-reads the same rows against zero weights
+      if (e1 < per_tx) {
+        const int t1 = e1 / p.P, c1 = e1 % p.P;
+        off1 = ((t1 / p.KZ) * p.dy * p.Zv + (t1 % p.KZ) * p.dz) * 16 + c1 * p.PS;
+      }
+      tab[e] = make_int2(off0, off1 - off0);
+    }
+    if (lane == 0) {
+      const uint32_t wbytes = (uint32_t)p.E * p.Nc * 16u;
+      mbar_expect_tx(bar_w, wbytes);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) + (size_t)ns * wbytes;
+      for (uint32_t o = 0; o < wbytes; o += 32768u) bulk_g2s(w_base + o, src + o, min(32768u, wbytes - o), bar_w);
+    }
+  }
+  for (int i = threadIdx.x; i < 2 * p.Nc; i += kThreads) sstat[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // =========================================== PRODUCERS ===========================================
+    const int ptid = threadIdx.x - 128;
+    const int plane = ptid % p.P;
+    const int pix0 = ptid / p.P, pstep = 128 / p.P;
+    const int nchunk = (p.RUN - pix0 + pstep - 1) / pstep;  // pixels this thread copies per x-plane
+    float sc[8], sh[8];
+    const bool xf = p.in_scale != nullptr;
+    if (xf) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = p.in_scale[plane * 8 + j];
+        sh[j] = p.in_shift[plane * 8 + j];
+      }
+    }
+    // (yv, zv) of this thread's first pixel
+    const int qf = q0 + pix0;
+    const int yv0 = qf / p.Zv, zv0 = qf - yv0 * p.Zv;
+    const int ystep = pstep / p.Zv, zstep = pstep - ystep * p.Zv;
+    const __half* in_n = p.in + (size_t)n * p.IX * p.IY * p.IZ * p.Cp + plane * 8;
+    for (int j = 0; j < nplanes; ++j) {
+      const int slot = j % p.R;
+      mbar_wait(bar_empty + 8 * slot, ((j / p.R) & 1) ^ 1);
+      const int xm = x0 + j - p.px;  // memory x of this virtual plane
+      const bool xok = xm >= 0 && xm < p.IX;
+      const __half* in_x = in_n + (size_t)(xok ? xm : 0) * p.IY * p.IZ * p.Cp;
+      unsigned char* dst = smem + p.off_a + slot * p.SLOT + plane * p.PS + pix0 * 16;
+      int yv = yv0, zv = zv0;
+      for (int c = 0; c < nchunk; c += 4) {
+        uint4 v[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ym = yv - p.py, zm = zv - p.pz;
+          ok[u] = xok && (c + u < nchunk) && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
+          v[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok[u]) v[u] = ldg_nc16(in_x + ((size_t)ym * p.IZ + zm) * p.Cp);
+          zv += zstep; yv += ystep;
+          if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (c + u >= nchunk) break;
+          if (xf && ok[u]) {
+            __half2* h = reinterpret_cast<__half2*>(&v[u]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float2 f = __half22float2(h[k]);
+              f.x = fmaf(f.x, sc[2 * k], sh[2 * k]);
+              f.y = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
+              if (p.in_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+              h[k] = __floats2half2_rn(f.x, f.y);
+            }
+          }
+          *reinterpret_cast<uint4*>(dst + (size_t)(c + u) * pstep * 16) = v[u];
+        }
+      }
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_full + 8 * slot);
+    }
+  } else if (warp == 8) {
+    // =========================================== MMA ISSUER ==========================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Nc >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
+      mbar_wait(bar_w, 0);
+      int next_wait = 0;
+      for (int i = 0; i < nout; ++i) {
+        const int last = i + (p.KX - 1) * p.dx;
+        for (; next_wait <= last; ++next_wait) mbar_wait(bar_full + 8 * (next_wait % p.R), (next_wait / p.R) & 1);
+        const int buf = i & 1;
+        mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int mb = 0; mb < p.MB; ++mb) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.MB + mb) * p.Nc);
+          uint32_t accum = 0;
+          for (int tx = 0; tx < p.KX; ++tx) {
+            const uint32_t a_slot = a_base + (uint32_t)(((i + tx * p.dx) % p.R) * p.SLOT + mb * 128 * 16);
+            const uint32_t w_tx = w_base + (uint32_t)(tx * p.E_tx) * (uint32_t)p.Nc * 16u;
+            for (int e = 0; e < p.npairs; ++e) {
+              const int2 t = tab[e];
+              const uint64_t ad = smem_desc(a_slot + (uint32_t)t.x, (uint32_t)t.y, 128u);
+              const uint64_t bd = smem_desc(w_tx + (uint32_t)(2 * e) * (uint32_t)p.Nc * 16u, (uint32_t)p.Nc * 16u, 128u);
+              umma_f16(d_tmem, ad, bd, idesc, accum);
+              accum = 1;
+            }
+          }
+        }
+        umma_commit(bar_empty + 8 * (i % p.R));  // plane i is not needed by later outputs
+        umma_commit(bar_tfull + 8 * buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================================== EPILOGUE ============================================
+    const int row = threadIdx.x;  // accumulator row within an M-block == TMEM lane
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const bool do_stats = p.stats != nullptr;
+    const bool affine = p.out_scale != nullptr;
+    for (int i = 0; i < nout; ++i) {
+      const int buf = i & 1;
+      mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
+      tc_fence_after();
+      const int ox = x0 + i;
+      for (int mb = 0; mb < p.MB; ++mb) {
+        const int q = q0 + mb * 128 + row;
+        const int oy = q / p.Zv, oz = q - oy * p.Zv;
+        const bool valid = oy < p.OY && oz < p.OZ;
+        const long long obase = p.out_base + n * p.out_sn + ox * p.out_sx + oy * p.out_sy + oz * p.out_sz + p.out_c_off;
+        for (int cc = 0; cc < p.Nc; cc += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + lane_base + (uint32_t)((buf * p.MB + mb) * p.Nc + cc), v);
+          const int ch0 = ns * p.Nc + cc;  // first output channel of this chunk
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (ch0 + j < p.cout) v[j] += p.bias[ch0 + j];
+          }
+          if (do_stats) {
+            float s1[16], s2[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              s1[j] = valid ? v[j] : 0.f;
+              s2[j] = s1[j] * s1[j];
+            }
+            const float r1 = reduce16(s1, lane);
+            const float r2 = reduce16(s2, lane);
+            if ((lane & 1) == 0) {
+              atomicAdd(&sstat[cc + (lane >> 1)], r1);
+              atomicAdd(&sstat[p.Nc + cc + (lane >> 1)], r2);
+            }
+          }
+          if (valid) {
+            if (affine) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (ch0 + j < p.cout) v[j] = fmaf(v[j], p.out_scale[ch0 + j], p.out_shift[ch0 + j]);
+            }
+            if (p.out_relu) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            const int nv = min(16, p.cout - ch0);
+            if (p.out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + obase + ch0;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (j < nv) o[j] = v[j];
+            } else {
+              __half* o = reinterpret_cast<__half*>(p.out) + obase + ch0;
+              if (nv >= 8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                __half2 h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+                *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(&h[0]);
+                if (nv == 16) {
+                  *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<uint4*>(&h[4]);
+                } else {
+#pragma unroll
+                  for (int j = 8; j < 16; ++j)
+                    if (j < nv) o[j] = __float2half_rn(v[j]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (j < nv) o[j] = __float2half_rn(v[j]);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+    }
+    if (do_stats) {
+      named_bar_sync(1, 128);
+      for (int c = row; c < p.Nc; c += 128) {
+        const int ch = ns * p.Nc + c;
+        if (ch < p.cout) {
+          atomicAdd(&p.stats[p.out_c_off + ch], (double)sstat[c]);
+          atomicAdd(&p.stats[p.stats_pitch + p.out_c_off + ch], (double)sstat[p.Nc + c]);
+        }
+      }
+    }
+  }
+
+  // ---- teardown --------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// weights: fp32 [taps][cin][cout] (hcu_weight_gather layout, one group) -> fp16 [nsplit][E][Nc][8]
+__global__ void pack_tc_kernel(const float* __restrict__ w, __half* __restrict__ out, int KX, int KYZ, int P, int E_tx,
+                               int Nc, int nsplit, int cin, int cout) {
+  const long long total = (long long)nsplit * KX * E_tx * Nc * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);
+    long long r = i >> 3;
+    const int nn = (int)(r % Nc); r /= Nc;
+    const int e = (int)(r % E_tx); r /= E_tx;
+    const int tx = (int)(r % KX);
+    const int ns = (int)(r / KX);
+    float v = 0.f;
+    if (e < KYZ * P) {
+      const int t = e / P, pl = e % P;
+      const int ci = pl * 8 + j, co = ns * Nc + nn;
+      if (ci < cin && co < cout) v = w[((long long)(tx * KYZ + t) * cin + ci) * cout + co];
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side configuration
+// ---------------------------------------------------------------------------------------------------
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// returns 0 and fills p (geometry part) when the TC kernel takes this descriptor, else a reason string
+static const char* configure(const HcuConvDesc* d, Params& p) {
+  if (d->dtype_in != HCU_F16) return "input must be fp16";
+  if (d->dtype_out != HCU_F16 && d->dtype_out != HCU_F32) return "output must be fp16 or fp32";
+  if (d->groups != 1) return "groups != 1";
+  if (d->in_cpitch % 8 != 0 || d->in_c_off != 0) return "input channel pitch must be a multiple of 8, offset 0";
+  const int P = d->in_cpitch / 8;
+  if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16) return "input channel pitch must be 8..128, power of two";
+  if (d->cin > d->in_cpitch) return "cin > pitch";
+  for (int i = 0; i < 3; ++i)
+    if (d->istep[i] != 1) return "strided gather";
+  if (d->cout < 2 && d->dtype_out == HCU_F16) return "single output channel";
+  p.N = d->batch; p.IX = d->in_size[0]; p.IY = d->in_size[1]; p.IZ = d->in_size[2];
+  p.Cp = d->in_cpitch; p.P = P;
+  p.OX = d->out_size[0]; p.OY = d->out_size[1]; p.OZ = d->out_size[2];
+  p.KX = d->taps[0]; p.KY = d->taps[1]; p.KZ = d->taps[2];
+  p.dx = d->dil[0]; p.dy = d->dil[1]; p.dz = d->dil[2];
+  p.px = d->pad[0]; p.py = d->pad[1]; p.pz = d->pad[2];
+  p.Yv = p.OY + (p.KY - 1) * p.dy;
+  p.Zv = p.OZ + (p.KZ - 1) * p.dz;
+  const int span = (p.KX - 1) * p.dx + 1;
+  if (span > kMaxRing) return "x extent of the filter too large";
+  const int per_tx = p.KY * p.KZ * P;
+  p.E_tx = round_up(per_tx, 2);
+  p.npairs = p.E_tx / 2;
+  if (p.npairs > kMaxPairs) return "too many taps per x-plane";
+  p.E = p.KX * p.E_tx;
+  p.cout = d->cout;
+  const int npad = round_up(d->cout, 16);
+  const int halo = (p.KY - 1) * p.dy * p.Zv + (p.KZ - 1) * p.dz;
+  const int plane_q = p.Yv * p.Zv;
+  // candidates: big M first; Nc as large as fits
+  const int m_cands[4] = {512, 384, 256, 128};
+  for (int pass = 0; pass < 2; ++pass) {          // pass 0: aim for 2 CTAs / SM, pass 1: whatever fits
+    const int budget = pass == 0 ? 110 * 1024 : kSmemLimit;
+    for (int mi = 0; mi < 4; ++mi) {
+      const int M = m_cands[mi];
+      if (M > 128 && M - 128 >= plane_q) continue;  // do not use a longer run than the plane needs
+      const int MB = M / 128;
+      int run = M + halo;
+      int ps = run * 16;
+      if (P > 1) {  // spread the channel planes over the banks: PS = g (mod 2g), g = max(16, 128 / P)
+        const int g = P >= 8 ? 16 : 128 / P;
+        ps = round_up(ps, 2 * g) + g;
+      }
+      const int slot = ps * P;
+      for (int nc = npad > 128 ? 128 : npad; nc >= 16; nc -= 16) {
+        if (npad % nc != 0) continue;
+        if (2 * MB * nc > 512) continue;
+        const int wbytes = p.E * nc * 16;
+        for (int R = std::min(span + 1, kMaxRing); R >= span; --R) {
+          const int off_w = 0;
+          const int off_a = round_up(wbytes, 128);
+          const int off_bar = off_a + R * slot;
+          const int off_tab = round_up(off_bar + 8 * (2 * R + 5) + 8, 16);
+          const int off_stat = off_tab + kMaxPairs * 8;
+          const int total = off_stat + 2 * nc * 4 + 128;
+          if (total > budget) continue;
+          p.M = M; p.MB = MB; p.RUN = run; p.PS = ps; p.SLOT = slot; p.R = R;
+          p.Nc = nc; p.nsplit = npad / nc;
+          p.off_w = off_w; p.off_a = off_a; p.off_bar = off_bar; p.off_tab = off_tab; p.off_stat = off_stat;
+          p.smem_bytes = total;
+          int cols = 2 * MB * nc, t = 32;
+          while (t < cols) t <<= 1;
+          p.tmem_cols = t;
+          p.n_runs = (plane_q + M - 1) / M;
+          return nullptr;
+        }
+      }
+    }
+  }
+  return "does not fit in shared memory";
+}
+
+}  // namespace tc
+}  // namespace hcu
+
+using namespace hcu;
+
+extern "C" int hcu_conv_tc_supported(const HcuConvDesc* d) {
+  if (d == nullptr) return 0;
+  tc::Params p;
+  return tc::configure(d, p) == nullptr ? 1 : 0;
+}
+
+extern "C" long long hcu_conv_tc_packed_bytes(const HcuConvDesc* d) {
+  tc::Params p;
+  if (d == nullptr || tc::configure(d, p) != nullptr) return -1;
+  return (long long)p.nsplit * p.E * p.Nc * 16;
+}
+
+extern "C" int hcu_conv_tc_pack(const HcuConvDesc* d, const float* w, void* packed, void* stream) {
+  HCU_CHECK_ARG(d && w && packed, "conv_tc_pack: null pointer");
+  tc::Params p;
+  const char* why = tc::configure(d, p);
+  HCU_CHECK_ARG(why == nullptr, "conv_tc_pack: unsupported descriptor (%s)", why);
+  const long long total = (long long)p.nsplit * p.E * p.Nc * 8;
+  int grid = (int)std::min<long long>((total + 255) / 256, 4096);
+  tc::pack_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed, p.KX, p.KY * p.KZ, p.P, p.E_tx, p.Nc,
+                                                             p.nsplit, d->cin, d->cout);
+  HCU_CHECK_LAUNCH("pack_tc");
+  return 0;
+}
+
+extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
+                               const float* in_scale, const float* in_shift, const float* out_scale,
+                               const float* out_shift, void* out, double* stats, void* stream) {
+  HCU_CHECK_ARG(d && in && packed && out, "conv_tc_fwd: null pointer");
+  HCU_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "conv_tc_fwd: in_scale/in_shift must come together");
+  HCU_CHECK_ARG((out_scale == nullptr) == (out_shift == nullptr), "conv_tc_fwd: out_scale/out_shift must come together");
+  tc::Params p;
+  const char* why = tc::configure(d, p);
+  if (why != nullptr) {
+    set_error("conv_tc_fwd: unsupported descriptor (%s)", why);
+    return HCU_ERR_UNSUPPORTED;
+  }
+  for (int i = 0; i < 3; ++i)
+    HCU_CHECK_ARG((long long)(d->out_size[i] - 1) * d->ostep[i] + d->ooff[i] < d->out_tsize[i],
+                  "conv_tc_fwd: output grid exceeds output tensor in dim %d", i);
+  HCU_CHECK_ARG(d->out_c_off >= 0 && d->out_c_off + d->cout <= d->out_cpitch, "conv_tc_fwd: output channel slice");
+  p.in = (const __half*)in; p.wp = (const __half*)packed; p.out = out;
+  p.bias = bias; p.in_scale = in_scale; p.in_shift = in_shift; p.out_scale = out_scale; p.out_shift = out_shift;
+  p.stats = stats; p.stats_pitch = d->out_cpitch;
+  const long long tz = d->out_cpitch, ty = tz * d->out_tsize[2], tx = ty * d->out_tsize[1], tn = tx * d->out_tsize[0];
+  p.out_sn = tn; p.out_sx = tx * d->ostep[0]; p.out_sy = ty * d->ostep[1]; p.out_sz = tz * d->ostep[2];
+  p.out_base = tx * d->ooff[0] + ty * d->ooff[1] + tz * d->ooff[2];
+  p.out_c_off = d->out_c_off; p.out_f32 = d->dtype_out == HCU_F32; p.in_relu = d->in_relu; p.out_relu = d->out_relu;
+  // x segmentation: enough CTAs to fill the machine ~2x, segments no shorter than 8 planes when possible
+  const long long base_items = (long long)p.N * p.n_runs * p.nsplit;
+  const int target = 2 * num_sms();
+  int nseg = (int)((target + base_items - 1) / base_items);
+  nseg = std::max(1, std::min(nseg, (p.OX + 7) / 8));
+  p.Lx = (p.OX + nseg - 1) / nseg;
+  p.n_xseg = (p.OX + p.Lx - 1) / p.Lx;
+  const long long grid = base_items * p.n_xseg;
+  HCU_CHECK_ARG(grid <= 0x7fffffffLL, "conv_tc_fwd: grid too large");
+  static int smem_attr = 0;
+  if (smem_attr < p.smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemLimit);
+    if (e != cudaSuccess) {
+      set_error("conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return HCU_ERR_CUDA;
+    }
+    smem_attr = tc::kSmemLimit;
+  }
+  tc::conv_tc_kernel<<<(unsigned)grid, tc::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(p);
+  HCU_CHECK_LAUNCH("conv_tc");
+  return 0;
+}

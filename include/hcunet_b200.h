@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 4
+#define HCU_ABI_VERSION 5
 
 typedef enum HcuStatus {
   HCU_OK = 0,
@@ -96,6 +96,18 @@ typedef struct HcuConvDesc {
 int hcu_conv_fwd(const HcuConvDesc* d, const void* in, const float* W, const float* bias,
                  const float* in_scale, const float* in_shift, const float* out_scale,
                  const float* out_shift, void* out, double* stats, void* stream);
+
+/* Tensor-core flavour of hcu_conv_fwd (tcgen05.mma, TMEM accumulators; conv_tc.cu): fp16 activations, groups == 1,
+ * istep == 1, input channel pitch in {8,16,32,64,128}.  hcu_conv_tc_supported() says whether a descriptor is taken
+ * (else use hcu_conv_fwd).  Weights: hcu_weight_gather's fp32 [taps][cin][cout] re-packed by hcu_conv_tc_pack into
+ * hcu_conv_tc_packed_bytes(d) bytes of fp16 UMMA core matrices.  Same semantics as hcu_conv_fwd otherwise.
+ * Replaces: nn.Conv3d/Conv2d.forward (unet.py:246-257), conv backward-data, ConvTranspose3d phases (unet.py:294). */
+int hcu_conv_tc_supported(const HcuConvDesc* d);
+long long hcu_conv_tc_packed_bytes(const HcuConvDesc* d);
+int hcu_conv_tc_pack(const HcuConvDesc* d, const float* w, void* packed, void* stream);
+int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
+                    const float* in_scale, const float* in_shift, const float* out_scale,
+                    const float* out_shift, void* out, double* stats, void* stream);
 
 /* Weight gradient of the same gather-convolution:
  *   R[g][t][ca][cb] = sum_{n,o} A(a[n, o*istep - pad + t*dil, a_c_off + g*a_c_gstep + ca]) * b[n, o, b_c_off + g*cb_n + cb]

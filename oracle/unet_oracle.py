@@ -76,12 +76,48 @@ def _bn(x, sd, prefix, training, new_buffers, momentum=0.1, eps=1e-5):
     return F.batch_norm(x, rm, rv, w, b, False, momentum, eps)
 
 
-def _block(x, sd, prefix, spec, training, new_buffers, acts):
+def tf32_round(t: torch.Tensor) -> torch.Tensor:
+    """Round fp32 to TF32 (10-bit mantissa, round-half-up in magnitude) -- what cuDNN's default
+    ``allow_tf32=True`` path does to conv inputs on the GPU.  Used only to CALIBRATE
+    the tolerance of the mixed-precision parity tests: it answers "how far from fp32 is the reference's own
+    default GPU arithmetic on this case"."""
+    i = t.detach().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _TF32Conv(torch.autograd.Function):
+    """conv / convT whose forward AND backward round their tensor-core inputs to TF32, like cuDNN with
+    ``allow_tf32=True`` (fwd: x, w; dgrad: dy, w; wgrad: x, dy).  Calibration only (see tf32_round)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, fn, kw):
+        ctx.save_for_backward(x, w)
+        ctx.fn, ctx.kw = fn, kw
+        return fn(tf32_round(x), tf32_round(w), b, **kw)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        with torch.enable_grad():
+            xx, ww = tf32_round(x).requires_grad_(True), tf32_round(w).requires_grad_(True)
+            dx, dw = torch.autograd.grad(ctx.fn(xx, ww, None, **ctx.kw), (xx, ww), tf32_round(dy))
+        return dx, dw, dy.sum(dim=[0] + list(range(2, dy.dim()))), None, None
+
+
+def _tconv(fn, tf32, x, w, b, **kw):
+    if not tf32:
+        return fn(x, w, b, **kw)
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+        return _TF32Conv.apply(x, w, b, fn, kw)
+    return fn(tf32_round(x), tf32_round(w), b, **kw)
+
+
+def _block(x, sd, prefix, spec, training, new_buffers, acts, tf32=False):
     """`unet.py:263-266` / `unet.py:313-314`: relu(bn1(conv1(x))); relu(bn2(conv2(x))), padding 0."""
     conv = F.conv2d if spec["image_dimensions"] == 2 else F.conv3d
     for i in ("1", "2"):
-        x = conv(x, sd[f"{prefix}.conv{i}.weight"], sd[f"{prefix}.conv{i}.bias"], stride=1, padding=0,
-                 dilation=spec["dilation"][f"conv{i}"], groups=spec["groups"][f"conv{i}"])
+        x = _tconv(conv, tf32, x, sd[f"{prefix}.conv{i}.weight"], sd[f"{prefix}.conv{i}.bias"], stride=1, padding=0,
+                   dilation=spec["dilation"][f"conv{i}"], groups=spec["groups"][f"conv{i}"])
         if acts is not None:
             acts[f"{prefix}.conv{i}"] = x
         x = F.relu(_bn(x, sd, f"{prefix}.batch{i}", training, new_buffers))
@@ -99,11 +135,12 @@ def _crop(x, y):
 
 
 def unet_forward(sd: Dict[str, torch.Tensor], spec: dict, x: torch.Tensor, training: bool = False,
-                 acts: Optional[dict] = None) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+                 acts: Optional[dict] = None, tf32: bool = False) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
     """Restates ``Unet_Constructor.forward`` (`unet.py:125-143`) on a reference-layout state_dict.
 
     Returns (logits, new_buffers); ``new_buffers`` holds the BN running stats a train-mode forward
     would have written in place.  ``acts`` (optional dict) collects every intermediate tensor.
+    ``tf32=True`` rounds every conv / convT tensor-core input (forward and backward) to TF32 first.
     """
     spec = normalise_spec(spec)
     dims = spec["image_dimensions"]
@@ -116,22 +153,22 @@ def unet_forward(sd: Dict[str, torch.Tensor], spec: dict, x: torch.Tensor, train
     new_buffers: Dict[str, torch.Tensor] = {}
     outputs: List[torch.Tensor] = []
     for i in range(nlev - 1):  # unet.py:128-131
-        x = _block(x, sd, f"down_steps.{i}", spec, training, new_buffers, acts)
+        x = _block(x, sd, f"down_steps.{i}", spec, training, new_buffers, acts, tf32)
         outputs.append(x)
         x = pool(x, spec["max_pool_kernel"])  # kernel == stride, floor mode, no padding (unet.py:123)
         if acts is not None:
             acts[f"down_steps.{i}.pool"] = x
-    x = _block(x, sd, f"down_steps.{nlev - 1}", spec, training, new_buffers, acts)  # unet.py:133
+    x = _block(x, sd, f"down_steps.{nlev - 1}", spec, training, new_buffers, acts, tf32)  # unet.py:133
     for i in range(nlev - 1):  # unet.py:135-136 -> Up.forward unet.py:309-315
         skip = outputs.pop()
-        x = convT(x, sd[f"up_steps.{i}.up_conv.weight"], sd[f"up_steps.{i}.up_conv.bias"],
-                  stride=spec["upsample_stride"], padding=0)  # unet.py:294-298: no groups / dilation
+        x = _tconv(convT, tf32, x, sd[f"up_steps.{i}.up_conv.weight"], sd[f"up_steps.{i}.up_conv.bias"],
+                   stride=spec["upsample_stride"], padding=0)  # unet.py:294-298: no groups / dilation
         if acts is not None:
             acts[f"up_steps.{i}.up_conv"] = x
         y = _crop(x, skip)  # unet.py:311 -- crops the UPSAMPLED tensor; the skip is only a size donor
         x = torch.cat((x, y), dim=1)  # unet.py:312 -- raises if skip is smaller than x anywhere
-        x = _block(x, sd, f"up_steps.{i}", spec, training, new_buffers, acts)
-    x = conv(x, sd["out_conv.weight"], sd["out_conv.bias"])  # unet.py:120,138
+        x = _block(x, sd, f"up_steps.{i}", spec, training, new_buffers, acts, tf32)
+    x = _tconv(conv, tf32, x, sd["out_conv.weight"], sd["out_conv.bias"])  # unet.py:120,138
     return x, new_buffers
 
 
@@ -236,7 +273,7 @@ def golden_inputs(kwargs: dict, xshape, seed: int):
     return x, mask, pwl
 
 
-def train_step_grads(sd: Dict[str, torch.Tensor], spec: dict, x, mask, pwl, method="pixel"):
+def train_step_grads(sd: Dict[str, torch.Tensor], spec: dict, x, mask, pwl, method="pixel", tf32=False):
     """One reference-semantics training forward+backward on CPU.  Returns
     (loss, logits, {param: grad}, new_buffers)."""
     leaf = {}
@@ -245,7 +282,7 @@ def train_step_grads(sd: Dict[str, torch.Tensor], spec: dict, x, mask, pwl, meth
             leaf[k] = v.detach().clone().requires_grad_(True)
         else:
             leaf[k] = v.detach().clone()
-    logits, new_buffers = unet_forward(leaf, spec, x, training=True)
+    logits, new_buffers = unet_forward(leaf, spec, x, training=True, tf32=tf32)
     loss = cross_entropy(logits, mask, pwl, method)
     loss.backward()
     grads = {k: v.grad for k, v in leaf.items() if v.requires_grad}

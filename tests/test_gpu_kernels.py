@@ -1,0 +1,153 @@
+"""Per-kernel parity (GPU): each hand-written kernel on its own, through the C ABI, against the fp32 oracle
+op (torch CPU) on the same inputs.  This is where the mixed path's 2e-3 gate lives: one layer, same inputs,
+rel-L2 <= 2e-3 (fp16 operands, fp32 accumulate; measured ~3e-4)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def P(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def to_cl(x, cpitch=None, dtype=torch.float16):
+    """[N,C,X,Y,Z] -> channels-last [N,X,Y,Z,cpitch] (zero padded channels)."""
+    n, c = x.shape[:2]
+    cp = cpitch or c
+    out = torch.zeros((n,) + tuple(x.shape[2:]) + (cp,), dtype=dtype)
+    out[..., :c] = x.permute(0, 2, 3, 4, 1).to(dtype)
+    return out.cuda().contiguous()
+
+
+def from_cl(y):
+    return y.permute(0, 4, 1, 2, 3).float().cpu()
+
+
+def run_tc(x, w, *, bias=None, dil=(1, 1, 1), pad=(0, 0, 0), cpitch=None, in_affine=None, in_relu=False,
+           out_affine=None, out_relu=False, want_stats=False, out_f32=False, use_simt=False):
+    """x [N,Cin,X,Y,Z] fp32 (fp16-representable), w [Cout,Cin,kx,ky,kz] -> (y [N,Cout,...], stats or None)."""
+    from hcunet_b200 import _lib
+    from hcunet_b200.engine import conv_desc
+
+    lib = _lib.load()
+    n, cin = x.shape[:2]
+    cout = w.shape[0]
+    taps = tuple(w.shape[2:])
+    isz = tuple(x.shape[2:])
+    osz = tuple(isz[i] + 2 * pad[i] - (taps[i] - 1) * dil[i] for i in range(3))
+    cp = cpitch or cin
+    xin = to_cl(x, cp)
+    odt = torch.float32 if out_f32 else torch.float16
+    y = torch.full((n,) + osz + (cout,), float("nan"), dtype=odt, device="cuda")
+    d = conv_desc(_lib.F16, _lib.F32 if out_f32 else _lib.F16, n, isz, cp, 0, cin, cin, osz, osz, cout, 0, cout, 1, taps,
+                  dil, pad=pad, in_relu=int(in_relu), out_relu=int(out_relu))
+    wg = w.permute(2, 3, 4, 1, 0).contiguous().float().cuda()  # [taps][cin][cout]
+    stats = torch.zeros((2, cout), dtype=torch.float64, device="cuda") if want_stats else None
+    isc = ish = osc = osh = None
+    if in_affine is not None:
+        isc = torch.zeros(cp, device="cuda"); ish = torch.zeros(cp, device="cuda")
+        isc[:cin], ish[:cin] = in_affine[0].cuda(), in_affine[1].cuda()
+    if out_affine is not None:
+        osc, osh = out_affine[0].cuda().contiguous(), out_affine[1].cuda().contiguous()
+    b = bias.cuda() if bias is not None else None
+    if use_simt:
+        _lib.check(lib.hcu_conv_fwd(C.byref(d), P(xin), P(wg), P(b), P(isc), P(ish), P(osc), P(osh), P(y), P(stats),
+                                    stream()), "conv_fwd")
+    else:
+        assert lib.hcu_conv_tc_supported(C.byref(d)) == 1
+        nb = lib.hcu_conv_tc_packed_bytes(C.byref(d))
+        packed = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        _lib.check(lib.hcu_conv_tc_pack(C.byref(d), P(wg), P(packed), stream()), "pack")
+        _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), P(xin), P(packed), P(b), P(isc), P(ish), P(osc), P(osh), P(y),
+                                       P(stats), stream()), "conv_tc_fwd")
+    torch.cuda.synchronize()
+    return from_cl(y), (stats.cpu() if stats is not None else None)
+
+
+def h16(t):
+    return t.half().float()
+
+
+CASES = [
+    # (N, Cin, Cout, in size, kernel, dilation, cpitch)
+    (1, 8, 8, (10, 12, 9), (3, 3, 2), (1, 1, 1), None),
+    (2, 8, 8, (9, 11, 7), (3, 3, 1), (1, 1, 1), None),
+    (1, 4, 8, (12, 10, 6), (3, 3, 2), (1, 1, 1), 8),       # first layer: 4 channels in a pitch of 8
+    (1, 16, 16, (8, 20, 31), (3, 3, 1), (1, 1, 1), None),
+    (2, 16, 32, (7, 9, 6), (3, 3, 2), (1, 1, 1), None),
+    (1, 32, 32, (6, 30, 29), (3, 3, 1), (1, 1, 1), None),
+    (1, 64, 64, (5, 12, 28), (3, 3, 2), (1, 1, 1), None),
+    (1, 64, 128, (5, 12, 10), (3, 3, 2), (1, 1, 1), None),
+    (1, 128, 128, (4, 10, 9), (3, 3, 1), (1, 1, 1), None),
+    (1, 8, 16, (14, 13, 6), (3, 3, 2), (2, 2, 1), None),   # dilation (g3d_dil)
+    (1, 16, 8, (40, 70, 31), (3, 3, 2), (1, 1, 1), None),  # several runs, several x segments
+    (1, 8, 24, (6, 9, 8), (1, 1, 1), (1, 1, 1), None),     # 1x1x1, cout not a multiple of 16
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_conv_tc_matches_fp32_conv(case):
+    n, cin, cout, isz, k, dil, cp = case
+    g = torch.Generator().manual_seed(hash(case) % 10000)
+    x = h16(torch.randn((n, cin) + isz, generator=g))
+    w = h16(torch.randn((cout, cin) + k, generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    ref = F.conv3d(x, w, b, dilation=dil)
+    y, stats = run_tc(x, w, bias=b, dil=dil, cpitch=cp, want_stats=True)
+    assert not torch.isnan(y).any(), "some outputs were never written"
+    assert rel_l2(y, ref) <= 1e-3, rel_l2(y, ref)   # fp16 output rounding only
+    npix = ref.numel() / cout
+    mean = stats[0] / npix
+    var = stats[1] / npix - mean * mean
+    assert torch.allclose(mean.float(), ref.mean(dim=(0, 2, 3, 4)), atol=2e-4, rtol=1e-4)
+    assert torch.allclose(var.float(), ref.var(dim=(0, 2, 3, 4), unbiased=False), atol=2e-4, rtol=1e-3)
+    # fp32 output: accumulation-order differences only
+    y32, _ = run_tc(x, w, bias=b, dil=dil, cpitch=cp, out_f32=True)
+    assert rel_l2(y32, ref) <= 2e-6, rel_l2(y32, ref)
+
+
+def test_conv_tc_fused_input_bn_relu_and_output_affine():
+    g = torch.Generator().manual_seed(3)
+    x = h16(torch.randn((2, 16, 9, 10, 7), generator=g))
+    w = h16(torch.randn((32, 16, 3, 3, 2), generator=g) / 17.0)
+    sc, sh = torch.rand(16, generator=g) + 0.5, torch.randn(16, generator=g) * 0.3
+    a = h16(F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)))  # the producer rounds A to fp16
+    osc, osh = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g)
+    ref = F.relu(F.conv3d(a, w) * osc.view(1, -1, 1, 1, 1) + osh.view(1, -1, 1, 1, 1))
+    y, _ = run_tc(x, w, in_affine=(sc, sh), in_relu=True, out_affine=(osc, osh), out_relu=True)
+    assert rel_l2(y, ref) <= 1e-3, rel_l2(y, ref)
+
+
+def test_conv_tc_zero_padding_is_dgrad():
+    """pad = (k-1)*dil with a flipped kernel is the data gradient of a valid convolution."""
+    g = torch.Generator().manual_seed(4)
+    dy = h16(torch.randn((1, 16, 7, 9, 6), generator=g))
+    w = h16(torch.randn((16, 8, 3, 3, 2), generator=g) / 12.0)  # forward weight [Cout=16, Cin=8]
+    ref = torch.nn.grad.conv3d_input((1, 8, 9, 11, 7), w, dy)
+    wd = w.flip(2, 3, 4).permute(1, 0, 2, 3, 4).contiguous()   # [Cin, Cout] flipped
+    y, _ = run_tc(dy, wd, pad=(2, 2, 1))
+    assert tuple(y.shape) == (1, 8, 9, 11, 7)
+    assert rel_l2(y, ref) <= 1e-3, rel_l2(y, ref)
+
+
+def test_conv_tc_agrees_with_simt_kernel():
+    g = torch.Generator().manual_seed(5)
+    x = h16(torch.randn((1, 32, 6, 14, 12), generator=g))
+    w = h16(torch.randn((32, 32, 3, 3, 1), generator=g) / 17.0)
+    a, sa = run_tc(x, w, want_stats=True)
+    b, sb = run_tc(x, w, want_stats=True, use_simt=True)
+    assert rel_l2(a, b) <= 6e-4
+    assert torch.allclose(sa, sb, rtol=1e-4, atol=1e-3)
