@@ -302,6 +302,16 @@ def main_ours(args):
             for i in range(min(args.steps, 5)):
                 step(*resident[i % NBUF])
         roof = prof.roofline(peaks, t_step * min(args.steps, 5))
+        if os.environ.get("HCUNET_PROFILE_OUT"):
+            nst = min(args.steps, 5)
+            rows = [dict(kernel=k[0], layer=k[1], ms=v["ms"] / nst, calls=v["calls"] / nst, bytes=v["bytes"] / nst,
+                         flops=v["flops"] / nst) for k, v in prof.by_layer().items()]
+            rows.sort(key=lambda r: -r["ms"])
+            with open(os.environ["HCUNET_PROFILE_OUT"], "w") as f:
+                for r in rows:
+                    gbs = r["bytes"] / (r["ms"] * 1e6) if r["ms"] > 0 else 0
+                    tfs = r["flops"] / (r["ms"] * 1e9) if r["ms"] > 0 else 0
+                    f.write(f"{r['ms']:9.4f} ms  {r['calls']:5.1f}x  {gbs:8.1f} GB/s {tfs:8.2f} TF/s  {r['kernel']:28s} {r['layer']}\n")
 
     line = None
     if rank == 0:

@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 F32, BF16, F16 = 0, 1, 2
 
@@ -60,6 +60,8 @@ SIGNATURES = {
     "hcu_conv_tc_pack": [C.POINTER(HcuConvDesc), P, P, P],
     "hcu_conv_tc_fwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
     "hcu_conv_wgrad_partial": [C.POINTER(HcuConvDesc), P, P, P, P, P, I32, P],
+    "hcu_conv_wgrad_tc_supported": [C.POINTER(HcuConvDesc)],
+    "hcu_conv_wgrad_tc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
     "hcu_weight_gather": [C.POINTER(HcuWeightMap), P, P, P],
     "hcu_weight_scatter": [C.POINTER(HcuWeightMap), P, I32, I64, F, P, I32, P, P],
     "hcu_nc_to_cl": [P, I32, P, I32, I64, I32, I64, I32, P, P],
@@ -142,7 +144,7 @@ def load():
     out._cdll = lib
     for name in SIGNATURES:
         raw = getattr(lib, name)
-        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_conv_tc_supported",
+        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_conv_tc_supported", "hcu_conv_wgrad_tc_supported",
                                          "hcu_conv_tc_packed_bytes") else _wrap(name, raw))
     _lib = out
     return out

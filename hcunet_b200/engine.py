@@ -12,6 +12,7 @@ folding the two K-halves of ``Up.conv1``'s weight, so no concatenated tensor is 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -224,6 +225,7 @@ class UnetEngine:
         self.spec = spec
         self._plans: Dict[tuple, Plan] = {}
         self._inv = None
+        self.use_tc = os.environ.get("HCUNET_TC", "1") != "0"
 
     @property
     def lib(self):
@@ -248,9 +250,27 @@ class UnetEngine:
         return out
 
     def _conv(self, d, x, w, bias=None, out=None, stats=None, in_scale=None, in_shift=None, out_scale=None,
-              out_shift=None):
-        _lib.check(self.lib.hcu_conv_fwd(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
-                                         _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), self._stream()),
+              out_shift=None, layer=None):
+        """One gather-convolution launch.  w: fp32 [g][taps][cin][cout].  fp16 activations take the tcgen05 kernel
+        whenever it supports the descriptor, everything else the FFMA kernel."""
+        lib = self.lib
+        m = d.batch * d.out_size[0] * d.out_size[1] * d.out_size[2]
+        esz_i = 4 if d.dtype_in == _lib.F32 else 2
+        esz_o = 4 if d.dtype_out == _lib.F32 else 2
+        nin = d.batch * d.in_size[0] * d.in_size[1] * d.in_size[2] * d.cin * d.groups
+        _lib.note(layer, nin * esz_i + m * d.cout * d.groups * esz_o,
+                  2 * m * d.cout * d.groups * d.cin * d.taps[0] * d.taps[1] * d.taps[2])
+        if self.use_tc and d.dtype_in == _lib.F16 and lib.hcu_conv_tc_supported(C.byref(d)):
+            packed = torch.empty(lib.hcu_conv_tc_packed_bytes(C.byref(d)), dtype=torch.uint8, device=x.device)
+            note = _lib._ProfState.note
+            _lib.check(lib.hcu_conv_tc_pack(C.byref(d), _ptr(w), _ptr(packed), self._stream()), "conv_tc_pack")
+            _lib._ProfState.note = note
+            _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), _ptr(x), _ptr(packed), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
+                                           _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), self._stream()),
+                       "conv_tc_fwd")
+            return
+        _lib.check(lib.hcu_conv_fwd(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
+                                    _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), self._stream()),
                    "conv_fwd")
 
     # ---- weight maps (reference layouts: Conv [Cout, Cin/g, kx, ky, kz]; ConvT [Cin, Cout, kx, ky, kz]) ----
@@ -282,6 +302,10 @@ class UnetEngine:
         return weight_map(1, u.k, u.cout, u.cin, sg=0, sa=T, sb=u.cout * T, st=(u.k[1] * u.k[2], u.k[2], 1))
 
     # ---- forward ------------------------------------------------------------------------------
+    # Data flow (training): every conv writes its RAW output y (+ per-channel sum / sum of squares from the fp32
+    # accumulators); BatchNorm + ReLU of layer L are never materialised -- they are applied by whoever READS y_L
+    # (the next conv's operand load, the max-pool pass, the weight-gradient's operand load).  Only y tensors, pooled
+    # activations and the up-convolution outputs exist in HBM.
     def forward(self, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor], x: torch.Tensor,
                 training: bool, save: bool, precision: str = "fp32"):
         """Returns (logits [B, Cout, *spatial] fp32, saved-state or None)."""
@@ -290,94 +314,99 @@ class UnetEngine:
         dev = x.device
         act_dtype = _ACT_DTYPE[precision]
         adt = _DT[act_dtype]
+        esz = 2 if act_dtype == torch.float16 else 4
         B = plan.batch
         x = x.contiguous()
         if x.dtype not in _DT:
             x = x.float()
         S = plan.in_sz[0] * plan.in_sz[1] * plan.in_sz[2]
-        cur = torch.empty((B, S, plan.in_channels), dtype=act_dtype, device=dev)
-        _lib.check(lib.hcu_nc_to_cl(_ptr(x), _DT[x.dtype], _ptr(cur), adt, B, plan.in_channels, S, plan.in_channels,
-                                    None, st), "nc_to_cl")
+        # fp16 path: pad the input channels to a multiple of 8 (16-byte pixels) so the first conv is tensor-core too
+        cp = -(-plan.in_channels // 8) * 8 if act_dtype == torch.float16 else plan.in_channels
+        cur = torch.empty((B, S, cp), dtype=act_dtype, device=dev)
+        _lib.note("input", x.numel() * x.element_size() + cur.numel() * esz, 0)
+        _lib.check(lib.hcu_nc_to_cl(_ptr(x), _DT[x.dtype], _ptr(cur), adt, B, plan.in_channels, S, cp, None, st),
+                   "nc_to_cl")
+        xf = None  # pending (scale, shift) + ReLU to apply when `cur` is read
         saved = [] if save else None
-        use_batch_stats = training
+        fold_eval = not save and not training  # inference: BN folded into the conv epilogue
+        logits = None
         for g in plan.steps:
             if isinstance(g, UpGeom):
-                out = self._up_forward(g, params, cur, B, act_dtype)
+                out = self._up_forward(g, params, cur, cp, xf, B, act_dtype)
                 if save:
-                    saved.append(("up", g, cur))
-                cur = out
+                    saved.append(("up", g, cur, cp, xf))
+                cur, cp, xf = out, g.cout, None
                 continue
             npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
             w = self._gather_w(self._wm_conv_fwd(g), params[g.name + ".weight"],
                                g.groups * g.taps[0] * g.taps[1] * g.taps[2] * g.cin_g * g.cout_g)
             bias = params[g.name + ".bias"]
+            isc, ish = (xf[0], xf[1]) if xf is not None else (None, None)
             if g.bn is None:  # out_conv: logits, fp32
                 y = torch.empty((B, npix // B, g.cout_t), dtype=torch.float32, device=dev)
-                d = conv_desc(adt, _lib.F32, B, g.in_sz, g.cin_t, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0,
-                              g.cout_g, g.groups, g.taps, g.dil)
-                self._conv(d, cur, w, bias, y)
+                d = conv_desc(adt, _lib.F32, B, g.in_sz, cp, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0,
+                              g.cout_g, g.groups, g.taps, g.dil, in_relu=int(xf is not None))
+                self._conv(d, cur, w, bias, y, in_scale=isc, in_shift=ish, layer=g.name)
                 if save:
-                    saved.append(("out", g, cur))
+                    saved.append(("out", g, cur, cp, xf))
                 if g.cout_t == 1:
                     logits = y.view((B, 1) + tuple(g.out_sz[:plan.dims]))
                 else:
                     logits = torch.empty((B, g.cout_t) + tuple(g.out_sz[:plan.dims]), dtype=torch.float32, device=dev)
                     _lib.check(lib.hcu_cl_to_nc(_ptr(y), _lib.F32, _ptr(logits), _lib.F32, B, g.cout_t, npix // B,
                                                 g.cout_t, None, st), "cl_to_nc")
-                cur = None
                 break
             gamma, beta = params[g.bn + ".weight"], params[g.bn + ".bias"]
             rm, rv = buffers[g.bn + ".running_mean"], buffers[g.bn + ".running_var"]
-            d = conv_desc(adt, adt, B, g.in_sz, g.cin_t, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0,
-                          g.cout_g, g.groups, g.taps, g.dil)
+            d = conv_desc(adt, adt, B, g.in_sz, cp, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0,
+                          g.cout_g, g.groups, g.taps, g.dil, in_relu=int(xf is not None))
             vec = torch.empty((4, g.cout_t), dtype=torch.float32, device=dev)  # mean, invstd, scale, shift
-            if not save and not use_batch_stats:
-                # inference: BN folded into the conv epilogue, activation written once
+            if fold_eval:
                 _lib.check(lib.hcu_bn_eval_affine(g.cout_t, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), BN_EPS,
                                                   _ptr(bias), _ptr(vec[2]), _ptr(vec[3]), st), "bn_eval_affine")
                 d.out_relu = 1
                 a = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
-                self._conv(d, cur, w, None, a, out_scale=vec[2], out_shift=vec[3])
+                self._conv(d, cur, w, None, a, out_scale=vec[2], out_shift=vec[3], layer=g.name)
                 if g.pool is not None:
-                    pooled, _ = self._pool(a, g, B, act_dtype, None, None, 0)
-                    a = pooled
-                cur = a
+                    a, _ = self._pool(a, g, B, act_dtype, None, None, 0, want_argmax=False)
+                cur, cp, xf = a, g.cout_t, None
                 continue
             y = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
-            if use_batch_stats:
+            if training:
                 stats = torch.zeros((2, g.cout_t), dtype=torch.float64, device=dev)
-                self._conv(d, cur, w, bias, y, stats=stats)
+                self._conv(d, cur, w, bias, y, stats=stats, in_scale=isc, in_shift=ish, layer=g.name)
                 _lib.check(lib.hcu_bn_finalize(_ptr(stats), g.cout_t, float(npix), _ptr(gamma), _ptr(beta), BN_EPS,
                                                BN_MOMENTUM, _ptr(rm), _ptr(rv), _ptr(vec[0]), _ptr(vec[1]),
                                                _ptr(vec[2]), _ptr(vec[3]), st), "bn_finalize")
             else:
-                # eval-mode forward that must be differentiable: running statistics, unfused
-                self._conv(d, cur, w, bias, y)
+                # eval-mode forward that must be differentiable: running statistics
+                self._conv(d, cur, w, bias, y, in_scale=isc, in_shift=ish, layer=g.name)
                 _lib.check(lib.hcu_bn_eval_affine(g.cout_t, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), BN_EPS, None,
                                                   _ptr(vec[2]), _ptr(vec[3]), st), "bn_eval_affine")
                 vec[0].copy_(rm)
                 vec[1].copy_(torch.rsqrt(rv + BN_EPS))
             argmax = None
+            a_in, a_cp, a_xf = cur, cp, xf
             if g.pool is not None:
-                a, argmax = self._pool(y, g, B, act_dtype, vec[2], vec[3], 1)
+                cur, argmax = self._pool(y, g, B, act_dtype, vec[2], vec[3], 1, want_argmax=save)
+                cp, xf = g.cout_t, None
             else:
-                a = torch.empty_like(y)
-                _lib.check(lib.hcu_bn_relu_apply(_ptr(y), adt, _ptr(a), adt, npix, g.cout_t, _ptr(vec[2]),
-                                                 _ptr(vec[3]), 1, st), "bn_relu_apply")
+                cur, cp, xf = y, g.cout_t, (vec[2], vec[3])
             if save:
-                saved.append(("conv", g, cur, y, vec, argmax))
-            cur = a
+                saved.append(("conv", g, a_in, a_cp, a_xf, y, vec, argmax))
         if training:
             nbt = [buffers[g.bn + ".num_batches_tracked"] for g in plan.steps
                    if isinstance(g, ConvGeom) and g.bn is not None]
             torch._foreach_add_(nbt, 1)
         return logits, (plan, saved, act_dtype, training)
 
-    def _pool(self, y, g: ConvGeom, B, act_dtype, scale, shift, relu):
+    def _pool(self, y, g: ConvGeom, B, act_dtype, scale, shift, relu, want_argmax=True):
         adt = _DT[act_dtype]
+        esz = 2 if act_dtype == torch.float16 else 4
         ps = g.pool_sz
         pooled = torch.empty((B, ps[0] * ps[1] * ps[2], g.cout_t), dtype=act_dtype, device=y.device)
         argmax = torch.empty((B, ps[0] * ps[1] * ps[2], g.cout_t), dtype=torch.uint8, device=y.device)
+        _lib.note(g.name, y.numel() * esz + pooled.numel() * (esz + 1), 0)
         _lib.check(self.lib.hcu_bn_relu_maxpool(_ptr(y), adt, _ptr(pooled), adt, _ptr(argmax), B, g.out_sz[0],
                                                 g.out_sz[1], g.out_sz[2], g.cout_t, g.pool[0], g.pool[1], g.pool[2],
                                                 _ptr(scale), _ptr(shift), relu, self._stream()), "bn_relu_maxpool")
@@ -393,16 +422,17 @@ class UnetEngine:
                     Q = tuple(-(-(u.out_sz[d] - phi[d]) // u.s[d]) for d in range(3))
                     yield phi, J, Q
 
-    def _up_forward(self, u: UpGeom, params, cur, B, act_dtype):
+    def _up_forward(self, u: UpGeom, params, cur, cp, xf, B, act_dtype):
         """ConvTranspose (`unet.py:294-298,310`) as prod(stride) stride-1 sub-convolutions, one per output phase."""
         adt = _DT[act_dtype]
         wt, bias = params[u.name + ".weight"], params[u.name + ".bias"]
         out = torch.empty((B, u.out_sz[0] * u.out_sz[1] * u.out_sz[2], u.cout), dtype=act_dtype, device=cur.device)
+        isc, ish = (xf[0], xf[1]) if xf is not None else (None, None)
         for phi, J, Q in self._phases(u):
             w = self._gather_w(self._wm_up_phase(u, phi, J), wt, J[0] * J[1] * J[2] * u.cin * u.cout)
-            d = conv_desc(adt, adt, B, u.in_sz, u.cin, 0, u.cin, u.cin, Q, u.out_sz, u.cout, 0, u.cout, 1, J,
-                          pad=tuple(j - 1 for j in J), ostep=u.s, ooff=phi)
-            self._conv(d, cur, w, bias, out)
+            d = conv_desc(adt, adt, B, u.in_sz, cp, 0, u.cin, u.cin, Q, u.out_sz, u.cout, 0, u.cout, 1, J,
+                          pad=tuple(j - 1 for j in J), ostep=u.s, ooff=phi, in_relu=int(xf is not None))
+            self._conv(d, cur, w, bias, out, in_scale=isc, in_shift=ish, layer=u.name)
         return out
 
     # ---- backward -----------------------------------------------------------------------------
@@ -411,6 +441,7 @@ class UnetEngine:
         lib, st = self.lib, self._stream()
         plan, saved, act_dtype, training = state
         adt = _DT[act_dtype]
+        esz = 2 if act_dtype == torch.float16 else 4
         dev = dlogits.device
         B = plan.batch
         grads: Dict[str, torch.Tensor] = {}
@@ -439,22 +470,25 @@ class UnetEngine:
         for item in reversed(saved):
             kind = item[0]
             if kind == "out":
-                _, g, a_in = item
+                _, g, a_in, a_cp, a_xf = item
                 npix = B * So
                 grads[g.name + ".bias"] = self._colsum(dcur, dcur_dt, npix, co, scratch)
-                grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, adt, dcur, dcur_dt, B, params[g.name + ".weight"])
+                grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, a_cp, a_xf, adt, dcur, dcur_dt, B,
+                                                             params[g.name + ".weight"])
                 dcur = self._dgrad_conv(g, dcur, dcur_dt, B, params[g.name + ".weight"], act_dtype)
                 dcur_dt = adt
             elif kind == "conv":
-                _, g, a_in, y, vec, argmax = item
+                _, g, a_in, a_cp, a_xf, y, vec, argmax = item
                 npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
                 if argmax is not None:
                     dfull = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
+                    _lib.note(g.name, dcur.numel() * (esz + 1) + dfull.numel() * esz, 0)
                     _lib.check(lib.hcu_maxpool_bwd(_ptr(dcur), dcur_dt, _ptr(argmax), _ptr(dfull), adt, B, g.out_sz[0],
                                                    g.out_sz[1], g.out_sz[2], g.cout_t, g.pool[0], g.pool[1],
                                                    g.pool[2], st), "maxpool_bwd")
                     dcur, dcur_dt = dfull, adt
                 sums = torch.zeros((2, g.cout_t), dtype=torch.float64, device=dev)
+                _lib.note(g.name, 2 * npix * g.cout_t * esz, 0)
                 _lib.check(lib.hcu_bn_bwd_stats(_ptr(dcur), dcur_dt, _ptr(y), adt, npix, g.cout_t, _ptr(vec[2]),
                                                 _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(sums), st),
                            "bn_bwd_stats")
@@ -467,35 +501,42 @@ class UnetEngine:
                                                    _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(coef), st),
                            "bn_bwd_finalize")
                 dy = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
+                _lib.note(g.name, 3 * npix * g.cout_t * esz, 0)
                 _lib.check(lib.hcu_bn_bwd_apply(_ptr(dcur), dcur_dt, _ptr(y), adt, _ptr(dy), adt, npix, g.cout_t,
                                                 _ptr(vec[2]), _ptr(vec[3]), 1, _ptr(coef), st), "bn_bwd_apply")
                 grads[g.bn + ".weight"], grads[g.bn + ".bias"], grads[g.name + ".bias"] = dgamma, dbeta, dbias
-                grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, adt, dy, adt, B, params[g.name + ".weight"])
+                grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, a_cp, a_xf, adt, dy, adt, B,
+                                                             params[g.name + ".weight"])
                 if g.first and not need_dx:
                     dcur = None
                 else:
-                    dcur = self._dgrad_conv(g, dy, adt, B, params[g.name + ".weight"], act_dtype)
+                    dcur = self._dgrad_conv(g, dy, adt, B, params[g.name + ".weight"], act_dtype,
+                                            out_cp=a_cp if g.first else None)
                     dcur_dt = adt
                 if g.first and need_dx:
                     S = plan.in_sz[0] * plan.in_sz[1] * plan.in_sz[2]
                     dx = torch.empty((B, plan.in_channels) + tuple(plan.in_sz[:plan.dims]), dtype=torch.float32,
                                      device=dev)
                     _lib.check(lib.hcu_cl_to_nc(_ptr(dcur), adt, _ptr(dx), _lib.F32, B, plan.in_channels, S,
-                                                plan.in_channels, _ptr(inv), st), "cl_to_nc")
+                                                a_cp, _ptr(inv), st), "cl_to_nc")
             else:  # "up"
-                _, u, a_in = item
+                _, u, a_in, a_cp, a_xf = item
                 npix_out = B * u.out_sz[0] * u.out_sz[1] * u.out_sz[2]
                 grads[u.name + ".bias"] = self._colsum(dcur, dcur_dt, npix_out, u.cout, scratch)
-                # weight gradient: R[t][co][ci] = sum_i dOut[i*s + t][co] * In[i][ci]
+                # weight gradient: R[t][co][ci] = sum_i dOut[i*s + t][co] * act(In[i])[ci]
                 T = u.k[0] * u.k[1] * u.k[2]
+                m = B * u.in_sz[0] * u.in_sz[1] * u.in_sz[2]
+                # the gather side (a) is dOut, the dense side (b) is the up-conv's input: its pending BN+ReLU has to
+                # be materialised once for the dense side
+                a_act = self._materialise(a_in, a_cp, a_xf, m, u.cin, act_dtype)
                 d = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin, 1,
                               u.k, istep=u.s)
-                m = B * u.in_sz[0] * u.in_sz[1] * u.in_sz[2]
                 roles = T * (-(-u.cout // 8)) * (-(-u.cin // 8))
                 ns = _nsplit(m, roles)
                 total = T * u.cout * u.cin
                 partial = torch.empty((ns, total), dtype=torch.float32, device=dev)
-                _lib.check(lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(dcur), None, None, _ptr(a_in), _ptr(partial), ns,
+                _lib.note(u.name, (npix_out * u.cout + m * u.cin) * esz, 2 * m * T * u.cin * u.cout)
+                _lib.check(lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(dcur), None, None, _ptr(a_act), _ptr(partial), ns,
                                                       st), "wgrad(up)")
                 gw = torch.empty_like(params[u.name + ".weight"])
                 wm = self._wm_up_dgrad(u)
@@ -507,9 +548,19 @@ class UnetEngine:
                 dprev = torch.empty((B, u.in_sz[0] * u.in_sz[1] * u.in_sz[2], u.cin), dtype=act_dtype, device=dev)
                 d2 = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin,
                                1, u.k, istep=u.s)
-                self._conv(d2, dcur, w, None, dprev)
+                self._conv(d2, dcur, w, None, dprev, layer=u.name + ".dgrad")
                 dcur, dcur_dt = dprev, adt
         return grads, dx
+
+    def _materialise(self, t, cp, xf, npix, c, act_dtype):
+        """relu(t * scale + shift) as a tensor (only where a kernel cannot apply the pending transform on load)."""
+        if xf is None:
+            return t
+        adt = _DT[act_dtype]
+        a = torch.empty_like(t)
+        _lib.check(self.lib.hcu_bn_relu_apply(_ptr(t), adt, _ptr(a), adt, npix, cp, _ptr(xf[0]), _ptr(xf[1]), 1,
+                                              self._stream()), "bn_relu_apply")
+        return a
 
     def _colsum(self, x, dt, npix, c, scratch):
         out = torch.empty(c, dtype=torch.float32, device=x.device)
@@ -517,30 +568,43 @@ class UnetEngine:
                                        self._stream()), "colsum")
         return out
 
-    def _wgrad_conv(self, g: ConvGeom, a_in, a_dt, dy, dy_dt, B, wref):
+    def _wgrad_conv(self, g: ConvGeom, a_in, a_cp, a_xf, a_dt, dy, dy_dt, B, wref):
         T = g.taps[0] * g.taps[1] * g.taps[2]
-        d = conv_desc(a_dt, dy_dt, B, g.in_sz, g.cin_t, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0, g.cout_g,
-                      g.groups, g.taps, g.dil)
+        d = conv_desc(a_dt, dy_dt, B, g.in_sz, a_cp, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0, g.cout_g,
+                      g.groups, g.taps, g.dil, in_relu=int(a_xf is not None))
         m = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
         roles = g.groups * T * (-(-g.cin_g // 8)) * (-(-g.cout_g // 8))
         ns = _nsplit(m, roles)
         total = g.groups * T * g.cin_g * g.cout_g
         partial = torch.empty((ns, total), dtype=torch.float32, device=dy.device)
-        _lib.check(self.lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(a_in), None, None, _ptr(dy), _ptr(partial), ns,
-                                                   self._stream()), "wgrad")
+        esz = 4 if a_dt == _lib.F32 else 2
+        nin = B * g.in_sz[0] * g.in_sz[1] * g.in_sz[2] * g.cin_t
+        _lib.note(g.name, (nin + m * g.cout_t) * esz, 2 * m * T * g.cin_g * g.cout_g * g.groups)
+        isc, ish = (a_xf[0], a_xf[1]) if a_xf is not None else (None, None)
         gw = torch.empty_like(wref)
         wm = self._wm_conv_fwd(g)
+        if self.use_tc and a_dt == _lib.F16 and dy_dt == _lib.F16 and self.lib.hcu_conv_wgrad_tc_supported(C.byref(d)):
+            wacc = partial[0]
+            _lib.check(self.lib.hcu_conv_wgrad_tc(C.byref(d), _ptr(a_in), _ptr(isc), _ptr(ish), _ptr(dy), _ptr(wacc),
+                                                  self._stream()), "wgrad_tc")
+            _lib.check(self.lib.hcu_weight_scatter(C.byref(wm), _ptr(wacc), 1, total, 1.0, _ptr(self._inv), 0, _ptr(gw),
+                                                   self._stream()), "weight_scatter")
+            return gw
+        _lib.check(self.lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(a_in), _ptr(isc), _ptr(ish), _ptr(dy), _ptr(partial),
+                                                   ns, self._stream()), "wgrad")
         _lib.check(self.lib.hcu_weight_scatter(C.byref(wm), _ptr(partial), ns, total, 1.0, _ptr(self._inv), 0, _ptr(gw),
                                                self._stream()), "weight_scatter")
         return gw
 
-    def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype):
+    def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype, out_cp=None):
         adt = _DT[act_dtype]
         T = g.taps[0] * g.taps[1] * g.taps[2]
         w = self._gather_w(self._wm_conv_dgrad(g), wref, g.groups * T * g.cin_g * g.cout_g)
-        dprev = torch.empty((B, g.in_sz[0] * g.in_sz[1] * g.in_sz[2], g.cin_t), dtype=act_dtype, device=dy.device)
+        cpo = out_cp or g.cin_t
+        alloc = torch.zeros if cpo != g.cin_t else torch.empty
+        dprev = alloc((B, g.in_sz[0] * g.in_sz[1] * g.in_sz[2], cpo), dtype=act_dtype, device=dy.device)
         pad = tuple((g.taps[i] - 1) * g.dil[i] for i in range(3))
-        d = conv_desc(dy_dt, adt, B, g.out_sz, g.cout_t, 0, g.cout_g, g.cout_g, g.in_sz, g.in_sz, g.cin_t, 0, g.cin_g,
+        d = conv_desc(dy_dt, adt, B, g.out_sz, g.cout_t, 0, g.cout_g, g.cout_g, g.in_sz, g.in_sz, cpo, 0, g.cin_g,
                       g.groups, g.taps, g.dil, pad=pad)
-        self._conv(d, dy, w, None, dprev)
+        self._conv(d, dy, w, None, dprev, layer=g.name + ".dgrad")
         return dprev

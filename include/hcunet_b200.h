@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 5
+#define HCU_ABI_VERSION 6
 
 typedef enum HcuStatus {
   HCU_OK = 0,
@@ -117,6 +117,13 @@ int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void* packed, co
  * Replaces: convolution_backward's weight gradient (autograd of unet.py:246-257,294-298). */
 int hcu_conv_wgrad_partial(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
                            const void* b, float* partial, int32_t nsplit, void* stream);
+
+/* Tensor-core flavour of the weight gradient (mma.sync m16n8k16, fp16 operands, fp32 accumulate; wgrad_mma.cu):
+ * wacc: fp32 [taps][cin][cout] (groups == 1), zeroed and accumulated by this call; feed it to hcu_weight_scatter with
+ * nsplit = 1.  hcu_conv_wgrad_tc_supported() says whether the descriptor is taken (else hcu_conv_wgrad_partial). */
+int hcu_conv_wgrad_tc_supported(const HcuConvDesc* d);
+int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
+                      float* wacc, void* stream);
 
 /* ---- weight layout transforms -------------------------------------------------------------
  * Generic strided gather between a reference-layout parameter and a packed GEMM-B tensor

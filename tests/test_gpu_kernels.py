@@ -151,3 +151,78 @@ def test_conv_tc_agrees_with_simt_kernel():
     b, sb = run_tc(x, w, want_stats=True, use_simt=True)
     assert rel_l2(a, b) <= 6e-4
     assert torch.allclose(sa, sb, rtol=1e-4, atol=1e-3)
+
+
+# ---- weight gradient on tensor cores (wgrad_mma.cu) ---------------------------------------------------------
+def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=False):
+    """x [N,Cin,...] activations (pre-transform), dy [N,Cout,...] -> dW [Cout,Cin,kx,ky,kz] fp32."""
+    from hcunet_b200 import _lib
+    from hcunet_b200.engine import conv_desc
+
+    lib = _lib.load()
+    n, cin = x.shape[:2]
+    cout = dy.shape[1]
+    isz, osz = tuple(x.shape[2:]), tuple(dy.shape[2:])
+    cp = cpitch or cin
+    xin, dyin = to_cl(x, cp), to_cl(dy)
+    d = conv_desc(_lib.F16, _lib.F16, n, isz, cp, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, dil,
+                  in_relu=int(in_affine is not None))
+    T = k[0] * k[1] * k[2]
+    isc = ish = None
+    if in_affine is not None:
+        isc = torch.zeros(cp, device="cuda"); ish = torch.zeros(cp, device="cuda")
+        isc[:cin], ish[:cin] = in_affine[0].cuda(), in_affine[1].cuda()
+    if use_simt:
+        ns = 4
+        part = torch.empty((ns, T * cin * cout), device="cuda")
+        _lib.check(lib.hcu_conv_wgrad_partial(C.byref(d), P(xin), P(isc), P(ish), P(dyin), P(part), ns, stream()))
+        wacc = part.sum(0)
+    else:
+        assert lib.hcu_conv_wgrad_tc_supported(C.byref(d)) == 1
+        wacc = torch.full((T * cin * cout,), float("nan"), device="cuda")
+        _lib.check(lib.hcu_conv_wgrad_tc(C.byref(d), P(xin), P(isc), P(ish), P(dyin), P(wacc), stream()), "wgrad_tc")
+    torch.cuda.synchronize()
+    return wacc.view(k[0], k[1], k[2], cin, cout).permute(4, 3, 0, 1, 2).cpu()
+
+
+WG_CASES = [
+    (1, 8, 8, (10, 12, 9), (3, 3, 2), (1, 1, 1), None),
+    (2, 4, 8, (9, 11, 7), (3, 3, 2), (1, 1, 1), 8),
+    (1, 8, 8, (9, 40, 31), (3, 3, 1), (1, 1, 1), None),
+    (1, 8, 16, (8, 12, 10), (3, 3, 2), (1, 1, 1), None),
+    (2, 16, 16, (7, 14, 9), (3, 3, 1), (1, 1, 1), None),
+    (1, 16, 32, (7, 9, 8), (3, 3, 2), (1, 1, 1), None),
+    (1, 32, 32, (6, 11, 9), (3, 3, 1), (1, 1, 1), None),
+    (1, 32, 64, (5, 9, 8), (3, 3, 2), (1, 1, 1), None),
+    (1, 64, 64, (5, 8, 7), (3, 3, 1), (1, 1, 1), None),
+    (1, 64, 128, (4, 8, 6), (3, 3, 2), (1, 1, 1), None),
+    (1, 128, 128, (4, 7, 6), (3, 3, 1), (1, 1, 1), None),
+    (1, 8, 16, (12, 13, 6), (3, 3, 2), (2, 2, 1), None),
+    (1, 16, 8, (5, 6, 7), (1, 1, 1), (1, 1, 1), None),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_wgrad_tc_matches_fp32(case):
+    n, cin, cout, isz, k, dil, cp = case
+    g = torch.Generator().manual_seed(hash(case) % 10000 + 1)
+    osz = tuple(isz[i] - (k[i] - 1) * dil[i] for i in range(3))
+    x = h16(torch.randn((n, cin) + isz, generator=g))
+    dy = h16(torch.randn((n, cout) + osz, generator=g))
+    ref = torch.nn.grad.conv3d_weight(x, (cout, cin) + k, dy, dilation=dil)
+    got = run_wgrad(x, dy, k, dil=dil, cpitch=cp)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)   # exact fp16 products, fp32 accumulate
+
+
+def test_wgrad_tc_fused_input_bn_relu():
+    g = torch.Generator().manual_seed(9)
+    x = h16(torch.randn((2, 16, 8, 9, 7), generator=g))
+    dy = h16(torch.randn((2, 32, 6, 7, 6), generator=g))
+    sc, sh = torch.rand(16, generator=g) + 0.5, torch.randn(16, generator=g) * 0.3
+    a = h16(F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)))
+    ref = torch.nn.grad.conv3d_weight(a, (32, 16, 3, 3, 2), dy)
+    got = run_wgrad(x, dy, (3, 3, 2), in_affine=(sc, sh))
+    assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)
+    simt = run_wgrad(x, dy, (3, 3, 2), in_affine=(sc, sh), use_simt=True)
+    assert rel_l2(simt, ref) <= 1e-3   # the FFMA kernel does not round the transformed activation to fp16
