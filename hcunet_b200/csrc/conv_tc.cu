@@ -21,6 +21,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -56,6 +57,7 @@ struct Params {
   // shared memory carve-up (bytes from the 128-aligned base)
   int off_w, off_a, off_bar, off_tab, off_stat, smem_bytes;
   int tmem_cols;
+  int debug;  // HCU_TC_DEBUG bits (profiling experiments only): 1 no global loads, 2 no epilogue math/stores, 4 no MMAs
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -160,11 +162,37 @@ __device__ __forceinline__ float reduce16(float* v, int lane) {
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n.reg .b32 rx;\n.reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------
+constexpr int kMaxChunk = 8;  // producer fast path: <= 8 16-byte chunks per thread per x-plane, addresses precomputed
+
+__device__ __forceinline__ uint4 bn_relu8(uint4 v, const float* sc, const float* sh, int relu) {
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 f = __half22float2(h[k]);
+    f.x = fmaf(f.x, sc[2 * k], sh[2 * k]);
+    f.y = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
+    if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+    h[k] = __floats2half2_rn(f.x, f.y);
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -174,9 +202,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * p.R, bar_tfull = bar_empty + 8 * p.R,
                  bar_tempty = bar_tfull + 16, bar_w = bar_tempty + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (2 * p.R + 5));
-  int2* tab = reinterpret_cast<int2*>(smem + p.off_tab);      // per pair: (A byte offset, LBO bytes)
+  uint4* mlist = reinterpret_cast<uint4*>(smem + p.off_tab);   // [R rotations][cnt] MMA descriptors of one output plane
   float* sstat = reinterpret_cast<float*>(smem + p.off_stat);  // [2][Nc]
   const uint32_t a_base = smem_u32(smem + p.off_a), w_base = smem_u32(smem + p.off_w);
+  const int R = p.R, MB = p.MB, Nc = p.Nc;
+  const int cnt = MB * p.KX * p.npairs;  // MMAs per output plane
 
   // ---- work item ---------------------------------------------------------------------------------
   int item = blockIdx.x;
@@ -192,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   // ---- one-time setup --------------------------------------------------------------------------------
   if (warp == 8) {
     if (lane == 0) {
-      for (int i = 0; i < p.R; ++i) {
+      for (int i = 0; i < R; ++i) {
         mbar_init(bar_full + 8 * i, 4);   // one arrive per producer warp
         mbar_init(bar_empty + 8 * i, 1);  // tcgen05.commit
       }
@@ -205,9 +235,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
-    // per-pair table: K16 step e -> entries 2e, 2e+1 of the (ty, tz, plane) list of one tx group
+    // Descriptor list.  For ring rotation r (= output plane index mod R) entry (mb, tx, e):
+    //   x = A descriptor low word, y = B descriptor low word, z = TMEM column of the accumulator, w = accumulate flag.
+    // K16 step e of a tx group covers entries 2e, 2e+1 of its (ty, tz, channel-plane) list.
     const int per_tx = p.KY * p.KZ * p.P;
-    for (int e = lane; e < p.npairs; e += 32) {
+    const uint32_t b_lbo = ((uint32_t)(Nc * 16) >> 4) << 16;
+    for (int idx = lane; idx < R * cnt; idx += 32) {
+      int k = idx % cnt;
+      const int r = idx / cnt;
+      const int e = k % p.npairs; k /= p.npairs;
+      const int tx = k % p.KX;
+      const int mb = k / p.KX;
       const int e0 = 2 * e, e1 = 2 * e + 1;
       const int t0 = e0 / p.P, c0 = e0 % p.P;
       const int off0 = ((t0 / p.KZ) * p.dy * p.Zv + (t0 % p.KZ) * p.dz) * 16 + c0 * p.PS;
@@ -216,16 +254,23 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         const int t1 = e1 / p.P, c1 = e1 % p.P;
         off1 = ((t1 / p.KZ) * p.dy * p.Zv + (t1 % p.KZ) * p.dz) * 16 + c1 * p.PS;
       }
-      tab[e] = make_int2(off0, off1 - off0);
+      int sl = r + tx * p.dx;
+      sl -= sl >= R ? R : 0;
+      uint4 q;
+      q.x = ((a_base + (uint32_t)(sl * p.SLOT + mb * 2048 + off0)) >> 4) | (((uint32_t)(off1 - off0) >> 4) << 16);
+      q.y = ((w_base + (uint32_t)((tx * p.E_tx + e0) * Nc * 16)) >> 4) | b_lbo;
+      q.z = (uint32_t)(mb * Nc);
+      q.w = (tx | e) ? 1u : 0u;
+      mlist[idx] = q;
     }
     if (lane == 0) {
-      const uint32_t wbytes = (uint32_t)p.E * p.Nc * 16u;
+      const uint32_t wbytes = (uint32_t)p.E * Nc * 16u;
       mbar_expect_tx(bar_w, wbytes);
       const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) + (size_t)ns * wbytes;
       for (uint32_t o = 0; o < wbytes; o += 32768u) bulk_g2s(w_base + o, src + o, min(32768u, wbytes - o), bar_w);
     }
   }
-  for (int i = threadIdx.x; i < 2 * p.Nc; i += kThreads) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < 2 * Nc; i += kThreads) sstat[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -239,6 +284,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     const int nchunk = (p.RUN - pix0 + pstep - 1) / pstep;  // pixels this thread copies per x-plane
     float sc[8], sh[8];
     const bool xf = p.in_scale != nullptr;
+    const int relu = p.in_relu;
     if (xf) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -250,106 +296,154 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     const int qf = q0 + pix0;
     const int yv0 = qf / p.Zv, zv0 = qf - yv0 * p.Zv;
     const int ystep = pstep / p.Zv, zstep = pstep - ystep * p.Zv;
-    const __half* in_n = p.in + (size_t)n * p.IX * p.IY * p.IZ * p.Cp + plane * 8;
+    const size_t xstride = (size_t)p.IY * p.IZ * p.Cp;
+    const __half* in_n = p.in + (size_t)n * p.IX * xstride + plane * 8;
+    const int sstep = pstep * 16;
+    unsigned char* dst0 = smem + p.off_a + plane * p.PS + pix0 * 16;
+    const bool fast = (p.RUN + pstep - 1) / pstep <= kMaxChunk;  // warp-uniform (CTA-uniform)
+    int goff[kMaxChunk];  // element offset of each chunk inside an x-plane, -1 = zero fill
+    if (fast) {
+      int yv = yv0, zv = zv0;
+#pragma unroll
+      for (int c = 0; c < kMaxChunk; ++c) {
+        const int ym = yv - p.py, zm = zv - p.pz;
+        const bool ok = c < nchunk && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
+        goff[c] = ok ? (ym * p.IZ + zm) * p.Cp : -1;
+        zv += zstep; yv += ystep;
+        if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+      }
+    }
+    int slot = 0;
+    uint32_t par = 1;
     for (int j = 0; j < nplanes; ++j) {
-      const int slot = j % p.R;
-      mbar_wait(bar_empty + 8 * slot, ((j / p.R) & 1) ^ 1);
+      mbar_wait(bar_empty + 8 * slot, par);
       const int xm = x0 + j - p.px;  // memory x of this virtual plane
       const bool xok = xm >= 0 && xm < p.IX;
-      const __half* in_x = in_n + (size_t)(xok ? xm : 0) * p.IY * p.IZ * p.Cp;
-      unsigned char* dst = smem + p.off_a + slot * p.SLOT + plane * p.PS + pix0 * 16;
-      int yv = yv0, zv = zv0;
-      for (int c = 0; c < nchunk; c += 4) {
-        uint4 v[4];
-        bool ok[4];
+      const __half* in_x = in_n + (size_t)(xok ? xm : 0) * xstride;
+      unsigned char* dst = dst0 + slot * p.SLOT;
+      if (fast) {
+        uint4 v[kMaxChunk];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int ym = yv - p.py, zm = zv - p.pz;
-          ok[u] = xok && (c + u < nchunk) && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
-          v[u] = make_uint4(0u, 0u, 0u, 0u);
-          if (ok[u]) v[u] = ldg_nc16(in_x + ((size_t)ym * p.IZ + zm) * p.Cp);
-          zv += zstep; yv += ystep;
-          if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+        for (int c = 0; c < kMaxChunk; ++c) {
+          v[c] = make_uint4(0u, 0u, 0u, 0u);
+          if (xok && goff[c] >= 0) v[c] = ldg_nc16(in_x + goff[c]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (c + u >= nchunk) break;
-          if (xf && ok[u]) {
-            __half2* h = reinterpret_cast<__half2*>(&v[u]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float2 f = __half22float2(h[k]);
-              f.x = fmaf(f.x, sc[2 * k], sh[2 * k]);
-              f.y = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
-              if (p.in_relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
-              h[k] = __floats2half2_rn(f.x, f.y);
-            }
+        for (int c = 0; c < kMaxChunk; ++c) {
+          if (c < nchunk) {
+            if (xf && xok && goff[c] >= 0) v[c] = bn_relu8(v[c], sc, sh, relu);
+            *reinterpret_cast<uint4*>(dst + c * sstep) = v[c];
           }
-          *reinterpret_cast<uint4*>(dst + (size_t)(c + u) * pstep * 16) = v[u];
+        }
+      } else {
+        int yv = yv0, zv = zv0;
+        for (int c = 0; c < nchunk; c += 4) {
+          uint4 v[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int ym = yv - p.py, zm = zv - p.pz;
+            ok[u] = xok && (c + u < nchunk) && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok[u]) v[u] = ldg_nc16(in_x + (size_t)(ym * p.IZ + zm) * p.Cp);
+            zv += zstep; yv += ystep;
+            if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (c + u >= nchunk) break;
+            if (xf && ok[u]) v[u] = bn_relu8(v[u], sc, sh, relu);
+            *reinterpret_cast<uint4*>(dst + (size_t)(c + u) * sstep) = v[u];
+          }
         }
       }
       fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * slot);
+      if (++slot == R) { slot = 0; par ^= 1; }
     }
   } else if (warp == 8) {
     // =========================================== MMA ISSUER ==========================================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.Nc >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
-      mbar_wait(bar_w, 0);
-      int next_wait = 0;
-      for (int i = 0; i < nout; ++i) {
-        const int last = i + (p.KX - 1) * p.dx;
-        for (; next_wait <= last; ++next_wait) mbar_wait(bar_full + 8 * (next_wait % p.R), (next_wait / p.R) & 1);
-        const int buf = i & 1;
-        mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        for (int mb = 0; mb < p.MB; ++mb) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)((buf * p.MB + mb) * p.Nc);
-          uint32_t accum = 0;
-          for (int tx = 0; tx < p.KX; ++tx) {
-            const uint32_t a_slot = a_base + (uint32_t)(((i + tx * p.dx) % p.R) * p.SLOT + mb * 128 * 16);
-            const uint32_t w_tx = w_base + (uint32_t)(tx * p.E_tx) * (uint32_t)p.Nc * 16u;
-            for (int e = 0; e < p.npairs; ++e) {
-              const int2 t = tab[e];
-              const uint64_t ad = smem_desc(a_slot + (uint32_t)t.x, (uint32_t)t.y, 128u);
-              const uint64_t bd = smem_desc(w_tx + (uint32_t)(2 * e) * (uint32_t)p.Nc * 16u, (uint32_t)p.Nc * 16u, 128u);
-              umma_f16(d_tmem, ad, bd, idesc, accum);
-              accum = 1;
-            }
-          }
-        }
-        umma_commit(bar_empty + 8 * (i % p.R));  // plane i is not needed by later outputs
+    // The whole warp runs this (warp-uniform values -> descriptors live in uniform registers, no per-thread
+    // waterfall); one elected lane issues tcgen05.mma / tcgen05.commit.  Everything is table driven: one 16-byte
+    // shared-memory read per MMA.
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(Nc >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
+    const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1 (bit 46)
+    const bool leader = elect_one();
+    mbar_wait(bar_w, 0);
+    const int lastoff = (p.KX - 1) * p.dx;
+    int next_wait = 0, wslot = 0;
+    uint32_t wpar = 0;
+    int i_mod = 0;
+    for (int i = 0; i < nout; ++i) {
+      for (; next_wait <= i + lastoff; ++next_wait) {
+        mbar_wait(bar_full + 8 * wslot, wpar);
+        if (++wslot == R) { wslot = 0; wpar ^= 1; }
+      }
+      const int buf = i & 1;
+      mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tb = tmem_base + (uint32_t)(buf * MB * Nc);
+      const uint4* L = mlist + i_mod * cnt;
+#pragma unroll 4
+      for (int k = 0; k < cnt; ++k) {
+        const uint4 q = L[k];
+        if (leader) umma_f16(tb + q.z, desc_hi | q.x, desc_hi | q.y, idesc, q.w);
+      }
+      if (leader) {
+        umma_commit(bar_empty + 8 * i_mod);  // plane i is not needed by later outputs
         umma_commit(bar_tfull + 8 * buf);
       }
+      __syncwarp();
+      i_mod = i_mod + 1 == R ? 0 : i_mod + 1;
     }
-    __syncwarp();
   } else {
     // =========================================== EPILOGUE ============================================
     const int row = threadIdx.x;  // accumulator row within an M-block == TMEM lane
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const bool do_stats = p.stats != nullptr;
     const bool affine = p.out_scale != nullptr;
+    const bool local_stats = do_stats && Nc == 16;  // one chunk: keep the sums in registers until the end
+    const int out_relu = p.out_relu, out_f32 = p.out_f32, cout = p.cout;
+    float t1[16], t2[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
+    // per M-block: offset of this thread's pixel inside an output x-plane (-1: wrap-around / out of range)
+    long long poff[4];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const int q = q0 + mb * 128 + row;
+      const int oy = q / p.Zv, oz = q - oy * p.Zv;
+      poff[mb] = (mb < MB && oy < p.OY && oz < p.OZ) ? oy * p.out_sy + oz * p.out_sz : -1;
+    }
+    const long long obase0 = p.out_base + n * p.out_sn + p.out_c_off + ns * Nc;
     for (int i = 0; i < nout; ++i) {
       const int buf = i & 1;
       mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
       tc_fence_after();
-      const int ox = x0 + i;
-      for (int mb = 0; mb < p.MB; ++mb) {
-        const int q = q0 + mb * 128 + row;
-        const int oy = q / p.Zv, oz = q - oy * p.Zv;
-        const bool valid = oy < p.OY && oz < p.OZ;
-        const long long obase = p.out_base + n * p.out_sn + ox * p.out_sx + oy * p.out_sy + oz * p.out_sz + p.out_c_off;
-        for (int cc = 0; cc < p.Nc; cc += 16) {
+      const long long obase = obase0 + (long long)(x0 + i) * p.out_sx;
+#pragma unroll
+      for (int mb = 0; mb < 4; ++mb) {
+        if (mb >= MB) break;
+        const bool valid = poff[mb] >= 0;
+        for (int cc = 0; cc < Nc; cc += 16) {
           float v[16];
-          tmem_ld16(tmem_base + lane_base + (uint32_t)((buf * p.MB + mb) * p.Nc + cc), v);
-          const int ch0 = ns * p.Nc + cc;  // first output channel of this chunk
+          tmem_ld16(tmem_base + lane_base + (uint32_t)((buf * MB + mb) * Nc + cc), v);
+          const int ch0 = ns * Nc + cc;  // first output channel of this chunk
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (ch0 + j < p.cout) v[j] += p.bias[ch0 + j];
+              if (ch0 + j < cout) v[j] += p.bias[ch0 + j];
           }
-          if (do_stats) {
+          if (local_stats) {
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                t1[j] += v[j];
+                t2[j] = fmaf(v[j], v[j], t2[j]);
+              }
+            }
+          } else if (do_stats) {
             float s1[16], s2[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -360,27 +454,27 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
             const float r2 = reduce16(s2, lane);
             if ((lane & 1) == 0) {
               atomicAdd(&sstat[cc + (lane >> 1)], r1);
-              atomicAdd(&sstat[p.Nc + cc + (lane >> 1)], r2);
+              atomicAdd(&sstat[Nc + cc + (lane >> 1)], r2);
             }
           }
           if (valid) {
             if (affine) {
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (ch0 + j < p.cout) v[j] = fmaf(v[j], p.out_scale[ch0 + j], p.out_shift[ch0 + j]);
+                if (ch0 + j < cout) v[j] = fmaf(v[j], p.out_scale[ch0 + j], p.out_shift[ch0 + j]);
             }
-            if (p.out_relu) {
+            if (out_relu) {
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            const int nv = min(16, p.cout - ch0);
-            if (p.out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + obase + ch0;
+            const int nv = min(16, cout - ch0);
+            if (out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + obase + poff[mb] + cc;
 #pragma unroll
               for (int j = 0; j < 16; ++j)
                 if (j < nv) o[j] = v[j];
             } else {
-              __half* o = reinterpret_cast<__half*>(p.out) + obase + ch0;
+              __half* o = reinterpret_cast<__half*>(p.out) + obase + poff[mb] + cc;
               if (nv >= 8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
                 __half2 h[8];
 #pragma unroll
@@ -406,13 +500,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
     }
+    if (local_stats) {
+      const float r1 = reduce16(t1, lane);
+      const float r2 = reduce16(t2, lane);
+      if ((lane & 1) == 0) {
+        atomicAdd(&sstat[lane >> 1], r1);
+        atomicAdd(&sstat[Nc + (lane >> 1)], r2);
+      }
+    }
     if (do_stats) {
       named_bar_sync(1, 128);
-      for (int c = row; c < p.Nc; c += 128) {
-        const int ch = ns * p.Nc + c;
-        if (ch < p.cout) {
+      for (int c = row; c < Nc; c += 128) {
+        const int ch = ns * Nc + c;
+        if (ch < cout) {
           atomicAdd(&p.stats[p.out_c_off + ch], (double)sstat[c]);
-          atomicAdd(&p.stats[p.stats_pitch + p.out_c_off + ch], (double)sstat[p.Nc + c]);
+          atomicAdd(&p.stats[p.stats_pitch + p.out_c_off + ch], (double)sstat[Nc + c]);
         }
       }
     }
@@ -486,8 +588,8 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   const int plane_q = p.Yv * p.Zv;
   // candidates: big M first; Nc as large as fits
   const int m_cands[4] = {512, 384, 256, 128};
-  for (int pass = 0; pass < 2; ++pass) {          // pass 0: aim for 2 CTAs / SM, pass 1: whatever fits
-    const int budget = pass == 0 ? 110 * 1024 : kSmemLimit;
+  for (int pass = 0; pass < 3; ++pass) {          // aim for 3, then 2 CTAs / SM, then whatever fits
+    const int budget = pass == 0 ? 74 * 1024 : (pass == 1 ? 110 * 1024 : kSmemLimit);
     for (int mi = 0; mi < 4; ++mi) {
       const int M = m_cands[mi];
       if (M > 128 && M - 128 >= plane_q) continue;  // do not use a longer run than the plane needs
@@ -503,12 +605,12 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
         if (npad % nc != 0) continue;
         if (2 * MB * nc > 512) continue;
         const int wbytes = p.E * nc * 16;
-        for (int R = std::min(span + 1, kMaxRing); R >= span; --R) {
+        for (int R = std::min(span + 3, kMaxRing); R >= span; --R) {
           const int off_w = 0;
           const int off_a = round_up(wbytes, 128);
           const int off_bar = off_a + R * slot;
           const int off_tab = round_up(off_bar + 8 * (2 * R + 5) + 8, 16);
-          const int off_stat = off_tab + kMaxPairs * 8;
+          const int off_stat = off_tab + R * MB * p.KX * p.npairs * 16;
           const int total = off_stat + 2 * nc * 4 + 128;
           if (total > budget) continue;
           p.M = M; p.MB = MB; p.RUN = run; p.PS = ps; p.SLOT = slot; p.R = R;
@@ -572,7 +674,13 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
   for (int i = 0; i < 3; ++i)
     HCU_CHECK_ARG((long long)(d->out_size[i] - 1) * d->ostep[i] + d->ooff[i] < d->out_tsize[i],
                   "conv_tc_fwd: output grid exceeds output tensor in dim %d", i);
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("HCU_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   HCU_CHECK_ARG(d->out_c_off >= 0 && d->out_c_off + d->cout <= d->out_cpitch, "conv_tc_fwd: output channel slice");
+  HCU_CHECK_ARG((long long)d->in_size[1] * d->in_size[2] * d->in_cpitch < 0x7fffffffLL, "conv_tc_fwd: x-plane too large");
   p.in = (const __half*)in; p.wp = (const __half*)packed; p.out = out;
   p.bias = bias; p.in_scale = in_scale; p.in_shift = in_shift; p.out_scale = out_scale; p.out_shift = out_shift;
   p.stats = stats; p.stats_pitch = d->out_cpitch;
@@ -580,15 +688,7 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
   p.out_sn = tn; p.out_sx = tx * d->ostep[0]; p.out_sy = ty * d->ostep[1]; p.out_sz = tz * d->ostep[2];
   p.out_base = tx * d->ooff[0] + ty * d->ooff[1] + tz * d->ooff[2];
   p.out_c_off = d->out_c_off; p.out_f32 = d->dtype_out == HCU_F32; p.in_relu = d->in_relu; p.out_relu = d->out_relu;
-  // x segmentation: enough CTAs to fill the machine ~2x, segments no shorter than 8 planes when possible
-  const long long base_items = (long long)p.N * p.n_runs * p.nsplit;
-  const int target = 2 * num_sms();
-  int nseg = (int)((target + base_items - 1) / base_items);
-  nseg = std::max(1, std::min(nseg, (p.OX + 7) / 8));
-  p.Lx = (p.OX + nseg - 1) / nseg;
-  p.n_xseg = (p.OX + p.Lx - 1) / p.Lx;
-  const long long grid = base_items * p.n_xseg;
-  HCU_CHECK_ARG(grid <= 0x7fffffffLL, "conv_tc_fwd: grid too large");
+
   static int smem_attr = 0;
   if (smem_attr < p.smem_bytes) {
     cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemLimit);
@@ -598,6 +698,37 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
     }
     smem_attr = tc::kSmemLimit;
   }
+  // x segmentation: the grid should fill whole waves of the CTAs that are really co-resident (registers, shared
+  // memory, TMEM columns), with segments no shorter than ~6 planes (each segment re-reads KX-1 planes)
+  static int regs_per_thread = 0;
+  if (regs_per_thread == 0) {
+    cudaFuncAttributes fa;
+    regs_per_thread = cudaFuncGetAttributes(&fa, tc::conv_tc_kernel) == cudaSuccess ? fa.numRegs : 128;
+  }
+  const int warps = tc::kThreads / 32;
+  int per_sm = 65536 / (((regs_per_thread * 32 + 255) / 256 * 256) * warps);   // register file
+  per_sm = std::min(per_sm, 233472 / (p.smem_bytes + 1024));                    // shared memory
+  per_sm = std::min(per_sm, 2048 / tc::kThreads);                               // threads
+  per_sm = std::max(1, std::min(per_sm, 512 / p.tmem_cols));                    // TMEM columns
+  if (p.debug & 8) fprintf(stderr, "conv_tc: per_sm %d smem %d tmem %d M %d R %d Nc %d\n", per_sm, p.smem_bytes, p.tmem_cols, p.M, p.R, p.Nc);
+  const long long slots = (long long)per_sm * num_sms();
+  const long long base_items = (long long)p.N * p.n_runs * p.nsplit;
+  const int max_seg = std::max(1, p.OX / 6);
+  int best_seg = 1;
+  double best_cost = 1e30;
+  for (int nseg = 1; nseg <= max_seg; ++nseg) {
+    const int lx = (p.OX + nseg - 1) / nseg;
+    const int segs = (p.OX + lx - 1) / lx;
+    const long long items = base_items * segs;
+    const long long waves = (items + slots - 1) / slots;
+    // time ~ waves * (planes per item incl. the KX-1 warm-up planes + fixed per-CTA overhead of ~4 planes)
+    const double cost = (double)waves * (lx + (p.KX - 1) * p.dx + 4);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best_seg = nseg; }
+  }
+  p.Lx = (p.OX + best_seg - 1) / best_seg;
+  p.n_xseg = (p.OX + p.Lx - 1) / p.Lx;
+  const long long grid = base_items * p.n_xseg;
+  HCU_CHECK_ARG(grid <= 0x7fffffffLL, "conv_tc_fwd: grid too large");
   tc::conv_tc_kernel<<<(unsigned)grid, tc::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(p);
   HCU_CHECK_LAUNCH("conv_tc");
   return 0;

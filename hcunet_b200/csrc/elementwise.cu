@@ -21,6 +21,8 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
 static inline int grid_for(long long work_items, int threads, int per_sm = 8) {
   long long blocks = (work_items + threads - 1) / threads;
   long long cap = (long long)num_sms() * per_sm;
@@ -104,6 +106,28 @@ __global__ void cl_to_nc_kernel(const TS* __restrict__ src, TD* __restrict__ dst
       if (cc < c && ss < s) dst[(b * c + cc) * s + ss] = from_f<TD>(tile[threadIdx.x][j]);
     }
     __syncthreads();
+  }
+}
+
+// small channel counts (the network input): one thread per spatial site gathers its channels (each channel read is
+// coalesced along s) and writes 16-byte groups of 8 fp16 channels
+template <typename TS>
+__global__ void nc_to_cl_h8_kernel(const TS* __restrict__ src, __half* __restrict__ dst, long long n, int c, long long s,
+                                   int cpitch, const float* __restrict__ dscale) {
+  const float mul = dscale != nullptr ? dscale[0] : 1.f;
+  const long long total = n * s;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long b = e / s, ss = e - b * s;
+    const TS* sp = src + b * c * s + ss;
+    for (int c0 = 0; c0 < cpitch; c0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < c) ? to_f(sp[(long long)(c0 + j) * s]) * mul : 0.f;
+      __half2 h[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      *reinterpret_cast<uint4*>(dst + e * cpitch + c0) = *reinterpret_cast<uint4*>(h);
+    }
   }
 }
 
@@ -248,6 +272,92 @@ __global__ void bn_relu_maxpool_kernel(const TY* __restrict__ y, TP* __restrict_
         }
     pooled[e] = from_f<TP>(best);
     argmax[e] = (uint8_t)bi;
+  }
+}
+
+// fp16, channels in groups of 8: one thread per (pooled voxel, 8 channels), 16-byte accesses
+__global__ void bn_relu_maxpool_h8_kernel(const __half* __restrict__ y, __half* __restrict__ pooled,
+                                          uint8_t* __restrict__ argmax, int n, int ix, int iy, int iz, int c, int px,
+                                          int py, int pz, const float* __restrict__ scale,
+                                          const float* __restrict__ shift, int relu) {
+  const int ox = ix / px, oy = iy / py, oz = iz / pz, c8 = c >> 3;
+  const long long total = (long long)n * ox * oy * oz * c8;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(e % c8);
+    long long r = e / c8;
+    const int z = (int)(r % oz); r /= oz;
+    const int yy = (int)(r % oy); r /= oy;
+    const int x = (int)(r % ox);
+    const int b = (int)(r / ox);
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
+    if (scale != nullptr) {
+      const float4 a0 = *reinterpret_cast<const float4*>(scale + cg * 8), a1 = *reinterpret_cast<const float4*>(scale + cg * 8 + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(shift + cg * 8), b1 = *reinterpret_cast<const float4*>(shift + cg * 8 + 4);
+      sc[0] = a0.x; sc[1] = a0.y; sc[2] = a0.z; sc[3] = a0.w; sc[4] = a1.x; sc[5] = a1.y; sc[6] = a1.z; sc[7] = a1.w;
+      sh[0] = b0.x; sh[1] = b0.y; sh[2] = b0.z; sh[3] = b0.w; sh[4] = b1.x; sh[5] = b1.y; sh[6] = b1.z; sh[7] = b1.w;
+    }
+    float best[8];
+    uint32_t bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int wx = 0; wx < px; ++wx)
+      for (int wy = 0; wy < py; ++wy)
+        for (int wz = 0; wz < pz; ++wz) {
+          const long long src = ((((long long)b * ix + (x * px + wx)) * iy + (yy * py + wy)) * iz + (z * pz + wz)) * c + cg * 8;
+          const uint4 raw = *reinterpret_cast<const uint4*>(y + src);
+          const __half2* h = reinterpret_cast<const __half2*>(&raw);
+          const uint32_t w = (uint32_t)((wx * py + wy) * pz + wz);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = __half22float2(h[j]);
+            if (scale != nullptr) { f.x = fmaf(f.x, sc[2 * j], sh[2 * j]); f.y = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]); }
+            if (relu) { f.x = f.x < 0.f ? 0.f : f.x; f.y = f.y < 0.f ? 0.f : f.y; }
+            if (f.x > best[2 * j] || f.x != f.x) { best[2 * j] = f.x; bi[2 * j] = w; }
+            if (f.y > best[2 * j + 1] || f.y != f.y) { best[2 * j + 1] = f.y; bi[2 * j + 1] = w; }
+          }
+        }
+    __half2 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = __floats2half2_rn(best[2 * j], best[2 * j + 1]);
+    *reinterpret_cast<uint4*>(pooled + e * 8) = *reinterpret_cast<uint4*>(o);
+    uint2 a;
+    a.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+    a.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+    *reinterpret_cast<uint2*>(argmax + e * 8) = a;
+  }
+}
+
+// covers every voxel inside a pooling window; the caller zero-fills dfull first when the input has a remainder
+__global__ void maxpool_bwd_h8_kernel(const __half* __restrict__ dpooled, const uint8_t* __restrict__ argmax,
+                                      __half* __restrict__ dfull, int n, int ix, int iy, int iz, int c, int px, int py,
+                                      int pz) {
+  const int ox = ix / px, oy = iy / py, oz = iz / pz, c8 = c >> 3;
+  const long long total = (long long)n * ox * oy * oz * c8;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(e % c8);
+    long long r = e / c8;
+    const int z = (int)(r % oz); r /= oz;
+    const int yy = (int)(r % oy); r /= oy;
+    const int x = (int)(r % ox);
+    const int b = (int)(r / ox);
+    const uint4 g = *reinterpret_cast<const uint4*>(dpooled + e * 8);
+    const uint2 a = *reinterpret_cast<const uint2*>(argmax + e * 8);
+    const unsigned short* gh = reinterpret_cast<const unsigned short*>(&g);
+    for (int wx = 0; wx < px; ++wx)
+      for (int wy = 0; wy < py; ++wy)
+        for (int wz = 0; wz < pz; ++wz) {
+          const uint32_t w = (uint32_t)((wx * py + wy) * pz + wz);
+          unsigned short o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+            o[j] = aj == w ? gh[j] : (unsigned short)0;
+          }
+          const long long dst = ((((long long)b * ix + (x * px + wx)) * iy + (yy * py + wy)) * iz + (z * pz + wz)) * c + cg * 8;
+          *reinterpret_cast<uint4*>(dfull + dst) = *reinterpret_cast<uint4*>(o);
+        }
   }
 }
 
@@ -474,6 +584,13 @@ extern "C" int hcu_zero(void* ptr, size_t bytes, void* stream) {
 extern "C" int hcu_nc_to_cl(const void* src, int32_t dtype_src, void* dst, int32_t dtype_dst, int64_t n, int32_t c,
                             int64_t s, int32_t cpitch, const float* dscale, void* stream) {
   HCU_CHECK_ARG(src && dst && n > 0 && c > 0 && s > 0 && cpitch >= c, "nc_to_cl: bad arguments");
+  if (dtype_dst == HCU_F16 && cpitch % 8 == 0 && cpitch <= 32 && (((uintptr_t)dst) & 15) == 0) {
+    const int g = grid_for(n * s, 256, 16);
+    HCU_DISPATCH_DTYPE(dtype_src, TS,
+        nc_to_cl_h8_kernel<TS><<<g, 256, 0, (cudaStream_t)stream>>>((const TS*)src, (__half*)dst, n, c, s, cpitch, dscale));
+    HCU_CHECK_LAUNCH("nc_to_cl_h8");
+    return 0;
+  }
   long long tiles = n * ((s + 31) / 32) * ((cpitch + 31) / 32);
   int grid = (int)(tiles < (long long)num_sms() * 16 ? tiles : (long long)num_sms() * 16);
   dim3 block(32, 8);
@@ -542,8 +659,6 @@ extern "C" int hcu_bn_eval_affine(int32_t c, const float* gamma, const float* be
   return 0;
 }
 
-static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
-
 extern "C" int hcu_bn_relu_apply(const void* y, int32_t dtype_y, void* a, int32_t dtype_a, int64_t npix, int32_t c,
                                  const float* scale, const float* shift, int32_t relu, void* stream) {
   HCU_CHECK_ARG(y && a && scale && shift && npix > 0 && c > 0, "bn_relu_apply: bad arguments");
@@ -568,6 +683,13 @@ extern "C" int hcu_bn_relu_maxpool(const void* y, int32_t dtype_y, void* pooled,
   HCU_CHECK_ARG((scale == nullptr) == (shift == nullptr), "maxpool: scale/shift come together");
   const long long total = (long long)n * (ix / px) * (iy / py) * (iz / pz) * c;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype_y == HCU_F16 && dtype_p == HCU_F16 && c % 8 == 0 && aligned16(y) && aligned16(pooled) &&
+      (((uintptr_t)argmax) & 7) == 0 && (scale == nullptr || (aligned16(scale) && aligned16(shift)))) {
+    bn_relu_maxpool_h8_kernel<<<grid_for(total / 8, 256, 16), 256, 0, st>>>((const __half*)y, (__half*)pooled, argmax, n, ix, iy,
+                                                                          iz, c, px, py, pz, scale, shift, relu);
+    HCU_CHECK_LAUNCH("bn_relu_maxpool_h8");
+    return 0;
+  }
   HCU_DISPATCH_ACT(dtype_y, TY, HCU_DISPATCH_ACT(dtype_p, TP,
       bn_relu_maxpool_kernel<TY, TP><<<grid_for(total, 256), 256, 0, st>>>((const TY*)y, (TP*)pooled, argmax, n, ix,
                                                                            iy, iz, c, px, py, pz, scale, shift,
@@ -582,6 +704,18 @@ extern "C" int hcu_maxpool_bwd(const void* dpooled, int32_t dtype_dp, const uint
   HCU_CHECK_ARG(dpooled && argmax && dfull && n > 0 && c > 0 && px > 0 && py > 0 && pz > 0, "maxpool_bwd: bad args");
   const long long total = (long long)n * ix * iy * iz * c;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype_dp == HCU_F16 && dtype_df == HCU_F16 && c % 8 == 0 && aligned16(dpooled) && aligned16(dfull) &&
+      (((uintptr_t)argmax) & 7) == 0) {
+    if (ix % px || iy % py || iz % pz) {
+      cudaError_t e = cudaMemsetAsync(dfull, 0, (size_t)total * 2, st);
+      if (e != cudaSuccess) { set_error("maxpool_bwd: memset: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
+    }
+    const long long work = (long long)n * (ix / px) * (iy / py) * (iz / pz) * (c / 8);
+    maxpool_bwd_h8_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>((const __half*)dpooled, argmax, (__half*)dfull, n, ix, iy,
+                                                                   iz, c, px, py, pz);
+    HCU_CHECK_LAUNCH("maxpool_bwd_h8");
+    return 0;
+  }
   HCU_DISPATCH_ACT(dtype_dp, TDP, HCU_DISPATCH_ACT(dtype_df, TDF,
       maxpool_bwd_kernel<TDP, TDF><<<grid_for(total, 256), 256, 0, st>>>((const TDP*)dpooled, argmax, (TDF*)dfull, n,
                                                                          ix, iy, iz, c, px, py, pz)));

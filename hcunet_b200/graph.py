@@ -1,0 +1,79 @@
+"""CUDA-graph capture of a whole training step (launch-bound inner loop -> one graph launch).
+
+A README-model step is ~300 kernel launches of 5 us .. 200 us each; enqueued one by one from Python the step is
+bound by the host.  Every kernel of the library is enqueued on the caller's stream without host synchronisation
+(include/hcunet_b200.h "Conventions"), so the step -- forward, pixel-weighted loss, backward, optimiser -- can be
+captured once and replayed:
+
+    step = GraphedTrainStep(model, optimizer, loss_fn, example=(image, mask, pwl))
+    loss = step(image, mask, pwl)          # copies into the static inputs, replays, returns the (static) loss
+
+The reference has nothing comparable (its loop is `tests/r_unet_test.py:24-56`: eager PyTorch, one op at a time).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+
+
+class GraphedTrainStep:
+    """zero_grad -> model(image) -> loss_fn(logits, mask, pwl) -> backward [-> grad_sync] -> optimizer.step.
+
+    ``grad_sync`` (e.g. ``GradSync.allreduce``) runs eagerly between two graphs (forward/backward and optimiser)
+    so that the collective is not captured; without it everything is ONE graph.  The optimizer must be
+    capture-safe (``torch.optim.Adam(..., fused=True, capturable=True)``).
+    """
+
+    def __init__(self, model, optimizer, loss_fn: Callable, example: Sequence[torch.Tensor],
+                 grad_sync: Optional[Callable] = None, warmup: int = 3):
+        self.model, self.optimizer, self.loss_fn, self.grad_sync = model, optimizer, loss_fn, grad_sync
+        self.static_in = [torch.empty_like(t, device=t.device) for t in example]
+        for s, t in zip(self.static_in, example):
+            s.copy_(t)
+        self.loss = None
+        # warm-up on a side stream (allocator, lazy attribute setting, optimizer state) as CUDA graphs require
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._fwd_bwd()
+                if grad_sync is not None:
+                    grad_sync()
+                optimizer.step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.g_main = torch.cuda.CUDAGraph()
+        self.g_opt = None
+        if grad_sync is None:
+            with torch.cuda.graph(self.g_main):
+                self._fwd_bwd()
+                optimizer.step()
+        else:
+            with torch.cuda.graph(self.g_main):
+                self._fwd_bwd()
+            self.g_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_opt, pool=self.g_main.pool()):
+                optimizer.step()
+
+    def _fwd_bwd(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        logits = self.model(self.static_in[0])
+        self.loss = self.loss_fn(logits, *self.static_in[1:])
+        self.loss.backward()
+
+    def load(self, *tensors, non_blocking=True):
+        """Copy one step's inputs (device or pinned-host tensors) into the static input buffers."""
+        for s, t in zip(self.static_in, tensors):
+            s.copy_(t, non_blocking=non_blocking)
+
+    def run(self):
+        self.g_main.replay()
+        if self.g_opt is not None:
+            self.grad_sync()
+            self.g_opt.replay()
+        return self.loss
+
+    def __call__(self, *tensors):
+        self.load(*tensors)
+        return self.run()

@@ -226,3 +226,48 @@ def test_wgrad_tc_fused_input_bn_relu():
     assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)
     simt = run_wgrad(x, dy, (3, 3, 2), in_affine=(sc, sh), use_simt=True)
     assert rel_l2(simt, ref) <= 1e-3   # the FFMA kernel does not round the transformed activation to fp16
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 9, 7, 5), (1, 16, 12, 10, 6), (1, 32, 5, 8, 3)])
+def test_fp16_vector_maxpool_matches_aten(shape):
+    """The 16-byte fp16 pool kernels: fused BN+ReLU, first-maximum tie rule, remainder rows get zero gradient."""
+    from hcunet_b200 import _lib
+
+    lib = _lib.load()
+    n, c, ix, iy, iz = shape
+    g = torch.Generator().manual_seed(sum(shape))
+    # values chosen so that x * sc + sh is exact in fp32 and fp16 (fma == mul + add): the comparison is bit-exact
+    x = h16(torch.randint(-3, 4, shape, generator=g).float() * 0.5)
+    sc = torch.tensor([0.5, 1.0, 2.0])[torch.randint(0, 3, (c,), generator=g)]
+    sh = torch.randint(-2, 3, (c,), generator=g).float() * 0.25
+    a = F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
+    a16 = h16(a).requires_grad_(True)   # pooled values are stored in fp16; ties decided on the fp32 values
+    ref, _ = F.max_pool3d(a.requires_grad_(True), (2, 2, 1), return_indices=True)
+    ox, oy, oz = ix // 2, iy // 2, iz
+    cl = to_cl(x)
+    pooled = torch.empty((n, ox, oy, oz, c), dtype=torch.float16, device="cuda")
+    arg = torch.empty((n, ox, oy, oz, c), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.hcu_bn_relu_maxpool(P(cl), _lib.F16, P(pooled), _lib.F16, P(arg), n, ix, iy, iz, c, 2, 2, 1,
+                                       P(sc.cuda()), P(sh.cuda()), 1, stream()))
+    assert torch.equal(from_cl(pooled), h16(ref.detach()))
+    go = h16(torch.randn(ref.shape, generator=g))
+    ref.backward(go)
+    dfull = torch.full((n, ix, iy, iz, c), float("nan"), dtype=torch.float16, device="cuda")
+    _lib.check(lib.hcu_maxpool_bwd(P(to_cl(go)), _lib.F16, P(arg), P(dfull), _lib.F16, n, ix, iy, iz, c, 2, 2, 1,
+                                   stream()))
+    want = a.grad
+    assert torch.equal(from_cl(dfull), want)
+
+
+def test_input_layout_kernel_pads_channels():
+    from hcunet_b200 import _lib
+
+    lib = _lib.load()
+    x = torch.randn(2, 4, 6, 5, 3)
+    dst = torch.full((2, 6 * 5 * 3, 8), float("nan"), dtype=torch.float16, device="cuda")
+    for src in (x.cuda(), x.half().cuda()):
+        _lib.check(lib.hcu_nc_to_cl(P(src), _lib.F32 if src.dtype == torch.float32 else _lib.F16, P(dst), _lib.F16, 2, 4,
+                                    90, 8, None, stream()))
+        got = dst.view(2, 6, 5, 3, 8).cpu().float()
+        assert torch.equal(got[..., :4], x.half().float().permute(0, 2, 3, 4, 1))
+        assert torch.equal(got[..., 4:], torch.zeros(2, 6, 5, 3, 4))

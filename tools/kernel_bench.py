@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Times single kernels at the README model's layer shapes (CUDA events, L2 flushed between launches).
+
+    python tools/kernel_bench.py conv  [layer ...]     # tcgen05 forward conv
+    python tools/kernel_bench.py wgrad [layer ...]     # tensor-core weight gradient
+    python tools/kernel_bench.py conv d0.conv2 --once  # one launch (for ncu)
+"""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hcunet_b200 import _lib  # noqa: E402
+from hcunet_b200.engine import conv_desc  # noqa: E402
+
+B = 4
+# name: (cin, cout, in size, kernel)   -- bench shape: batch 4 of 4x256x256x32
+LAYERS = {
+    "d0.conv1": (8, 8, (256, 256, 32), (3, 3, 2)),
+    "d0.conv2": (8, 8, (254, 254, 31), (3, 3, 1)),
+    "d1.conv1": (8, 16, (126, 126, 31), (3, 3, 2)),
+    "d1.conv2": (16, 16, (124, 124, 30), (3, 3, 1)),
+    "d2.conv1": (16, 32, (61, 61, 30), (3, 3, 2)),
+    "d2.conv2": (32, 32, (59, 59, 29), (3, 3, 1)),
+    "d3.conv1": (32, 64, (28, 28, 29), (3, 3, 2)),
+    "d3.conv2": (64, 64, (26, 26, 28), (3, 3, 1)),
+    "d4.conv1": (64, 128, (12, 12, 28), (3, 3, 2)),
+    "d4.conv2": (128, 128, (10, 10, 27), (3, 3, 1)),
+    "u0.conv1": (64, 64, (16, 16, 28), (3, 3, 2)),
+    "u3.conv1": (8, 8, (72, 72, 28), (3, 3, 2)),
+}
+
+
+def P(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def main():
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    once = "--once" in sys.argv
+    notransform = "--raw" in sys.argv
+    kind = args[0] if args else "conv"
+    names = args[1:] or list(LAYERS)
+    lib = _lib.load()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
+    for name in names:
+        cin, cout, isz, k = LAYERS[name]
+        osz = tuple(isz[i] - k[i] + 1 for i in range(3))
+        x = torch.randn((B,) + isz + (cin,), device="cuda").half()
+        sc = torch.rand(cin, device="cuda") + 0.5
+        sh = torch.randn(cin, device="cuda") * 0.1
+        if notransform:
+            sc = sh = None
+        T = k[0] * k[1] * k[2]
+        nin, nout = x.numel(), B * osz[0] * osz[1] * osz[2] * cout
+        if kind == "conv":
+            d = conv_desc(_lib.F16, _lib.F16, B, isz, cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, in_relu=1)
+            w = torch.randn(T * cin * cout, device="cuda") / (T * cin) ** 0.5
+            packed = torch.empty(lib.hcu_conv_tc_packed_bytes(C.byref(d)), dtype=torch.uint8, device="cuda")
+            _lib.check(lib.hcu_conv_tc_pack(C.byref(d), P(w), P(packed), st))
+            y = torch.empty((B,) + osz + (cout,), dtype=torch.float16, device="cuda")
+            stats = torch.zeros((2, cout), dtype=torch.float64, device="cuda")
+            fn = lambda: _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), P(x), P(packed), None, P(sc), P(sh), None, None, P(y),
+                                                        P(stats), st))
+        else:
+            dy = torch.randn((B,) + osz + (cout,), device="cuda").half()
+            d = conv_desc(_lib.F16, _lib.F16, B, isz, cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, in_relu=1)
+            wacc = torch.empty(T * cin * cout, device="cuda")
+            fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
+        if once:
+            fn()
+            torch.cuda.synchronize()
+            continue
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        byt = (nin + nout) * 2
+        fl = 2 * (nout // cout) * T * cin * cout
+        print(f"{kind:5s} {name:9s} {ms*1e3:8.1f} us  {byt/ms/1e6:7.1f} GB/s  {fl/ms/1e9:7.2f} TF/s  (min {min(ts)*1e3:.1f} us)")
+
+
+if __name__ == "__main__":
+    main()
