@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 F32, BF16, F16 = 0, 1, 2
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "hcu_conv_tc_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_tc_packed_bytes": [C.POINTER(HcuConvDesc)],
     "hcu_conv_tc_pack": [C.POINTER(HcuConvDesc), P, P, P],
+    "hcu_conv_tc_pack_ref": [C.POINTER(HcuConvDesc), C.POINTER(HcuWeightMap), P, P, P],
     "hcu_conv_tc_fwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
     "hcu_conv_wgrad_partial": [C.POINTER(HcuConvDesc), P, P, P, P, P, I32, P],
     "hcu_conv_wgrad_tc_supported": [C.POINTER(HcuConvDesc)],

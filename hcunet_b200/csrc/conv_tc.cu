@@ -337,11 +337,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         }
       } else {
         int yv = yv0, zv = zv0;
-        for (int c = 0; c < nchunk; c += 4) {
-          uint4 v[4];
-          bool ok[4];
+        for (int c = 0; c < nchunk; c += 8) {
+          uint4 v[8];
+          bool ok[8];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             const int ym = yv - p.py, zm = zv - p.pz;
             ok[u] = xok && (c + u < nchunk) && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
             v[u] = make_uint4(0u, 0u, 0u, 0u);
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
             if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
           }
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 8; ++u) {
             if (c + u >= nchunk) break;
             if (xf && ok[u]) v[u] = bn_relu8(v[u], sc, sh, relu);
             *reinterpret_cast<uint4*>(dst + (size_t)(c + u) * sstep) = v[u];
@@ -550,6 +550,31 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, __half* __restrict__
   }
 }
 
+// weights straight from the reference-layout parameter (HcuWeightMap) -> fp16 [nsplit][E][Nc][8]
+__global__ void pack_tc_ref_kernel(HcuWeightMap m, const float* __restrict__ ref, __half* __restrict__ out, int KX, int KYZ,
+                                   int P, int E_tx, int Nc, int nsplit, int cin, int cout) {
+  const long long total = (long long)nsplit * KX * E_tx * Nc * 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7);
+    long long r = i >> 3;
+    const int nn = (int)(r % Nc); r /= Nc;
+    const int e = (int)(r % E_tx); r /= E_tx;
+    const int tx = (int)(r % KX);
+    const int ns = (int)(r / KX);
+    float v = 0.f;
+    if (e < KYZ * P) {
+      const int t = e / P, pl = e % P;
+      const int ci = pl * 8 + j, co = ns * Nc + nn;
+      if (ci < cin && co < cout) {
+        const long long idx = wm_index(m, ((long long)(tx * KYZ + t) * cin + ci) * cout + co);
+        v = ref[idx];
+        if (m.fold) v += ref[idx + m.fold_stride];
+      }
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-side configuration
 // ---------------------------------------------------------------------------------------------------
@@ -659,6 +684,23 @@ extern "C" int hcu_conv_tc_pack(const HcuConvDesc* d, const float* w, void* pack
   return 0;
 }
 
+extern "C" int hcu_conv_tc_pack_ref(const HcuConvDesc* d, const HcuWeightMap* m, const float* ref, void* packed,
+                                    void* stream) {
+  HCU_CHECK_ARG(d && m && ref && packed, "conv_tc_pack_ref: null pointer");
+  tc::Params p;
+  const char* why = tc::configure(d, p);
+  HCU_CHECK_ARG(why == nullptr, "conv_tc_pack_ref: unsupported descriptor (%s)", why);
+  HCU_CHECK_ARG(m->groups == 1 && m->j[0] == d->taps[0] && m->j[1] == d->taps[1] && m->j[2] == d->taps[2] &&
+                    m->na == d->cin && m->nb == d->cout,
+                "conv_tc_pack_ref: weight map does not match the descriptor");
+  const long long total = (long long)p.nsplit * p.E * p.Nc * 8;
+  int grid = (int)std::min<long long>((total + 255) / 256, 4096);
+  tc::pack_tc_ref_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*m, ref, (__half*)packed, p.KX, p.KY * p.KZ, p.P, p.E_tx,
+                                                                 p.Nc, p.nsplit, d->cin, d->cout);
+  HCU_CHECK_LAUNCH("pack_tc_ref");
+  return 0;
+}
+
 extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
                                const float* in_scale, const float* in_shift, const float* out_scale,
                                const float* out_shift, void* out, double* stats, void* stream) {
@@ -713,7 +755,7 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
   if (p.debug & 8) fprintf(stderr, "conv_tc: per_sm %d smem %d tmem %d M %d R %d Nc %d\n", per_sm, p.smem_bytes, p.tmem_cols, p.M, p.R, p.Nc);
   const long long slots = (long long)per_sm * num_sms();
   const long long base_items = (long long)p.N * p.n_runs * p.nsplit;
-  const int max_seg = std::max(1, p.OX / 6);
+  const int max_seg = p.OX;
   int best_seg = 1;
   double best_cost = 1e30;
   for (int nseg = 1; nseg <= max_seg; ++nseg) {
@@ -721,8 +763,8 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
     const int segs = (p.OX + lx - 1) / lx;
     const long long items = base_items * segs;
     const long long waves = (items + slots - 1) / slots;
-    // time ~ waves * (planes per item incl. the KX-1 warm-up planes + fixed per-CTA overhead of ~4 planes)
-    const double cost = (double)waves * (lx + (p.KX - 1) * p.dx + 4);
+    // time ~ waves * (planes per item incl. the KX-1 warm-up planes + fixed per-CTA overhead of ~3 planes)
+    const double cost = (double)waves * (lx + (p.KX - 1) * p.dx + 3);
     if (cost < best_cost - 1e-9) { best_cost = cost; best_seg = nseg; }
   }
   p.Lx = (p.OX + best_seg - 1) / best_seg;

@@ -132,17 +132,6 @@ __global__ void nc_to_cl_h8_kernel(const TS* __restrict__ src, __half* __restric
 }
 
 // ---- weights --------------------------------------------------------------------------------
-__device__ __forceinline__ long long wm_index(const HcuWeightMap& m, long long e) {
-  const int b = (int)(e % m.nb); e /= m.nb;
-  const int a = (int)(e % m.na); e /= m.na;
-  const int jz = (int)(e % m.j[2]); e /= m.j[2];
-  const int jy = (int)(e % m.j[1]); e /= m.j[1];
-  const int jx = (int)(e % m.j[0]);
-  const int g = (int)(e / m.j[0]);
-  return m.base + g * m.sg + a * m.sa + b * m.sb + (long long)(m.t0[0] + jx * m.tstep[0]) * m.st[0] +
-         (long long)(m.t0[1] + jy * m.tstep[1]) * m.st[1] + (long long)(m.t0[2] + jz * m.tstep[2]) * m.st[2];
-}
-
 __global__ void weight_gather_kernel(HcuWeightMap m, const float* __restrict__ ref, float* __restrict__ packed,
                                      long long total) {
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;

@@ -20,8 +20,6 @@
 namespace hcu {
 namespace wg {
 
-constexpr int kThreads = 128;
-constexpr int kWarps = 4;
 constexpr int kSmemLimit = 227 * 1024;
 
 struct Params {
@@ -63,17 +61,22 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, const uint
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-template <int MTC, int NTC>
-__global__ void __launch_bounds__(kThreads) wgrad_mma_kernel(const Params p) {
+// Warps are arranged WM (tile groups) x WP (pixel slices): warp (wm, wp) owns m-tiles [mt0 + wm*MTC, +MTC) x NTC n-tiles
+// and every WP-th 16-pixel block.  Few output tiles (Cout <= 16): WM = 1, the warps split the pixels; many tiles
+// (Cout >= 64): WP = 1, the warps split the tiles so the staged planes are re-used by 8x more MMAs.
+template <int MTC, int NTC, int WM, int WP>
+__global__ void __launch_bounds__(32 * WM * WP) wgrad_mma_kernel(const Params p) {
+  constexpr int kThreads = 32 * WM * WP;
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp % WM, wp = warp / WM;
 
   int item = blockIdx.x;
   const int run = item % p.n_runs; item /= p.n_runs;
   const int xs = item % p.n_xseg;
   const int n = item / p.n_xseg;
   const int mchunk = blockIdx.y % p.n_mchunk, nchunk = blockIdx.y / p.n_mchunk;
-  const int mt0 = mchunk * MTC, nt0 = nchunk * NTC;
+  const int mt0 = mchunk * (MTC * WM) + wm * MTC, nt0 = nchunk * NTC;
   const int x0 = xs * p.Lx;
   const int nout = min(p.Lx, p.OX - x0);
   const int span = (p.KX - 1) * p.dx + 1;
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_mma_kernel(const Params p) {
     uint32_t slot_addr[MTC];
 #pragma unroll
     for (int m = 0; m < MTC; ++m) slot_addr[m] = a_base + (uint32_t)(((i + a_tx[m] * p.dx) % p.R) * p.SLOT + a_off[m]);
-    for (int blk = warp; blk < nblk; blk += kWarps) {
+    for (int blk = wp; blk < nblk; blk += WP) {
       uint32_t bf[NTC][2];
 #pragma unroll
       for (int nn = 0; nn < NTC; ++nn) {
@@ -219,13 +222,33 @@ __global__ void __launch_bounds__(kThreads) wgrad_mma_kernel(const Params p) {
     __syncthreads();
   }
 
-  // ---- reduce the 4 warps in shared memory, then one atomic per element into the global accumulator ---------
-  float* red = reinterpret_cast<float*>(smem);  // [MTC*16][NTC*8]
-  constexpr int RW = NTC * 8;
-  for (int e = tid; e < MTC * 16 * RW; e += kThreads) red[e] = 0.f;
-  __syncthreads();
-  {
-    const int g = lane >> 2, t2 = (lane & 3) * 2;
+  // ---- WP > 1: reduce the pixel slices in shared memory; then one atomic per element into the global accumulator
+  auto flush = [&](int row, int col, float v) {  // row within this warp's MTC*16 rows, col within NTC*8
+    const int mt = mt0 + row / 16;
+    const int slot = 2 * mt + ((row & 15) >> 3);
+    const int co = nt0 * 8 + col;
+    if (mt < p.MTOT && slot < p.E && co < p.cout && nt0 + col / 8 < p.NTOT) {
+      const int tap = slot / p.P, pl = slot - tap * p.P;
+      const int ci = pl * 8 + (row & 7);
+      if (ci < p.cin) atomicAdd(&p.wacc[((size_t)tap * p.cin + ci) * p.cout + co], v);
+    }
+  };
+  const int g = lane >> 2, t2 = (lane & 3) * 2;
+  if (WP == 1) {
+#pragma unroll
+    for (int m = 0; m < MTC; ++m)
+#pragma unroll
+      for (int nn = 0; nn < NTC; ++nn) {
+        flush(m * 16 + g, nn * 8 + t2, acc[m][nn][0]);
+        flush(m * 16 + g, nn * 8 + t2 + 1, acc[m][nn][1]);
+        flush(m * 16 + g + 8, nn * 8 + t2, acc[m][nn][2]);
+        flush(m * 16 + g + 8, nn * 8 + t2 + 1, acc[m][nn][3]);
+      }
+  } else {
+    constexpr int RW = NTC * 8, RH = MTC * 16;
+    float* red = reinterpret_cast<float*>(smem) + wm * RH * RW;  // [WM][MTC*16][NTC*8]
+    for (int e = tid; e < WM * RH * RW; e += kThreads) reinterpret_cast<float*>(smem)[e] = 0.f;
+    __syncthreads();
 #pragma unroll
     for (int m = 0; m < MTC; ++m)
 #pragma unroll
@@ -236,24 +259,15 @@ __global__ void __launch_bounds__(kThreads) wgrad_mma_kernel(const Params p) {
         atomicAdd(r0 + 8 * RW, acc[m][nn][2]);
         atomicAdd(r0 + 8 * RW + 1, acc[m][nn][3]);
       }
-  }
-  __syncthreads();
-  for (int e = tid; e < MTC * 16 * RW; e += kThreads) {
-    const int row = e / RW, col = e - row * RW;
-    const int mt = mt0 + row / 16;
-    const int slot = 2 * mt + ((row & 15) >> 3);
-    const int co = (nt0 * 8) + col;
-    if (mt < p.MTOT && slot < p.E && co < p.cout && nt0 + col / 8 < p.NTOT) {
-      const int tap = slot / p.P, pl = slot - tap * p.P;
-      const int ci = pl * 8 + (row & 7);
-      if (ci < p.cin) atomicAdd(&p.wacc[((size_t)tap * p.cin + ci) * p.cout + co], red[e]);
-    }
+    __syncthreads();
+    // each warp group flushes its own rows (mt0 is per-wm)
+    for (int e = wp * 32 + lane; e < RH * RW; e += WP * 32) flush(e / RW, e % RW, red[e]);
   }
 }
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-static const char* configure(const HcuConvDesc* d, Params& p, int& mtc, int& ntc) {
+static const char* configure(const HcuConvDesc* d, Params& p, int& mtc, int& ntc, int& wmg, int& wpg) {
   if (d->dtype_in != HCU_F16 || d->dtype_out != HCU_F16) return "fp16 only";
   if (d->groups != 1) return "groups != 1";
   if (d->in_cpitch % 8 != 0 || d->in_c_off != 0 || d->cin > d->in_cpitch) return "input channel layout";
@@ -278,14 +292,16 @@ static const char* configure(const HcuConvDesc* d, Params& p, int& mtc, int& ntc
   p.MTOT = (p.E + 1) / 2;
   p.NTOT = Po;
   // register tile: all n-tiles up to 8 per CTA, m-tiles so that MTC * NTC <= 24
-  if (Po == 1) { mtc = 9; ntc = 1; }
-  else if (Po == 2) { mtc = 9; ntc = 2; }
-  else if (Po == 4) { mtc = 6; ntc = 4; }
-  else { mtc = 3; ntc = 8; }
-  p.n_mchunk = (p.MTOT + mtc - 1) / mtc;
+  if (Po == 1) { mtc = 9; ntc = 1; wmg = 1; wpg = 4; }
+  else if (Po == 2) { mtc = 9; ntc = 2; wmg = 1; wpg = 4; }
+  else if (Po == 4) { mtc = 6; ntc = 4; wmg = 4; wpg = 2; }
+  else { mtc = 3; ntc = 8; wmg = 8; wpg = 1; }
+  const int nthreads = 32 * wmg * wpg;
+  p.n_mchunk = (p.MTOT + mtc * wmg - 1) / (mtc * wmg);
   p.n_nchunk = (p.NTOT + ntc - 1) / ntc;
   const int halo = (p.KY - 1) * p.dy_ * p.Zv + (p.KZ - 1) * p.dz;
   const int plane_q = p.Yv * p.Zv;
+  (void)nthreads;
   const int m_cands[4] = {512, 256, 128, 64};
   for (int pass = 0; pass < 2; ++pass) {
     const int budget = pass == 0 ? 72 * 1024 : kSmemLimit;
@@ -299,7 +315,7 @@ static const char* configure(const HcuConvDesc* d, Params& p, int& mtc, int& ntc
       if (Po > 1) { const int g = Po >= 8 ? 16 : 128 / Po; dps = round_up(dps, 2 * g) + g; }
       const int slot = ps * P;
       const int off_dy = round_up(p.R * slot, 128);
-      const int total = std::max(off_dy + dps * Po, mtc * 16 * ntc * 8 * 4) + 128;
+      const int total = std::max(off_dy + dps * Po, wpg > 1 ? wmg * mtc * 16 * ntc * 8 * 4 : 0) + 128;
       if (total > budget) continue;
       p.M = M; p.RUN = run; p.PS = ps; p.SLOT = slot; p.DPS = dps; p.off_dy = off_dy; p.smem_bytes = total;
       p.n_runs = (plane_q + M - 1) / M;
@@ -309,9 +325,10 @@ static const char* configure(const HcuConvDesc* d, Params& p, int& mtc, int& ntc
   return "does not fit in shared memory";
 }
 
-template <int MTC, int NTC>
+template <int MTC, int NTC, int WM, int WP>
 static int launch(const Params& p, cudaStream_t st) {
-  auto kern = wgrad_mma_kernel<MTC, NTC>;
+  auto kern = wgrad_mma_kernel<MTC, NTC, WM, WP>;
+  constexpr int kThreads = 32 * WM * WP;
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
@@ -334,8 +351,8 @@ using namespace hcu;
 extern "C" int hcu_conv_wgrad_tc_supported(const HcuConvDesc* d) {
   if (d == nullptr) return 0;
   wg::Params p;
-  int a, b;
-  return wg::configure(d, p, a, b) == nullptr ? 1 : 0;
+  int a, b, c, e;
+  return wg::configure(d, p, a, b, c, e) == nullptr ? 1 : 0;
 }
 
 extern "C" int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
@@ -343,8 +360,8 @@ extern "C" int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const floa
   HCU_CHECK_ARG(d && a && dy && wacc, "wgrad_tc: null pointer");
   HCU_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr), "wgrad_tc: a_scale/a_shift must come together");
   wg::Params p;
-  int mtc, ntc;
-  const char* why = wg::configure(d, p, mtc, ntc);
+  int mtc, ntc, wmg, wpg;
+  const char* why = wg::configure(d, p, mtc, ntc, wmg, wpg);
   if (why != nullptr) {
     set_error("wgrad_tc: unsupported descriptor (%s)", why);
     return HCU_ERR_UNSUPPORTED;
@@ -361,8 +378,8 @@ extern "C" int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const floa
   nseg = std::max(1, std::min(nseg, (p.OX + 3) / 4));
   p.Lx = (p.OX + nseg - 1) / nseg;
   p.n_xseg = (p.OX + p.Lx - 1) / p.Lx;
-  if (mtc == 9 && ntc == 1) return wg::launch<9, 1>(p, st);
-  if (mtc == 9 && ntc == 2) return wg::launch<9, 2>(p, st);
-  if (mtc == 6 && ntc == 4) return wg::launch<6, 4>(p, st);
-  return wg::launch<3, 8>(p, st);
+  if (mtc == 9 && ntc == 1) return wg::launch<9, 1, 1, 4>(p, st);
+  if (mtc == 9 && ntc == 2) return wg::launch<9, 2, 1, 4>(p, st);
+  if (mtc == 6 && ntc == 4) return wg::launch<6, 4, 4, 2>(p, st);
+  return wg::launch<3, 8, 8, 1>(p, st);
 }

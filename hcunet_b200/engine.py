@@ -249,26 +249,30 @@ class UnetEngine:
         _lib.check(self.lib.hcu_weight_gather(C.byref(wm), _ptr(ref), _ptr(out), self._stream()), "weight_gather")
         return out
 
-    def _conv(self, d, x, w, bias=None, out=None, stats=None, in_scale=None, in_shift=None, out_scale=None,
+    def _conv(self, d, x, wspec, bias=None, out=None, stats=None, in_scale=None, in_shift=None, out_scale=None,
               out_shift=None, layer=None):
-        """One gather-convolution launch.  w: fp32 [g][taps][cin][cout].  fp16 activations take the tcgen05 kernel
-        whenever it supports the descriptor, everything else the FFMA kernel."""
+        """One gather-convolution launch.  wspec = (HcuWeightMap, reference-layout parameter, packed element count).
+        fp16 activations take the tcgen05 kernel whenever it supports the descriptor (weights gathered, folded and
+        packed to fp16 UMMA tiles in one launch), everything else the FFMA kernel (fp32 [g][taps][cin][cout])."""
         lib = self.lib
+        wm, ref, nw = wspec
         m = d.batch * d.out_size[0] * d.out_size[1] * d.out_size[2]
         esz_i = 4 if d.dtype_in == _lib.F32 else 2
         esz_o = 4 if d.dtype_out == _lib.F32 else 2
         nin = d.batch * d.in_size[0] * d.in_size[1] * d.in_size[2] * d.cin * d.groups
-        _lib.note(layer, nin * esz_i + m * d.cout * d.groups * esz_o,
-                  2 * m * d.cout * d.groups * d.cin * d.taps[0] * d.taps[1] * d.taps[2])
+        nbytes = nin * esz_i + m * d.cout * d.groups * esz_o
+        flops = 2 * m * d.cout * d.groups * d.cin * d.taps[0] * d.taps[1] * d.taps[2]
         if self.use_tc and d.dtype_in == _lib.F16 and lib.hcu_conv_tc_supported(C.byref(d)):
             packed = torch.empty(lib.hcu_conv_tc_packed_bytes(C.byref(d)), dtype=torch.uint8, device=x.device)
-            note = _lib._ProfState.note
-            _lib.check(lib.hcu_conv_tc_pack(C.byref(d), _ptr(w), _ptr(packed), self._stream()), "conv_tc_pack")
-            _lib._ProfState.note = note
+            _lib.check(lib.hcu_conv_tc_pack_ref(C.byref(d), C.byref(wm), _ptr(ref), _ptr(packed), self._stream()),
+                       "conv_tc_pack_ref")
+            _lib.note(layer, nbytes, flops)
             _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), _ptr(x), _ptr(packed), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
                                            _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), self._stream()),
                        "conv_tc_fwd")
             return
+        w = self._gather_w(wm, ref, nw)
+        _lib.note(layer, nbytes, flops)
         _lib.check(lib.hcu_conv_fwd(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
                                     _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), self._stream()),
                    "conv_fwd")
@@ -329,6 +333,9 @@ class UnetEngine:
         xf = None  # pending (scale, shift) + ReLU to apply when `cur` is read
         saved = [] if save else None
         fold_eval = not save and not training  # inference: BN folded into the conv epilogue
+        nstat = sum(2 * g.cout_t for g in plan.steps if isinstance(g, ConvGeom) and g.bn is not None)
+        zero_ws = torch.zeros(nstat, dtype=torch.float64, device=dev) if training else None  # one memset per forward
+        zoff = 0
         logits = None
         for g in plan.steps:
             if isinstance(g, UpGeom):
@@ -338,8 +345,8 @@ class UnetEngine:
                 cur, cp, xf = out, g.cout, None
                 continue
             npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
-            w = self._gather_w(self._wm_conv_fwd(g), params[g.name + ".weight"],
-                               g.groups * g.taps[0] * g.taps[1] * g.taps[2] * g.cin_g * g.cout_g)
+            w = (self._wm_conv_fwd(g), params[g.name + ".weight"],
+                 g.groups * g.taps[0] * g.taps[1] * g.taps[2] * g.cin_g * g.cout_g)
             bias = params[g.name + ".bias"]
             isc, ish = (xf[0], xf[1]) if xf is not None else (None, None)
             if g.bn is None:  # out_conv: logits, fp32
@@ -373,7 +380,8 @@ class UnetEngine:
                 continue
             y = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
             if training:
-                stats = torch.zeros((2, g.cout_t), dtype=torch.float64, device=dev)
+                stats = zero_ws[zoff:zoff + 2 * g.cout_t].view(2, g.cout_t)
+                zoff += 2 * g.cout_t
                 self._conv(d, cur, w, bias, y, stats=stats, in_scale=isc, in_shift=ish, layer=g.name)
                 _lib.check(lib.hcu_bn_finalize(_ptr(stats), g.cout_t, float(npix), _ptr(gamma), _ptr(beta), BN_EPS,
                                                BN_MOMENTUM, _ptr(rm), _ptr(rv), _ptr(vec[0]), _ptr(vec[1]),
@@ -429,7 +437,7 @@ class UnetEngine:
         out = torch.empty((B, u.out_sz[0] * u.out_sz[1] * u.out_sz[2], u.cout), dtype=act_dtype, device=cur.device)
         isc, ish = (xf[0], xf[1]) if xf is not None else (None, None)
         for phi, J, Q in self._phases(u):
-            w = self._gather_w(self._wm_up_phase(u, phi, J), wt, J[0] * J[1] * J[2] * u.cin * u.cout)
+            w = (self._wm_up_phase(u, phi, J), wt, J[0] * J[1] * J[2] * u.cin * u.cout)
             d = conv_desc(adt, adt, B, u.in_sz, cp, 0, u.cin, u.cin, Q, u.out_sz, u.cout, 0, u.cout, 1, J,
                           pad=tuple(j - 1 for j in J), ostep=u.s, ooff=phi, in_relu=int(xf is not None))
             self._conv(d, cur, w, bias, out, in_scale=isc, in_shift=ish, layer=u.name)
@@ -467,6 +475,9 @@ class UnetEngine:
             dcur_dt = adt
         self._inv = inv
         dx = None
+        nstat = sum(2 * it[1].cout_t for it in saved if it[0] == "conv")
+        zero_ws = torch.zeros(nstat, dtype=torch.float64, device=dev)  # one memset for every BN-backward reduction
+        zoff = 0
         for item in reversed(saved):
             kind = item[0]
             if kind == "out":
@@ -487,7 +498,8 @@ class UnetEngine:
                                                    g.out_sz[1], g.out_sz[2], g.cout_t, g.pool[0], g.pool[1],
                                                    g.pool[2], st), "maxpool_bwd")
                     dcur, dcur_dt = dfull, adt
-                sums = torch.zeros((2, g.cout_t), dtype=torch.float64, device=dev)
+                sums = zero_ws[zoff:zoff + 2 * g.cout_t].view(2, g.cout_t)
+                zoff += 2 * g.cout_t
                 _lib.note(g.name, 2 * npix * g.cout_t * esz, 0)
                 _lib.check(lib.hcu_bn_bwd_stats(_ptr(dcur), dcur_dt, _ptr(y), adt, npix, g.cout_t, _ptr(vec[2]),
                                                 _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(sums), st),
@@ -544,7 +556,7 @@ class UnetEngine:
                                                   st), "weight_scatter(up)")
                 grads[u.name + ".weight"] = gw
                 # data gradient: strided gather convolution over dOut
-                w = self._gather_w(wm, params[u.name + ".weight"], total)
+                w = (wm, params[u.name + ".weight"], total)
                 dprev = torch.empty((B, u.in_sz[0] * u.in_sz[1] * u.in_sz[2], u.cin), dtype=act_dtype, device=dev)
                 d2 = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin,
                                1, u.k, istep=u.s)
@@ -599,7 +611,7 @@ class UnetEngine:
     def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype, out_cp=None):
         adt = _DT[act_dtype]
         T = g.taps[0] * g.taps[1] * g.taps[2]
-        w = self._gather_w(self._wm_conv_dgrad(g), wref, g.groups * T * g.cin_g * g.cout_g)
+        w = (self._wm_conv_dgrad(g), wref, g.groups * T * g.cin_g * g.cout_g)
         cpo = out_cp or g.cin_t
         alloc = torch.zeros if cpo != g.cin_t else torch.empty
         dprev = alloc((B, g.in_sz[0] * g.in_sz[1] * g.in_sz[2], cpo), dtype=act_dtype, device=dy.device)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 6
+#define HCU_ABI_VERSION 7
 
 typedef enum HcuStatus {
   HCU_OK = 0,
@@ -89,6 +89,8 @@ typedef struct HcuConvDesc {
   int32_t reserved[4];
 } HcuConvDesc;
 
+struct HcuWeightMap;
+
 /* W: fp32 [groups][taps][cin][cout].  bias/out_scale/out_shift: fp32 [groups*cout] or NULL.
  * in_scale/in_shift: fp32 [in_cpitch] or NULL.  stats: fp64 [2][out_cpitch] (sum, sumsq) or NULL;
  * stats see the value after bias, before out_scale/out_shift/ReLU.
@@ -105,6 +107,8 @@ int hcu_conv_fwd(const HcuConvDesc* d, const void* in, const float* W, const flo
 int hcu_conv_tc_supported(const HcuConvDesc* d);
 long long hcu_conv_tc_packed_bytes(const HcuConvDesc* d);
 int hcu_conv_tc_pack(const HcuConvDesc* d, const float* w, void* packed, void* stream);
+/* same, straight from the reference-layout parameter through a HcuWeightMap (gather + fold + fp16 pack in one launch) */
+int hcu_conv_tc_pack_ref(const HcuConvDesc* d, const struct HcuWeightMap* m, const float* ref, void* packed, void* stream);
 int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
                     const float* in_scale, const float* in_shift, const float* out_scale,
                     const float* out_shift, void* out, double* stats, void* stream);

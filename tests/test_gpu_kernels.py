@@ -241,20 +241,23 @@ def test_fp16_vector_maxpool_matches_aten(shape):
     sc = torch.tensor([0.5, 1.0, 2.0])[torch.randint(0, 3, (c,), generator=g)]
     sh = torch.randint(-2, 3, (c,), generator=g).float() * 0.25
     a = F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))
-    a16 = h16(a).requires_grad_(True)   # pooled values are stored in fp16; ties decided on the fp32 values
     ref, _ = F.max_pool3d(a.requires_grad_(True), (2, 2, 1), return_indices=True)
     ox, oy, oz = ix // 2, iy // 2, iz
     cl = to_cl(x)
     pooled = torch.empty((n, ox, oy, oz, c), dtype=torch.float16, device="cuda")
     arg = torch.empty((n, ox, oy, oz, c), dtype=torch.uint8, device="cuda")
+    scd, shd = sc.cuda(), sh.cuda()   # keep the device tensors alive while the kernel uses their pointers
     _lib.check(lib.hcu_bn_relu_maxpool(P(cl), _lib.F16, P(pooled), _lib.F16, P(arg), n, ix, iy, iz, c, 2, 2, 1,
-                                       P(sc.cuda()), P(sh.cuda()), 1, stream()))
+                                       P(scd), P(shd), 1, stream()))
+    torch.cuda.synchronize()
     assert torch.equal(from_cl(pooled), h16(ref.detach()))
     go = h16(torch.randn(ref.shape, generator=g))
     ref.backward(go)
     dfull = torch.full((n, ix, iy, iz, c), float("nan"), dtype=torch.float16, device="cuda")
-    _lib.check(lib.hcu_maxpool_bwd(P(to_cl(go)), _lib.F16, P(arg), P(dfull), _lib.F16, n, ix, iy, iz, c, 2, 2, 1,
+    gcl = to_cl(go)
+    _lib.check(lib.hcu_maxpool_bwd(P(gcl), _lib.F16, P(arg), P(dfull), _lib.F16, n, ix, iy, iz, c, 2, 2, 1,
                                    stream()))
+    torch.cuda.synchronize()
     want = a.grad
     assert torch.equal(from_cl(dfull), want)
 
