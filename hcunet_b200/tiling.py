@@ -1,0 +1,97 @@
+"""Overlap-tile inference sharded over GPUs with no communication (SURVEY.md sections 3.4, 8e; BASELINE config 5).
+
+Valid convolutions make output blocks independent: output voxels ``[a, b)`` (``a`` a multiple of the pooling
+stride ``align``, 16 for the README model) depend on input voxels ``[a, b + margin)`` only (``margin`` = 184 for the
+README model).  The tile grid over (X, Y) is partitioned across ranks; each rank runs its tiles through the model in
+``eval()`` mode and writes its blocks of the logits.  Z is never tiled: the Z up-convolution is a full correlation
+whose edge taps see implicit zeros (`unet.py:294-298`).
+
+This replaces the *sharding arithmetic* of the reference's serial tiler (`segment.py:73-126`: one tile at a time, host
+round trip per tile, GPU-memory table that has no entry for a B200); the reference's reflection padding / thresholding
+around it are out of scope this round ("next" item 1).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from .engine import plan_unet
+from .parallel import shard_range
+
+
+def tile_geometry(spec: dict) -> Tuple[int, int, int]:
+    """(align, margin_xy, margin_z): outputs at multiples of ``align`` need ``margin_xy`` more input voxels per XY
+    dim; the logits are ``margin_z`` shorter than the input in Z.  Derived from the planner, not hard-coded."""
+    dims = spec["image_dimensions"]
+    pool = spec["max_pool_kernel"]
+    pool = (pool,) * dims if isinstance(pool, int) else tuple(pool)
+    stride = spec["upsample_stride"]
+    stride = (stride,) * dims if isinstance(stride, int) else tuple(stride)
+    levels = len(spec["feature_sizes"]) - 1
+    if pool[0] != pool[1] or stride[0] != stride[1] or pool[0] != stride[0]:
+        raise NotImplementedError("tiling needs equal pooling / up-sampling strides in X and Y")
+    align = pool[0] ** levels
+    # find a consistent size: in = align * b + r  ->  out = in - margin
+    base = None
+    for n in range(align * 8, align * 40):
+        try:
+            shape = (1, spec["in_channels"], n, n) + ((8 * 4,) if dims == 3 else ())
+            p = plan_unet(spec, shape)
+        except RuntimeError:
+            continue
+        try:
+            p2 = plan_unet(spec, shape[:2] + (n + align, n + align) + shape[4:])
+        except RuntimeError:
+            continue
+        if p2.out_sz[0] - p.out_sz[0] == align:
+            base = (n, p.out_sz[0], p.out_sz[2] if dims == 3 else 1, shape[4] if dims == 3 else 1)
+            break
+    if base is None:
+        raise RuntimeError("could not find a tile size the model accepts")
+    n, out, oz, iz = base
+    return align, n - out, iz - oz
+
+
+def tile_grid(out_xy: Tuple[int, int], tile_out: int, align: int) -> List[Tuple[int, int, int, int]]:
+    """Output blocks (x0, x1, y0, y1) with origins at multiples of ``align`` covering an ``out_xy`` logit plane."""
+    if tile_out % align:
+        raise ValueError(f"tile_out must be a multiple of {align}")
+    tiles = []
+    for x0 in range(0, out_xy[0], tile_out):
+        for y0 in range(0, out_xy[1], tile_out):
+            tiles.append((x0, min(out_xy[0], x0 + tile_out), y0, min(out_xy[1], y0 + tile_out)))
+    return tiles
+
+
+def shard_tiles(tiles, world: int, rank: int):
+    lo, hi = shard_range(len(tiles), world, rank)
+    return tiles[lo:hi]
+
+
+@torch.no_grad()
+def predict_tiled(model, stack: torch.Tensor, tile_out: int = 256, world: int = 1, rank: int = 0,
+                  out: Optional[torch.Tensor] = None, device=None):
+    """Logits of this rank's share of the overlap tiles.  ``stack`` [1, C, X, Y, Z] may live on the host (pinned) or
+    on the device; returns (out, tiles) where ``out`` [1, Cout, X - margin, Y - margin, Z - mz] holds this rank's
+    blocks (zeros elsewhere; concatenating / summing the ranks' outputs needs no reduction of overlapping data)."""
+    spec = model.model_specification
+    if spec["image_dimensions"] != 3:
+        raise NotImplementedError("predict_tiled handles 3D stacks")
+    if model.training:
+        raise RuntimeError("tiled inference needs model.eval(): batch statistics differ per tile")
+    align, margin, mz = tile_geometry(spec)
+    X, Y, Z = stack.shape[2:]
+    # only whole `align` blocks are produced: a caller with a ragged stack pads it first (the reference pads every
+    # stack with reflections before tiling, `segment.py:70`)
+    ox, oy = (X - margin) // align * align, (Y - margin) // align * align
+    if ox <= 0 or oy <= 0:
+        raise RuntimeError(f"stack {tuple(stack.shape)} is smaller than the receptive field ({margin} + {align})")
+    device = device or next(model.parameters()).device
+    tiles = shard_tiles(tile_grid((ox, oy), tile_out, align), world, rank)
+    if out is None:
+        out = torch.zeros((1, spec["out_channels"], ox, oy, Z - mz), dtype=torch.float32, device=device)
+    for (x0, x1, y0, y1) in tiles:
+        xin = stack[:, :, x0:x1 + margin, y0:y1 + margin, :]
+        out[:, :, x0:x1, y0:y1] = model(xin.to(device, non_blocking=True))
+    return out, tiles

@@ -295,3 +295,32 @@ def test_skip_connection_is_dead_like_the_reference():
     with torch.no_grad():
         a, b = m(fx["x"].cuda()), m2(fx["x"].cuda())
     assert rel_l2(a, b) <= 1e-6
+
+
+def test_tiled_inference_equals_monolithic_and_shards_without_overlap():
+    """Valid convs make overlap tiles independent: tiles sharded over 3 emulated ranks, no collective."""
+    import hcunet_b200 as H
+    from hcunet_b200.tiling import predict_tiled, tile_geometry, tile_grid
+
+    fx = load_golden("g3d_small")
+    m = build(fx, "fp32").eval()
+    align, margin, mz = tile_geometry(m.model_specification)
+    g = torch.Generator().manual_seed(8)
+    stack = torch.randn((1, 4, margin + 8 * align + 5, margin + 6 * align, 7), generator=g).pin_memory()
+    with torch.no_grad():
+        # monolithic reference on the aligned part + the CPU oracle
+        whole = m(stack[:, :, : margin + 8 * align, :, :].cuda())
+        want, _ = O.unet_forward(fx["state_dict"], fx["kwargs"], stack[:, :, : margin + 8 * align], training=False)
+    assert rel_l2(whole, want) <= 1e-5
+    total = None
+    seen = 0
+    for r in range(3):
+        out, tiles = predict_tiled(m, stack, tile_out=3 * align, world=3, rank=r)
+        seen += len(tiles)
+        total = out if total is None else total + out
+    assert seen == len(tile_grid((8 * align, 6 * align), 3 * align, align)) == 6
+    assert total.shape[2] == 8 * align and total.shape[4] == 7 - mz   # the ragged +5 rows are not produced
+    assert rel_l2(total[:, :, : 8 * align], want) <= 1e-5
+    m.train()
+    with pytest.raises(RuntimeError):
+        predict_tiled(m, stack)
