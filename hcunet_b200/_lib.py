@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 F32, BF16, F16 = 0, 1, 2
 
@@ -35,6 +35,10 @@ class HcuWeightMap(C.Structure):
         ("base", C.c_int64), ("sg", C.c_int64), ("sa", C.c_int64), ("sb", C.c_int64), ("st", C.c_int64 * 3),
         ("t0", C.c_int32 * 3), ("tstep", C.c_int32 * 3), ("fold", C.c_int32), ("fold_stride", C.c_int64),
     ]
+
+
+class HcuPoolGeom(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("n", "ix", "iy", "iz", "px", "py", "pz")]
 
 
 class HcuLossDesc(C.Structure):
@@ -73,9 +77,9 @@ SIGNATURES = {
     "hcu_bn_relu_apply": [P, I32, P, I32, I64, I32, P, P, I32, P],
     "hcu_bn_relu_maxpool": [P, I32, P, I32, P, I32, I32, I32, I32, I32, I32, I32, I32, P, P, I32, P],
     "hcu_maxpool_bwd": [P, I32, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
-    "hcu_bn_bwd_stats": [P, I32, P, I32, I64, I32, P, P, P, P, I32, P, P],
+    "hcu_bn_bwd_stats": [P, I32, P, I32, I64, I32, P, P, P, P, I32, P, C.POINTER(HcuPoolGeom), P, P],
     "hcu_bn_bwd_finalize": [P, I32, D, P, P, P, I32, F, P, P, P, P, P, P],
-    "hcu_bn_bwd_apply": [P, I32, P, I32, P, I32, I64, I32, P, P, I32, P, P],
+    "hcu_bn_bwd_apply": [P, I32, P, I32, P, I32, I64, I32, P, P, I32, P, P, C.POINTER(HcuPoolGeom), P],
     "hcu_colsum": [P, I32, I64, I32, I32, I32, F, P, P, P, P],
     "hcu_wbce_fwd": [C.POINTER(HcuLossDesc), P, P, P, P, P, P],
     "hcu_wbce_bwd": [C.POINTER(HcuLossDesc), P, P, P, P, F, P, P, P],

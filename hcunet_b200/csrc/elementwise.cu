@@ -375,6 +375,132 @@ __global__ void maxpool_bwd_kernel(const TDP* __restrict__ dpooled, const uint8_
   }
 }
 
+// ---- fp16, 8 channels per thread (16-byte accesses); optional fused max-pool backward -------------------------
+// When `argmax` is given, `da` is the gradient of the POOLED tensor: the gradient of voxel (x,y,z) is
+// dpooled[window] if this voxel was the window's argmax, else 0 (nothing full-resolution is materialised).
+struct PoolGeom { int n, ix, iy, iz, px, py, pz, ox, oy, oz; };
+
+__device__ __forceinline__ void load_g8(const __half* __restrict__ da, const uint8_t* __restrict__ argmax, const PoolGeom& pg,
+                                        long long pix, int cg, int c, float* g) {
+  uint4 raw;
+  if (argmax == nullptr) {
+    raw = *reinterpret_cast<const uint4*>(da + pix * c + cg * 8);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); g[2 * j] = f.x; g[2 * j + 1] = f.y; }
+    return;
+  }
+  long long r = pix;
+  const int z = (int)(r % pg.iz); r /= pg.iz;
+  const int y = (int)(r % pg.iy); r /= pg.iy;
+  const int x = (int)(r % pg.ix);
+  const long long b = r / pg.ix;
+  const int qx = x / pg.px, qy = y / pg.py, qz = z / pg.pz;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (qx >= pg.ox || qy >= pg.oy || qz >= pg.oz) return;
+  const long long pe = (((b * pg.ox + qx) * pg.oy + qy) * pg.oz + qz) * c + cg * 8;
+  const uint32_t w = (uint32_t)(((x - qx * pg.px) * pg.py + (y - qy * pg.py)) * pg.pz + (z - qz * pg.pz));
+  raw = *reinterpret_cast<const uint4*>(da + pe);
+  const uint2 a = *reinterpret_cast<const uint2*>(argmax + pe);
+  const __half* h = reinterpret_cast<const __half*>(&raw);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+    if (aj == w) g[j] = __half2float(h[j]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __restrict__ da, const __half* __restrict__ y,
+                                                             long long npix, int c, const float* __restrict__ scale,
+                                                             const float* __restrict__ shift, const float* __restrict__ mean,
+                                                             const float* __restrict__ invstd, int relu,
+                                                             const uint8_t* __restrict__ argmax, PoolGeom pg,
+                                                             double* __restrict__ sums) {
+  extern __shared__ float sh[];  // [2][c]
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int c8 = c >> 3;
+  const long long total = npix * c8, stride = (long long)gridDim.x * blockDim.x;  // stride % c8 == 0 (c8 | 256)
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cg = (int)(e % c8);
+  float sc[8], sf[8], mu[8], is[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[cg * 8 + j]; sf[j] = shift[cg * 8 + j]; mu[j] = mean[cg * 8 + j]; is[j] = invstd[cg * 8 + j];
+    s1[j] = 0.f; s2[j] = 0.f;
+  }
+  for (; e < total; e += stride) {
+    const long long pix = e / c8;
+    const uint4 yr = *reinterpret_cast<const uint4*>(y + pix * c + cg * 8);
+    float g[8];
+    load_g8(da, argmax, pg, pix, cg, c, g);
+    const __half2* yh = reinterpret_cast<const __half2*>(&yr);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 yv = __half22float2(yh[j]);
+      float g0 = g[2 * j], g1 = g[2 * j + 1];
+      if (relu && fmaf(yv.x, sc[2 * j], sf[2 * j]) <= 0.f) g0 = 0.f;
+      if (relu && fmaf(yv.y, sc[2 * j + 1], sf[2 * j + 1]) <= 0.f) g1 = 0.f;
+      s1[2 * j] += g0; s1[2 * j + 1] += g1;
+      s2[2 * j] = fmaf(g0, (yv.x - mu[2 * j]) * is[2 * j], s2[2 * j]);
+      s2[2 * j + 1] = fmaf(g1, (yv.y - mu[2 * j + 1]) * is[2 * j + 1], s2[2 * j + 1]);
+    }
+  }
+  // lanes l and l' hold the same channel group when l = l' (mod c8): butterfly over the other lane bits first
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    for (int off = 16; off >= c8; off >>= 1) {
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+    }
+  }
+  if ((threadIdx.x & 31) < c8 || c8 > 16) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[cg * 8 + j], s1[j]);
+      atomicAdd(&sh[c + cg * 8 + j], s2[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) atomicAdd(&sums[i], (double)sh[i]);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_h8_kernel(const __half* __restrict__ da, const __half* __restrict__ y,
+                                                             __half* __restrict__ dy, long long npix, int c,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             int relu, const float* __restrict__ coef,
+                                                             const uint8_t* __restrict__ argmax, PoolGeom pg) {
+  const int c8 = c >> 3;
+  const long long total = npix * c8, stride = (long long)gridDim.x * blockDim.x;
+  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cg = (int)(e % c8);
+  float sc[8], sf[8], c1[8], c2[8], c3[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[cg * 8 + j]; sf[j] = shift[cg * 8 + j];
+    c1[j] = coef[cg * 8 + j]; c2[j] = coef[c + cg * 8 + j]; c3[j] = coef[2 * c + cg * 8 + j];
+  }
+  for (; e < total; e += stride) {
+    const long long pix = e / c8;
+    const uint4 yr = *reinterpret_cast<const uint4*>(y + pix * c + cg * 8);
+    float g[8];
+    load_g8(da, argmax, pg, pix, cg, c, g);
+    const __half2* yh = reinterpret_cast<const __half2*>(&yr);
+    __half2 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 yv = __half22float2(yh[j]);
+      float g0 = g[2 * j], g1 = g[2 * j + 1];
+      if (relu && fmaf(yv.x, sc[2 * j], sf[2 * j]) <= 0.f) g0 = 0.f;
+      if (relu && fmaf(yv.y, sc[2 * j + 1], sf[2 * j + 1]) <= 0.f) g1 = 0.f;
+      o[j] = __floats2half2_rn(fmaf(c1[2 * j], g0, fmaf(c2[2 * j], yv.x, c3[2 * j])),
+                               fmaf(c1[2 * j + 1], g1, fmaf(c2[2 * j + 1], yv.y, c3[2 * j + 1])));
+    }
+    *reinterpret_cast<uint4*>(dy + pix * c + cg * 8) = *reinterpret_cast<uint4*>(o);
+  }
+}
+
 // pass 1 of BN(+ReLU) backward: per-channel sums of g and g*xhat.
 // Each thread walks pixels for a fixed channel group so per-thread partials stay in registers.
 template <typename TD, typename TY>
@@ -712,11 +838,31 @@ extern "C" int hcu_maxpool_bwd(const void* dpooled, int32_t dtype_dp, const uint
   return 0;
 }
 
+static int fill_pool(const HcuPoolGeom* g, int64_t npix, PoolGeom& pg, const char* who) {
+  HCU_CHECK_ARG(g != nullptr && g->n > 0 && g->px > 0 && g->py > 0 && g->pz > 0, "%s: bad pool geometry", who);
+  HCU_CHECK_ARG((int64_t)g->n * g->ix * g->iy * g->iz == npix, "%s: pool geometry does not match npix", who);
+  pg.n = g->n; pg.ix = g->ix; pg.iy = g->iy; pg.iz = g->iz; pg.px = g->px; pg.py = g->py; pg.pz = g->pz;
+  pg.ox = g->ix / g->px; pg.oy = g->iy / g->py; pg.oz = g->iz / g->pz;
+  return 0;
+}
+
 extern "C" int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix,
                                 int32_t c, const float* scale, const float* shift, const float* mean,
-                                const float* invstd, int32_t relu, double* sums, void* stream) {
+                                const float* invstd, int32_t relu, const uint8_t* argmax, const HcuPoolGeom* pool,
+                                double* sums, void* stream) {
   HCU_CHECK_ARG(da && y && scale && shift && mean && invstd && sums && npix > 0 && c > 0, "bn_bwd_stats: bad args");
   HCU_CHECK_ARG(c <= 4096, "bn_bwd_stats: too many channels");
+  if (dtype_da == HCU_F16 && dtype_y == HCU_F16 && c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0 && aligned16(da) && aligned16(y) &&
+      (argmax == nullptr || (((uintptr_t)argmax) & 7) == 0)) {
+    PoolGeom pg = {};
+    if (argmax != nullptr) { int rc = fill_pool(pool, npix, pg, "bn_bwd_stats"); if (rc) return rc; }
+    const int grid = grid_for(npix * (c / 8), 256 * 4, 8);
+    bn_bwd_stats_h8_kernel<<<grid, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+        (const __half*)da, (const __half*)y, npix, c, scale, shift, mean, invstd, relu, argmax, pg, sums);
+    HCU_CHECK_LAUNCH("bn_bwd_stats_h8");
+    return 0;
+  }
+  HCU_CHECK_ARG(argmax == nullptr, "bn_bwd_stats: the fused max-pool backward needs fp16 tensors with c %% 8 == 0");
   const long long total = npix * c;
   int threads, grid;
   channel_fixed_geometry(total, c, threads, grid);
@@ -742,8 +888,20 @@ extern "C" int hcu_bn_bwd_finalize(const double* sums, int32_t c, double count, 
 
 extern "C" int hcu_bn_bwd_apply(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, void* dy,
                                 int32_t dtype_dy, int64_t npix, int32_t c, const float* scale, const float* shift,
-                                int32_t relu, const float* coef, void* stream) {
+                                int32_t relu, const float* coef, const uint8_t* argmax, const HcuPoolGeom* pool,
+                                void* stream) {
   HCU_CHECK_ARG(da && y && dy && scale && shift && coef && npix > 0 && c > 0, "bn_bwd_apply: bad args");
+  if (dtype_da == HCU_F16 && dtype_y == HCU_F16 && dtype_dy == HCU_F16 && c % 8 == 0 && 256 % (c / 8) == 0 && aligned16(da) &&
+      aligned16(y) && aligned16(dy) && (argmax == nullptr || (((uintptr_t)argmax) & 7) == 0)) {
+    PoolGeom pg = {};
+    if (argmax != nullptr) { int rc = fill_pool(pool, npix, pg, "bn_bwd_apply"); if (rc) return rc; }
+    const int grid = grid_for(npix * (c / 8), 256 * 2, 16);
+    bn_bwd_apply_h8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)da, (const __half*)y, (__half*)dy, npix, c,
+                                                                   scale, shift, relu, coef, argmax, pg);
+    HCU_CHECK_LAUNCH("bn_bwd_apply_h8");
+    return 0;
+  }
+  HCU_CHECK_ARG(argmax == nullptr, "bn_bwd_apply: the fused max-pool backward needs fp16 tensors with c %% 8 == 0");
   const long long total = npix * c;
   const bool vec = (c % 4 == 0) && aligned16(da) && aligned16(y) && aligned16(dy) && aligned16(scale) &&
                    aligned16(shift) && aligned16(coef);

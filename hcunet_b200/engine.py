@@ -491,7 +491,13 @@ class UnetEngine:
             elif kind == "conv":
                 _, g, a_in, a_cp, a_xf, y, vec, argmax = item
                 npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
-                if argmax is not None:
+                pool_arg, pool_geom = None, None
+                if (argmax is not None and act_dtype == torch.float16 and g.cout_t % 8 == 0 and 256 % (g.cout_t // 8) == 0
+                        and dcur_dt == _lib.F16):
+                    # fp16: the max-pool backward is fused into the two BN-backward passes (no full-resolution dA)
+                    pool_arg = argmax
+                    pool_geom = _lib.HcuPoolGeom(B, g.out_sz[0], g.out_sz[1], g.out_sz[2], g.pool[0], g.pool[1], g.pool[2])
+                elif argmax is not None:
                     dfull = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
                     _lib.note(g.name, dcur.numel() * (esz + 1) + dfull.numel() * esz, 0)
                     _lib.check(lib.hcu_maxpool_bwd(_ptr(dcur), dcur_dt, _ptr(argmax), _ptr(dfull), adt, B, g.out_sz[0],
@@ -502,7 +508,8 @@ class UnetEngine:
                 zoff += 2 * g.cout_t
                 _lib.note(g.name, 2 * npix * g.cout_t * esz, 0)
                 _lib.check(lib.hcu_bn_bwd_stats(_ptr(dcur), dcur_dt, _ptr(y), adt, npix, g.cout_t, _ptr(vec[2]),
-                                                _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(sums), st),
+                                                _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(pool_arg),
+                                                C.byref(pool_geom) if pool_geom is not None else None, _ptr(sums), st),
                            "bn_bwd_stats")
                 dgamma = torch.empty(g.cout_t, dtype=torch.float32, device=dev)
                 dbeta = torch.empty_like(dgamma)
@@ -515,7 +522,8 @@ class UnetEngine:
                 dy = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
                 _lib.note(g.name, 3 * npix * g.cout_t * esz, 0)
                 _lib.check(lib.hcu_bn_bwd_apply(_ptr(dcur), dcur_dt, _ptr(y), adt, _ptr(dy), adt, npix, g.cout_t,
-                                                _ptr(vec[2]), _ptr(vec[3]), 1, _ptr(coef), st), "bn_bwd_apply")
+                                                _ptr(vec[2]), _ptr(vec[3]), 1, _ptr(coef), _ptr(pool_arg),
+                                                C.byref(pool_geom) if pool_geom is not None else None, st), "bn_bwd_apply")
                 grads[g.bn + ".weight"], grads[g.bn + ".bias"], grads[g.name + ".bias"] = dgamma, dbeta, dbias
                 grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, a_cp, a_xf, adt, dy, adt, B,
                                                              params[g.name + ".weight"])

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 7
+#define HCU_ABI_VERSION 8
 
 typedef enum HcuStatus {
   HCU_OK = 0,
@@ -184,20 +184,24 @@ int hcu_bn_relu_maxpool(const void* y, int32_t dtype_y, void* pooled, int32_t dt
 int hcu_maxpool_bwd(const void* dpooled, int32_t dtype_dp, const uint8_t* argmax, void* dfull, int32_t dtype_df,
                     int32_t n, int32_t ix, int32_t iy, int32_t iz, int32_t c, int32_t px, int32_t py, int32_t pz,
                     void* stream);
+/* geometry of the max-pool that followed a BN+ReLU block (kernel == stride): [n][ix][iy][iz] -> [n][ix/px][iy/py][iz/pz] */
+typedef struct HcuPoolGeom { int32_t n, ix, iy, iz, px, py, pz; } HcuPoolGeom;
 /* BatchNorm+ReLU backward, pass 1: g = da * [y*scale+shift > 0 or !relu];
- * sums[0][c] += sum g, sums[1][c] += sum g*(y-mean)*invstd   (fp64). */
+ * sums[0][c] += sum g, sums[1][c] += sum g*(y-mean)*invstd   (fp64).
+ * Fused max-pool backward (fp16, c % 8 == 0): when `argmax` != NULL, `da` is the gradient of the POOLED tensor and
+ * `pool` its geometry; the full-resolution gradient (hcu_maxpool_bwd's output) is formed on the fly. */
 int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix, int32_t c,
                      const float* scale, const float* shift, const float* mean, const float* invstd,
-                     int32_t relu, double* sums, void* stream);
+                     int32_t relu, const uint8_t* argmax, const HcuPoolGeom* pool, double* sums, void* stream);
 /* pass 2 (tiny): dgamma, dbeta, conv-bias grad and the coefficients of dy = c1*g + c2*y + c3.
  * training != 0: batch-stat backward; training == 0: running-stat (eval) backward. */
 int hcu_bn_bwd_finalize(const double* sums, int32_t c, double count, const float* gamma, const float* mean,
                         const float* invstd, int32_t training, float grad_scale, const float* dscale, float* dgamma,
                         float* dbeta, float* dbias, float* coef, void* stream);
-/* pass 3: dy = c1[c]*g + c2[c]*y + c3[c]. */
+/* pass 3: dy = c1[c]*g + c2[c]*y + c3[c]  (same optional fused max-pool backward). */
 int hcu_bn_bwd_apply(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, void* dy, int32_t dtype_dy,
                      int64_t npix, int32_t c, const float* scale, const float* shift, int32_t relu,
-                     const float* coef, void* stream);
+                     const float* coef, const uint8_t* argmax, const HcuPoolGeom* pool, void* stream);
 /* out[c] (+)= scale * sum over pixels of x[pix][c_off + c]  (bias gradients of convT / out_conv). */
 int hcu_colsum(const void* x, int32_t dtype_x, int64_t npix, int32_t cpitch, int32_t c_off, int32_t c,
                float scale, const float* dscale, double* scratch, float* out, void* stream);
