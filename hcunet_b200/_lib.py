@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 F32, BF16, F16 = 0, 1, 2
 
@@ -25,7 +25,8 @@ class HcuConvDesc(C.Structure):
         ("out_c_off", C.c_int32), ("cout", C.c_int32), ("groups", C.c_int32),
         ("taps", C.c_int32 * 3), ("dil", C.c_int32 * 3), ("pad", C.c_int32 * 3),
         ("istep", C.c_int32 * 3), ("ostep", C.c_int32 * 3), ("ooff", C.c_int32 * 3),
-        ("in_relu", C.c_int32), ("out_relu", C.c_int32), ("reserved", C.c_int32 * 4),
+        ("in_relu", C.c_int32), ("out_relu", C.c_int32), ("ophase", C.c_int32), ("iphase", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -34,6 +35,7 @@ class HcuWeightMap(C.Structure):
         ("groups", C.c_int32), ("j", C.c_int32 * 3), ("na", C.c_int32), ("nb", C.c_int32),
         ("base", C.c_int64), ("sg", C.c_int64), ("sa", C.c_int64), ("sb", C.c_int64), ("st", C.c_int64 * 3),
         ("t0", C.c_int32 * 3), ("tstep", C.c_int32 * 3), ("fold", C.c_int32), ("fold_stride", C.c_int64),
+        ("phase_on", C.c_int32), ("ph", C.c_int32 * 3), ("pst", C.c_int64 * 3),
     ]
 
 

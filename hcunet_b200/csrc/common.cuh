@@ -96,13 +96,23 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // element e of a packed [g][jx][jy][jz][a][b] weight tensor -> index into the reference-layout parameter
 __device__ __forceinline__ long long wm_index(const HcuWeightMap& m, long long e) {
-  const int b = (int)(e % m.nb); e /= m.nb;
-  const int a = (int)(e % m.na); e /= m.na;
+  const int nph = m.phase_on ? m.ph[0] * m.ph[1] * m.ph[2] : 1;
+  const int nbf = m.phase_on == 2 ? m.nb * nph : m.nb, naf = m.phase_on == 1 ? m.na * nph : m.na;
+  int b = (int)(e % nbf); e /= nbf;
+  int a = (int)(e % naf); e /= naf;
   const int jz = (int)(e % m.j[2]); e /= m.j[2];
   const int jy = (int)(e % m.j[1]); e /= m.j[1];
   const int jx = (int)(e % m.j[0]);
   const int g = (int)(e / m.j[0]);
-  return m.base + g * m.sg + a * m.sa + b * m.sb + (long long)(m.t0[0] + jx * m.tstep[0]) * m.st[0] +
+  long long idx = m.base;
+  if (m.phase_on) {
+    int phi;
+    if (m.phase_on == 1) { phi = a / m.na; a -= phi * m.na; } else { phi = b / m.nb; b -= phi * m.nb; }
+    const int pz = phi % m.ph[2]; phi /= m.ph[2];
+    const int py = phi % m.ph[1], px = phi / m.ph[1];
+    idx += px * m.pst[0] + py * m.pst[1] + pz * m.pst[2];
+  }
+  return idx + g * m.sg + a * m.sa + b * m.sb + (long long)(m.t0[0] + jx * m.tstep[0]) * m.st[0] +
          (long long)(m.t0[1] + jy * m.tstep[1]) * m.st[1] + (long long)(m.t0[2] + jz * m.tstep[2]) * m.st[2];
 }
 

@@ -54,6 +54,13 @@ struct Params {
   int n_runs, Lx, n_xseg;
   long long out_sn, out_sx, out_sy, out_sz, out_base;
   int out_c_off, out_f32, in_relu, out_relu;
+  // input addressing (elements): coarse strides + per-phase offsets (iphase folds stride phases into the channel planes)
+  long long in_ns, in_xs;
+  int in_ys, in_zs, Pc, ips[3];
+  long long in_ph[3];
+  // output stride phases (ophase): cout = [nph][cpp]
+  int ops[3], cpp;
+  long long out_ph[3];
   // shared memory carve-up (bytes from the 128-aligned base)
   int off_w, off_a, off_bar, off_tab, off_stat, smem_bytes;
   int tmem_cols;
@@ -296,8 +303,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     const int qf = q0 + pix0;
     const int yv0 = qf / p.Zv, zv0 = qf - yv0 * p.Zv;
     const int ystep = pstep / p.Zv, zstep = pstep - ystep * p.Zv;
-    const size_t xstride = (size_t)p.IY * p.IZ * p.Cp;
-    const __half* in_n = p.in + (size_t)n * p.IX * xstride + plane * 8;
+    const size_t xstride = (size_t)p.in_xs;
+    // channel plane -> (stride phase, 8-channel group): the phase selects a sub-lattice of the full-resolution tensor
+    long long plane_off = (long long)plane * 8;
+    if (p.ips[0] * p.ips[1] * p.ips[2] > 1) {
+      int phi = plane / p.Pc;
+      const int cg = plane - phi * p.Pc;
+      const int fz = phi % p.ips[2]; phi /= p.ips[2];
+      const int fy = phi % p.ips[1], fx = phi / p.ips[1];
+      plane_off = (long long)cg * 8 + fx * p.in_ph[0] + fy * p.in_ph[1] + fz * p.in_ph[2];
+    }
+    const __half* in_n = p.in + (size_t)n * p.in_ns + plane_off;
     const int sstep = pstep * 16;
     unsigned char* dst0 = smem + p.off_a + plane * p.PS + pix0 * 16;
     const bool fast = (p.RUN + pstep - 1) / pstep <= kMaxChunk;  // warp-uniform (CTA-uniform)
@@ -308,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       for (int c = 0; c < kMaxChunk; ++c) {
         const int ym = yv - p.py, zm = zv - p.pz;
         const bool ok = c < nchunk && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
-        goff[c] = ok ? (ym * p.IZ + zm) * p.Cp : -1;
+        goff[c] = ok ? ym * p.in_ys + zm * p.in_zs : -1;
         zv += zstep; yv += ystep;
         if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
       }
@@ -345,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
             const int ym = yv - p.py, zm = zv - p.pz;
             ok[u] = xok && (c + u < nchunk) && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
             v[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok[u]) v[u] = ldg_nc16(in_x + (size_t)(ym * p.IZ + zm) * p.Cp);
+            if (ok[u]) v[u] = ldg_nc16(in_x + (size_t)ym * p.in_ys + (size_t)zm * p.in_zs);
             zv += zstep; yv += ystep;
             if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
           }
@@ -405,6 +421,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     const bool affine = p.out_scale != nullptr;
     const bool local_stats = do_stats && Nc == 16;  // one chunk: keep the sums in registers until the end
     const int out_relu = p.out_relu, out_f32 = p.out_f32, cout = p.cout;
+    const bool phased = p.ops[0] * p.ops[1] * p.ops[2] > 1;
     float t1[16], t2[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
@@ -433,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (ch0 + j < cout) v[j] += p.bias[ch0 + j];
+              if (ch0 + j < cout) v[j] += p.bias[phased ? (ch0 + j) % p.cpp : ch0 + j];
           }
           if (local_stats) {
             if (valid) {
@@ -468,7 +485,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
               for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             const int nv = min(16, cout - ch0);
-            if (out_f32) {
+            if (phased) {
+              // each 8-channel half of the chunk belongs to one stride phase: its own spatial offset
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int ch = ch0 + 8 * hh;
+                if (ch < cout) {
+                  int phi = ch / p.cpp;
+                  const int co = ch - phi * p.cpp;
+                  const int fz = phi % p.ops[2]; phi /= p.ops[2];
+                  const int fy = phi % p.ops[1], fx = phi / p.ops[1];
+                  __half* o = reinterpret_cast<__half*>(p.out) + (obase - ns * Nc) + poff[mb] + fx * p.out_ph[0] +
+                              fy * p.out_ph[1] + fz * p.out_ph[2] + co;
+                  __half2 h[4];
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[8 * hh + 2 * j], v[8 * hh + 2 * j + 1]);
+                  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
+                }
+              }
+            } else if (out_f32) {
               float* o = reinterpret_cast<float*>(p.out) + obase + poff[mb] + cc;
 #pragma unroll
               for (int j = 0; j < 16; ++j)
@@ -587,8 +622,34 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   if (d->groups != 1) return "groups != 1";
   if (d->in_cpitch % 8 != 0 || d->in_c_off != 0) return "input channel pitch must be a multiple of 8, offset 0";
   const int P = d->in_cpitch / 8;
-  if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16) return "input channel pitch must be 8..128, power of two";
+  if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16 && P != 32) return "input channel pitch must be 8..256, power of two";
   if (d->cin > d->in_cpitch) return "cin > pitch";
+  for (int i = 0; i < 3; ++i) {
+    p.ops[i] = std::max(1, (d->ophase >> (8 * i)) & 0xff);
+    p.ips[i] = std::max(1, (d->iphase >> (8 * i)) & 0xff);
+  }
+  const int nph_o = p.ops[0] * p.ops[1] * p.ops[2], nph_i = p.ips[0] * p.ips[1] * p.ips[2];
+  if (nph_o > 1) {
+    if (d->dtype_out != HCU_F16 || d->cout % nph_o || (d->cout / nph_o) % 8 || d->out_c_off % 8 || d->out_cpitch % 8)
+      return "ophase needs fp16 output and 8-channel aligned phases";
+    for (int i = 0; i < 3; ++i)
+      if (d->ostep[i] < p.ops[i]) return "ophase larger than the output step";
+  }
+  if (nph_i > 1 && (d->cin != d->in_cpitch || d->cin % nph_i || (d->cin / nph_i) % 8)) return "iphase needs 8-channel aligned phases";
+  p.cpp = d->cout / nph_o;
+  p.Pc = P / nph_i;
+  {
+    // element strides of the (full-resolution) input tensor per COARSE step, and per phase step
+    const long long cr = d->in_cpitch / nph_i;
+    const long long fz = (long long)d->in_size[2] * p.ips[2], fy = (long long)d->in_size[1] * p.ips[1],
+                    fx = (long long)d->in_size[0] * p.ips[0];
+    p.in_ph[2] = cr; p.in_ph[1] = fz * cr; p.in_ph[0] = fy * fz * cr;
+    p.in_zs = (int)(p.ips[2] * cr);
+    if (fz * cr * p.ips[1] * d->in_size[1] >= 0x7fffffffLL) return "x-plane too large";
+    p.in_ys = (int)(p.ips[1] * fz * cr);
+    p.in_xs = p.ips[0] * fy * fz * cr;
+    p.in_ns = fx * fy * fz * cr;
+  }
   for (int i = 0; i < 3; ++i)
     if (d->istep[i] != 1) return "strided gather";
   if (d->cout < 2 && d->dtype_out == HCU_F16) return "single output channel";
@@ -690,9 +751,12 @@ extern "C" int hcu_conv_tc_pack_ref(const HcuConvDesc* d, const HcuWeightMap* m,
   tc::Params p;
   const char* why = tc::configure(d, p);
   HCU_CHECK_ARG(why == nullptr, "conv_tc_pack_ref: unsupported descriptor (%s)", why);
-  HCU_CHECK_ARG(m->groups == 1 && m->j[0] == d->taps[0] && m->j[1] == d->taps[1] && m->j[2] == d->taps[2] &&
-                    m->na == d->cin && m->nb == d->cout,
-                "conv_tc_pack_ref: weight map does not match the descriptor");
+  {
+    const int nph = m->phase_on ? m->ph[0] * m->ph[1] * m->ph[2] : 1;
+    HCU_CHECK_ARG(m->groups == 1 && m->j[0] == d->taps[0] && m->j[1] == d->taps[1] && m->j[2] == d->taps[2] &&
+                      m->na * (m->phase_on == 1 ? nph : 1) == d->cin && m->nb * (m->phase_on == 2 ? nph : 1) == d->cout,
+                  "conv_tc_pack_ref: weight map does not match the descriptor");
+  }
   const long long total = (long long)p.nsplit * p.E * p.Nc * 8;
   int grid = (int)std::min<long long>((total + 255) / 256, 4096);
   tc::pack_tc_ref_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*m, ref, (__half*)packed, p.KX, p.KY * p.KZ, p.P, p.E_tx,
@@ -714,14 +778,15 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
     return HCU_ERR_UNSUPPORTED;
   }
   for (int i = 0; i < 3; ++i)
-    HCU_CHECK_ARG((long long)(d->out_size[i] - 1) * d->ostep[i] + d->ooff[i] < d->out_tsize[i],
+    HCU_CHECK_ARG((long long)(d->out_size[i] - 1) * d->ostep[i] + d->ooff[i] + (((d->ophase >> (8 * i)) & 0xff) > 1 ? ((d->ophase >> (8 * i)) & 0xff) - 1 : 0) <
+                      d->out_tsize[i],
                   "conv_tc_fwd: output grid exceeds output tensor in dim %d", i);
   {
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("HCU_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
-  HCU_CHECK_ARG(d->out_c_off >= 0 && d->out_c_off + d->cout <= d->out_cpitch, "conv_tc_fwd: output channel slice");
+  HCU_CHECK_ARG(d->out_c_off >= 0 && d->out_c_off + p.cpp <= d->out_cpitch, "conv_tc_fwd: output channel slice");
   HCU_CHECK_ARG((long long)d->in_size[1] * d->in_size[2] * d->in_cpitch < 0x7fffffffLL, "conv_tc_fwd: x-plane too large");
   p.in = (const __half*)in; p.wp = (const __half*)packed; p.out = out;
   p.bias = bias; p.in_scale = in_scale; p.in_shift = in_shift; p.out_scale = out_scale; p.out_shift = out_shift;
@@ -730,6 +795,8 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
   p.out_sn = tn; p.out_sx = tx * d->ostep[0]; p.out_sy = ty * d->ostep[1]; p.out_sz = tz * d->ostep[2];
   p.out_base = tx * d->ooff[0] + ty * d->ooff[1] + tz * d->ooff[2];
   p.out_c_off = d->out_c_off; p.out_f32 = d->dtype_out == HCU_F32; p.in_relu = d->in_relu; p.out_relu = d->out_relu;
+  p.out_ph[0] = tx; p.out_ph[1] = ty; p.out_ph[2] = tz;
+  HCU_CHECK_ARG(p.ops[0] * p.ops[1] * p.ops[2] == 1 || stats == nullptr, "conv_tc_fwd: no statistics with ophase");
 
   static int smem_attr = 0;
   if (smem_attr < p.smem_bytes) {

@@ -728,7 +728,8 @@ extern "C" int hcu_cl_to_nc(const void* src, int32_t dtype_src, void* dst, int32
 }
 
 static long long wm_total(const HcuWeightMap* m) {
-  return (long long)m->groups * m->j[0] * m->j[1] * m->j[2] * m->na * m->nb;
+  const long long nph = m->phase_on ? (long long)m->ph[0] * m->ph[1] * m->ph[2] : 1;
+  return (long long)m->groups * m->j[0] * m->j[1] * m->j[2] * m->na * m->nb * nph;
 }
 
 extern "C" int hcu_weight_gather(const HcuWeightMap* m, const float* ref, float* packed, void* stream) {

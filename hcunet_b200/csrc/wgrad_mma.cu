@@ -37,6 +37,10 @@ struct Params {
   int n_runs, Lx, n_xseg, n_mchunk, n_nchunk;
   int in_relu;
   int off_dy, smem_bytes;
+  // dy addressing (elements): coarse strides + stride-phase offsets (HcuConvDesc.ophase on the dy side)
+  long long dy_ns, dy_xs;
+  int dy_ys, dy_zs, Poc, dps[3];
+  long long dy_ph[3];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -143,9 +147,17 @@ __global__ void __launch_bounds__(32 * WM * WP) wgrad_mma_kernel(const Params p)
   const int dy0 = dqf / p.Zv, dz0 = dqf - dy0 * p.Zv;
   const int dystep = dstep / p.Zv, dzstep = dstep - dystep * p.Zv;
   const int nchunk_d = (p.M - dpix0 + dstep - 1) / dstep;
-  const __half* dy_n = p.dy + (size_t)n * p.OX * p.OY * p.OZ * p.Cop + dplane * 8;
+  long long dplane_off = (long long)dplane * 8;
+  if (p.dps[0] * p.dps[1] * p.dps[2] > 1) {
+    int phi = dplane / p.Poc;
+    const int cg = dplane - phi * p.Poc;
+    const int fz = phi % p.dps[2]; phi /= p.dps[2];
+    const int fy = phi % p.dps[1], fx = phi / p.dps[1];
+    dplane_off = (long long)cg * 8 + fx * p.dy_ph[0] + fy * p.dy_ph[1] + fz * p.dy_ph[2];
+  }
+  const __half* dy_n = p.dy + (size_t)n * p.dy_ns + dplane_off;
   auto stage_dy = [&](int i) {
-    const __half* d_x = dy_n + (size_t)(x0 + i) * p.OY * p.OZ * p.Cop;
+    const __half* d_x = dy_n + (size_t)(x0 + i) * p.dy_xs;
     unsigned char* dst = smem + p.off_dy + dplane * p.DPS + dpix0 * 16;
     int oy = dy0, oz = dz0;
     for (int c = 0; c < nchunk_d; c += 4) {
@@ -153,7 +165,7 @@ __global__ void __launch_bounds__(32 * WM * WP) wgrad_mma_kernel(const Params p)
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         v[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (c + u < nchunk_d && oy < p.OY && oz < p.OZ) v[u] = ldg_nc16(d_x + ((size_t)oy * p.OZ + oz) * p.Cop);
+        if (c + u < nchunk_d && oy < p.OY && oz < p.OZ) v[u] = ldg_nc16(d_x + (size_t)oy * p.dy_ys + (size_t)oz * p.dy_zs);
         oz += dzstep; oy += dystep;
         if (oz >= p.Zv) { oz -= p.Zv; ++oy; }
       }
@@ -274,9 +286,28 @@ static const char* configure(const HcuConvDesc* d, Params& p, int& mtc, int& ntc
   if (d->out_cpitch % 8 != 0 || d->out_c_off != 0 || d->cout > d->out_cpitch) return "dy channel layout";
   const int P = d->in_cpitch / 8, Po = d->out_cpitch / 8;
   if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16) return "input channel pitch";
-  if (Po != 1 && Po != 2 && Po != 4 && Po != 8 && Po != 16) return "dy channel pitch";
-  for (int i = 0; i < 3; ++i)
-    if (d->istep[i] != 1 || d->ostep[i] != 1 || d->ooff[i] != 0 || d->out_tsize[i] != d->out_size[i]) return "strided";
+  if (Po != 1 && Po != 2 && Po != 4 && Po != 8 && Po != 16 && Po != 32) return "dy channel pitch";
+  if (d->iphase) return "iphase";
+  for (int i = 0; i < 3; ++i) p.dps[i] = std::max(1, (d->ophase >> (8 * i)) & 0xff);
+  const int nph = p.dps[0] * p.dps[1] * p.dps[2];
+  if (nph > 1 && (d->cout != d->out_cpitch || d->cout % nph || (d->cout / nph) % 8)) return "ophase needs 8-channel aligned phases";
+  for (int i = 0; i < 3; ++i) {
+    if (d->istep[i] != 1 || d->ooff[i] != 0) return "strided";
+    if (nph == 1 && (d->ostep[i] != 1 || d->out_tsize[i] != d->out_size[i])) return "strided";
+    if (nph > 1 && (d->ostep[i] != p.dps[i] || d->out_tsize[i] != d->out_size[i] * p.dps[i])) return "phase geometry";
+  }
+  p.Poc = Po / nph;
+  {
+    const long long cr = d->out_cpitch / nph;
+    const long long fz = (long long)d->out_size[2] * p.dps[2], fy = (long long)d->out_size[1] * p.dps[1],
+                    fx = (long long)d->out_size[0] * p.dps[0];
+    p.dy_ph[2] = cr; p.dy_ph[1] = fz * cr; p.dy_ph[0] = fy * fz * cr;
+    p.dy_zs = (int)(p.dps[2] * cr);
+    if (fz * cr * p.dps[1] * d->out_size[1] >= 0x7fffffffLL) return "x-plane too large";
+    p.dy_ys = (int)(p.dps[1] * fz * cr);
+    p.dy_xs = p.dps[0] * fy * fz * cr;
+    p.dy_ns = fx * fy * fz * cr;
+  }
   p.N = d->batch; p.IX = d->in_size[0]; p.IY = d->in_size[1]; p.IZ = d->in_size[2];
   p.Cp = d->in_cpitch; p.P = P; p.cin = d->cin;
   p.OX = d->out_size[0]; p.OY = d->out_size[1]; p.OZ = d->out_size[2];

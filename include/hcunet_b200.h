@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 8
+#define HCU_ABI_VERSION 9
 
 typedef enum HcuStatus {
   HCU_OK = 0,
@@ -86,7 +86,17 @@ typedef struct HcuConvDesc {
   int32_t ooff[3];         /* output offset (transposed-conv phase) */
   int32_t in_relu;         /* apply ReLU after the input affine */
   int32_t out_relu;        /* apply ReLU in the epilogue */
-  int32_t reserved[4];
+  /* Stride phases of a transposed convolution folded into the channel dimension (tensor-core kernels only;
+   * packed as sx | sy << 8 | sz << 16, 0 = none).  With nph = sx*sy*sz:
+   *  ophase: the `cout` output channels are [nph][cout / nph]; channel block phi = (phix, phiy, phiz) (z fastest) of
+   *          output position o is written to spatial position o*ostep + ooff + phi, channel out_c_off + co.
+   *          (ConvTranspose forward with kernel % stride == 0: ONE launch instead of one per phase.)
+   *  iphase: the `cin` input channels are [nph][cin / nph]; channel block phi of input position i is READ from
+   *          spatial position i*s + phi of a tensor of spatial size in_size*s and channel pitch in_cpitch / nph.
+   *          (ConvTranspose data gradient; hcu_conv_wgrad_tc applies it to its `b` = dy side via `ophase`.) */
+  int32_t ophase;
+  int32_t iphase;
+  int32_t reserved[2];
 } HcuConvDesc;
 
 struct HcuWeightMap;
@@ -133,6 +143,7 @@ int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const float* a_scale,
  * Generic strided gather between a reference-layout parameter and a packed GEMM-B tensor
  * P[g][jx][jy][jz][a][b]:
  *   ref_index = base + g*sg + a*sa + b*sb + sum_d (t0[d] + j_d*tstep[d]) * st[d]   (+ fold_stride if fold)
+ *               (+ sum_d phi_d * pst[d] when a phase is folded into a / b)
  * gather : P = ref[idx] (+ ref[idx+fold_stride] when fold)      -- forward / dgrad / phase weights
  * scatter: ref[idx] (and ref[idx+fold_stride]) = scale * sum_{s<nsplit} P_s   -- wgrad results
  * `dscale` (every function that has it): optional DEVICE fp32 scalar multiplied into `scale`; it carries
@@ -144,6 +155,10 @@ typedef struct HcuWeightMap {
   int32_t t0[3], tstep[3];
   int32_t fold;            /* 0/1 */
   int64_t fold_stride;
+  /* stride phases folded into a channel index (see HcuConvDesc.ophase): phase_on = 0 none, 1: the `a` index is
+   * [nph][na], 2: the `b` index is [nph][nb]; nph = ph[0]*ph[1]*ph[2]; phase (phix,phiy,phiz) adds sum phi_d*pst[d] */
+  int32_t phase_on, ph[3];
+  int64_t pst[3];
 } HcuWeightMap;
 int hcu_weight_gather(const HcuWeightMap* m, const float* ref, float* packed, void* stream);
 int hcu_weight_scatter(const HcuWeightMap* m, const float* partial, int32_t nsplit, int64_t split_stride,
