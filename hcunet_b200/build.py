@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         src, obj = pair
         if not force and not _stale(obj, [src] + headers):
             return None
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("HCU_EXTRA_NVCC_FLAGS", "").split() + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")

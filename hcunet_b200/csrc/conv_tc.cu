@@ -29,9 +29,11 @@ namespace hcu {
 
 namespace tc {
 
-constexpr int kThreads = 288;
+constexpr int kIssuers = 1;     // MMA-issuing warps (each issues the M-blocks mb = w, w + kIssuers, ...)
+constexpr int kThreads = 256 + 32 * kIssuers;
 constexpr int kMaxPairs = 64;   // (ty, tz, channel-plane) K16 steps per tx
-constexpr int kMaxRing = 8;
+constexpr int kMaxRing = 12;
+constexpr int kMaxTab = 160;    // KX * npairs K16 steps of one output plane (constant-bank table in the kernel parameters)
 constexpr int kSmemLimit = 227 * 1024;
 
 struct Params {
@@ -64,6 +66,11 @@ struct Params {
   // shared memory carve-up (bytes from the 128-aligned base)
   int off_w, off_a, off_bar, off_tab, off_stat, smem_bytes;
   int tmem_cols;
+  int D;         // producer look-ahead in planes (loads in flight beyond the published planes)
+  int epi_fast;  // fp16 output, 8-channel aligned, no stride phases: vector epilogue
+  // K16 step (tx, e): x = (byte offset of the first K8 slab inside a ring slot >> 4) | (offset of the second slab >> 4) << 16
+  //                   y = byte offset of the B tile inside the packed weights >> 4
+  uint2 tab[kMaxTab];
   int debug;  // HCU_TC_DEBUG bits (profiling experiments only): 1 no global loads, 2 no epilogue math/stores, 4 no MMAs
 };
 
@@ -79,19 +86,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded spin: a protocol bug traps (kernel error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (kernel error) after ~2 s instead of hanging the GPU.  The suspend-time hint lets
+// the hardware park the thread until the phase completes, so waiting warps do not burn issue slots.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (unsigned long long it = 0; !ok; ++it) {
-    asm volatile(
-        "{\n.reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (it > (1ull << 24)) __trap();
-  }
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -148,6 +160,42 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 8 accumulator columns of this thread's TMEM lane, no wait: pair with tmem_wait_ld() + tmem_pin8()
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// orders every later use of r[0..7] after the preceding (volatile) wait
+__device__ __forceinline__ void tmem_pin8(uint32_t* r) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])::"memory");
+}
+
+// sum over the 32 lanes of 8 per-lane values; every lane of a group of 4 (lane >> 2) ends up with channel lane >> 2
+__device__ __forceinline__ float reduce8(float* v, int lane) {
+#pragma unroll
+  for (int h = 4, off = 16; h >= 1; h >>= 1, off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < h; ++i) {
+      const float keep = up ? v[i + h] : v[i];
+      const float send = up ? v[i] : v[i + h];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  float r = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 2);
+  return r + __shfl_xor_sync(0xffffffffu, r, 1);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
@@ -184,18 +232,43 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// ---------------------------------------------------------------------------------------------------
-constexpr int kMaxChunk = 8;  // producer fast path: <= 8 16-byte chunks per thread per x-plane, addresses precomputed
+// Stage timing (compile with -DHCU_TC_PROF; experiments only): cycles spent waiting at each barrier vs. total per role
+#ifdef HCU_TC_PROF
+#define PROF_DECL long long pw0 = 0, pw1 = 0, pt0 = clock64()
+#define PROF_WAIT(acc, stmt) { const long long t_ = clock64(); stmt; acc += clock64() - t_; }
+#define PROF_REPORT(role, n0, n1, iters)                                                                   \
+  if (blockIdx.x == gridDim.x / 2 && lane == 0)                                                            \
+    printf("conv_tc prof %-8s warp %d: total %lld cyc, %s %lld, %s %lld, iters %d -> %lld cyc/iter busy\n", role, warp, \
+           clock64() - pt0, n0, pw0, n1, pw1, iters, (clock64() - pt0 - pw0 - pw1) / max(1, iters))
+#else
+#define PROF_DECL
+#define PROF_WAIT(acc, stmt) stmt
+#define PROF_REPORT(role, n0, n1, iters)
+#endif
 
-__device__ __forceinline__ uint4 bn_relu8(uint4 v, const float* sc, const float* sh, int relu) {
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxChunk = 12;  // producer fast path: <= 12 16-byte chunks per thread per x-plane, addresses precomputed
+
+// BatchNorm affine + ReLU of 8 fp16 channels: fp32 multiply-add (one rounding, like the reference's fp32 op followed
+// by the fp16 store), ReLU on the packed halves.  A pure-half formulation ((x - c) * s + d, 4 instead of 6 instructions per
+// channel pair) was measured: +25 % end-to-end logit error on the ill-conditioned 5-level fixture, so it is not used.
+struct BnH8 {
+  float sc[8], sh[8];
+};
+__device__ __forceinline__ void bn_h8_setup(BnH8& b, const float* scale, const float* shift) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { b.sc[j] = scale[j]; b.sh[j] = shift[j]; }
+}
+__device__ __forceinline__ uint4 bn_relu8(uint4 v, const BnH8& b, int relu) {
   __half2* h = reinterpret_cast<__half2*>(&v);
+  const __half2 zero = __float2half2_rn(0.f);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     float2 f = __half22float2(h[k]);
-    f.x = fmaf(f.x, sc[2 * k], sh[2 * k]);
-    f.y = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
-    if (relu) { f.x = fmaxf(f.x, 0.f); f.y = fmaxf(f.y, 0.f); }
+    f.x = fmaf(f.x, b.sc[2 * k], b.sh[2 * k]);
+    f.y = fmaf(f.y, b.sc[2 * k + 1], b.sh[2 * k + 1]);
     h[k] = __floats2half2_rn(f.x, f.y);
+    if (relu) h[k] = __hmax2_nan(h[k], zero);
   }
   return v;
 }
@@ -209,11 +282,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * p.R, bar_tfull = bar_empty + 8 * p.R,
                  bar_tempty = bar_tfull + 16, bar_w = bar_tempty + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (2 * p.R + 5));
-  uint4* mlist = reinterpret_cast<uint4*>(smem + p.off_tab);   // [R rotations][cnt] MMA descriptors of one output plane
   float* sstat = reinterpret_cast<float*>(smem + p.off_stat);  // [2][Nc]
+  float* sbias = sstat + 2 * p.Nc;                             // [3][Nc]: bias, out_scale, out_shift of this column chunk
   const uint32_t a_base = smem_u32(smem + p.off_a), w_base = smem_u32(smem + p.off_w);
   const int R = p.R, MB = p.MB, Nc = p.Nc;
-  const int cnt = MB * p.KX * p.npairs;  // MMAs per output plane
 
   // ---- work item ---------------------------------------------------------------------------------
   int item = blockIdx.x;
@@ -231,10 +303,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     if (lane == 0) {
       for (int i = 0; i < R; ++i) {
         mbar_init(bar_full + 8 * i, 4);   // one arrive per producer warp
-        mbar_init(bar_empty + 8 * i, 1);  // tcgen05.commit
+        mbar_init(bar_empty + 8 * i, kIssuers);  // tcgen05.commit of every issuer
       }
       for (int i = 0; i < 2; ++i) {
-        mbar_init(bar_tfull + 8 * i, 1);   // tcgen05.commit
+        mbar_init(bar_tfull + 8 * i, kIssuers);   // tcgen05.commit of every issuer
         mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
       }
       mbar_init(bar_w, 1);
@@ -242,34 +314,6 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
-    // Descriptor list.  For ring rotation r (= output plane index mod R) entry (mb, tx, e):
-    //   x = A descriptor low word, y = B descriptor low word, z = TMEM column of the accumulator, w = accumulate flag.
-    // K16 step e of a tx group covers entries 2e, 2e+1 of its (ty, tz, channel-plane) list.
-    const int per_tx = p.KY * p.KZ * p.P;
-    const uint32_t b_lbo = ((uint32_t)(Nc * 16) >> 4) << 16;
-    for (int idx = lane; idx < R * cnt; idx += 32) {
-      int k = idx % cnt;
-      const int r = idx / cnt;
-      const int e = k % p.npairs; k /= p.npairs;
-      const int tx = k % p.KX;
-      const int mb = k / p.KX;
-      const int e0 = 2 * e, e1 = 2 * e + 1;
-      const int t0 = e0 / p.P, c0 = e0 % p.P;
-      const int off0 = ((t0 / p.KZ) * p.dy * p.Zv + (t0 % p.KZ) * p.dz) * 16 + c0 * p.PS;
-      int off1 = off0;  // odd tail: second K8 half re-reads the same rows against zero weights
-      if (e1 < per_tx) {
-        const int t1 = e1 / p.P, c1 = e1 % p.P;
-        off1 = ((t1 / p.KZ) * p.dy * p.Zv + (t1 % p.KZ) * p.dz) * 16 + c1 * p.PS;
-      }
-      int sl = r + tx * p.dx;
-      sl -= sl >= R ? R : 0;
-      uint4 q;
-      q.x = ((a_base + (uint32_t)(sl * p.SLOT + mb * 2048 + off0)) >> 4) | (((uint32_t)(off1 - off0) >> 4) << 16);
-      q.y = ((w_base + (uint32_t)((tx * p.E_tx + e0) * Nc * 16)) >> 4) | b_lbo;
-      q.z = (uint32_t)(mb * Nc);
-      q.w = (tx | e) ? 1u : 0u;
-      mlist[idx] = q;
-    }
     if (lane == 0) {
       const uint32_t wbytes = (uint32_t)p.E * Nc * 16u;
       mbar_expect_tx(bar_w, wbytes);
@@ -278,6 +322,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     }
   }
   for (int i = threadIdx.x; i < 2 * Nc; i += kThreads) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < Nc; i += kThreads) {
+    const int ch = (blockIdx.x % p.nsplit) * Nc + i;  // ns
+    const bool in = ch < p.cout;
+    sbias[i] = (in && p.bias != nullptr) ? p.bias[ch % p.cpp] : 0.f;
+    sbias[Nc + i] = (in && p.out_scale != nullptr) ? p.out_scale[ch] : 1.f;
+    sbias[2 * Nc + i] = (in && p.out_shift != nullptr) ? p.out_shift[ch] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -285,20 +336,19 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
 
   if (warp >= 4 && warp < 8) {
     // =========================================== PRODUCERS ===========================================
+    // cp.async (16 B, zero-fill for padding) straight into the UMMA layout, D = R - span planes in flight per thread
+    // beyond the ones the MMA is using; a landed plane is transformed IN PLACE (previous layer's BatchNorm + ReLU:
+    // every thread touches only the chunks it copied itself), made visible to the async proxy and published.
+    PROF_DECL;
     const int ptid = threadIdx.x - 128;
     const int plane = ptid % p.P;
     const int pix0 = ptid / p.P, pstep = 128 / p.P;
     const int nchunk = (p.RUN - pix0 + pstep - 1) / pstep;  // pixels this thread copies per x-plane
-    float sc[8], sh[8];
+    const int nmax = (p.RUN + pstep - 1) / pstep;           // CTA-uniform upper bound of nchunk
     const bool xf = p.in_scale != nullptr;
     const int relu = p.in_relu;
-    if (xf) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sc[j] = p.in_scale[plane * 8 + j];
-        sh[j] = p.in_shift[plane * 8 + j];
-      }
-    }
+    BnH8 bn;
+    if (xf) bn_h8_setup(bn, p.in_scale + plane * 8, p.in_shift + plane * 8);
     // (yv, zv) of this thread's first pixel
     const int qf = q0 + pix0;
     const int yv0 = qf / p.Zv, zv0 = qf - yv0 * p.Zv;
@@ -315,70 +365,109 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     }
     const __half* in_n = p.in + (size_t)n * p.in_ns + plane_off;
     const int sstep = pstep * 16;
-    unsigned char* dst0 = smem + p.off_a + plane * p.PS + pix0 * 16;
-    const bool fast = (p.RUN + pstep - 1) / pstep <= kMaxChunk;  // warp-uniform (CTA-uniform)
-    int goff[kMaxChunk];  // element offset of each chunk inside an x-plane, -1 = zero fill
+    const uint32_t dst0 = a_base + (uint32_t)(plane * p.PS + pix0 * 16);
+    const bool fast = nmax <= kMaxChunk;  // CTA-uniform
+    int goff[kMaxChunk];  // element offset of each chunk inside an x-plane; -1 = zero fill, -2 = not this thread's
     if (fast) {
       int yv = yv0, zv = zv0;
 #pragma unroll
       for (int c = 0; c < kMaxChunk; ++c) {
         const int ym = yv - p.py, zm = zv - p.pz;
-        const bool ok = c < nchunk && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
-        goff[c] = ok ? ym * p.in_ys + zm * p.in_zs : -1;
+        const bool ok = ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
+        goff[c] = c < nchunk ? (ok ? ym * p.in_ys + zm * p.in_zs : -1) : -2;
         zv += zstep; yv += ystep;
         if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
       }
     }
-    int slot = 0;
+    const int D = p.D;  // planes in flight (1 .. 3; 0 = synchronous); the host keeps R >= span + D + slack
+    int slot_i = 0, slot_f = 0;
     uint32_t par = 1;
-    for (int j = 0; j < nplanes; ++j) {
-      mbar_wait(bar_empty + 8 * slot, par);
-      const int xm = x0 + j - p.px;  // memory x of this virtual plane
-      const bool xok = xm >= 0 && xm < p.IX;
-      const __half* in_x = in_n + (size_t)(xok ? xm : 0) * xstride;
-      unsigned char* dst = dst0 + slot * p.SLOT;
-      if (fast) {
-        uint4 v[kMaxChunk];
+    auto finish = [&](int jf) {  // plane jf has landed: transform in place, publish
+      if (xf) {
+        const int xm = x0 + jf - p.px;
+        if (xm >= 0 && xm < p.IX) {  // warp-uniform
+          unsigned char* dp = smem + p.off_a + slot_f * p.SLOT + plane * p.PS + pix0 * 16;
+          if (fast) {
 #pragma unroll
-        for (int c = 0; c < kMaxChunk; ++c) {
-          v[c] = make_uint4(0u, 0u, 0u, 0u);
-          if (xok && goff[c] >= 0) v[c] = ldg_nc16(in_x + goff[c]);
-        }
+            for (int g = 0; g < kMaxChunk; g += 4) {
+              if (g < nmax) {  // CTA-uniform
+                uint4 v[4];
 #pragma unroll
-        for (int c = 0; c < kMaxChunk; ++c) {
-          if (c < nchunk) {
-            if (xf && xok && goff[c] >= 0) v[c] = bn_relu8(v[c], sc, sh, relu);
-            *reinterpret_cast<uint4*>(dst + c * sstep) = v[c];
-          }
-        }
-      } else {
-        int yv = yv0, zv = zv0;
-        for (int c = 0; c < nchunk; c += 8) {
-          uint4 v[8];
-          bool ok[8];
+                for (int u = 0; u < 4; ++u) {
+                  v[u] = make_uint4(0u, 0u, 0u, 0u);
+                  if (goff[g + u] >= 0) v[u] = *reinterpret_cast<const uint4*>(dp + (g + u) * sstep);
+                }
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int ym = yv - p.py, zm = zv - p.pz;
-            ok[u] = xok && (c + u < nchunk) && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
-            v[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok[u]) v[u] = ldg_nc16(in_x + (size_t)ym * p.in_ys + (size_t)zm * p.in_zs);
-            zv += zstep; yv += ystep;
-            if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
-          }
+                for (int u = 0; u < 4; ++u) v[u] = bn_relu8(v[u], bn, relu);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            if (c + u >= nchunk) break;
-            if (xf && ok[u]) v[u] = bn_relu8(v[u], sc, sh, relu);
-            *reinterpret_cast<uint4*>(dst + (size_t)(c + u) * sstep) = v[u];
+                for (int u = 0; u < 4; ++u)
+                  if (goff[g + u] >= 0) *reinterpret_cast<uint4*>(dp + (g + u) * sstep) = v[u];
+              }
+            }
+          } else {
+            int yv = yv0, zv = zv0;
+            for (int c = 0; c < nchunk; ++c) {
+              const int ym = yv - p.py, zm = zv - p.pz;
+              if (ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ) {
+                uint4* q = reinterpret_cast<uint4*>(dp + (size_t)c * sstep);
+                *q = bn_relu8(*q, bn, relu);
+              }
+              zv += zstep; yv += ystep;
+              if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+            }
           }
         }
       }
-      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_full + 8 * slot);
-      if (++slot == R) { slot = 0; par ^= 1; }
+      if (lane == 0) mbar_arrive(bar_full + 8 * slot_f);
+      if (++slot_f == R) slot_f = 0;
+    };
+    for (int j = 0; j < nplanes + D; ++j) {
+      // groups committed so far = planes 0 .. j-1; publish plane j-D before (possibly) blocking on the ring
+      if (D > 0 && j >= D) {
+        PROF_WAIT(pw1, {
+          if (D == 1) cp_async_wait<0>();
+          else if (D == 2) cp_async_wait<1>();
+          else cp_async_wait<2>();
+        });
+        finish(j - D);
+      }
+      if (j < nplanes) {
+        PROF_WAIT(pw0, mbar_wait(bar_empty + 8 * slot_i, par));
+        const int xm = x0 + j - p.px;  // memory x of this virtual plane
+        const bool xok = xm >= 0 && xm < p.IX;
+        const __half* in_x = in_n + (size_t)(xok ? xm : 0) * xstride;
+        const uint32_t dst = dst0 + (uint32_t)(slot_i * p.SLOT);
+        if (p.debug & 1) {
+        } else if (fast) {
+#pragma unroll
+          for (int c = 0; c < kMaxChunk; ++c) {
+            if (c < nmax && goff[c] != -2) {
+              const bool ok = xok && goff[c] >= 0;
+              cp_async16(dst + c * sstep, ok ? in_x + goff[c] : in_n, ok ? 16u : 0u);
+            }
+          }
+        } else {
+          int yv = yv0, zv = zv0;
+          for (int c = 0; c < nchunk; ++c) {
+            const int ym = yv - p.py, zm = zv - p.pz;
+            const bool ok = xok && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
+            cp_async16(dst + c * sstep, ok ? in_x + ((size_t)ym * p.in_ys + (size_t)zm * p.in_zs) : in_n, ok ? 16u : 0u);
+            zv += zstep; yv += ystep;
+            if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+          }
+        }
+        if (++slot_i == R) { slot_i = 0; par ^= 1; }
+      }
+      cp_async_commit();  // one group per iteration (possibly empty) keeps the group arithmetic uniform
+      if (D == 0) {
+        cp_async_wait<0>();
+        finish(j);
+      }
     }
-  } else if (warp == 8) {
+    PROF_REPORT("producer", "wait_empty", "wait_cpasync", nplanes);
+  } else if (warp >= 8) {
     // =========================================== MMA ISSUER ==========================================
     // The whole warp runs this (warp-uniform values -> descriptors live in uniform registers, no per-thread
     // waterfall); one elected lane issues tcgen05.mma / tcgen05.commit.  Everything is table driven: one 16-byte
@@ -386,6 +475,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     const uint32_t idesc = (1u << 4) | ((uint32_t)(Nc >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
     const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1 (bit 46)
     const bool leader = elect_one();
+    const uint32_t a_desc0 = a_base >> 4;
+    const uint32_t wdesc = (w_base >> 4) | ((((uint32_t)(Nc * 16)) >> 4) << 16);  // B: LBO = next K8 slab
+    PROF_DECL;
     mbar_wait(bar_w, 0);
     const int lastoff = (p.KX - 1) * p.dx;
     int next_wait = 0, wslot = 0;
@@ -393,18 +485,36 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     int i_mod = 0;
     for (int i = 0; i < nout; ++i) {
       for (; next_wait <= i + lastoff; ++next_wait) {
-        mbar_wait(bar_full + 8 * wslot, wpar);
+        PROF_WAIT(pw0, mbar_wait(bar_full + 8 * wslot, wpar));
         if (++wslot == R) { wslot = 0; wpar ^= 1; }
       }
       const int buf = i & 1;
-      mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1);
+      PROF_WAIT(pw1, mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1));
       tc_fence_after();
       const uint32_t tb = tmem_base + (uint32_t)(buf * MB * Nc);
-      const uint4* L = mlist + i_mod * cnt;
-#pragma unroll 4
-      for (int k = 0; k < cnt; ++k) {
-        const uint4 q = L[k];
-        if (leader) umma_f16(tb + q.z, desc_hi | q.x, desc_hi | q.y, idesc, q.w);
+      // every operand below is warp-uniform (kernel parameters + uniform counters): the descriptors are built in the
+      // uniform datapath straight from the constant-bank table; the M-blocks are unrolled so that the four MMAs of a
+      // K16 step issue back to back (they accumulate into different TMEM tiles)
+      if (!(p.debug & 4)) {
+        for (int tx = 0; tx < p.KX; ++tx) {
+          int sl = i_mod + tx * p.dx;
+          sl -= sl >= R ? R : 0;
+          const uint32_t abase = a_desc0 + (uint32_t)(sl * (p.SLOT >> 4));
+          const uint2* T = p.tab + tx * p.npairs;
+#pragma unroll 1
+          for (int e = 0; e < p.npairs; ++e) {
+            const uint2 t = T[e];
+            const uint32_t acc = (uint32_t)(tx | e);
+            const uint64_t ad = desc_hi | (uint64_t)(abase + t.x), bd = desc_hi | (uint64_t)(wdesc + t.y);
+            if (elect_one()) {
+              umma_f16(tb, ad, bd, idesc, acc);
+              if (MB > 1) umma_f16(tb + (uint32_t)Nc, ad + 128u, bd, idesc, acc);
+              if (MB > 2) umma_f16(tb + (uint32_t)(2 * Nc), ad + 256u, bd, idesc, acc);
+              if (MB > 3) umma_f16(tb + (uint32_t)(3 * Nc), ad + 384u, bd, idesc, acc);
+            }
+            __syncwarp();
+          }
+        }
       }
       if (leader) {
         umma_commit(bar_empty + 8 * i_mod);  // plane i is not needed by later outputs
@@ -413,116 +523,251 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       __syncwarp();
       i_mod = i_mod + 1 == R ? 0 : i_mod + 1;
     }
+    PROF_REPORT("mma", "wait_full", "wait_tempty", nout);
   } else {
     // =========================================== EPILOGUE ============================================
+    PROF_DECL;
     const int row = threadIdx.x;  // accumulator row within an M-block == TMEM lane
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     const bool do_stats = p.stats != nullptr;
     const bool affine = p.out_scale != nullptr;
-    const bool local_stats = do_stats && Nc == 16;  // one chunk: keep the sums in registers until the end
-    const int out_relu = p.out_relu, out_f32 = p.out_f32, cout = p.cout;
-    const bool phased = p.ops[0] * p.ops[1] * p.ops[2] > 1;
-    float t1[16], t2[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
-    // per M-block: offset of this thread's pixel inside an output x-plane (-1: wrap-around / out of range)
-    long long poff[4];
+    const bool has_bias = p.bias != nullptr;
+    const int out_relu = p.out_relu, cout = p.cout;
+    const int nch = min(Nc, cout - ns * Nc);  // real output channels of this CTA's column chunk
+    // per M-block: element offset of this thread's pixel inside an output x-plane (-1: wrap-around / out of range)
+    int poff[4];
 #pragma unroll
     for (int mb = 0; mb < 4; ++mb) {
       const int q = q0 + mb * 128 + row;
       const int oy = q / p.Zv, oz = q - oy * p.Zv;
-      poff[mb] = (mb < MB && oy < p.OY && oz < p.OZ) ? oy * p.out_sy + oz * p.out_sz : -1;
+      poff[mb] = (mb < MB && oy < p.OY && oz < p.OZ) ? (int)(oy * p.out_sy + oz * p.out_sz) : -1;
     }
     const long long obase0 = p.out_base + n * p.out_sn + p.out_c_off + ns * Nc;
-    for (int i = 0; i < nout; ++i) {
-      const int buf = i & 1;
-      mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1);
-      tc_fence_after();
-      const long long obase = obase0 + (long long)(x0 + i) * p.out_sx;
+
+    if (p.epi_fast && nch == 8) {
+      // ---- 8 output channels (the HBM-bound first / last levels): every M-block's 8 columns are fetched with ONE wait,
+      // the accumulator buffer is released before the arithmetic, statistics stay in registers until the end
+      float t1[8], t2[8];
 #pragma unroll
-      for (int mb = 0; mb < 4; ++mb) {
-        if (mb >= MB) break;
-        const bool valid = poff[mb] >= 0;
-        for (int cc = 0; cc < Nc; cc += 16) {
-          float v[16];
-          tmem_ld16(tmem_base + lane_base + (uint32_t)((buf * MB + mb) * Nc + cc), v);
-          const int ch0 = ns * Nc + cc;  // first output channel of this chunk
-          if (p.bias != nullptr) {
+      for (int j = 0; j < 8; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
+      float bs[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (ch0 + j < cout) v[j] += p.bias[phased ? (ch0 + j) % p.cpp : ch0 + j];
-          }
-          if (local_stats) {
-            if (valid) {
+      for (int j = 0; j < 8; ++j) bs[j] = sbias[j];
+      for (int i = 0; i < nout; ++i) {
+        const int buf = i & 1;
+        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1));
+        tc_fence_after();
+        if (p.debug & 2) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+          continue;
+        }
+        uint32_t r[4][8];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
+        for (int mb = 0; mb < 4; ++mb)
+          if (mb < MB) tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)((buf * MB + mb) * Nc), r[mb]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb)
+          if (mb < MB) tmem_pin8(r[mb]);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        __half* oplane = reinterpret_cast<__half*>(p.out) + obase0 + (long long)(x0 + i) * p.out_sx;
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+          if (mb < MB && poff[mb] >= 0) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[mb][j]);
+            if (has_bias) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) v[j] += bs[j];
+            }
+            if (do_stats) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
                 t1[j] += v[j];
                 t2[j] = fmaf(v[j], v[j], t2[j]);
               }
             }
-          } else if (do_stats) {
-            float s1[16], s2[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              s1[j] = valid ? v[j] : 0.f;
-              s2[j] = s1[j] * s1[j];
-            }
-            const float r1 = reduce16(s1, lane);
-            const float r2 = reduce16(s2, lane);
-            if ((lane & 1) == 0) {
-              atomicAdd(&sstat[cc + (lane >> 1)], r1);
-              atomicAdd(&sstat[Nc + cc + (lane >> 1)], r2);
-            }
-          }
-          if (valid) {
             if (affine) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (ch0 + j < cout) v[j] = fmaf(v[j], p.out_scale[ch0 + j], p.out_shift[ch0 + j]);
+              for (int j = 0; j < 8; j += 4) {
+                const float4 a = *reinterpret_cast<const float4*>(&sbias[Nc + j]);
+                const float4 b = *reinterpret_cast<const float4*>(&sbias[2 * Nc + j]);
+                v[j] = fmaf(v[j], a.x, b.x); v[j + 1] = fmaf(v[j + 1], a.y, b.y);
+                v[j + 2] = fmaf(v[j + 2], a.z, b.z); v[j + 3] = fmaf(v[j + 3], a.w, b.w);
+              }
             }
             if (out_relu) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            const int nv = min(16, cout - ch0);
-            if (phased) {
-              // each 8-channel half of the chunk belongs to one stride phase: its own spatial offset
+            __half2 h[4];
 #pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                const int ch = ch0 + 8 * hh;
-                if (ch < cout) {
-                  int phi = ch / p.cpp;
-                  const int co = ch - phi * p.cpp;
-                  const int fz = phi % p.ops[2]; phi /= p.ops[2];
-                  const int fy = phi % p.ops[1], fx = phi / p.ops[1];
-                  __half* o = reinterpret_cast<__half*>(p.out) + (obase - ns * Nc) + poff[mb] + fx * p.out_ph[0] +
-                              fy * p.out_ph[1] + fz * p.out_ph[2] + co;
-                  __half2 h[4];
+            for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            if (!(p.debug & 16)) *reinterpret_cast<uint4*>(oplane + poff[mb]) = *reinterpret_cast<uint4*>(h);
+          }
+        }
+      }
+      if (do_stats) {
+        const float r1 = reduce8(t1, lane);
+        const float r2 = reduce8(t2, lane);
+        if ((lane & 3) == 0) {
+          atomicAdd(&sstat[lane >> 2], r1);
+          atomicAdd(&sstat[Nc + (lane >> 2)], r2);
+        }
+      }
+    } else if (p.epi_fast) {
+      // ---- multiples of 16 channels (an odd 8-channel tail is handled by the store predicate), fp16 vector stores
+      const bool local_stats = do_stats && Nc == 16;  // one chunk: keep the sums in registers until the end
+      float t1[16], t2[16];
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[8 * hh + 2 * j], v[8 * hh + 2 * j + 1]);
-                  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
+      for (int j = 0; j < 16; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
+      for (int i = 0; i < nout; ++i) {
+        const int buf = i & 1;
+        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1));
+        tc_fence_after();
+        __half* oplane = reinterpret_cast<__half*>(p.out) + obase0 + (long long)(x0 + i) * p.out_sx;
+#pragma unroll
+        for (int mb = 0; mb < 4; ++mb) {
+          if (mb >= MB) break;
+          const bool valid = poff[mb] >= 0;
+          for (int cc = 0; cc < nch; cc += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + lane_base + (uint32_t)((buf * MB + mb) * Nc + cc), v);
+            if (has_bias) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                const float4 b = *reinterpret_cast<const float4*>(&sbias[cc + j]);
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+              }
+            }
+            if (local_stats) {
+              if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  t1[j] += v[j];
+                  t2[j] = fmaf(v[j], v[j], t2[j]);
                 }
               }
-            } else if (out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + obase + poff[mb] + cc;
+            } else if (do_stats) {
+              float s1[16], s2[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (j < nv) o[j] = v[j];
-            } else {
-              __half* o = reinterpret_cast<__half*>(p.out) + obase + poff[mb] + cc;
-              if (nv >= 8 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                __half2 h[8];
+              for (int j = 0; j < 16; ++j) {
+                s1[j] = valid ? v[j] : 0.f;
+                s2[j] = s1[j] * s1[j];
+              }
+              const float r1 = reduce16(s1, lane);
+              const float r2 = reduce16(s2, lane);
+              if ((lane & 1) == 0) {
+                atomicAdd(&sstat[cc + (lane >> 1)], r1);
+                atomicAdd(&sstat[Nc + cc + (lane >> 1)], r2);
+              }
+            }
+            if (valid) {
+              if (affine) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
-                *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(&h[0]);
-                if (nv == 16) {
-                  *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<uint4*>(&h[4]);
-                } else {
-#pragma unroll
-                  for (int j = 8; j < 16; ++j)
-                    if (j < nv) o[j] = __float2half_rn(v[j]);
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 a = *reinterpret_cast<const float4*>(&sbias[Nc + cc + j]);
+                  const float4 b = *reinterpret_cast<const float4*>(&sbias[2 * Nc + cc + j]);
+                  v[j] = fmaf(v[j], a.x, b.x); v[j + 1] = fmaf(v[j + 1], a.y, b.y);
+                  v[j + 2] = fmaf(v[j + 2], a.z, b.z); v[j + 3] = fmaf(v[j + 3], a.w, b.w);
                 }
+              }
+              if (out_relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              __half2 h[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+              __half* o = oplane + poff[mb] + cc;
+              *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(&h[0]);
+              if (cc + 8 < nch) *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<uint4*>(&h[4]);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+      }
+      if (local_stats) {
+        const float r1 = reduce16(t1, lane);
+        const float r2 = reduce16(t2, lane);
+        if ((lane & 1) == 0) {
+          atomicAdd(&sstat[lane >> 1], r1);
+          atomicAdd(&sstat[Nc + (lane >> 1)], r2);
+        }
+      }
+    } else {
+      // ---- generic: fp32 output, channel counts that are not a multiple of 8, stride-phase scatter
+      const int out_f32 = p.out_f32;
+      const bool phased = p.ops[0] * p.ops[1] * p.ops[2] > 1;
+      for (int i = 0; i < nout; ++i) {
+        const int buf = i & 1;
+        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1));
+        tc_fence_after();
+        const long long obase = obase0 + (long long)(x0 + i) * p.out_sx;
+#pragma unroll 1
+        for (int mb = 0; mb < MB; ++mb) {
+          const bool valid = poff[mb] >= 0;
+#pragma unroll 1
+          for (int cc = 0; cc < nch; cc += 16) {
+            float v[16];
+            tmem_ld16(tmem_base + lane_base + (uint32_t)((buf * MB + mb) * Nc + cc), v);
+            const int ch0 = ns * Nc + cc;  // first output channel of this chunk
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += sbias[cc + j];
+            if (do_stats) {
+              float s1[16], s2[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                s1[j] = valid ? v[j] : 0.f;
+                s2[j] = s1[j] * s1[j];
+              }
+              const float r1 = reduce16(s1, lane);
+              const float r2 = reduce16(s2, lane);
+              if ((lane & 1) == 0) {
+                atomicAdd(&sstat[cc + (lane >> 1)], r1);
+                atomicAdd(&sstat[Nc + cc + (lane >> 1)], r2);
+              }
+            }
+            if (valid) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], sbias[Nc + cc + j], sbias[2 * Nc + cc + j]);
+              if (out_relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+              }
+              const int nv = min(16, cout - ch0);
+              if (phased) {
+                // each 8-channel half of the chunk belongs to one stride phase: its own spatial offset
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int ch = ch0 + 8 * hh;
+                  if (ch < cout) {
+                    int phi = ch / p.cpp;
+                    const int co = ch - phi * p.cpp;
+                    const int fz = phi % p.ops[2]; phi /= p.ops[2];
+                    const int fy = phi % p.ops[1], fx = phi / p.ops[1];
+                    __half* o = reinterpret_cast<__half*>(p.out) + (obase - ns * Nc) + poff[mb] + fx * p.out_ph[0] +
+                                fy * p.out_ph[1] + fz * p.out_ph[2] + co;
+                    __half2 h[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[8 * hh + 2 * j], v[8 * hh + 2 * j + 1]);
+                    *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
+                  }
+                }
+              } else if (out_f32) {
+                float* o = reinterpret_cast<float*>(p.out) + obase + poff[mb] + cc;
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (j < nv) o[j] = v[j];
               } else {
+                __half* o = reinterpret_cast<__half*>(p.out) + obase + poff[mb] + cc;
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                   if (j < nv) o[j] = __float2half_rn(v[j]);
@@ -530,19 +775,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
             }
           }
         }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-    }
-    if (local_stats) {
-      const float r1 = reduce16(t1, lane);
-      const float r2 = reduce16(t2, lane);
-      if ((lane & 1) == 0) {
-        atomicAdd(&sstat[lane >> 1], r1);
-        atomicAdd(&sstat[Nc + (lane >> 1)], r2);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       }
     }
+    PROF_REPORT("epilogue", "wait_tfull", "-", nout);
     if (do_stats) {
       named_bar_sync(1, 128);
       for (int c = row; c < Nc; c += 128) {
@@ -554,6 +792,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       }
     }
   }
+
 
   // ---- teardown --------------------------------------------------------------------------------------
   tc_fence_before();
@@ -661,6 +900,11 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   p.px = d->pad[0]; p.py = d->pad[1]; p.pz = d->pad[2];
   p.Yv = p.OY + (p.KY - 1) * p.dy;
   p.Zv = p.OZ + (p.KZ - 1) * p.dz;
+  {
+    static int zal = -1;
+    if (zal < 0) { const char* e = getenv("HCU_TC_ZALIGN"); zal = e ? atoi(e) : 1; }
+    if (zal > 1 && p.Zv > zal) p.Zv = round_up(p.Zv, zal);
+  }
   const int span = (p.KX - 1) * p.dx + 1;
   if (span > kMaxRing) return "x extent of the filter too large";
   const int per_tx = p.KY * p.KZ * P;
@@ -674,39 +918,62 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   const int plane_q = p.Yv * p.Zv;
   // candidates: big M first; Nc as large as fits
   const int m_cands[4] = {512, 384, 256, 128};
-  for (int pass = 0; pass < 3; ++pass) {          // aim for 3, then 2 CTAs / SM, then whatever fits
-    const int budget = pass == 0 ? 74 * 1024 : (pass == 1 ? 110 * 1024 : kSmemLimit);
-    for (int mi = 0; mi < 4; ++mi) {
-      const int M = m_cands[mi];
-      if (M > 128 && M - 128 >= plane_q) continue;  // do not use a longer run than the plane needs
-      const int MB = M / 128;
-      int run = M + halo;
-      int ps = run * 16;
-      if (P > 1) {  // spread the channel planes over the banks: PS = g (mod 2g), g = max(16, 128 / P)
-        const int g = P >= 8 ? 16 : 128 / P;
-        ps = round_up(ps, 2 * g) + g;
-      }
-      const int slot = ps * P;
-      for (int nc = npad > 128 ? 128 : npad; nc >= 16; nc -= 16) {
-        if (npad % nc != 0) continue;
-        if (2 * MB * nc > 512) continue;
-        const int wbytes = p.E * nc * 16;
-        for (int R = std::min(span + 3, kMaxRing); R >= span; --R) {
+  if (p.KX * p.npairs > kMaxTab) return "too many K16 steps per output plane";
+  // Ring depth R = span (planes the MMA of one output needs) + D (planes in flight, unpublished) + slack (published planes
+  // the MMA has not consumed yet: lets producer and MMA overlap instead of alternating).  Sweeps: want D = 2 + slack 3,
+  // then D = 2 + slack 2, D = 1 + slack 1, anything.  Within a sweep aim for 2 CTAs / SM (the register file allows no
+  // more), then whatever fits; big M first; Nc as large as fits.
+  const int want[4] = {5, 4, 2, 0};
+  for (int pass = 0; pass < 2; ++pass) {
+    const int budget = pass == 0 ? 112 * 1024 : kSmemLimit;
+    for (int sweep = 0; sweep < 4; ++sweep) {
+      for (int mi = 0; mi < 4; ++mi) {
+        const int M = m_cands[mi];
+        if (M > 128 && M - 128 >= plane_q) continue;  // do not use a longer run than the plane needs
+        const int MB = M / 128;
+        int run = M + halo;
+        int ps = run * 16;
+        if (P > 1) {  // spread the channel planes over the banks: PS = g (mod 2g), g = max(16, 128 / P)
+          const int g = P >= 8 ? 16 : 128 / P;
+          ps = round_up(ps, 2 * g) + g;
+        }
+        const int slot = ps * P;
+        for (int nc = npad > 128 ? 128 : npad; nc >= 16; nc -= 16) {
+          if (npad % nc != 0) continue;
+          if (2 * MB * nc > 512) continue;
+          const int wbytes = p.E * nc * 16;
+          const int R = span + want[sweep];
+          if (R > kMaxRing) continue;
           const int off_w = 0;
           const int off_a = round_up(wbytes, 128);
           const int off_bar = off_a + R * slot;
-          const int off_tab = round_up(off_bar + 8 * (2 * R + 5) + 8, 16);
-          const int off_stat = off_tab + R * MB * p.KX * p.npairs * 16;
-          const int total = off_stat + 2 * nc * 4 + 128;
+          const int off_stat = round_up(off_bar + 8 * (2 * R + 5) + 8, 16);
+          const int total = off_stat + 5 * nc * 4 + 128;
           if (total > budget) continue;
           p.M = M; p.MB = MB; p.RUN = run; p.PS = ps; p.SLOT = slot; p.R = R;
+          p.D = want[sweep] >= 4 ? 2 : (want[sweep] >= 2 ? 1 : 0);
           p.Nc = nc; p.nsplit = npad / nc;
-          p.off_w = off_w; p.off_a = off_a; p.off_bar = off_bar; p.off_tab = off_tab; p.off_stat = off_stat;
+          p.off_w = off_w; p.off_a = off_a; p.off_bar = off_bar; p.off_tab = 0; p.off_stat = off_stat;
           p.smem_bytes = total;
           int cols = 2 * MB * nc, t = 32;
           while (t < cols) t <<= 1;
           p.tmem_cols = t;
           p.n_runs = (plane_q + M - 1) / M;
+          // K16 steps of one tx group: entries 2e, 2e+1 of its (ty, tz, channel-plane) list
+          for (int tx = 0; tx < p.KX; ++tx)
+            for (int e = 0; e < p.npairs; ++e) {
+              const int e0 = 2 * e, e1 = 2 * e + 1;
+              const int t0 = e0 / P, c0 = e0 % P;
+              const int off0 = ((t0 / p.KZ) * p.dy * p.Zv + (t0 % p.KZ) * p.dz) * 16 + c0 * ps;
+              int off1 = off0;  // odd tail: the second K8 half re-reads the same rows against zero weights
+              if (e1 < per_tx) {
+                const int t1 = e1 / P, c1 = e1 % P;
+                off1 = ((t1 / p.KZ) * p.dy * p.Zv + (t1 % p.KZ) * p.dz) * 16 + c1 * ps;
+              }
+              if (off1 < off0 || ((off1 - off0) >> 4) > 0x3fff) return "K8 slab stride not encodable";
+              p.tab[tx * p.npairs + e].x = ((uint32_t)off0 >> 4) | (((uint32_t)(off1 - off0) >> 4) << 16);
+              p.tab[tx * p.npairs + e].y = (uint32_t)((tx * p.E_tx + e0) * nc * 16) >> 4;
+            }
           return nullptr;
         }
       }
@@ -796,6 +1063,9 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
   p.out_base = tx * d->ooff[0] + ty * d->ooff[1] + tz * d->ooff[2];
   p.out_c_off = d->out_c_off; p.out_f32 = d->dtype_out == HCU_F32; p.in_relu = d->in_relu; p.out_relu = d->out_relu;
   p.out_ph[0] = tx; p.out_ph[1] = ty; p.out_ph[2] = tz;
+  HCU_CHECK_ARG(tx * d->ostep[0] < 0x7fffffffLL, "conv_tc_fwd: output x-plane too large");
+  p.epi_fast = d->dtype_out == HCU_F16 && p.ops[0] * p.ops[1] * p.ops[2] == 1 && d->cout % 8 == 0 && d->out_cpitch % 8 == 0 &&
+               d->out_c_off % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   HCU_CHECK_ARG(p.ops[0] * p.ops[1] * p.ops[2] == 1 || stats == nullptr, "conv_tc_fwd: no statistics with ophase");
 
   static int smem_attr = 0;

@@ -30,6 +30,8 @@ LAYERS = {
     "d4.conv2": (128, 128, (10, 10, 27), (3, 3, 1)),
     "u0.conv1": (64, 64, (16, 16, 28), (3, 3, 2)),
     "u3.conv1": (8, 8, (72, 72, 28), (3, 3, 2)),
+    "x.n48": (8, 48, (256, 256, 32), (3, 3, 2)),
+    "x.n128": (8, 128, (256, 256, 32), (3, 3, 2)),
 }
 
 
