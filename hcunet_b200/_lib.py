@@ -11,9 +11,10 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 F32, BF16, F16 = 0, 1, 2
+BATCH_JOB_BYTES = 256
 
 
 class HcuConvDesc(C.Structure):
@@ -69,6 +70,13 @@ SIGNATURES = {
     "hcu_conv_wgrad_partial": [C.POINTER(HcuConvDesc), P, P, P, P, P, I32, P],
     "hcu_conv_wgrad_tc_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_wgrad_tc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
+    "hcu_conv_wgrad_tc_acc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
+    "hcu_conv_tc_pack_batch_build": [C.POINTER(HcuConvDesc), C.POINTER(HcuWeightMap), C.POINTER(I64), C.POINTER(I64), I32, P,
+                                     C.POINTER(I32)],
+    "hcu_conv_tc_pack_batch": [P, I32, I32, P, P, P],
+    "hcu_weight_scatter_batch_build": [C.POINTER(HcuWeightMap), C.POINTER(I32), C.POINTER(I64), C.POINTER(I64), I32, P,
+                                       C.POINTER(I32)],
+    "hcu_weight_scatter_batch": [P, I32, I32, P, F, P, P, P],
     "hcu_weight_gather": [C.POINTER(HcuWeightMap), P, P, P],
     "hcu_weight_scatter": [C.POINTER(HcuWeightMap), P, I32, I64, F, P, I32, P, P],
     "hcu_nc_to_cl": [P, I32, P, I32, I64, I32, I64, I32, P, P],
@@ -152,7 +160,7 @@ def load():
     for name in SIGNATURES:
         raw = getattr(lib, name)
         setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_conv_tc_supported", "hcu_conv_wgrad_tc_supported",
-                                         "hcu_conv_tc_packed_bytes") else _wrap(name, raw))
+                                         "hcu_conv_tc_packed_bytes", "hcu_conv_tc_pack_batch_build", "hcu_weight_scatter_batch_build") else _wrap(name, raw))
     _lib = out
     return out
 

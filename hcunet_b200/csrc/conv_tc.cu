@@ -22,6 +22,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -849,6 +850,63 @@ __global__ void pack_tc_ref_kernel(HcuWeightMap m, const float* __restrict__ ref
   }
 }
 
+
+// ---- batched weight packing: one launch for every tensor-core conv of a step ------------------------------------
+struct PackJob {
+  HcuWeightMap m;
+  long long ref_off, out_off, total;
+  int KX, KYZ, P, E_tx, Nc, nsplit, cin, cout;
+  int block0, nblocks;
+};
+static_assert(sizeof(PackJob) <= HCU_BATCH_JOB_BYTES, "PackJob does not fit its table slot");
+constexpr int kPackPerBlock = 2048;  // elements per block (256 threads x 8)
+
+__global__ void __launch_bounds__(256) pack_tc_batch_kernel(const unsigned char* __restrict__ jobs, int n,
+                                                            const float* __restrict__ params, unsigned char* __restrict__ packed) {
+  __shared__ PackJob J;
+  __shared__ int jidx;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n - 1;  // last job whose block0 <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      const PackJob* pj = reinterpret_cast<const PackJob*>(jobs + (size_t)mid * HCU_BATCH_JOB_BYTES);
+      if (pj->block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    jidx = lo;
+  }
+  __syncthreads();
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + (size_t)jidx * HCU_BATCH_JOB_BYTES);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = threadIdx.x; i < (int)(sizeof(PackJob) / 4); i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+  const float* ref = params + J.ref_off;
+  __half* out = reinterpret_cast<__half*>(packed + J.out_off);
+  const long long base = (long long)(blockIdx.x - J.block0) * kPackPerBlock;
+  for (int k = threadIdx.x; k < kPackPerBlock; k += 256) {
+    const long long i = base + k;
+    if (i >= J.total) break;
+    const int j = (int)(i & 7);
+    long long r = i >> 3;
+    const int nn = (int)(r % J.Nc); r /= J.Nc;
+    const int e = (int)(r % J.E_tx); r /= J.E_tx;
+    const int tx = (int)(r % J.KX);
+    const int ns = (int)(r / J.KX);
+    float v = 0.f;
+    if (e < J.KYZ * J.P) {
+      const int t = e / J.P, pl = e % J.P;
+      const int ci = pl * 8 + j, co = ns * J.Nc + nn;
+      if (ci < J.cin && co < J.cout) {
+        const long long idx = wm_index(J.m, ((long long)(tx * J.KYZ + t) * J.cin + ci) * J.cout + co);
+        v = ref[idx];
+        if (J.m.fold) v += ref[idx + J.m.fold_stride];
+      }
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-side configuration
 // ---------------------------------------------------------------------------------------------------
@@ -1029,6 +1087,47 @@ extern "C" int hcu_conv_tc_pack_ref(const HcuConvDesc* d, const HcuWeightMap* m,
   tc::pack_tc_ref_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*m, ref, (__half*)packed, p.KX, p.KY * p.KZ, p.P, p.E_tx,
                                                                  p.Nc, p.nsplit, d->cin, d->cout);
   HCU_CHECK_LAUNCH("pack_tc_ref");
+  return 0;
+}
+
+
+extern "C" int hcu_conv_tc_pack_batch_build(const HcuConvDesc* descs, const HcuWeightMap* maps, const int64_t* ref_off,
+                                            const int64_t* out_off, int32_t n, void* host_jobs, int32_t* blocks) {
+  HCU_CHECK_ARG(descs && maps && ref_off && out_off && host_jobs && blocks && n > 0, "conv_tc_pack_batch_build: bad arguments");
+  int b0 = 0;
+  for (int i = 0; i < n; ++i) {
+    tc::Params p;
+    const char* why = tc::configure(&descs[i], p);
+    HCU_CHECK_ARG(why == nullptr, "conv_tc_pack_batch_build: job %d: unsupported descriptor (%s)", i, why);
+    const HcuWeightMap* m = &maps[i];
+    const int nph = m->phase_on ? m->ph[0] * m->ph[1] * m->ph[2] : 1;
+    HCU_CHECK_ARG(m->groups == 1 && m->j[0] == descs[i].taps[0] && m->j[1] == descs[i].taps[1] && m->j[2] == descs[i].taps[2] &&
+                      m->na * (m->phase_on == 1 ? nph : 1) == descs[i].cin && m->nb * (m->phase_on == 2 ? nph : 1) == descs[i].cout,
+                  "conv_tc_pack_batch_build: job %d: weight map does not match the descriptor", i);
+    HCU_CHECK_ARG(out_off[i] % 16 == 0, "conv_tc_pack_batch_build: job %d: packed offset not 16-byte aligned", i);
+    tc::PackJob j;
+    memset(&j, 0, sizeof(j));
+    j.m = *m; j.ref_off = ref_off[i]; j.out_off = out_off[i];
+    j.total = (long long)p.nsplit * p.E * p.Nc * 8;
+    j.KX = p.KX; j.KYZ = p.KY * p.KZ; j.P = p.P; j.E_tx = p.E_tx; j.Nc = p.Nc; j.nsplit = p.nsplit;
+    j.cin = descs[i].cin; j.cout = descs[i].cout;
+    j.block0 = b0;
+    j.nblocks = (int)((j.total + tc::kPackPerBlock - 1) / tc::kPackPerBlock);
+    b0 += j.nblocks;
+    unsigned char* slot = reinterpret_cast<unsigned char*>(host_jobs) + (size_t)i * HCU_BATCH_JOB_BYTES;
+    memset(slot, 0, HCU_BATCH_JOB_BYTES);
+    memcpy(slot, &j, sizeof(j));
+  }
+  *blocks = b0;
+  return 0;
+}
+
+extern "C" int hcu_conv_tc_pack_batch(const void* dev_jobs, int32_t n, int32_t blocks, const float* params, void* packed,
+                                      void* stream) {
+  HCU_CHECK_ARG(dev_jobs && params && packed && n > 0 && blocks > 0, "conv_tc_pack_batch: bad arguments");
+  tc::pack_tc_batch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)dev_jobs, n, params,
+                                                                     (unsigned char*)packed);
+  HCU_CHECK_LAUNCH("pack_tc_batch");
   return 0;
 }
 

@@ -6,6 +6,8 @@
 
 #include <atomic>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace hcu {
@@ -160,6 +162,53 @@ __global__ void weight_scatter_kernel(HcuWeightMap m, const float* __restrict__ 
       ref[idx] = s;
       if (m.fold) ref[idx + m.fold_stride] = s;
     }
+  }
+}
+
+
+// ---- batched weight-gradient scatter: one launch for every parameter of a step ---------------------------------
+struct ScatterJob {
+  HcuWeightMap m;
+  long long part_off, ref_off, total;
+  int nsplit, block0, nblocks, pad;
+};
+static_assert(sizeof(ScatterJob) <= HCU_BATCH_JOB_BYTES, "ScatterJob does not fit its table slot");
+constexpr int kScatterPerBlock = 1024;
+
+__global__ void __launch_bounds__(256) weight_scatter_batch_kernel(const unsigned char* __restrict__ jobs, int n,
+                                                                   const float* __restrict__ partial, float scale,
+                                                                   const float* __restrict__ dscale, float* __restrict__ grads) {
+  __shared__ ScatterJob J;
+  __shared__ int jidx;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      const ScatterJob* pj = reinterpret_cast<const ScatterJob*>(jobs + (size_t)mid * HCU_BATCH_JOB_BYTES);
+      if (pj->block0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    jidx = lo;
+  }
+  __syncthreads();
+  {
+    const int* src = reinterpret_cast<const int*>(jobs + (size_t)jidx * HCU_BATCH_JOB_BYTES);
+    int* dst = reinterpret_cast<int*>(&J);
+    for (int i = threadIdx.x; i < (int)(sizeof(ScatterJob) / 4); i += 256) dst[i] = src[i];
+  }
+  __syncthreads();
+  if (dscale != nullptr) scale *= dscale[0];
+  const float* part = partial + J.part_off;
+  float* ref = grads + J.ref_off;
+  const long long base = (long long)(blockIdx.x - J.block0) * kScatterPerBlock;
+  for (int k = threadIdx.x; k < kScatterPerBlock; k += 256) {
+    const long long e = base + k;
+    if (e >= J.total) break;
+    float s = 0.f;
+    for (int i = 0; i < J.nsplit; ++i) s += part[(long long)i * J.total + e];
+    s *= scale;
+    const long long idx = wm_index(J.m, e);
+    ref[idx] = s;
+    if (J.m.fold) ref[idx + J.m.fold_stride] = s;
   }
 }
 
@@ -749,6 +798,36 @@ extern "C" int hcu_weight_scatter(const HcuWeightMap* m, const float* partial, i
   weight_scatter_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(*m, partial, nsplit, split_stride,
                                                                                 scale, dscale, accumulate, ref, total);
   HCU_CHECK_LAUNCH("weight_scatter");
+  return 0;
+}
+
+
+extern "C" int hcu_weight_scatter_batch_build(const HcuWeightMap* maps, const int32_t* nsplit, const int64_t* part_off,
+                                              const int64_t* ref_off, int32_t n, void* host_jobs, int32_t* blocks) {
+  HCU_CHECK_ARG(maps && nsplit && part_off && ref_off && host_jobs && blocks && n > 0, "weight_scatter_batch_build: bad arguments");
+  int b0 = 0;
+  for (int i = 0; i < n; ++i) {
+    ScatterJob j;
+    memset(&j, 0, sizeof(j));
+    j.m = maps[i]; j.part_off = part_off[i]; j.ref_off = ref_off[i]; j.total = wm_total(&maps[i]);
+    HCU_CHECK_ARG(j.total > 0 && nsplit[i] > 0, "weight_scatter_batch_build: job %d: bad sizes", i);
+    j.nsplit = nsplit[i]; j.block0 = b0;
+    j.nblocks = (int)((j.total + kScatterPerBlock - 1) / kScatterPerBlock);
+    b0 += j.nblocks;
+    unsigned char* slot = reinterpret_cast<unsigned char*>(host_jobs) + (size_t)i * HCU_BATCH_JOB_BYTES;
+    memset(slot, 0, HCU_BATCH_JOB_BYTES);
+    memcpy(slot, &j, sizeof(j));
+  }
+  *blocks = b0;
+  return 0;
+}
+
+extern "C" int hcu_weight_scatter_batch(const void* dev_jobs, int32_t n, int32_t blocks, const float* partial, float scale,
+                                        const float* dscale, float* grads, void* stream) {
+  HCU_CHECK_ARG(dev_jobs && partial && grads && n > 0 && blocks > 0, "weight_scatter_batch: bad arguments");
+  weight_scatter_batch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)dev_jobs, n, partial, scale,
+                                                                        dscale, grads);
+  HCU_CHECK_LAUNCH("weight_scatter_batch");
   return 0;
 }
 

@@ -386,8 +386,8 @@ extern "C" int hcu_conv_wgrad_tc_supported(const HcuConvDesc* d) {
   return wg::configure(d, p, a, b, c, e) == nullptr ? 1 : 0;
 }
 
-extern "C" int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
-                                 const void* dy, float* wacc, void* stream) {
+static int wgrad_tc_impl(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
+                         const void* dy, float* wacc, void* stream, bool zero) {
   HCU_CHECK_ARG(d && a && dy && wacc, "wgrad_tc: null pointer");
   HCU_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr), "wgrad_tc: a_scale/a_shift must come together");
   wg::Params p;
@@ -400,8 +400,10 @@ extern "C" int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const floa
   p.a = (const __half*)a; p.dy = (const __half*)dy; p.wacc = wacc; p.a_scale = a_scale; p.a_shift = a_shift;
   p.in_relu = d->in_relu;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(wacc, 0, sizeof(float) * (size_t)d->taps[0] * d->taps[1] * d->taps[2] * d->cin * d->cout, st);
-  if (e != cudaSuccess) { set_error("wgrad_tc: memset: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
+  if (zero) {
+    cudaError_t e = cudaMemsetAsync(wacc, 0, sizeof(float) * (size_t)d->taps[0] * d->taps[1] * d->taps[2] * d->cin * d->cout, st);
+    if (e != cudaSuccess) { set_error("wgrad_tc: memset: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
+  }
   // x segmentation: ~3 CTAs per SM in flight, several waves
   const long long base_items = (long long)p.N * p.n_runs * p.n_mchunk * p.n_nchunk;
   const int target = 6 * num_sms();
@@ -413,4 +415,14 @@ extern "C" int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const floa
   if (mtc == 9 && ntc == 2) return wg::launch<9, 2, 1, 4>(p, st);
   if (mtc == 6 && ntc == 4) return wg::launch<6, 4, 4, 2>(p, st);
   return wg::launch<3, 8, 8, 1>(p, st);
+}
+
+extern "C" int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
+                                 const void* dy, float* wacc, void* stream) {
+  return wgrad_tc_impl(d, a, a_scale, a_shift, dy, wacc, stream, true);
+}
+
+extern "C" int hcu_conv_wgrad_tc_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
+                                     const void* dy, float* wacc, void* stream) {
+  return wgrad_tc_impl(d, a, a_scale, a_shift, dy, wacc, stream, false);
 }

@@ -210,12 +210,98 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 def _nsplit(m: int, roles: int) -> int:
     """How many CTAs rows split the pixel reduction of a weight gradient."""
     target = 148 * 8 * 3
     n = max(1, -(-target // max(1, roles)))
     n = min(n, max(1, m // 256))
     return int(min(n, 2048))
+
+
+class _StepCache:
+    """What one (input shape, precision, mode) step needs every time, recorded on its first execution:
+
+    * the tensor-core weight packs of every conv launch (forward, data gradient, transposed-conv phases) -- replayed
+      as ONE ``hcu_conv_tc_pack_batch`` launch into a persistent buffer at the start of the forward;
+    * the weight-gradient scatters -- every weight gradient accumulates into a slice of a persistent fp32 workspace
+      (one memset per backward) and ONE ``hcu_weight_scatter_batch`` launch writes all of them, in the reference
+      layouts, into a freshly allocated flat gradient buffer the returned gradients are views of.
+    The job tables hold geometry and offsets only; the parameter addresses they were built against are re-checked on
+    every step (``ptr_sig``) and the cache re-records itself when they move."""
+
+    def __init__(self):
+        self.ready = False
+        self.fwd_done = False
+        self.bwd_done = False
+        self.pack_jobs: Dict[str, tuple] = {}      # key -> (HcuConvDesc, HcuWeightMap, param name, packed bytes)
+        self.scatter_jobs: Dict[str, tuple] = {}   # weight name -> (HcuWeightMap, nsplit, element count)
+        self.ptr_sig = None
+        self.pack_base = 0
+        self.packed = None
+        self.pack_off: Dict[str, int] = {}
+        self.pack_table = None
+        self.pack_blocks = 0
+        self.wacc = None
+        self.part_off: Dict[str, int] = {}
+        self.g_off: Dict[str, int] = {}
+        self.g_total = 0
+        self.scatter_table = None
+        self.scatter_blocks = 0
+
+    @staticmethod
+    def _sig(params, names):
+        return tuple(params[n].data_ptr() for n in names)
+
+    def finalize(self, lib, params, device):
+        n = len(self.pack_jobs)
+        if n:
+            names = [j[2] for j in self.pack_jobs.values()]
+            self.pack_base = min(params[nm].data_ptr() for nm in names)
+            descs = (HcuConvDesc * n)(*[j[0] for j in self.pack_jobs.values()])
+            maps = (HcuWeightMap * n)(*[j[1] for j in self.pack_jobs.values()])
+            ref_off = (C.c_int64 * n)(*[(params[nm].data_ptr() - self.pack_base) // 4 for nm in names])
+            offs, cur = [], 0
+            for key, j in self.pack_jobs.items():
+                self.pack_off[key] = cur
+                offs.append(cur)
+                cur += -(-j[3] // 256) * 256
+            out_off = (C.c_int64 * n)(*offs)
+            host = C.create_string_buffer(n * _lib.BATCH_JOB_BYTES)
+            blocks = C.c_int32(0)
+            _lib.check(lib.hcu_conv_tc_pack_batch_build(descs, maps, ref_off, out_off, n, host, C.byref(blocks)),
+                       "conv_tc_pack_batch_build")
+            self.pack_blocks = blocks.value
+            self.pack_table = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(device)
+            self.packed = torch.empty(cur, dtype=torch.uint8, device=device)
+        m = len(self.scatter_jobs)
+        if m:
+            maps = (HcuWeightMap * m)(*[j[0] for j in self.scatter_jobs.values()])
+            nsp = (C.c_int32 * m)(*[j[1] for j in self.scatter_jobs.values()])
+            po, go, pc, gc = [], [], 0, 0
+            for name, j in self.scatter_jobs.items():
+                self.part_off[name], self.g_off[name] = pc, gc
+                po.append(pc)
+                go.append(gc)
+                pc += j[1] * j[2]
+                gc += params[name].numel()
+            self.g_total = gc
+            host = C.create_string_buffer(m * _lib.BATCH_JOB_BYTES)
+            blocks = C.c_int32(0)
+            _lib.check(lib.hcu_weight_scatter_batch_build(maps, nsp, (C.c_int64 * m)(*po), (C.c_int64 * m)(*go), m, host,
+                                                          C.byref(blocks)), "weight_scatter_batch_build")
+            self.scatter_blocks = blocks.value
+            self.scatter_table = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(device)
+            self.wacc = torch.empty(pc, dtype=torch.float32, device=device)
+        self.ptr_sig = self._sig(params, [j[2] for j in self.pack_jobs.values()])
+        self.ready = True
 
 
 class UnetEngine:
@@ -226,6 +312,12 @@ class UnetEngine:
         self._plans: Dict[tuple, Plan] = {}
         self._inv = None
         self.use_tc = os.environ.get("HCUNET_TC", "1") != "0"
+        self.use_batch = os.environ.get("HCUNET_BATCH", "1") != "0"      # batched packs / scatters (_StepCache)
+        self.overlap_wgrad = os.environ.get("HCUNET_OVERLAP", "1") != "0"  # weight gradients on a side stream
+        self._caches: Dict[tuple, _StepCache] = {}
+        self._cache: Optional[_StepCache] = None   # cache of the call in progress
+        self._side = None
+        self._keep: List[torch.Tensor] = []
 
     @property
     def lib(self):
@@ -250,12 +342,12 @@ class UnetEngine:
         return out
 
     def _conv(self, d, x, wspec, bias=None, out=None, stats=None, in_scale=None, in_shift=None, out_scale=None,
-              out_shift=None, layer=None):
+              out_shift=None, layer=None, key=None):
         """One gather-convolution launch.  wspec = (HcuWeightMap, reference-layout parameter, packed element count).
         fp16 activations take the tcgen05 kernel whenever it supports the descriptor (weights gathered, folded and
         packed to fp16 UMMA tiles in one launch), everything else the FFMA kernel (fp32 [g][taps][cin][cout])."""
         lib = self.lib
-        wm, ref, nw = wspec
+        wm, ref, nw = wspec[:3]
         m = d.batch * d.out_size[0] * d.out_size[1] * d.out_size[2]
         esz_i = 4 if d.dtype_in == _lib.F32 else 2
         esz_o = 4 if d.dtype_out == _lib.F32 else 2
@@ -263,11 +355,19 @@ class UnetEngine:
         nbytes = nin * esz_i + m * d.cout * d.groups * esz_o
         flops = 2 * m * d.cout * d.groups * d.cin * d.taps[0] * d.taps[1] * d.taps[2]
         if self.use_tc and d.dtype_in == _lib.F16 and lib.hcu_conv_tc_supported(C.byref(d)):
-            packed = torch.empty(lib.hcu_conv_tc_packed_bytes(C.byref(d)), dtype=torch.uint8, device=x.device)
-            _lib.check(lib.hcu_conv_tc_pack_ref(C.byref(d), C.byref(wm), _ptr(ref), _ptr(packed), self._stream()),
-                       "conv_tc_pack_ref")
+            cache, key = self._cache, key or layer
+            if cache is not None and cache.ready and key in cache.pack_off:
+                pk = C.c_void_p(cache.packed.data_ptr() + cache.pack_off[key])  # packed by this step's batch launch
+            else:
+                nb = lib.hcu_conv_tc_packed_bytes(C.byref(d))
+                packed = torch.empty(nb, dtype=torch.uint8, device=x.device)
+                _lib.check(lib.hcu_conv_tc_pack_ref(C.byref(d), C.byref(wm), _ptr(ref), _ptr(packed), self._stream()),
+                           "conv_tc_pack_ref")
+                pk = _ptr(packed)
+                if cache is not None and not cache.ready and isinstance(wspec[3] if len(wspec) > 3 else None, str):
+                    cache.pack_jobs[key] = (HcuConvDesc.from_buffer_copy(d), HcuWeightMap.from_buffer_copy(wm), wspec[3], nb)
             _lib.note(layer, nbytes, flops)
-            _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), _ptr(x), _ptr(packed), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
+            _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), _ptr(x), pk, _ptr(bias), _ptr(in_scale), _ptr(in_shift),
                                            _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), self._stream()),
                        "conv_tc_fwd")
             return
@@ -317,6 +417,21 @@ class UnetEngine:
         plan = self.plan(x.shape)
         dev = x.device
         act_dtype = _ACT_DTYPE[precision]
+        cache = None
+        if self.use_batch and self.use_tc and act_dtype == torch.float16:
+            ckey = (tuple(x.shape), precision, bool(training), bool(save), dev.index)
+            cache = self._caches.get(ckey)
+            if cache is None:
+                cache = self._caches[ckey] = _StepCache()
+            if cache.ready and cache.ptr_sig != cache._sig(params, [j[2] for j in cache.pack_jobs.values()]):
+                cache = self._caches[ckey] = _StepCache()   # parameters were re-allocated: record again
+            if not cache.ready and cache.fwd_done and (cache.bwd_done or not save):
+                cache.finalize(lib, params, dev)
+            if cache.ready and cache.pack_table is not None:
+                _lib.check(lib.hcu_conv_tc_pack_batch(_ptr(cache.pack_table), len(cache.pack_jobs), cache.pack_blocks,
+                                                      C.c_void_p(cache.pack_base), _ptr(cache.packed), st),
+                           "conv_tc_pack_batch")
+        self._cache = cache
         adt = _DT[act_dtype]
         esz = 2 if act_dtype == torch.float16 else 4
         B = plan.batch
@@ -346,7 +461,7 @@ class UnetEngine:
                 continue
             npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
             w = (self._wm_conv_fwd(g), params[g.name + ".weight"],
-                 g.groups * g.taps[0] * g.taps[1] * g.taps[2] * g.cin_g * g.cout_g)
+                 g.groups * g.taps[0] * g.taps[1] * g.taps[2] * g.cin_g * g.cout_g, g.name + ".weight")
             bias = params[g.name + ".bias"]
             isc, ish = (xf[0], xf[1]) if xf is not None else (None, None)
             if g.bn is None:  # out_conv: logits, fp32
@@ -406,7 +521,10 @@ class UnetEngine:
             nbt = [buffers[g.bn + ".num_batches_tracked"] for g in plan.steps
                    if isinstance(g, ConvGeom) and g.bn is not None]
             torch._foreach_add_(nbt, 1)
-        return logits, (plan, saved, act_dtype, training)
+        if cache is not None:
+            cache.fwd_done = True
+        self._cache = None
+        return logits, (plan, saved, act_dtype, training, cache)
 
     def _pool(self, y, g: ConvGeom, B, act_dtype, scale, shift, relu, want_argmax=True):
         adt = _DT[act_dtype]
@@ -437,17 +555,31 @@ class UnetEngine:
         out = torch.empty((B, u.out_sz[0] * u.out_sz[1] * u.out_sz[2], u.cout), dtype=act_dtype, device=cur.device)
         isc, ish = (xf[0], xf[1]) if xf is not None else (None, None)
         for phi, J, Q in self._phases(u):
-            w = (self._wm_up_phase(u, phi, J), wt, J[0] * J[1] * J[2] * u.cin * u.cout)
+            w = (self._wm_up_phase(u, phi, J), wt, J[0] * J[1] * J[2] * u.cin * u.cout, u.name + ".weight")
             d = conv_desc(adt, adt, B, u.in_sz, cp, 0, u.cin, u.cin, Q, u.out_sz, u.cout, 0, u.cout, 1, J,
                           pad=tuple(j - 1 for j in J), ostep=u.s, ooff=phi, in_relu=int(xf is not None))
-            self._conv(d, cur, w, bias, out, in_scale=isc, in_shift=ish, layer=u.name)
+            self._conv(d, cur, w, bias, out, in_scale=isc, in_shift=ish, layer=u.name,
+                       key=f"{u.name}.phase{phi[0]}{phi[1]}{phi[2]}")
         return out
 
     # ---- backward -----------------------------------------------------------------------------
     def backward(self, params: Dict[str, torch.Tensor], state, dlogits: torch.Tensor, need_dx: bool):
         """Returns ({param name: grad}, dx or None)."""
         lib, st = self.lib, self._stream()
-        plan, saved, act_dtype, training = state
+        plan, saved, act_dtype, training, cache = state
+        self._cache = cache
+        batched = cache is not None and cache.ready and cache.scatter_table is not None
+        self._gflat = torch.empty(cache.g_total, dtype=torch.float32, device=dlogits.device) if batched else None
+        side = None
+        if batched and self.overlap_wgrad and _lib._ProfState.profiler is None:
+            if self._side is None or self._side.device != dlogits.device:
+                self._side = torch.cuda.Stream(device=dlogits.device)
+            side = self._side
+            side.wait_stream(torch.cuda.current_stream())
+        self._wstream = side
+        if batched:
+            with torch.cuda.stream(side) if side is not None else _NullCtx():
+                cache.wacc.zero_()
         adt = _DT[act_dtype]
         esz = 2 if act_dtype == torch.float16 else 4
         dev = dlogits.device
@@ -554,22 +686,28 @@ class UnetEngine:
                 roles = T * (-(-u.cout // 8)) * (-(-u.cin // 8))
                 ns = _nsplit(m, roles)
                 total = T * u.cout * u.cin
-                partial = torch.empty((ns, total), dtype=torch.float32, device=dev)
-                _lib.note(u.name, (npix_out * u.cout + m * u.cin) * esz, 2 * m * T * u.cin * u.cout)
-                _lib.check(lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(dcur), None, None, _ptr(a_act), _ptr(partial), ns,
-                                                      st), "wgrad(up)")
-                gw = torch.empty_like(params[u.name + ".weight"])
                 wm = self._wm_up_dgrad(u)
-                _lib.check(lib.hcu_weight_scatter(C.byref(wm), _ptr(partial), ns, total, 1.0, _ptr(inv), 0, _ptr(gw),
-                                                  st), "weight_scatter(up)")
-                grads[u.name + ".weight"] = gw
+                note = (u.name, (npix_out * u.cout + m * u.cin) * esz, 2 * m * T * u.cin * u.cout)
+                grads[u.name + ".weight"] = self._wgrad_dispatch(u.name + ".weight", params[u.name + ".weight"], d, dcur,
+                                                                 None, None, a_act, wm, total, ns, note)
                 # data gradient: strided gather convolution over dOut
-                w = (wm, params[u.name + ".weight"], total)
+                w = (wm, params[u.name + ".weight"], total, u.name + ".weight")
                 dprev = torch.empty((B, u.in_sz[0] * u.in_sz[1] * u.in_sz[2], u.cin), dtype=act_dtype, device=dev)
                 d2 = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin,
                                1, u.k, istep=u.s)
                 self._conv(d2, dcur, w, None, dprev, layer=u.name + ".dgrad")
                 dcur, dcur_dt = dprev, adt
+        if batched:
+            with torch.cuda.stream(side) if side is not None else _NullCtx():
+                _lib.check(lib.hcu_weight_scatter_batch(_ptr(cache.scatter_table), len(cache.scatter_jobs),
+                                                        cache.scatter_blocks, _ptr(cache.wacc), 1.0, _ptr(inv),
+                                                        _ptr(self._gflat), self._stream()), "weight_scatter_batch")
+            if side is not None:
+                torch.cuda.current_stream().wait_stream(side)
+        if cache is not None:
+            cache.bwd_done = True
+        self._keep.clear()
+        self._cache, self._gflat, self._wstream = None, None, None
         return grads, dx
 
     def _materialise(self, t, cp, xf, npix, c, act_dtype):
@@ -596,30 +734,60 @@ class UnetEngine:
         roles = g.groups * T * (-(-g.cin_g // 8)) * (-(-g.cout_g // 8))
         ns = _nsplit(m, roles)
         total = g.groups * T * g.cin_g * g.cout_g
-        partial = torch.empty((ns, total), dtype=torch.float32, device=dy.device)
         esz = 4 if a_dt == _lib.F32 else 2
         nin = B * g.in_sz[0] * g.in_sz[1] * g.in_sz[2] * g.cin_t
-        _lib.note(g.name, (nin + m * g.cout_t) * esz, 2 * m * T * g.cin_g * g.cout_g * g.groups)
+        note = (g.name, (nin + m * g.cout_t) * esz, 2 * m * T * g.cin_g * g.cout_g * g.groups)
         isc, ish = (a_xf[0], a_xf[1]) if a_xf is not None else (None, None)
-        gw = torch.empty_like(wref)
-        wm = self._wm_conv_fwd(g)
-        if self.use_tc and a_dt == _lib.F16 and dy_dt == _lib.F16 and self.lib.hcu_conv_wgrad_tc_supported(C.byref(d)):
-            wacc = partial[0]
-            _lib.check(self.lib.hcu_conv_wgrad_tc(C.byref(d), _ptr(a_in), _ptr(isc), _ptr(ish), _ptr(dy), _ptr(wacc),
-                                                  self._stream()), "wgrad_tc")
-            _lib.check(self.lib.hcu_weight_scatter(C.byref(wm), _ptr(wacc), 1, total, 1.0, _ptr(self._inv), 0, _ptr(gw),
-                                                   self._stream()), "weight_scatter")
+        return self._wgrad_dispatch(g.name + ".weight", wref, d, a_in, isc, ish, dy, self._wm_conv_fwd(g), total, ns, note)
+
+    def _wgrad_dispatch(self, wname, wref, d, a, isc, ish, b, wm, total, ns, note):
+        """Weight gradient of one conv: tensor-core kernel when it takes the descriptor, else the FFMA split-K kernel;
+        result scattered into the reference layout.  With a ready step cache the kernel runs on the side stream
+        (overlapping the data-gradient chain), accumulates into the persistent workspace and the scatter is left to
+        the one batched launch at the end of the backward."""
+        lib, cache = self.lib, self._cache
+        tc = bool(self.use_tc and d.dtype_in == _lib.F16 and d.dtype_out == _lib.F16 and
+                  lib.hcu_conv_wgrad_tc_supported(C.byref(d)))
+        nsplit = 1 if tc else ns
+        if cache is not None and cache.ready and wname in cache.part_off and cache.scatter_jobs[wname][1:] == (nsplit, total):
+            off = cache.part_off[wname]
+            part = cache.wacc[off:off + nsplit * total]
+            goff = cache.g_off[wname]
+            gw = self._gflat[goff:goff + wref.numel()].view(wref.shape)
+            side = self._wstream
+            if side is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                side.wait_event(ev)
+                self._keep.extend(t for t in (a, b, isc, ish) if t is not None)  # alive until the streams join
+            with torch.cuda.stream(side) if side is not None else _NullCtx():
+                _lib.note(*note)
+                if tc:
+                    _lib.check(lib.hcu_conv_wgrad_tc_acc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part),
+                                                         self._stream()), "wgrad_tc")
+                else:
+                    _lib.check(lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part),
+                                                          nsplit, self._stream()), "wgrad")
             return gw
-        _lib.check(self.lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(a_in), _ptr(isc), _ptr(ish), _ptr(dy), _ptr(partial),
-                                                   ns, self._stream()), "wgrad")
-        _lib.check(self.lib.hcu_weight_scatter(C.byref(wm), _ptr(partial), ns, total, 1.0, _ptr(self._inv), 0, _ptr(gw),
-                                               self._stream()), "weight_scatter")
+        partial = torch.empty((nsplit, total), dtype=torch.float32, device=wref.device)
+        gw = torch.empty_like(wref)
+        _lib.note(*note)
+        if tc:
+            _lib.check(lib.hcu_conv_wgrad_tc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial),
+                                             self._stream()), "wgrad_tc")
+        else:
+            _lib.check(lib.hcu_conv_wgrad_partial(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial),
+                                                  nsplit, self._stream()), "wgrad")
+        _lib.check(lib.hcu_weight_scatter(C.byref(wm), _ptr(partial), nsplit, total, 1.0, _ptr(self._inv), 0, _ptr(gw),
+                                          self._stream()), "weight_scatter")
+        if cache is not None and not cache.ready:
+            cache.scatter_jobs[wname] = (HcuWeightMap.from_buffer_copy(wm), nsplit, total)
         return gw
 
     def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype, out_cp=None):
         adt = _DT[act_dtype]
         T = g.taps[0] * g.taps[1] * g.taps[2]
-        w = (self._wm_conv_dgrad(g), wref, g.groups * T * g.cin_g * g.cout_g)
+        w = (self._wm_conv_dgrad(g), wref, g.groups * T * g.cin_g * g.cout_g, g.name + ".weight")
         cpo = out_cp or g.cin_t
         alloc = torch.zeros if cpo != g.cin_t else torch.empty
         dprev = alloc((B, g.in_sz[0] * g.in_sz[1] * g.in_sz[2], cpo), dtype=act_dtype, device=dy.device)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 9
+#define HCU_ABI_VERSION 10
 
 typedef enum HcuStatus {
   HCU_OK = 0,
@@ -138,6 +138,9 @@ int hcu_conv_wgrad_partial(const HcuConvDesc* d, const void* a, const float* a_s
 int hcu_conv_wgrad_tc_supported(const HcuConvDesc* d);
 int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
                       float* wacc, void* stream);
+/* Same, but ACCUMULATES into a `wacc` the caller has zeroed (one memset for every layer of a step). */
+int hcu_conv_wgrad_tc_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
+                          float* wacc, void* stream);
 
 /* ---- weight layout transforms -------------------------------------------------------------
  * Generic strided gather between a reference-layout parameter and a packed GEMM-B tensor
@@ -161,6 +164,27 @@ typedef struct HcuWeightMap {
   int64_t pst[3];
 } HcuWeightMap;
 int hcu_weight_gather(const HcuWeightMap* m, const float* ref, float* packed, void* stream);
+/*
+ * Batched forms (one launch for every layer of a step instead of one per layer; the per-layer calls stay available).
+ * The caller owns a job table: hcu_*_batch_build fills `n` jobs of HCU_BATCH_JOB_BYTES bytes each into HOST memory,
+ * the caller copies them to the device once (they only hold geometry and OFFSETS, no pointers) and passes the device
+ * copy to the launch together with the base pointers.  `blocks` (build output) is the grid size of the launch.
+ *  pack   : job i packs the reference-layout parameter at params + ref_off[i] (float elements) into
+ *           packed + out_off[i] (bytes; hcu_conv_tc_packed_bytes(&descs[i]) bytes, 16-byte aligned offsets).
+ *  scatter: job i reduces nsplit[i] partial results at partial + part_off[i] (float elements, split stride =
+ *           the job's element count) and writes scale * sum into grads + ref_off[i] (float elements) through maps[i]
+ *           (same semantics as hcu_weight_scatter with accumulate = 0).
+ */
+#define HCU_BATCH_JOB_BYTES 256
+int hcu_conv_tc_pack_batch_build(const HcuConvDesc* descs, const HcuWeightMap* maps, const int64_t* ref_off,
+                                 const int64_t* out_off, int32_t n, void* host_jobs, int32_t* blocks);
+int hcu_conv_tc_pack_batch(const void* dev_jobs, int32_t n, int32_t blocks, const float* params, void* packed,
+                           void* stream);
+int hcu_weight_scatter_batch_build(const HcuWeightMap* maps, const int32_t* nsplit, const int64_t* part_off,
+                                   const int64_t* ref_off, int32_t n, void* host_jobs, int32_t* blocks);
+int hcu_weight_scatter_batch(const void* dev_jobs, int32_t n, int32_t blocks, const float* partial, float scale,
+                             const float* dscale, float* grads, void* stream);
+
 int hcu_weight_scatter(const HcuWeightMap* m, const float* partial, int32_t nsplit, int64_t split_stride,
                        float scale, const float* dscale, int32_t accumulate, float* ref, void* stream);
 
