@@ -197,8 +197,10 @@ def conv_desc(dt_in, dt_out, batch, in_size, in_cpitch, in_c_off, in_c_gstep, ci
 
 
 def weight_map(groups, j, na, nb, sg, sa, sb, st, t0=(0, 0, 0), tstep=(1, 1, 1), base=0, fold=0,
-               fold_stride=0) -> HcuWeightMap:
+               fold_stride=0, phase_on=0, ph=(1, 1, 1), pst=(0, 0, 0)) -> HcuWeightMap:
     m = HcuWeightMap()
+    m.phase_on, m.ph = phase_on, _i3(ph)
+    m.pst = (C.c_int64 * 3)(*[int(e) for e in pst])
     m.groups, m.j, m.na, m.nb = groups, _i3(j), na, nb
     m.base, m.sg, m.sa, m.sb = base, sg, sa, sb
     m.st = (C.c_int64 * 3)(*[int(e) for e in st])
@@ -401,6 +403,33 @@ class UnetEngine:
                           tstep=tuple(-u.s[d] for d in range(3)))
 
     @staticmethod
+    def _up_fusable(u: UpGeom) -> bool:
+        """All stride phases share one tap count (kernel % stride == 0) and every phase is a whole number of 8-channel
+        groups: the transposed convolution runs as ONE stride-1 convolution with the phases folded into the channels."""
+        return all(u.k[d] % u.s[d] == 0 for d in range(3)) and u.cout % 8 == 0 and u.cin % 8 == 0 and \
+            u.s[0] * u.s[1] * u.s[2] > 1
+
+    @staticmethod
+    def _wm_up_fused(u: UpGeom, J) -> HcuWeightMap:
+        """GEMM-B [taps J][cin][(phase, cout)]: W[ci][co][phi + s*(J-1-t)] (forward and weight gradient)."""
+        T = u.k[0] * u.k[1] * u.k[2]
+        st = (u.k[1] * u.k[2], u.k[2], 1)
+        return weight_map(1, J, u.cin, u.cout, sg=0, sa=u.cout * T, sb=T, st=st,
+                          t0=tuple(u.s[d] * (J[d] - 1) for d in range(3)), tstep=tuple(-u.s[d] for d in range(3)),
+                          phase_on=2, ph=u.s, pst=st)
+
+    @staticmethod
+    def _wm_up_fused_dgrad(u: UpGeom, J) -> HcuWeightMap:
+        """GEMM-B [taps J][(phase, cout)][cin]: W[ci][co][phi + s*t] (data gradient: a valid correlation over the phases)."""
+        T = u.k[0] * u.k[1] * u.k[2]
+        st = (u.k[1] * u.k[2], u.k[2], 1)
+        return weight_map(1, J, u.cout, u.cin, sg=0, sa=T, sb=u.cout * T, st=st, tstep=u.s, phase_on=1, ph=u.s, pst=st)
+
+    @staticmethod
+    def _phase_word(s3) -> int:
+        return int(s3[0]) | (int(s3[1]) << 8) | (int(s3[2]) << 16)
+
+    @staticmethod
     def _wm_up_dgrad(u: UpGeom) -> HcuWeightMap:
         T = u.k[0] * u.k[1] * u.k[2]
         return weight_map(1, u.k, u.cout, u.cin, sg=0, sa=T, sb=u.cout * T, st=(u.k[1] * u.k[2], u.k[2], 1))
@@ -554,6 +583,17 @@ class UnetEngine:
         wt, bias = params[u.name + ".weight"], params[u.name + ".bias"]
         out = torch.empty((B, u.out_sz[0] * u.out_sz[1] * u.out_sz[2], u.cout), dtype=act_dtype, device=cur.device)
         isc, ish = (xf[0], xf[1]) if xf is not None else (None, None)
+        if self.use_tc and act_dtype == torch.float16 and self._up_fusable(u):
+            nph = u.s[0] * u.s[1] * u.s[2]
+            J = tuple(u.k[d] // u.s[d] for d in range(3))
+            Q = tuple(u.out_sz[d] // u.s[d] for d in range(3))
+            d = conv_desc(adt, adt, B, u.in_sz, cp, 0, u.cin, u.cin, Q, u.out_sz, u.cout, 0, nph * u.cout, 1, J,
+                          pad=tuple(j - 1 for j in J), ostep=u.s, in_relu=int(xf is not None))
+            d.ophase = self._phase_word(u.s)
+            if self.lib.hcu_conv_tc_supported(C.byref(d)):
+                w = (self._wm_up_fused(u, J), wt, nph * J[0] * J[1] * J[2] * u.cin * u.cout, u.name + ".weight")
+                self._conv(d, cur, w, bias, out, in_scale=isc, in_shift=ish, layer=u.name, key=u.name + ".fused")
+                return out
         for phi, J, Q in self._phases(u):
             w = (self._wm_up_phase(u, phi, J), wt, J[0] * J[1] * J[2] * u.cin * u.cout, u.name + ".weight")
             d = conv_desc(adt, adt, B, u.in_sz, cp, 0, u.cin, u.cin, Q, u.out_sz, u.cout, 0, u.cout, 1, J,
@@ -675,27 +715,50 @@ class UnetEngine:
                 _, u, a_in, a_cp, a_xf = item
                 npix_out = B * u.out_sz[0] * u.out_sz[1] * u.out_sz[2]
                 grads[u.name + ".bias"] = self._colsum(dcur, dcur_dt, npix_out, u.cout, scratch)
-                # weight gradient: R[t][co][ci] = sum_i dOut[i*s + t][co] * act(In[i])[ci]
                 T = u.k[0] * u.k[1] * u.k[2]
                 m = B * u.in_sz[0] * u.in_sz[1] * u.in_sz[2]
-                # the gather side (a) is dOut, the dense side (b) is the up-conv's input: its pending BN+ReLU has to
-                # be materialised once for the dense side
-                a_act = self._materialise(a_in, a_cp, a_xf, m, u.cin, act_dtype)
-                d = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin, 1,
-                              u.k, istep=u.s)
-                roles = T * (-(-u.cout // 8)) * (-(-u.cin // 8))
-                ns = _nsplit(m, roles)
-                total = T * u.cout * u.cin
-                wm = self._wm_up_dgrad(u)
-                note = (u.name, (npix_out * u.cout + m * u.cin) * esz, 2 * m * T * u.cin * u.cout)
-                grads[u.name + ".weight"] = self._wgrad_dispatch(u.name + ".weight", params[u.name + ".weight"], d, dcur,
-                                                                 None, None, a_act, wm, total, ns, note)
-                # data gradient: strided gather convolution over dOut
-                w = (wm, params[u.name + ".weight"], total, u.name + ".weight")
-                dprev = torch.empty((B, u.in_sz[0] * u.in_sz[1] * u.in_sz[2], u.cin), dtype=act_dtype, device=dev)
-                d2 = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin,
-                               1, u.k, istep=u.s)
-                self._conv(d2, dcur, w, None, dprev, layer=u.name + ".dgrad")
+                wt = params[u.name + ".weight"]
+                dprev = torch.empty((B, m // B, u.cin), dtype=act_dtype, device=dev)
+                done = False
+                if self.use_tc and act_dtype == torch.float16 and dcur_dt == _lib.F16 and self._up_fusable(u):
+                    # stride phases folded into the channels: both gradients on the tensor-core kernels, one launch each
+                    nph = u.s[0] * u.s[1] * u.s[2]
+                    J = tuple(u.k[d] // u.s[d] for d in range(3))
+                    Q = tuple(u.out_sz[d] // u.s[d] for d in range(3))
+                    isc, ish = (a_xf[0], a_xf[1]) if a_xf is not None else (None, None)
+                    dw = conv_desc(adt, adt, B, u.in_sz, a_cp, 0, u.cin, u.cin, Q, u.out_sz, nph * u.cout, 0, nph * u.cout,
+                                   1, J, pad=tuple(j - 1 for j in J), ostep=u.s, in_relu=int(a_xf is not None))
+                    dw.ophase = self._phase_word(u.s)
+                    dd = conv_desc(adt, adt, B, Q, nph * u.cout, 0, nph * u.cout, nph * u.cout, u.in_sz, u.in_sz, u.cin, 0,
+                                   u.cin, 1, J)
+                    dd.iphase = self._phase_word(u.s)
+                    if lib.hcu_conv_wgrad_tc_supported(C.byref(dw)) and lib.hcu_conv_tc_supported(C.byref(dd)):
+                        total = nph * J[0] * J[1] * J[2] * u.cin * u.cout
+                        note = (u.name, (npix_out * u.cout + m * u.cin) * esz, 2 * m * T * u.cin * u.cout)
+                        grads[u.name + ".weight"] = self._wgrad_dispatch(u.name + ".weight", wt, dw, a_in, isc, ish, dcur,
+                                                                         self._wm_up_fused(u, J), total, 1, note)
+                        w = (self._wm_up_fused_dgrad(u, J), wt, total, u.name + ".weight")
+                        self._conv(dd, dcur, w, None, dprev, layer=u.name + ".dgrad")
+                        done = True
+                if not done:
+                    # weight gradient: R[t][co][ci] = sum_i dOut[i*s + t][co] * act(In[i])[ci]
+                    # the gather side (a) is dOut, the dense side (b) is the up-conv's input: its pending BN+ReLU has to
+                    # be materialised once for the dense side
+                    a_act = self._materialise(a_in, a_cp, a_xf, m, u.cin, act_dtype)
+                    d = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin, 1,
+                                  u.k, istep=u.s)
+                    roles = T * (-(-u.cout // 8)) * (-(-u.cin // 8))
+                    ns = _nsplit(m, roles)
+                    total = T * u.cout * u.cin
+                    wm = self._wm_up_dgrad(u)
+                    note = (u.name, (npix_out * u.cout + m * u.cin) * esz, 2 * m * T * u.cin * u.cout)
+                    grads[u.name + ".weight"] = self._wgrad_dispatch(u.name + ".weight", wt, d, dcur, None, None, a_act, wm,
+                                                                     total, ns, note)
+                    # data gradient: strided gather convolution over dOut
+                    w = (wm, wt, total, u.name + ".weight")
+                    d2 = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin,
+                                   1, u.k, istep=u.s)
+                    self._conv(d2, dcur, w, None, dprev, layer=u.name + ".dgrad")
                 dcur, dcur_dt = dprev, adt
         if batched:
             with torch.cuda.stream(side) if side is not None else _NullCtx():
