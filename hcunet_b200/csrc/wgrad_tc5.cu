@@ -1,0 +1,494 @@
+// Weight gradient of the gather-convolution on the 5th-generation tensor cores, for the CHANNEL-RICH levels.
+//
+//   dW[tap][ci][co] = sum_{n, q} act(a[n, q + shift(tap), ci]) * dy[n, q, co]
+//
+// Same "flat shift" staging as conv_tc.cu / wgrad_mma.cu: an x-plane is a flat array of (y, z) pixels stored in
+// shared memory as [channel-plane of 8][pixel][8 x fp16].  Read with the PIXEL index as the GEMM's K dimension this is
+// exactly the canonical no-swizzle MN-MAJOR UMMA operand: 8 channels (M or N) contiguous in 16 bytes, the 8 pixels of
+// a K-group 16 bytes apart (LBO = 128 B to the next group), channel planes SBO = plane stride apart.  A filter tap
+// only moves the START ADDRESS of the A operand by a whole number of pixels, so
+//   D[tap] (M = Cin rows, N = Cout columns, fp32 in TMEM) += A(a-plane shifted by the tap)^T * B(dy-plane)
+// is one tcgen05.mma (M = 128, K = 16 pixels) per tap and 16-pixel chunk, with nothing re-arranged.  Rows >= Cin of the
+// M = 128 tile read whatever follows in shared memory and are never stored.
+//
+// A CTA owns (image n, x-segment, run of M flat positions, group of taps): the taps x Cout accumulators of a layer
+// (up to 18 x 128 columns) exceed the 512 TMEM columns, so the taps are split into groups of <= 512 / Cout over CTAs --
+// on these levels the pixels are few and the extra staging is cheap, the tap split is what fills the SMs.
+// Roles (288 threads): warps 0-3 epilogue (TMEM lane = ci; vector red.add into the caller's zeroed accumulator),
+// warps 4-7 producers (cp.async, previous layer's BatchNorm + ReLU applied in place, wrap-around / out-of-range dy
+// positions zero-filled), warp 8 TMEM allocation + MMA issue.
+//
+// wgrad_mma.cu (mma.sync) stays the kernel of the 8/16-channel levels, where M = 128 rows would be 94 % padding.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace hcu {
+namespace wg5 {
+
+constexpr int kThreads = 288;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kMaxTaps = 64;
+
+struct Params {
+  const __half* a;
+  const __half* dy;
+  float* wacc;  // fp32 [taps][cin][cout], zeroed by the caller
+  const float* a_scale;
+  const float* a_shift;
+  int N, IX, IY, IZ, Cp, P, cin;
+  int OX, OY, OZ, Cop, Po, cout;
+  int KX, KY, KZ, dx, dy_, dz, px, py, pz;
+  int Yv, Zv;
+  int M, RUN, PS, SLOT, DPS, DSLOT, R, RD, D;
+  int Nc, TG, NG, taps;
+  int n_runs, Lx, n_xseg;
+  int in_relu, vec4;
+  int off_d, off_bar, smem_bytes, tmem_cols;
+  // per tap: tx and the byte offset (>> 4) of its (ty, tz) shift inside a ring slot
+  int tap_tx[kMaxTaps];
+  int tap_off[kMaxTaps];
+};
+
+// ---- PTX wrappers (see conv_tc.cu for the commented originals) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(20000u)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n.reg .b32 rx;\n.reg .pred px;\n"
+      "elect.sync rx|px, %1;\n"
+      "@px mov.s32 %0, 1;\n}"
+      : "+r"(pred)
+      : "r"(0xffffffffu));
+  return pred != 0;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ uint4 bn_relu8(uint4 v, const float* sc, const float* sh, int relu) {
+  __half2* h = reinterpret_cast<__half2*>(&v);
+  const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 f = __half22float2(h[k]);
+    f.x = fmaf(f.x, sc[2 * k], sh[2 * k]);
+    f.y = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
+    h[k] = __floats2half2_rn(f.x, f.y);
+    if (relu) h[k] = __hmax2_nan(h[k], zero);
+  }
+  return v;
+}
+
+// MN-major, no swizzle: LBO = next 8-row K group, SBO = next 8-element M/N group (channel plane)
+__device__ __forceinline__ uint64_t desc_hi_mn(uint32_t sbo_bytes) {
+  return (uint64_t)(((sbo_bytes >> 4) & 0x3FFF) | (1u << 14)) << 32;  // SBO | descriptor version 1 (bit 46)
+}
+
+__global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int R = p.R, RD = p.RD;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  // barrier map: full_a[R], empty_a[R], full_d[RD], empty_d[RD], done
+  const uint32_t bar_fa = smem_u32(bars), bar_ea = bar_fa + 8 * R, bar_fd = bar_ea + 8 * R, bar_ed = bar_fd + 8 * RD,
+                 bar_done = bar_ed + 8 * RD;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (2 * R + 2 * RD + 1));
+  const uint32_t a_base = smem_u32(smem), d_base = smem_u32(smem + p.off_d);
+
+  // ---- work item ---------------------------------------------------------------------------------
+  int item = blockIdx.x;
+  const int grp = item % p.NG; item /= p.NG;
+  const int run = item % p.n_runs; item /= p.n_runs;
+  const int xs = item % p.n_xseg;
+  const int n = item / p.n_xseg;
+  const int x0 = xs * p.Lx;
+  const int nout = min(p.Lx, p.OX - x0);
+  const int q0 = run * p.M;
+  const int t_lo = grp * p.TG, t_hi = min(p.taps, t_lo + p.TG);
+  const int txlo = p.tap_tx[t_lo], txhi = p.tap_tx[t_hi - 1];
+  const int span = (txhi - txlo) * p.dx + 1;   // a-planes one output plane needs
+  const int nplanes = nout + span - 1;          // a-planes this CTA stages: virtual x = x0 + txlo*dx + j
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < R; ++i) { mbar_init(bar_fa + 8 * i, 4); mbar_init(bar_ea + 8 * i, 1); }
+      for (int i = 0; i < RD; ++i) { mbar_init(bar_fd + 8 * i, 4); mbar_init(bar_ed + 8 * i, 1); }
+      mbar_init(bar_done, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // =========================================== PRODUCERS ===========================================
+    const int ptid = threadIdx.x - 128;
+    // a: [P planes][RUN pixels]
+    const int plane = ptid % p.P, pix0 = ptid / p.P, pstep = 128 / p.P;
+    const int nchunk = (p.RUN - pix0 + pstep - 1) / pstep;
+    const bool xf = p.a_scale != nullptr;
+    const int relu = p.in_relu;
+    float sc[8], sh[8];
+    if (xf) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = p.a_scale[plane * 8 + j]; sh[j] = p.a_shift[plane * 8 + j]; }
+    }
+    const int qf = q0 + pix0;
+    const int yv0 = qf / p.Zv, zv0 = qf - yv0 * p.Zv;
+    const int ystep = pstep / p.Zv, zstep = pstep - ystep * p.Zv;
+    const __half* a_n = p.a + (size_t)n * p.IX * p.IY * p.IZ * p.Cp + plane * 8;
+    const size_t a_xs = (size_t)p.IY * p.IZ * p.Cp;
+    // dy: [Po planes][M pixels]
+    const int dplane = ptid % p.Po, dpix0 = ptid / p.Po, dstep = 128 / p.Po;
+    const int nchunk_d = (p.M - dpix0 + dstep - 1) / dstep;
+    const int dqf = q0 + dpix0;
+    const int dy0 = dqf / p.Zv, dz0 = dqf - dy0 * p.Zv;
+    const int dystep = dstep / p.Zv, dzstep = dstep - dystep * p.Zv;
+    const __half* d_n = p.dy + (size_t)n * p.OX * p.OY * p.OZ * p.Cop + dplane * 8;
+    const size_t d_xs = (size_t)p.OY * p.OZ * p.Cop;
+
+    const int D = p.D;
+    // One pipeline over "steps": step j stages a-plane j (j < nplanes) and dy-plane j - (span - 1) (when >= 0).
+    int sa_i = 0, sa_f = 0, sd_i = 0, sd_f = 0;
+    uint32_t par_a = 1, par_d = 1;
+    auto finish = [&](int jf) {
+      // a-plane jf
+      if (xf) {
+        const int xm = x0 + txlo * p.dx + jf - p.px;
+        if (xm >= 0 && xm < p.IX) {
+          unsigned char* dp = smem + sa_f * p.SLOT + plane * p.PS + pix0 * 16;
+          int yv = yv0, zv = zv0;
+          for (int c = 0; c < nchunk; ++c) {
+            const int ym = yv - p.py, zm = zv - p.pz;
+            if (ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ) {
+              uint4* q = reinterpret_cast<uint4*>(dp + (size_t)c * pstep * 16);
+              *q = bn_relu8(*q, sc, sh, relu);
+            }
+            zv += zstep; yv += ystep;
+            if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar_fa + 8 * sa_f);
+        if (jf >= span - 1) mbar_arrive(bar_fd + 8 * sd_f);
+      }
+      if (++sa_f == R) sa_f = 0;
+      if (jf >= span - 1 && ++sd_f == RD) sd_f = 0;
+    };
+    for (int j = 0; j < nplanes + D; ++j) {
+      if (D > 0 && j >= D) {
+        if (D == 1) cp_async_wait<0>();
+        else cp_async_wait<1>();
+        finish(j - D);
+      }
+      if (j < nplanes) {
+        mbar_wait(bar_ea + 8 * sa_i, par_a);
+        {
+          const int xm = x0 + txlo * p.dx + j - p.px;
+          const bool xok = xm >= 0 && xm < p.IX;
+          const __half* a_x = a_n + (size_t)(xok ? xm : 0) * a_xs;
+          const uint32_t dst = a_base + (uint32_t)(sa_i * p.SLOT + plane * p.PS + pix0 * 16);
+          int yv = yv0, zv = zv0;
+          for (int c = 0; c < nchunk; ++c) {
+            const int ym = yv - p.py, zm = zv - p.pz;
+            const bool ok = xok && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
+            cp_async16(dst + c * pstep * 16, ok ? a_x + ((size_t)ym * p.IZ + zm) * p.Cp : a_n, ok ? 16u : 0u);
+            zv += zstep; yv += ystep;
+            if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+          }
+        }
+        if (++sa_i == R) { sa_i = 0; par_a ^= 1; }
+        if (j >= span - 1) {
+          mbar_wait(bar_ed + 8 * sd_i, par_d);
+          const int i = j - (span - 1);  // output plane
+          const __half* d_x = d_n + (size_t)(x0 + i) * d_xs;
+          const uint32_t dst = d_base + (uint32_t)(sd_i * p.DSLOT + dplane * p.DPS + dpix0 * 16);
+          int oy = dy0, oz = dz0;
+          for (int c = 0; c < nchunk_d; ++c) {
+            const bool ok = oy < p.OY && oz < p.OZ;
+            cp_async16(dst + c * dstep * 16, ok ? d_x + ((size_t)oy * p.OZ + oz) * p.Cop : d_n, ok ? 16u : 0u);
+            oz += dzstep; oy += dystep;
+            if (oz >= p.Zv) { oz -= p.Zv; ++oy; }
+          }
+          if (++sd_i == RD) { sd_i = 0; par_d ^= 1; }
+        }
+      }
+      cp_async_commit();
+      if (D == 0) {
+        cp_async_wait<0>();
+        finish(j);
+      }
+    }
+  } else if (warp == 8) {
+    // =========================================== MMA ISSUER ==========================================
+    const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Nc >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t a_hi = desc_hi_mn((uint32_t)p.PS), b_hi = desc_hi_mn((uint32_t)p.DPS);
+    const uint32_t lbo = (128u >> 4) << 16;
+    const int nchunks = p.M / 16;
+    int wa = 0, wd = 0, next_a = 0;
+    uint32_t pa = 0, pd = 0;
+    int i_mod = 0;  // ring slot of a-plane i (the oldest plane output i needs)
+    for (int i = 0; i < nout; ++i) {
+      for (; next_a <= i + span - 1; ++next_a) {
+        mbar_wait(bar_fa + 8 * wa, pa);
+        if (++wa == R) { wa = 0; pa ^= 1; }
+      }
+      mbar_wait(bar_fd + 8 * wd, pd);
+      tc_fence_after();
+      const uint32_t bbase = ((d_base + (uint32_t)(wd * p.DSLOT)) >> 4) | lbo;
+      for (int t = t_lo; t < t_hi; ++t) {
+        int sl = i_mod + (p.tap_tx[t] - txlo) * p.dx;
+        sl -= sl >= R ? R : 0;
+        const uint32_t abase = (((a_base + (uint32_t)(sl * p.SLOT)) >> 4) + (uint32_t)p.tap_off[t]) | lbo;
+        const uint32_t tcol = tmem_base + (uint32_t)((t - t_lo) * p.Nc);
+        const uint32_t first = (uint32_t)i;  // accumulate flag of chunk 0: overwrite only on the CTA's first plane
+        if (elect_one()) {
+          for (int c = 0; c < nchunks; ++c)
+            umma_f16(tcol, a_hi | (uint64_t)(abase + (uint32_t)(c * 16)), b_hi | (uint64_t)(bbase + (uint32_t)(c * 16)), idesc,
+                     first | (uint32_t)c);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) {
+        umma_commit(bar_ea + 8 * i_mod);  // a-plane i is not needed by later outputs
+        umma_commit(bar_ed + 8 * wd);
+        if (i == nout - 1) umma_commit(bar_done);
+      }
+      __syncwarp();
+      if (++wd == RD) { wd = 0; pd ^= 1; }
+      i_mod = i_mod + 1 == R ? 0 : i_mod + 1;
+    }
+  } else {
+    // =========================================== EPILOGUE ============================================
+    const int ci = threadIdx.x;  // TMEM lane == accumulator row == input channel
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    mbar_wait(bar_done, 0);
+    tc_fence_after();
+    for (int t = t_lo; t < t_hi; ++t) {
+      for (int cc = 0; cc < p.Nc; cc += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + lane_base + (uint32_t)((t - t_lo) * p.Nc + cc), v);
+        if (ci < p.cin) {
+          float* o = p.wacc + ((size_t)t * p.cin + ci) * p.cout + cc;
+          if (p.vec4) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              if (cc + j < p.cout) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (cc + j < p.cout) atomicAdd(o + j, v[j]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+static const char* configure(const HcuConvDesc* d, Params& p) {
+  if (d->dtype_in != HCU_F16 || d->dtype_out != HCU_F16) return "fp16 only";
+  if (d->groups != 1) return "groups != 1";
+  if (d->ophase || d->iphase) return "stride phases";
+  if (d->in_cpitch % 8 != 0 || d->in_c_off != 0 || d->cin > d->in_cpitch) return "input channel layout";
+  if (d->out_cpitch % 8 != 0 || d->out_c_off != 0 || d->cout > d->out_cpitch) return "dy channel layout";
+  const int P = d->in_cpitch / 8, Po = d->out_cpitch / 8;
+  if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16) return "input channel pitch";
+  if (Po != 1 && Po != 2 && Po != 4 && Po != 8 && Po != 16) return "dy channel pitch";
+  if (d->cin > 128 || d->cout > 256) return "more than 128 input / 256 output channels";
+  for (int i = 0; i < 3; ++i)
+    if (d->istep[i] != 1 || d->ostep[i] != 1 || d->ooff[i] != 0 || d->out_tsize[i] != d->out_size[i]) return "strided";
+  p.N = d->batch; p.IX = d->in_size[0]; p.IY = d->in_size[1]; p.IZ = d->in_size[2];
+  p.Cp = d->in_cpitch; p.P = P; p.cin = d->cin;
+  p.OX = d->out_size[0]; p.OY = d->out_size[1]; p.OZ = d->out_size[2];
+  p.Cop = d->out_cpitch; p.Po = Po; p.cout = d->cout;
+  p.KX = d->taps[0]; p.KY = d->taps[1]; p.KZ = d->taps[2];
+  p.dx = d->dil[0]; p.dy_ = d->dil[1]; p.dz = d->dil[2];
+  p.px = d->pad[0]; p.py = d->pad[1]; p.pz = d->pad[2];
+  p.Yv = p.OY + (p.KY - 1) * p.dy_;
+  p.Zv = p.OZ + (p.KZ - 1) * p.dz;
+  p.taps = p.KX * p.KY * p.KZ;
+  if (p.taps > kMaxTaps) return "too many taps";
+  p.Nc = round_up(d->cout, 16);
+  if (p.Nc > 256) return "too many output channels";
+  p.TG = std::min(p.taps, 512 / p.Nc);
+  p.NG = (p.taps + p.TG - 1) / p.TG;
+  {
+    int cols = p.TG * p.Nc, t = 32;
+    while (t < cols) t <<= 1;
+    p.tmem_cols = t;
+  }
+  const int halo = (p.KY - 1) * p.dy_ * p.Zv + (p.KZ - 1) * p.dz;
+  const int plane_q = p.Yv * p.Zv;
+  // widest x extent a tap group can have
+  int max_span = 1;
+  for (int g = 0; g < p.NG; ++g) {
+    const int lo = g * p.TG, hi = std::min(p.taps, lo + p.TG) - 1;
+    max_span = std::max(max_span, (hi / (p.KY * p.KZ) - lo / (p.KY * p.KZ)) * p.dx + 1);
+  }
+  if (max_span > 8) return "x extent";
+  const int m_cands[3] = {256, 128, 64};
+  const int want[3] = {3, 2, 0};  // ring slack beyond the span: (look-ahead D, published slack) = (2,1), (1,1), (0,0)
+  for (int wi = 0; wi < 3; ++wi) {
+    for (int mi = 0; mi < 3; ++mi) {
+      const int M = m_cands[mi];
+      if (M > 64 && M / 2 >= plane_q) continue;
+      const int run = M + halo;
+      int ps = run * 16, dps = M * 16;
+      // spread the channel planes over the banks for the producers' 16-byte accesses (conv_tc.cu does the same):
+      // plane stride = g (mod 2g), g = max(16, 128 / planes)
+      if (P > 1) { const int g = P >= 8 ? 16 : 128 / P; ps = round_up(ps, 2 * g) + g; }
+      if (Po > 1) { const int g = Po >= 8 ? 16 : 128 / Po; dps = round_up(dps, 2 * g) + g; }
+      const int slot = ps * P, dslot = dps * Po;
+      const int R = max_span + want[wi], RD = want[wi] >= 2 ? 3 : 2;
+      const int D = want[wi] >= 3 ? 2 : (want[wi] >= 2 ? 1 : 0);
+      // the M = 128 / N = Nc tiles read 16 (Nc / 8) planes from a slot's base: keep those reads inside the allocation
+      const int a_end = (R - 1) * slot + 16 * ps;
+      const int off_d = round_up(std::max(R * slot, a_end), 128);
+      const int d_end = off_d + (RD - 1) * dslot + (p.Nc / 8) * dps;
+      const int off_bar = round_up(std::max(off_d + RD * dslot, d_end), 128);
+      const int total = off_bar + 8 * (2 * R + 2 * RD + 1) + 16 + 128;
+      if (total > kSmemLimit) continue;
+      if (ps / 16 > 0x3FFF || dps / 16 > 0x3FFF) continue;
+      p.M = M; p.RUN = run; p.PS = ps; p.SLOT = slot; p.DPS = dps; p.DSLOT = dslot; p.R = R; p.RD = RD; p.D = D;
+      p.off_d = off_d; p.off_bar = off_bar; p.smem_bytes = total;
+      p.n_runs = (plane_q + M - 1) / M;
+      for (int t = 0; t < p.taps; ++t) {
+        const int tz = t % p.KZ, tq = t / p.KZ;
+        const int ty = tq % p.KY, tx = tq / p.KY;
+        p.tap_tx[t] = tx;
+        p.tap_off[t] = ty * p.dy_ * p.Zv + tz * p.dz;  // pixels == 16-byte units
+      }
+      return nullptr;
+    }
+  }
+  return "does not fit in shared memory";
+}
+
+}  // namespace wg5
+}  // namespace hcu
+
+using namespace hcu;
+
+extern "C" int hcu_conv_wgrad_tc5_supported(const HcuConvDesc* d) {
+  if (d == nullptr) return 0;
+  wg5::Params p;
+  return wg5::configure(d, p) == nullptr ? 1 : 0;
+}
+
+extern "C" int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
+                                      const void* dy, float* wacc, void* stream) {
+  HCU_CHECK_ARG(d && a && dy && wacc, "wgrad_tc5: null pointer");
+  HCU_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr), "wgrad_tc5: a_scale/a_shift must come together");
+  wg5::Params p;
+  const char* why = wg5::configure(d, p);
+  if (why != nullptr) {
+    set_error("wgrad_tc5: unsupported descriptor (%s)", why);
+    return HCU_ERR_UNSUPPORTED;
+  }
+  p.a = (const __half*)a; p.dy = (const __half*)dy; p.wacc = wacc; p.a_scale = a_scale; p.a_shift = a_shift;
+  p.in_relu = d->in_relu;
+  p.vec4 = (d->cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(wacc) & 15) == 0);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wg5::wgrad_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg5::kSmemLimit);
+    if (e != cudaSuccess) { set_error("wgrad_tc5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
+    attr = true;
+  }
+  // x segmentation: about two waves of CTAs, segments no shorter than 4 planes
+  const long long base_items = (long long)p.N * p.n_runs * p.NG;
+  const int per_sm = std::max(1, std::min(233472 / (p.smem_bytes + 1024), 512 / p.tmem_cols));
+  const long long target = 2LL * per_sm * num_sms();
+  int nseg = (int)((target + base_items - 1) / base_items);
+  nseg = std::max(1, std::min(nseg, (p.OX + 3) / 4));
+  p.Lx = (p.OX + nseg - 1) / nseg;
+  p.n_xseg = (p.OX + p.Lx - 1) / p.Lx;
+  const long long grid = base_items * p.n_xseg;
+  HCU_CHECK_ARG(grid <= 0x7fffffffLL, "wgrad_tc5: grid too large");
+  wg5::wgrad_tc5_kernel<<<(unsigned)grid, wg5::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(p);
+  HCU_CHECK_LAUNCH("wgrad_tc5");
+  return 0;
+}

@@ -314,6 +314,7 @@ class UnetEngine:
         self._plans: Dict[tuple, Plan] = {}
         self._inv = None
         self.use_tc = os.environ.get("HCUNET_TC", "1") != "0"
+        self.use_tc5 = os.environ.get("HCUNET_WGRAD5", "1") != "0"      # tcgen05 weight gradient on the channel-rich levels
         self.use_batch = os.environ.get("HCUNET_BATCH", "1") != "0"      # batched packs / scatters (_StepCache)
         self.overlap_wgrad = os.environ.get("HCUNET_OVERLAP", "1") != "0"  # weight gradients on a side stream
         self._caches: Dict[tuple, _StepCache] = {}
@@ -809,8 +810,11 @@ class UnetEngine:
         (overlapping the data-gradient chain), accumulates into the persistent workspace and the scatter is left to
         the one batched launch at the end of the backward."""
         lib, cache = self.lib, self._cache
-        tc = bool(self.use_tc and d.dtype_in == _lib.F16 and d.dtype_out == _lib.F16 and
-                  lib.hcu_conv_wgrad_tc_supported(C.byref(d)))
+        f16 = self.use_tc and d.dtype_in == _lib.F16 and d.dtype_out == _lib.F16
+        # channel-rich levels: tcgen05 kernel (M = 128 rows of Cin would be mostly padding below 32 input channels)
+        tc5 = bool(f16 and self.use_tc5 and (d.in_cpitch >= 32 or (d.in_cpitch >= 16 and d.cout >= 32)) and
+                   lib.hcu_conv_wgrad_tc5_supported(C.byref(d)))
+        tc = bool(f16 and (tc5 or lib.hcu_conv_wgrad_tc_supported(C.byref(d))))
         nsplit = 1 if tc else ns
         if cache is not None and cache.ready and wname in cache.part_off and cache.scatter_jobs[wname][1:] == (nsplit, total):
             off = cache.part_off[wname]
@@ -825,7 +829,10 @@ class UnetEngine:
                 self._keep.extend(t for t in (a, b, isc, ish) if t is not None)  # alive until the streams join
             with torch.cuda.stream(side) if side is not None else _NullCtx():
                 _lib.note(*note)
-                if tc:
+                if tc5:
+                    _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part),
+                                                          self._stream()), "wgrad_tc5")
+                elif tc:
                     _lib.check(lib.hcu_conv_wgrad_tc_acc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part),
                                                          self._stream()), "wgrad_tc")
                 else:
@@ -835,7 +842,11 @@ class UnetEngine:
         partial = torch.empty((nsplit, total), dtype=torch.float32, device=wref.device)
         gw = torch.empty_like(wref)
         _lib.note(*note)
-        if tc:
+        if tc5:
+            partial.zero_()
+            _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial),
+                                                  self._stream()), "wgrad_tc5")
+        elif tc:
             _lib.check(lib.hcu_conv_wgrad_tc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial),
                                              self._stream()), "wgrad_tc")
         else:

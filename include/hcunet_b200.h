@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 10
+#define HCU_ABI_VERSION 11
 
 typedef enum HcuStatus {
   HCU_OK = 0,
@@ -141,6 +141,12 @@ int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const float* a_scale,
 /* Same, but ACCUMULATES into a `wacc` the caller has zeroed (one memset for every layer of a step). */
 int hcu_conv_wgrad_tc_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
                           float* wacc, void* stream);
+/* tcgen05 flavour for the channel-rich levels (wgrad_tc5.cu): the staged planes are MN-major UMMA operands with the
+ * pixel index as K, one M = 128 (Cin rows) x N = Cout MMA per tap and 16 pixels, taps split over CTAs by TMEM capacity.
+ * Same contract as hcu_conv_wgrad_tc_acc (accumulates into a zeroed fp32 [taps][cin][cout]). */
+int hcu_conv_wgrad_tc5_supported(const HcuConvDesc* d);
+int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
+                           float* wacc, void* stream);
 
 /* ---- weight layout transforms -------------------------------------------------------------
  * Generic strided gather between a reference-layout parameter and a packed GEMM-B tensor

@@ -154,7 +154,7 @@ def test_conv_tc_agrees_with_simt_kernel():
 
 
 # ---- weight gradient on tensor cores (wgrad_mma.cu) ---------------------------------------------------------
-def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=False):
+def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=False, use_tc5=False):
     """x [N,Cin,...] activations (pre-transform), dy [N,Cout,...] -> dW [Cout,Cin,kx,ky,kz] fp32."""
     from hcunet_b200 import _lib
     from hcunet_b200.engine import conv_desc
@@ -177,6 +177,10 @@ def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=
         part = torch.empty((ns, T * cin * cout), device="cuda")
         _lib.check(lib.hcu_conv_wgrad_partial(C.byref(d), P(xin), P(isc), P(ish), P(dyin), P(part), ns, stream()))
         wacc = part.sum(0)
+    elif use_tc5:
+        assert lib.hcu_conv_wgrad_tc5_supported(C.byref(d)) == 1
+        wacc = torch.zeros((T * cin * cout,), device="cuda")   # the tcgen05 kernel accumulates into a zeroed buffer
+        _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), P(xin), P(isc), P(ish), P(dyin), P(wacc), stream()), "wgrad_tc5")
     else:
         assert lib.hcu_conv_wgrad_tc_supported(C.byref(d)) == 1
         wacc = torch.full((T * cin * cout,), float("nan"), device="cuda")
@@ -213,6 +217,39 @@ def test_wgrad_tc_matches_fp32(case):
     got = run_wgrad(x, dy, k, dil=dil, cpitch=cp)
     assert not torch.isnan(got).any()
     assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)   # exact fp16 products, fp32 accumulate
+
+
+# ---- weight gradient on tcgen05 (wgrad_tc5.cu, channel-rich levels) -----------------------------------------
+WG5_CASES = [c for c in WG_CASES if c[1] >= 16 or c[2] >= 32] + [
+    (2, 32, 32, (9, 20, 19), (3, 3, 1), (1, 1, 1), None),      # several runs per plane, several x segments
+    (4, 64, 128, (12, 12, 28), (3, 3, 2), (1, 1, 1), None),    # d4.conv1 of the bench (tap groups of 4)
+    (2, 128, 64, (6, 16, 9), (3, 3, 2), (1, 1, 1), None),      # Up.conv1 shape class
+    (1, 32, 32, (11, 12, 10), (3, 3, 2), (2, 2, 1), None),     # dilation
+]
+
+
+@pytest.mark.parametrize("case", WG5_CASES)
+def test_wgrad_tc5_matches_fp32(case):
+    n, cin, cout, isz, k, dil, cp = case
+    g = torch.Generator().manual_seed(hash(case) % 10000 + 3)
+    osz = tuple(isz[i] - (k[i] - 1) * dil[i] for i in range(3))
+    x = h16(torch.randn((n, cin) + isz, generator=g))
+    dy = h16(torch.randn((n, cout) + osz, generator=g))
+    ref = torch.nn.grad.conv3d_weight(x, (cout, cin) + k, dy, dilation=dil)
+    got = run_wgrad(x, dy, k, dil=dil, cpitch=cp, use_tc5=True)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)   # exact fp16 products, fp32 accumulate
+
+
+def test_wgrad_tc5_fused_input_bn_relu():
+    g = torch.Generator().manual_seed(19)
+    x = h16(torch.randn((2, 32, 8, 9, 7), generator=g))
+    dy = h16(torch.randn((2, 64, 6, 7, 6), generator=g))
+    sc, sh = torch.rand(32, generator=g) + 0.5, torch.randn(32, generator=g) * 0.3
+    a = h16(F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)))
+    ref = torch.nn.grad.conv3d_weight(a, (64, 32, 3, 3, 2), dy)
+    got = run_wgrad(x, dy, (3, 3, 2), in_affine=(sc, sh), use_tc5=True)
+    assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)
 
 
 def test_wgrad_tc_fused_input_bn_relu():
