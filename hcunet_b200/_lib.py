@@ -11,10 +11,11 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 F32, BF16, F16 = 0, 1, 2
 BATCH_JOB_BYTES = 256
+STAT_BINS = 4
 
 
 class HcuConvDesc(C.Structure):

@@ -116,6 +116,49 @@ __device__ __forceinline__ long long wm_index(const HcuWeightMap& m, long long e
          (long long)(m.t0[1] + jy * m.tstep[1]) * m.st[1] + (long long)(m.t0[2] + jz * m.tstep[2]) * m.st[2];
 }
 
+// 32-bit index arithmetic flavour (the batched kernels: element counts < 2^31; 64-bit '/' '%' cost ~10x more)
+// element e of a packed [g][jx][jy][jz][a][b] weight tensor -> index into the reference-layout parameter
+__device__ __forceinline__ long long wm_index32(const HcuWeightMap& m, uint32_t e) {
+  const int nph = m.phase_on ? m.ph[0] * m.ph[1] * m.ph[2] : 1;
+  const int nbf = m.phase_on == 2 ? m.nb * nph : m.nb, naf = m.phase_on == 1 ? m.na * nph : m.na;
+  int b = (int)(e % nbf); e /= nbf;
+  int a = (int)(e % naf); e /= naf;
+  const int jz = (int)(e % m.j[2]); e /= m.j[2];
+  const int jy = (int)(e % m.j[1]); e /= m.j[1];
+  const int jx = (int)(e % m.j[0]);
+  const int g = (int)(e / m.j[0]);
+  long long idx = m.base;
+  if (m.phase_on) {
+    int phi;
+    if (m.phase_on == 1) { phi = a / m.na; a -= phi * m.na; } else { phi = b / m.nb; b -= phi * m.nb; }
+    const int pz = phi % m.ph[2]; phi /= m.ph[2];
+    const int py = phi % m.ph[1], px = phi / m.ph[1];
+    idx += px * m.pst[0] + py * m.pst[1] + pz * m.pst[2];
+  }
+  return idx + g * m.sg + a * m.sa + b * m.sb + (long long)(m.t0[0] + jx * m.tstep[0]) * m.st[0] +
+         (long long)(m.t0[1] + jy * m.tstep[1]) * m.st[1] + (long long)(m.t0[2] + jz * m.tstep[2]) * m.st[2];
+}
+
+// Division of a 31-bit unsigned by a runtime constant in 3 instructions (64-bit '/' and '%' cost ~100 each and made the
+// index decomposition of the memory-bound kernels the bottleneck): q = (umulhi(n, m) + n) >> s, valid for n < 2^31.
+struct FastDiv {
+  uint32_t d, m, s;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  uint32_t s = 0;
+  while ((1ull << s) < d) ++s;
+  f.s = s;
+  f.m = (uint32_t)((((1ull << 32) * ((1ull << s) - d)) / d) + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return (__umulhi(n, f.m) + n) >> f.s; }
+__device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
+  q = fdiv(n, f);
+  r = n - q * f.d;
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -787,8 +787,9 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       for (int c = row; c < Nc; c += 128) {
         const int ch = ns * Nc + c;
         if (ch < cout) {
-          atomicAdd(&p.stats[p.out_c_off + ch], (double)sstat[c]);
-          atomicAdd(&p.stats[p.stats_pitch + p.out_c_off + ch], (double)sstat[Nc + c]);
+          double* sb = p.stats + (size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * p.stats_pitch;
+          atomicAdd(&sb[p.out_c_off + ch], (double)sstat[c]);
+          atomicAdd(&sb[p.stats_pitch + p.out_c_off + ch], (double)sstat[Nc + c]);
         }
       }
     }
@@ -888,17 +889,17 @@ __global__ void __launch_bounds__(256) pack_tc_batch_kernel(const unsigned char*
     const long long i = base + k;
     if (i >= J.total) break;
     const int j = (int)(i & 7);
-    long long r = i >> 3;
-    const int nn = (int)(r % J.Nc); r /= J.Nc;
-    const int e = (int)(r % J.E_tx); r /= J.E_tx;
-    const int tx = (int)(r % J.KX);
-    const int ns = (int)(r / J.KX);
+    uint32_t r = (uint32_t)(i >> 3);  // 32-bit index arithmetic: job sizes are < 2^31 (checked at build time)
+    const int nn = (int)(r % (uint32_t)J.Nc); r /= (uint32_t)J.Nc;
+    const int e = (int)(r % (uint32_t)J.E_tx); r /= (uint32_t)J.E_tx;
+    const int tx = (int)(r % (uint32_t)J.KX);
+    const int ns = (int)(r / (uint32_t)J.KX);
     float v = 0.f;
     if (e < J.KYZ * J.P) {
       const int t = e / J.P, pl = e % J.P;
       const int ci = pl * 8 + j, co = ns * J.Nc + nn;
       if (ci < J.cin && co < J.cout) {
-        const long long idx = wm_index(J.m, ((long long)(tx * J.KYZ + t) * J.cin + ci) * J.cout + co);
+        const long long idx = wm_index32(J.m, (uint32_t)(((tx * J.KYZ + t) * J.cin + ci) * J.cout + co));
         v = ref[idx];
         if (J.m.fold) v += ref[idx + J.m.fold_stride];
       }
@@ -1109,6 +1110,7 @@ extern "C" int hcu_conv_tc_pack_batch_build(const HcuConvDesc* descs, const HcuW
     memset(&j, 0, sizeof(j));
     j.m = *m; j.ref_off = ref_off[i]; j.out_off = out_off[i];
     j.total = (long long)p.nsplit * p.E * p.Nc * 8;
+    HCU_CHECK_ARG(j.total < 0x7fffffffLL, "conv_tc_pack_batch_build: job %d too large", i);
     j.KX = p.KX; j.KYZ = p.KY * p.KZ; j.P = p.P; j.E_tx = p.E_tx; j.Nc = p.Nc; j.nsplit = p.nsplit;
     j.cin = descs[i].cin; j.cout = descs[i].cout;
     j.block0 = b0;

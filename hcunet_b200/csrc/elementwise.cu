@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) weight_scatter_batch_kernel(const unsigne
     float s = 0.f;
     for (int i = 0; i < J.nsplit; ++i) s += part[(long long)i * J.total + e];
     s *= scale;
-    const long long idx = wm_index(J.m, e);
+    const long long idx = wm_index32(J.m, (uint32_t)e);
     ref[idx] = s;
     if (J.m.fold) ref[idx + J.m.fold_stride] = s;
   }
@@ -219,8 +219,10 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int c, doub
                                    float* invstd, float* scale, float* shift) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
-  const double mu = stats[i] / count;
-  double var = stats[c + i] / count - mu * mu;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = 0; b < HCU_STAT_BINS; ++b) { s1 += stats[(size_t)b * 2 * c + i]; s2 += stats[(size_t)b * 2 * c + c + i]; }
+  const double mu = s1 / count;
+  double var = s2 / count - mu * mu;
   if (var < 0.0) var = 0.0;
   const float is = (float)(1.0 / sqrt(var + (double)eps));
   const float muf = (float)mu;
@@ -317,16 +319,15 @@ __global__ void bn_relu_maxpool_kernel(const TY* __restrict__ y, TP* __restrict_
 __global__ void bn_relu_maxpool_h8_kernel(const __half* __restrict__ y, __half* __restrict__ pooled,
                                           uint8_t* __restrict__ argmax, int n, int ix, int iy, int iz, int c, int px,
                                           int py, int pz, const float* __restrict__ scale,
-                                          const float* __restrict__ shift, int relu) {
-  const int ox = ix / px, oy = iy / py, oz = iz / pz, c8 = c >> 3;
-  const long long total = (long long)n * ox * oy * oz * c8;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(e % c8);
-    long long r = e / c8;
-    const int z = (int)(r % oz); r /= oz;
-    const int yy = (int)(r % oy); r /= oy;
-    const int x = (int)(r % ox);
-    const int b = (int)(r / ox);
+                                          const float* __restrict__ shift, int relu, FastDiv dc8, FastDiv doz, FastDiv doy,
+                                          FastDiv dox, uint32_t total) {
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    uint32_t r, ucg, uz, uy, ux, ub;
+    fdivmod(e, dc8, r, ucg);
+    fdivmod(r, doz, r, uz);
+    fdivmod(r, doy, r, uy);
+    fdivmod(r, dox, ub, ux);
+    const int cg = (int)ucg, z = (int)uz, yy = (int)uy, x = (int)ux, b = (int)ub;
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = 1.f; sh[j] = 0.f; }
@@ -359,11 +360,11 @@ __global__ void bn_relu_maxpool_h8_kernel(const __half* __restrict__ y, __half* 
     __half2 o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = __floats2half2_rn(best[2 * j], best[2 * j + 1]);
-    *reinterpret_cast<uint4*>(pooled + e * 8) = *reinterpret_cast<uint4*>(o);
+    *reinterpret_cast<uint4*>(pooled + (size_t)e * 8) = *reinterpret_cast<uint4*>(o);
     uint2 a;
     a.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
     a.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
-    *reinterpret_cast<uint2*>(argmax + e * 8) = a;
+    *reinterpret_cast<uint2*>(argmax + (size_t)e * 8) = a;
   }
 }
 
@@ -427,29 +428,31 @@ __global__ void maxpool_bwd_kernel(const TDP* __restrict__ dpooled, const uint8_
 // ---- fp16, 8 channels per thread (16-byte accesses); optional fused max-pool backward -------------------------
 // When `argmax` is given, `da` is the gradient of the POOLED tensor: the gradient of voxel (x,y,z) is
 // dpooled[window] if this voxel was the window's argmax, else 0 (nothing full-resolution is materialised).
-struct PoolGeom { int n, ix, iy, iz, px, py, pz, ox, oy, oz; };
+struct PoolGeom {
+  int n, ix, iy, iz, px, py, pz, ox, oy, oz;
+  FastDiv diz, diy, dix, dpx, dpy, dpz;
+};
 
 __device__ __forceinline__ void load_g8(const __half* __restrict__ da, const uint8_t* __restrict__ argmax, const PoolGeom& pg,
-                                        long long pix, int cg, int c, float* g) {
+                                        uint32_t pix, int cg, int c, float* g) {
   uint4 raw;
   if (argmax == nullptr) {
-    raw = *reinterpret_cast<const uint4*>(da + pix * c + cg * 8);
+    raw = *reinterpret_cast<const uint4*>(da + (size_t)pix * c + cg * 8);
     const __half2* h = reinterpret_cast<const __half2*>(&raw);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); g[2 * j] = f.x; g[2 * j + 1] = f.y; }
     return;
   }
-  long long r = pix;
-  const int z = (int)(r % pg.iz); r /= pg.iz;
-  const int y = (int)(r % pg.iy); r /= pg.iy;
-  const int x = (int)(r % pg.ix);
-  const long long b = r / pg.ix;
-  const int qx = x / pg.px, qy = y / pg.py, qz = z / pg.pz;
+  uint32_t r, z, y, x, b;
+  fdivmod(pix, pg.diz, r, z);
+  fdivmod(r, pg.diy, r, y);
+  fdivmod(r, pg.dix, b, x);
+  const uint32_t qx = fdiv(x, pg.dpx), qy = fdiv(y, pg.dpy), qz = fdiv(z, pg.dpz);
 #pragma unroll
   for (int j = 0; j < 8; ++j) g[j] = 0.f;
-  if (qx >= pg.ox || qy >= pg.oy || qz >= pg.oz) return;
-  const long long pe = (((b * pg.ox + qx) * pg.oy + qy) * pg.oz + qz) * c + cg * 8;
-  const uint32_t w = (uint32_t)(((x - qx * pg.px) * pg.py + (y - qy * pg.py)) * pg.pz + (z - qz * pg.pz));
+  if ((int)qx >= pg.ox || (int)qy >= pg.oy || (int)qz >= pg.oz) return;
+  const size_t pe = ((((size_t)b * pg.ox + qx) * pg.oy + qy) * pg.oz + qz) * c + cg * 8;
+  const uint32_t w = ((x - qx * pg.px) * pg.py + (y - qy * pg.py)) * pg.pz + (z - qz * pg.pz);
   raw = *reinterpret_cast<const uint4*>(da + pe);
   const uint2 a = *reinterpret_cast<const uint2*>(argmax + pe);
   const __half* h = reinterpret_cast<const __half*>(&raw);
@@ -469,10 +472,10 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __re
   extern __shared__ float sh[];  // [2][c]
   for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
-  const int c8 = c >> 3;
-  const long long total = npix * c8, stride = (long long)gridDim.x * blockDim.x;  // stride % c8 == 0 (c8 | 256)
-  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const int cg = (int)(e % c8);
+  const int c8 = c >> 3, lc8 = __ffs(c8) - 1;  // c8 is a power of two (c8 | 256)
+  const uint32_t total = (uint32_t)(npix * c8), stride = gridDim.x * blockDim.x;  // stride % c8 == 0
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = (int)(e & (uint32_t)(c8 - 1));
   float sc[8], sf[8], mu[8], is[8], s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -480,8 +483,8 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __re
     s1[j] = 0.f; s2[j] = 0.f;
   }
   for (; e < total; e += stride) {
-    const long long pix = e / c8;
-    const uint4 yr = *reinterpret_cast<const uint4*>(y + pix * c + cg * 8);
+    const uint32_t pix = e >> lc8;
+    const uint4 yr = *reinterpret_cast<const uint4*>(y + (size_t)pix * c + cg * 8);
     float g[8];
     load_g8(da, argmax, pg, pix, cg, c, g);
     const __half2* yh = reinterpret_cast<const __half2*>(&yr);
@@ -512,7 +515,8 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __re
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) atomicAdd(&sums[i], (double)sh[i]);
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x)
+    atomicAdd(&sums[(size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * c + i], (double)sh[i]);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_h8_kernel(const __half* __restrict__ da, const __half* __restrict__ y,
@@ -520,10 +524,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_h8_kernel(const __half* __re
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              int relu, const float* __restrict__ coef,
                                                              const uint8_t* __restrict__ argmax, PoolGeom pg) {
-  const int c8 = c >> 3;
-  const long long total = npix * c8, stride = (long long)gridDim.x * blockDim.x;
-  long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const int cg = (int)(e % c8);
+  const int c8 = c >> 3, lc8 = __ffs(c8) - 1;
+  const uint32_t total = (uint32_t)(npix * c8), stride = gridDim.x * blockDim.x;
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = (int)(e & (uint32_t)(c8 - 1));
   float sc[8], sf[8], c1[8], c2[8], c3[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -531,8 +535,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_h8_kernel(const __half* __re
     c1[j] = coef[cg * 8 + j]; c2[j] = coef[c + cg * 8 + j]; c3[j] = coef[2 * c + cg * 8 + j];
   }
   for (; e < total; e += stride) {
-    const long long pix = e / c8;
-    const uint4 yr = *reinterpret_cast<const uint4*>(y + pix * c + cg * 8);
+    const uint32_t pix = e >> lc8;
+    const uint4 yr = *reinterpret_cast<const uint4*>(y + (size_t)pix * c + cg * 8);
     float g[8];
     load_g8(da, argmax, pg, pix, cg, c, g);
     const __half2* yh = reinterpret_cast<const __half2*>(&yr);
@@ -546,7 +550,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_h8_kernel(const __half* __re
       o[j] = __floats2half2_rn(fmaf(c1[2 * j], g0, fmaf(c2[2 * j], yv.x, c3[2 * j])),
                                fmaf(c1[2 * j + 1], g1, fmaf(c2[2 * j + 1], yv.y, c3[2 * j + 1])));
     }
-    *reinterpret_cast<uint4*>(dy + pix * c + cg * 8) = *reinterpret_cast<uint4*>(o);
+    *reinterpret_cast<uint4*>(dy + (size_t)pix * c + cg * 8) = *reinterpret_cast<uint4*>(o);
   }
 }
 
@@ -590,7 +594,8 @@ __global__ void bn_bwd_stats_kernel(const TD* __restrict__ da, const TY* __restr
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) atomicAdd(&sums[i], (double)sh[i]);
+  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x)
+    atomicAdd(&sums[(size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * c + i], (double)sh[i]);
 }
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int c, double count,
@@ -601,7 +606,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int c, d
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
   if (dscale != nullptr) grad_scale *= dscale[0];
-  const double sg = sums[i], sgx = sums[c + i];
+  double sg = 0.0, sgx = 0.0;
+  for (int b = 0; b < HCU_STAT_BINS; ++b) { sg += sums[(size_t)b * 2 * c + i]; sgx += sums[(size_t)b * 2 * c + c + i]; }
   if (dgamma != nullptr) dgamma[i] = (float)(sgx * grad_scale);
   if (dbeta != nullptr) dbeta[i] = (float)(sg * grad_scale);
   const double s = (double)gamma[i] * (double)invstd[i];
@@ -810,7 +816,7 @@ extern "C" int hcu_weight_scatter_batch_build(const HcuWeightMap* maps, const in
     ScatterJob j;
     memset(&j, 0, sizeof(j));
     j.m = maps[i]; j.part_off = part_off[i]; j.ref_off = ref_off[i]; j.total = wm_total(&maps[i]);
-    HCU_CHECK_ARG(j.total > 0 && nsplit[i] > 0, "weight_scatter_batch_build: job %d: bad sizes", i);
+    HCU_CHECK_ARG(j.total > 0 && j.total < 0x7fffffffLL && nsplit[i] > 0, "weight_scatter_batch_build: job %d: bad sizes", i);
     j.nsplit = nsplit[i]; j.block0 = b0;
     j.nblocks = (int)((j.total + kScatterPerBlock - 1) / kScatterPerBlock);
     b0 += j.nblocks;
@@ -880,8 +886,11 @@ extern "C" int hcu_bn_relu_maxpool(const void* y, int32_t dtype_y, void* pooled,
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype_y == HCU_F16 && dtype_p == HCU_F16 && c % 8 == 0 && aligned16(y) && aligned16(pooled) &&
       (((uintptr_t)argmax) & 7) == 0 && (scale == nullptr || (aligned16(scale) && aligned16(shift)))) {
-    bn_relu_maxpool_h8_kernel<<<grid_for(total / 8, 256, 16), 256, 0, st>>>((const __half*)y, (__half*)pooled, argmax, n, ix, iy,
-                                                                          iz, c, px, py, pz, scale, shift, relu);
+    const long long work = (long long)n * (ix / px) * (iy / py) * (iz / pz) * (c / 8);
+    HCU_CHECK_ARG(work < 0x7fffffffLL, "bn_relu_maxpool: more than 2^31 pooled vectors");
+    bn_relu_maxpool_h8_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(
+        (const __half*)y, (__half*)pooled, argmax, n, ix, iy, iz, c, px, py, pz, scale, shift, relu, make_fastdiv(c / 8),
+        make_fastdiv(iz / pz), make_fastdiv(iy / py), make_fastdiv(ix / px), (uint32_t)work);
     HCU_CHECK_LAUNCH("bn_relu_maxpool_h8");
     return 0;
   }
@@ -923,6 +932,8 @@ static int fill_pool(const HcuPoolGeom* g, int64_t npix, PoolGeom& pg, const cha
   HCU_CHECK_ARG((int64_t)g->n * g->ix * g->iy * g->iz == npix, "%s: pool geometry does not match npix", who);
   pg.n = g->n; pg.ix = g->ix; pg.iy = g->iy; pg.iz = g->iz; pg.px = g->px; pg.py = g->py; pg.pz = g->pz;
   pg.ox = g->ix / g->px; pg.oy = g->iy / g->py; pg.oz = g->iz / g->pz;
+  pg.diz = make_fastdiv(g->iz); pg.diy = make_fastdiv(g->iy); pg.dix = make_fastdiv(g->ix);
+  pg.dpx = make_fastdiv(g->px); pg.dpy = make_fastdiv(g->py); pg.dpz = make_fastdiv(g->pz);
   return 0;
 }
 
@@ -933,7 +944,7 @@ extern "C" int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y,
   HCU_CHECK_ARG(da && y && scale && shift && mean && invstd && sums && npix > 0 && c > 0, "bn_bwd_stats: bad args");
   HCU_CHECK_ARG(c <= 4096, "bn_bwd_stats: too many channels");
   if (dtype_da == HCU_F16 && dtype_y == HCU_F16 && c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0 && aligned16(da) && aligned16(y) &&
-      (argmax == nullptr || (((uintptr_t)argmax) & 7) == 0)) {
+      npix * (c / 8) < 0x7fffffffLL && (argmax == nullptr || (((uintptr_t)argmax) & 7) == 0)) {
     PoolGeom pg = {};
     if (argmax != nullptr) { int rc = fill_pool(pool, npix, pg, "bn_bwd_stats"); if (rc) return rc; }
     const int grid = grid_for(npix * (c / 8), 256 * 4, 8);
@@ -972,7 +983,7 @@ extern "C" int hcu_bn_bwd_apply(const void* da, int32_t dtype_da, const void* y,
                                 void* stream) {
   HCU_CHECK_ARG(da && y && dy && scale && shift && coef && npix > 0 && c > 0, "bn_bwd_apply: bad args");
   if (dtype_da == HCU_F16 && dtype_y == HCU_F16 && dtype_dy == HCU_F16 && c % 8 == 0 && 256 % (c / 8) == 0 && aligned16(da) &&
-      aligned16(y) && aligned16(dy) && (argmax == nullptr || (((uintptr_t)argmax) & 7) == 0)) {
+      aligned16(y) && aligned16(dy) && npix * (c / 8) < 0x7fffffffLL && (argmax == nullptr || (((uintptr_t)argmax) & 7) == 0)) {
     PoolGeom pg = {};
     if (argmax != nullptr) { int rc = fill_pool(pool, npix, pg, "bn_bwd_apply"); if (rc) return rc; }
     const int grid = grid_for(npix * (c / 8), 256 * 2, 16);

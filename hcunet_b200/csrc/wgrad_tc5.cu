@@ -318,9 +318,14 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
         const uint32_t tcol = tmem_base + (uint32_t)((t - t_lo) * p.Nc);
         const uint32_t first = (uint32_t)i;  // accumulate flag of chunk 0: overwrite only on the CTA's first plane
         if (elect_one()) {
-          for (int c = 0; c < nchunks; ++c)
-            umma_f16(tcol, a_hi | (uint64_t)(abase + (uint32_t)(c * 16)), b_hi | (uint64_t)(bbase + (uint32_t)(c * 16)), idesc,
-                     first | (uint32_t)c);
+          // nchunks is a multiple of 4 (M = 64 / 128 / 256): four MMAs per trip, descriptors advance by constants
+          for (int c = 0; c < nchunks; c += 4) {
+            const uint64_t ad = a_hi | (uint64_t)(abase + (uint32_t)(c * 16)), bd = b_hi | (uint64_t)(bbase + (uint32_t)(c * 16));
+            umma_f16(tcol, ad, bd, idesc, first | (uint32_t)c);
+            umma_f16(tcol, ad + 16u, bd + 16u, idesc, 1u);
+            umma_f16(tcol, ad + 32u, bd + 32u, idesc, 1u);
+            umma_f16(tcol, ad + 48u, bd + 48u, idesc, 1u);
+          }
         }
         __syncwarp();
       }
@@ -395,7 +400,13 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   p.Nc = round_up(d->cout, 16);
   if (p.Nc > 256) return "too many output channels";
   p.TG = std::min(p.taps, 512 / p.Nc);
+  {
+    static int tgmax = -1;
+    if (tgmax < 0) { const char* e = getenv("HCU_WG5_TG"); tgmax = e ? atoi(e) : 0; }
+    if (tgmax > 0) p.TG = std::min(p.TG, tgmax);
+  }
   p.NG = (p.taps + p.TG - 1) / p.TG;
+  p.TG = (p.taps + p.NG - 1) / p.NG;  // balance the groups
   {
     int cols = p.TG * p.Nc, t = 32;
     while (t < cols) t <<= 1;
@@ -484,6 +495,14 @@ extern "C" int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const
   const long long target = 2LL * per_sm * num_sms();
   int nseg = (int)((target + base_items - 1) / base_items);
   nseg = std::max(1, std::min(nseg, (p.OX + 3) / 4));
+  {
+    static int fseg = -1;
+    if (fseg < 0) { const char* e = getenv("HCU_WG5_NSEG"); fseg = e ? atoi(e) : 0; }
+    if (fseg > 0) nseg = std::min(fseg, p.OX);
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("HCU_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (dbg & 8) fprintf(stderr, "wgrad_tc5: M %d R %d RD %d D %d Nc %d TG %d NG %d n_runs %d nseg %d smem %d tmem %d per_sm %d\n", p.M, p.R, p.RD, p.D, p.Nc, p.TG, p.NG, p.n_runs, nseg, p.smem_bytes, p.tmem_cols, per_sm);
+  }
   p.Lx = (p.OX + nseg - 1) / nseg;
   p.n_xseg = (p.OX + p.Lx - 1) / p.Lx;
   const long long grid = base_items * p.n_xseg;

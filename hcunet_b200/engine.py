@@ -478,7 +478,8 @@ class UnetEngine:
         xf = None  # pending (scale, shift) + ReLU to apply when `cur` is read
         saved = [] if save else None
         fold_eval = not save and not training  # inference: BN folded into the conv epilogue
-        nstat = sum(2 * g.cout_t for g in plan.steps if isinstance(g, ConvGeom) and g.bn is not None)
+        SB = _lib.STAT_BINS  # binned fp64 reductions (include/hcunet_b200.h "HCU_STAT_BINS")
+        nstat = sum(2 * g.cout_t * SB for g in plan.steps if isinstance(g, ConvGeom) and g.bn is not None)
         zero_ws = torch.zeros(nstat, dtype=torch.float64, device=dev) if training else None  # one memset per forward
         zoff = 0
         logits = None
@@ -525,8 +526,8 @@ class UnetEngine:
                 continue
             y = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
             if training:
-                stats = zero_ws[zoff:zoff + 2 * g.cout_t].view(2, g.cout_t)
-                zoff += 2 * g.cout_t
+                stats = zero_ws[zoff:zoff + 2 * g.cout_t * SB]
+                zoff += 2 * g.cout_t * SB
                 self._conv(d, cur, w, bias, y, stats=stats, in_scale=isc, in_shift=ish, layer=g.name)
                 _lib.check(lib.hcu_bn_finalize(_ptr(stats), g.cout_t, float(npix), _ptr(gamma), _ptr(beta), BN_EPS,
                                                BN_MOMENTUM, _ptr(rm), _ptr(rv), _ptr(vec[0]), _ptr(vec[1]),
@@ -648,7 +649,8 @@ class UnetEngine:
             dcur_dt = adt
         self._inv = inv
         dx = None
-        nstat = sum(2 * it[1].cout_t for it in saved if it[0] == "conv")
+        SB = _lib.STAT_BINS
+        nstat = sum(2 * it[1].cout_t * SB for it in saved if it[0] == "conv")
         zero_ws = torch.zeros(nstat, dtype=torch.float64, device=dev)  # one memset for every BN-backward reduction
         zoff = 0
         for item in reversed(saved):
@@ -677,8 +679,8 @@ class UnetEngine:
                                                    g.out_sz[1], g.out_sz[2], g.cout_t, g.pool[0], g.pool[1],
                                                    g.pool[2], st), "maxpool_bwd")
                     dcur, dcur_dt = dfull, adt
-                sums = zero_ws[zoff:zoff + 2 * g.cout_t].view(2, g.cout_t)
-                zoff += 2 * g.cout_t
+                sums = zero_ws[zoff:zoff + 2 * g.cout_t * SB]
+                zoff += 2 * g.cout_t * SB
                 _lib.note(g.name, 2 * npix * g.cout_t * esz, 0)
                 _lib.check(lib.hcu_bn_bwd_stats(_ptr(dcur), dcur_dt, _ptr(y), adt, npix, g.cout_t, _ptr(vec[2]),
                                                 _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(pool_arg),
@@ -812,7 +814,7 @@ class UnetEngine:
         lib, cache = self.lib, self._cache
         f16 = self.use_tc and d.dtype_in == _lib.F16 and d.dtype_out == _lib.F16
         # channel-rich levels: tcgen05 kernel (M = 128 rows of Cin would be mostly padding below 32 input channels)
-        tc5 = bool(f16 and self.use_tc5 and (d.in_cpitch >= 32 or (d.in_cpitch >= 16 and d.cout >= 32)) and
+        tc5 = bool(f16 and self.use_tc5 and d.in_cpitch >= 32 and
                    lib.hcu_conv_wgrad_tc5_supported(C.byref(d)))
         tc = bool(f16 and (tc5 or lib.hcu_conv_wgrad_tc_supported(C.byref(d))))
         nsplit = 1 if tc else ns

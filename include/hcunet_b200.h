@@ -29,7 +29,13 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 11
+#define HCU_ABI_VERSION 12
+
+/* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
+ * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
+ * serialise: thousands of CTAs on 2c addresses cost more than the memory pass itself), the finalize kernels add the
+ * bins in a fixed order.  The caller zeroes the whole [HCU_STAT_BINS][2][c] buffer. */
+#define HCU_STAT_BINS 4
 
 typedef enum HcuStatus {
   HCU_OK = 0,

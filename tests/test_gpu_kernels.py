@@ -55,7 +55,7 @@ def run_tc(x, w, *, bias=None, dil=(1, 1, 1), pad=(0, 0, 0), cpitch=None, in_aff
     d = conv_desc(_lib.F16, _lib.F32 if out_f32 else _lib.F16, n, isz, cp, 0, cin, cin, osz, osz, cout, 0, cout, 1, taps,
                   dil, pad=pad, in_relu=int(in_relu), out_relu=int(out_relu))
     wg = w.permute(2, 3, 4, 1, 0).contiguous().float().cuda()  # [taps][cin][cout]
-    stats = torch.zeros((2, cout), dtype=torch.float64, device="cuda") if want_stats else None
+    stats = torch.zeros((_lib.STAT_BINS, 2, cout), dtype=torch.float64, device="cuda") if want_stats else None
     isc = ish = osc = osh = None
     if in_affine is not None:
         isc = torch.zeros(cp, device="cuda"); ish = torch.zeros(cp, device="cuda")
@@ -74,7 +74,7 @@ def run_tc(x, w, *, bias=None, dil=(1, 1, 1), pad=(0, 0, 0), cpitch=None, in_aff
         _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), P(xin), P(packed), P(b), P(isc), P(ish), P(osc), P(osh), P(y),
                                        P(stats), stream()), "conv_tc_fwd")
     torch.cuda.synchronize()
-    return from_cl(y), (stats.cpu() if stats is not None else None)
+    return from_cl(y), (stats.sum(0).cpu() if stats is not None else None)   # binned reduction buffers
 
 
 def h16(t):

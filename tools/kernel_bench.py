@@ -29,6 +29,7 @@ LAYERS = {
     "d4.conv1": (64, 128, (12, 12, 28), (3, 3, 2)),
     "d4.conv2": (128, 128, (10, 10, 27), (3, 3, 1)),
     "u0.conv1": (64, 64, (16, 16, 28), (3, 3, 2)),
+    "u1.conv1": (32, 32, (24, 24, 28), (3, 3, 2)),
     "u3.conv1": (8, 8, (72, 72, 28), (3, 3, 2)),
     "x.n48": (8, 48, (256, 256, 32), (3, 3, 2)),
     "x.n128": (8, 128, (256, 256, 32), (3, 3, 2)),
@@ -64,14 +65,18 @@ def main():
             packed = torch.empty(lib.hcu_conv_tc_packed_bytes(C.byref(d)), dtype=torch.uint8, device="cuda")
             _lib.check(lib.hcu_conv_tc_pack(C.byref(d), P(w), P(packed), st))
             y = torch.empty((B,) + osz + (cout,), dtype=torch.float16, device="cuda")
-            stats = torch.zeros((2, cout), dtype=torch.float64, device="cuda")
+            stats = torch.zeros((_lib.STAT_BINS, 2, cout), dtype=torch.float64, device="cuda")
             fn = lambda: _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), P(x), P(packed), None, P(sc), P(sh), None, None, P(y),
                                                         P(stats), st))
         else:
             dy = torch.randn((B,) + osz + (cout,), device="cuda").half()
             d = conv_desc(_lib.F16, _lib.F16, B, isz, cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, in_relu=1)
             wacc = torch.empty(T * cin * cout, device="cuda")
-            fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
+            if kind == "wgrad5":
+                wacc.zero_()
+                fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
+            else:
+                fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
         if once:
             fn()
             torch.cuda.synchronize()
