@@ -162,6 +162,12 @@ def main_reference(args):
 # ----------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------
+def _stage(msg):
+    """Progress marker on stderr (multi-GPU hangs are otherwise silent)."""
+    if os.environ.get("HCUNET_BENCH_VERBOSE", "0") != "0":
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def main_ours(args):
     import torch
     import torch.distributed as dist
@@ -178,6 +184,7 @@ def main_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    _stage("process group up")
     B, (C, X, Y), Z = args.batch, SHAPE[:3], args.z
 
     torch.manual_seed(0)
@@ -185,6 +192,7 @@ def main_ours(args):
     model.precision = args.precision
     model = model.to(dev).train()
     sync = GradSync(model, world)          # broadcast params from rank 0; fp32 mean all-reduce of the gradients
+    _stage("parameters broadcast")
     use_graph = os.environ.get("HCUNET_BENCH_GRAPH", "1") != "0"
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
 
@@ -212,9 +220,11 @@ def main_ours(args):
 
     for _ in range(2):  # the first two steps record the step cache (per-layer weight packs / scatters, more launches)
         eager_step(*resident[0])
+    _stage("eager recording steps done")
     l0 = _lib.launch_count()
     eager_step(*resident[0])
     torch.cuda.synchronize()
+    _stage("eager steady-state step done")
     launches_per_step = _lib.launch_count() - l0  # library kernels of one steady-state step (graph replays re-launch the same set)
     if use_graph:
         from hcunet_b200.graph import GraphedTrainStep
@@ -224,6 +234,7 @@ def main_ours(args):
         # one CUDA-graph launch per step; the inputs are copied into the graph's static buffers (device->device here,
         # pinned host->device in the e2e leg) inside the timed region
         step = gstep
+        _stage("graph captured")
     else:
         step = eager_step
 
@@ -256,7 +267,9 @@ def main_ours(args):
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    _stage("warm-up done")
     t_res = timed(res_step, args.steps)
+    _stage("timed region done")
     launches = launches_per_step * args.steps
     # the flush is not part of the workload: time it alone and subtract
     t_flush = timed(lambda i: flush.zero_(), args.steps)
@@ -302,6 +315,7 @@ def main_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_e2e = float(t) / args.steps
+    _stage("e2e region done")
     clk = clocks.stop() if rank == 0 else None
 
     # ---- per-kernel CUDA-event profile of the same step -> roofline of the dominant kernel ------------
@@ -317,7 +331,11 @@ def main_ours(args):
         prof = profiler.KernelProfile()
         with prof:
             for i in range(min(args.steps, 5)):
-                eager_step(*resident[i % NBUF])  # eager: per-kernel events need individual launches
+                # eager: per-kernel events need individual launches.  No gradient all-reduce here: only rank 0 profiles
+                # (a collective entered by one rank would dead-lock), and the collective is not one of this library's kernels
+                opt.zero_grad(set_to_none=True)
+                H.cross_entropy(model(resident[i % NBUF][0]), resident[i % NBUF][1], resident[i % NBUF][2], "pixel").backward()
+                opt.step()
         roof = prof.roofline(peaks, t_step * min(args.steps, 5))
         if os.environ.get("HCUNET_PROFILE_OUT"):
             nst = min(args.steps, 5)
