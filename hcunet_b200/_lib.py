@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 F32, BF16, F16 = 0, 1, 2
 BATCH_JOB_BYTES = 256
@@ -72,6 +72,8 @@ SIGNATURES = {
     "hcu_conv_wgrad_tc_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_wgrad_tc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
     "hcu_conv_wgrad_tc_acc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
+    "hcu_conv_wgrad_ws_supported": [C.POINTER(HcuConvDesc)],
+    "hcu_conv_wgrad_ws_acc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
     "hcu_conv_wgrad_tc5_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_wgrad_tc5_acc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
     "hcu_conv_tc_pack_batch_build": [C.POINTER(HcuConvDesc), C.POINTER(HcuWeightMap), C.POINTER(I64), C.POINTER(I64), I32, P,
@@ -162,7 +164,7 @@ def load():
     out._cdll = lib
     for name in SIGNATURES:
         raw = getattr(lib, name)
-        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_conv_tc_supported", "hcu_conv_wgrad_tc_supported", "hcu_conv_wgrad_tc5_supported",
+        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_conv_tc_supported", "hcu_conv_wgrad_tc_supported", "hcu_conv_wgrad_tc5_supported", "hcu_conv_wgrad_ws_supported",
                                          "hcu_conv_tc_packed_bytes", "hcu_conv_tc_pack_batch_build", "hcu_weight_scatter_batch_build") else _wrap(name, raw))
     _lib = out
     return out

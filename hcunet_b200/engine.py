@@ -314,6 +314,7 @@ class UnetEngine:
         self._plans: Dict[tuple, Plan] = {}
         self._inv = None
         self.use_tc = os.environ.get("HCUNET_TC", "1") != "0"
+        self.use_ws = os.environ.get("HCUNET_WGRADWS", "1") != "0"      # warp-specialised weight gradient (8/16-channel levels)
         self.use_tc5 = os.environ.get("HCUNET_WGRAD5", "1") != "0"      # tcgen05 weight gradient on the channel-rich levels
         self.use_batch = os.environ.get("HCUNET_BATCH", "1") != "0"      # batched packs / scatters (_StepCache)
         self.overlap_wgrad = os.environ.get("HCUNET_OVERLAP", "1") != "0"  # weight gradients on a side stream
@@ -816,7 +817,9 @@ class UnetEngine:
         # channel-rich levels: tcgen05 kernel (M = 128 rows of Cin would be mostly padding below 32 input channels)
         tc5 = bool(f16 and self.use_tc5 and d.in_cpitch >= 32 and
                    lib.hcu_conv_wgrad_tc5_supported(C.byref(d)))
-        tc = bool(f16 and (tc5 or lib.hcu_conv_wgrad_tc_supported(C.byref(d))))
+        # 8/16-channel levels: warp-specialised mma.sync pipeline
+        ws = bool(f16 and not tc5 and self.use_ws and lib.hcu_conv_wgrad_ws_supported(C.byref(d)))
+        tc = bool(f16 and (tc5 or ws or lib.hcu_conv_wgrad_tc_supported(C.byref(d))))
         nsplit = 1 if tc else ns
         if cache is not None and cache.ready and wname in cache.part_off and cache.scatter_jobs[wname][1:] == (nsplit, total):
             off = cache.part_off[wname]
@@ -831,9 +834,10 @@ class UnetEngine:
                 self._keep.extend(t for t in (a, b, isc, ish) if t is not None)  # alive until the streams join
             with torch.cuda.stream(side) if side is not None else _NullCtx():
                 _lib.note(*note)
-                if tc5:
-                    _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part),
-                                                          self._stream()), "wgrad_tc5")
+                if tc5 or ws:
+                    fn = lib.hcu_conv_wgrad_tc5_acc if tc5 else lib.hcu_conv_wgrad_ws_acc
+                    _lib.check(fn(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part), self._stream()),
+                               "wgrad_tc5" if tc5 else "wgrad_ws")
                 elif tc:
                     _lib.check(lib.hcu_conv_wgrad_tc_acc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part),
                                                          self._stream()), "wgrad_tc")
@@ -844,10 +848,11 @@ class UnetEngine:
         partial = torch.empty((nsplit, total), dtype=torch.float32, device=wref.device)
         gw = torch.empty_like(wref)
         _lib.note(*note)
-        if tc5:
+        if tc5 or ws:
             partial.zero_()
-            _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial),
-                                                  self._stream()), "wgrad_tc5")
+            fn = lib.hcu_conv_wgrad_tc5_acc if tc5 else lib.hcu_conv_wgrad_ws_acc
+            _lib.check(fn(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial), self._stream()),
+                       "wgrad_tc5" if tc5 else "wgrad_ws")
         elif tc:
             _lib.check(lib.hcu_conv_wgrad_tc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial),
                                              self._stream()), "wgrad_tc")

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 12
+#define HCU_ABI_VERSION 13
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -147,9 +147,14 @@ int hcu_conv_wgrad_tc(const HcuConvDesc* d, const void* a, const float* a_scale,
 /* Same, but ACCUMULATES into a `wacc` the caller has zeroed (one memset for every layer of a step). */
 int hcu_conv_wgrad_tc_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
                           float* wacc, void* stream);
-/* tcgen05 flavour for the channel-rich levels (wgrad_tc5.cu): the staged planes are MN-major UMMA operands with the
+/* hcu_conv_wgrad_ws_*: warp-specialised mma.sync pipeline for the 8/16-channel levels (wgrad_ws.cu; producer warps
+ * stage planes with cp.async while consumer warps run ldmatrix + MMA); same contract as hcu_conv_wgrad_tc_acc.
+ * tcgen05 flavour for the channel-rich levels (wgrad_tc5.cu): the staged planes are MN-major UMMA operands with the
  * pixel index as K, one M = 128 (Cin rows) x N = Cout MMA per tap and 16 pixels, taps split over CTAs by TMEM capacity.
  * Same contract as hcu_conv_wgrad_tc_acc (accumulates into a zeroed fp32 [taps][cin][cout]). */
+int hcu_conv_wgrad_ws_supported(const HcuConvDesc* d);
+int hcu_conv_wgrad_ws_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
+                          float* wacc, void* stream);
 int hcu_conv_wgrad_tc5_supported(const HcuConvDesc* d);
 int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
                            float* wacc, void* stream);

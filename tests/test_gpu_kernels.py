@@ -154,7 +154,7 @@ def test_conv_tc_agrees_with_simt_kernel():
 
 
 # ---- weight gradient on tensor cores (wgrad_mma.cu) ---------------------------------------------------------
-def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=False, use_tc5=False):
+def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=False, use_tc5=False, use_ws=False):
     """x [N,Cin,...] activations (pre-transform), dy [N,Cout,...] -> dW [Cout,Cin,kx,ky,kz] fp32."""
     from hcunet_b200 import _lib
     from hcunet_b200.engine import conv_desc
@@ -177,6 +177,10 @@ def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=
         part = torch.empty((ns, T * cin * cout), device="cuda")
         _lib.check(lib.hcu_conv_wgrad_partial(C.byref(d), P(xin), P(isc), P(ish), P(dyin), P(part), ns, stream()))
         wacc = part.sum(0)
+    elif use_ws:
+        assert lib.hcu_conv_wgrad_ws_supported(C.byref(d)) == 1
+        wacc = torch.zeros((T * cin * cout,), device="cuda")
+        _lib.check(lib.hcu_conv_wgrad_ws_acc(C.byref(d), P(xin), P(isc), P(ish), P(dyin), P(wacc), stream()), "wgrad_ws")
     elif use_tc5:
         assert lib.hcu_conv_wgrad_tc5_supported(C.byref(d)) == 1
         wacc = torch.zeros((T * cin * cout,), device="cuda")   # the tcgen05 kernel accumulates into a zeroed buffer
@@ -217,6 +221,38 @@ def test_wgrad_tc_matches_fp32(case):
     got = run_wgrad(x, dy, k, dil=dil, cpitch=cp)
     assert not torch.isnan(got).any()
     assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)   # exact fp16 products, fp32 accumulate
+
+
+# ---- warp-specialised weight gradient (wgrad_ws.cu, 8/16-channel levels) ------------------------------------
+WGS_CASES = [c for c in WG_CASES if (c[6] or c[1]) <= 32 and c[2] <= 8] + [
+    (2, 8, 8, (40, 60, 33), (3, 3, 2), (1, 1, 1), None),       # several runs, several x segments, ragged tail
+    (1, 16, 8, (20, 45, 31), (3, 3, 1), (1, 1, 1), None),
+    (1, 32, 8, (9, 30, 20), (3, 3, 2), (1, 1, 1), None),
+]
+
+
+@pytest.mark.parametrize("case", WGS_CASES)
+def test_wgrad_ws_matches_fp32(case):
+    n, cin, cout, isz, k, dil, cp = case
+    g = torch.Generator().manual_seed(hash(case) % 10000 + 5)
+    osz = tuple(isz[i] - (k[i] - 1) * dil[i] for i in range(3))
+    x = h16(torch.randn((n, cin) + isz, generator=g))
+    dy = h16(torch.randn((n, cout) + osz, generator=g))
+    ref = torch.nn.grad.conv3d_weight(x, (cout, cin) + k, dy, dilation=dil)
+    got = run_wgrad(x, dy, k, dil=dil, cpitch=cp, use_ws=True)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)   # exact fp16 products, fp32 accumulate
+
+
+def test_wgrad_ws_fused_input_bn_relu():
+    g = torch.Generator().manual_seed(29)
+    x = h16(torch.randn((2, 8, 12, 19, 17), generator=g))
+    dy = h16(torch.randn((2, 8, 10, 17, 16), generator=g))
+    sc, sh = torch.rand(8, generator=g) + 0.5, torch.randn(8, generator=g) * 0.3
+    a = h16(F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)))
+    ref = torch.nn.grad.conv3d_weight(a, (8, 8, 3, 3, 2), dy)
+    got = run_wgrad(x, dy, (3, 3, 2), in_affine=(sc, sh), use_ws=True)
+    assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)
 
 
 # ---- weight gradient on tcgen05 (wgrad_tc5.cu, channel-rich levels) -----------------------------------------

@@ -75,6 +75,9 @@ def main():
             if kind == "wgrad5":
                 wacc.zero_()
                 fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
+            elif kind == "wgradws":
+                wacc.zero_()
+                fn = lambda: _lib.check(lib.hcu_conv_wgrad_ws_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
             else:
                 fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
         if once:
