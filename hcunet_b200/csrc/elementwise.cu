@@ -482,11 +482,7 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __re
     sc[j] = scale[cg * 8 + j]; sf[j] = shift[cg * 8 + j]; mu[j] = mean[cg * 8 + j]; is[j] = invstd[cg * 8 + j];
     s1[j] = 0.f; s2[j] = 0.f;
   }
-  for (; e < total; e += stride) {
-    const uint32_t pix = e >> lc8;
-    const uint4 yr = *reinterpret_cast<const uint4*>(y + (size_t)pix * c + cg * 8);
-    float g[8];
-    load_g8(da, argmax, pg, pix, cg, c, g);
+  auto accum = [&](const uint4& yr, const float* g) {
     const __half2* yh = reinterpret_cast<const __half2*>(&yr);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -498,6 +494,24 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __re
       s2[2 * j] = fmaf(g0, (yv.x - mu[2 * j]) * is[2 * j], s2[2 * j]);
       s2[2 * j + 1] = fmaf(g1, (yv.y - mu[2 * j + 1]) * is[2 * j + 1], s2[2 * j + 1]);
     }
+  };
+  // two elements per trip: four independent 16-byte loads in flight per thread
+  for (; e + stride < total; e += 2 * stride) {
+    const uint32_t pix0 = e >> lc8, pix1 = (e + stride) >> lc8;
+    const uint4 y0 = *reinterpret_cast<const uint4*>(y + (size_t)pix0 * c + cg * 8);
+    const uint4 y1 = *reinterpret_cast<const uint4*>(y + (size_t)pix1 * c + cg * 8);
+    float g0[8], g1[8];
+    load_g8(da, argmax, pg, pix0, cg, c, g0);
+    load_g8(da, argmax, pg, pix1, cg, c, g1);
+    accum(y0, g0);
+    accum(y1, g1);
+  }
+  if (e < total) {
+    const uint32_t pix = e >> lc8;
+    const uint4 yr = *reinterpret_cast<const uint4*>(y + (size_t)pix * c + cg * 8);
+    float g[8];
+    load_g8(da, argmax, pg, pix, cg, c, g);
+    accum(yr, g);
   }
   // lanes l and l' hold the same channel group when l = l' (mod c8): butterfly over the other lane bits first
 #pragma unroll
@@ -947,7 +961,7 @@ extern "C" int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y,
       npix * (c / 8) < 0x7fffffffLL && (argmax == nullptr || (((uintptr_t)argmax) & 7) == 0)) {
     PoolGeom pg = {};
     if (argmax != nullptr) { int rc = fill_pool(pool, npix, pg, "bn_bwd_stats"); if (rc) return rc; }
-    const int grid = grid_for(npix * (c / 8), 256 * 4, 8);
+    const int grid = grid_for(npix * (c / 8), 256 * 4, 12);
     bn_bwd_stats_h8_kernel<<<grid, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
         (const __half*)da, (const __half*)y, npix, c, scale, shift, mean, invstd, relu, argmax, pg, sums);
     HCU_CHECK_LAUNCH("bn_bwd_stats_h8");
