@@ -67,6 +67,7 @@ struct Params {
   // shared memory carve-up (bytes from the 128-aligned base)
   int off_w, off_a, off_bar, off_tab, off_stat, smem_bytes;
   int tmem_cols;
+  int wide;      // x-fused MMAs: one MMA feeds up to KX output planes (N = w * Nc), 4 accumulator slots per M-block
   int D;         // producer look-ahead in planes (loads in flight beyond the published planes)
   int epi_fast;  // fp16 output, 8-channel aligned, no stride phases: vector epilogue
   // K16 step (tx, e): x = (byte offset of the first K8 slab inside a ring slot >> 4) | (offset of the second slab >> 4) << 16
@@ -279,10 +280,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-  // barrier map: full[R], empty[R], tfull[2], tempty[2], wbar
+  // barrier map: full[R], empty[R], tfull[4], tempty[4], wbar (2 accumulator buffers normally, 4 slots in wide mode)
   const uint32_t bar_full = smem_u32(bars), bar_empty = bar_full + 8 * p.R, bar_tfull = bar_empty + 8 * p.R,
-                 bar_tempty = bar_tfull + 16, bar_w = bar_tempty + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (2 * p.R + 5));
+                 bar_tempty = bar_tfull + 32, bar_w = bar_tempty + 32;
+  const int NB = p.wide ? 4 : 2;  // accumulator slots an output plane rotates through
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (2 * p.R + 9));
   float* sstat = reinterpret_cast<float*>(smem + p.off_stat);  // [2][Nc]
   float* sbias = sstat + 2 * p.Nc;                             // [3][Nc]: bias, out_scale, out_shift of this column chunk
   const uint32_t a_base = smem_u32(smem + p.off_a), w_base = smem_u32(smem + p.off_w);
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         mbar_init(bar_full + 8 * i, 4);   // one arrive per producer warp
         mbar_init(bar_empty + 8 * i, kIssuers);  // tcgen05.commit of every issuer
       }
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < 4; ++i) {
         mbar_init(bar_tfull + 8 * i, kIssuers);   // tcgen05.commit of every issuer
         mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
       }
@@ -480,49 +482,108 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     const uint32_t wdesc = (w_base >> 4) | ((((uint32_t)(Nc * 16)) >> 4) << 16);  // B: LBO = next K8 slab
     PROF_DECL;
     mbar_wait(bar_w, 0);
-    const int lastoff = (p.KX - 1) * p.dx;
-    int next_wait = 0, wslot = 0;
-    uint32_t wpar = 0;
-    int i_mod = 0;
-    for (int i = 0; i < nout; ++i) {
-      for (; next_wait <= i + lastoff; ++next_wait) {
-        PROF_WAIT(pw0, mbar_wait(bar_full + 8 * wslot, wpar));
-        if (++wslot == R) { wslot = 0; wpar ^= 1; }
-      }
-      const int buf = i & 1;
-      PROF_WAIT(pw1, mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1));
-      tc_fence_after();
-      const uint32_t tb = tmem_base + (uint32_t)(buf * MB * Nc);
-      // every operand below is warp-uniform (kernel parameters + uniform counters): the descriptors are built in the
-      // uniform datapath straight from the constant-bank table; the M-blocks are unrolled so that the four MMAs of a
-      // K16 step issue back to back (they accumulate into different TMEM tiles)
-      if (!(p.debug & 4)) {
-        for (int tx = 0; tx < p.KX; ++tx) {
-          int sl = i_mod + tx * p.dx;
-          sl -= sl >= R ? R : 0;
-          const uint32_t abase = a_desc0 + (uint32_t)(sl * (p.SLOT >> 4));
-          const uint2* T = p.tab + tx * p.npairs;
-#pragma unroll 1
+    if (p.wide) {
+      // x-fused schedule: input plane j feeds the output planes i = j - tx (tx = 0 .. KX-1) in ONE MMA per K16 step whose
+      // N spans their accumulator slots (4 slots per M-block, consecutive outputs in consecutive columns) against the
+      // weights laid out [K8 slab][KX-1-tx][Nc]: the A operand is fetched once per input plane instead of once per
+      // (input plane, tx).  A window that wraps around the slot ring is split in two, and the first K16 step of a new
+      // output plane (tx = 0) is issued on its own with accumulate = 0.
+      const int KX = p.KX;
+      const uint32_t wrow = (uint32_t)Nc;                               // 16-byte units per (KX-1-tx) block
+      const uint32_t wlbo = (((uint32_t)(KX * Nc * 16)) >> 4) << 16;    // next K8 slab
+      const uint32_t idesc0 = (1u << 4) | ((128u >> 4) << 24);
+      int wslot2 = 0;
+      uint32_t wpar2 = 0;
+      for (int j = 0; j < nplanes; ++j) {
+        PROF_WAIT(pw0, mbar_wait(bar_full + 8 * wslot2, wpar2));
+        if (j < nout) PROF_WAIT(pw1, mbar_wait(bar_tempty + 8 * (j & 3), ((j >> 2) & 1) ^ 1));
+        tc_fence_after();
+        const int i_lo = max(0, j - (KX - 1)), i_hi = min(j, nout - 1);
+        const uint32_t abase = a_desc0 + (uint32_t)(wslot2 * (p.SLOT >> 4));
+        // one MMA group (all M-blocks) for the outputs [ia, ib] (no slot wrap inside), K16 step e
+        auto emit = [&](int ia, int ib, const uint2 t, uint32_t acc) {
+          const uint32_t w = (uint32_t)(ib - ia + 1);
+          const uint32_t idw = idesc0 | (((w * (uint32_t)Nc) >> 3) << 17);
+          const uint32_t col = tmem_base + (uint32_t)((ia & 3) * Nc);
+          const uint64_t ad = desc_hi | (uint64_t)(abase + t.x);
+          const uint64_t bd = desc_hi | (uint64_t)(((w_base >> 4) + t.y + (uint32_t)(KX - 1 - (j - ia)) * wrow) | wlbo);
+          if (elect_one()) {
+            umma_f16(col, ad, bd, idw, acc);
+            if (MB > 1) umma_f16(col + (uint32_t)(4 * Nc), ad + 128u, bd, idw, acc);
+            if (MB > 2) umma_f16(col + (uint32_t)(8 * Nc), ad + 256u, bd, idw, acc);
+            if (MB > 3) umma_f16(col + (uint32_t)(12 * Nc), ad + 384u, bd, idw, acc);
+          }
+          __syncwarp();
+        };
+        auto emit_range = [&](int ia, int ib, const uint2 t, uint32_t acc) {  // split where the slot ring wraps
+          if (ia > ib) return;
+          const int first = min(ib - ia + 1, 4 - (ia & 3));
+          emit(ia, ia + first - 1, t, acc);
+          if (ia + first <= ib) emit(ia + first, ib, t, acc);
+        };
+        if (!(p.debug & 4) && i_lo <= i_hi) {
           for (int e = 0; e < p.npairs; ++e) {
-            const uint2 t = T[e];
-            const uint32_t acc = (uint32_t)(tx | e);
-            const uint64_t ad = desc_hi | (uint64_t)(abase + t.x), bd = desc_hi | (uint64_t)(wdesc + t.y);
-            if (elect_one()) {
-              umma_f16(tb, ad, bd, idesc, acc);
-              if (MB > 1) umma_f16(tb + (uint32_t)Nc, ad + 128u, bd, idesc, acc);
-              if (MB > 2) umma_f16(tb + (uint32_t)(2 * Nc), ad + 256u, bd, idesc, acc);
-              if (MB > 3) umma_f16(tb + (uint32_t)(3 * Nc), ad + 384u, bd, idesc, acc);
+            const uint2 t = p.tab[e];
+            if (e == 0 && i_hi == j) {  // output plane j starts here
+              emit_range(i_lo, j - 1, t, 1u);
+              emit(j, j, t, 0u);
+            } else {
+              emit_range(i_lo, i_hi, t, 1u);
             }
-            __syncwarp();
           }
         }
+        if (elect_one()) {
+          umma_commit(bar_empty + 8 * wslot2);                              // this input plane is consumed
+          if (j >= KX - 1) umma_commit(bar_tfull + 8 * ((j - (KX - 1)) & 3));  // output j-(KX-1) is complete
+        }
+        __syncwarp();
+        if (++wslot2 == R) { wslot2 = 0; wpar2 ^= 1; }
       }
-      if (leader) {
-        umma_commit(bar_empty + 8 * i_mod);  // plane i is not needed by later outputs
-        umma_commit(bar_tfull + 8 * buf);
+    } else {
+      const int lastoff = (p.KX - 1) * p.dx;
+      int next_wait = 0, wslot = 0;
+      uint32_t wpar = 0;
+      int i_mod = 0;
+      for (int i = 0; i < nout; ++i) {
+        for (; next_wait <= i + lastoff; ++next_wait) {
+          PROF_WAIT(pw0, mbar_wait(bar_full + 8 * wslot, wpar));
+          if (++wslot == R) { wslot = 0; wpar ^= 1; }
+        }
+        const int buf = i & 1;
+        PROF_WAIT(pw1, mbar_wait(bar_tempty + 8 * buf, ((i >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t tb = tmem_base + (uint32_t)(buf * MB * Nc);
+        // every operand below is warp-uniform (kernel parameters + uniform counters): the descriptors are built in the
+        // uniform datapath straight from the constant-bank table; the M-blocks are unrolled so that the four MMAs of a
+        // K16 step issue back to back (they accumulate into different TMEM tiles)
+        if (!(p.debug & 4)) {
+          for (int tx = 0; tx < p.KX; ++tx) {
+            int sl = i_mod + tx * p.dx;
+            sl -= sl >= R ? R : 0;
+            const uint32_t abase = a_desc0 + (uint32_t)(sl * (p.SLOT >> 4));
+            const uint2* T = p.tab + tx * p.npairs;
+  #pragma unroll 1
+            for (int e = 0; e < p.npairs; ++e) {
+              const uint2 t = T[e];
+              const uint32_t acc = (uint32_t)(tx | e);
+              const uint64_t ad = desc_hi | (uint64_t)(abase + t.x), bd = desc_hi | (uint64_t)(wdesc + t.y);
+              if (elect_one()) {
+                umma_f16(tb, ad, bd, idesc, acc);
+                if (MB > 1) umma_f16(tb + (uint32_t)Nc, ad + 128u, bd, idesc, acc);
+                if (MB > 2) umma_f16(tb + (uint32_t)(2 * Nc), ad + 256u, bd, idesc, acc);
+                if (MB > 3) umma_f16(tb + (uint32_t)(3 * Nc), ad + 384u, bd, idesc, acc);
+              }
+              __syncwarp();
+            }
+          }
+        }
+        if (leader) {
+          umma_commit(bar_empty + 8 * i_mod);  // plane i is not needed by later outputs
+          umma_commit(bar_tfull + 8 * buf);
+        }
+        __syncwarp();
+        i_mod = i_mod + 1 == R ? 0 : i_mod + 1;
       }
-      __syncwarp();
-      i_mod = i_mod + 1 == R ? 0 : i_mod + 1;
     }
     PROF_REPORT("mma", "wait_full", "wait_tempty", nout);
   } else {
@@ -555,8 +616,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) bs[j] = sbias[j];
       for (int i = 0; i < nout; ++i) {
-        const int buf = i & 1;
-        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1));
+        const int buf = i & (NB - 1);
+        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i / NB) & 1));
         tc_fence_after();
         if (p.debug & 2) {
           tc_fence_before();
@@ -567,7 +628,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         uint32_t r[4][8];
 #pragma unroll
         for (int mb = 0; mb < 4; ++mb)
-          if (mb < MB) tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)((buf * MB + mb) * Nc), r[mb]);
+          if (mb < MB) tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)((p.wide ? mb * 4 + buf : buf * MB + mb) * Nc), r[mb]);
         tmem_wait_ld();
 #pragma unroll
         for (int mb = 0; mb < 4; ++mb)
@@ -628,8 +689,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
 #pragma unroll
       for (int j = 0; j < 16; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
       for (int i = 0; i < nout; ++i) {
-        const int buf = i & 1;
-        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1));
+        const int buf = i & (NB - 1);
+        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i / NB) & 1));
         tc_fence_after();
         __half* oplane = reinterpret_cast<__half*>(p.out) + obase0 + (long long)(x0 + i) * p.out_sx;
 #pragma unroll
@@ -638,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
           const bool valid = poff[mb] >= 0;
           for (int cc = 0; cc < nch; cc += 16) {
             float v[16];
-            tmem_ld16(tmem_base + lane_base + (uint32_t)((buf * MB + mb) * Nc + cc), v);
+            tmem_ld16(tmem_base + lane_base + (uint32_t)((p.wide ? mb * 4 + buf : buf * MB + mb) * Nc + cc), v);
             if (has_bias) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
@@ -708,8 +769,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       const int out_f32 = p.out_f32;
       const bool phased = p.ops[0] * p.ops[1] * p.ops[2] > 1;
       for (int i = 0; i < nout; ++i) {
-        const int buf = i & 1;
-        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i >> 1) & 1));
+        const int buf = i & (NB - 1);
+        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i / NB) & 1));
         tc_fence_after();
         const long long obase = obase0 + (long long)(x0 + i) * p.out_sx;
 #pragma unroll 1
@@ -718,7 +779,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
 #pragma unroll 1
           for (int cc = 0; cc < nch; cc += 16) {
             float v[16];
-            tmem_ld16(tmem_base + lane_base + (uint32_t)((buf * MB + mb) * Nc + cc), v);
+            tmem_ld16(tmem_base + lane_base + (uint32_t)((p.wide ? mb * 4 + buf : buf * MB + mb) * Nc + cc), v);
             const int ch0 = ns * Nc + cc;  // first output channel of this chunk
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] += sbias[cc + j];
@@ -806,16 +867,27 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
 }
 
 // weights: fp32 [taps][cin][cout] (hcu_weight_gather layout, one group) -> fp16 [nsplit][E][Nc][8]
+// packed weight layouts: normal [nsplit][tx][K8 slab e][Nc][8]; wide (x-fused MMAs) [e][KX-1-tx][Nc][8]
+__device__ __forceinline__ void unpack_index(uint32_t r, int KX, int E_tx, int Nc, int wide, int& nn, int& e, int& tx, int& ns) {
+  nn = (int)(r % (uint32_t)Nc); r /= (uint32_t)Nc;
+  if (wide) {
+    tx = KX - 1 - (int)(r % (uint32_t)KX);
+    e = (int)(r / (uint32_t)KX);
+    ns = 0;
+  } else {
+    e = (int)(r % (uint32_t)E_tx); r /= (uint32_t)E_tx;
+    tx = (int)(r % (uint32_t)KX);
+    ns = (int)(r / (uint32_t)KX);
+  }
+}
+
 __global__ void pack_tc_kernel(const float* __restrict__ w, __half* __restrict__ out, int KX, int KYZ, int P, int E_tx,
-                               int Nc, int nsplit, int cin, int cout) {
+                               int Nc, int nsplit, int cin, int cout, int wide) {
   const long long total = (long long)nsplit * KX * E_tx * Nc * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i & 7);
-    long long r = i >> 3;
-    const int nn = (int)(r % Nc); r /= Nc;
-    const int e = (int)(r % E_tx); r /= E_tx;
-    const int tx = (int)(r % KX);
-    const int ns = (int)(r / KX);
+    int nn, e, tx, ns;
+    unpack_index((uint32_t)(i >> 3), KX, E_tx, Nc, wide, nn, e, tx, ns);
     float v = 0.f;
     if (e < KYZ * P) {
       const int t = e / P, pl = e % P;
@@ -828,15 +900,12 @@ __global__ void pack_tc_kernel(const float* __restrict__ w, __half* __restrict__
 
 // weights straight from the reference-layout parameter (HcuWeightMap) -> fp16 [nsplit][E][Nc][8]
 __global__ void pack_tc_ref_kernel(HcuWeightMap m, const float* __restrict__ ref, __half* __restrict__ out, int KX, int KYZ,
-                                   int P, int E_tx, int Nc, int nsplit, int cin, int cout) {
+                                   int P, int E_tx, int Nc, int nsplit, int cin, int cout, int wide) {
   const long long total = (long long)nsplit * KX * E_tx * Nc * 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i & 7);
-    long long r = i >> 3;
-    const int nn = (int)(r % Nc); r /= Nc;
-    const int e = (int)(r % E_tx); r /= E_tx;
-    const int tx = (int)(r % KX);
-    const int ns = (int)(r / KX);
+    int nn, e, tx, ns;
+    unpack_index((uint32_t)(i >> 3), KX, E_tx, Nc, wide, nn, e, tx, ns);
     float v = 0.f;
     if (e < KYZ * P) {
       const int t = e / P, pl = e % P;
@@ -857,7 +926,7 @@ struct PackJob {
   HcuWeightMap m;
   long long ref_off, out_off, total;
   int KX, KYZ, P, E_tx, Nc, nsplit, cin, cout;
-  int block0, nblocks;
+  int block0, nblocks, wide, pad_;
 };
 static_assert(sizeof(PackJob) <= HCU_BATCH_JOB_BYTES, "PackJob does not fit its table slot");
 constexpr int kPackPerBlock = 2048;  // elements per block (256 threads x 8)
@@ -889,11 +958,8 @@ __global__ void __launch_bounds__(256) pack_tc_batch_kernel(const unsigned char*
     const long long i = base + k;
     if (i >= J.total) break;
     const int j = (int)(i & 7);
-    uint32_t r = (uint32_t)(i >> 3);  // 32-bit index arithmetic: job sizes are < 2^31 (checked at build time)
-    const int nn = (int)(r % (uint32_t)J.Nc); r /= (uint32_t)J.Nc;
-    const int e = (int)(r % (uint32_t)J.E_tx); r /= (uint32_t)J.E_tx;
-    const int tx = (int)(r % (uint32_t)J.KX);
-    const int ns = (int)(r / (uint32_t)J.KX);
+    int nn, e, tx, ns;  // 32-bit index arithmetic: job sizes are < 2^31 (checked at build time)
+    unpack_index((uint32_t)(i >> 3), J.KX, J.E_tx, J.Nc, J.wide, nn, e, tx, ns);
     float v = 0.f;
     if (e < J.KYZ * J.P) {
       const int t = e / J.P, pl = e % J.P;
@@ -983,6 +1049,11 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   // then D = 2 + slack 2, D = 1 + slack 1, anything.  Within a sweep aim for 2 CTAs / SM (the register file allows no
   // more), then whatever fits; big M first; Nc as large as fits.
   const int want[4] = {5, 4, 2, 0};
+  static int wide_on = -1;
+  if (wide_on < 0) { const char* e = getenv("HCU_TC_WIDE"); wide_on = e ? atoi(e) : 1; }
+  // x-fused ("wide") MMAs for the 8..32-channel levels: the tensor pipe's time there is the shared-memory fetch of the A
+  // operand (profiles/r01_umma_rate.txt), which this mode does once per input plane instead of once per (plane, tx)
+  const bool can_wide = wide_on && p.KX >= 2 && p.KX <= 3 && p.dx == 1 && npad <= 32;
   for (int pass = 0; pass < 2; ++pass) {
     const int budget = pass == 0 ? 112 * 1024 : kSmemLimit;
     for (int sweep = 0; sweep < 4; ++sweep) {
@@ -990,6 +1061,8 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
         const int M = m_cands[mi];
         if (M > 128 && M - 128 >= plane_q) continue;  // do not use a longer run than the plane needs
         const int MB = M / 128;
+        const bool wide = can_wide && 4 * MB * npad <= 256;  // 4 accumulator slots per M-block, two CTAs per SM
+        if (can_wide && !wide && MB > 1) continue;            // prefer a shorter run that can go wide
         int run = M + halo;
         int ps = run * 16;
         if (P > 1) {  // spread the channel planes over the banks: PS = g (mod 2g), g = max(16, 128 / P)
@@ -999,22 +1072,23 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
         const int slot = ps * P;
         for (int nc = npad > 128 ? 128 : npad; nc >= 16; nc -= 16) {
           if (npad % nc != 0) continue;
-          if (2 * MB * nc > 512) continue;
+          if (wide && nc != npad) break;
+          if ((wide ? 4 : 2) * MB * nc > 512) continue;
           const int wbytes = p.E * nc * 16;
-          const int R = span + want[sweep];
+          const int R = (wide ? 1 : span) + want[sweep];  // wide: every input plane is consumed by ONE step
           if (R > kMaxRing) continue;
           const int off_w = 0;
           const int off_a = round_up(wbytes, 128);
           const int off_bar = off_a + R * slot;
-          const int off_stat = round_up(off_bar + 8 * (2 * R + 5) + 8, 16);
+          const int off_stat = round_up(off_bar + 8 * (2 * R + 9) + 8, 16);
           const int total = off_stat + 5 * nc * 4 + 128;
           if (total > budget) continue;
-          p.M = M; p.MB = MB; p.RUN = run; p.PS = ps; p.SLOT = slot; p.R = R;
+          p.M = M; p.MB = MB; p.RUN = run; p.PS = ps; p.SLOT = slot; p.R = R; p.wide = wide ? 1 : 0;
           p.D = want[sweep] >= 4 ? 2 : (want[sweep] >= 2 ? 1 : 0);
           p.Nc = nc; p.nsplit = npad / nc;
           p.off_w = off_w; p.off_a = off_a; p.off_bar = off_bar; p.off_tab = 0; p.off_stat = off_stat;
           p.smem_bytes = total;
-          int cols = 2 * MB * nc, t = 32;
+          int cols = (wide ? 4 : 2) * MB * nc, t = 32;
           while (t < cols) t <<= 1;
           p.tmem_cols = t;
           p.n_runs = (plane_q + M - 1) / M;
@@ -1031,7 +1105,8 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
               }
               if (off1 < off0 || ((off1 - off0) >> 4) > 0x3fff) return "K8 slab stride not encodable";
               p.tab[tx * p.npairs + e].x = ((uint32_t)off0 >> 4) | (((uint32_t)(off1 - off0) >> 4) << 16);
-              p.tab[tx * p.npairs + e].y = (uint32_t)((tx * p.E_tx + e0) * nc * 16) >> 4;
+              // wide: [K8 slab][KX-1-tx][Nc] -- the tx block is added by the issuer; normal: [tx][K8 slab][Nc]
+              p.tab[tx * p.npairs + e].y = wide ? (uint32_t)(e0 * p.KX * nc) : (uint32_t)((tx * p.E_tx + e0) * nc * 16) >> 4;
             }
           return nullptr;
         }
@@ -1066,7 +1141,7 @@ extern "C" int hcu_conv_tc_pack(const HcuConvDesc* d, const float* w, void* pack
   const long long total = (long long)p.nsplit * p.E * p.Nc * 8;
   int grid = (int)std::min<long long>((total + 255) / 256, 4096);
   tc::pack_tc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, (__half*)packed, p.KX, p.KY * p.KZ, p.P, p.E_tx, p.Nc,
-                                                             p.nsplit, d->cin, d->cout);
+                                                             p.nsplit, d->cin, d->cout, p.wide);
   HCU_CHECK_LAUNCH("pack_tc");
   return 0;
 }
@@ -1086,7 +1161,7 @@ extern "C" int hcu_conv_tc_pack_ref(const HcuConvDesc* d, const HcuWeightMap* m,
   const long long total = (long long)p.nsplit * p.E * p.Nc * 8;
   int grid = (int)std::min<long long>((total + 255) / 256, 4096);
   tc::pack_tc_ref_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*m, ref, (__half*)packed, p.KX, p.KY * p.KZ, p.P, p.E_tx,
-                                                                 p.Nc, p.nsplit, d->cin, d->cout);
+                                                                 p.Nc, p.nsplit, d->cin, d->cout, p.wide);
   HCU_CHECK_LAUNCH("pack_tc_ref");
   return 0;
 }
@@ -1112,7 +1187,7 @@ extern "C" int hcu_conv_tc_pack_batch_build(const HcuConvDesc* descs, const HcuW
     j.total = (long long)p.nsplit * p.E * p.Nc * 8;
     HCU_CHECK_ARG(j.total < 0x7fffffffLL, "conv_tc_pack_batch_build: job %d too large", i);
     j.KX = p.KX; j.KYZ = p.KY * p.KZ; j.P = p.P; j.E_tx = p.E_tx; j.Nc = p.Nc; j.nsplit = p.nsplit;
-    j.cin = descs[i].cin; j.cout = descs[i].cout;
+    j.cin = descs[i].cin; j.cout = descs[i].cout; j.wide = p.wide;
     j.block0 = b0;
     j.nblocks = (int)((j.total + tc::kPackPerBlock - 1) / tc::kPackPerBlock);
     b0 += j.nblocks;
