@@ -236,12 +236,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // Stage timing (compile with -DHCU_TC_PROF; experiments only): cycles spent waiting at each barrier vs. total per role
 #ifdef HCU_TC_PROF
-#define PROF_DECL long long pw0 = 0, pw1 = 0, pt0 = clock64()
+#define PROF_DECL long long pw0 = 0, pw1 = 0, pw2 = 0, pt0 = clock64()
 #define PROF_WAIT(acc, stmt) { const long long t_ = clock64(); stmt; acc += clock64() - t_; }
 #define PROF_REPORT(role, n0, n1, iters)                                                                   \
   if (blockIdx.x == gridDim.x / 2 && lane == 0)                                                            \
-    printf("conv_tc prof %-8s warp %d: total %lld cyc, %s %lld, %s %lld, iters %d -> %lld cyc/iter busy\n", role, warp, \
-           clock64() - pt0, n0, pw0, n1, pw1, iters, (clock64() - pt0 - pw0 - pw1) / max(1, iters))
+    printf("conv_tc prof %-8s warp %d: total %lld cyc, %s %lld, %s %lld, fence %lld, iters %d -> %lld cyc/iter busy\n", role, warp, \
+           clock64() - pt0, n0, pw0, n1, pw1, pw2, iters, (clock64() - pt0 - pw0 - pw1) / max(1, iters))
 #else
 #define PROF_DECL
 #define PROF_WAIT(acc, stmt) stmt
@@ -249,6 +249,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 #endif
 
 // ---------------------------------------------------------------------------------------------------
+// compile-time chunk counts for the producer's unrolled loops: a predicated-off chunk still costs its issue slots (the
+// 12-way unrolled loops executed ~1400 instructions per plane for 5 live chunks), so the loops are instantiated per count
+template <int N>
+struct IC { static constexpr int value = N; };
+#define HCU_DISPATCH_NCHUNK(n, fn)            \
+  do {                                        \
+    if ((n) <= 4) fn(IC<4>{});                \
+    else if ((n) <= 5) fn(IC<5>{});           \
+    else if ((n) <= 6) fn(IC<6>{});           \
+    else if ((n) <= 8) fn(IC<8>{});           \
+    else if ((n) <= 10) fn(IC<10>{});         \
+    else fn(IC<12>{});                        \
+  } while (0)
 constexpr int kMaxChunk = 12;  // producer fast path: <= 12 16-byte chunks per thread per x-plane, addresses precomputed
 
 // BatchNorm affine + ReLU of 8 fp16 channels: fp32 multiply-add (one rounding, like the reference's fp32 op followed
@@ -391,22 +404,25 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         if (xm >= 0 && xm < p.IX) {  // warp-uniform
           unsigned char* dp = smem + p.off_a + slot_f * p.SLOT + plane * p.PS + pix0 * 16;
           if (fast) {
+            auto body = [&](auto NC) {
+              constexpr int N = decltype(NC)::value;
 #pragma unroll
-            for (int g = 0; g < kMaxChunk; g += 4) {
-              if (g < nmax) {  // CTA-uniform
+              for (int g = 0; g < N; g += 4) {
                 uint4 v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   v[u] = make_uint4(0u, 0u, 0u, 0u);
-                  if (goff[g + u] >= 0) v[u] = *reinterpret_cast<const uint4*>(dp + (g + u) * sstep);
+                  if (g + u < N && goff[g + u] >= 0) v[u] = *reinterpret_cast<const uint4*>(dp + (g + u) * sstep);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = bn_relu8(v[u], bn, relu);
+                for (int u = 0; u < 4; ++u)
+                  if (g + u < N) v[u] = bn_relu8(v[u], bn, relu);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                  if (goff[g + u] >= 0) *reinterpret_cast<uint4*>(dp + (g + u) * sstep) = v[u];
+                  if (g + u < N && goff[g + u] >= 0) *reinterpret_cast<uint4*>(dp + (g + u) * sstep) = v[u];
               }
-            }
+            };
+            HCU_DISPATCH_NCHUNK(nmax, body);
           } else {
             int yv = yv0, zv = zv0;
             for (int c = 0; c < nchunk; ++c) {
@@ -421,7 +437,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
           }
         }
       }
-      fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
+      PROF_WAIT(pw2, fence_proxy_async());  // generic-proxy writes -> visible to the tensor core's async proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_full + 8 * slot_f);
       if (++slot_f == R) slot_f = 0;
@@ -444,13 +460,17 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         const uint32_t dst = dst0 + (uint32_t)(slot_i * p.SLOT);
         if (p.debug & 1) {
         } else if (fast) {
+          auto body = [&](auto NC) {
+            constexpr int N = decltype(NC)::value;
 #pragma unroll
-          for (int c = 0; c < kMaxChunk; ++c) {
-            if (c < nmax && goff[c] != -2) {
-              const bool ok = xok && goff[c] >= 0;
-              cp_async16(dst + c * sstep, ok ? in_x + goff[c] : in_n, ok ? 16u : 0u);
+            for (int c = 0; c < N; ++c) {
+              if (goff[c] != -2) {
+                const bool ok = xok && goff[c] >= 0;
+                cp_async16(dst + c * sstep, ok ? in_x + goff[c] : in_n, ok ? 16u : 0u);
+              }
             }
-          }
+          };
+          HCU_DISPATCH_NCHUNK(nmax, body);
         } else {
           int yv = yv0, zv = zv0;
           for (int c = 0; c < nchunk; ++c) {
