@@ -75,6 +75,12 @@ def main():
             if kind == "wgrad5":
                 wacc.zero_()
                 fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
+            elif kind == "wgrad_auto":   # what the engine picks: warp-specialised kernel when it takes the shape
+                wacc.zero_()
+                if lib.hcu_conv_wgrad_ws_supported(C.byref(d)):
+                    fn = lambda: _lib.check(lib.hcu_conv_wgrad_ws_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
+                else:
+                    fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
             elif kind == "wgradws":
                 wacc.zero_()
                 fn = lambda: _lib.check(lib.hcu_conv_wgrad_ws_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
