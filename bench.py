@@ -337,6 +337,20 @@ def main_ours(args):
                 H.cross_entropy(model(resident[i % NBUF][0]), resident[i % NBUF][1], resident[i % NBUF][2], "pixel").backward()
                 opt.step()
         roof = prof.roofline(peaks, t_step * min(args.steps, 5))
+        # DRAM traffic of the dominant kernel: not measurable live (needs ncu); the committed capture of the same command
+        # (tools/gpu_profile.sh -> profiles/*_traffic.json) is reported per launch, like `achieved`
+        try:
+            import glob
+            for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json"))):
+                tj = json.load(open(f))
+                if roof is not None and tj.get("kernel") == roof.get("kernel"):
+                    roof["traffic"] = tj["dram_bytes_per_launch"]
+                    roof["traffic_unit"] = "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)"
+                    roof["traffic_source"] = os.path.relpath(f, ROOT)
+                    roof["algorithmic_bytes_per_launch"] = roof["achieved"] * 1e9 * roof["avg_launch_ms"] / 1e3 \
+                        if roof.get("unit") == "GB/s" else None
+        except Exception:
+            pass
         if os.environ.get("HCUNET_PROFILE_OUT"):
             nst = min(args.steps, 5)
             rows = [dict(kernel=k[0], layer=k[1], ms=v["ms"] / nst, calls=v["calls"] / nst, bytes=v["bytes"] / nst,

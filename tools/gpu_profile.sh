@@ -13,3 +13,6 @@ ncu --set full --clock-control none --import-source on -k regex:"wgrad_ws_kernel
   python tools/kernel_bench.py wgrad_auto d0.conv1 d0.conv2 d1.conv1 d1.conv2 --once > $OUT/ncu_full2.log 2>&1; echo "ncu full wgrad rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"wgrad_tc5_kernel" -c 3 -f -o $OUT/full_wgrad5_$TAG \
   python tools/kernel_bench.py wgrad5 d2.conv2 d3.conv2 d4.conv1 --once > $OUT/ncu_full3.log 2>&1; echo "ncu full wgrad5 rc=$?"
+# DRAM traffic of every conv_tc launch of one steady-state step (bench.py reports the per-launch mean as roofline.traffic)
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_tc_kernel" --launch-skip 102 -c 52 --csv \
+  --log-file $OUT/conv_tc_dram_$TAG.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-profile > $OUT/ncu_dram.log 2>&1; echo "ncu dram rc=$?"
