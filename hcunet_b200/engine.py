@@ -321,6 +321,8 @@ class UnetEngine:
         self._caches: Dict[tuple, _StepCache] = {}
         self._cache: Optional[_StepCache] = None   # cache of the call in progress
         self._side = None
+        self._side2 = None
+        self.n_side = int(os.environ.get("HCUNET_SIDE_STREAMS", "1"))  # 2 was measured: no gain
         self._keep: List[torch.Tensor] = []
 
     @property
@@ -617,12 +619,16 @@ class UnetEngine:
         if batched and self.overlap_wgrad and _lib._ProfState.profiler is None:
             if self._side is None or self._side.device != dlogits.device:
                 self._side = torch.cuda.Stream(device=dlogits.device)
+                self._side2 = torch.cuda.Stream(device=dlogits.device)
             side = self._side
             side.wait_stream(torch.cuda.current_stream())
         self._wstream = side
+        self._wflip = 0
         if batched:
             with torch.cuda.stream(side) if side is not None else _NullCtx():
                 cache.wacc.zero_()
+            if side is not None and self.n_side > 1:
+                self._side2.wait_stream(side)   # the second gradient stream starts behind the workspace memset
         adt = _DT[act_dtype]
         esz = 2 if act_dtype == torch.float16 else 4
         dev = dlogits.device
@@ -765,6 +771,8 @@ class UnetEngine:
                     self._conv(d2, dcur, w, None, dprev, layer=u.name + ".dgrad")
                 dcur, dcur_dt = dprev, adt
         if batched:
+            if side is not None and self.n_side > 1:
+                side.wait_stream(self._side2)
             with torch.cuda.stream(side) if side is not None else _NullCtx():
                 _lib.check(lib.hcu_weight_scatter_batch(_ptr(cache.scatter_table), len(cache.scatter_jobs),
                                                         cache.scatter_blocks, _ptr(cache.wacc), 1.0, _ptr(inv),
@@ -788,9 +796,18 @@ class UnetEngine:
         return a
 
     def _colsum(self, x, dt, npix, c, scratch):
+        """Per-channel sum (bias gradients of the layers without a BatchNorm behind them).  Only a gradient comes out of
+        it, so with a side stream it leaves the data-gradient chain like the weight gradients do."""
         out = torch.empty(c, dtype=torch.float32, device=x.device)
-        _lib.check(self.lib.hcu_colsum(_ptr(x), dt, npix, c, 0, c, 1.0, _ptr(self._inv), _ptr(scratch), _ptr(out),
-                                       self._stream()), "colsum")
+        side = getattr(self, "_wstream", None)
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            side.wait_event(ev)
+            self._keep.append(x)
+        with torch.cuda.stream(side) if side is not None else _NullCtx():
+            _lib.check(self.lib.hcu_colsum(_ptr(x), dt, npix, c, 0, c, 1.0, _ptr(self._inv), _ptr(scratch), _ptr(out),
+                                           self._stream()), "colsum")
         return out
 
     def _wgrad_conv(self, g: ConvGeom, a_in, a_cp, a_xf, a_dt, dy, dy_dt, B, wref):
@@ -828,6 +845,9 @@ class UnetEngine:
             gw = self._gflat[goff:goff + wref.numel()].view(wref.shape)
             side = self._wstream
             if side is not None:
+                if self.n_side > 1:  # alternate two gradient streams: the small deep-level kernels overlap each other too
+                    self._wflip ^= 1
+                    side = self._side2 if self._wflip else side
                 ev = torch.cuda.Event()
                 ev.record()
                 side.wait_event(ev)
