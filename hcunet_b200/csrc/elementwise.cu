@@ -79,6 +79,17 @@ __global__ void nc_to_cl_kernel(const TS* __restrict__ src, TD* __restrict__ dst
   }
 }
 
+// single channel: both layouts are the same array -- a cast (and the optional device scale), nothing to transpose
+template <typename TS, typename TD>
+__global__ void cast_scale_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long total, int cpitch,
+                                  const float* __restrict__ dscale) {
+  const float mul = dscale != nullptr ? dscale[0] : 1.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    dst[i * cpitch] = from_f<TD>(to_f(src[i]) * mul);
+    for (int k = 1; k < cpitch; ++k) dst[i * cpitch + k] = from_f<TD>(0.f);  // zero padding channels
+  }
+}
+
 template <typename TS, typename TD>
 __global__ void cl_to_nc_kernel(const TS* __restrict__ src, TD* __restrict__ dst, long long n, int c, long long s,
                                 int cpitch, const float* __restrict__ dscale) {
@@ -778,6 +789,13 @@ extern "C" int hcu_nc_to_cl(const void* src, int32_t dtype_src, void* dst, int32
   long long tiles = n * ((s + 31) / 32) * ((cpitch + 31) / 32);
   int grid = (int)(tiles < (long long)num_sms() * 16 ? tiles : (long long)num_sms() * 16);
   dim3 block(32, 8);
+  if (c == 1 && cpitch <= 8) {
+    HCU_DISPATCH_DTYPE(dtype_src, TS, HCU_DISPATCH_ACT(dtype_dst, TD,
+        cast_scale_kernel<TS, TD><<<grid_for(n * s, 256), 256, 0, (cudaStream_t)stream>>>((const TS*)src, (TD*)dst, n * s, cpitch,
+                                                                                      dscale)));
+    HCU_CHECK_LAUNCH("nc_to_cl(cast)");
+    return 0;
+  }
   HCU_DISPATCH_DTYPE(dtype_src, TS, HCU_DISPATCH_ACT(dtype_dst, TD,
       nc_to_cl_kernel<TS, TD><<<grid, block, 0, (cudaStream_t)stream>>>((const TS*)src, (TD*)dst, n, c, s, cpitch, dscale)));
   HCU_CHECK_LAUNCH("nc_to_cl");

@@ -646,12 +646,15 @@ class UnetEngine:
             _lib.check(lib.hcu_grad_scale(_ptr(dlogits), dlogits.numel(), GRAD_SCALE_TARGET,
                                           _ptr(scratch.view(torch.int32)), _ptr(scales), st), "grad_scale")
             scl, inv = scales[0:1], scales[1:2]
+        dcur_cp = co
         if co == 1 and scl is None:
             dcur = dlogits.view(B, So, 1)
             dcur_dt = _lib.F32
         else:
-            dcur = torch.empty((B, So, co), dtype=act_dtype, device=dev)
-            _lib.check(lib.hcu_nc_to_cl(_ptr(dlogits), _lib.F32, _ptr(dcur), adt, B, co, So, co, _ptr(scl), st),
+            # fp16: channel pitch padded to 8 (zeros) so the out_conv gradients take the tensor-core kernels too
+            dcur_cp = -(-co // 8) * 8 if act_dtype == torch.float16 else co
+            dcur = torch.empty((B, So, dcur_cp), dtype=act_dtype, device=dev)
+            _lib.check(lib.hcu_nc_to_cl(_ptr(dlogits), _lib.F32, _ptr(dcur), adt, B, co, So, dcur_cp, _ptr(scl), st),
                        "nc_to_cl")
             dcur_dt = adt
         self._inv = inv
@@ -665,10 +668,10 @@ class UnetEngine:
             if kind == "out":
                 _, g, a_in, a_cp, a_xf = item
                 npix = B * So
-                grads[g.name + ".bias"] = self._colsum(dcur, dcur_dt, npix, co, scratch)
+                grads[g.name + ".bias"] = self._colsum(dcur, dcur_dt, npix, co, scratch, cpitch=dcur_cp)
                 grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, a_cp, a_xf, adt, dcur, dcur_dt, B,
-                                                             params[g.name + ".weight"])
-                dcur = self._dgrad_conv(g, dcur, dcur_dt, B, params[g.name + ".weight"], act_dtype)
+                                                             params[g.name + ".weight"], dy_cp=dcur_cp)
+                dcur = self._dgrad_conv(g, dcur, dcur_dt, B, params[g.name + ".weight"], act_dtype, dy_cp=dcur_cp)
                 dcur_dt = adt
             elif kind == "conv":
                 _, g, a_in, a_cp, a_xf, y, vec, argmax = item
@@ -795,7 +798,7 @@ class UnetEngine:
                                               self._stream()), "bn_relu_apply")
         return a
 
-    def _colsum(self, x, dt, npix, c, scratch):
+    def _colsum(self, x, dt, npix, c, scratch, cpitch=None):
         """Per-channel sum (bias gradients of the layers without a BatchNorm behind them).  Only a gradient comes out of
         it, so with a side stream it leaves the data-gradient chain like the weight gradients do."""
         out = torch.empty(c, dtype=torch.float32, device=x.device)
@@ -806,13 +809,13 @@ class UnetEngine:
             side.wait_event(ev)
             self._keep.append(x)
         with torch.cuda.stream(side) if side is not None else _NullCtx():
-            _lib.check(self.lib.hcu_colsum(_ptr(x), dt, npix, c, 0, c, 1.0, _ptr(self._inv), _ptr(scratch), _ptr(out),
-                                           self._stream()), "colsum")
+            _lib.check(self.lib.hcu_colsum(_ptr(x), dt, npix, cpitch or c, 0, c, 1.0, _ptr(self._inv), _ptr(scratch),
+                                           _ptr(out), self._stream()), "colsum")
         return out
 
-    def _wgrad_conv(self, g: ConvGeom, a_in, a_cp, a_xf, a_dt, dy, dy_dt, B, wref):
+    def _wgrad_conv(self, g: ConvGeom, a_in, a_cp, a_xf, a_dt, dy, dy_dt, B, wref, dy_cp=None):
         T = g.taps[0] * g.taps[1] * g.taps[2]
-        d = conv_desc(a_dt, dy_dt, B, g.in_sz, a_cp, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0, g.cout_g,
+        d = conv_desc(a_dt, dy_dt, B, g.in_sz, a_cp, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, dy_cp or g.cout_t, 0, g.cout_g,
                       g.groups, g.taps, g.dil, in_relu=int(a_xf is not None))
         m = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
         roles = g.groups * T * (-(-g.cin_g // 8)) * (-(-g.cout_g // 8))
@@ -885,7 +888,7 @@ class UnetEngine:
             cache.scatter_jobs[wname] = (HcuWeightMap.from_buffer_copy(wm), nsplit, total)
         return gw
 
-    def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype, out_cp=None):
+    def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype, out_cp=None, dy_cp=None):
         adt = _DT[act_dtype]
         T = g.taps[0] * g.taps[1] * g.taps[2]
         w = (self._wm_conv_dgrad(g), wref, g.groups * T * g.cin_g * g.cout_g, g.name + ".weight")
@@ -893,7 +896,7 @@ class UnetEngine:
         alloc = torch.zeros if cpo != g.cin_t else torch.empty
         dprev = alloc((B, g.in_sz[0] * g.in_sz[1] * g.in_sz[2], cpo), dtype=act_dtype, device=dy.device)
         pad = tuple((g.taps[i] - 1) * g.dil[i] for i in range(3))
-        d = conv_desc(dy_dt, adt, B, g.out_sz, g.cout_t, 0, g.cout_g, g.cout_g, g.in_sz, g.in_sz, cpo, 0, g.cin_g,
+        d = conv_desc(dy_dt, adt, B, g.out_sz, dy_cp or g.cout_t, 0, g.cout_g, g.cout_g, g.in_sz, g.in_sz, cpo, 0, g.cin_g,
                       g.groups, g.taps, g.dil, pad=pad)
         self._conv(d, dy, w, None, dprev, layer=g.name + ".dgrad")
         return dprev
