@@ -474,7 +474,7 @@ __device__ __forceinline__ void load_g8(const __half* __restrict__ da, const uin
   }
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __restrict__ da, const __half* __restrict__ y,
+__global__ void __launch_bounds__(256, 3) bn_bwd_stats_h8_kernel(const __half* __restrict__ da, const __half* __restrict__ y,
                                                              long long npix, int c, const float* __restrict__ scale,
                                                              const float* __restrict__ shift, const float* __restrict__ mean,
                                                              const float* __restrict__ invstd, int relu,
@@ -487,10 +487,12 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __re
   const uint32_t total = (uint32_t)(npix * c8), stride = gridDim.x * blockDim.x;  // stride % c8 == 0
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   const int cg = (int)(e & (uint32_t)(c8 - 1));
-  float sc[8], sf[8], mu[8], is[8], s1[8], s2[8];
+  // the loop accumulates sum(g) and sum(g * y) only; sum(g * xhat) = invstd * (sum(g*y) - mean * sum(g)) is formed per
+  // block in fp64 when the block's partials are flushed (fewer registers -> more blocks per SM, half the arithmetic)
+  float sc[8], sf[8], s1[8], s2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    sc[j] = scale[cg * 8 + j]; sf[j] = shift[cg * 8 + j]; mu[j] = mean[cg * 8 + j]; is[j] = invstd[cg * 8 + j];
+    sc[j] = scale[cg * 8 + j]; sf[j] = shift[cg * 8 + j];
     s1[j] = 0.f; s2[j] = 0.f;
   }
   auto accum = [&](const uint4& yr, const float* g) {
@@ -502,8 +504,8 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __re
       if (relu && fmaf(yv.x, sc[2 * j], sf[2 * j]) <= 0.f) g0 = 0.f;
       if (relu && fmaf(yv.y, sc[2 * j + 1], sf[2 * j + 1]) <= 0.f) g1 = 0.f;
       s1[2 * j] += g0; s1[2 * j + 1] += g1;
-      s2[2 * j] = fmaf(g0, (yv.x - mu[2 * j]) * is[2 * j], s2[2 * j]);
-      s2[2 * j + 1] = fmaf(g1, (yv.y - mu[2 * j + 1]) * is[2 * j + 1], s2[2 * j + 1]);
+      s2[2 * j] = fmaf(g0, yv.x, s2[2 * j]);
+      s2[2 * j + 1] = fmaf(g1, yv.y, s2[2 * j + 1]);
     }
   };
   // two elements per trip: four independent 16-byte loads in flight per thread
@@ -540,8 +542,12 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_h8_kernel(const __half* __re
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x)
-    atomicAdd(&sums[(size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * c + i], (double)sh[i]);
+  double* sb = sums + (size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * c;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    const double sg = (double)sh[i], sgy = (double)sh[c + i];
+    atomicAdd(&sb[i], sg);
+    atomicAdd(&sb[c + i], (double)invstd[i] * (sgy - (double)mean[i] * sg));
+  }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_h8_kernel(const __half* __restrict__ da, const __half* __restrict__ y,
