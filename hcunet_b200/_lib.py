@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 F32, BF16, F16 = 0, 1, 2
 BATCH_JOB_BYTES = 256
@@ -41,6 +41,18 @@ class HcuWeightMap(C.Structure):
     ]
 
 
+class HcuBnFin(C.Structure):
+    _fields_ = [("count", C.c_double), ("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float),
+                ("momentum", C.c_float), ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("mean", C.c_void_p),
+                ("invstd", C.c_void_p), ("scale", C.c_void_p), ("shift", C.c_void_p), ("counter", C.c_void_p)]
+
+
+class HcuBnBwdFin(C.Structure):
+    _fields_ = [("count", C.c_double), ("gamma", C.c_void_p), ("training", C.c_int32), ("grad_scale", C.c_float),
+                ("dscale", C.c_void_p), ("dgamma", C.c_void_p), ("dbeta", C.c_void_p), ("dbias", C.c_void_p),
+                ("coef", C.c_void_p), ("counter", C.c_void_p)]
+
+
 class HcuPoolGeom(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n", "ix", "iy", "iz", "px", "py", "pz")]
 
@@ -68,6 +80,7 @@ SIGNATURES = {
     "hcu_conv_tc_pack": [C.POINTER(HcuConvDesc), P, P, P],
     "hcu_conv_tc_pack_ref": [C.POINTER(HcuConvDesc), C.POINTER(HcuWeightMap), P, P, P],
     "hcu_conv_tc_fwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
+    "hcu_conv_tc_fwd_bn": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, C.POINTER(HcuBnFin), P],
     "hcu_conv_wgrad_partial": [C.POINTER(HcuConvDesc), P, P, P, P, P, I32, P],
     "hcu_conv_wgrad_tc_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_wgrad_tc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
@@ -93,6 +106,8 @@ SIGNATURES = {
     "hcu_bn_relu_maxpool": [P, I32, P, I32, P, I32, I32, I32, I32, I32, I32, I32, I32, P, P, I32, P],
     "hcu_maxpool_bwd": [P, I32, P, P, I32, I32, I32, I32, I32, I32, I32, I32, I32, P],
     "hcu_bn_bwd_stats": [P, I32, P, I32, I64, I32, P, P, P, P, I32, P, C.POINTER(HcuPoolGeom), P, P],
+    "hcu_bn_bwd_stats_fin": [P, I32, P, I32, I64, I32, P, P, P, P, I32, P, C.POINTER(HcuPoolGeom), P,
+                             C.POINTER(HcuBnBwdFin), P],
     "hcu_bn_bwd_finalize": [P, I32, D, P, P, P, I32, F, P, P, P, P, P, P],
     "hcu_bn_bwd_apply": [P, I32, P, I32, P, I32, I64, I32, P, P, I32, P, P, C.POINTER(HcuPoolGeom), P],
     "hcu_colsum": [P, I32, I64, I32, I32, I32, F, P, P, P, P],

@@ -48,6 +48,7 @@ struct Params {
   const float* out_shift;
   double* stats;
   int stats_pitch;
+  HcuBnFin fin;  // optional fused BatchNorm finalize (fin.counter == nullptr: none)
   int N, IX, IY, IZ, Cp, P;
   int OX, OY, OZ;
   int KX, KY, KZ, dx, dy, dz, px, py, pz;
@@ -874,6 +875,39 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         }
       }
     }
+    if (do_stats && p.fin.counter != nullptr) {
+      // fused hcu_bn_finalize: the CTA that takes the last ticket sees every CTA's partial sums
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (row == 0) sstat[0] = (atomicAdd(p.fin.counter, 1u) == gridDim.x - 1) ? 1.f : 0.f;
+      named_bar_sync(1, 128);
+      if (sstat[0] != 0.f) {
+        __threadfence();
+        const int pitch = p.stats_pitch;
+        for (int ch = row; ch < cout; ch += 128) {
+          double s1 = 0.0, s2 = 0.0;
+          for (int b = 0; b < HCU_STAT_BINS; ++b) {
+            s1 += __ldcg(&p.stats[(size_t)b * 2 * pitch + p.out_c_off + ch]);
+            s2 += __ldcg(&p.stats[(size_t)b * 2 * pitch + pitch + p.out_c_off + ch]);
+          }
+          const double mu = s1 / p.fin.count;
+          double var = s2 / p.fin.count - mu * mu;
+          if (var < 0.0) var = 0.0;
+          const float is = (float)(1.0 / sqrt(var + (double)p.fin.eps));
+          const float muf = (float)mu;
+          p.fin.mean[ch] = muf;
+          p.fin.invstd[ch] = is;
+          const float sc = p.fin.gamma[ch] * is;
+          p.fin.scale[ch] = sc;
+          p.fin.shift[ch] = p.fin.beta[ch] - muf * sc;
+          if (p.fin.running_mean != nullptr) {
+            const double unbiased = p.fin.count > 1.0 ? var * p.fin.count / (p.fin.count - 1.0) : var;
+            p.fin.running_mean[ch] = (1.f - p.fin.momentum) * p.fin.running_mean[ch] + p.fin.momentum * muf;
+            p.fin.running_var[ch] = (1.f - p.fin.momentum) * p.fin.running_var[ch] + p.fin.momentum * (float)unbiased;
+          }
+        }
+      }
+    }
   }
 
 
@@ -1228,9 +1262,9 @@ extern "C" int hcu_conv_tc_pack_batch(const void* dev_jobs, int32_t n, int32_t b
   return 0;
 }
 
-extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
-                               const float* in_scale, const float* in_shift, const float* out_scale,
-                               const float* out_shift, void* out, double* stats, void* stream) {
+static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
+                            const float* in_scale, const float* in_shift, const float* out_scale,
+                            const float* out_shift, void* out, double* stats, const HcuBnFin* fin, void* stream) {
   HCU_CHECK_ARG(d && in && packed && out, "conv_tc_fwd: null pointer");
   HCU_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "conv_tc_fwd: in_scale/in_shift must come together");
   HCU_CHECK_ARG((out_scale == nullptr) == (out_shift == nullptr), "conv_tc_fwd: out_scale/out_shift must come together");
@@ -1254,6 +1288,13 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
   p.in = (const __half*)in; p.wp = (const __half*)packed; p.out = out;
   p.bias = bias; p.in_scale = in_scale; p.in_shift = in_shift; p.out_scale = out_scale; p.out_shift = out_shift;
   p.stats = stats; p.stats_pitch = d->out_cpitch;
+  memset(&p.fin, 0, sizeof(p.fin));
+  if (fin != nullptr) {
+    HCU_CHECK_ARG(stats && fin->gamma && fin->beta && fin->mean && fin->invstd && fin->scale && fin->shift && fin->counter &&
+                      fin->count > 0 && d->out_c_off == 0 && d->out_cpitch == d->cout,
+                  "conv_tc_fwd_bn: bad finalize arguments");
+    p.fin = *fin;
+  }
   const long long tz = d->out_cpitch, ty = tz * d->out_tsize[2], tx = ty * d->out_tsize[1], tn = tx * d->out_tsize[0];
   p.out_sn = tn; p.out_sx = tx * d->ostep[0]; p.out_sy = ty * d->ostep[1]; p.out_sz = tz * d->ostep[2];
   p.out_base = tx * d->ooff[0] + ty * d->ooff[1] + tz * d->ooff[2];
@@ -1307,4 +1348,16 @@ extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void*
   tc::conv_tc_kernel<<<(unsigned)grid, tc::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(p);
   HCU_CHECK_LAUNCH("conv_tc");
   return 0;
+}
+
+extern "C" int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
+                               const float* in_scale, const float* in_shift, const float* out_scale,
+                               const float* out_shift, void* out, double* stats, void* stream) {
+  return conv_tc_fwd_impl(d, in, packed, bias, in_scale, in_shift, out_scale, out_shift, out, stats, nullptr, stream);
+}
+
+extern "C" int hcu_conv_tc_fwd_bn(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
+                                  const float* in_scale, const float* in_shift, const float* out_scale,
+                                  const float* out_shift, void* out, double* stats, const HcuBnFin* fin, void* stream) {
+  return conv_tc_fwd_impl(d, in, packed, bias, in_scale, in_shift, out_scale, out_shift, out, stats, fin, stream);
 }

@@ -474,12 +474,16 @@ __device__ __forceinline__ void load_g8(const __half* __restrict__ da, const uin
   }
 }
 
+__device__ __forceinline__ void bn_bwd_finalize_one(const double* sums, int c, int i, double count, const float* gamma,
+                                                    const float* mean, const float* invstd, int training, float grad_scale,
+                                                    float* dgamma, float* dbeta, float* dbias, float* coef);
+
 __global__ void __launch_bounds__(256, 3) bn_bwd_stats_h8_kernel(const __half* __restrict__ da, const __half* __restrict__ y,
                                                              long long npix, int c, const float* __restrict__ scale,
                                                              const float* __restrict__ shift, const float* __restrict__ mean,
                                                              const float* __restrict__ invstd, int relu,
                                                              const uint8_t* __restrict__ argmax, PoolGeom pg,
-                                                             double* __restrict__ sums) {
+                                                             double* __restrict__ sums, HcuBnBwdFin fin) {
   extern __shared__ float sh[];  // [2][c]
   for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
@@ -547,6 +551,21 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_stats_h8_kernel(const __half* _
     const double sg = (double)sh[i], sgy = (double)sh[c + i];
     atomicAdd(&sb[i], sg);
     atomicAdd(&sb[c + i], (double)invstd[i] * (sgy - (double)mean[i] * sg));
+  }
+  if (fin.counter != nullptr) {  // fused hcu_bn_bwd_finalize: the block that takes the last ticket sees every partial sum
+    __shared__ int last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      float gs = fin.grad_scale;
+      if (fin.dscale != nullptr) gs *= fin.dscale[0];
+      for (int i = threadIdx.x; i < c; i += blockDim.x)
+        bn_bwd_finalize_one(sums, c, i, fin.count, fin.gamma, mean, invstd, fin.training, gs, fin.dgamma, fin.dbeta,
+                            fin.dbias, fin.coef);
+    }
   }
 }
 
@@ -629,16 +648,14 @@ __global__ void bn_bwd_stats_kernel(const TD* __restrict__ da, const TY* __restr
     atomicAdd(&sums[(size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * c + i], (double)sh[i]);
 }
 
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int c, double count,
-                                       const float* __restrict__ gamma, const float* __restrict__ mean,
-                                       const float* __restrict__ invstd, int training, float grad_scale,
-                                       const float* __restrict__ dscale, float* dgamma, float* dbeta, float* dbias,
-                                       float* coef) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  if (dscale != nullptr) grad_scale *= dscale[0];
+__device__ __forceinline__ void bn_bwd_finalize_one(const double* sums, int c, int i, double count, const float* gamma,
+                                                    const float* mean, const float* invstd, int training, float grad_scale,
+                                                    float* dgamma, float* dbeta, float* dbias, float* coef) {
   double sg = 0.0, sgx = 0.0;
-  for (int b = 0; b < HCU_STAT_BINS; ++b) { sg += sums[(size_t)b * 2 * c + i]; sgx += sums[(size_t)b * 2 * c + c + i]; }
+  for (int b = 0; b < HCU_STAT_BINS; ++b) {
+    sg += __ldcg(&sums[(size_t)b * 2 * c + i]);
+    sgx += __ldcg(&sums[(size_t)b * 2 * c + c + i]);
+  }
   if (dgamma != nullptr) dgamma[i] = (float)(sgx * grad_scale);
   if (dbeta != nullptr) dbeta[i] = (float)(sg * grad_scale);
   const double s = (double)gamma[i] * (double)invstd[i];
@@ -657,6 +674,17 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int c, d
   coef[i] = (float)c1;
   coef[c + i] = (float)c2;
   coef[2 * c + i] = (float)c3;
+}
+
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int c, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, int training, float grad_scale,
+                                       const float* __restrict__ dscale, float* dgamma, float* dbeta, float* dbias,
+                                       float* coef) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  if (dscale != nullptr) grad_scale *= dscale[0];
+  bn_bwd_finalize_one(sums, c, i, count, gamma, mean, invstd, training, grad_scale, dgamma, dbeta, dbias, coef);
 }
 
 template <typename TD, typename TY, typename TO, bool VEC>
@@ -975,19 +1003,26 @@ static int fill_pool(const HcuPoolGeom* g, int64_t npix, PoolGeom& pg, const cha
   return 0;
 }
 
-extern "C" int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix,
-                                int32_t c, const float* scale, const float* shift, const float* mean,
-                                const float* invstd, int32_t relu, const uint8_t* argmax, const HcuPoolGeom* pool,
-                                double* sums, void* stream) {
+extern "C" int hcu_bn_bwd_finalize(const double* sums, int32_t c, double count, const float* gamma, const float* mean,
+                                   const float* invstd, int32_t training, float grad_scale, const float* dscale,
+                                   float* dgamma, float* dbeta, float* dbias, float* coef, void* stream);
+
+static int bn_bwd_stats_impl(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix,
+                             int32_t c, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, int32_t relu, const uint8_t* argmax, const HcuPoolGeom* pool,
+                             double* sums, const HcuBnBwdFin* fin, void* stream) {
   HCU_CHECK_ARG(da && y && scale && shift && mean && invstd && sums && npix > 0 && c > 0, "bn_bwd_stats: bad args");
   HCU_CHECK_ARG(c <= 4096, "bn_bwd_stats: too many channels");
   if (dtype_da == HCU_F16 && dtype_y == HCU_F16 && c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0 && aligned16(da) && aligned16(y) &&
       npix * (c / 8) < 0x7fffffffLL && (argmax == nullptr || (((uintptr_t)argmax) & 7) == 0)) {
     PoolGeom pg = {};
     if (argmax != nullptr) { int rc = fill_pool(pool, npix, pg, "bn_bwd_stats"); if (rc) return rc; }
+    HcuBnBwdFin f;
+    memset(&f, 0, sizeof(f));
+    if (fin != nullptr) f = *fin;
     const int grid = grid_for(npix * (c / 8), 256 * 4, 12);
     bn_bwd_stats_h8_kernel<<<grid, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
-        (const __half*)da, (const __half*)y, npix, c, scale, shift, mean, invstd, relu, argmax, pg, sums);
+        (const __half*)da, (const __half*)y, npix, c, scale, shift, mean, invstd, relu, argmax, pg, sums, f);
     HCU_CHECK_LAUNCH("bn_bwd_stats_h8");
     return 0;
   }
@@ -1001,7 +1036,27 @@ extern "C" int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y,
                                                                                  scale, shift, mean, invstd, relu,
                                                                                  sums)));
   HCU_CHECK_LAUNCH("bn_bwd_stats");
+  if (fin != nullptr)
+    return hcu_bn_bwd_finalize(sums, c, fin->count, fin->gamma, mean, invstd, fin->training, fin->grad_scale, fin->dscale,
+                               fin->dgamma, fin->dbeta, fin->dbias, fin->coef, stream);
   return 0;
+}
+
+extern "C" int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix,
+                                int32_t c, const float* scale, const float* shift, const float* mean,
+                                const float* invstd, int32_t relu, const uint8_t* argmax, const HcuPoolGeom* pool,
+                                double* sums, void* stream) {
+  return bn_bwd_stats_impl(da, dtype_da, y, dtype_y, npix, c, scale, shift, mean, invstd, relu, argmax, pool, sums, nullptr,
+                           stream);
+}
+
+extern "C" int hcu_bn_bwd_stats_fin(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix,
+                                    int32_t c, const float* scale, const float* shift, const float* mean,
+                                    const float* invstd, int32_t relu, const uint8_t* argmax, const HcuPoolGeom* pool,
+                                    double* sums, const HcuBnBwdFin* fin, void* stream) {
+  HCU_CHECK_ARG(fin && fin->gamma && fin->coef && fin->counter && fin->count > 0, "bn_bwd_stats_fin: bad finalize arguments");
+  return bn_bwd_stats_impl(da, dtype_da, y, dtype_y, npix, c, scale, shift, mean, invstd, relu, argmax, pool, sums, fin,
+                           stream);
 }
 
 extern "C" int hcu_bn_bwd_finalize(const double* sums, int32_t c, double count, const float* gamma, const float* mean,

@@ -348,7 +348,7 @@ class UnetEngine:
         return out
 
     def _conv(self, d, x, wspec, bias=None, out=None, stats=None, in_scale=None, in_shift=None, out_scale=None,
-              out_shift=None, layer=None, key=None):
+              out_shift=None, layer=None, key=None, bn_fin=None):
         """One gather-convolution launch.  wspec = (HcuWeightMap, reference-layout parameter, packed element count).
         fp16 activations take the tcgen05 kernel whenever it supports the descriptor (weights gathered, folded and
         packed to fp16 UMMA tiles in one launch), everything else the FFMA kernel (fp32 [g][taps][cin][cout])."""
@@ -373,10 +373,15 @@ class UnetEngine:
                 if cache is not None and not cache.ready and isinstance(wspec[3] if len(wspec) > 3 else None, str):
                     cache.pack_jobs[key] = (HcuConvDesc.from_buffer_copy(d), HcuWeightMap.from_buffer_copy(wm), wspec[3], nb)
             _lib.note(layer, nbytes, flops)
+            if bn_fin is not None:  # BatchNorm finalize as the kernel's fused tail (returns True: no separate launch)
+                _lib.check(lib.hcu_conv_tc_fwd_bn(C.byref(d), _ptr(x), pk, _ptr(bias), _ptr(in_scale), _ptr(in_shift),
+                                                  _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats),
+                                                  C.byref(bn_fin), self._stream()), "conv_tc_fwd_bn")
+                return True
             _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), _ptr(x), pk, _ptr(bias), _ptr(in_scale), _ptr(in_shift),
                                            _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), self._stream()),
                        "conv_tc_fwd")
-            return
+            return False
         w = self._gather_w(wm, ref, nw)
         _lib.note(layer, nbytes, flops)
         _lib.check(lib.hcu_conv_fwd(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
@@ -483,7 +488,10 @@ class UnetEngine:
         fold_eval = not save and not training  # inference: BN folded into the conv epilogue
         SB = _lib.STAT_BINS  # binned fp64 reductions (include/hcunet_b200.h "HCU_STAT_BINS")
         nstat = sum(2 * g.cout_t * SB for g in plan.steps if isinstance(g, ConvGeom) and g.bn is not None)
-        zero_ws = torch.zeros(nstat, dtype=torch.float64, device=dev) if training else None  # one memset per forward
+        nbn = sum(1 for g in plan.steps if isinstance(g, ConvGeom) and g.bn is not None)
+        # one memset per forward: the binned statistics + one 8-byte "last CTA" ticket counter per BatchNorm
+        zero_ws = torch.zeros(nstat + nbn, dtype=torch.float64, device=dev) if training else None
+        kbn = 0
         zoff = 0
         logits = None
         for g in plan.steps:
@@ -531,10 +539,15 @@ class UnetEngine:
             if training:
                 stats = zero_ws[zoff:zoff + 2 * g.cout_t * SB]
                 zoff += 2 * g.cout_t * SB
-                self._conv(d, cur, w, bias, y, stats=stats, in_scale=isc, in_shift=ish, layer=g.name)
-                _lib.check(lib.hcu_bn_finalize(_ptr(stats), g.cout_t, float(npix), _ptr(gamma), _ptr(beta), BN_EPS,
-                                               BN_MOMENTUM, _ptr(rm), _ptr(rv), _ptr(vec[0]), _ptr(vec[1]),
-                                               _ptr(vec[2]), _ptr(vec[3]), st), "bn_finalize")
+                fin = _lib.HcuBnFin(float(npix), gamma.data_ptr(), beta.data_ptr(), BN_EPS, BN_MOMENTUM, rm.data_ptr(),
+                                    rv.data_ptr(), vec[0].data_ptr(), vec[1].data_ptr(), vec[2].data_ptr(),
+                                    vec[3].data_ptr(), zero_ws.data_ptr() + 8 * (nstat + kbn))
+                kbn += 1
+                fused = self._conv(d, cur, w, bias, y, stats=stats, in_scale=isc, in_shift=ish, layer=g.name, bn_fin=fin)
+                if not fused:
+                    _lib.check(lib.hcu_bn_finalize(_ptr(stats), g.cout_t, float(npix), _ptr(gamma), _ptr(beta), BN_EPS,
+                                                   BN_MOMENTUM, _ptr(rm), _ptr(rv), _ptr(vec[0]), _ptr(vec[1]),
+                                                   _ptr(vec[2]), _ptr(vec[3]), st), "bn_finalize")
             else:
                 # eval-mode forward that must be differentiable: running statistics
                 self._conv(d, cur, w, bias, y, in_scale=isc, in_shift=ish, layer=g.name)
@@ -661,7 +674,10 @@ class UnetEngine:
         dx = None
         SB = _lib.STAT_BINS
         nstat = sum(2 * it[1].cout_t * SB for it in saved if it[0] == "conv")
-        zero_ws = torch.zeros(nstat, dtype=torch.float64, device=dev)  # one memset for every BN-backward reduction
+        nbn = sum(1 for it in saved if it[0] == "conv")
+        # one memset for every BN-backward reduction + one 8-byte ticket counter per BatchNorm
+        zero_ws = torch.zeros(nstat + nbn, dtype=torch.float64, device=dev)
+        kbn = 0
         zoff = 0
         for item in reversed(saved):
             kind = item[0]
@@ -692,18 +708,18 @@ class UnetEngine:
                 sums = zero_ws[zoff:zoff + 2 * g.cout_t * SB]
                 zoff += 2 * g.cout_t * SB
                 _lib.note(g.name, 2 * npix * g.cout_t * esz, 0)
-                _lib.check(lib.hcu_bn_bwd_stats(_ptr(dcur), dcur_dt, _ptr(y), adt, npix, g.cout_t, _ptr(vec[2]),
-                                                _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(pool_arg),
-                                                C.byref(pool_geom) if pool_geom is not None else None, _ptr(sums), st),
-                           "bn_bwd_stats")
                 dgamma = torch.empty(g.cout_t, dtype=torch.float32, device=dev)
                 dbeta = torch.empty_like(dgamma)
                 dbias = torch.empty_like(dgamma)
                 coef = torch.empty((3, g.cout_t), dtype=torch.float32, device=dev)
-                _lib.check(lib.hcu_bn_bwd_finalize(_ptr(sums), g.cout_t, float(npix), _ptr(params[g.bn + ".weight"]),
-                                                   _ptr(vec[0]), _ptr(vec[1]), 1 if training else 0, 1.0, _ptr(inv),
-                                                   _ptr(dgamma), _ptr(dbeta), _ptr(dbias), _ptr(coef), st),
-                           "bn_bwd_finalize")
+                fin = _lib.HcuBnBwdFin(float(npix), params[g.bn + ".weight"].data_ptr(), 1 if training else 0, 1.0,
+                                       inv.data_ptr() if inv is not None else None, dgamma.data_ptr(), dbeta.data_ptr(),
+                                       dbias.data_ptr(), coef.data_ptr(), zero_ws.data_ptr() + 8 * (nstat + kbn))
+                kbn += 1
+                _lib.check(lib.hcu_bn_bwd_stats_fin(_ptr(dcur), dcur_dt, _ptr(y), adt, npix, g.cout_t, _ptr(vec[2]),
+                                                    _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(pool_arg),
+                                                    C.byref(pool_geom) if pool_geom is not None else None, _ptr(sums),
+                                                    C.byref(fin), st), "bn_bwd_stats_fin")
                 dy = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
                 _lib.note(g.name, 3 * npix * g.cout_t * esz, 0)
                 _lib.check(lib.hcu_bn_bwd_apply(_ptr(dcur), dcur_dt, _ptr(y), adt, _ptr(dy), adt, npix, g.cout_t,

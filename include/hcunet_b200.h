@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 13
+#define HCU_ABI_VERSION 14
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -105,6 +105,36 @@ typedef struct HcuConvDesc {
   int32_t reserved[2];
 } HcuConvDesc;
 
+/* Optional fused tails ("last CTA done" pattern: the CTA that takes the last ticket of `counter` -- a uint32 the caller
+ * zeroes -- runs the tiny per-channel finalize inside the producing kernel, saving one dependent launch per layer):
+ *  HcuBnFin    : what hcu_bn_finalize computes, run at the end of hcu_conv_tc_fwd_bn;
+ *  HcuBnBwdFin : what hcu_bn_bwd_finalize computes, run at the end of hcu_bn_bwd_stats_fin. */
+typedef struct HcuBnFin {
+  double count;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum;
+  float* running_mean;   /* may be NULL together with running_var */
+  float* running_var;
+  float* mean;
+  float* invstd;
+  float* scale;
+  float* shift;
+  uint32_t* counter;
+} HcuBnFin;
+typedef struct HcuBnBwdFin {
+  double count;
+  const float* gamma;
+  int32_t training;
+  float grad_scale;
+  const float* dscale;   /* optional device scalar multiplied into grad_scale */
+  float* dgamma;
+  float* dbeta;
+  float* dbias;          /* may be NULL */
+  float* coef;           /* [3][c] */
+  uint32_t* counter;
+} HcuBnBwdFin;
+
 struct HcuWeightMap;
 
 /* W: fp32 [groups][taps][cin][cout].  bias/out_scale/out_shift: fp32 [groups*cout] or NULL.
@@ -128,6 +158,11 @@ int hcu_conv_tc_pack_ref(const HcuConvDesc* d, const struct HcuWeightMap* m, con
 int hcu_conv_tc_fwd(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
                     const float* in_scale, const float* in_shift, const float* out_scale,
                     const float* out_shift, void* out, double* stats, void* stream);
+/* Same, plus the BatchNorm finalize of the produced statistics as a fused tail (fin may be NULL). */
+int hcu_conv_tc_fwd_bn(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
+                    const float* in_scale, const float* in_shift, const float* out_scale,
+                    const float* out_shift, void* out, double* stats, const HcuBnFin* fin,
+                       void* stream);
 
 /* Weight gradient of the same gather-convolution:
  *   R[g][t][ca][cb] = sum_{n,o} A(a[n, o*istep - pad + t*dil, a_c_off + g*a_c_gstep + ca]) * b[n, o, b_c_off + g*cb_n + cb]
@@ -249,6 +284,11 @@ typedef struct HcuPoolGeom { int32_t n, ix, iy, iz, px, py, pz; } HcuPoolGeom;
 int hcu_bn_bwd_stats(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix, int32_t c,
                      const float* scale, const float* shift, const float* mean, const float* invstd,
                      int32_t relu, const uint8_t* argmax, const HcuPoolGeom* pool, double* sums, void* stream);
+/* pass 1 + pass 2 in one call: fused tail on the fp16 vector path (one launch), two launches otherwise. */
+int hcu_bn_bwd_stats_fin(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, int64_t npix, int32_t c,
+                         const float* scale, const float* shift, const float* mean, const float* invstd,
+                         int32_t relu, const uint8_t* argmax, const HcuPoolGeom* pool, double* sums,
+                         const HcuBnBwdFin* fin, void* stream);
 /* pass 2 (tiny): dgamma, dbeta, conv-bias grad and the coefficients of dy = c1*g + c2*y + c3.
  * training != 0: batch-stat backward; training == 0: running-stat (eval) backward. */
 int hcu_bn_bwd_finalize(const double* sums, int32_t c, double count, const float* gamma, const float* mean,
