@@ -921,13 +921,13 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
 }
 
 // weights: fp32 [taps][cin][cout] (hcu_weight_gather layout, one group) -> fp16 [nsplit][E][Nc][8]
-// packed weight layouts: normal [nsplit][tx][K8 slab e][Nc][8]; wide (x-fused MMAs) [e][KX-1-tx][Nc][8]
+// packed weight layouts: normal [nsplit][tx][K8 slab e][Nc][8]; wide (x-fused MMAs) [nsplit][e][KX-1-tx][Nc][8]
 __device__ __forceinline__ void unpack_index(uint32_t r, int KX, int E_tx, int Nc, int wide, int& nn, int& e, int& tx, int& ns) {
   nn = (int)(r % (uint32_t)Nc); r /= (uint32_t)Nc;
   if (wide) {
-    tx = KX - 1 - (int)(r % (uint32_t)KX);
-    e = (int)(r / (uint32_t)KX);
-    ns = 0;
+    tx = KX - 1 - (int)(r % (uint32_t)KX); r /= (uint32_t)KX;
+    e = (int)(r % (uint32_t)E_tx);
+    ns = (int)(r / (uint32_t)E_tx);
   } else {
     e = (int)(r % (uint32_t)E_tx); r /= (uint32_t)E_tx;
     tx = (int)(r % (uint32_t)KX);
@@ -1107,16 +1107,16 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   if (wide_on < 0) { const char* e = getenv("HCU_TC_WIDE"); wide_on = e ? atoi(e) : 1; }
   // x-fused ("wide") MMAs for the 8..32-channel levels: the tensor pipe's time there is the shared-memory fetch of the A
   // operand (profiles/r01_umma_rate.txt), which this mode does once per input plane instead of once per (plane, tx)
-  const bool can_wide = wide_on && p.KX >= 2 && p.KX <= 3 && p.dx == 1 && npad <= 32;
-  for (int pass = 0; pass < 2; ++pass) {
+  const bool can_wide = wide_on && p.KX >= 2 && p.KX <= 3 && p.dx == 1;
+  const bool small_wide = can_wide && npad <= 32;  // the byte-bound levels: insist on the wide mode
+  auto search = [&](int pass) -> bool {
     const int budget = pass == 0 ? 112 * 1024 : kSmemLimit;
     for (int sweep = 0; sweep < 4; ++sweep) {
       for (int mi = 0; mi < 4; ++mi) {
         const int M = m_cands[mi];
         if (M > 128 && M - 128 >= plane_q) continue;  // do not use a longer run than the plane needs
         const int MB = M / 128;
-        const bool wide = can_wide && 4 * MB * npad <= 256;  // 4 accumulator slots per M-block, two CTAs per SM
-        if (can_wide && !wide && MB > 1) continue;            // prefer a shorter run that can go wide
+        if (small_wide && 4 * MB * npad > 256 && MB > 1) continue;  // prefer a shorter run that can go wide at 2 CTAs / SM
         int run = M + halo;
         int ps = run * 16;
         if (P > 1) {  // spread the channel planes over the banks: PS = g (mod 2g), g = max(16, 128 / P)
@@ -1126,7 +1126,8 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
         const int slot = ps * P;
         for (int nc = npad > 128 ? 128 : npad; nc >= 16; nc -= 16) {
           if (npad % nc != 0) continue;
-          if (wide && nc != npad) break;
+          // wide: 4 accumulator slots per M-block in TMEM, an MMA spans up to KX slots (N = KX * nc <= 256)
+          const bool wide = can_wide && p.KX * nc <= 256 && 4 * MB * nc <= 512 && (!small_wide || 4 * MB * nc <= 256);
           if ((wide ? 4 : 2) * MB * nc > 512) continue;
           const int wbytes = p.E * nc * 16;
           const int R = (wide ? 1 : span) + want[sweep];  // wide: every input plane is consumed by ONE step
@@ -1157,17 +1158,29 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
                 const int t1 = e1 / P, c1 = e1 % P;
                 off1 = ((t1 / p.KZ) * p.dy * p.Zv + (t1 % p.KZ) * p.dz) * 16 + c1 * ps;
               }
-              if (off1 < off0 || ((off1 - off0) >> 4) > 0x3fff) return "K8 slab stride not encodable";
+              if (off1 < off0 || ((off1 - off0) >> 4) > 0x3fff) return false;
               p.tab[tx * p.npairs + e].x = ((uint32_t)off0 >> 4) | (((uint32_t)(off1 - off0) >> 4) << 16);
               // wide: [K8 slab][KX-1-tx][Nc] -- the tx block is added by the issuer; normal: [tx][K8 slab][Nc]
               p.tab[tx * p.npairs + e].y = wide ? (uint32_t)(e0 * p.KX * nc) : (uint32_t)((tx * p.E_tx + e0) * nc * 16) >> 4;
             }
-          return nullptr;
+          return true;
         }
       }
     }
-  }
-  return "does not fit in shared memory";
+    return false;
+  };
+  // Two candidates: the best configuration that leaves room for two CTAs per SM, and the best one using the whole SM.
+  // The deep levels' weights force a split of the output channels over CTAs (nsplit) at the small budget, and every
+  // split re-fetches the A operand: tensor-pipe time per output ~ nsplit * (32 + Nc/4) clk per K16 step
+  // (profiles/r01_umma_rate.txt).  Take the whole-SM configuration when it cuts that by more than a quarter.
+  Params p0 = p, p1 = p;
+  bool ok0, ok1;
+  { ok0 = search(0); p0 = p; }
+  { ok1 = search(1); p1 = p; }
+  if (!ok0 && !ok1) return "does not fit in shared memory";
+  auto cost = [](const Params& q) { return (double)q.nsplit * (32.0 + q.Nc / 4.0) * (q.wide ? 0.55 : 1.0); };
+  if (ok0 && (!ok1 || cost(p1) > 0.75 * cost(p0))) p = p0; else p = p1;
+  return nullptr;
 }
 
 }  // namespace tc
