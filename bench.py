@@ -331,6 +331,9 @@ def main_ours(args):
         prof = profiler.KernelProfile()
         with prof:
             for i in range(min(args.steps, 5)):
+                # Park the GPU behind a ~12 ms spin so the host enqueues the whole step before the first kernel runs:
+                # the event pairs then bracket kernel time, not host launch latency (small kernels were inflated 2-10x).
+                torch.cuda._sleep(int(12e-3 * 1.9e9))
                 # eager: per-kernel events need individual launches.  No gradient all-reduce here: only rank 0 profiles
                 # (a collective entered by one rank would dead-lock), and the collective is not one of this library's kernels
                 opt.zero_grad(set_to_none=True)

@@ -13,6 +13,10 @@ import torch
 from . import _lib
 
 
+# entry points that launch the same kernel (the *_bn / *_fin forms only add a fused tail)
+_ALIAS = {"hcu_conv_tc_fwd_bn": "hcu_conv_tc_fwd", "hcu_bn_bwd_stats_fin": "hcu_bn_bwd_stats"}
+
+
 class KernelProfile:
     def __init__(self):
         self.records = []
@@ -32,7 +36,7 @@ class KernelProfile:
         """{kernel name: dict(ms, calls, bytes, flops)} summed over the profiled region."""
         agg = defaultdict(lambda: dict(ms=0.0, calls=0, bytes=0, flops=0))
         for name, note, e0, e1 in self.records:
-            a = agg[name]
+            a = agg[_ALIAS.get(name, name)]
             a["ms"] += e0.elapsed_time(e1)
             a["calls"] += 1
             if note is not None:
@@ -43,7 +47,7 @@ class KernelProfile:
     def by_layer(self):
         agg = defaultdict(lambda: dict(ms=0.0, calls=0, bytes=0, flops=0))
         for name, note, e0, e1 in self.records:
-            key = (name, note[0] if note else None)
+            key = (_ALIAS.get(name, name), note[0] if note else None)
             a = agg[key]
             a["ms"] += e0.elapsed_time(e1)
             a["calls"] += 1
@@ -77,5 +81,6 @@ class KernelProfile:
                 "share_of_kernel_time": top["ms"] / total_ms if total_ms else None,
                 "other_bound_frac": (gbs / hbm if bound == "tensor" else tfs / tf),
                 "kernel_time_shares": shares,
-                "timing": "CUDA events around every C-ABI call on the launching stream, instrumented steps right after "
+                "timing": "CUDA events around every C-ABI call on the launching stream (the caller parks the GPU behind a spin "
+                          "while the host enqueues, so the pairs bracket kernel time); instrumented steps right after "
                           "the timed region (same step, same inputs)"}
