@@ -325,7 +325,7 @@ static const char* configure(const HcuConvDesc* d, Params& p, int& mtc, int& ntc
   // register tile: all n-tiles up to 8 per CTA, m-tiles so that MTC * NTC <= 24
   if (Po == 1) { mtc = 9; ntc = 1; wmg = 1; wpg = 4; }
   else if (Po == 2) { mtc = 9; ntc = 2; wmg = 1; wpg = 4; }
-  else if (Po == 4) { mtc = 6; ntc = 4; wmg = 4; wpg = 2; }
+  else if (Po == 4) { mtc = 3; ntc = 4; wmg = 4; wpg = 2; }  // 48 accumulator registers: two CTAs per SM (6x4 needed 200 registers)
   else { mtc = 3; ntc = 8; wmg = 8; wpg = 1; }
   const int nthreads = 32 * wmg * wpg;
   p.n_mchunk = (p.MTOT + mtc * wmg - 1) / (mtc * wmg);
@@ -413,7 +413,7 @@ static int wgrad_tc_impl(const HcuConvDesc* d, const void* a, const float* a_sca
   p.n_xseg = (p.OX + p.Lx - 1) / p.Lx;
   if (mtc == 9 && ntc == 1) return wg::launch<9, 1, 1, 4>(p, st);
   if (mtc == 9 && ntc == 2) return wg::launch<9, 2, 1, 4>(p, st);
-  if (mtc == 6 && ntc == 4) return wg::launch<6, 4, 4, 2>(p, st);
+  if (mtc == 3 && ntc == 4) return wg::launch<3, 4, 4, 2>(p, st);
   return wg::launch<3, 8, 8, 1>(p, st);
 }
 
