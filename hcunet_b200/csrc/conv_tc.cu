@@ -299,8 +299,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
                  bar_tempty = bar_tfull + 32, bar_w = bar_tempty + 32;
   const int NB = p.wide ? 4 : 2;  // accumulator slots an output plane rotates through
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (2 * p.R + 9));
-  float* sstat = reinterpret_cast<float*>(smem + p.off_stat);  // [2][Nc]
-  float* sbias = sstat + 2 * p.Nc;                             // [3][Nc]: bias, out_scale, out_shift of this column chunk
+  // per-channel sum / sum of squares, one slot PER EPILOGUE WARP: every slot has a single writer and the four are added
+  // in a fixed order, so the statistics (hence the whole forward) do not depend on the order warps happen to run in
+  float* sstat = reinterpret_cast<float*>(smem + p.off_stat);  // [4 warps][2][Nc]
+  float* sbias = sstat + 8 * p.Nc;                             // [3][Nc]: bias, out_scale, out_shift of this column chunk
   const uint32_t a_base = smem_u32(smem + p.off_a), w_base = smem_u32(smem + p.off_w);
   const int R = p.R, MB = p.MB, Nc = p.Nc;
 
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       for (uint32_t o = 0; o < wbytes; o += 32768u) bulk_g2s(w_base + o, src + o, min(32768u, wbytes - o), bar_w);
     }
   }
-  for (int i = threadIdx.x; i < 2 * Nc; i += kThreads) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < 8 * Nc; i += kThreads) sstat[i] = 0.f;
   for (int i = threadIdx.x; i < Nc; i += kThreads) {
     const int ch = (blockIdx.x % p.nsplit) * Nc + i;  // ns
     const bool in = ch < p.cout;
@@ -699,8 +701,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         const float r1 = reduce8(t1, lane);
         const float r2 = reduce8(t2, lane);
         if ((lane & 3) == 0) {
-          atomicAdd(&sstat[lane >> 2], r1);
-          atomicAdd(&sstat[Nc + (lane >> 2)], r2);
+          sstat[warp * 2 * Nc + (lane >> 2)] = r1;
+          sstat[warp * 2 * Nc + Nc + (lane >> 2)] = r2;
         }
       }
     } else if (p.epi_fast) {
@@ -746,8 +748,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
               const float r1 = reduce16(s1, lane);
               const float r2 = reduce16(s2, lane);
               if ((lane & 1) == 0) {
-                atomicAdd(&sstat[cc + (lane >> 1)], r1);
-                atomicAdd(&sstat[Nc + cc + (lane >> 1)], r2);
+                sstat[warp * 2 * Nc + cc + (lane >> 1)] += r1;   // this lane is the slot's only writer
+                sstat[warp * 2 * Nc + Nc + cc + (lane >> 1)] += r2;
               }
             }
             if (valid) {
@@ -781,8 +783,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         const float r1 = reduce16(t1, lane);
         const float r2 = reduce16(t2, lane);
         if ((lane & 1) == 0) {
-          atomicAdd(&sstat[lane >> 1], r1);
-          atomicAdd(&sstat[Nc + (lane >> 1)], r2);
+          sstat[warp * 2 * Nc + (lane >> 1)] = r1;
+          sstat[warp * 2 * Nc + Nc + (lane >> 1)] = r2;
         }
       }
     } else {
@@ -814,8 +816,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
               const float r1 = reduce16(s1, lane);
               const float r2 = reduce16(s2, lane);
               if ((lane & 1) == 0) {
-                atomicAdd(&sstat[cc + (lane >> 1)], r1);
-                atomicAdd(&sstat[Nc + cc + (lane >> 1)], r2);
+                sstat[warp * 2 * Nc + cc + (lane >> 1)] += r1;   // this lane is the slot's only writer
+                sstat[warp * 2 * Nc + Nc + cc + (lane >> 1)] += r2;
               }
             }
             if (valid) {
@@ -870,8 +872,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         const int ch = ns * Nc + c;
         if (ch < cout) {
           double* sb = p.stats + (size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * p.stats_pitch;
-          atomicAdd(&sb[p.out_c_off + ch], (double)sstat[c]);
-          atomicAdd(&sb[p.stats_pitch + p.out_c_off + ch], (double)sstat[Nc + c]);
+          const float q1 = ((sstat[c] + sstat[2 * Nc + c]) + sstat[4 * Nc + c]) + sstat[6 * Nc + c];
+          const float q2 = ((sstat[Nc + c] + sstat[3 * Nc + c]) + sstat[5 * Nc + c]) + sstat[7 * Nc + c];
+          atomicAdd(&sb[p.out_c_off + ch], (double)q1);
+          atomicAdd(&sb[p.stats_pitch + p.out_c_off + ch], (double)q2);
         }
       }
     }
@@ -1136,7 +1140,7 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
           const int off_a = round_up(wbytes, 128);
           const int off_bar = off_a + R * slot;
           const int off_stat = round_up(off_bar + 8 * (2 * R + 9) + 8, 16);
-          const int total = off_stat + 5 * nc * 4 + 128;
+          const int total = off_stat + 11 * nc * 4 + 128;
           if (total > budget) continue;
           p.M = M; p.MB = MB; p.RUN = run; p.PS = ps; p.SLOT = slot; p.R = R; p.wide = wide ? 1 : 0;
           p.D = want[sweep] >= 4 ? 2 : (want[sweep] >= 2 ? 1 : 0);

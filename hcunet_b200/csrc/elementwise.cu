@@ -484,8 +484,9 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_stats_h8_kernel(const __half* _
                                                              const float* __restrict__ invstd, int relu,
                                                              const uint8_t* __restrict__ argmax, PoolGeom pg,
                                                              double* __restrict__ sums, HcuBnBwdFin fin) {
-  extern __shared__ float sh[];  // [2][c]
-  for (int i = threadIdx.x; i < 2 * c; i += blockDim.x) sh[i] = 0.f;
+  // [8 warps][2][c]: one slot per warp (single writer), added in a fixed order -> run-to-run reproducible sums
+  extern __shared__ float sh[];
+  for (int i = threadIdx.x; i < 16 * c; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
   const int c8 = c >> 3, lc8 = __ffs(c8) - 1;  // c8 is a power of two (c8 | 256)
   const uint32_t total = (uint32_t)(npix * c8), stride = gridDim.x * blockDim.x;  // stride % c8 == 0
@@ -538,17 +539,21 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_stats_h8_kernel(const __half* _
       s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
     }
   }
-  if ((threadIdx.x & 31) < c8 || c8 > 16) {
+  if ((threadIdx.x & 31) < c8 || c8 > 16) {  // after the butterfly: one lane per channel group in this warp
+    float* sw = sh + (threadIdx.x >> 5) * 2 * c;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[cg * 8 + j], s1[j]);
-      atomicAdd(&sh[c + cg * 8 + j], s2[j]);
+      sw[cg * 8 + j] = s1[j];
+      sw[c + cg * 8 + j] = s2[j];
     }
   }
   __syncthreads();
   double* sb = sums + (size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * c;
   for (int i = threadIdx.x; i < c; i += blockDim.x) {
-    const double sg = (double)sh[i], sgy = (double)sh[c + i];
+    float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { q1 += sh[w * 2 * c + i]; q2 += sh[w * 2 * c + c + i]; }
+    const double sg = (double)q1, sgy = (double)q2;
     atomicAdd(&sb[i], sg);
     atomicAdd(&sb[c + i], (double)invstd[i] * (sgy - (double)mean[i] * sg));
   }
@@ -1013,7 +1018,7 @@ static int bn_bwd_stats_impl(const void* da, int32_t dtype_da, const void* y, in
                              double* sums, const HcuBnBwdFin* fin, void* stream) {
   HCU_CHECK_ARG(da && y && scale && shift && mean && invstd && sums && npix > 0 && c > 0, "bn_bwd_stats: bad args");
   HCU_CHECK_ARG(c <= 4096, "bn_bwd_stats: too many channels");
-  if (dtype_da == HCU_F16 && dtype_y == HCU_F16 && c % 8 == 0 && c <= 2048 && 256 % (c / 8) == 0 && aligned16(da) && aligned16(y) &&
+  if (dtype_da == HCU_F16 && dtype_y == HCU_F16 && c % 8 == 0 && c <= 512 && 256 % (c / 8) == 0 && aligned16(da) && aligned16(y) &&
       npix * (c / 8) < 0x7fffffffLL && (argmax == nullptr || (((uintptr_t)argmax) & 7) == 0)) {
     PoolGeom pg = {};
     if (argmax != nullptr) { int rc = fill_pool(pool, npix, pg, "bn_bwd_stats"); if (rc) return rc; }
@@ -1021,7 +1026,7 @@ static int bn_bwd_stats_impl(const void* da, int32_t dtype_da, const void* y, in
     memset(&f, 0, sizeof(f));
     if (fin != nullptr) f = *fin;
     const int grid = grid_for(npix * (c / 8), 256 * 4, 12);
-    bn_bwd_stats_h8_kernel<<<grid, 256, 2 * c * sizeof(float), (cudaStream_t)stream>>>(
+    bn_bwd_stats_h8_kernel<<<grid, 256, 16 * c * sizeof(float), (cudaStream_t)stream>>>(
         (const __half*)da, (const __half*)y, npix, c, scale, shift, mean, invstd, relu, argmax, pg, sums, f);
     HCU_CHECK_LAUNCH("bn_bwd_stats_h8");
     return 0;
