@@ -396,7 +396,7 @@ def main_ours(args):
         dist.barrier()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            cb = run_cpu(2, 1, Z)
+            cb = run_cpu(12, 2, Z)   # bounded sample: ~4 s of CPU work on the box's cores
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         else:
             line["cpu_baseline"] = None
