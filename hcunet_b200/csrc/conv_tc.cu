@@ -75,6 +75,12 @@ struct Params {
   //                   y = byte offset of the B tile inside the packed weights >> 4
   uint2 tab[kMaxTab];
   int debug;  // HCU_TC_DEBUG bits (profiling experiments only): 1 no global loads, 2 no epilogue math/stores, 4 no MMAs
+  // ---- K-streamed kernel (conv_ks_kernel, the channel-rich levels) ----
+  int ks;        // this descriptor runs on conv_ks_kernel
+  int PC, NCH;   // channel planes per A stage / B tile, chunks = P / PC
+  int RA, RB;    // ring depths of the A stages and the B tiles
+  int BT;        // bytes of one B tile = PC * Nc * 16
+  int n_last;    // flat positions of one x-plane that hold outputs (all images stacked: rows = N * Yv)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -288,6 +294,58 @@ __device__ __forceinline__ uint4 bn_relu8(uint4 v, const BnH8& b, int relu) {
   }
   return v;
 }
+
+// Per-channel statistics of a CTA (one slot per epilogue warp, added in a fixed order) -> the caller's binned fp64
+// accumulators, then the optional fused hcu_bn_finalize: the CTA that takes the last ticket sees every CTA's partial sums.
+// Called by the 128 epilogue threads (row = threadIdx.x < 128).
+template <typename PT>
+__device__ __forceinline__ void stats_tail(const PT& p, float* sstat, int row, int ns, int Nc) {
+  const int cout = p.cout;
+  named_bar_sync(1, 128);
+  for (int c = row; c < Nc; c += 128) {
+    const int ch = ns * Nc + c;
+    if (ch < cout) {
+      double* sb = p.stats + (size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * p.stats_pitch;
+      const float q1 = ((sstat[c] + sstat[2 * Nc + c]) + sstat[4 * Nc + c]) + sstat[6 * Nc + c];
+      const float q2 = ((sstat[Nc + c] + sstat[3 * Nc + c]) + sstat[5 * Nc + c]) + sstat[7 * Nc + c];
+      atomicAdd(&sb[p.out_c_off + ch], (double)q1);
+      atomicAdd(&sb[p.stats_pitch + p.out_c_off + ch], (double)q2);
+    }
+  }
+  if (p.fin.counter != nullptr) {
+    __threadfence();
+    named_bar_sync(1, 128);
+    if (row == 0) sstat[0] = (atomicAdd(p.fin.counter, 1u) == gridDim.x - 1) ? 1.f : 0.f;
+    named_bar_sync(1, 128);
+    if (sstat[0] != 0.f) {
+      __threadfence();
+      const int pitch = p.stats_pitch;
+      for (int ch = row; ch < cout; ch += 128) {
+        double s1 = 0.0, s2 = 0.0;
+        for (int b = 0; b < HCU_STAT_BINS; ++b) {
+          s1 += __ldcg(&p.stats[(size_t)b * 2 * pitch + p.out_c_off + ch]);
+          s2 += __ldcg(&p.stats[(size_t)b * 2 * pitch + pitch + p.out_c_off + ch]);
+        }
+        const double mu = s1 / p.fin.count;
+        double var = s2 / p.fin.count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float is = (float)(1.0 / sqrt(var + (double)p.fin.eps));
+        const float muf = (float)mu;
+        p.fin.mean[ch] = muf;
+        p.fin.invstd[ch] = is;
+        const float sc = p.fin.gamma[ch] * is;
+        p.fin.scale[ch] = sc;
+        p.fin.shift[ch] = p.fin.beta[ch] - muf * sc;
+        if (p.fin.running_mean != nullptr) {
+          const double unbiased = p.fin.count > 1.0 ? var * p.fin.count / (p.fin.count - 1.0) : var;
+          p.fin.running_mean[ch] = (1.f - p.fin.momentum) * p.fin.running_mean[ch] + p.fin.momentum * muf;
+          p.fin.running_var[ch] = (1.f - p.fin.momentum) * p.fin.running_var[ch] + p.fin.momentum * (float)unbiased;
+        }
+      }
+    }
+  }
+}
+
 
 __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -866,52 +924,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       }
     }
     PROF_REPORT("epilogue", "wait_tfull", "-", nout);
-    if (do_stats) {
-      named_bar_sync(1, 128);
-      for (int c = row; c < Nc; c += 128) {
-        const int ch = ns * Nc + c;
-        if (ch < cout) {
-          double* sb = p.stats + (size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * p.stats_pitch;
-          const float q1 = ((sstat[c] + sstat[2 * Nc + c]) + sstat[4 * Nc + c]) + sstat[6 * Nc + c];
-          const float q2 = ((sstat[Nc + c] + sstat[3 * Nc + c]) + sstat[5 * Nc + c]) + sstat[7 * Nc + c];
-          atomicAdd(&sb[p.out_c_off + ch], (double)q1);
-          atomicAdd(&sb[p.stats_pitch + p.out_c_off + ch], (double)q2);
-        }
-      }
-    }
-    if (do_stats && p.fin.counter != nullptr) {
-      // fused hcu_bn_finalize: the CTA that takes the last ticket sees every CTA's partial sums
-      __threadfence();
-      named_bar_sync(1, 128);
-      if (row == 0) sstat[0] = (atomicAdd(p.fin.counter, 1u) == gridDim.x - 1) ? 1.f : 0.f;
-      named_bar_sync(1, 128);
-      if (sstat[0] != 0.f) {
-        __threadfence();
-        const int pitch = p.stats_pitch;
-        for (int ch = row; ch < cout; ch += 128) {
-          double s1 = 0.0, s2 = 0.0;
-          for (int b = 0; b < HCU_STAT_BINS; ++b) {
-            s1 += __ldcg(&p.stats[(size_t)b * 2 * pitch + p.out_c_off + ch]);
-            s2 += __ldcg(&p.stats[(size_t)b * 2 * pitch + pitch + p.out_c_off + ch]);
-          }
-          const double mu = s1 / p.fin.count;
-          double var = s2 / p.fin.count - mu * mu;
-          if (var < 0.0) var = 0.0;
-          const float is = (float)(1.0 / sqrt(var + (double)p.fin.eps));
-          const float muf = (float)mu;
-          p.fin.mean[ch] = muf;
-          p.fin.invstd[ch] = is;
-          const float sc = p.fin.gamma[ch] * is;
-          p.fin.scale[ch] = sc;
-          p.fin.shift[ch] = p.fin.beta[ch] - muf * sc;
-          if (p.fin.running_mean != nullptr) {
-            const double unbiased = p.fin.count > 1.0 ? var * p.fin.count / (p.fin.count - 1.0) : var;
-            p.fin.running_mean[ch] = (1.f - p.fin.momentum) * p.fin.running_mean[ch] + p.fin.momentum * muf;
-            p.fin.running_var[ch] = (1.f - p.fin.momentum) * p.fin.running_var[ch] + p.fin.momentum * (float)unbiased;
-          }
-        }
-      }
-    }
+    if (do_stats) stats_tail(p, sstat, row, ns, Nc);
   }
 
 
@@ -923,6 +936,292 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
+
+// ===================================================================================================
+// K-streamed variant for the CHANNEL-RICH levels (>= 64 input channels: the classic 2D U-Net's 64..1024-channel
+// layers, the bottom of the 3D model).  conv_tc_kernel keeps ALL weights of its column chunk in shared memory beside
+// the ring of x-planes; with >= 256 input channels neither the weights nor one x-plane of all channels fit.  Here the
+// GEMM's K dimension is streamed instead: a CTA owns a tile of M = MB * 128 flat output positions of ONE output
+// x-plane (the planes of all images of the batch are stacked into one flat index: rows = N * Yv, so tiny planes still
+// fill the M = 128 rows of an MMA) and Nc output channels, with the fp32 accumulators resident in TMEM for the whole
+// K loop.  K is walked as (tx, channel chunk of PC 8-channel planes, (ty, tz)):
+//   A stage  = the flat run [q0, q0 + M + halo) of input plane ox + tx*dx, PC channel planes, staged ONCE per (tx, chunk)
+//              by the producer warps (cp.async with zero fill, previous layer's BatchNorm + ReLU applied in place) in
+//              the same no-swizzle K-major core-matrix layout [plane of 8 ch][pixel][8]: the KY*KZ taps are descriptor
+//              start-address shifts of that one buffer ("flat shift", as in conv_tc_kernel);
+//   B tile   = weights of (tx, ty, tz, chunk): PC * Nc * 16 contiguous bytes of the SAME packed layout
+//              [nsplit][tx][K8 slab = tap * P + plane][Nc][8] conv_tc_kernel uses, fetched by one cp.async.bulk each
+//              into a ring by a dedicated loader warp.
+// Per (A stage, tap): PC / 2 K16 steps x MB tcgen05.mma.  The epilogue runs once per CTA.
+// Roles (320 threads): warps 0-3 epilogue, 4-7 A producers, warp 8 TMEM + MMA issue, warp 9 B-tile loader.
+// ===================================================================================================
+constexpr int kKsThreads = 320;
+
+__global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int RA = p.RA, RB = p.RB, MB = p.MB, Nc = p.Nc, PC = p.PC;
+  const int KYZ = p.KY * p.KZ;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  // barrier map: full_a[RA], empty_a[RA], full_b[RB], empty_b[RB], tfull
+  const uint32_t bar_fa = smem_u32(bars), bar_ea = bar_fa + 8 * RA, bar_fb = bar_ea + 8 * RA, bar_eb = bar_fb + 8 * RB,
+                 bar_t = bar_eb + 8 * RB;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (2 * RA + 2 * RB + 1));
+  float* sstat = reinterpret_cast<float*>(smem + p.off_stat);  // [4 warps][2][Nc]
+  float* sbias = sstat + 8 * Nc;                               // [3][Nc]
+  int* soff = reinterpret_cast<int*>(smem + p.off_tab);        // [RUN]: element offset of a staged pixel, -1 = zero fill
+  const uint32_t a_base = smem_u32(smem + p.off_a), b_base = smem_u32(smem + p.off_w);
+
+  // ---- work item: (output x-plane, run of M flat positions over the stacked images, column chunk) ----
+  int item = blockIdx.x;
+  const int ns = item % p.nsplit; item /= p.nsplit;
+  const int run = item % p.n_runs;
+  const int ox = item / p.n_runs;
+  const int q0 = run * p.M;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      for (int i = 0; i < RA; ++i) { mbar_init(bar_fa + 8 * i, 4); mbar_init(bar_ea + 8 * i, 1); }
+      for (int i = 0; i < RB; ++i) { mbar_init(bar_fb + 8 * i, 1); mbar_init(bar_eb + 8 * i, 1); }
+      mbar_init(bar_t, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  }
+  for (int i = threadIdx.x; i < 8 * Nc; i += kKsThreads) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < Nc; i += kKsThreads) {
+    const int ch = ns * Nc + i;
+    const bool in = ch < p.cout;
+    sbias[i] = (in && p.bias != nullptr) ? p.bias[ch % p.cpp] : 0.f;
+    sbias[Nc + i] = (in && p.out_scale != nullptr) ? p.out_scale[ch] : 1.f;
+    sbias[2 * Nc + i] = (in && p.out_shift != nullptr) ? p.out_shift[ch] : 0.f;
+  }
+  for (int i = threadIdx.x; i < p.RUN; i += kKsThreads) {
+    const int v = q0 + i;
+    const int r = v / p.Zv, vz = v - r * p.Zv;
+    const int nn = r / p.Yv, vy = r - nn * p.Yv;
+    const int iy = vy - p.py, iz = vz - p.pz;
+    const bool ok = nn < p.N && iy >= 0 && iy < p.IY && iz >= 0 && iz < p.IZ;
+    soff[i] = ok ? (int)(nn * p.in_ns) + iy * p.in_ys + iz * p.in_zs : -1;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // =========================================== A PRODUCERS =========================================
+    const int ptid = threadIdx.x - 128;
+    const int pl = ptid % PC, pix0 = ptid / PC, pstep = 128 / PC;
+    const bool xf = p.in_scale != nullptr;
+    const int relu = p.in_relu;
+    const uint32_t sstep = (uint32_t)pstep * 16u;
+    const int nstage = p.KX * p.NCH;
+    int slot_i = 0, slot_f = 0;
+    uint32_t par = 1;
+    auto finish = [&](int st) {  // stage st has landed: transform in place, publish
+      const int tx = st / p.NCH, c = st - tx * p.NCH;
+      const int xm = ox + tx * p.dx - p.px;
+      if (xf && xm >= 0 && xm < p.IX) {
+        BnH8 bn;
+        bn_h8_setup(bn, p.in_scale + (c * PC + pl) * 8, p.in_shift + (c * PC + pl) * 8);
+        unsigned char* dp = smem + p.off_a + slot_f * p.SLOT + pl * p.PS + pix0 * 16;
+        for (int i = pix0; i < p.RUN; i += pstep, dp += sstep) {
+          if (soff[i] >= 0) {
+            uint4* q = reinterpret_cast<uint4*>(dp);
+            *q = bn_relu8(*q, bn, relu);
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_fa + 8 * slot_f);
+      if (++slot_f == RA) slot_f = 0;
+    };
+    for (int st = 0; st < nstage; ++st) {
+      const int tx = st / p.NCH, c = st - tx * p.NCH;
+      mbar_wait(bar_ea + 8 * slot_i, par);
+      const int xm = ox + tx * p.dx - p.px;
+      const bool xok = xm >= 0 && xm < p.IX;
+      const __half* src = p.in + (size_t)(xok ? xm : 0) * (size_t)p.in_xs + (c * PC + pl) * 8;
+      uint32_t dst = a_base + (uint32_t)(slot_i * p.SLOT + pl * p.PS + pix0 * 16);
+      for (int i = pix0; i < p.RUN; i += pstep, dst += sstep) {
+        const int o = soff[i];
+        const bool ok = xok && o >= 0;
+        cp_async16(dst, ok ? src + o : p.in, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (++slot_i == RA) { slot_i = 0; par ^= 1; }
+      if (st >= 1) {  // one stage in flight behind the one just issued
+        cp_async_wait<1>();
+        finish(st - 1);
+      }
+    }
+    cp_async_wait<0>();
+    finish(nstage - 1);
+  } else if (warp == 8) {
+    // =========================================== MMA ISSUER ==========================================
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(Nc >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
+    const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1
+    const uint32_t lbo_a = ((uint32_t)p.PS >> 4) << 16;                    // next K8 slab = next channel plane
+    const uint32_t lbo_b = (((uint32_t)(Nc * 16)) >> 4) << 16;
+    const uint32_t kstep_a = 2u * ((uint32_t)p.PS >> 4), kstep_b = 2u * (uint32_t)Nc;
+    int sa = 0, sb = 0;
+    uint32_t pa = 0, pb = 0;
+    uint32_t acc = 0;
+    const int nstage = p.KX * p.NCH;
+    for (int st = 0; st < nstage; ++st) {
+      mbar_wait(bar_fa + 8 * sa, pa);
+      tc_fence_after();
+      const uint32_t abase = (a_base + (uint32_t)(sa * p.SLOT)) >> 4;
+      int ty = 0, tz = 0;
+      for (int t = 0; t < KYZ; ++t) {
+        mbar_wait(bar_fb + 8 * sb, pb);
+        tc_fence_after();
+        const uint32_t bbase = (b_base + (uint32_t)(sb * p.BT)) >> 4;
+        const uint32_t tap = (uint32_t)(ty * p.dy * p.Zv + tz * p.dz);  // pixels == 16-byte units
+        for (int k = 0; k < PC / 2; ++k) {
+          const uint64_t ad = desc_hi | (uint64_t)((abase + tap + (uint32_t)k * kstep_a) | lbo_a);
+          const uint64_t bd = desc_hi | (uint64_t)((bbase + (uint32_t)k * kstep_b) | lbo_b);
+          if (elect_one()) {
+            umma_f16(tmem_base, ad, bd, idesc, acc);
+            if (MB > 1) umma_f16(tmem_base + (uint32_t)Nc, ad + 128u, bd, idesc, acc);
+            if (MB > 2) umma_f16(tmem_base + (uint32_t)(2 * Nc), ad + 256u, bd, idesc, acc);
+            if (MB > 3) umma_f16(tmem_base + (uint32_t)(3 * Nc), ad + 384u, bd, idesc, acc);
+          }
+          __syncwarp();
+          acc = 1u;
+        }
+        if (elect_one()) umma_commit(bar_eb + 8 * sb);  // this B tile is consumed
+        __syncwarp();
+        if (++sb == RB) { sb = 0; pb ^= 1; }
+        if (++tz == p.KZ) { tz = 0; ++ty; }
+      }
+      if (elect_one()) umma_commit(bar_ea + 8 * sa);    // this A stage is consumed
+      __syncwarp();
+      if (++sa == RA) { sa = 0; pa ^= 1; }
+    }
+    if (elect_one()) umma_commit(bar_t);
+    __syncwarp();
+  } else if (warp == 9) {
+    // =========================================== B LOADER ============================================
+    if (lane == 0) {
+      const unsigned char* wsrc = reinterpret_cast<const unsigned char*>(p.wp) + (size_t)ns * p.E * Nc * 16;
+      const uint32_t bt = (uint32_t)p.BT;
+      int sb = 0;
+      uint32_t pb = 1;
+      for (int tx = 0; tx < p.KX; ++tx)
+        for (int c = 0; c < p.NCH; ++c)
+          for (int t = 0; t < KYZ; ++t) {
+            mbar_wait(bar_eb + 8 * sb, pb);
+            mbar_expect_tx(bar_fb + 8 * sb, bt);
+            bulk_g2s(b_base + (uint32_t)sb * bt, wsrc + ((size_t)(tx * p.E_tx + t * p.P + c * PC)) * Nc * 16, bt, bar_fb + 8 * sb);
+            if (++sb == RB) { sb = 0; pb ^= 1; }
+          }
+    }
+  } else {
+    // =========================================== EPILOGUE ============================================
+    const int row = threadIdx.x;  // accumulator row within an M-block == TMEM lane
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const bool do_stats = p.stats != nullptr;
+    const bool affine = p.out_scale != nullptr;
+    const bool has_bias = p.bias != nullptr;
+    const int out_relu = p.out_relu, cout = p.cout;
+    const int nch = min(Nc, cout - ns * Nc);
+    const bool phased = p.ops[0] * p.ops[1] * p.ops[2] > 1;
+    long long poff[4];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb) {
+      const int q = q0 + mb * 128 + row;
+      const int r = q / p.Zv, oz = q - r * p.Zv;
+      const int nn = r / p.Yv, oy = r - nn * p.Yv;
+      poff[mb] = (mb < MB && nn < p.N && oy < p.OY && oz < p.OZ) ? nn * p.out_sn + oy * p.out_sy + oz * p.out_sz : -1;
+    }
+    __half* obase = reinterpret_cast<__half*>(p.out) + p.out_base + (long long)ox * p.out_sx + p.out_c_off;
+    mbar_wait(bar_t, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int mb = 0; mb < MB; ++mb) {
+      const bool valid = poff[mb] >= 0;
+#pragma unroll 1
+      for (int cc = 0; cc < nch; cc += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + lane_base + (uint32_t)(mb * Nc + cc), v);
+        if (has_bias) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(&sbias[cc + j]);
+            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+          }
+        }
+        if (do_stats) {
+          float s1[16], s2[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            s1[j] = valid ? v[j] : 0.f;
+            s2[j] = s1[j] * s1[j];
+          }
+          const float r1 = reduce16(s1, lane);
+          const float r2 = reduce16(s2, lane);
+          if ((lane & 1) == 0) {
+            sstat[warp * 2 * Nc + cc + (lane >> 1)] += r1;   // this lane is the slot's only writer
+            sstat[warp * 2 * Nc + Nc + cc + (lane >> 1)] += r2;
+          }
+        }
+        if (valid) {
+          if (affine) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 a = *reinterpret_cast<const float4*>(&sbias[Nc + cc + j]);
+              const float4 b = *reinterpret_cast<const float4*>(&sbias[2 * Nc + cc + j]);
+              v[j] = fmaf(v[j], a.x, b.x); v[j + 1] = fmaf(v[j + 1], a.y, b.y);
+              v[j + 2] = fmaf(v[j + 2], a.z, b.z); v[j + 3] = fmaf(v[j + 3], a.w, b.w);
+            }
+          }
+          if (out_relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          __half2 h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+          if (phased) {
+            // each 8-channel half of the chunk belongs to one stride phase: its own spatial offset
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int ch = ns * Nc + cc + 8 * hh;
+              if (ch < cout) {
+                int phi = ch / p.cpp;
+                const int co = ch - phi * p.cpp;
+                const int fz = phi % p.ops[2]; phi /= p.ops[2];
+                const int fy = phi % p.ops[1], fx = phi / p.ops[1];
+                __half* o = obase + poff[mb] + fx * p.out_ph[0] + fy * p.out_ph[1] + fz * p.out_ph[2] + co;
+                *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(&h[4 * hh]);
+              }
+            }
+          } else {
+            __half* o = obase + poff[mb] + ns * Nc + cc;
+            *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(&h[0]);
+            if (cc + 8 < nch) *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<uint4*>(&h[4]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    if (do_stats) stats_tail(p, sstat, row, ns, Nc);
+  }
+
+  // ---- teardown --------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
 
 // weights: fp32 [taps][cin][cout] (hcu_weight_gather layout, one group) -> fp16 [nsplit][E][Nc][8]
 // packed weight layouts: normal [nsplit][tx][K8 slab e][Nc][8]; wide (x-fused MMAs) [nsplit][e][KX-1-tx][Nc][8]
@@ -1038,7 +1337,8 @@ __global__ void __launch_bounds__(256) pack_tc_batch_kernel(const unsigned char*
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // returns 0 and fills p (geometry part) when the TC kernel takes this descriptor, else a reason string
-static const char* configure(const HcuConvDesc* d, Params& p) {
+static const char* configure_classic(const HcuConvDesc* d, Params& p) {
+  p.ks = 0;
   if (d->dtype_in != HCU_F16) return "input must be fp16";
   if (d->dtype_out != HCU_F16 && d->dtype_out != HCU_F32) return "output must be fp16 or fp32";
   if (d->groups != 1) return "groups != 1";
@@ -1187,6 +1487,160 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   return nullptr;
 }
 
+// ---- K-streamed kernel: geometry, tile search --------------------------------------------------------------------
+// Work per CTA: (output x-plane, run of M = MB * 128 flat positions over the stacked images, Nc output channels).  The
+// search minimises waves * max(tensor time, L2 streaming time) + fixed cost over (M, Nc, PC) under the shared-memory and
+// TMEM budgets.  A 2D problem (Z == 1) is re-read as ONE x-plane of Y x Z = image rows x columns, so that the filter
+// rows are flat shifts as well (a 2D image row as an "x-plane" would leave an MMA's 128 rows mostly empty on the deep
+// levels: 28 pixels wide at the bottom of the classic U-Net).
+static bool ks_flat2d(const HcuConvDesc* d) {
+  return d->in_size[2] == 1 && d->out_size[2] == 1 && d->taps[2] == 1 && d->pad[2] == 0;
+}
+
+static const char* configure_ks(const HcuConvDesc* d, Params& p) {
+  p.ks = 1;
+  if (d->dtype_in != HCU_F16 || d->dtype_out != HCU_F16) return "fp16 in and out";
+  if (d->groups != 1) return "groups != 1";
+  if (d->in_cpitch % 32 != 0 || d->in_c_off != 0 || d->cin != d->in_cpitch) return "input channels: dense multiple of 32";
+  if (d->cin < 64) return "fewer than 64 input channels";
+  if (d->iphase) return "iphase";
+  if (d->cout % 8 != 0 || d->out_cpitch % 8 != 0 || d->out_c_off % 8 != 0) return "output channels: multiples of 8";
+  for (int i = 0; i < 3; ++i) {
+    p.ops[i] = std::max(1, (d->ophase >> (8 * i)) & 0xff);
+    p.ips[i] = 1;
+    if (d->istep[i] != 1) return "strided gather";
+  }
+  const int nph_o = p.ops[0] * p.ops[1] * p.ops[2];
+  if (nph_o > 1) {
+    if (d->cout % nph_o || (d->cout / nph_o) % 8) return "ophase needs 8-channel aligned phases";
+    for (int i = 0; i < 3; ++i)
+      if (d->ostep[i] < p.ops[i]) return "ophase larger than the output step";
+  }
+  p.cpp = d->cout / nph_o;
+  const int P = d->in_cpitch / 8;
+  p.P = P; p.Pc = P; p.Cp = d->in_cpitch;
+  p.N = d->batch;
+  p.cout = d->cout;
+  // axis roles: a (march / separate planes), b, c (flat plane).  2D: a is a dummy axis of extent 1.
+  const bool flat2d = ks_flat2d(d);
+  const int A = flat2d ? -1 : 0, B = flat2d ? 0 : 1, Cc = flat2d ? 1 : 2;
+  auto get = [&](const int32_t* v, int ax, int dflt) { return ax < 0 ? dflt : v[ax]; };
+  p.IX = get(d->in_size, A, 1); p.IY = d->in_size[B]; p.IZ = d->in_size[Cc];
+  p.OX = get(d->out_size, A, 1); p.OY = d->out_size[B]; p.OZ = d->out_size[Cc];
+  p.KX = get(d->taps, A, 1); p.KY = d->taps[B]; p.KZ = d->taps[Cc];
+  p.dx = get(d->dil, A, 1); p.dy = d->dil[B]; p.dz = d->dil[Cc];
+  p.px = get(d->pad, A, 0); p.py = d->pad[B]; p.pz = d->pad[Cc];
+  {
+    const long long cz = d->in_cpitch, cy = cz * d->in_size[2], cx = cy * d->in_size[1], cn = cx * d->in_size[0];
+    const long long st[3] = {cx, cy, cz};
+    if (cn * d->batch >= 0x7fffffffLL) return "input tensor too large for 32-bit offsets";
+    p.in_ns = cn;
+    p.in_xs = A < 0 ? 0 : st[A];
+    p.in_ys = (int)st[B];
+    p.in_zs = (int)st[Cc];
+    p.in_ph[0] = p.in_ph[1] = p.in_ph[2] = 0;
+  }
+  p.Yv = p.OY + (p.KY - 1) * p.dy;
+  p.Zv = p.OZ + (p.KZ - 1) * p.dz;
+  const int KYZ = p.KY * p.KZ;
+  if (p.KX > 8 || KYZ > 64) return "too many taps";
+  p.E_tx = KYZ * P;
+  p.npairs = p.E_tx / 2;
+  p.E = p.KX * p.E_tx;
+  p.wide = 0;
+  const int npad = round_up(d->cout, 16);
+  const int halo = (p.KY - 1) * p.dy * p.Zv + (p.KZ - 1) * p.dz;
+  const long long n_last = ((long long)(p.N - 1) * p.Yv + p.OY - 1) * p.Zv + p.OZ;
+  if (n_last + 512 + halo >= 0x7fffffffLL) return "plane too large";
+  p.n_last = (int)n_last;
+  const int sms = 148;
+  double best = 1e300;
+  Params b = p;
+  bool found = false;
+  const int m_cands[3] = {512, 256, 128};
+  // reserved[1] (tests): forced tile, MB | Nc << 8 | PC << 20 (0 fields = free)
+  const int f_mb = d->reserved[1] & 0xf, f_nc = (d->reserved[1] >> 8) & 0xfff, f_pc = (d->reserved[1] >> 20) & 0xf;
+  for (int mi = 0; mi < 3; ++mi) {
+    const int M = m_cands[mi], MB = M / 128;
+    if (f_mb ? MB != f_mb : (M > 128 && M - 128 >= n_last)) continue;
+    const int run = M + halo;
+    for (int nc = std::min(npad, 256); nc >= 16; nc -= 16) {
+      if (npad % nc != 0 || MB * nc > 512) continue;
+      if (f_nc && nc != f_nc) continue;
+      for (int pc = 8; pc >= 4; pc >>= 1) {
+        if (P % pc != 0 || (f_pc && pc != f_pc)) continue;
+        const int bt = pc * nc * 16;
+        if (bt > 32768) continue;
+        int ps = run * 16;
+        { const int g = pc >= 8 ? 16 : 128 / pc; ps = round_up(ps, 2 * g) + g; }
+        if ((ps >> 4) > 0x3fff) continue;
+        const int slot = ps * pc;
+        for (int ra = 3; ra >= 2; --ra) {
+          for (int rb = 6; rb >= 2; rb -= 2) {
+            const int off_w = 0;
+            const int off_a = round_up(rb * bt, 128);
+            const int off_tab = off_a + ra * slot;
+            const int off_bar = round_up(off_tab + run * 4, 8);
+            const int off_stat = round_up(off_bar + 8 * (2 * ra + 2 * rb + 1) + 8, 16);
+            const int total = off_stat + 11 * nc * 4 + 128;
+            if (total > kSmemLimit) continue;
+            const int nch = P / pc;
+            const double mma1 = std::max(32.0 + nc / 4.0, nc / 2.0);
+            const double t_mma = (double)p.KX * nch * KYZ * (pc / 2) * MB * mma1;
+            const double bytes = (double)p.KX * nch * ((double)run * pc * 16 + (double)KYZ * bt);
+            const double t_mem = bytes / 20.0;
+            const double t_cta = std::max(t_mma, t_mem) + 4000.0 + MB * (nc / 16) * 150.0 + (ra < 3 ? 0.05 * t_mma : 0.0) +
+                                 (rb < 4 ? 0.05 * t_mma : 0.0);
+            const long long n_runs = (n_last + M - 1) / M;
+            const long long items = (long long)p.OX * n_runs * (npad / nc);
+            const double cost = (double)((items + sms - 1) / sms) * t_cta;
+            if (cost < best) {
+              best = cost; found = true;
+              b = p;
+              b.M = M; b.MB = MB; b.RUN = run; b.PS = ps; b.SLOT = slot; b.PC = pc; b.NCH = nch; b.RA = ra; b.RB = rb; b.BT = bt;
+              b.R = ra; b.D = 1;
+              b.Nc = nc; b.nsplit = npad / nc;
+              b.off_w = off_w; b.off_a = off_a; b.off_tab = off_tab; b.off_bar = off_bar; b.off_stat = off_stat;
+              b.smem_bytes = total;
+              int t = 32;
+              while (t < MB * nc) t <<= 1;
+              b.tmem_cols = t;
+              b.n_runs = (int)n_runs;
+              b.Lx = 1; b.n_xseg = p.OX;
+            }
+            goto next_pc;  // deepest rings that fit
+          }
+        }
+      next_pc:;
+      }
+    }
+  }
+  if (!found) return "does not fit in shared memory";
+  p = b;
+  return nullptr;
+}
+
+// Which kernel takes a descriptor.  reserved[0] is a hint (tests / experiments): 0 auto, 1 classic only, 2 K-streamed only.
+// Auto: the classic kernel (whole weight slice resident, x-march ring: every input element fetched ~once) unless it cannot
+// take the descriptor or has to split the output channels over CTAs (each split re-stages the A operand).
+static const char* configure(const HcuConvDesc* d, Params& p) {
+  static int ks_mode = -1;
+  if (ks_mode < 0) { const char* e = getenv("HCU_TC_KS"); ks_mode = e ? atoi(e) : 1; }
+  const int hint = d->reserved[0];
+  if (hint == 2) return configure_ks(d, p);
+  Params pc;
+  memset(&pc, 0, sizeof(pc));
+  const char* why_c = configure_classic(d, pc);
+  if (hint == 1 || ks_mode == 0) { p = pc; return why_c; }
+  if (why_c == nullptr && pc.nsplit == 1 && ks_mode != 2) { p = pc; return nullptr; }
+  Params pk;
+  memset(&pk, 0, sizeof(pk));
+  const char* why_k = configure_ks(d, pk);
+  if (why_k == nullptr) { p = pk; return nullptr; }
+  p = pc;
+  return why_c;
+}
+
 }  // namespace tc
 }  // namespace hcu
 
@@ -1196,6 +1650,20 @@ extern "C" int hcu_conv_tc_supported(const HcuConvDesc* d) {
   if (d == nullptr) return 0;
   tc::Params p;
   return tc::configure(d, p) == nullptr ? 1 : 0;
+}
+
+extern "C" int hcu_conv_tc_describe(const HcuConvDesc* d, char* buf, int32_t n) {
+  if (d == nullptr || buf == nullptr || n <= 0) return HCU_ERR_INVALID;
+  tc::Params p;
+  const char* why = tc::configure(d, p);
+  if (why != nullptr) { snprintf(buf, (size_t)n, "unsupported: %s", why); return 0; }
+  if (p.ks)
+    snprintf(buf, (size_t)n, "ks M=%d Nc=%d nsplit=%d PC=%d RA=%d RB=%d runs=%d grid=%lld smem=%d tmem=%d", p.M, p.Nc, p.nsplit, p.PC,
+             p.RA, p.RB, p.n_runs, (long long)p.OX * p.n_runs * p.nsplit, p.smem_bytes, p.tmem_cols);
+  else
+    snprintf(buf, (size_t)n, "classic M=%d Nc=%d nsplit=%d wide=%d R=%d D=%d runs=%d smem=%d tmem=%d", p.M, p.Nc, p.nsplit, p.wide,
+             p.R, p.D, p.n_runs, p.smem_bytes, p.tmem_cols);
+  return 0;
 }
 
 extern "C" long long hcu_conv_tc_packed_bytes(const HcuConvDesc* d) {
@@ -1322,6 +1790,29 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
                d->out_c_off % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   HCU_CHECK_ARG(p.ops[0] * p.ops[1] * p.ops[2] == 1 || stats == nullptr, "conv_tc_fwd: no statistics with ophase");
 
+  if (p.ks) {
+    HCU_CHECK_ARG(d->dtype_out == HCU_F16 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv_tc_fwd: K-streamed kernel needs a 16-byte aligned fp16 output");
+    if (tc::ks_flat2d(d)) {  // (x, y) of the descriptor are the flat plane's (row, column); no march axis
+      p.out_sx = 0; p.out_sy = tx * d->ostep[0]; p.out_sz = ty * d->ostep[1];
+    }
+    static int ks_attr = 0;
+    if (!ks_attr) {
+      cudaError_t e = cudaFuncSetAttribute(tc::conv_ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemLimit);
+      if (e != cudaSuccess) {
+        set_error("conv_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return HCU_ERR_CUDA;
+      }
+      ks_attr = 1;
+    }
+    const long long grid = (long long)p.OX * p.n_runs * p.nsplit;
+    HCU_CHECK_ARG(grid <= 0x7fffffffLL, "conv_tc_fwd: grid too large");
+    if (p.debug & 8)
+      fprintf(stderr, "conv_ks: grid %lld smem %d tmem %d M %d Nc %d PC %d RA %d RB %d runs %d\n", grid, p.smem_bytes, p.tmem_cols, p.M,
+              p.Nc, p.PC, p.RA, p.RB, p.n_runs);
+    tc::conv_ks_kernel<<<(unsigned)grid, tc::kKsThreads, p.smem_bytes, (cudaStream_t)stream>>>(p);
+    HCU_CHECK_LAUNCH("conv_ks");
+    return 0;
+  }
   static int smem_attr = 0;
   if (smem_attr < p.smem_bytes) {
     cudaError_t e = cudaFuncSetAttribute(tc::conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemLimit);

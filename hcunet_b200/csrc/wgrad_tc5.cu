@@ -46,6 +46,7 @@ struct Params {
   int Yv, Zv;
   int M, RUN, PS, SLOT, DPS, DSLOT, R, RD, D;
   int Nc, TG, NG, taps;
+  int n_cb, n_ob;  // channel blocks over CTAs: 128 input channels (16 planes) x Nc output channels each; P / Po = planes per block
   int n_runs, Lx, n_xseg;
   int in_relu, vec4;
   int off_d, off_bar, smem_bytes, tmem_cols;
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
   // ---- work item ---------------------------------------------------------------------------------
   int item = blockIdx.x;
   const int grp = item % p.NG; item /= p.NG;
+  const int cb = item % p.n_cb; item /= p.n_cb;
+  const int ob = item % p.n_ob; item /= p.n_ob;
   const int run = item % p.n_runs; item /= p.n_runs;
   const int xs = item % p.n_xseg;
   const int n = item / p.n_xseg;
@@ -203,12 +206,12 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
     float sc[8], sh[8];
     if (xf) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { sc[j] = p.a_scale[plane * 8 + j]; sh[j] = p.a_shift[plane * 8 + j]; }
+      for (int j = 0; j < 8; ++j) { sc[j] = p.a_scale[(cb * p.P + plane) * 8 + j]; sh[j] = p.a_shift[(cb * p.P + plane) * 8 + j]; }
     }
     const int qf = q0 + pix0;
     const int yv0 = qf / p.Zv, zv0 = qf - yv0 * p.Zv;
     const int ystep = pstep / p.Zv, zstep = pstep - ystep * p.Zv;
-    const __half* a_n = p.a + (size_t)n * p.IX * p.IY * p.IZ * p.Cp + plane * 8;
+    const __half* a_n = p.a + (size_t)n * p.IX * p.IY * p.IZ * p.Cp + (cb * p.P + plane) * 8;
     const size_t a_xs = (size_t)p.IY * p.IZ * p.Cp;
     // dy: [Po planes][M pixels]
     const int dplane = ptid % p.Po, dpix0 = ptid / p.Po, dstep = 128 / p.Po;
@@ -216,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
     const int dqf = q0 + dpix0;
     const int dy0 = dqf / p.Zv, dz0 = dqf - dy0 * p.Zv;
     const int dystep = dstep / p.Zv, dzstep = dstep - dystep * p.Zv;
-    const __half* d_n = p.dy + (size_t)n * p.OX * p.OY * p.OZ * p.Cop + dplane * 8;
+    const __half* d_n = p.dy + (size_t)n * p.OX * p.OY * p.OZ * p.Cop + (ob * p.Po + dplane) * 8;
     const size_t d_xs = (size_t)p.OY * p.OZ * p.Cop;
 
     const int D = p.D;
@@ -340,7 +343,8 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
     }
   } else {
     // =========================================== EPILOGUE ============================================
-    const int ci = threadIdx.x;  // TMEM lane == accumulator row == input channel
+    const int ci = cb * 128 + threadIdx.x;  // TMEM lane == accumulator row == input channel (of this CTA's block)
+    const int co0 = ob * p.Nc;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     mbar_wait(bar_done, 0);
     tc_fence_after();
@@ -349,15 +353,15 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
         float v[16];
         tmem_ld16(tmem_base + lane_base + (uint32_t)((t - t_lo) * p.Nc + cc), v);
         if (ci < p.cin) {
-          float* o = p.wacc + ((size_t)t * p.cin + ci) * p.cout + cc;
+          float* o = p.wacc + ((size_t)t * p.cin + ci) * p.cout + co0 + cc;
           if (p.vec4) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
-              if (cc + j < p.cout) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (co0 + cc + j < p.cout) red_add_v4(o + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (cc + j < p.cout) atomicAdd(o + j, v[j]);
+              if (co0 + cc + j < p.cout) atomicAdd(o + j, v[j]);
           }
         }
       }
@@ -380,24 +384,42 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   if (d->ophase || d->iphase) return "stride phases";
   if (d->in_cpitch % 8 != 0 || d->in_c_off != 0 || d->cin > d->in_cpitch) return "input channel layout";
   if (d->out_cpitch % 8 != 0 || d->out_c_off != 0 || d->cout > d->out_cpitch) return "dy channel layout";
-  const int P = d->in_cpitch / 8, Po = d->out_cpitch / 8;
+  const int Pt = d->in_cpitch / 8, Pot = d->out_cpitch / 8;  // channel planes of the whole tensors
+  // channel blocks: a CTA takes <= 128 input channels (the M = 128 rows of the accumulator) and <= 128 output channels
+  const int P = std::min(Pt, 16), Po = std::min(Pot, 16);
   if (P != 1 && P != 2 && P != 4 && P != 8 && P != 16) return "input channel pitch";
   if (Po != 1 && Po != 2 && Po != 4 && Po != 8 && Po != 16) return "dy channel pitch";
-  if (d->cin > 128 || d->cout > 256) return "more than 128 input / 256 output channels";
+  if (Pt % P != 0 || Pot % Po != 0) return "channel pitch not a whole number of blocks";
+  p.n_cb = Pt / P; p.n_ob = Pot / Po;
+  if ((p.n_cb > 1 && d->cin != d->in_cpitch) || (p.n_ob > 1 && d->cout != d->out_cpitch)) return "channel blocks need dense channels";
   for (int i = 0; i < 3; ++i)
     if (d->istep[i] != 1 || d->ostep[i] != 1 || d->ooff[i] != 0 || d->out_tsize[i] != d->out_size[i]) return "strided";
-  p.N = d->batch; p.IX = d->in_size[0]; p.IY = d->in_size[1]; p.IZ = d->in_size[2];
+  p.N = d->batch;
   p.Cp = d->in_cpitch; p.P = P; p.cin = d->cin;
-  p.OX = d->out_size[0]; p.OY = d->out_size[1]; p.OZ = d->out_size[2];
   p.Cop = d->out_cpitch; p.Po = Po; p.cout = d->cout;
-  p.KX = d->taps[0]; p.KY = d->taps[1]; p.KZ = d->taps[2];
-  p.dx = d->dil[0]; p.dy_ = d->dil[1]; p.dz = d->dil[2];
-  p.px = d->pad[0]; p.py = d->pad[1]; p.pz = d->pad[2];
+  // A 2D problem with short image rows is re-read as ONE x-plane of rows x columns: the filter rows become flat shifts
+  // too, and a run of M positions spans several rows instead of leaving most of an MMA's K = 16-pixel chunks empty
+  // (a 30-pixel row of the classic U-Net's bottom levels fills 12 % of a 256-position run).
+  const bool flat2d = d->in_size[2] == 1 && d->out_size[2] == 1 && d->taps[2] == 1 && d->pad[2] == 0 && d->dil[2] == 1 &&
+                      d->out_size[1] + (d->taps[1] - 1) * d->dil[1] < 192;
+  if (flat2d) {
+    p.IX = 1; p.IY = d->in_size[0]; p.IZ = d->in_size[1];
+    p.OX = 1; p.OY = d->out_size[0]; p.OZ = d->out_size[1];
+    p.KX = 1; p.KY = d->taps[0]; p.KZ = d->taps[1];
+    p.dx = 1; p.dy_ = d->dil[0]; p.dz = d->dil[1];
+    p.px = 0; p.py = d->pad[0]; p.pz = d->pad[1];
+  } else {
+    p.IX = d->in_size[0]; p.IY = d->in_size[1]; p.IZ = d->in_size[2];
+    p.OX = d->out_size[0]; p.OY = d->out_size[1]; p.OZ = d->out_size[2];
+    p.KX = d->taps[0]; p.KY = d->taps[1]; p.KZ = d->taps[2];
+    p.dx = d->dil[0]; p.dy_ = d->dil[1]; p.dz = d->dil[2];
+    p.px = d->pad[0]; p.py = d->pad[1]; p.pz = d->pad[2];
+  }
   p.Yv = p.OY + (p.KY - 1) * p.dy_;
   p.Zv = p.OZ + (p.KZ - 1) * p.dz;
   p.taps = p.KX * p.KY * p.KZ;
   if (p.taps > kMaxTaps) return "too many taps";
-  p.Nc = round_up(d->cout, 16);
+  p.Nc = p.n_ob > 1 ? Po * 8 : round_up(d->cout, 16);
   if (p.Nc > 256) return "too many output channels";
   p.TG = std::min(p.taps, 512 / p.Nc);
   {
@@ -490,7 +512,7 @@ extern "C" int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const
     attr = true;
   }
   // x segmentation: about two waves of CTAs, segments no shorter than 4 planes
-  const long long base_items = (long long)p.N * p.n_runs * p.NG;
+  const long long base_items = (long long)p.N * p.n_runs * p.NG * p.n_cb * p.n_ob;
   const int per_sm = std::max(1, std::min(233472 / (p.smem_bytes + 1024), 512 / p.tmem_cols));
   const long long target = 2LL * per_sm * num_sms();
   int nseg = (int)((target + base_items - 1) / base_items);

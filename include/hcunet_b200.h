@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 14
+#define HCU_ABI_VERSION 15
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -102,7 +102,8 @@ typedef struct HcuConvDesc {
    *          (ConvTranspose data gradient; hcu_conv_wgrad_tc applies it to its `b` = dy side via `ophase`.) */
   int32_t ophase;
   int32_t iphase;
-  int32_t reserved[2];
+  int32_t reserved[2];     /* [0]: tensor-core kernel hint (see hcu_conv_tc_describe); [1]: 0, or a forced
+                            * K-streamed tile for tests: MB | Nc << 8 | PC << 20 */
 } HcuConvDesc;
 
 /* Optional fused tails ("last CTA done" pattern: the CTA that takes the last ticket of `counter` -- a uint32 the caller
@@ -151,6 +152,11 @@ int hcu_conv_fwd(const HcuConvDesc* d, const void* in, const float* W, const flo
  * hcu_conv_tc_packed_bytes(d) bytes of fp16 UMMA core matrices.  Same semantics as hcu_conv_fwd otherwise.
  * Replaces: nn.Conv3d/Conv2d.forward (unet.py:246-257), conv backward-data, ConvTranspose3d phases (unet.py:294). */
 int hcu_conv_tc_supported(const HcuConvDesc* d);
+/* Which kernel and tile configuration a descriptor gets (text, for logs / tests): "classic ..." = conv_tc_kernel (weight
+ * slice resident in shared memory, x-march ring), "ks ..." = conv_ks_kernel (K-streamed, >= 64 input channels: A stages
+ * and weight tiles streamed through shared memory, accumulators resident in TMEM), "unsupported: why".
+ * HcuConvDesc.reserved[0] is a kernel hint: 0 auto, 1 classic only, 2 K-streamed only. */
+int hcu_conv_tc_describe(const HcuConvDesc* d, char* buf, int32_t n);
 long long hcu_conv_tc_packed_bytes(const HcuConvDesc* d);
 int hcu_conv_tc_pack(const HcuConvDesc* d, const float* w, void* packed, void* stream);
 /* same, straight from the reference-layout parameter through a HcuWeightMap (gather + fold + fp16 pack in one launch) */

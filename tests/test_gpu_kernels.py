@@ -37,7 +37,7 @@ def from_cl(y):
 
 
 def run_tc(x, w, *, bias=None, dil=(1, 1, 1), pad=(0, 0, 0), cpitch=None, in_affine=None, in_relu=False,
-           out_affine=None, out_relu=False, want_stats=False, out_f32=False, use_simt=False):
+           out_affine=None, out_relu=False, want_stats=False, out_f32=False, use_simt=False, hint=0, tile=0):
     """x [N,Cin,X,Y,Z] fp32 (fp16-representable), w [Cout,Cin,kx,ky,kz] -> (y [N,Cout,...], stats or None)."""
     from hcunet_b200 import _lib
     from hcunet_b200.engine import conv_desc
@@ -54,6 +54,14 @@ def run_tc(x, w, *, bias=None, dil=(1, 1, 1), pad=(0, 0, 0), cpitch=None, in_aff
     y = torch.full((n,) + osz + (cout,), float("nan"), dtype=odt, device="cuda")
     d = conv_desc(_lib.F16, _lib.F32 if out_f32 else _lib.F16, n, isz, cp, 0, cin, cin, osz, osz, cout, 0, cout, 1, taps,
                   dil, pad=pad, in_relu=int(in_relu), out_relu=int(out_relu))
+    d.reserved[0] = hint   # 0 auto, 1 classic kernel, 2 K-streamed kernel
+    d.reserved[1] = tile   # forced K-streamed tile: MB | Nc << 8 | PC << 20
+    if hint:
+        buf = C.create_string_buffer(256)
+        lib.hcu_conv_tc_describe(C.byref(d), buf, 256)
+        if tile and b"does not fit" in buf.value:
+            pytest.skip("forced tile does not fit in shared memory")
+        assert buf.value.decode().startswith("ks " if hint == 2 else "classic "), buf.value
     wg = w.permute(2, 3, 4, 1, 0).contiguous().float().cuda()  # [taps][cin][cout]
     stats = torch.zeros((_lib.STAT_BINS, 2, cout), dtype=torch.float64, device="cuda") if want_stats else None
     isc = ish = osc = osh = None
@@ -151,6 +159,71 @@ def test_conv_tc_agrees_with_simt_kernel():
     b, sb = run_tc(x, w, want_stats=True, use_simt=True)
     assert rel_l2(a, b) <= 6e-4
     assert torch.allclose(sa, sb, rtol=1e-4, atol=1e-3)
+
+
+# ---- K-streamed tcgen05 kernel (conv_ks_kernel: >= 64 input channels, weights and activations streamed) ----------
+KS_CASES = [
+    # (N, Cin, Cout, in size, kernel, dilation, pad)
+    (1, 64, 64, (5, 12, 28), (3, 3, 2), (1, 1, 1), (0, 0, 0)),      # 3D: x march = separate planes, (y, z) flat
+    (2, 128, 64, (4, 10, 9), (3, 3, 1), (1, 1, 1), (0, 0, 0)),      # two images stacked in one flat run
+    (3, 64, 128, (30, 30, 1), (3, 3, 1), (1, 1, 1), (0, 0, 0)),     # 2D: the whole image is the flat plane
+    (16, 256, 64, (12, 12, 1), (3, 3, 1), (1, 1, 1), (0, 0, 0)),    # 2D bottom level: 16 tiny images in 5 runs
+    (2, 512, 32, (14, 14, 1), (3, 3, 1), (1, 1, 1), (0, 0, 0)),     # 64 channel planes, 16 chunks
+    (1, 64, 272, (9, 20, 1), (3, 3, 1), (1, 1, 1), (0, 0, 0)),      # cout not a multiple of the column chunk: N-split + tail
+    (2, 64, 64, (40, 70, 1), (3, 3, 1), (1, 1, 1), (0, 0, 0)),      # several runs per image
+    (1, 64, 32, (7, 9, 6), (3, 3, 2), (1, 1, 1), (2, 2, 1)),        # zero padding (the data-gradient form), 3D
+    (2, 96, 64, (11, 13, 1), (3, 3, 1), (1, 1, 1), (2, 2, 0)),      # zero padding, 2D, 12 channel planes
+    (1, 64, 64, (14, 13, 6), (3, 3, 2), (2, 2, 1), (0, 0, 0)),      # dilation
+    (2, 128, 256, (6, 6, 1), (1, 1, 1), (1, 1, 1), (0, 0, 0)),      # 1x1 (the transposed convs' GEMM)
+]
+
+
+def ks_tile(mb, nc, pc):
+    return mb | (nc << 8) | (pc << 20)
+
+
+# the tile search picks small tiles for small problems: force the big ones the full-size layers use as well
+KS_TILES = [0, ks_tile(4, 64, 4), ks_tile(2, 32, 8), ks_tile(1, 64, 4), ks_tile(4, 128, 8), ks_tile(2, 256, 4)]
+
+
+@pytest.mark.parametrize("tile", KS_TILES)
+@pytest.mark.parametrize("case", KS_CASES)
+def test_conv_ks_matches_fp32_conv(case, tile):
+    n, cin, cout, isz, k, dil, pad = case
+    if tile and cout % ((tile >> 8) & 0xfff):
+        pytest.skip("column chunk does not divide cout")
+    g = torch.Generator().manual_seed(hash(case) % 10000)
+    x = h16(torch.randn((n, cin) + isz, generator=g))
+    w = h16(torch.randn((cout, cin) + k, generator=g) / (cin * k[0] * k[1] * k[2]) ** 0.5)
+    b = torch.randn(cout, generator=g)
+    ref = F.conv3d(x, w, b, dilation=dil, padding=pad)
+    y, stats = run_tc(x, w, bias=b, dil=dil, pad=pad, want_stats=True, hint=2, tile=tile)
+    assert not torch.isnan(y).any(), "some outputs were never written"
+    assert rel_l2(y, ref) <= 1e-3, rel_l2(y, ref)   # fp16 output rounding only
+    npix = ref.numel() / cout
+    mean = stats[0] / npix
+    var = stats[1] / npix - mean * mean
+    assert torch.allclose(mean.float(), ref.mean(dim=(0, 2, 3, 4)), atol=2e-4, rtol=1e-4)
+    assert torch.allclose(var.float(), ref.var(dim=(0, 2, 3, 4), unbiased=False), atol=2e-4, rtol=1e-3)
+
+
+def test_conv_ks_fused_input_bn_relu_and_output_affine_and_classic_agreement():
+    g = torch.Generator().manual_seed(13)
+    x = h16(torch.randn((2, 64, 9, 10, 7), generator=g))
+    w = h16(torch.randn((64, 64, 3, 3, 2), generator=g) / 34.0)
+    sc, sh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g) * 0.3
+    a = h16(F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)))  # the producer rounds A to fp16
+    osc, osh = torch.rand(64, generator=g) + 0.5, torch.randn(64, generator=g)
+    ref = F.relu(F.conv3d(a, w) * osc.view(1, -1, 1, 1, 1) + osh.view(1, -1, 1, 1, 1))
+    y, _ = run_tc(x, w, in_affine=(sc, sh), in_relu=True, out_affine=(osc, osh), out_relu=True, hint=2)
+    assert rel_l2(y, ref) <= 1e-3, rel_l2(y, ref)
+    # zero padding is applied AFTER the input transform (padding pixels stay zero), and both kernels agree
+    yk, sk = run_tc(x, w, in_affine=(sc, sh), in_relu=True, pad=(2, 2, 1), want_stats=True, hint=2)
+    yc, sc_ = run_tc(x, w, in_affine=(sc, sh), in_relu=True, pad=(2, 2, 1), want_stats=True, hint=1)
+    refp = F.conv3d(a, w, padding=(2, 2, 1))
+    assert rel_l2(yk, refp) <= 1e-3, rel_l2(yk, refp)
+    assert rel_l2(yk, yc) <= 6e-4
+    assert torch.allclose(sk, sc_, rtol=1e-4, atol=1e-3)
 
 
 # ---- weight gradient on tensor cores (wgrad_mma.cu) ---------------------------------------------------------
@@ -261,6 +334,14 @@ WG5_CASES = [c for c in WG_CASES if c[1] >= 16 or c[2] >= 32] + [
     (4, 64, 128, (12, 12, 28), (3, 3, 2), (1, 1, 1), None),    # d4.conv1 of the bench (tap groups of 4)
     (2, 128, 64, (6, 16, 9), (3, 3, 2), (1, 1, 1), None),      # Up.conv1 shape class
     (1, 32, 32, (11, 12, 10), (3, 3, 2), (2, 2, 1), None),     # dilation
+    # channel blocks over CTAs (> 128 input / output channels) and the 2D "whole image = one flat plane" reading
+    (3, 64, 64, (30, 28, 1), (3, 3, 1), (1, 1, 1), None),      # 2D, short rows: flat plane
+    (2, 256, 128, (14, 14, 1), (3, 3, 1), (1, 1, 1), None),    # two input-channel blocks
+    (2, 128, 256, (12, 13, 1), (3, 3, 1), (1, 1, 1), None),    # two output-channel blocks
+    (1, 512, 384, (9, 10, 1), (3, 3, 1), (1, 1, 1), None),     # 4 x 3 blocks
+    (1, 256, 256, (4, 9, 8), (3, 3, 2), (1, 1, 1), None),      # 3D with blocks
+    (2, 256, 256, (6, 6, 1), (1, 1, 1), (1, 1, 1), None),      # 1x1
+    (1, 32, 32, (9, 200, 1), (3, 3, 1), (1, 1, 1), None),      # 2D, long rows: row-by-row planes as before
 ]
 
 
@@ -285,6 +366,14 @@ def test_wgrad_tc5_fused_input_bn_relu():
     a = h16(F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)))
     ref = torch.nn.grad.conv3d_weight(a, (64, 32, 3, 3, 2), dy)
     got = run_wgrad(x, dy, (3, 3, 2), in_affine=(sc, sh), use_tc5=True)
+    assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)
+    # input-channel blocks take their own slice of the scale / shift vectors
+    x = h16(torch.randn((2, 256, 9, 8, 1), generator=g))
+    dy = h16(torch.randn((2, 64, 7, 6, 1), generator=g))
+    sc, sh = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.3
+    a = h16(F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)))
+    ref = torch.nn.grad.conv3d_weight(a, (64, 256, 3, 3, 1), dy)
+    got = run_wgrad(x, dy, (3, 3, 1), in_affine=(sc, sh), use_tc5=True)
     assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)
 
 

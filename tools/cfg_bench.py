@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Train-step timing + per-layer CUDA-event profile of the BASELINE.json parity configurations that are not the bench
+line (bench.py measures configs[1]):
+
+    python tools/cfg_bench.py cfg3 [--batch 16] [--steps 5] [--out gpurun_out/cfg3_layers.txt]   # 2D classic U-Net, 572^2
+    python tools/cfg_bench.py cfg4 [--batch 4]                                                   # README 3D, 256x256x64
+
+One JSON line on stdout (same keys as bench.py where they apply), the per-layer table in --out.
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import hcunet_b200 as H  # noqa: E402
+from hcunet_b200 import _lib, profiler  # noqa: E402
+from hcunet_b200.graph import GraphedTrainStep  # noqa: E402
+
+README_3D = dict(image_dimensions=3, in_channels=4, out_channels=1, feature_sizes=[8, 16, 32, 64, 128],
+                 kernel={"conv1": (3, 3, 2), "conv2": (3, 3, 1)}, upsample_kernel=(2, 2, 2), max_pool_kernel=(2, 2, 1),
+                 upsample_stride=(2, 2, 1), dilation=1, groups=1)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("config", choices=["cfg3", "cfg4"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--precision", default="mixed")
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    if args.config == "cfg3":
+        B = args.batch or 16
+        model = H.Unet_Constructor()   # the reference's defaults: 2D, in 3, out 2, features 32..1024, 3x3, up 2x2 stride 2
+        xs, ms = (B, 3, 572, 572), (B, 2, 572, 572)
+        workload = "classic 2D U-Net [32..1024] k(3,3), ConvTranspose2d s2: train step on 572x572x3 tiles"
+        flops_fwd = 169471 * 572 * 572 * B
+    else:
+        B = args.batch or 4
+        model = H.Unet_Constructor(**README_3D)
+        xs, ms = (B, 4, 256, 256, 64), (B, 1, 256, 256, 64)
+        workload = "README 3D U-Net: train step on 256x256x64 patches"
+        flops_fwd = 10769 * 256 * 256 * 64 * B
+    model.precision = args.precision
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn(xs, generator=g).half().to(dev)
+    msk = (torch.rand(ms, generator=g) > 0.7).half().to(dev)
+    pwl = (torch.rand(ms, generator=g) * 3).half().to(dev)
+    loss_fn = lambda lg, m, w: H.cross_entropy(lg, m, w, "pixel")  # noqa: E731
+
+    def eager():
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(model(img), msk, pwl)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(2):
+        l_first = float(eager())
+    l0 = _lib.launch_count()
+    eager()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    step = eager if args.no_graph else GraphedTrainStep(model, opt, loss_fn, (img, msk, pwl))
+    run = (lambda: step()) if args.no_graph else (lambda: step.run())
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    for _ in range(args.warmup):
+        flush.zero_(); run()
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e[0].record()
+    for _ in range(args.steps):
+        flush.zero_(); run()
+    e[1].record()
+    e[2].record()
+    for _ in range(args.steps):
+        flush.zero_()
+    e[3].record()
+    torch.cuda.synchronize()
+    ms_step = (e[0].elapsed_time(e[1]) - e[2].elapsed_time(e[3])) / args.steps
+    l_last = float(step.loss if not args.no_graph else eager())
+    nvox = B
+    for v in xs[2:]:
+        nvox *= v
+    prof = profiler.KernelProfile()
+    with prof:
+        for _ in range(2):
+            torch.cuda._sleep(int(40e-3 * 1.9e9))
+            eager()
+    tab = prof.table()
+    tot = sum(v["ms"] for v in tab.values())
+    line = {"config": args.config, "workload": workload, "batch": B, "precision": args.precision, "ms_per_step": ms_step,
+            "voxels_per_s": nvox / (ms_step / 1e3), "train_tflops": 3 * flops_fwd / (ms_step / 1e3) / 1e12,
+            "fwd_gflop": flops_fwd / 1e9, "launches_per_step": int(launches), "loss_first_last": [l_first, l_last],
+            "kernel_ms_per_step": {k: round(v["ms"] / 2, 4) for k, v in sorted(tab.items(), key=lambda kv: -kv[1]["ms"])},
+            "kernel_ms_sum": tot / 2}
+    print(json.dumps(line))
+    if args.out:
+        rows = [dict(kernel=k[0], layer=k[1], ms=v["ms"] / 2, calls=v["calls"] / 2, bytes=v["bytes"] / 2, flops=v["flops"] / 2)
+                for k, v in prof.by_layer().items()]
+        rows.sort(key=lambda r: -r["ms"])
+        with open(args.out, "w") as f:
+            for r in rows:
+                gbs = r["bytes"] / (r["ms"] * 1e6) if r["ms"] > 0 else 0
+                tfs = r["flops"] / (r["ms"] * 1e9) if r["ms"] > 0 else 0
+                f.write(f"{r['ms']:9.4f} ms  {r['calls']:5.1f}x  {gbs:8.1f} GB/s {tfs:8.2f} TF/s  {r['kernel']:28s} {r['layer']}\n")
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,8 @@
     python tools/kernel_bench.py conv  [layer ...]     # tcgen05 forward conv
     python tools/kernel_bench.py wgrad [layer ...]     # tensor-core weight gradient
     python tools/kernel_bench.py conv d0.conv2 --once  # one launch (for ncu)
+    python tools/kernel_bench.py conv c3.d4.conv2 --hint=2            # force the K-streamed kernel (1: classic)
+    python tools/kernel_bench.py conv c3.d4.conv2 --hint=2 --tile=4,128,8   # ... and its tile (MB, Nc, PC)
 """
 import ctypes as C
 import os
@@ -33,6 +35,20 @@ LAYERS = {
     "u3.conv1": (8, 8, (72, 72, 28), (3, 3, 2)),
     "x.n48": (8, 48, (256, 256, 32), (3, 3, 2)),
     "x.n128": (8, 128, (256, 256, 32), (3, 3, 2)),
+    # classic 2D U-Net, batch 16 of 3 x 572 x 572 (BASELINE config 3): 5th entry = batch
+    "c3.d1.conv2": (64, 64, (282, 282, 1), (3, 3, 1), 16),
+    "c3.d2.conv1": (64, 128, (140, 140, 1), (3, 3, 1), 16),
+    "c3.d2.conv2": (128, 128, (138, 138, 1), (3, 3, 1), 16),
+    "c3.d3.conv1": (128, 256, (68, 68, 1), (3, 3, 1), 16),
+    "c3.d3.conv2": (256, 256, (66, 66, 1), (3, 3, 1), 16),
+    "c3.d4.conv1": (256, 512, (32, 32, 1), (3, 3, 1), 16),
+    "c3.d4.conv2": (512, 512, (30, 30, 1), (3, 3, 1), 16),
+    "c3.d5.conv1": (512, 1024, (14, 14, 1), (3, 3, 1), 16),
+    "c3.d5.conv2": (1024, 1024, (12, 12, 1), (3, 3, 1), 16),
+    "c3.u0.conv1": (512, 512, (20, 20, 1), (3, 3, 1), 16),
+    "c3.u1.conv1": (256, 256, (32, 32, 1), (3, 3, 1), 16),
+    "c3.u2.conv1": (128, 128, (56, 56, 1), (3, 3, 1), 16),
+    "c3.u3.conv1": (64, 64, (104, 104, 1), (3, 3, 1), 16),
 }
 
 
@@ -44,13 +60,21 @@ def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     once = "--once" in sys.argv
     notransform = "--raw" in sys.argv
+    hint, tile = 0, 0
+    for a in sys.argv[1:]:
+        if a.startswith("--hint="):
+            hint = int(a[7:])
+        if a.startswith("--tile="):
+            mb, nc, pc = (int(v) for v in a[7:].split(","))
+            tile = mb | (nc << 8) | (pc << 20)
     kind = args[0] if args else "conv"
     names = args[1:] or list(LAYERS)
     lib = _lib.load()
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")
     for name in names:
-        cin, cout, isz, k = LAYERS[name]
+        cin, cout, isz, k = LAYERS[name][:4]
+        B = LAYERS[name][4] if len(LAYERS[name]) > 4 else 4
         osz = tuple(isz[i] - k[i] + 1 for i in range(3))
         x = torch.randn((B,) + isz + (cin,), device="cuda").half()
         sc = torch.rand(cin, device="cuda") + 0.5
@@ -61,6 +85,12 @@ def main():
         nin, nout = x.numel(), B * osz[0] * osz[1] * osz[2] * cout
         if kind == "conv":
             d = conv_desc(_lib.F16, _lib.F16, B, isz, cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, in_relu=1)
+            d.reserved[0], d.reserved[1] = hint, tile
+            buf = C.create_string_buffer(256)
+            lib.hcu_conv_tc_describe(C.byref(d), buf, 256)
+            if buf.value.startswith(b"unsupported"):
+                print(f"{kind:5s} {name:12s} {buf.value.decode()}")
+                continue
             w = torch.randn(T * cin * cout, device="cuda") / (T * cin) ** 0.5
             packed = torch.empty(lib.hcu_conv_tc_packed_bytes(C.byref(d)), dtype=torch.uint8, device="cuda")
             _lib.check(lib.hcu_conv_tc_pack(C.byref(d), P(w), P(packed), st))
@@ -102,7 +132,8 @@ def main():
         ms = sorted(ts)[len(ts) // 2]
         byt = (nin + nout) * 2
         fl = 2 * (nout // cout) * T * cin * cout
-        print(f"{kind:5s} {name:9s} {ms*1e3:8.1f} us  {byt/ms/1e6:7.1f} GB/s  {fl/ms/1e9:7.2f} TF/s  (min {min(ts)*1e3:.1f} us)")
+        cfg = ("  " + buf.value.decode()) if kind == "conv" else ""
+        print(f"{kind:5s} {name:12s} {ms*1e3:8.1f} us  {byt/ms/1e6:7.1f} GB/s  {fl/ms/1e9:7.2f} TF/s  (min {min(ts)*1e3:.1f} us){cfg}")
 
 
 if __name__ == "__main__":
