@@ -46,6 +46,7 @@ struct Params {
   int Yv, Zv;
   int M, RUN, PS, SLOT, DPS, DSLOT, R, RD, D;
   int Nc, TG, NG, taps;
+  int flat;        // 2D with short rows: all images stacked into ONE flat plane, the CTA marches over runs of M positions (OX = runs)
   int n_cb, n_ob;  // channel blocks over CTAs: 128 input channels (16 planes) x Nc output channels each; P / Po = planes per block
   int n_runs, Lx, n_xseg;
   int in_relu, vec4;
@@ -208,19 +209,26 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
 #pragma unroll
       for (int j = 0; j < 8; ++j) { sc[j] = p.a_scale[(cb * p.P + plane) * 8 + j]; sh[j] = p.a_shift[(cb * p.P + plane) * 8 + j]; }
     }
-    const int qf = q0 + pix0;
-    const int yv0 = qf / p.Zv, zv0 = qf - yv0 * p.Zv;
     const int ystep = pstep / p.Zv, zstep = pstep - ystep * p.Zv;
+    const int flat = p.flat;
     const __half* a_n = p.a + (size_t)n * p.IX * p.IY * p.IZ * p.Cp + (cb * p.P + plane) * 8;
-    const size_t a_xs = (size_t)p.IY * p.IZ * p.Cp;
+    const size_t a_xs = flat ? 0 : (size_t)p.IY * p.IZ * p.Cp;
+    const size_t a_is = (size_t)p.IY * p.IZ * p.Cp;   // flat: image stride (IX == 1)
     // dy: [Po planes][M pixels]
     const int dplane = ptid % p.Po, dpix0 = ptid / p.Po, dstep = 128 / p.Po;
     const int nchunk_d = (p.M - dpix0 + dstep - 1) / dstep;
-    const int dqf = q0 + dpix0;
-    const int dy0 = dqf / p.Zv, dz0 = dqf - dy0 * p.Zv;
     const int dystep = dstep / p.Zv, dzstep = dstep - dystep * p.Zv;
     const __half* d_n = p.dy + (size_t)n * p.OX * p.OY * p.OZ * p.Cop + (ob * p.Po + dplane) * 8;
-    const size_t d_xs = (size_t)p.OY * p.OZ * p.Cop;
+    const size_t d_xs = flat ? 0 : (size_t)p.OY * p.OZ * p.Cop;
+    const size_t d_is = (size_t)p.OY * p.OZ * p.Cop;
+    // first position of this thread in step j: (image, virtual row, virtual column).  Normal mode: the run is fixed and the
+    // step moves along x; flat mode: the step IS the run (x0 + j), positions run over the stacked images.
+    auto first = [&](int step, int px0, int& im, int& yv, int& zv) {
+      const int qf = (flat ? (x0 + step) * p.M : q0) + px0;
+      const int r = qf / p.Zv;
+      zv = qf - r * p.Zv;
+      if (flat) { im = r / p.Yv; yv = r - im * p.Yv; } else { im = 0; yv = r; }
+    };
 
     const int D = p.D;
     // One pipeline over "steps": step j stages a-plane j (j < nplanes) and dy-plane j - (span - 1) (when >= 0).
@@ -230,17 +238,19 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
       // a-plane jf
       if (xf) {
         const int xm = x0 + txlo * p.dx + jf - p.px;
-        if (xm >= 0 && xm < p.IX) {
+        if (flat || (xm >= 0 && xm < p.IX)) {
           unsigned char* dp = smem + sa_f * p.SLOT + plane * p.PS + pix0 * 16;
-          int yv = yv0, zv = zv0;
+          int im, yv, zv;
+          first(jf, pix0, im, yv, zv);
           for (int c = 0; c < nchunk; ++c) {
             const int ym = yv - p.py, zm = zv - p.pz;
-            if (ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ) {
+            if (im < p.N && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ) {
               uint4* q = reinterpret_cast<uint4*>(dp + (size_t)c * pstep * 16);
               *q = bn_relu8(*q, sc, sh, relu);
             }
             zv += zstep; yv += ystep;
             if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+            if (flat && yv >= p.Yv) { yv -= p.Yv; ++im; }
           }
         }
       }
@@ -263,16 +273,18 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
         mbar_wait(bar_ea + 8 * sa_i, par_a);
         {
           const int xm = x0 + txlo * p.dx + j - p.px;
-          const bool xok = xm >= 0 && xm < p.IX;
+          const bool xok = flat || (xm >= 0 && xm < p.IX);
           const __half* a_x = a_n + (size_t)(xok ? xm : 0) * a_xs;
           const uint32_t dst = a_base + (uint32_t)(sa_i * p.SLOT + plane * p.PS + pix0 * 16);
-          int yv = yv0, zv = zv0;
+          int im, yv, zv;
+          first(j, pix0, im, yv, zv);
           for (int c = 0; c < nchunk; ++c) {
             const int ym = yv - p.py, zm = zv - p.pz;
-            const bool ok = xok && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
-            cp_async16(dst + c * pstep * 16, ok ? a_x + ((size_t)ym * p.IZ + zm) * p.Cp : a_n, ok ? 16u : 0u);
+            const bool ok = xok && im < p.N && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
+            cp_async16(dst + c * pstep * 16, ok ? a_x + (size_t)im * a_is + ((size_t)ym * p.IZ + zm) * p.Cp : a_n, ok ? 16u : 0u);
             zv += zstep; yv += ystep;
             if (zv >= p.Zv) { zv -= p.Zv; ++yv; }
+            if (flat && yv >= p.Yv) { yv -= p.Yv; ++im; }
           }
         }
         if (++sa_i == R) { sa_i = 0; par_a ^= 1; }
@@ -281,12 +293,14 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
           const int i = j - (span - 1);  // output plane
           const __half* d_x = d_n + (size_t)(x0 + i) * d_xs;
           const uint32_t dst = d_base + (uint32_t)(sd_i * p.DSLOT + dplane * p.DPS + dpix0 * 16);
-          int oy = dy0, oz = dz0;
+          int im, oy, oz;
+          first(i, dpix0, im, oy, oz);
           for (int c = 0; c < nchunk_d; ++c) {
-            const bool ok = oy < p.OY && oz < p.OZ;
-            cp_async16(dst + c * dstep * 16, ok ? d_x + ((size_t)oy * p.OZ + oz) * p.Cop : d_n, ok ? 16u : 0u);
+            const bool ok = im < p.N && oy < p.OY && oz < p.OZ;
+            cp_async16(dst + c * dstep * 16, ok ? d_x + (size_t)im * d_is + ((size_t)oy * p.OZ + oz) * p.Cop : d_n, ok ? 16u : 0u);
             oz += dzstep; oy += dystep;
             if (oz >= p.Zv) { oz -= p.Zv; ++oy; }
+            if (flat && oy >= p.Yv) { oy -= p.Yv; ++im; }
           }
           if (++sd_i == RD) { sd_i = 0; par_d ^= 1; }
         }
@@ -397,11 +411,14 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   p.N = d->batch;
   p.Cp = d->in_cpitch; p.P = P; p.cin = d->cin;
   p.Cop = d->out_cpitch; p.Po = Po; p.cout = d->cout;
-  // A 2D problem with short image rows is re-read as ONE x-plane of rows x columns: the filter rows become flat shifts
-  // too, and a run of M positions spans several rows instead of leaving most of an MMA's K = 16-pixel chunks empty
-  // (a 30-pixel row of the classic U-Net's bottom levels fills 12 % of a 256-position run).
+  // A 2D problem with SHORT image rows (the bottom levels of the classic U-Net: 12 .. 32 pixels) is re-read as one flat
+  // plane of rows x columns with all images of the batch stacked (rows = N * Yv): the filter rows become flat shifts too
+  // and the CTA marches over consecutive RUNS of M positions (the "x" axis of the kernel is the run index), instead of
+  // leaving most of an MMA's K = 16-pixel chunks empty (a 30-pixel row fills 23 % of a 128-position run).  Longer rows
+  // keep the row-by-row march: every staged run would carry 2 rows of halo.
   const bool flat2d = d->in_size[2] == 1 && d->out_size[2] == 1 && d->taps[2] == 1 && d->pad[2] == 0 && d->dil[2] == 1 &&
-                      d->out_size[1] + (d->taps[1] - 1) * d->dil[1] < 192;
+                      d->out_size[1] + (d->taps[1] - 1) * d->dil[1] < 40;
+  p.flat = flat2d ? 1 : 0;
   if (flat2d) {
     p.IX = 1; p.IY = d->in_size[0]; p.IZ = d->in_size[1];
     p.OX = 1; p.OY = d->out_size[0]; p.OZ = d->out_size[1];
@@ -435,7 +452,10 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
     p.tmem_cols = t;
   }
   const int halo = (p.KY - 1) * p.dy_ * p.Zv + (p.KZ - 1) * p.dz;
-  const int plane_q = p.Yv * p.Zv;
+  // flat: positions of the stacked images that hold outputs (the tail rows of the last image are never needed)
+  const long long plane_qq = p.flat ? ((long long)(p.N - 1) * p.Yv + p.OY - 1) * p.Zv + p.OZ : (long long)p.Yv * p.Zv;
+  if (plane_qq >= 0x3fffffffLL) return "plane too large";
+  const int plane_q = (int)plane_qq;
   // widest x extent a tap group can have
   int max_span = 1;
   for (int g = 0; g < p.NG; ++g) {
@@ -469,6 +489,10 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
       p.M = M; p.RUN = run; p.PS = ps; p.SLOT = slot; p.DPS = dps; p.DSLOT = dslot; p.R = R; p.RD = RD; p.D = D;
       p.off_d = off_d; p.off_bar = off_bar; p.smem_bytes = total;
       p.n_runs = (plane_q + M - 1) / M;
+      if (p.flat) {  // the run index becomes the kernel's x axis (segmented over CTAs by the launch code)
+        p.OX = p.n_runs;
+        p.n_runs = 1;
+      }
       for (int t = 0; t < p.taps; ++t) {
         const int tz = t % p.KZ, tq = t / p.KZ;
         const int ty = tq % p.KY, tx = tq / p.KY;
@@ -512,7 +536,7 @@ extern "C" int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const
     attr = true;
   }
   // x segmentation: about two waves of CTAs, segments no shorter than 4 planes
-  const long long base_items = (long long)p.N * p.n_runs * p.NG * p.n_cb * p.n_ob;
+  const long long base_items = (long long)(p.flat ? 1 : p.N) * p.n_runs * p.NG * p.n_cb * p.n_ob;
   const int per_sm = std::max(1, std::min(233472 / (p.smem_bytes + 1024), 512 / p.tmem_cols));
   const long long target = 2LL * per_sm * num_sms();
   int nseg = (int)((target + base_items - 1) / base_items);
