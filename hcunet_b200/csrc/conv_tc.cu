@@ -1019,6 +1019,7 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
     const int relu = p.in_relu;
     const uint32_t sstep = (uint32_t)pstep * 16u;
     const int nstage = p.KX * p.NCH;
+    const bool phased_in = p.ips[0] * p.ips[1] * p.ips[2] > 1;
     int slot_i = 0, slot_f = 0;
     uint32_t par = 1;
     auto finish = [&](int st) {  // stage st has landed: transform in place, publish
@@ -1045,7 +1046,15 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
       mbar_wait(bar_ea + 8 * slot_i, par);
       const int xm = ox + tx * p.dx - p.px;
       const bool xok = xm >= 0 && xm < p.IX;
-      const __half* src = p.in + (size_t)(xok ? xm : 0) * (size_t)p.in_xs + (c * PC + pl) * 8;
+      long long plane_off = (long long)(c * PC + pl) * 8;
+      if (phased_in) {  // channel plane -> (stride phase, 8-channel group): the phase selects a sub-lattice of the input
+        int phi = (c * PC + pl) / p.Pc;
+        const int cg = (c * PC + pl) - phi * p.Pc;
+        const int fz = phi % p.ips[2]; phi /= p.ips[2];
+        const int fy = phi % p.ips[1], fx = phi / p.ips[1];
+        plane_off = (long long)cg * 8 + fx * p.in_ph[0] + fy * p.in_ph[1] + fz * p.in_ph[2];
+      }
+      const __half* src = p.in + (size_t)(xok ? xm : 0) * (size_t)p.in_xs + plane_off;
       uint32_t dst = a_base + (uint32_t)(slot_i * p.SLOT + pl * p.PS + pix0 * 16);
       for (int i = pix0; i < p.RUN; i += pstep, dst += sstep) {
         const int o = soff[i];
@@ -1503,22 +1512,22 @@ static const char* configure_ks(const HcuConvDesc* d, Params& p) {
   if (d->groups != 1) return "groups != 1";
   if (d->in_cpitch % 32 != 0 || d->in_c_off != 0 || d->cin != d->in_cpitch) return "input channels: dense multiple of 32";
   if (d->cin < 64) return "fewer than 64 input channels";
-  if (d->iphase) return "iphase";
   if (d->cout % 8 != 0 || d->out_cpitch % 8 != 0 || d->out_c_off % 8 != 0) return "output channels: multiples of 8";
   for (int i = 0; i < 3; ++i) {
     p.ops[i] = std::max(1, (d->ophase >> (8 * i)) & 0xff);
-    p.ips[i] = 1;
+    p.ips[i] = std::max(1, (d->iphase >> (8 * i)) & 0xff);
     if (d->istep[i] != 1) return "strided gather";
   }
-  const int nph_o = p.ops[0] * p.ops[1] * p.ops[2];
+  const int nph_o = p.ops[0] * p.ops[1] * p.ops[2], nph_i = p.ips[0] * p.ips[1] * p.ips[2];
   if (nph_o > 1) {
     if (d->cout % nph_o || (d->cout / nph_o) % 8) return "ophase needs 8-channel aligned phases";
     for (int i = 0; i < 3; ++i)
       if (d->ostep[i] < p.ops[i]) return "ophase larger than the output step";
   }
+  if (nph_i > 1 && (d->cin % nph_i || (d->cin / nph_i) % 8)) return "iphase needs 8-channel aligned phases";
   p.cpp = d->cout / nph_o;
   const int P = d->in_cpitch / 8;
-  p.P = P; p.Pc = P; p.Cp = d->in_cpitch;
+  p.P = P; p.Pc = P / nph_i; p.Cp = d->in_cpitch;
   p.N = d->batch;
   p.cout = d->cout;
   // axis roles: a (march / separate planes), b, c (flat plane).  2D: a is a dummy axis of extent 1.
@@ -1531,14 +1540,17 @@ static const char* configure_ks(const HcuConvDesc* d, Params& p) {
   p.dx = get(d->dil, A, 1); p.dy = d->dil[B]; p.dz = d->dil[Cc];
   p.px = get(d->pad, A, 0); p.py = d->pad[B]; p.pz = d->pad[Cc];
   {
-    const long long cz = d->in_cpitch, cy = cz * d->in_size[2], cx = cy * d->in_size[1], cn = cx * d->in_size[0];
-    const long long st[3] = {cx, cy, cz};
-    if (cn * d->batch >= 0x7fffffffLL) return "input tensor too large for 32-bit offsets";
-    p.in_ns = cn;
+    // element strides of the (full-resolution) input tensor per COARSE step of each descriptor axis, and per phase step
+    const long long cr = d->in_cpitch / nph_i;
+    const long long fz = cr, fy = fz * d->in_size[2] * p.ips[2], fx = fy * d->in_size[1] * p.ips[1],
+                    fn = fx * d->in_size[0] * p.ips[0];
+    const long long st[3] = {fx * p.ips[0], fy * p.ips[1], fz * p.ips[2]};
+    if (fn * d->batch >= 0x7fffffffLL) return "input tensor too large for 32-bit offsets";
+    p.in_ns = fn;
     p.in_xs = A < 0 ? 0 : st[A];
     p.in_ys = (int)st[B];
     p.in_zs = (int)st[Cc];
-    p.in_ph[0] = p.in_ph[1] = p.in_ph[2] = 0;
+    p.in_ph[0] = fx; p.in_ph[1] = fy; p.in_ph[2] = fz;
   }
   p.Yv = p.OY + (p.KY - 1) * p.dy;
   p.Zv = p.OZ + (p.KZ - 1) * p.dz;

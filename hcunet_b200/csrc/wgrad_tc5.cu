@@ -46,6 +46,9 @@ struct Params {
   int Yv, Zv;
   int M, RUN, PS, SLOT, DPS, DSLOT, R, RD, D;
   int Nc, TG, NG, taps;
+  // dy addressing (elements): image / x / y / z strides of the COARSE grid, stride-phase decomposition of the channel planes
+  long long d_is, d_xs, d_ph[3];
+  int d_ys, d_zs, dps[3], Pc_o;
   int flat;        // 2D with short rows: all images stacked into ONE flat plane, the CTA marches over runs of M positions (OX = runs)
   int n_cb, n_ob;  // channel blocks over CTAs: 128 input channels (16 planes) x Nc output channels each; P / Po = planes per block
   int n_runs, Lx, n_xseg;
@@ -218,9 +221,19 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
     const int dplane = ptid % p.Po, dpix0 = ptid / p.Po, dstep = 128 / p.Po;
     const int nchunk_d = (p.M - dpix0 + dstep - 1) / dstep;
     const int dystep = dstep / p.Zv, dzstep = dstep - dystep * p.Zv;
-    const __half* d_n = p.dy + (size_t)n * p.OX * p.OY * p.OZ * p.Cop + (ob * p.Po + dplane) * 8;
-    const size_t d_xs = flat ? 0 : (size_t)p.OY * p.OZ * p.Cop;
-    const size_t d_is = (size_t)p.OY * p.OZ * p.Cop;
+    // channel plane -> (stride phase, 8-channel group): a phase selects a sub-lattice of the full-resolution dy tensor
+    long long dplane_off = (long long)(ob * p.Po + dplane) * 8;
+    if (p.dps[0] * p.dps[1] * p.dps[2] > 1) {
+      const int vp = ob * p.Po + dplane;
+      int phi = vp / p.Pc_o;
+      const int cg = vp - phi * p.Pc_o;
+      const int fz = phi % p.dps[2]; phi /= p.dps[2];
+      const int fy = phi % p.dps[1], fx = phi / p.dps[1];
+      dplane_off = (long long)cg * 8 + fx * p.d_ph[0] + fy * p.d_ph[1] + fz * p.d_ph[2];
+    }
+    const __half* d_n = p.dy + (size_t)n * (size_t)p.d_is + dplane_off;
+    const size_t d_xs = flat ? 0 : (size_t)p.d_xs;
+    const size_t d_is = (size_t)p.d_is;
     // first position of this thread in step j: (image, virtual row, virtual column).  Normal mode: the run is fixed and the
     // step moves along x; flat mode: the step IS the run (x0 + j), positions run over the stacked images.
     auto first = [&](int step, int px0, int& im, int& yv, int& zv) {
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
           first(i, dpix0, im, oy, oz);
           for (int c = 0; c < nchunk_d; ++c) {
             const bool ok = im < p.N && oy < p.OY && oz < p.OZ;
-            cp_async16(dst + c * dstep * 16, ok ? d_x + (size_t)im * d_is + ((size_t)oy * p.OZ + oz) * p.Cop : d_n, ok ? 16u : 0u);
+            cp_async16(dst + c * dstep * 16, ok ? d_x + (size_t)im * d_is + ((size_t)oy * p.d_ys + (size_t)oz * p.d_zs) : d_n, ok ? 16u : 0u);
             oz += dzstep; oy += dystep;
             if (oz >= p.Zv) { oz -= p.Zv; ++oy; }
             if (flat && oy >= p.Yv) { oy -= p.Yv; ++im; }
@@ -395,7 +408,10 @@ static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static const char* configure(const HcuConvDesc* d, Params& p) {
   if (d->dtype_in != HCU_F16 || d->dtype_out != HCU_F16) return "fp16 only";
   if (d->groups != 1) return "groups != 1";
-  if (d->ophase || d->iphase) return "stride phases";
+  if (d->iphase) return "iphase";
+  for (int i = 0; i < 3; ++i) p.dps[i] = std::max(1, (d->ophase >> (8 * i)) & 0xff);
+  const int nph = p.dps[0] * p.dps[1] * p.dps[2];
+  if (nph > 1 && (d->cout != d->out_cpitch || d->cout % nph || (d->cout / nph) % 8)) return "ophase needs 8-channel aligned phases";
   if (d->in_cpitch % 8 != 0 || d->in_c_off != 0 || d->cin > d->in_cpitch) return "input channel layout";
   if (d->out_cpitch % 8 != 0 || d->out_c_off != 0 || d->cout > d->out_cpitch) return "dy channel layout";
   const int Pt = d->in_cpitch / 8, Pot = d->out_cpitch / 8;  // channel planes of the whole tensors
@@ -407,7 +423,7 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   p.n_cb = Pt / P; p.n_ob = Pot / Po;
   if ((p.n_cb > 1 && d->cin != d->in_cpitch) || (p.n_ob > 1 && d->cout != d->out_cpitch)) return "channel blocks need dense channels";
   for (int i = 0; i < 3; ++i)
-    if (d->istep[i] != 1 || d->ostep[i] != 1 || d->ooff[i] != 0 || d->out_tsize[i] != d->out_size[i]) return "strided";
+    if (d->istep[i] != 1 || d->ostep[i] != p.dps[i] || d->ooff[i] != 0 || d->out_tsize[i] != d->out_size[i] * p.dps[i]) return "strided";
   p.N = d->batch;
   p.Cp = d->in_cpitch; p.P = P; p.cin = d->cin;
   p.Cop = d->out_cpitch; p.Po = Po; p.cout = d->cout;
@@ -419,6 +435,19 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   const bool flat2d = d->in_size[2] == 1 && d->out_size[2] == 1 && d->taps[2] == 1 && d->pad[2] == 0 && d->dil[2] == 1 &&
                       d->out_size[1] + (d->taps[1] - 1) * d->dil[1] < 40;
   p.flat = flat2d ? 1 : 0;
+  {
+    // dy (ophase: the `cout` channels are [nph][cout / nph], phase phi of coarse position o lives at o * s + phi of the
+    // full-resolution tensor whose channel pitch is cout / nph)
+    const long long cr = d->out_cpitch / nph;
+    const long long tz = cr, ty = tz * d->out_tsize[2], tx = ty * d->out_tsize[1];
+    const long long cs[3] = {tx * p.dps[0], ty * p.dps[1], tz * p.dps[2]};  // coarse strides per descriptor axis
+    if (cs[0] >= 0x7fffffffLL) return "dy plane too large";
+    p.d_is = tx * d->out_tsize[0];
+    p.d_ph[0] = tx; p.d_ph[1] = ty; p.d_ph[2] = tz;
+    p.Pc_o = (int)(cr / 8);
+    if (flat2d) { p.d_xs = 0; p.d_ys = (int)cs[0]; p.d_zs = (int)cs[1]; }
+    else { p.d_xs = cs[0]; p.d_ys = (int)cs[1]; p.d_zs = (int)cs[2]; }
+  }
   if (flat2d) {
     p.IX = 1; p.IY = d->in_size[0]; p.IZ = d->in_size[1];
     p.OX = 1; p.OY = d->out_size[0]; p.OZ = d->out_size[1];

@@ -761,7 +761,8 @@ class UnetEngine:
                     dd = conv_desc(adt, adt, B, Q, nph * u.cout, 0, nph * u.cout, nph * u.cout, u.in_sz, u.in_sz, u.cin, 0,
                                    u.cin, 1, J)
                     dd.iphase = self._phase_word(u.s)
-                    if lib.hcu_conv_wgrad_tc_supported(C.byref(dw)) and lib.hcu_conv_tc_supported(C.byref(dd)):
+                    if (lib.hcu_conv_wgrad_tc_supported(C.byref(dw)) or lib.hcu_conv_wgrad_tc5_supported(C.byref(dw))) and \
+                            lib.hcu_conv_tc_supported(C.byref(dd)):
                         total = nph * J[0] * J[1] * J[2] * u.cin * u.cout
                         note = (u.name, (npix_out * u.cout + m * u.cin) * esz, 2 * m * T * u.cin * u.cout)
                         grads[u.name + ".weight"] = self._wgrad_dispatch(u.name + ".weight", wt, dw, a_in, isc, ish, dcur,

@@ -153,6 +153,48 @@ def test_fresh_input_matches_oracle(precision):
     assert rel_l2(xg.grad, xo.grad) <= tol_grad
 
 
+CHANNEL_RICH = {
+    # classic-U-Net-like 2D levels: K-streamed tcgen05 convs (64..256 input channels), weight gradients split into
+    # 128-channel blocks, ConvTranspose 256 -> 128 with its stride phases folded into 512 channels (forward: ophase on the
+    # K-streamed kernel; data gradient: iphase on it; weight gradient: ophase on the dy side of the tcgen05 kernel)
+    "rich2d": (dict(image_dimensions=2, in_channels=3, out_channels=2, feature_sizes=[64, 128, 256], kernel=(3, 3),
+                    upsample_kernel=(2, 2), max_pool_kernel=(2, 2), upsample_stride=2, dilation=1, groups=1),
+               (2, 3, 60, 52), (2, 2, 60, 52)),
+    # the bottom of the README 3D model at full width
+    "rich3d": (dict(O.README_3D, feature_sizes=[64, 128]), (1, 4, 22, 20, 6), (1, 1, 22, 20, 6)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CHANNEL_RICH))
+def test_channel_rich_models_match_oracle(name):
+    import hcunet_b200 as H
+
+    kwargs, xs, ms = CHANNEL_RICH[name]
+    tol = TOL["mixed"]
+    torch.manual_seed(31)
+    m = H.Unet_Constructor(**kwargs)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(xs, generator=g)
+    mask = (torch.rand(ms, generator=g) > 0.5).float()
+    pwl = torch.rand(ms, generator=g)
+    loss_o, logits_o, grads_o, _ = O.train_step_grads(sd, kwargs, x, mask, pwl)
+    tol_out, tol_grad, _ = calibrated(tol, "mixed", sd, kwargs, x, mask, pwl, logits_o, grads_o)
+    m.precision = "mixed"
+    m = m.cuda().train()
+    logits = m(x.cuda())
+    loss = H.cross_entropy(logits, mask.cuda(), pwl.cuda(), "pixel")
+    loss.backward()
+    assert rel_l2(logits, logits_o) <= tol_out, (rel_l2(logits, logits_o), tol_out)
+    assert abs(float(loss) - float(loss_o)) <= tol_out * abs(float(loss_o))
+    worst = {}
+    for k, gr in grads_o.items():
+        if not is_dead_bias(k):
+            worst[k] = rel_l2(dict(m.named_parameters())[k].grad, gr)
+    bad = {k: v for k, v in worst.items() if v > tol_grad}
+    assert not bad, (bad, tol_grad)
+
+
 def test_too_small_and_bad_inputs_raise():
     import hcunet_b200 as H
 
