@@ -1063,7 +1063,9 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
       }
       cp_async_commit();
       if (++slot_i == RA) { slot_i = 0; par ^= 1; }
-      if (st >= 1) {  // one stage in flight behind the one just issued
+      // ONE stage in flight behind the one just issued.  Two (measured, RA = 3): 645 -> 503 TFLOP/s on the 256-channel 2D
+      // level -- the producer blocks on the ring with a landed stage still unpublished, so the MMA sees one stage less
+      if (st >= 1) {
         cp_async_wait<1>();
         finish(st - 1);
       }
@@ -1587,43 +1589,61 @@ static const char* configure_ks(const HcuConvDesc* d, Params& p) {
         { const int g = pc >= 8 ? 16 : 128 / pc; ps = round_up(ps, 2 * g) + g; }
         if ((ps >> 4) > 0x3fff) continue;
         const int slot = ps * pc;
+        // ring depths: a third A stage first (measured on the (256, 256) tile: RA = 3 / RB = 2 733 TFLOP/s, RA = 2 / RB = 3
+        // 668), then weight tiles worth up to 64 KB in flight behind the one being consumed; among equals the smaller footprint
+        static int f_ra = -1, f_rb = -1;
+        if (f_ra < 0) { const char* e = getenv("HCU_KS_RA"); f_ra = e ? atoi(e) : 0; e = getenv("HCU_KS_RB"); f_rb = e ? atoi(e) : 0; }
+        int best_ra = 0, best_rb = 0, best_total = 0;
+        double best_score = -1.0;
+        int offs[5] = {0, 0, 0, 0, 0};
         for (int ra = 3; ra >= 2; --ra) {
-          for (int rb = 6; rb >= 2; rb -= 2) {
-            const int off_w = 0;
+          for (int rb = 8; rb >= 2; --rb) {
+            if ((f_ra && ra != f_ra) || (f_rb && rb != f_rb)) continue;
             const int off_a = round_up(rb * bt, 128);
             const int off_tab = off_a + ra * slot;
             const int off_bar = round_up(off_tab + run * 4, 8);
             const int off_stat = round_up(off_bar + 8 * (2 * ra + 2 * rb + 1) + 8, 16);
             const int total = off_stat + 11 * nc * 4 + 128;
             if (total > kSmemLimit) continue;
-            const int nch = P / pc;
-            const double mma1 = std::max(32.0 + nc / 4.0, nc / 2.0);
-            const double t_mma = (double)p.KX * nch * KYZ * (pc / 2) * MB * mma1;
-            const double bytes = (double)p.KX * nch * ((double)run * pc * 16 + (double)KYZ * bt);
-            const double t_mem = bytes / 20.0;
-            const double t_cta = std::max(t_mma, t_mem) + 4000.0 + MB * (nc / 16) * 150.0 + (ra < 3 ? 0.05 * t_mma : 0.0) +
-                                 (rb < 4 ? 0.05 * t_mma : 0.0);
-            const long long n_runs = (n_last + M - 1) / M;
-            const long long items = (long long)p.OX * n_runs * (npad / nc);
-            const double cost = (double)((items + sms - 1) / sms) * t_cta;
-            if (cost < best) {
-              best = cost; found = true;
-              b = p;
-              b.M = M; b.MB = MB; b.RUN = run; b.PS = ps; b.SLOT = slot; b.PC = pc; b.NCH = nch; b.RA = ra; b.RB = rb; b.BT = bt;
-              b.R = ra; b.D = 1;
-              b.Nc = nc; b.nsplit = npad / nc;
-              b.off_w = off_w; b.off_a = off_a; b.off_tab = off_tab; b.off_bar = off_bar; b.off_stat = off_stat;
-              b.smem_bytes = total;
-              int t = 32;
-              while (t < MB * nc) t <<= 1;
-              b.tmem_cols = t;
-              b.n_runs = (int)n_runs;
-              b.Lx = 1; b.n_xseg = p.OX;
+            const double score = 2.0 * (ra - 1) + std::min(1.0, (double)(rb - 1) * bt / 65536.0) - 1e-7 * total;
+            if (score > best_score) {
+              best_score = score; best_ra = ra; best_rb = rb; best_total = total;
+              offs[0] = off_a; offs[1] = off_tab; offs[2] = off_bar; offs[3] = off_stat;
             }
-            goto next_pc;  // deepest rings that fit
           }
         }
-      next_pc:;
+        if (best_ra == 0) continue;
+        {
+          const int ra = best_ra, rb = best_rb, total = best_total;
+          const int off_w = 0, off_a = offs[0], off_tab = offs[1], off_bar = offs[2], off_stat = offs[3];
+          const int nch = P / pc;
+          // one M = 128, K = 16 MMA: shared-memory operand fetch (32 + N/4 clk, profiles/r01_umma_rate.txt) vs tensor rate
+          // (N/2 clk), times a measured efficiency of the issue / barrier machinery per column-chunk width (2D U-Net 256- and
+          // 512-channel levels: (M, Nc) = (256, 256) runs at 730 TFLOP/s, (512, 128) at 620 - 645, (256, 128) at 510 - 520)
+          const double mma1 = std::max(32.0 + nc / 4.0, nc / 2.0) * (nc >= 256 ? 1.0 : nc >= 128 ? 1.18 : 1.35);
+          const double t_mma = (double)p.KX * nch * KYZ * (pc / 2) * MB * mma1;
+          const double bytes = (double)p.KX * nch * ((double)run * pc * 16 + (double)KYZ * bt);
+          const double t_mem = bytes / 40.0;  // L2 -> shared memory per SM: 27 B/clk measured without being the limiter
+          const double t_cta = std::max(t_mma, t_mem) + 4000.0 + MB * (nc / 16) * 150.0 + (ra < 3 ? 0.10 * t_mma : 0.0) +
+                               ((rb - 1) * bt < 65536 ? 0.03 * t_mma : 0.0);
+          const long long n_runs = (n_last + M - 1) / M;
+          const long long items = (long long)p.OX * n_runs * (npad / nc);
+          const double cost = (double)((items + sms - 1) / sms) * t_cta;
+          if (cost < best) {
+            best = cost; found = true;
+            b = p;
+            b.M = M; b.MB = MB; b.RUN = run; b.PS = ps; b.SLOT = slot; b.PC = pc; b.NCH = nch; b.RA = ra; b.RB = rb; b.BT = bt;
+            b.R = ra; b.D = 1;
+            b.Nc = nc; b.nsplit = npad / nc;
+            b.off_w = off_w; b.off_a = off_a; b.off_tab = off_tab; b.off_bar = off_bar; b.off_stat = off_stat;
+            b.smem_bytes = total;
+            int t = 32;
+            while (t < MB * nc) t <<= 1;
+            b.tmem_cols = t;
+            b.n_runs = (int)n_runs;
+            b.Lx = 1; b.n_xseg = p.OX;
+          }
+        }
       }
     }
   }

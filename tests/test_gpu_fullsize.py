@@ -131,3 +131,79 @@ def test_fullsize_graph_step_equals_eager_step():
         if a.is_floating_point() and "running" not in k:
             # Adam's first step moves every weight by ~lr * sign(grad): compare the moved weights
             assert rel_l2(b, a) <= 1e-3, (k, rel_l2(b, a))
+
+
+# ---- BASELINE.json configs[2]: the classic 2D U-Net (features 32..1024) on 572x572x3 tiles -------------------------
+# Its 64..1024-channel levels run on the K-streamed tcgen05 kernel (conv_ks_kernel: images of the batch stacked into one
+# flat index, 2D images read as one flat plane) and the channel-blocked tcgen05 weight gradient.
+SHAPE2D = (4, 3, 572, 572)
+
+
+def make2d(precision, seed=0):
+    import hcunet_b200 as H
+
+    torch.manual_seed(seed)
+    m = H.Unet_Constructor()   # the reference's defaults (unet.py:16-27): 2D, in 3, out 2, features [32 .. 1024]
+    m.precision = precision
+    return m.cuda()
+
+
+def data2d(seed=9, batch=SHAPE2D[0]):
+    g = torch.Generator().manual_seed(seed)
+    shp = (batch,) + SHAPE2D[1:]
+    x = torch.randn(shp, generator=g).half().cuda()
+    mask = (torch.rand((batch, 2) + SHAPE2D[2:], generator=g) > 0.7).half().cuda()
+    pwl = (torch.rand((batch, 2) + SHAPE2D[2:], generator=g) * 3).half().cuda()
+    return x, mask, pwl
+
+
+def test_fullsize_2d_eval_forward_is_per_image_bit_exact():
+    m = make2d("mixed")
+    x, _, _ = data2d()
+    m.train()
+    with torch.no_grad():
+        m(x)
+        m.eval()
+        full = m(x)
+        assert full.shape == (4, 2, 196, 196)   # valid convolutions + the reference's dead skips: 572 -> 196
+        assert torch.isfinite(full).all()
+        for b in (0, 2):
+            # alone, the image is tiled differently by every kernel (other run boundaries in the stacked flat index,
+            # other column-chunk splits): the arithmetic per output pixel must not depend on that
+            alone = m(x[b:b + 1].contiguous())
+            assert torch.equal(alone[0], full[b]), f"image {b}: max diff {float((alone[0] - full[b]).abs().max())}"
+
+
+def test_fullsize_2d_mixed_agrees_with_fp32_path():
+    x, _, _ = data2d(batch=1)
+    m32 = make2d("fp32").train()
+    m16 = make2d("mixed").train()
+    m16.load_state_dict(m32.state_dict())
+    with torch.no_grad():
+        a = m32(x.float())    # strict fp32 FFMA kernels
+        b = m16(x)            # fp16 storage, tcgen05 fp32 accumulate
+    err = rel_l2(b, a)
+    agree = float(((a > 0) == (b > 0)).float().mean())
+    assert err <= 4e-2, err
+    assert agree >= 0.99, agree
+
+
+def test_fullsize_2d_gradients_are_linear_in_the_loss():
+    import hcunet_b200 as H
+
+    m = make2d("mixed").train()
+    x, mask, pwl = data2d()
+    sd = copy.deepcopy(m.state_dict())
+    grads = []
+    for scale in (1.0, 2.0):
+        m.load_state_dict(sd)
+        m.zero_grad(set_to_none=True)
+        loss = H.cross_entropy(m(x), mask, pwl, "pixel") * scale
+        loss.backward()
+        grads.append({k: p.grad.detach().clone() for k, p in m.named_parameters()})
+    for k in grads[0]:
+        g1, g2 = grads[0][k], grads[1][k]
+        if k.endswith(".bias") and (".conv1." in k or ".conv2." in k or ".up_conv." in k):
+            continue
+        assert torch.isfinite(g1).all(), k
+        assert rel_l2(g2, 2 * g1) <= 1e-4, (k, rel_l2(g2, 2 * g1))
