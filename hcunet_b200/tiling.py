@@ -20,9 +20,10 @@ from .engine import plan_unet
 from .parallel import shard_range
 
 
-def tile_geometry(spec: dict) -> Tuple[int, int, int]:
-    """(align, margin_xy, margin_z): outputs at multiples of ``align`` need ``margin_xy`` more input voxels per XY
-    dim; the logits are ``margin_z`` shorter than the input in Z.  Derived from the planner, not hard-coded."""
+def _geometry(spec: dict) -> Tuple[int, int, int, int]:
+    """(align, margin_xy, margin_z, residue): an XY input extent ``n`` with ``n % align == residue`` loses no voxel to a
+    pooling floor at any level, and then the logits are exactly ``n - margin_xy`` wide (README model: 16, 184, 5, 12 --
+    SURVEY.md section 8d "in = 16 b + 124").  Derived from the planner, not hard-coded."""
     dims = spec["image_dimensions"]
     pool = spec["max_pool_kernel"]
     pool = (pool,) * dims if isinstance(pool, int) else tuple(pool)
@@ -32,25 +33,49 @@ def tile_geometry(spec: dict) -> Tuple[int, int, int]:
     if pool[0] != pool[1] or stride[0] != stride[1] or pool[0] != stride[0]:
         raise NotImplementedError("tiling needs equal pooling / up-sampling strides in X and Y")
     align = pool[0] ** levels
-    # find a consistent size: in = align * b + r  ->  out = in - margin
-    base = None
+    zin = 8 * 4
+
+    def out_of(n):
+        shape = (1, spec["in_channels"], n, n) + ((zin,) if dims == 3 else ())
+        try:
+            return plan_unet(spec, shape).out_sz
+        except RuntimeError:
+            return None
+
+    # The margin n - out(n) is smallest on the residue class where no pooling level floors; every other class loses voxels.
+    best = None
     for n in range(align * 8, align * 40):
-        try:
-            shape = (1, spec["in_channels"], n, n) + ((8 * 4,) if dims == 3 else ())
-            p = plan_unet(spec, shape)
-        except RuntimeError:
+        o, o2 = out_of(n), out_of(n + align)
+        if o is None or o2 is None or o2[0] - o[0] != align:
             continue
-        try:
-            p2 = plan_unet(spec, shape[:2] + (n + align, n + align) + shape[4:])
-        except RuntimeError:
-            continue
-        if p2.out_sz[0] - p.out_sz[0] == align:
-            base = (n, p.out_sz[0], p.out_sz[2] if dims == 3 else 1, shape[4] if dims == 3 else 1)
-            break
-    if base is None:
+        m = n - o[0]
+        if best is None or m < best[1]:
+            best = (n % align, m, (zin - o[2]) if dims == 3 else 0)
+    if best is None:
         raise RuntimeError("could not find a tile size the model accepts")
-    n, out, oz, iz = base
-    return align, n - out, iz - oz
+    return align, best[1], best[2], best[0]
+
+
+def tile_geometry(spec: dict) -> Tuple[int, int, int]:
+    """(align, margin_xy, margin_z): outputs at multiples of ``align`` need ``margin_xy`` more input voxels per XY
+    dim; the logits are ``margin_z`` shorter than the input in Z."""
+    return _geometry(spec)[:3]
+
+
+def tile_input_extent(spec: dict, want_out: int, avail: int) -> int:
+    """Smallest XY input extent that yields >= ``want_out`` logit rows without a pooling floor, at most ``avail``."""
+    align, margin, _, res = _geometry(spec)
+    n = want_out + margin
+    n += (res - n) % align
+    while n > avail:
+        n -= align
+    return n
+
+
+def tiled_output_extent(spec: dict, x: int) -> int:
+    """Logit rows an XY stack extent ``x`` produces under tiling (the largest floor-free input extent minus the margin)."""
+    align, margin, _, res = _geometry(spec)
+    return x - ((x - res) % align) - margin
 
 
 def tile_grid(out_xy: Tuple[int, int], tile_out: int, align: int) -> List[Tuple[int, int, int, int]]:
@@ -82,9 +107,11 @@ def predict_tiled(model, stack: torch.Tensor, tile_out: int = 256, world: int = 
         raise RuntimeError("tiled inference needs model.eval(): batch statistics differ per tile")
     align, margin, mz = tile_geometry(spec)
     X, Y, Z = stack.shape[2:]
-    # only whole `align` blocks are produced: a caller with a ragged stack pads it first (the reference pads every
-    # stack with reflections before tiling, `segment.py:70`)
-    ox, oy = (X - margin) // align * align, (Y - margin) // align * align
+    # A tile's input extent must sit on the residue class where no pooling level floors (README model: 16 b + 124), so an
+    # interior tile reads a few voxels more than tile_out + margin and the surplus logit rows (identical to the
+    # neighbour's first rows) are dropped.  A ragged stack produces the rows its largest floor-free extent allows; the
+    # reference pads every stack with reflections before tiling (`segment.py:70`).
+    ox, oy = tiled_output_extent(spec, X), tiled_output_extent(spec, Y)
     if ox <= 0 or oy <= 0:
         raise RuntimeError(f"stack {tuple(stack.shape)} is smaller than the receptive field ({margin} + {align})")
     device = device or next(model.parameters()).device
@@ -92,6 +119,9 @@ def predict_tiled(model, stack: torch.Tensor, tile_out: int = 256, world: int = 
     if out is None:
         out = torch.zeros((1, spec["out_channels"], ox, oy, Z - mz), dtype=torch.float32, device=device)
     for (x0, x1, y0, y1) in tiles:
-        xin = stack[:, :, x0:x1 + margin, y0:y1 + margin, :]
-        out[:, :, x0:x1, y0:y1] = model(xin.to(device, non_blocking=True))
+        nx = tile_input_extent(spec, x1 - x0, X - x0)
+        ny = tile_input_extent(spec, y1 - y0, Y - y0)
+        xin = stack[:, :, x0:x0 + nx, y0:y0 + ny, :]
+        logits = model(xin.to(device, non_blocking=True))
+        out[:, :, x0:x1, y0:y1] = logits[:, :, : x1 - x0, : y1 - y0]
     return out, tiles

