@@ -79,7 +79,8 @@ struct Params {
   int ks;        // this descriptor runs on conv_ks_kernel
   int PC, NCH;   // channel planes per A stage / B tile, chunks = P / PC
   int RA, RB;    // ring depths of the A stages and the B tiles
-  int BT;        // bytes of one B tile = PC * Nc * 16
+  int BT;        // bytes of one B tile (one tap of one chunk) = PC * Nc * 16
+  int TB;        // B tiles (consecutive taps of a chunk) per ring slot / barrier round
   int n_last;    // flat positions of one x-plane that hold outputs (all images stacked: rows = N * Yv)
 };
 
@@ -1088,27 +1089,29 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
       tc_fence_after();
       const uint32_t abase = (a_base + (uint32_t)(sa * p.SLOT)) >> 4;
       int ty = 0, tz = 0;
-      for (int t = 0; t < KYZ; ++t) {
+      for (int t = 0; t < KYZ; t += p.TB) {
         mbar_wait(bar_fb + 8 * sb, pb);
         tc_fence_after();
-        const uint32_t bbase = (b_base + (uint32_t)(sb * p.BT)) >> 4;
-        const uint32_t tap = (uint32_t)(ty * p.dy * p.Zv + tz * p.dz);  // pixels == 16-byte units
-        for (int k = 0; k < PC / 2; ++k) {
-          const uint64_t ad = desc_hi | (uint64_t)((abase + tap + (uint32_t)k * kstep_a) | lbo_a);
-          const uint64_t bd = desc_hi | (uint64_t)((bbase + (uint32_t)k * kstep_b) | lbo_b);
-          if (elect_one()) {
-            umma_f16(tmem_base, ad, bd, idesc, acc);
-            if (MB > 1) umma_f16(tmem_base + (uint32_t)Nc, ad + 128u, bd, idesc, acc);
-            if (MB > 2) umma_f16(tmem_base + (uint32_t)(2 * Nc), ad + 256u, bd, idesc, acc);
-            if (MB > 3) umma_f16(tmem_base + (uint32_t)(3 * Nc), ad + 384u, bd, idesc, acc);
+        for (int tt = 0; tt < p.TB; ++tt) {
+          const uint32_t bbase = (b_base + (uint32_t)((sb * p.TB + tt) * p.BT)) >> 4;
+          const uint32_t tap = (uint32_t)(ty * p.dy * p.Zv + tz * p.dz);  // pixels == 16-byte units
+          for (int k = 0; k < PC / 2; ++k) {
+            const uint64_t ad = desc_hi | (uint64_t)((abase + tap + (uint32_t)k * kstep_a) | lbo_a);
+            const uint64_t bd = desc_hi | (uint64_t)((bbase + (uint32_t)k * kstep_b) | lbo_b);
+            if (elect_one()) {
+              umma_f16(tmem_base, ad, bd, idesc, acc);
+              if (MB > 1) umma_f16(tmem_base + (uint32_t)Nc, ad + 128u, bd, idesc, acc);
+              if (MB > 2) umma_f16(tmem_base + (uint32_t)(2 * Nc), ad + 256u, bd, idesc, acc);
+              if (MB > 3) umma_f16(tmem_base + (uint32_t)(3 * Nc), ad + 384u, bd, idesc, acc);
+            }
+            __syncwarp();
+            acc = 1u;
           }
-          __syncwarp();
-          acc = 1u;
+          if (++tz == p.KZ) { tz = 0; ++ty; }
         }
-        if (elect_one()) umma_commit(bar_eb + 8 * sb);  // this B tile is consumed
+        if (elect_one()) umma_commit(bar_eb + 8 * sb);  // these B tiles are consumed
         __syncwarp();
         if (++sb == RB) { sb = 0; pb ^= 1; }
-        if (++tz == p.KZ) { tz = 0; ++ty; }
       }
       if (elect_one()) umma_commit(bar_ea + 8 * sa);    // this A stage is consumed
       __syncwarp();
@@ -1125,10 +1128,12 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
       uint32_t pb = 1;
       for (int tx = 0; tx < p.KX; ++tx)
         for (int c = 0; c < p.NCH; ++c)
-          for (int t = 0; t < KYZ; ++t) {
+          for (int t = 0; t < KYZ; t += p.TB) {
             mbar_wait(bar_eb + 8 * sb, pb);
-            mbar_expect_tx(bar_fb + 8 * sb, bt);
-            bulk_g2s(b_base + (uint32_t)sb * bt, wsrc + ((size_t)(tx * p.E_tx + t * p.P + c * PC)) * Nc * 16, bt, bar_fb + 8 * sb);
+            mbar_expect_tx(bar_fb + 8 * sb, bt * (uint32_t)p.TB);
+            for (int tt = 0; tt < p.TB; ++tt)
+              bulk_g2s(b_base + (uint32_t)(sb * p.TB + tt) * bt, wsrc + ((size_t)(tx * p.E_tx + (t + tt) * p.P + c * PC)) * Nc * 16, bt,
+                       bar_fb + 8 * sb);
             if (++sb == RB) { sb = 0; pb ^= 1; }
           }
     }
@@ -1153,43 +1158,36 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
     __half* obase = reinterpret_cast<__half*>(p.out) + p.out_base + (long long)ox * p.out_sx + p.out_c_off;
     mbar_wait(bar_t, 0);
     tc_fence_after();
+    // column chunk outermost: the per-channel sums of the MB M-blocks are added per thread first, ONE shuffle reduction
+    // per 16 columns (it was one per M-block: the reductions were most of the epilogue's instructions)
 #pragma unroll 1
-    for (int mb = 0; mb < MB; ++mb) {
-      const bool valid = poff[mb] >= 0;
+    for (int cc = 0; cc < nch; cc += 16) {
+      float s1[16], s2[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+      float bs[16], oa[16], ob[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { bs[j] = sbias[cc + j]; oa[j] = sbias[Nc + cc + j]; ob[j] = sbias[2 * Nc + cc + j]; }
 #pragma unroll 1
-      for (int cc = 0; cc < nch; cc += 16) {
+      for (int mb = 0; mb < MB; ++mb) {
+        const bool valid = poff[mb] >= 0;
         float v[16];
         tmem_ld16(tmem_base + lane_base + (uint32_t)(mb * Nc + cc), v);
         if (has_bias) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(&sbias[cc + j]);
-            v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-          }
+          for (int j = 0; j < 16; ++j) v[j] += bs[j];
         }
-        if (do_stats) {
-          float s1[16], s2[16];
+        if (do_stats && valid) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            s1[j] = valid ? v[j] : 0.f;
-            s2[j] = s1[j] * s1[j];
-          }
-          const float r1 = reduce16(s1, lane);
-          const float r2 = reduce16(s2, lane);
-          if ((lane & 1) == 0) {
-            sstat[warp * 2 * Nc + cc + (lane >> 1)] += r1;   // this lane is the slot's only writer
-            sstat[warp * 2 * Nc + Nc + cc + (lane >> 1)] += r2;
+            s1[j] += v[j];
+            s2[j] = fmaf(v[j], v[j], s2[j]);
           }
         }
         if (valid) {
           if (affine) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 a = *reinterpret_cast<const float4*>(&sbias[Nc + cc + j]);
-              const float4 b = *reinterpret_cast<const float4*>(&sbias[2 * Nc + cc + j]);
-              v[j] = fmaf(v[j], a.x, b.x); v[j + 1] = fmaf(v[j + 1], a.y, b.y);
-              v[j + 2] = fmaf(v[j + 2], a.z, b.z); v[j + 3] = fmaf(v[j + 3], a.w, b.w);
-            }
+            for (int j = 0; j < 16; ++j) v[j] = fmaf(v[j], oa[j], ob[j]);
           }
           if (out_relu) {
 #pragma unroll
@@ -1217,6 +1215,14 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
             *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(&h[0]);
             if (cc + 8 < nch) *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<uint4*>(&h[4]);
           }
+        }
+      }
+      if (do_stats) {
+        const float r1 = reduce16(s1, lane);
+        const float r2 = reduce16(s2, lane);
+        if ((lane & 1) == 0) {
+          sstat[warp * 2 * Nc + cc + (lane >> 1)] = r1;   // this lane is the slot's only writer
+          sstat[warp * 2 * Nc + Nc + cc + (lane >> 1)] = r2;
         }
       }
     }
@@ -1589,6 +1595,9 @@ static const char* configure_ks(const HcuConvDesc* d, Params& p) {
         if (P % pc != 0 || (f_pc && pc != f_pc)) continue;
         const int bt = pc * nc * 16;
         if (bt > 32768) continue;
+        // one barrier round per filter row of a chunk (KZ taps) while the slot stays <= 24 KB: fewer, larger rounds
+        const int tb = (p.KZ > 1 && p.KZ * bt <= 24576) ? p.KZ : 1;
+        const int bslot = tb * bt;
         int ps = run * 16;
         { const int g = pc >= 8 ? 16 : 128 / pc; ps = round_up(ps, 2 * g) + g; }
         if ((ps >> 4) > 0x3fff) continue;
@@ -1603,13 +1612,13 @@ static const char* configure_ks(const HcuConvDesc* d, Params& p) {
         for (int ra = 3; ra >= 2; --ra) {
           for (int rb = 8; rb >= 2; --rb) {
             if ((f_ra && ra != f_ra) || (f_rb && rb != f_rb)) continue;
-            const int off_a = round_up(rb * bt, 128);
+            const int off_a = round_up(rb * bslot, 128);
             const int off_tab = off_a + ra * slot;
             const int off_bar = round_up(off_tab + run * 4, 8);
             const int off_stat = round_up(off_bar + 8 * (2 * ra + 2 * rb + 1) + 8, 16);
             const int total = off_stat + 11 * nc * 4 + 128;
             if (total > kSmemLimit) continue;
-            const double score = 2.0 * (ra - 1) + std::min(1.0, (double)(rb - 1) * bt / 65536.0) - 1e-7 * total;
+            const double score = 2.0 * (ra - 1) + std::min(1.0, (double)(rb - 1) * bslot / 65536.0) - 1e-7 * total;
             if (score > best_score) {
               best_score = score; best_ra = ra; best_rb = rb; best_total = total;
               offs[0] = off_a; offs[1] = off_tab; offs[2] = off_bar; offs[3] = off_stat;
@@ -1623,20 +1632,20 @@ static const char* configure_ks(const HcuConvDesc* d, Params& p) {
           const int nch = P / pc;
           // one M = 128, K = 16 MMA: shared-memory operand fetch (32 + N/4 clk, profiles/r01_umma_rate.txt) vs tensor rate
           // (N/2 clk), times a measured efficiency of the issue / barrier machinery per column-chunk width (2D U-Net 256- and
-          // 512-channel levels: (M, Nc) = (256, 256) runs at 730 TFLOP/s, (512, 128) at 620 - 645, (256, 128) at 510 - 520)
-          const double mma1 = std::max(32.0 + nc / 4.0, nc / 2.0) * (nc >= 256 ? 1.0 : nc >= 128 ? 1.18 : 1.35);
+          // 512-channel levels: (M, Nc) = (256, 256) runs at 730 TFLOP/s = 174 clk per MMA, (512, 128) at 620 - 645 = 100 clk, (256, 128) at 510 - 520)
+          const double mma1 = std::max(32.0 + nc / 4.0, nc / 2.0) * (nc >= 256 ? 1.36 : nc >= 128 ? 1.56 : 1.8);
           const double t_mma = (double)p.KX * nch * KYZ * (pc / 2) * MB * mma1;
           const double bytes = (double)p.KX * nch * ((double)run * pc * 16 + (double)KYZ * bt);
-          const double t_mem = bytes / 40.0;  // L2 -> shared memory per SM: 27 B/clk measured without being the limiter
+          const double t_mem = bytes / 28.0;  // L2 -> shared memory per SM: 27 B/clk measured on the (256, 256) tile
           const double t_cta = std::max(t_mma, t_mem) + 4000.0 + MB * (nc / 16) * 150.0 + (ra < 3 ? 0.10 * t_mma : 0.0) +
-                               ((rb - 1) * bt < 65536 ? 0.03 * t_mma : 0.0);
+                               ((rb - 1) * bslot < 65536 ? 0.03 * t_mma : 0.0);
           const long long n_runs = (n_last + M - 1) / M;
           const long long items = (long long)p.OX * n_runs * (npad / nc);
           const double cost = (double)((items + sms - 1) / sms) * t_cta;
           if (cost < best) {
             best = cost; found = true;
             b = p;
-            b.M = M; b.MB = MB; b.RUN = run; b.PS = ps; b.SLOT = slot; b.PC = pc; b.NCH = nch; b.RA = ra; b.RB = rb; b.BT = bt;
+            b.M = M; b.MB = MB; b.RUN = run; b.PS = ps; b.SLOT = slot; b.PC = pc; b.NCH = nch; b.RA = ra; b.RB = rb; b.BT = bt; b.TB = tb;
             b.R = ra; b.D = 1;
             b.Nc = nc; b.nsplit = npad / nc;
             b.off_w = off_w; b.off_a = off_a; b.off_tab = off_tab; b.off_bar = off_bar; b.off_stat = off_stat;

@@ -49,7 +49,7 @@ struct Params {
   // dy addressing (elements): image / x / y / z strides of the COARSE grid, stride-phase decomposition of the channel planes
   long long d_is, d_xs, d_ph[3];
   int d_ys, d_zs, dps[3], Pc_o;
-  int flat;        // 2D with short rows: all images stacked into ONE flat plane, the CTA marches over runs of M positions (OX = runs)
+  int flat;        // 2D: all images stacked into ONE flat plane, tap groups = filter rows, the CTA marches over runs: all images stacked into ONE flat plane, the CTA marches over runs of M positions (OX = runs)
   int n_cb, n_ob;  // channel blocks over CTAs: 128 input channels (16 planes) x Nc output channels each; P / Po = planes per block
   int n_runs, Lx, n_xseg;
   int in_relu, vec4;
@@ -236,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
     const size_t d_is = (size_t)p.d_is;
     // first position of this thread in step j: (image, virtual row, virtual column).  Normal mode: the run is fixed and the
     // step moves along x; flat mode: the step IS the run (x0 + j), positions run over the stacked images.
+    const int a_shift = flat ? p.tap_off[t_lo] : 0;  // flat: the group's filter row moves the staged window, not the taps
     auto first = [&](int step, int px0, int& im, int& yv, int& zv) {
       const int qf = (flat ? (x0 + step) * p.M : q0) + px0;
       const int r = qf / p.Zv;
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
         if (flat || (xm >= 0 && xm < p.IX)) {
           unsigned char* dp = smem + sa_f * p.SLOT + plane * p.PS + pix0 * 16;
           int im, yv, zv;
-          first(jf, pix0, im, yv, zv);
+          first(jf, pix0 + a_shift, im, yv, zv);
           for (int c = 0; c < nchunk; ++c) {
             const int ym = yv - p.py, zm = zv - p.pz;
             if (im < p.N && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ) {
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
           const __half* a_x = a_n + (size_t)(xok ? xm : 0) * a_xs;
           const uint32_t dst = a_base + (uint32_t)(sa_i * p.SLOT + plane * p.PS + pix0 * 16);
           int im, yv, zv;
-          first(j, pix0, im, yv, zv);
+          first(j, pix0 + a_shift, im, yv, zv);
           for (int c = 0; c < nchunk; ++c) {
             const int ym = yv - p.py, zm = zv - p.pz;
             const bool ok = xok && im < p.N && ym >= 0 && ym < p.IY && zm >= 0 && zm < p.IZ;
@@ -330,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
     const uint64_t a_hi = desc_hi_mn((uint32_t)p.PS), b_hi = desc_hi_mn((uint32_t)p.DPS);
     const uint32_t lbo = (128u >> 4) << 16;
     const int nchunks = p.M / 16;
+    const int a_shift_m = p.flat ? p.tap_off[t_lo] : 0;
     int wa = 0, wd = 0, next_a = 0;
     uint32_t pa = 0, pd = 0;
     int i_mod = 0;  // ring slot of a-plane i (the oldest plane output i needs)
@@ -344,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
       for (int t = t_lo; t < t_hi; ++t) {
         int sl = i_mod + (p.tap_tx[t] - txlo) * p.dx;
         sl -= sl >= R ? R : 0;
-        const uint32_t abase = (((a_base + (uint32_t)(sl * p.SLOT)) >> 4) + (uint32_t)p.tap_off[t]) | lbo;
+        const uint32_t abase = (((a_base + (uint32_t)(sl * p.SLOT)) >> 4) + (uint32_t)(p.tap_off[t] - a_shift_m)) | lbo;
         const uint32_t tcol = tmem_base + (uint32_t)((t - t_lo) * p.Nc);
         const uint32_t first = (uint32_t)i;  // accumulate flag of chunk 0: overwrite only on the CTA's first plane
         if (elect_one()) {
@@ -427,13 +429,16 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   p.N = d->batch;
   p.Cp = d->in_cpitch; p.P = P; p.cin = d->cin;
   p.Cop = d->out_cpitch; p.Po = Po; p.cout = d->cout;
-  // A 2D problem with SHORT image rows (the bottom levels of the classic U-Net: 12 .. 32 pixels) is re-read as one flat
-  // plane of rows x columns with all images of the batch stacked (rows = N * Yv): the filter rows become flat shifts too
-  // and the CTA marches over consecutive RUNS of M positions (the "x" axis of the kernel is the run index), instead of
-  // leaving most of an MMA's K = 16-pixel chunks empty (a 30-pixel row fills 23 % of a 128-position run).  Longer rows
-  // keep the row-by-row march: every staged run would carry 2 rows of halo.
-  const bool flat2d = d->in_size[2] == 1 && d->out_size[2] == 1 && d->taps[2] == 1 && d->pad[2] == 0 && d->dil[2] == 1 &&
-                      d->out_size[1] + (d->taps[1] - 1) * d->dil[1] < 40;
+  // A 2D problem is re-read as one flat plane of rows x columns with all images of the batch stacked (rows = N * Yv): a
+  // filter row becomes a flat shift of Zv positions, the CTA marches over consecutive RUNS of M positions (the kernel's
+  // "x" axis is the run index) and every 16-pixel K chunk of an MMA is full, instead of one image row per step (a
+  // 30-pixel row of the classic U-Net's bottom levels fills 12 % of a 256-position run, a 138-pixel row 54 %).  The tap
+  // groups are whole filter rows: the group's row only moves the staged window, so a run carries KZ - 1 positions of halo.
+  static int flat_on = -1;
+  if (flat_on < 0) { const char* e = getenv("HCU_WG5_FLAT"); flat_on = e ? atoi(e) : 1; }
+  const int nc_blk = (Pot / Po) > 1 ? Po * 8 : round_up(d->cout, 16);
+  const bool flat2d = flat_on && d->in_size[2] == 1 && d->out_size[2] == 1 && d->taps[2] == 1 && d->pad[2] == 0 && d->dil[2] == 1 &&
+                      nc_blk <= 256 && 512 / nc_blk >= d->taps[1];
   p.flat = flat2d ? 1 : 0;
   {
     // dy (ophase: the `cout` channels are [nph][cout / nph], phase phi of coarse position o lives at o * s + phi of the
@@ -475,12 +480,19 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   }
   p.NG = (p.taps + p.TG - 1) / p.TG;
   p.TG = (p.taps + p.NG - 1) / p.NG;  // balance the groups
+  int flat_rpg = 1;
+  if (p.flat) {  // whole filter rows per group; several rows only while their halo stays small
+    flat_rpg = std::max(1, std::min(p.KY, (512 / p.Nc) / p.KZ));
+    if ((flat_rpg - 1) * p.dy_ * p.Zv + (p.KZ - 1) * p.dz > 64) flat_rpg = 1;
+    p.TG = flat_rpg * p.KZ;
+    p.NG = (p.KY + flat_rpg - 1) / flat_rpg;
+  }
   {
     int cols = p.TG * p.Nc, t = 32;
     while (t < cols) t <<= 1;
     p.tmem_cols = t;
   }
-  const int halo = (p.KY - 1) * p.dy_ * p.Zv + (p.KZ - 1) * p.dz;
+  const int halo = p.flat ? (flat_rpg - 1) * p.dy_ * p.Zv + (p.KZ - 1) * p.dz : (p.KY - 1) * p.dy_ * p.Zv + (p.KZ - 1) * p.dz;
   // flat: positions of the stacked images that hold outputs (the tail rows of the last image are never needed)
   const long long plane_qq = p.flat ? ((long long)(p.N - 1) * p.Yv + p.OY - 1) * p.Zv + p.OZ : (long long)p.Yv * p.Zv;
   if (plane_qq >= 0x3fffffffLL) return "plane too large";
@@ -494,8 +506,11 @@ static const char* configure(const HcuConvDesc* d, Params& p) {
   if (max_span > 8) return "x extent";
   const int m_cands[3] = {256, 128, 64};
   const int want[3] = {3, 2, 0};  // ring slack beyond the span: (look-ahead D, published slack) = (2,1), (1,1), (0,0)
-  for (int wi = 0; wi < 3; ++wi) {
-    for (int mi = 0; mi < 3; ++mi) {
+  // normal mode: deepest ring first, then the longest run; flat mode: the longest run that still gets a pipelined ring
+  for (int it = 0; it < 9; ++it) {
+    {
+      const int wi = p.flat ? it % 3 : it / 3, mi = p.flat ? it / 3 : it % 3;
+      if (p.flat && wi == 2 && mi < 2) continue;  // a synchronous ring only for the shortest run
       const int M = m_cands[mi];
       if (M > 64 && M / 2 >= plane_q) continue;
       const int run = M + halo;
