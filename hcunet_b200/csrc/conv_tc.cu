@@ -1596,7 +1596,9 @@ static const char* configure_ks(const HcuConvDesc* d, Params& p) {
         const int bt = pc * nc * 16;
         if (bt > 32768) continue;
         // one barrier round per filter row of a chunk (KZ taps) while the slot stays <= 24 KB: fewer, larger rounds
-        const int tb = (p.KZ > 1 && p.KZ * bt <= 24576) ? p.KZ : 1;
+        static int tb_on = -1;
+        if (tb_on < 0) { const char* e = getenv("HCU_KS_TB"); tb_on = e ? atoi(e) : 1; }
+        const int tb = (tb_on && p.KZ > 1 && p.KZ * bt <= 24576) ? p.KZ : 1;
         const int bslot = tb * bt;
         int ps = run * 16;
         { const int g = pc >= 8 ? 16 : 128 / pc; ps = round_up(ps, 2 * g) + g; }

@@ -15,7 +15,11 @@ want = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram_rd"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps_active%"),
         ("launch__registers_per_thread", "regs"), ("launch__shared_mem_per_block_dynamic", "smem/block"),
         ("launch__occupancy_limit_registers", "occ_lim_regs"), ("launch__occupancy_limit_shared_mem", "occ_lim_smem"),
-        ("launch__waves_per_multiprocessor", "waves")]
+        ("launch__waves_per_multiprocessor", "waves"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_active%"),
+        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
+        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex%"),
+        ("lts__t_sector_hit_rate.pct", "l2_hit%")]
 for r in rows[2:]:
     name = r[idx["Kernel Name"]].split("(")[0]
     print(f"{name}  grid {r[idx['Grid Size']]} block {r[idx['Block Size']]}")
