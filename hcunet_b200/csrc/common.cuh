@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "../../include/hcunet_b200.h"
 
@@ -157,6 +159,38 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv& f) { return 
 __device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv& f, uint32_t& q, uint32_t& r) {
   q = fdiv(n, f);
   r = n - q * f.d;
+}
+
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
+// A kernel launched with launch_pdl() may START while its predecessor in the stream is still running: everything it does
+// before pdl_wait() (barrier init, TMEM allocation, index tables built from the kernel parameters -- no global memory) overlaps
+// the predecessor's tail; pdl_wait() returns once the predecessor grid has completed and its writes are visible.  Every such
+// kernel calls pdl_launch_dependents() only AFTER its own pdl_wait(): by induction everything older than the immediate
+// predecessor is complete when a kernel starts.  Works inside CUDA-graph capture (programmatic dependency edges).
+// Without the launch attribute pdl_wait() is a no-op.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// HCU_PDL is a bit mask: 1 = the tensor-core conv kernels (default), 2 = the BatchNorm-backward / max-pool kernels.
+// Measured on the bench step (README 3D model, CUDA graph): convs only 3.19 -> 3.13 ms; with the memory-bound kernels as
+// well 3.26 ms -- their early-resident CTAs spin in pdl_wait() on slots the side stream's weight-gradient CTAs would use.
+inline int pdl_mask() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("HCU_PDL"); on = e ? atoi(e) : 1; }
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_mask() & cls) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 inline int num_sms() {

@@ -392,14 +392,18 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     }
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
-    if (lane == 0) {
-      const uint32_t wbytes = (uint32_t)p.E * Nc * 16u;
-      mbar_expect_tx(bar_w, wbytes);
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) + (size_t)ns * wbytes;
-      for (uint32_t o = 0; o < wbytes; o += 32768u) bulk_g2s(w_base + o, src + o, min(32768u, wbytes - o), bar_w);
-    }
   }
   for (int i = threadIdx.x; i < 8 * Nc; i += kThreads) sstat[i] = 0.f;
+  // ---- everything above touched no global memory: it overlapped the previous kernel's tail (PDL) ----
+  pdl_wait();
+  pdl_launch_dependents();
+  if (warp == 8 && lane == 0) {
+    const uint32_t wbytes = (uint32_t)p.E * Nc * 16u;
+    fence_barrier_init();
+    mbar_expect_tx(bar_w, wbytes);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.wp) + (size_t)ns * wbytes;
+    for (uint32_t o = 0; o < wbytes; o += 32768u) bulk_g2s(w_base + o, src + o, min(32768u, wbytes - o), bar_w);
+  }
   for (int i = threadIdx.x; i < Nc; i += kThreads) {
     const int ch = (blockIdx.x % p.nsplit) * Nc + i;  // ns
     const bool in = ch < p.cout;
@@ -992,13 +996,6 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
     tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   }
   for (int i = threadIdx.x; i < 8 * Nc; i += kKsThreads) sstat[i] = 0.f;
-  for (int i = threadIdx.x; i < Nc; i += kKsThreads) {
-    const int ch = ns * Nc + i;
-    const bool in = ch < p.cout;
-    sbias[i] = (in && p.bias != nullptr) ? p.bias[ch % p.cpp] : 0.f;
-    sbias[Nc + i] = (in && p.out_scale != nullptr) ? p.out_scale[ch] : 1.f;
-    sbias[2 * Nc + i] = (in && p.out_shift != nullptr) ? p.out_shift[ch] : 0.f;
-  }
   for (int i = threadIdx.x; i < p.RUN; i += kKsThreads) {
     const int v = q0 + i;
     const int r = v / p.Zv, vz = v - r * p.Zv;
@@ -1006,6 +1003,16 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
     const int iy = vy - p.py, iz = vz - p.pz;
     const bool ok = nn < p.N && iy >= 0 && iy < p.IY && iz >= 0 && iz < p.IZ;
     soff[i] = ok ? (int)(nn * p.in_ns) + iy * p.in_ys + iz * p.in_zs : -1;
+  }
+  // ---- everything above touched no global memory: it overlapped the previous kernel's tail (PDL) ----
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int i = threadIdx.x; i < Nc; i += kKsThreads) {
+    const int ch = ns * Nc + i;
+    const bool in = ch < p.cout;
+    sbias[i] = (in && p.bias != nullptr) ? p.bias[ch % p.cpp] : 0.f;
+    sbias[Nc + i] = (in && p.out_scale != nullptr) ? p.out_scale[ch] : 1.f;
+    sbias[2 * Nc + i] = (in && p.out_shift != nullptr) ? p.out_shift[ch] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -1856,7 +1863,7 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
     if (p.debug & 8)
       fprintf(stderr, "conv_ks: grid %lld smem %d tmem %d M %d Nc %d PC %d RA %d RB %d runs %d\n", grid, p.smem_bytes, p.tmem_cols, p.M,
               p.Nc, p.PC, p.RA, p.RB, p.n_runs);
-    tc::conv_ks_kernel<<<(unsigned)grid, tc::kKsThreads, p.smem_bytes, (cudaStream_t)stream>>>(p);
+    launch_pdl(1, tc::conv_ks_kernel, dim3((unsigned)grid), dim3(tc::kKsThreads), (size_t)p.smem_bytes, (cudaStream_t)stream, p);
     HCU_CHECK_LAUNCH("conv_ks");
     return 0;
   }
@@ -1900,7 +1907,7 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
   p.n_xseg = (p.OX + p.Lx - 1) / p.Lx;
   const long long grid = base_items * p.n_xseg;
   HCU_CHECK_ARG(grid <= 0x7fffffffLL, "conv_tc_fwd: grid too large");
-  tc::conv_tc_kernel<<<(unsigned)grid, tc::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(p);
+  launch_pdl(1, tc::conv_tc_kernel, dim3((unsigned)grid), dim3(tc::kThreads), (size_t)p.smem_bytes, (cudaStream_t)stream, p);
   HCU_CHECK_LAUNCH("conv_tc");
   return 0;
 }

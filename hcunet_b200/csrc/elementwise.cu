@@ -332,6 +332,8 @@ __global__ void bn_relu_maxpool_h8_kernel(const __half* __restrict__ y, __half* 
                                           int py, int pz, const float* __restrict__ scale,
                                           const float* __restrict__ shift, int relu, FastDiv dc8, FastDiv doz, FastDiv doy,
                                           FastDiv dox, uint32_t total) {
+  pdl_wait();  // PDL: the launch overlapped the previous kernel's tail; nothing above touched global memory
+  pdl_launch_dependents();
   for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     uint32_t r, ucg, uz, uy, ux, ub;
     fdivmod(e, dc8, r, ucg);
@@ -488,6 +490,8 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_stats_h8_kernel(const __half* _
   extern __shared__ float sh[];
   for (int i = threadIdx.x; i < 16 * c; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
+  pdl_wait();  // PDL: the launch overlapped the previous kernel's tail; nothing above touched global memory
+  pdl_launch_dependents();
   const int c8 = c >> 3, lc8 = __ffs(c8) - 1;  // c8 is a power of two (c8 | 256)
   const uint32_t total = (uint32_t)(npix * c8), stride = gridDim.x * blockDim.x;  // stride % c8 == 0
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,6 +583,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_h8_kernel(const __half* __re
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              int relu, const float* __restrict__ coef,
                                                              const uint8_t* __restrict__ argmax, PoolGeom pg) {
+  pdl_wait();  // PDL: the launch overlapped the previous kernel's tail; nothing above touched global memory
+  pdl_launch_dependents();
   const int c8 = c >> 3, lc8 = __ffs(c8) - 1;
   const uint32_t total = (uint32_t)(npix * c8), stride = gridDim.x * blockDim.x;
   uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -959,9 +965,9 @@ extern "C" int hcu_bn_relu_maxpool(const void* y, int32_t dtype_y, void* pooled,
       (((uintptr_t)argmax) & 7) == 0 && (scale == nullptr || (aligned16(scale) && aligned16(shift)))) {
     const long long work = (long long)n * (ix / px) * (iy / py) * (iz / pz) * (c / 8);
     HCU_CHECK_ARG(work < 0x7fffffffLL, "bn_relu_maxpool: more than 2^31 pooled vectors");
-    bn_relu_maxpool_h8_kernel<<<grid_for(work, 256, 16), 256, 0, st>>>(
-        (const __half*)y, (__half*)pooled, argmax, n, ix, iy, iz, c, px, py, pz, scale, shift, relu, make_fastdiv(c / 8),
-        make_fastdiv(iz / pz), make_fastdiv(iy / py), make_fastdiv(ix / px), (uint32_t)work);
+    launch_pdl(2, bn_relu_maxpool_h8_kernel, dim3(grid_for(work, 256, 16)), dim3(256), (size_t)0, st,
+               (const __half*)y, (__half*)pooled, argmax, n, ix, iy, iz, c, px, py, pz, scale, shift, relu, make_fastdiv(c / 8),
+               make_fastdiv(iz / pz), make_fastdiv(iy / py), make_fastdiv(ix / px), (uint32_t)work);
     HCU_CHECK_LAUNCH("bn_relu_maxpool_h8");
     return 0;
   }
@@ -1026,8 +1032,8 @@ static int bn_bwd_stats_impl(const void* da, int32_t dtype_da, const void* y, in
     memset(&f, 0, sizeof(f));
     if (fin != nullptr) f = *fin;
     const int grid = grid_for(npix * (c / 8), 256 * 4, 12);
-    bn_bwd_stats_h8_kernel<<<grid, 256, 16 * c * sizeof(float), (cudaStream_t)stream>>>(
-        (const __half*)da, (const __half*)y, npix, c, scale, shift, mean, invstd, relu, argmax, pg, sums, f);
+    launch_pdl(2, bn_bwd_stats_h8_kernel, dim3(grid), dim3(256), 16 * c * sizeof(float), (cudaStream_t)stream,
+               (const __half*)da, (const __half*)y, npix, c, scale, shift, mean, invstd, relu, argmax, pg, sums, f);
     HCU_CHECK_LAUNCH("bn_bwd_stats_h8");
     return 0;
   }
@@ -1085,8 +1091,8 @@ extern "C" int hcu_bn_bwd_apply(const void* da, int32_t dtype_da, const void* y,
     PoolGeom pg = {};
     if (argmax != nullptr) { int rc = fill_pool(pool, npix, pg, "bn_bwd_apply"); if (rc) return rc; }
     const int grid = grid_for(npix * (c / 8), 256 * 2, 16);
-    bn_bwd_apply_h8_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)da, (const __half*)y, (__half*)dy, npix, c,
-                                                                   scale, shift, relu, coef, argmax, pg);
+    launch_pdl(2, bn_bwd_apply_h8_kernel, dim3(grid), dim3(256), (size_t)0, (cudaStream_t)stream, (const __half*)da, (const __half*)y,
+               (__half*)dy, npix, c, scale, shift, relu, coef, argmax, pg);
     HCU_CHECK_LAUNCH("bn_bwd_apply_h8");
     return 0;
   }
