@@ -121,3 +121,55 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle|oracle/", src, flags=re.M), \
                     f"{f} reaches into oracle/"
+
+
+def test_every_conv_of_the_baseline_configs_gets_a_tensor_core_kernel():
+    """Host-only routing check (no GPU): every convolution / data gradient / weight gradient of BASELINE.json configs[1]
+    (README 3D model) and configs[2] (classic 2D U-Net, 572x572x3, batch 16) is taken by a tensor-core kernel -- the
+    64..1024-channel levels of the 2D model by the K-streamed one -- and no layer falls back to the FFMA kernels."""
+    import ctypes as C
+
+    from hcunet_b200 import _lib
+    from hcunet_b200.engine import ConvGeom, conv_desc, plan_unet
+    import hcunet_b200 as H
+
+    lib = _lib.load()
+
+    def describe(d):
+        buf = C.create_string_buffer(256)
+        assert lib.hcu_conv_tc_describe(C.byref(d), buf, 256) == 0
+        return buf.value.decode()
+
+    readme = dict(image_dimensions=3, in_channels=4, out_channels=1, feature_sizes=[8, 16, 32, 64, 128],
+                  kernel={"conv1": (3, 3, 2), "conv2": (3, 3, 1)}, upsample_kernel=(2, 2, 2), max_pool_kernel=(2, 2, 1),
+                  upsample_stride=(2, 2, 1), dilation=1, groups=1)
+    cases = [(H.Unet_Constructor(**readme).model_specification, (4, 4, 256, 256, 32)),
+             (H.Unet_Constructor().model_specification, (16, 3, 572, 572))]
+    kinds = set()
+    for spec, shape in cases:
+        plan = plan_unet(spec, shape)
+        for g in plan.steps:
+            if not isinstance(g, ConvGeom) or g.name == "out_conv":   # the 1x1 logits conv has its own fp32-output descriptors
+                continue
+            cpi, cpo = max(8, g.cin_t), max(8, g.cout_t)
+            d = conv_desc(_lib.F16, _lib.F16, plan.batch, g.in_sz, cpi, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, cpo, 0,
+                          g.cout_g, g.groups, g.taps, g.dil)
+            pad = tuple((g.taps[i] - 1) * g.dil[i] for i in range(3))
+            dd = conv_desc(_lib.F16, _lib.F16, plan.batch, g.out_sz, cpo, 0, g.cout_g, g.cout_g, g.in_sz, g.in_sz, cpi, 0,
+                           g.cin_g, g.groups, g.taps, g.dil, pad=pad)
+            for what, desc in (("fwd", d), ("dgrad", dd)):
+                text = describe(desc)
+                assert text.startswith(("classic ", "ks ")), (g.name, what, text)
+                kinds.add(text.split()[0])
+                if g.cin_t >= 256 and what == "fwd":
+                    assert text.startswith("ks "), (g.name, text)     # neither the weights nor an x-plane fit otherwise
+            wg = lib.hcu_conv_wgrad_tc5_supported(C.byref(d)) or lib.hcu_conv_wgrad_ws_supported(C.byref(d)) or \
+                lib.hcu_conv_wgrad_tc_supported(C.byref(d))
+            assert wg, g.name
+    assert kinds == {"classic", "ks"}
+    # the kernel hint and the forced tile are honoured
+    d = conv_desc(_lib.F16, _lib.F16, 16, (66, 66, 1), 256, 0, 256, 256, (64, 64, 1), (64, 64, 1), 256, 0, 256, 1, (3, 3, 1))
+    d.reserved[0], d.reserved[1] = 2, 2 | (256 << 8) | (4 << 20)
+    assert describe(d).startswith("ks M=256 Nc=256 nsplit=1 PC=4")
+    d.reserved[0], d.reserved[1] = 1, 0
+    assert describe(d).startswith(("classic ", "unsupported"))
