@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 F32, BF16, F16 = 0, 1, 2
 BATCH_JOB_BYTES = 256
@@ -74,6 +74,7 @@ SIGNATURES = {
     "hcu_last_error": [],
     "hcu_launch_count": [],
     "hcu_zero": [P, C.c_size_t, P],
+    "hcu_h2d_tile": [P, I64, I64, I64, I64, I64, P, P],
     "hcu_conv_fwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
     "hcu_conv_tc_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_tc_describe": [C.POINTER(HcuConvDesc), C.c_char_p, I32],
@@ -180,7 +181,7 @@ def load():
     out._cdll = lib
     for name in SIGNATURES:
         raw = getattr(lib, name)
-        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_conv_tc_supported", "hcu_conv_wgrad_tc_supported", "hcu_conv_wgrad_tc5_supported", "hcu_conv_wgrad_ws_supported",
+        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_h2d_tile", "hcu_conv_tc_supported", "hcu_conv_wgrad_tc_supported", "hcu_conv_wgrad_tc5_supported", "hcu_conv_wgrad_ws_supported",
                                          "hcu_conv_tc_packed_bytes", "hcu_conv_tc_describe", "hcu_conv_tc_pack_batch_build", "hcu_weight_scatter_batch_build") else _wrap(name, raw))
     _lib = out
     return out

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 15
+#define HCU_ABI_VERSION 16
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -53,6 +53,15 @@ const char* hcu_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long hcu_launch_count(void);
 int hcu_zero(void* ptr, size_t bytes, void* stream);
+/* Strided host -> device copy of one overlap tile: a gather kernel reading the pinned (UVA-mapped) host memory in 16-byte
+ * units when everything is 16-byte aligned, else `planes` cudaMemcpy2DAsync calls; enqueued on `stream`.  Plane p
+ * is `rows` rows of `row_bytes` contiguous bytes, `src_row_pitch` bytes apart in (pinned) host memory, packed densely on
+ * the device; planes are `src_plane_pitch` bytes apart in the source.  For an NCDHW stack tile [C][nx][ny][Z] cut out of
+ * [C][X][Y][Z]: planes = C, rows = nx, row_bytes = ny*Z*esz, src_row_pitch = Y*Z*esz, src_plane_pitch = X*Y*Z*esz.
+ * Replaces the tile slice + `.to(device)` of the reference's tiler (segment.py:91), which materialises a contiguous copy
+ * of the tile on the host first. */
+int hcu_h2d_tile(const void* src, int64_t planes, int64_t src_plane_pitch, int64_t rows, int64_t src_row_pitch,
+                 int64_t row_bytes, void* dst, void* stream);
 
 /* ---- generic gather-convolution descriptor -------------------------------------------------
  * One launch computes, for every output position o = (n, ox, oy, oz) of an OX*OY*OZ grid and

@@ -151,6 +151,17 @@ def cfg5(args, dev):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    # the forward pass of one interior tile alone (input resident on the device)
+    x0, x1, y0, y1 = tiles[0]
+    nx, ny = tiling.tile_input_extent(model.model_specification, x1 - x0, X - x0), tiling.tile_input_extent(model.model_specification, y1 - y0, Y - y0)
+    xin = tiling._tile_to_device(stack, x0, nx, y0, ny, dev)
+    fw = []
+    with torch.no_grad():
+        for _ in range(4):
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(); model(xin); f1.record()
+            torch.cuda.synchronize()
+            fw.append(f0.elapsed_time(f1))
     ntiles_all = len(tiling.tile_grid(((X - margin) // align * align, (Y - margin) // align * align), args.tile_out, align))
     out_vox = sum((x1 - x0) * (y1 - y0) for x0, x1, y0, y1 in tiles) * (Z - mz)
     in_vox = sum((x1 - x0 + margin) * (y1 - y0 + margin) for x0, x1, y0, y1 in tiles) * Z
@@ -159,6 +170,8 @@ def cfg5(args, dev):
             "align": align, "margin": margin, "ms_this_rank": ms, "output_voxels_this_rank": out_vox,
             "input_voxels_this_rank": in_vox, "output_voxels_per_s": out_vox / (ms / 1e3),
             "input_voxels_per_s": in_vox / (ms / 1e3), "finite": bool(torch.isfinite(out).all()),
+            "tile_input": [4, nx, ny, Z], "tile_forward_ms": sorted(fw)[len(fw) // 2],
+            "tile_forward_input_voxels_per_s": nx * ny * Z / (sorted(fw)[len(fw) // 2] / 1e3),
             "whole_stack_seconds_at_world": ms / 1e3 * ntiles_all / max(1, len(tiles)) / args.world,
             "note": "tiles copied pinned host -> device inside the timed region; no inter-rank communication"}
     print(json.dumps(line))
