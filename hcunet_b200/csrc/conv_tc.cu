@@ -298,12 +298,12 @@ __device__ __forceinline__ uint4 bn_relu8(uint4 v, const BnH8& b, int relu) {
 
 // Per-channel statistics of a CTA (one slot per epilogue warp, added in a fixed order) -> the caller's binned fp64
 // accumulators, then the optional fused hcu_bn_finalize: the CTA that takes the last ticket sees every CTA's partial sums.
-// Called by the 128 epilogue threads (row = threadIdx.x < 128).
+// Called by the nthr epilogue threads (row = 0 .. nthr-1).
 template <typename PT>
-__device__ __forceinline__ void stats_tail(const PT& p, float* sstat, int row, int ns, int Nc) {
+__device__ __forceinline__ void stats_tail(const PT& p, float* sstat, int row, int ns, int Nc, int nthr = 128) {
   const int cout = p.cout;
-  named_bar_sync(1, 128);
-  for (int c = row; c < Nc; c += 128) {
+  named_bar_sync(1, nthr);
+  for (int c = row; c < Nc; c += nthr) {
     const int ch = ns * Nc + c;
     if (ch < cout) {
       double* sb = p.stats + (size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * p.stats_pitch;
@@ -315,13 +315,13 @@ __device__ __forceinline__ void stats_tail(const PT& p, float* sstat, int row, i
   }
   if (p.fin.counter != nullptr) {
     __threadfence();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, nthr);
     if (row == 0) sstat[0] = (atomicAdd(p.fin.counter, 1u) == gridDim.x - 1) ? 1.f : 0.f;
-    named_bar_sync(1, 128);
+    named_bar_sync(1, nthr);
     if (sstat[0] != 0.f) {
       __threadfence();
       const int pitch = p.stats_pitch;
-      for (int ch = row; ch < cout; ch += 128) {
+      for (int ch = row; ch < cout; ch += nthr) {
         double s1 = 0.0, s2 = 0.0;
         for (int b = 0; b < HCU_STAT_BINS; ++b) {
           s1 += __ldcg(&p.stats[(size_t)b * 2 * pitch + p.out_c_off + ch]);
@@ -1080,7 +1080,8 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
     }
     cp_async_wait<0>();
     finish(nstage - 1);
-  } else if (warp == 8) {
+  }
+  if (warp == 8) {
     // =========================================== MMA ISSUER ==========================================
     const uint32_t idesc = (1u << 4) | ((uint32_t)(Nc >> 3) << 17) | ((128u >> 4) << 24);  // f16 x f16 -> f32, K-major
     const uint64_t desc_hi = (uint64_t)((128u >> 4) | (1u << 14)) << 32;  // SBO = 128 B, descriptor version 1
@@ -1144,10 +1145,14 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
             if (++sb == RB) { sb = 0; pb ^= 1; }
           }
     }
-  } else {
+  }
+  if (warp < 8) {
     // =========================================== EPILOGUE ============================================
-    const int row = threadIdx.x;  // accumulator row within an M-block == TMEM lane
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // Warps 0-3 take the lower half of the CTA's column chunks; the producer warps 4-7 (done staging by now) the upper half:
+    // warp w reads TMEM lanes 32 * (w % 4) .. +31, so the two groups split the COLUMNS of the same accumulator rows.
+    const int row = threadIdx.x & 127;  // accumulator row within an M-block == TMEM lane
+    const int ewarp = warp & 3, half = warp >> 2;
+    const uint32_t lane_base = (uint32_t)(ewarp * 32) << 16;
     const bool do_stats = p.stats != nullptr;
     const bool affine = p.out_scale != nullptr;
     const bool has_bias = p.bias != nullptr;
@@ -1167,8 +1172,10 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
     tc_fence_after();
     // column chunk outermost: the per-channel sums of the MB M-blocks are added per thread first, ONE shuffle reduction
     // per 16 columns (it was one per M-block: the reductions were most of the epilogue's instructions)
+    const int nchunks16 = (nch + 15) >> 4, csplit = ((nchunks16 + 1) >> 1) << 4;
+    const int c_lo = half ? csplit : 0, c_hi = half ? nch : min(nch, csplit);
 #pragma unroll 1
-    for (int cc = 0; cc < nch; cc += 16) {
+    for (int cc = c_lo; cc < c_hi; cc += 16) {
       float s1[16], s2[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
@@ -1228,13 +1235,13 @@ __global__ void __launch_bounds__(kKsThreads, 1) conv_ks_kernel(const Params p) 
         const float r1 = reduce16(s1, lane);
         const float r2 = reduce16(s2, lane);
         if ((lane & 1) == 0) {
-          sstat[warp * 2 * Nc + cc + (lane >> 1)] = r1;   // this lane is the slot's only writer
-          sstat[warp * 2 * Nc + Nc + cc + (lane >> 1)] = r2;
+          sstat[ewarp * 2 * Nc + cc + (lane >> 1)] = r1;   // this lane is the slot's only writer
+          sstat[ewarp * 2 * Nc + Nc + cc + (lane >> 1)] = r2;
         }
       }
     }
     tc_fence_before();
-    if (do_stats) stats_tail(p, sstat, row, ns, Nc);
+    if (do_stats) stats_tail(p, sstat, (int)threadIdx.x, ns, Nc, 256);
   }
 
   // ---- teardown --------------------------------------------------------------------------------------

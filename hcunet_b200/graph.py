@@ -77,3 +77,33 @@ class GraphedTrainStep:
     def __call__(self, *tensors):
         self.load(*tensors)
         return self.run()
+
+
+class GraphedForward:
+    """Inference forward (`model.eval()`, no grad) of a fixed input shape as ONE CUDA-graph launch.
+
+    An eager eval forward of a 1 x 4 x 256 x 256 x 32 stack is ~60 launches of 5 .. 50 us each and is bound by the host
+    (1.5 ms); replayed from a graph it is bound by the kernels.  ``out = fwd(x)`` copies ``x`` (device or pinned host) into
+    the static input and returns the static output tensor (overwritten by the next call)."""
+
+    def __init__(self, model, example: torch.Tensor, warmup: int = 2):
+        if model.training:
+            raise RuntimeError("GraphedForward captures an eval-mode forward: call model.eval() first")
+        self.model = model
+        self.static_in = torch.empty_like(example, device=next(model.parameters()).device)
+        self.static_in.copy_(example)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                model(self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.out = model(self.static_in)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.out

@@ -28,7 +28,7 @@ README_3D = dict(image_dimensions=3, in_channels=4, out_channels=1, feature_size
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("config", choices=["cfg3", "cfg4", "cfg5"])
+    ap.add_argument("config", choices=["cfg1", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--world", type=int, default=8)
     ap.add_argument("--tile-out", type=int, default=512)
     ap.add_argument("--batch", type=int, default=None)
@@ -42,6 +42,8 @@ def main():
     torch.manual_seed(0)
     if args.config == "cfg5":
         return cfg5(args, dev)
+    if args.config == "cfg1":
+        return cfg1(args, dev)
     if args.config == "cfg3":
         B = args.batch or 16
         model = H.Unet_Constructor()   # the reference's defaults: 2D, in 3, out 2, features 32..1024, 3x3, up 2x2 stride 2
@@ -119,6 +121,60 @@ def main():
                 gbs = r["bytes"] / (r["ms"] * 1e6) if r["ms"] > 0 else 0
                 tfs = r["flops"] / (r["ms"] * 1e9) if r["ms"] > 0 else 0
                 f.write(f"{r['ms']:9.4f} ms  {r['calls']:5.1f}x  {gbs:8.1f} GB/s {tfs:8.2f} TF/s  {r['kernel']:28s} {r['layer']}\n")
+
+
+def cfg1(args, dev):
+    """BASELINE.json configs[0] (with the shape correction of SURVEY.md section 0.4): README 3D model, eval-mode forward of
+    one 1 x 4 x 256 x 256 x 32 stack (fp32 NCDHW in, fp32 logits 1 x 1 x 68 x 68 x 27 out), through model(x)."""
+    model = H.Unet_Constructor(**README_3D)
+    model.precision = args.precision
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((1, 4, 256, 256, 32), generator=g)
+    xh = x.pin_memory()
+    xd = x.to(dev)
+    with torch.no_grad():
+        model.train()
+        model(xd)           # populate the BatchNorm running statistics (SURVEY 8d, cfg1)
+        model.eval()
+        for _ in range(5):
+            y = model(xd)
+        torch.cuda.synchronize()
+        ts, te = [], []
+        for _ in range(20):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); y = model(xd); e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        for _ in range(20):   # end to end: pinned host input -> device, forward, logits back to the host
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); yh = model(xh.to(dev, non_blocking=True)).cpu(); e1.record()
+            torch.cuda.synchronize()
+            te.append(e0.elapsed_time(e1))
+    ms, mse = sorted(ts)[len(ts) // 2], sorted(te)[len(te) // 2]
+    from hcunet_b200.graph import GraphedForward
+    gf = GraphedForward(model, xd)
+    yg = gf(xd)
+    torch.cuda.synchronize()
+    same = bool(torch.equal(yg, y))
+    tg, tge = [], []
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); gf(xd); e1.record()
+        torch.cuda.synchronize()
+        tg.append(e0.elapsed_time(e1))
+    for _ in range(20):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); yh = gf(xh).cpu(); e1.record()
+        torch.cuda.synchronize()
+        tge.append(e0.elapsed_time(e1))
+    msg, msge = sorted(tg)[len(tg) // 2], sorted(tge)[len(tge) // 2]
+    nvox = 256 * 256 * 32
+    print(json.dumps({"config": "cfg1", "workload": "README 3D U-Net eval forward, 1x4x256x256x32", "precision": args.precision,
+                      "out_shape": list(y.shape), "ms_forward": ms, "voxels_per_s": nvox / (ms / 1e3), "ms_e2e": mse,
+                      "e2e_voxels_per_s": nvox / (mse / 1e3), "ms_forward_graph": msg, "graph_voxels_per_s": nvox / (msg / 1e3),
+                      "ms_e2e_graph": msge, "graph_equals_eager": same, "fwd_gflop": 10205 * nvox / 1e9,
+                      "finite": bool(torch.isfinite(y).all())}))
 
 
 def cfg5(args, dev):
