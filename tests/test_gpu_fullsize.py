@@ -220,3 +220,26 @@ def test_fullsize_2d_gradients_are_linear_in_the_loss():
             continue
         assert torch.isfinite(g1).all(), k
         assert rel_l2(g2, 2 * g1) <= 1e-4, (k, rel_l2(g2, 2 * g1))
+
+
+def test_fullsize_graphed_eval_forward_equals_eager():
+    """BASELINE.json configs[0]: eval-mode forward of one 1x4x256x256x32 stack; the CUDA-graph replay is bit-identical."""
+    from hcunet_b200.graph import GraphedForward
+
+    m = make("mixed")
+    x, _, _ = data()
+    x1 = x[:1].contiguous()
+    with torch.no_grad():
+        m.train()
+        m(x1)
+        m.eval()
+        eager = m(x1).clone()
+    assert eager.shape == (1, 1, 68, 68, 27)
+    with pytest.raises(RuntimeError):
+        GraphedForward(m.train(), x1)
+    gf = GraphedForward(m.eval(), x1)
+    assert torch.equal(gf(x1), eager)
+    other = x[1:2].contiguous()
+    with torch.no_grad():
+        want = m(other).clone()
+    assert torch.equal(gf(other.cpu().pin_memory()), want)    # pinned host input, new content
