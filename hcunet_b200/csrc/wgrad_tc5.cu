@@ -157,7 +157,11 @@ __device__ __forceinline__ uint64_t desc_hi_mn(uint32_t sbo_bytes) {
   return (uint64_t)(((sbo_bytes >> 4) & 0x3FFF) | (1u << 14)) << 32;  // SBO | descriptor version 1 (bit 46)
 }
 
-__global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) {
+// NPW = producer warps: 4 (288 threads, two CTAs per SM) or 8 (416 threads) for the configurations whose shared memory
+// leaves one CTA per SM anyway -- there the staging (cp.async + index arithmetic + BatchNorm in place) by 4 warps took as
+// long as the MMAs of a step (ncu: tensor pipe 13 % active, L2 25 %).
+template <int NPW>
+__global__ void __launch_bounds__(160 + 32 * NPW, NPW == 4 ? 2 : 1) wgrad_tc5_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int R = p.R, RD = p.RD;
@@ -184,10 +188,10 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
   const int span = (txhi - txlo) * p.dx + 1;   // a-planes one output plane needs
   const int nplanes = nout + span - 1;          // a-planes this CTA stages: virtual x = x0 + txlo*dx + j
 
-  if (warp == 8) {
+  if (warp == 4 + NPW) {
     if (lane == 0) {
-      for (int i = 0; i < R; ++i) { mbar_init(bar_fa + 8 * i, 4); mbar_init(bar_ea + 8 * i, 1); }
-      for (int i = 0; i < RD; ++i) { mbar_init(bar_fd + 8 * i, 4); mbar_init(bar_ed + 8 * i, 1); }
+      for (int i = 0; i < R; ++i) { mbar_init(bar_fa + 8 * i, NPW); mbar_init(bar_ea + 8 * i, 1); }
+      for (int i = 0; i < RD; ++i) { mbar_init(bar_fd + 8 * i, NPW); mbar_init(bar_ed + 8 * i, 1); }
       mbar_init(bar_done, 1);
       fence_barrier_init();
     }
@@ -199,11 +203,11 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= 4 && warp < 4 + NPW) {
     // =========================================== PRODUCERS ===========================================
     const int ptid = threadIdx.x - 128;
     // a: [P planes][RUN pixels]
-    const int plane = ptid % p.P, pix0 = ptid / p.P, pstep = 128 / p.P;
+    const int plane = ptid % p.P, pix0 = ptid / p.P, pstep = (32 * NPW) / p.P;
     const int nchunk = (p.RUN - pix0 + pstep - 1) / pstep;
     const bool xf = p.a_scale != nullptr;
     const int relu = p.in_relu;
@@ -218,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
     const size_t a_xs = flat ? 0 : (size_t)p.IY * p.IZ * p.Cp;
     const size_t a_is = (size_t)p.IY * p.IZ * p.Cp;   // flat: image stride (IX == 1)
     // dy: [Po planes][M pixels]
-    const int dplane = ptid % p.Po, dpix0 = ptid / p.Po, dstep = 128 / p.Po;
+    const int dplane = ptid % p.Po, dpix0 = ptid / p.Po, dstep = (32 * NPW) / p.Po;
     const int nchunk_d = (p.M - dpix0 + dstep - 1) / dstep;
     const int dystep = dstep / p.Zv, dzstep = dstep - dystep * p.Zv;
     // channel plane -> (stride phase, 8-channel group): a phase selects a sub-lattice of the full-resolution dy tensor
@@ -325,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
         finish(j);
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == 4 + NPW) {
     // =========================================== MMA ISSUER ==========================================
     const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.Nc >> 3) << 17) | ((128u >> 4) << 24);
     const uint64_t a_hi = desc_hi_mn((uint32_t)p.PS), b_hi = desc_hi_mn((uint32_t)p.DPS);
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 2) wgrad_tc5_kernel(const Params p) 
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 4 + NPW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -576,7 +580,8 @@ extern "C" int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const
   p.vec4 = (d->cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(wacc) & 15) == 0);
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(wg5::wgrad_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg5::kSmemLimit);
+    cudaError_t e = cudaFuncSetAttribute(wg5::wgrad_tc5_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg5::kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wg5::wgrad_tc5_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, wg5::kSmemLimit);
     if (e != cudaSuccess) { set_error("wgrad_tc5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
     attr = true;
   }
@@ -598,7 +603,12 @@ extern "C" int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const
   p.n_xseg = (p.OX + p.Lx - 1) / p.Lx;
   const long long grid = base_items * p.n_xseg;
   HCU_CHECK_ARG(grid <= 0x7fffffffLL, "wgrad_tc5: grid too large");
-  wg5::wgrad_tc5_kernel<<<(unsigned)grid, wg5::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(p);
+  static int npw8 = -1;
+  if (npw8 < 0) { const char* e = getenv("HCU_WG5_NPW8"); npw8 = e ? atoi(e) : 1; }
+  if (npw8 && per_sm == 1)   // one CTA per SM anyway: twice the producer warps
+    wg5::wgrad_tc5_kernel<8><<<(unsigned)grid, 160 + 32 * 8, p.smem_bytes, (cudaStream_t)stream>>>(p);
+  else
+    wg5::wgrad_tc5_kernel<4><<<(unsigned)grid, 160 + 32 * 4, p.smem_bytes, (cudaStream_t)stream>>>(p);
   HCU_CHECK_LAUNCH("wgrad_tc5");
   return 0;
 }
