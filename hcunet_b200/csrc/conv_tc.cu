@@ -1342,23 +1342,56 @@ __global__ void __launch_bounds__(256) pack_tc_batch_kernel(const unsigned char*
   const float* ref = params + J.ref_off;
   __half* out = reinterpret_cast<__half*>(packed + J.out_off);
   const long long base = (long long)(blockIdx.x - J.block0) * kPackPerBlock;
-  for (int k = threadIdx.x; k < kPackPerBlock; k += 256) {
-    const long long i = base + k;
+  // One thread per 16-byte output unit (8 consecutive input channels of one K8 slab row): the index decomposition -- a
+  // dozen 32-bit divisions -- is done once per unit instead of once per element (the per-element kernel took 0.63 ms per
+  // step for the 31 M parameters of the classic 2D U-Net: 100 G elements/s, instruction bound).
+  for (int k = threadIdx.x; k < kPackPerBlock / 8; k += 256) {
+    const long long i = base + 8 * k;
     if (i >= J.total) break;
-    const int j = (int)(i & 7);
     int nn, e, tx, ns;  // 32-bit index arithmetic: job sizes are < 2^31 (checked at build time)
     unpack_index((uint32_t)(i >> 3), J.KX, J.E_tx, J.Nc, J.wide, nn, e, tx, ns);
-    float v = 0.f;
-    if (e < J.KYZ * J.P) {
-      const int t = e / J.P, pl = e % J.P;
-      const int ci = pl * 8 + j, co = ns * J.Nc + nn;
-      if (ci < J.cin && co < J.cout) {
-        const long long idx = wm_index32(J.m, (uint32_t)(((tx * J.KYZ + t) * J.cin + ci) * J.cout + co));
-        v = ref[idx];
-        if (J.m.fold) v += ref[idx + J.m.fold_stride];
+    __half h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = __float2half_rn(0.f);
+    const int co = ns * J.Nc + nn;
+    if (e < J.KYZ * J.P && co < J.cout) {
+      const int t = e / J.P, pl = e - t * J.P;
+      // tap (tx, t) -> (jx, jy, jz) of the map; output channel b -> (phase, b) when the phases sit on the b side
+      const HcuWeightMap& m = J.m;
+      const int tl = tx * J.KYZ + t;
+      const int jz = tl % m.j[2], tq = tl / m.j[2];
+      const int jy = tq % m.j[1], jx = tq / m.j[1];
+      long long idx0 = m.base + (long long)(m.t0[0] + jx * m.tstep[0]) * m.st[0] + (long long)(m.t0[1] + jy * m.tstep[1]) * m.st[1] +
+                       (long long)(m.t0[2] + jz * m.tstep[2]) * m.st[2];
+      int b = co;
+      if (m.phase_on == 2) {
+        int phi = b / m.nb;
+        b -= phi * m.nb;
+        const int pz = phi % m.ph[2]; phi /= m.ph[2];
+        const int py = phi % m.ph[1], px = phi / m.ph[1];
+        idx0 += px * m.pst[0] + py * m.pst[1] + pz * m.pst[2];
+      }
+      idx0 += (long long)b * m.sb;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        int a = pl * 8 + j;
+        if (a < J.cin) {
+          long long idx = idx0;
+          if (m.phase_on == 1) {
+            int phi = a / m.na;
+            a -= phi * m.na;
+            const int pz = phi % m.ph[2]; phi /= m.ph[2];
+            const int py = phi % m.ph[1], px = phi / m.ph[1];
+            idx += px * m.pst[0] + py * m.pst[1] + pz * m.pst[2];
+          }
+          idx += (long long)a * m.sa;
+          float v = ref[idx];
+          if (m.fold) v += ref[idx + m.fold_stride];
+          h[j] = __float2half_rn(v);
+        }
       }
     }
-    out[i] = __float2half_rn(v);
+    *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(h);
   }
 }
 

@@ -195,6 +195,40 @@ def test_channel_rich_models_match_oracle(name):
     assert not bad, (bad, tol_grad)
 
 
+@pytest.mark.parametrize("name", sorted(CHANNEL_RICH) + ["readme_small"])
+def test_batched_weight_pack_equals_per_layer_pack(name):
+    """The first training steps pack every layer's weights with one launch per layer (`hcu_conv_tc_pack_ref`); once the
+    step cache is recorded ONE launch packs them all (`hcu_conv_tc_pack_batch`, one thread per 16-byte unit).  Same
+    weights, same input: the forward is bit-reproducible, so the logits must be identical; folded (`cat(x, x)`), flipped
+    (data gradient) and stride-phase (transposed conv) maps are all in these models."""
+    import hcunet_b200 as H
+
+    if name == "readme_small":
+        kwargs, xs, ms = dict(O.README_3D, feature_sizes=[8, 16, 32]), (2, 4, 60, 52, 6), (2, 1, 60, 52, 6)
+    else:
+        kwargs, xs, ms = CHANNEL_RICH[name]
+    torch.manual_seed(41)
+    m = H.Unet_Constructor(**kwargs)
+    m.precision = "mixed"
+    m = m.cuda().train()
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(xs, generator=g).cuda()
+    mask = (torch.rand(ms, generator=g) > 0.5).float().cuda()
+    pwl = torch.rand(ms, generator=g).cuda()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    outs = []
+    for _ in range(4):
+        m.load_state_dict(sd)          # same BatchNorm buffers for every pass
+        m.zero_grad(set_to_none=True)
+        logits = m(x)
+        H.cross_entropy(logits, mask, pwl, "pixel").backward()
+        outs.append((logits.detach().clone(), {k: p.grad.detach().clone() for k, p in m.named_parameters()}))
+    assert torch.equal(outs[0][0], outs[-1][0])
+    for k, g0 in outs[0][1].items():
+        if not is_dead_bias(k):
+            assert rel_l2(outs[-1][1][k], g0) <= 1e-5, k
+
+
 def test_too_small_and_bad_inputs_raise():
     import hcunet_b200 as H
 
