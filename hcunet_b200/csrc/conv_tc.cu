@@ -1477,9 +1477,9 @@ static const char* configure_classic(const HcuConvDesc* d, Params& p) {
   // operand (profiles/r01_umma_rate.txt), which this mode does once per input plane instead of once per (plane, tx)
   const bool can_wide = wide_on && p.KX >= 2 && p.KX <= 3 && p.dx == 1;
   const bool small_wide = can_wide && npad <= 32;  // the byte-bound levels: insist on the wide mode
-  auto search = [&](int pass) -> bool {
+  auto search = [&](int pass, bool full_n) -> bool {
     const int budget = pass == 0 ? 112 * 1024 : kSmemLimit;
-    for (int sweep = 0; sweep < 4; ++sweep) {
+    for (int sweep = 0; sweep < (full_n ? 3 : 4); ++sweep) {
       for (int mi = 0; mi < 4; ++mi) {
         const int M = m_cands[mi];
         if (M > 128 && M - 128 >= plane_q) continue;  // do not use a longer run than the plane needs
@@ -1494,6 +1494,7 @@ static const char* configure_classic(const HcuConvDesc* d, Params& p) {
         const int slot = ps * P;
         for (int nc = npad > 128 ? 128 : npad; nc >= 16; nc -= 16) {
           if (npad % nc != 0) continue;
+          if (full_n && nc != npad) break;  // this search wants every output channel in one CTA
           // wide: 4 accumulator slots per M-block in TMEM, an MMA spans up to KX slots (N = KX * nc <= 256)
           const bool wide = can_wide && p.KX * nc <= 256 && 4 * MB * nc <= 512 && (!small_wide || 4 * MB * nc <= 256);
           if ((wide ? 4 : 2) * MB * nc > 512) continue;
@@ -1543,8 +1544,15 @@ static const char* configure_classic(const HcuConvDesc* d, Params& p) {
   // (profiles/r01_umma_rate.txt).  Take the whole-SM configuration when it cuts that by more than a quarter.
   Params p0 = p, p1 = p;
   bool ok0, ok1;
-  { ok0 = search(0); p0 = p; }
-  { ok1 = search(1); p1 = p; }
+  { ok0 = search(0, false); p0 = p; }
+  if (ok0 && p0.nsplit > 1) {
+    // The deepest ring only fitted beside a SLICE of the weights: a shallower (still pipelined) ring with all output
+    // channels in the CTA keeps two CTAs per SM without re-staging the A operand per slice.  (Classic 2D U-Net, 32 -> 32
+    // channels on 568-pixel rows: the whole-SM configuration ran one 9-warp CTA per SM at 11 % tensor-pipe activity.)
+    Params keep = p0;
+    if (search(0, true)) p0 = p; else p0 = keep;
+  }
+  { ok1 = search(1, false); p1 = p; }
   if (!ok0 && !ok1) return "does not fit in shared memory";
   auto cost = [](const Params& q) { return (double)q.nsplit * (32.0 + q.Nc / 4.0) * (q.wide ? 0.55 : 1.0); };
   if (ok0 && (!ok1 || cost(p1) > 0.75 * cost(p0))) p = p0; else p = p1;

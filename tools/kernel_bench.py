@@ -36,6 +36,8 @@ LAYERS = {
     "x.n48": (8, 48, (256, 256, 32), (3, 3, 2)),
     "x.n128": (8, 128, (256, 256, 32), (3, 3, 2)),
     # classic 2D U-Net, batch 16 of 3 x 572 x 572 (BASELINE config 3): 5th entry = batch
+    "c3.d0.conv2": (32, 32, (570, 570, 1), (3, 3, 1), 16),
+    "c3.d1.conv1": (32, 64, (284, 284, 1), (3, 3, 1), 16),
     "c3.d1.conv2": (64, 64, (282, 282, 1), (3, 3, 1), 16),
     "c3.d2.conv1": (64, 128, (140, 140, 1), (3, 3, 1), 16),
     "c3.d2.conv2": (128, 128, (138, 138, 1), (3, 3, 1), 16),
