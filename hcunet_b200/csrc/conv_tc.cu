@@ -1553,6 +1553,10 @@ static const char* configure_classic(const HcuConvDesc* d, Params& p) {
     if (search(0, true)) p0 = p; else p0 = keep;
   }
   { ok1 = search(1, false); p1 = p; }
+  if (ok1 && p1.nsplit > 1) {
+    Params keep = p1;
+    if (search(1, true)) p1 = p; else p1 = keep;
+  }
   if (!ok0 && !ok1) return "does not fit in shared memory";
   auto cost = [](const Params& q) { return (double)q.nsplit * (32.0 + q.Nc / 4.0) * (q.wide ? 0.55 : 1.0); };
   if (ok0 && (!ok1 || cost(p1) > 0.75 * cost(p0))) p = p0; else p = p1;
