@@ -18,6 +18,13 @@
 //
 // Roles (288 threads): warps 0-3 epilogue (thread = accumulator row / TMEM lane), warps 4-7 producers,
 // warp 8 = TMEM allocation + barrier init + weight bulk copy (cp.async.bulk) + MMA issue (lane 0).
+//
+// Two kernels share this file, the packed weight layout and the C entry points (configure() picks per descriptor,
+// hcu_conv_tc_describe() says which): conv_tc_kernel below (the weight slice of its column chunk resident in shared
+// memory, x-march ring of planes: every input element fetched ~once -- the 8..64-channel levels) and conv_ks_kernel
+// (K-streamed: activations AND weights streamed through rings, accumulators resident in TMEM -- from 64 input channels up,
+// when the weights no longer fit beside the planes).  Both are launched with programmatic dependent launch: their prologue
+// (barrier init, TMEM allocation, index tables) overlaps the predecessor's tail.
 #include <cuda.h>
 
 #include <algorithm>
