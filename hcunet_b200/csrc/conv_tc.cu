@@ -1677,7 +1677,7 @@ static const char* configure_ks(const HcuConvDesc* d, Params& p) {
         int best_ra = 0, best_rb = 0, best_total = 0;
         double best_score = -1.0;
         int offs[5] = {0, 0, 0, 0, 0};
-        for (int ra = 3; ra >= 2; --ra) {
+        for (int ra = (f_ra > 3 ? f_ra : 3); ra >= 2; --ra) {
           for (int rb = 8; rb >= 2; --rb) {
             if ((f_ra && ra != f_ra) || (f_rb && rb != f_rb)) continue;
             const int off_a = round_up(rb * bslot, 128);
