@@ -18,6 +18,10 @@
  *     The reference layout [N][C][X][Y][Z] only exists at the boundary (hcu_nc_to_cl /
  *     hcu_cl_to_nc).  Parameters stay in the reference (PyTorch) layout in fp32 and are
  *     gathered into GEMM-B layouts by hcu_weight_gather.
+ *   - the tensor-core conv kernels are launched with PROGRAMMATIC DEPENDENT LAUNCH (cudaLaunchKernelEx,
+ *     programmaticStreamSerialization): their prologue may overlap the previous kernel of the stream, they touch global
+ *     memory only after griddepcontrol.wait.  A caller needs to do nothing: stream order is preserved, and the launches are
+ *     capturable (programmatic edges).  HCU_PDL=0 in the environment launches them normally.
  */
 #ifndef HCUNET_B200_H
 #define HCUNET_B200_H
