@@ -110,35 +110,61 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port (reference algorithm on torch CPU fp32)
 # ----------------------------------------------------------------------------------------------------
-def cpu_step_fn(z):
+def cpu_step_fn(z, batch):
+    """One CPU training step of the workload: forward (train-mode BN) + pixel-weighted loss + backward + Adam.
+    The UNMODIFIED reference modules (`hcat/unet.py`, `hcat/loss.py`; from /root/reference in the build container, from the
+    staged copies under oracle/_ref on the GPU box) when they are there -> kind "reference"; else the oracle port."""
     import torch
 
-    import hcunet_b200 as H
+    from oracle import ref_loader as R
     from oracle import unet_oracle as O
+
+    x, mask, pwl = O.golden_inputs(O.README_3D, (batch, SHAPE[0], SHAPE[1], SHAPE[2], z), 0)
+    image, mask, pwl = x.half(), mask.half(), pwl.half()      # what the reference dataloader yields (transforms.py:133)
+    if R.reference_available():
+        torch.manual_seed(0)
+        model = R.build_reference_unet(**O.README_3D).train()
+        loss_fn = R.load_reference_loss().cross_entropy
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3)    # tests/r_unet_test.py:24
+
+        def step():  # tests/r_unet_test.py:24-56 pattern (SURVEY 3.2)
+            opt.zero_grad()
+            out = model(image.float())
+            loss = loss_fn(out, mask, pwl, "pixel")
+            loss.backward()
+            opt.step()
+            return float(loss)
+
+        return step, batch * SHAPE[1] * SHAPE[2] * z, "reference", f"unmodified hcat/unet.py + hcat/loss.py from {R.REFERENCE_ROOT}"
+
+    import hcunet_b200 as H
 
     torch.manual_seed(0)
     m = H.Unet_Constructor(**O.README_3D)  # parameter container only: identical init to the reference
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    x, mask, pwl = O.golden_inputs(O.README_3D, (1, SHAPE[0], SHAPE[1], SHAPE[2], z), 0)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k}
+    opt = torch.optim.Adam(list(leaves.values()), lr=1e-3)
 
     def step():
-        # forward (train-mode BN) + pixel-weighted loss + backward, exactly the reference's op sequence
-        loss, _, grads, newbuf = O.train_step_grads(sd, O.README_3D, x, mask, pwl)
-        with torch.no_grad():  # plain Adam-free SGD-like touch of every parameter so the step has an update
-            for k, g in grads.items():
-                sd[k] = sd[k] - 1e-3 * g
+        loss, _, grads, newbuf = O.train_step_grads(sd, O.README_3D, image.float(), mask, pwl)
+        for k, p in leaves.items():
+            p.grad = grads[k]
+        opt.step()
+        with torch.no_grad():
+            for k, p in leaves.items():
+                sd[k] = p.detach()
             sd.update(newbuf)
         return float(loss)
 
-    return step, SHAPE[1] * SHAPE[2] * z
+    return step, batch * SHAPE[1] * SHAPE[2] * z, "port", "oracle/unet_oracle.py (oracle/_ref not staged)"
 
 
-def run_cpu(steps, warmup, z):
+def run_cpu(steps, warmup, z, batch=1):
     import torch
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step, vox = cpu_step_fn(z)
+    step, vox, kind, what = cpu_step_fn(z, batch)
     for _ in range(warmup):
         step()
     ts = []
@@ -147,23 +173,27 @@ def run_cpu(steps, warmup, z):
         step()
         ts.append(time.perf_counter() - t0)
     t = sum(ts) / len(ts)
-    return {"value": vox / t, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) of batch 1 x {SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]}x{z} (the GPU step is batch 4 of the same "
-                      f"patch), oracle/unet_oracle.py on torch {torch.__version__} CPU fp32, {cores} threads",
-            "ms_per_step": t * 1e3}
+    return {"value": vox / t, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{steps} train step(s) (fwd + pixel loss + bwd + Adam) of batch {batch} x {SHAPE[0]}x{SHAPE[1]}x{SHAPE[2]}x{z}, "
+                      f"{what}, torch {torch.__version__} CPU fp32, {cores} threads",
+            "ms_per_step": t * 1e3, "batch": batch}
 
 
 def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb = run_cpu(max(1, args.steps), max(0, args.warmup), args.z)
+    # the GPU arm's config: batch 4 of the patch per step; steps bounded so the run ends within a few minutes
+    k_steps, k_warm = max(1, min(args.steps, 60)), max(0, min(args.warmup, 5))
+    cb = run_cpu(k_steps, k_warm, args.z, batch=args.batch)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+            "steps": k_steps, "warmup": k_warm, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic (seeded), random-init weights",
-            "config": {"workload": WORKLOAD, "patch": [SHAPE[0], SHAPE[1], SHAPE[2], args.z], "batch_per_step": 1,
-                       "note": "reference CPU path = oracle port of hcat/unet.py + hcat/loss.py (the reference is pure "
-                               "Python on torch; it cannot travel to the GPU box), bounded sample of the GPU workload"},
+            "config": {"workload": WORKLOAD, "patch": [SHAPE[0], SHAPE[1], SHAPE[2], args.z], "batch_per_gpu": args.batch,
+                       "global_batch": args.batch, "precision": "fp32", "parallelism": "cpu", "optimizer": "Adam lr 1e-3",
+                       "note": "the reference's own CPU path on this box's host cores; kind 'reference' = the unmodified "
+                               "reference modules staged under oracle/_ref by build(), 'port' = the oracle restatement",
+                       "timed_steps": k_steps},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -418,7 +448,7 @@ def main_ours(args):
         dist.barrier()
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
-            cb = run_cpu(12, 2, Z)   # bounded sample: ~4 s of CPU work on the box's cores
+            cb = run_cpu(8, 2, Z, batch=1)   # bounded sample (batch 1 of the same patch): ~5 s of CPU work on the box's cores
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         else:
             line["cpu_baseline"] = None

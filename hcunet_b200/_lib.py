@@ -11,7 +11,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 16
+ABI_VERSION = 17
 
 F32, BF16, F16 = 0, 1, 2
 BATCH_JOB_BYTES = 256
@@ -37,7 +37,7 @@ class HcuWeightMap(C.Structure):
         ("groups", C.c_int32), ("j", C.c_int32 * 3), ("na", C.c_int32), ("nb", C.c_int32),
         ("base", C.c_int64), ("sg", C.c_int64), ("sa", C.c_int64), ("sb", C.c_int64), ("st", C.c_int64 * 3),
         ("t0", C.c_int32 * 3), ("tstep", C.c_int32 * 3), ("fold", C.c_int32), ("fold_stride", C.c_int64),
-        ("phase_on", C.c_int32), ("ph", C.c_int32 * 3), ("pst", C.c_int64 * 3),
+        ("phase_on", C.c_int32), ("ph", C.c_int32 * 3), ("bdiag", C.c_int32), ("pst", C.c_int64 * 3),
     ]
 
 

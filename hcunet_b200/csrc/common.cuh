@@ -97,16 +97,23 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // element e of a packed [g][jx][jy][jz][a][b] weight tensor -> index into the reference-layout parameter
+// (-1: a structural zero of a block-diagonal map)
 __device__ __forceinline__ long long wm_index(const HcuWeightMap& m, long long e) {
   const int nph = m.phase_on ? m.ph[0] * m.ph[1] * m.ph[2] : 1;
-  const int nbf = m.phase_on == 2 ? m.nb * nph : m.nb, naf = m.phase_on == 1 ? m.na * nph : m.na;
+  const int nbf = (m.phase_on == 2 ? m.nb * nph : m.nb) * (m.bdiag > 1 ? m.bdiag : 1),
+            naf = (m.phase_on == 1 ? m.na * nph : m.na) * (m.bdiag > 1 ? m.bdiag : 1);
   int b = (int)(e % nbf); e /= nbf;
   int a = (int)(e % naf); e /= naf;
   const int jz = (int)(e % m.j[2]); e /= m.j[2];
   const int jy = (int)(e % m.j[1]); e /= m.j[1];
   const int jx = (int)(e % m.j[0]);
-  const int g = (int)(e / m.j[0]);
+  int g = (int)(e / m.j[0]);
   long long idx = m.base;
+  if (m.bdiag > 1) {  // dense view of a grouped weight: off-diagonal blocks do not exist in the reference tensor
+    g = a / m.na;
+    if (b / m.nb != g) return -1;
+    a -= g * m.na; b -= g * m.nb;
+  }
   if (m.phase_on) {
     int phi;
     if (m.phase_on == 1) { phi = a / m.na; a -= phi * m.na; } else { phi = b / m.nb; b -= phi * m.nb; }
@@ -122,14 +129,20 @@ __device__ __forceinline__ long long wm_index(const HcuWeightMap& m, long long e
 // element e of a packed [g][jx][jy][jz][a][b] weight tensor -> index into the reference-layout parameter
 __device__ __forceinline__ long long wm_index32(const HcuWeightMap& m, uint32_t e) {
   const int nph = m.phase_on ? m.ph[0] * m.ph[1] * m.ph[2] : 1;
-  const int nbf = m.phase_on == 2 ? m.nb * nph : m.nb, naf = m.phase_on == 1 ? m.na * nph : m.na;
+  const int nbf = (m.phase_on == 2 ? m.nb * nph : m.nb) * (m.bdiag > 1 ? m.bdiag : 1),
+            naf = (m.phase_on == 1 ? m.na * nph : m.na) * (m.bdiag > 1 ? m.bdiag : 1);
   int b = (int)(e % nbf); e /= nbf;
   int a = (int)(e % naf); e /= naf;
   const int jz = (int)(e % m.j[2]); e /= m.j[2];
   const int jy = (int)(e % m.j[1]); e /= m.j[1];
   const int jx = (int)(e % m.j[0]);
-  const int g = (int)(e / m.j[0]);
+  int g = (int)(e / m.j[0]);
   long long idx = m.base;
+  if (m.bdiag > 1) {  // dense view of a grouped weight: off-diagonal blocks do not exist in the reference tensor
+    g = a / m.na;
+    if (b / m.nb != g) return -1;
+    a -= g * m.na; b -= g * m.nb;
+  }
   if (m.phase_on) {
     int phi;
     if (m.phase_on == 1) { phi = a / m.na; a -= phi * m.na; } else { phi = b / m.nb; b -= phi * m.nb; }

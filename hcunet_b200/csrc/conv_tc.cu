@@ -1307,8 +1307,10 @@ __global__ void pack_tc_ref_kernel(HcuWeightMap m, const float* __restrict__ ref
       const int ci = pl * 8 + j, co = ns * Nc + nn;
       if (ci < cin && co < cout) {
         const long long idx = wm_index(m, ((long long)(tx * KYZ + t) * cin + ci) * cout + co);
-        v = ref[idx];
-        if (m.fold) v += ref[idx + m.fold_stride];
+        if (idx >= 0) {
+          v = ref[idx];
+          if (m.fold) v += ref[idx + m.fold_stride];
+        }
       }
     }
     out[i] = __float2half_rn(v);
@@ -1371,6 +1373,8 @@ __global__ void __launch_bounds__(256) pack_tc_batch_kernel(const unsigned char*
       long long idx0 = m.base + (long long)(m.t0[0] + jx * m.tstep[0]) * m.st[0] + (long long)(m.t0[1] + jy * m.tstep[1]) * m.st[1] +
                        (long long)(m.t0[2] + jz * m.tstep[2]) * m.st[2];
       int b = co;
+      int gb = 0;
+      if (m.bdiag > 1) { gb = b / m.nb; b -= gb * m.nb; idx0 += (long long)gb * m.sg; }
       if (m.phase_on == 2) {
         int phi = b / m.nb;
         b -= phi * m.nb;
@@ -1384,6 +1388,10 @@ __global__ void __launch_bounds__(256) pack_tc_batch_kernel(const unsigned char*
         int a = pl * 8 + j;
         if (a < J.cin) {
           long long idx = idx0;
+          if (m.bdiag > 1) {
+            if (a / m.na != gb) continue;  // structural zero of the block-diagonal weight
+            a -= gb * m.na;
+          }
           if (m.phase_on == 1) {
             int phi = a / m.na;
             a -= phi * m.na;
@@ -1806,8 +1814,10 @@ extern "C" int hcu_conv_tc_pack_ref(const HcuConvDesc* d, const HcuWeightMap* m,
   HCU_CHECK_ARG(why == nullptr, "conv_tc_pack_ref: unsupported descriptor (%s)", why);
   {
     const int nph = m->phase_on ? m->ph[0] * m->ph[1] * m->ph[2] : 1;
+    const int bd = m->bdiag > 1 ? m->bdiag : 1;
+    HCU_CHECK_ARG(bd == 1 || m->phase_on == 0, "conv_tc_pack_ref: block-diagonal maps carry no stride phases");
     HCU_CHECK_ARG(m->groups == 1 && m->j[0] == d->taps[0] && m->j[1] == d->taps[1] && m->j[2] == d->taps[2] &&
-                      m->na * (m->phase_on == 1 ? nph : 1) == d->cin && m->nb * (m->phase_on == 2 ? nph : 1) == d->cout,
+                      m->na * bd * (m->phase_on == 1 ? nph : 1) == d->cin && m->nb * bd * (m->phase_on == 2 ? nph : 1) == d->cout,
                   "conv_tc_pack_ref: weight map does not match the descriptor");
   }
   const long long total = (long long)p.nsplit * p.E * p.Nc * 8;
@@ -1829,8 +1839,10 @@ extern "C" int hcu_conv_tc_pack_batch_build(const HcuConvDesc* descs, const HcuW
     HCU_CHECK_ARG(why == nullptr, "conv_tc_pack_batch_build: job %d: unsupported descriptor (%s)", i, why);
     const HcuWeightMap* m = &maps[i];
     const int nph = m->phase_on ? m->ph[0] * m->ph[1] * m->ph[2] : 1;
+    const int bd = m->bdiag > 1 ? m->bdiag : 1;
+    HCU_CHECK_ARG(bd == 1 || m->phase_on == 0, "conv_tc_pack_batch_build: job %d: block-diagonal maps carry no stride phases", i);
     HCU_CHECK_ARG(m->groups == 1 && m->j[0] == descs[i].taps[0] && m->j[1] == descs[i].taps[1] && m->j[2] == descs[i].taps[2] &&
-                      m->na * (m->phase_on == 1 ? nph : 1) == descs[i].cin && m->nb * (m->phase_on == 2 ? nph : 1) == descs[i].cout,
+                      m->na * bd * (m->phase_on == 1 ? nph : 1) == descs[i].cin && m->nb * bd * (m->phase_on == 2 ? nph : 1) == descs[i].cout,
                   "conv_tc_pack_batch_build: job %d: weight map does not match the descriptor", i);
     HCU_CHECK_ARG(out_off[i] % 16 == 0, "conv_tc_pack_batch_build: job %d: packed offset not 16-byte aligned", i);
     tc::PackJob j;

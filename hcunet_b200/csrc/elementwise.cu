@@ -152,8 +152,11 @@ __global__ void weight_gather_kernel(HcuWeightMap m, const float* __restrict__ r
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
     const long long idx = wm_index(m, e);
-    float v = ref[idx];
-    if (m.fold) v += ref[idx + m.fold_stride];
+    float v = 0.f;
+    if (idx >= 0) {
+      v = ref[idx];
+      if (m.fold) v += ref[idx + m.fold_stride];
+    }
     packed[e] = v;
   }
 }
@@ -168,6 +171,7 @@ __global__ void weight_scatter_kernel(HcuWeightMap m, const float* __restrict__ 
     for (int i = 0; i < nsplit; ++i) s += partial[(long long)i * split_stride + e];
     s *= scale;
     const long long idx = wm_index(m, e);
+    if (idx < 0) continue;
     if (accumulate) {
       ref[idx] += s;
       if (m.fold) ref[idx + m.fold_stride] += s;
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(256) weight_scatter_batch_kernel(const unsigne
     for (int i = 0; i < J.nsplit; ++i) s += part[(long long)i * J.total + e];
     s *= scale;
     const long long idx = wm_index32(J.m, (uint32_t)e);
+    if (idx < 0) continue;
     ref[idx] = s;
     if (J.m.fold) ref[idx + J.m.fold_stride] = s;
   }
@@ -919,7 +924,8 @@ extern "C" int hcu_cl_to_nc(const void* src, int32_t dtype_src, void* dst, int32
 
 static long long wm_total(const HcuWeightMap* m) {
   const long long nph = m->phase_on ? (long long)m->ph[0] * m->ph[1] * m->ph[2] : 1;
-  return (long long)m->groups * m->j[0] * m->j[1] * m->j[2] * m->na * m->nb * nph;
+  const long long bd = m->bdiag > 1 ? m->bdiag : 1;
+  return (long long)m->groups * m->j[0] * m->j[1] * m->j[2] * m->na * m->nb * nph * bd * bd;
 }
 
 extern "C" int hcu_weight_gather(const HcuWeightMap* m, const float* ref, float* packed, void* stream) {

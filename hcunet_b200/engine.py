@@ -197,9 +197,9 @@ def conv_desc(dt_in, dt_out, batch, in_size, in_cpitch, in_c_off, in_c_gstep, ci
 
 
 def weight_map(groups, j, na, nb, sg, sa, sb, st, t0=(0, 0, 0), tstep=(1, 1, 1), base=0, fold=0,
-               fold_stride=0, phase_on=0, ph=(1, 1, 1), pst=(0, 0, 0)) -> HcuWeightMap:
+               fold_stride=0, phase_on=0, ph=(1, 1, 1), pst=(0, 0, 0), bdiag=0) -> HcuWeightMap:
     m = HcuWeightMap()
-    m.phase_on, m.ph = phase_on, _i3(ph)
+    m.phase_on, m.ph, m.bdiag = phase_on, _i3(ph), bdiag
     m.pst = (C.c_int64 * 3)(*[int(e) for e in pst])
     m.groups, m.j, m.na, m.nb = groups, _i3(j), na, nb
     m.base, m.sg, m.sa, m.sb = base, sg, sa, sb
@@ -324,6 +324,10 @@ class UnetEngine:
         self._side2 = None
         self.n_side = int(os.environ.get("HCUNET_SIDE_STREAMS", "1"))  # 2 was measured: no gain
         self._keep: List[torch.Tensor] = []
+        # Test instrumentation (tests/test_gpu_teacher.py): ``tap(tag, tensor, channels, spatial)`` is called on the current
+        # stream right after every stored tensor of a step has been produced (channels-last [B, S, C pitch]); it may read
+        # the tensor or overwrite it in place.  None in normal operation.
+        self.tap = None
 
     @property
     def lib(self):
@@ -337,6 +341,10 @@ class UnetEngine:
             p = plan_unet(self.spec, xshape)
             self._plans[key] = p
         return p
+
+    def _tap(self, tag, t, c, sz):
+        if self.tap is not None and t is not None:
+            self.tap(tag, t, int(c), tuple(int(v) for v in sz))
 
     # ---- small wrappers -----------------------------------------------------------------------
     def _stream(self):
@@ -389,20 +397,28 @@ class UnetEngine:
                    "conv_fwd")
 
     # ---- weight maps (reference layouts: Conv [Cout, Cin/g, kx, ky, kz]; ConvT [Cin, Cout, kx, ky, kz]) ----
-    @staticmethod
-    def _wm_conv_fwd(g: ConvGeom) -> HcuWeightMap:
-        T = g.taps[0] * g.taps[1] * g.taps[2]
-        rc = g.ref_cin_g
-        return weight_map(g.groups, g.taps, g.cin_g, g.cout_g, sg=g.cout_g * rc * T, sa=T, sb=rc * T,
-                          st=(g.taps[1] * g.taps[2], g.taps[2], 1), fold=int(g.fold), fold_stride=g.cin_g * T)
+    def _eff(self, g: ConvGeom, f16: bool):
+        """(groups, cin, cout, bdiag) a conv is LAUNCHED with.  fp16 path: a grouped convolution (`groups=2` of the
+        production model, `main.py:46-55`) runs as ONE dense tensor-core convolution over block-diagonal packed weights
+        (HcuWeightMap.bdiag): its groups have 2 .. 64 channels, far below a tensor-core tile."""
+        if f16 and self.use_tc and g.groups > 1:
+            return 1, g.cin_t, g.cout_t, g.groups
+        return g.groups, g.cin_g, g.cout_g, 0
 
     @staticmethod
-    def _wm_conv_dgrad(g: ConvGeom) -> HcuWeightMap:
+    def _wm_conv_fwd(g: ConvGeom, bdiag: int = 0) -> HcuWeightMap:
         T = g.taps[0] * g.taps[1] * g.taps[2]
         rc = g.ref_cin_g
-        return weight_map(g.groups, g.taps, g.cout_g, g.cin_g, sg=g.cout_g * rc * T, sa=rc * T, sb=T,
+        return weight_map(1 if bdiag else g.groups, g.taps, g.cin_g, g.cout_g, sg=g.cout_g * rc * T, sa=T, sb=rc * T,
+                          st=(g.taps[1] * g.taps[2], g.taps[2], 1), fold=int(g.fold), fold_stride=g.cin_g * T, bdiag=bdiag)
+
+    @staticmethod
+    def _wm_conv_dgrad(g: ConvGeom, bdiag: int = 0) -> HcuWeightMap:
+        T = g.taps[0] * g.taps[1] * g.taps[2]
+        rc = g.ref_cin_g
+        return weight_map(1 if bdiag else g.groups, g.taps, g.cout_g, g.cin_g, sg=g.cout_g * rc * T, sa=rc * T, sb=T,
                           st=(g.taps[1] * g.taps[2], g.taps[2], 1), t0=tuple(t - 1 for t in g.taps),
-                          tstep=(-1, -1, -1), fold=int(g.fold), fold_stride=g.cin_g * T)
+                          tstep=(-1, -1, -1), fold=int(g.fold), fold_stride=g.cin_g * T, bdiag=bdiag)
 
     @staticmethod
     def _wm_up_phase(u: UpGeom, phi, J) -> HcuWeightMap:
@@ -483,6 +499,7 @@ class UnetEngine:
         _lib.note("input", x.numel() * x.element_size() + cur.numel() * esz, 0)
         _lib.check(lib.hcu_nc_to_cl(_ptr(x), _DT[x.dtype], _ptr(cur), adt, B, plan.in_channels, S, cp, None, st),
                    "nc_to_cl")
+        self._tap("input", cur, plan.in_channels, plan.in_sz)
         xf = None  # pending (scale, shift) + ReLU to apply when `cur` is read
         saved = [] if save else None
         fold_eval = not save and not training  # inference: BN folded into the conv epilogue
@@ -499,18 +516,21 @@ class UnetEngine:
                 out = self._up_forward(g, params, cur, cp, xf, B, act_dtype)
                 if save:
                     saved.append(("up", g, cur, cp, xf))
+                self._tap(g.name + ".out", out, g.cout, g.out_sz)
                 cur, cp, xf = out, g.cout, None
                 continue
             npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
-            w = (self._wm_conv_fwd(g), params[g.name + ".weight"],
-                 g.groups * g.taps[0] * g.taps[1] * g.taps[2] * g.cin_g * g.cout_g, g.name + ".weight")
+            eg, ecin, ecout, bd = self._eff(g, act_dtype == torch.float16)
+            w = (self._wm_conv_fwd(g, bd), params[g.name + ".weight"],
+                 eg * g.taps[0] * g.taps[1] * g.taps[2] * ecin * ecout, g.name + ".weight")
             bias = params[g.name + ".bias"]
             isc, ish = (xf[0], xf[1]) if xf is not None else (None, None)
             if g.bn is None:  # out_conv: logits, fp32
                 y = torch.empty((B, npix // B, g.cout_t), dtype=torch.float32, device=dev)
-                d = conv_desc(adt, _lib.F32, B, g.in_sz, cp, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0,
-                              g.cout_g, g.groups, g.taps, g.dil, in_relu=int(xf is not None))
+                d = conv_desc(adt, _lib.F32, B, g.in_sz, cp, 0, ecin, ecin, g.out_sz, g.out_sz, g.cout_t, 0,
+                              ecout, eg, g.taps, g.dil, in_relu=int(xf is not None))
                 self._conv(d, cur, w, bias, y, in_scale=isc, in_shift=ish, layer=g.name)
+                self._tap("logits", y, g.cout_t, g.out_sz)
                 if save:
                     saved.append(("out", g, cur, cp, xf))
                 if g.cout_t == 1:
@@ -522,8 +542,8 @@ class UnetEngine:
                 break
             gamma, beta = params[g.bn + ".weight"], params[g.bn + ".bias"]
             rm, rv = buffers[g.bn + ".running_mean"], buffers[g.bn + ".running_var"]
-            d = conv_desc(adt, adt, B, g.in_sz, cp, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, g.cout_t, 0,
-                          g.cout_g, g.groups, g.taps, g.dil, in_relu=int(xf is not None))
+            d = conv_desc(adt, adt, B, g.in_sz, cp, 0, ecin, ecin, g.out_sz, g.out_sz, g.cout_t, 0,
+                          ecout, eg, g.taps, g.dil, in_relu=int(xf is not None))
             vec = torch.empty((4, g.cout_t), dtype=torch.float32, device=dev)  # mean, invstd, scale, shift
             if fold_eval:
                 _lib.check(lib.hcu_bn_eval_affine(g.cout_t, _ptr(gamma), _ptr(beta), _ptr(rm), _ptr(rv), BN_EPS,
@@ -531,8 +551,10 @@ class UnetEngine:
                 d.out_relu = 1
                 a = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
                 self._conv(d, cur, w, None, a, out_scale=vec[2], out_shift=vec[3], layer=g.name)
+                self._tap(g.name + ".a", a, g.cout_t, g.out_sz)
                 if g.pool is not None:
                     a, _ = self._pool(a, g, B, act_dtype, None, None, 0, want_argmax=False)
+                    self._tap(g.name + ".pool", a, g.cout_t, g.pool_sz)
                 cur, cp, xf = a, g.cout_t, None
                 continue
             y = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
@@ -555,10 +577,13 @@ class UnetEngine:
                                                   _ptr(vec[2]), _ptr(vec[3]), st), "bn_eval_affine")
                 vec[0].copy_(rm)
                 vec[1].copy_(torch.rsqrt(rv + BN_EPS))
+            self._tap(g.name + ".y", y, g.cout_t, g.out_sz)
+            self._tap(g.name + ".bn", vec, g.cout_t, (1, 1, 1))
             argmax = None
             a_in, a_cp, a_xf = cur, cp, xf
             if g.pool is not None:
                 cur, argmax = self._pool(y, g, B, act_dtype, vec[2], vec[3], 1, want_argmax=save)
+                self._tap(g.name + ".pool", cur, g.cout_t, g.pool_sz)
                 cp, xf = g.cout_t, None
             else:
                 cur, cp, xf = y, g.cout_t, (vec[2], vec[3])
@@ -670,6 +695,7 @@ class UnetEngine:
             _lib.check(lib.hcu_nc_to_cl(_ptr(dlogits), _lib.F32, _ptr(dcur), adt, B, co, So, dcur_cp, _ptr(scl), st),
                        "nc_to_cl")
             dcur_dt = adt
+        self._tap("dlogits", dcur, co, plan.out_sz)
         self._inv = inv
         dx = None
         SB = _lib.STAT_BINS
@@ -689,6 +715,7 @@ class UnetEngine:
                                                              params[g.name + ".weight"], dy_cp=dcur_cp)
                 dcur = self._dgrad_conv(g, dcur, dcur_dt, B, params[g.name + ".weight"], act_dtype, dy_cp=dcur_cp)
                 dcur_dt = adt
+                self._tap(g.name + ".dgrad", dcur, g.cin_t, g.in_sz)
             elif kind == "conv":
                 _, g, a_in, a_cp, a_xf, y, vec, argmax = item
                 npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
@@ -725,6 +752,7 @@ class UnetEngine:
                 _lib.check(lib.hcu_bn_bwd_apply(_ptr(dcur), dcur_dt, _ptr(y), adt, _ptr(dy), adt, npix, g.cout_t,
                                                 _ptr(vec[2]), _ptr(vec[3]), 1, _ptr(coef), _ptr(pool_arg),
                                                 C.byref(pool_geom) if pool_geom is not None else None, st), "bn_bwd_apply")
+                self._tap(g.name + ".dy", dy, g.cout_t, g.out_sz)
                 grads[g.bn + ".weight"], grads[g.bn + ".bias"], grads[g.name + ".bias"] = dgamma, dbeta, dbias
                 grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, a_cp, a_xf, adt, dy, adt, B,
                                                              params[g.name + ".weight"])
@@ -734,6 +762,7 @@ class UnetEngine:
                     dcur = self._dgrad_conv(g, dy, adt, B, params[g.name + ".weight"], act_dtype,
                                             out_cp=a_cp if g.first else None)
                     dcur_dt = adt
+                    self._tap(g.name + ".dgrad", dcur, g.cin_t, g.in_sz)
                 if g.first and need_dx:
                     S = plan.in_sz[0] * plan.in_sz[1] * plan.in_sz[2]
                     dx = torch.empty((B, plan.in_channels) + tuple(plan.in_sz[:plan.dims]), dtype=torch.float32,
@@ -789,6 +818,7 @@ class UnetEngine:
                     d2 = conv_desc(dcur_dt, adt, B, u.out_sz, u.cout, 0, u.cout, u.cout, u.in_sz, u.in_sz, u.cin, 0, u.cin,
                                    1, u.k, istep=u.s)
                     self._conv(d2, dcur, w, None, dprev, layer=u.name + ".dgrad")
+                self._tap(u.name + ".dgrad", dprev, u.cin, u.in_sz)
                 dcur, dcur_dt = dprev, adt
         if batched:
             if side is not None and self.n_side > 1:
@@ -832,17 +862,18 @@ class UnetEngine:
 
     def _wgrad_conv(self, g: ConvGeom, a_in, a_cp, a_xf, a_dt, dy, dy_dt, B, wref, dy_cp=None):
         T = g.taps[0] * g.taps[1] * g.taps[2]
-        d = conv_desc(a_dt, dy_dt, B, g.in_sz, a_cp, 0, g.cin_g, g.cin_g, g.out_sz, g.out_sz, dy_cp or g.cout_t, 0, g.cout_g,
-                      g.groups, g.taps, g.dil, in_relu=int(a_xf is not None))
+        eg, ecin, ecout, bd = self._eff(g, a_dt == _lib.F16 and dy_dt == _lib.F16)
+        d = conv_desc(a_dt, dy_dt, B, g.in_sz, a_cp, 0, ecin, ecin, g.out_sz, g.out_sz, dy_cp or g.cout_t, 0, ecout,
+                      eg, g.taps, g.dil, in_relu=int(a_xf is not None))
         m = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
-        roles = g.groups * T * (-(-g.cin_g // 8)) * (-(-g.cout_g // 8))
+        roles = eg * T * (-(-ecin // 8)) * (-(-ecout // 8))
         ns = _nsplit(m, roles)
-        total = g.groups * T * g.cin_g * g.cout_g
+        total = eg * T * ecin * ecout
         esz = 4 if a_dt == _lib.F32 else 2
         nin = B * g.in_sz[0] * g.in_sz[1] * g.in_sz[2] * g.cin_t
         note = (g.name, (nin + m * g.cout_t) * esz, 2 * m * T * g.cin_g * g.cout_g * g.groups)
         isc, ish = (a_xf[0], a_xf[1]) if a_xf is not None else (None, None)
-        return self._wgrad_dispatch(g.name + ".weight", wref, d, a_in, isc, ish, dy, self._wm_conv_fwd(g), total, ns, note)
+        return self._wgrad_dispatch(g.name + ".weight", wref, d, a_in, isc, ish, dy, self._wm_conv_fwd(g, bd), total, ns, note)
 
     def _wgrad_dispatch(self, wname, wref, d, a, isc, ish, b, wm, total, ns, note):
         """Weight gradient of one conv: tensor-core kernel when it takes the descriptor, else the FFMA split-K kernel;
@@ -908,12 +939,13 @@ class UnetEngine:
     def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype, out_cp=None, dy_cp=None):
         adt = _DT[act_dtype]
         T = g.taps[0] * g.taps[1] * g.taps[2]
-        w = (self._wm_conv_dgrad(g), wref, g.groups * T * g.cin_g * g.cout_g, g.name + ".weight")
+        eg, ecin, ecout, bd = self._eff(g, dy_dt == _lib.F16 and act_dtype == torch.float16)
+        w = (self._wm_conv_dgrad(g, bd), wref, eg * T * ecin * ecout, g.name + ".weight")
         cpo = out_cp or g.cin_t
         alloc = torch.zeros if cpo != g.cin_t else torch.empty
         dprev = alloc((B, g.in_sz[0] * g.in_sz[1] * g.in_sz[2], cpo), dtype=act_dtype, device=dy.device)
         pad = tuple((g.taps[i] - 1) * g.dil[i] for i in range(3))
-        d = conv_desc(dy_dt, adt, B, g.out_sz, dy_cp or g.cout_t, 0, g.cout_g, g.cout_g, g.in_sz, g.in_sz, cpo, 0, g.cin_g,
-                      g.groups, g.taps, g.dil, pad=pad)
+        d = conv_desc(dy_dt, adt, B, g.out_sz, dy_cp or g.cout_t, 0, ecout, ecout, g.in_sz, g.in_sz, cpo, 0, ecin,
+                      eg, g.taps, g.dil, pad=pad)
         self._conv(d, dy, w, None, dprev, layer=g.name + ".dgrad")
         return dprev

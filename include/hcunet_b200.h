@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 16
+#define HCU_ABI_VERSION 17
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -232,6 +232,11 @@ typedef struct HcuWeightMap {
   /* stride phases folded into a channel index (see HcuConvDesc.ophase): phase_on = 0 none, 1: the `a` index is
    * [nph][na], 2: the `b` index is [nph][nb]; nph = ph[0]*ph[1]*ph[2]; phase (phix,phiy,phiz) adds sum phi_d*pst[d] */
   int32_t phase_on, ph[3];
+  /* block-diagonal: bdiag = G > 1 (groups must be 1, no phases) makes the packed tensor DENSE [taps][G*na][G*nb] over a
+   * grouped reference weight (`groups=G` of nn.Conv, main.py:46-55): entry (a, b) maps to group a/na's block when
+   * a/na == b/nb (sg = group stride) and is ZERO otherwise -- gathers/packs write 0 there, scatters skip it.  The grouped
+   * convolution then runs as one dense tensor-core convolution. */
+  int32_t bdiag;
   int64_t pst[3];
 } HcuWeightMap;
 int hcu_weight_gather(const HcuWeightMap* m, const float* ref, float* packed, void* stream);

@@ -19,7 +19,49 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("HCUNET_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+"""``oracle/_ref/hcat/{unet,loss}.py``: byte-for-byte copies of the two reference modules of the hot path, staged by
+``stage_reference()`` (called from ``__graft_entry__.build()`` in the build container).  The directory is git-ignored
+(no reference source enters the history) but travels with the repo snapshot to the GPU box, where ``/root/reference``
+does not exist -- so ``bench.py --impl reference`` can time the UNMODIFIED reference there."""
+
+
+def _pick_root() -> str:
+    env = os.environ.get("HCUNET_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile(os.path.join("/root/reference", "hcat", "unet.py")):
+        return "/root/reference"
+    return STAGED_ROOT
+
+
+REFERENCE_ROOT = _pick_root()
+
+
+def stage_reference() -> bool:
+    """Copy `hcat/unet.py` and `hcat/loss.py` from the mounted reference into ``oracle/_ref/hcat/`` (unmodified; a
+    sha256 manifest is written next to them).  Returns False when the reference is not mounted."""
+    import hashlib
+    import shutil
+
+    src = "/root/reference/hcat"
+    if not os.path.isfile(os.path.join(src, "unet.py")):
+        return False
+    dst = os.path.join(STAGED_ROOT, "hcat")
+    os.makedirs(dst, exist_ok=True)
+    lines = []
+    for f in ("unet.py", "loss.py"):
+        shutil.copyfile(os.path.join(src, f), os.path.join(dst, f))
+        with open(os.path.join(dst, f), "rb") as fh:
+            lines.append(f"{hashlib.sha256(fh.read()).hexdigest()}  hcat/{f}")
+    with open(os.path.join(STAGED_ROOT, "MANIFEST.sha256"), "w") as fh:
+        fh.write("\n".join(lines) + "\n")
+    return True
+
+
+def reference_is_live() -> bool:
+    """True when the modules come from the mounted reference tree (build container), not the staged copies."""
+    return REFERENCE_ROOT != STAGED_ROOT and reference_available()
 
 _cache = {}
 

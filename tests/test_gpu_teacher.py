@@ -1,0 +1,184 @@
+"""Teacher-forced parity of the MIXED path: every tensor the engine stores in HBM during a training step (input cast,
+each conv's raw output + BatchNorm vectors, pooled tensors, up-convolution outputs, logits, the scaled dlogits, every
+BatchNorm-backward output dy, every data gradient) and every parameter gradient is compared with the fp16-storage
+emulation of the reference (``oracle/mixed_oracle.py``, pinned to the reference-minted fixtures with its rounding hooks
+off) -- and then OVERWRITTEN with the emulation's tensor, so that the next kernel reads exactly what the oracle's next
+op reads.
+
+Why: end to end, the random-init batch-statistics networks of the fixtures amplify a single fp16 rounding flip; two
+CORRECT implementations of the same fp16-storage arithmetic that merely accumulate their fp32 sums in a different order
+differ by 1e-3 .. 1e-2 on the logits and 4 % .. 30 % on the deep gradients (``mixed_oracle.accumulation_floor``,
+printed by tests/test_gpu_parity.py).  Teacher forcing removes the amplification: what is left per tensor is the
+accumulation order of ONE kernel, so the gates below are tight -- stored tensors 5e-4 (a handful of one-ulp fp16
+flips), parameter gradients 2e-3 (fp32 atomics over up to millions of pixels) -- and a wrong tap, phase, fold, scale or
+mask in any single launch of the real step configuration fails at the layer it happens in.
+"""
+import pytest
+import torch
+
+from conftest import MODEL_CASES, load_golden
+from oracle import mixed_oracle as M
+from oracle import unet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_STORED = 5e-4
+TOL_GRAD = 2e-3
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def is_dead_bias(name):
+    return name.endswith(".bias") and (".conv1." in name or ".conv2." in name or ".up_conv." in name)
+
+
+def to_cl(ref):
+    """NC(D)HW fp32 -> [B, S, C] channels-last."""
+    b, c = ref.shape[:2]
+    return ref.reshape(b, c, -1).permute(0, 2, 1).contiguous()
+
+
+class Teacher:
+    def __init__(self, taps):
+        self.taps, self.report, self.seen = taps, {}, []
+
+    def __call__(self, tag, t, c, sz):
+        ref = self.taps.get(tag)
+        assert ref is not None, f"the engine stored a tensor the oracle does not know: {tag}"
+        self.seen.append(tag)
+        if tag.endswith(".bn"):
+            want = ref.to(t.device)
+            self.report[tag] = max(rel_l2(t[i], want[i]) for i in range(4))
+            t.copy_(want)
+            return
+        want = to_cl(ref).to(t.device)
+        assert t.shape[0] == want.shape[0] and t.shape[1] == want.shape[1] and t.shape[2] >= c == want.shape[2], \
+            (tag, tuple(t.shape), tuple(want.shape))
+        self.report[tag] = rel_l2(t[:, :, :c].float(), want)
+        if t.shape[2] > c:
+            assert float(t[:, :, c:].float().abs().max()) == 0.0, f"{tag}: channel padding is not zero"
+        t[:, :, :c].copy_(want)
+
+
+def run_case(kwargs, sd, x, mask, pwl, steps=3):
+    import hcunet_b200 as H
+
+    taps = {}
+    loss_e, logits_e, grads_e, _ = M.train_step(sd, kwargs, x, mask, pwl, taps=taps)
+    m = H.Unet_Constructor(**kwargs)
+    m.load_state_dict(sd)
+    m.precision = "mixed"
+    m = m.cuda().train()
+    xg, mg, pg = x.cuda(), mask.cuda(), pwl.cuda()
+    worst_stored, worst_grad = {}, {}
+    for step in range(steps):  # steps 1-2 record the step cache (per-layer packs / scatters), step 3 is the batched path
+        teacher = Teacher(taps)
+        m._engine.tap = teacher
+        m.load_state_dict(sd)
+        m.zero_grad(set_to_none=True)
+        logits = m(xg)
+        loss = H.cross_entropy(logits, mg, pg, "pixel")
+        loss.backward()
+        torch.cuda.synchronize()
+        m._engine.tap = None
+        missing = set(taps) - set(teacher.seen) - {"grad_scale"}
+        assert not missing, f"tensors of the oracle the engine never stored: {sorted(missing)}"
+        assert abs(float(loss) - float(loss_e)) <= 1e-5 * abs(float(loss_e))
+        for tag, r in teacher.report.items():
+            worst_stored[tag] = max(worst_stored.get(tag, 0.0), r)
+        gmax = max(float(g.abs().max()) for g in grads_e.values())
+        for k, p in m.named_parameters():
+            assert p.grad is not None, k
+            if is_dead_bias(k):  # analytically zero: absolute
+                assert float((p.grad.cpu() - grads_e[k]).abs().max()) <= 1e-4 * gmax + 1e-7, k
+                continue
+            worst_grad[k] = max(worst_grad.get(k, 0.0), rel_l2(p.grad, grads_e[k]))
+    return worst_stored, worst_grad
+
+
+def check(name, worst_stored, worst_grad):
+    ws = max(worst_stored.items(), key=lambda kv: kv[1])
+    wg = max(worst_grad.items(), key=lambda kv: kv[1])
+    print(f"{name}: teacher-forced worst stored tensor {ws[1]:.2e} ({ws[0]}), worst gradient {wg[1]:.2e} ({wg[0]}), "
+          f"{len(worst_stored)} tensors, {len(worst_grad)} gradients")
+    bad = {k: v for k, v in worst_stored.items() if v > TOL_STORED}
+    assert not bad, bad
+    bad = {k: v for k, v in worst_grad.items() if v > TOL_GRAD}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("name", MODEL_CASES)
+def test_teacher_forced_step_matches_emulation_golden_cases(name):
+    fx = load_golden(name)
+    check(name, *run_case(fx["kwargs"], fx["state_dict"], fx["x"], fx["mask"], fx["pwl"]))
+
+
+RICH = {
+    "rich2d": (dict(image_dimensions=2, in_channels=3, out_channels=2, feature_sizes=[64, 128, 256], kernel=(3, 3),
+                    upsample_kernel=(2, 2), max_pool_kernel=(2, 2), upsample_stride=2, dilation=1, groups=1),
+               (2, 3, 60, 52)),
+    "rich3d": (dict(O.README_3D, feature_sizes=[64, 128]), (1, 4, 22, 20, 6)),
+    "mid3d": (dict(O.README_3D, feature_sizes=[16, 32, 64]), (2, 4, 76, 68, 9)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RICH))
+def test_teacher_forced_step_matches_emulation_channel_rich(name):
+    import hcunet_b200 as H
+
+    kwargs, xs = RICH[name]
+    torch.manual_seed(31)
+    sd = {k: v.detach().clone() for k, v in H.Unet_Constructor(**kwargs).state_dict().items()}
+    x, mask, pwl = O.golden_inputs(kwargs, xs, 6)
+    check(name, *run_case(kwargs, sd, x, mask, pwl))
+
+
+def test_teacher_forced_step_matches_emulation_cfg1_full_size():
+    """BASELINE config 1/2 patch (README model, 4 x 256 x 256 x 32): the kernel configurations the bench runs."""
+    import hcunet_b200 as H
+
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in H.Unet_Constructor(**O.README_3D).state_dict().items()}
+    x, mask, pwl = O.golden_inputs(O.README_3D, (1, 4, 256, 256, 32), 0)
+    check("cfg1", *run_case(O.README_3D, sd, x, mask, pwl, steps=3))
+
+
+@pytest.mark.parametrize("name", ["g3d_small", "g3d_readme", "g2d_small"])
+def test_teacher_forced_eval_forward_matches_emulation(name):
+    import hcunet_b200 as H
+
+    fx = load_golden(name)
+    sd = dict(fx["state_dict"])
+    # running statistics that keep the network alive (the fixtures' one-step buffers kill every ReLU of some cases)
+    _, _, _, nb = O.train_step_grads(sd, fx["kwargs"], fx["x"], fx["mask"], fx["pwl"])
+    for k, v in nb.items():
+        if "running_mean" in k:
+            sd[k] = (v - 0.9 * sd[k]) / 0.1   # the batch statistics themselves
+        elif "running_var" in k:
+            sd[k] = ((v - 0.9 * sd[k]) / 0.1).clamp_min(1e-3)
+    taps = {}
+    want = M.eval_forward(sd, fx["kwargs"], fx["x"], taps=taps)
+    assert float(want.std()) > 1e-3, "dead network: the eval check would be vacuous"
+    m = H.Unet_Constructor(**fx["kwargs"])
+    m.load_state_dict(sd)
+    m.precision = "mixed"
+    m = m.cuda().eval()
+    teacher = Teacher(taps)
+    m._engine.tap = teacher
+    with torch.no_grad():
+        got = m(fx["x"].cuda())
+    m._engine.tap = None
+    assert not set(taps) - set(teacher.seen)
+    ws = max(teacher.report.items(), key=lambda kv: kv[1])
+    print(f"{name}: eval teacher-forced worst stored tensor {ws[1]:.2e} ({ws[0]})")
+    assert ws[1] <= TOL_STORED, ws
+    # and end to end WITHOUT forcing: no batch statistics in eval mode, so the chain is well conditioned
+    with torch.no_grad():
+        free = m(fx["x"].cuda())
+    err = rel_l2(free, want)
+    agree = float(((free.cpu() > 0) == (want > 0)).float().mean())
+    print(f"{name}: eval end to end vs emulation {err:.2e}, agreement {agree:.5f}")
+    assert err <= 2e-3 and agree >= 0.999, (err, agree)
