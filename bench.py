@@ -237,22 +237,29 @@ def main_ours(args):
     use_graph = os.environ.get("HCUNET_BENCH_GRAPH", "1") != "0"
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
 
-    # synthetic patches: NBUF distinct batches so consecutive steps never reuse a cached input
+    # Synthetic patches as the reference dataloader finds them on disk (dataloader.py:40-58): the RAW stack [Z, Y, X, C] uint8
+    # as skimage.io.imread yields it, mask / pwl [Z, Y, X].  hcunet_b200.StackLoader is the input path (to_float -> reshape ->
+    # normalize -> to_tensor on the device + the origin crop of mask / pwl the loss reads, loss.py:51-56).
+    # NBUF distinct batches so consecutive steps never reuse a cached input.
     NBUF = 3
+    loader = H.StackLoader(model)
+    ext = loader.label_extent((B, Z, Y, X, C))
     g = torch.Generator().manual_seed(1234 + rank)
     host = []
     for _ in range(NBUF):
-        img = torch.randn((B, C, X, Y, Z), generator=g).half().pin_memory()
-        msk = (torch.rand((B, 1, X, Y, Z), generator=g) > 0.7).half().pin_memory()
-        pwl = (torch.rand((B, 1, X, Y, Z), generator=g) * 3).half().pin_memory()
+        img = torch.randint(0, 256, (B, Z, Y, X, C), generator=g, dtype=torch.uint8).pin_memory()
+        msk = (torch.rand((B, Z, Y, X), generator=g) > 0.7).half().pin_memory()
+        pwl = (torch.rand((B, Z, Y, X), generator=g) * 3).half().pin_memory()
         host.append((img, msk, pwl))
-    resident = [tuple(t.to(dev) for t in h) for h in host]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    # resident inputs: the raw stack in HBM + the label crops the loss reads
+    resident = [(h[0].to(dev), loader.labels(h[1], ext), loader.labels(h[2], ext)) for h in host]
+    crop_bytes = 2 * B * ext[0] * ext[1] * ext[2] * 2      # mask + pwl crops, fp16, read in place from pinned host memory
+    h2d_bytes = host[0][0].numel() * host[0][0].element_size() + crop_bytes
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
-    def eager_step(img, msk, pwl):
+    def eager_step(raw, msk, pwl):
         opt.zero_grad(set_to_none=True)
-        logits = model(img)
+        logits = model(loader.image(raw))
         loss = H.cross_entropy(logits, msk, pwl, "pixel")
         loss.backward()
         sync.allreduce()
@@ -271,7 +278,7 @@ def main_ours(args):
         from hcunet_b200.graph import GraphedTrainStep
 
         gstep = GraphedTrainStep(model, opt, lambda lg, m, w: H.cross_entropy(lg, m, w, "pixel"), resident[0],
-                                 grad_sync=sync.allreduce if world > 1 else None)
+                                 grad_sync=sync.allreduce if world > 1 else None, input_fn=loader.image)
         # one CUDA-graph launch per step; the inputs are copied into the graph's static buffers (device->device here,
         # pinned host->device in the e2e leg) inside the timed region
         step = gstep
@@ -323,13 +330,13 @@ def main_ours(args):
         # Two captured graphs of the same step (same model, same optimiser), each with its own static input buffers: the
         # copy stream fills graph B's inputs from pinned host memory while graph A runs -- no device-to-device staging copy.
         gstep2 = GraphedTrainStep(model, opt, lambda lg, m, w: H.cross_entropy(lg, m, w, "pixel"), resident[0],
-                                  grad_sync=sync.allreduce if world > 1 else None)
+                                  grad_sync=sync.allreduce if world > 1 else None, input_fn=loader.image)
         gsteps = [gstep, gstep2]
         slots = [tuple(g_.static_in) for g_ in gsteps]
         _stage("second graph captured (double-buffered inputs)")
     else:
         gsteps = None
-        slots = [tuple(torch.empty_like(t, device=dev) for t in host[0]) for _ in range(2)]
+        slots = [tuple(torch.empty_like(t) for t in resident[0]) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
     losses = []
@@ -338,8 +345,10 @@ def main_ours(args):
         s = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(freed[s])
-            for d, h in zip(slots[s], host[i % NBUF]):
-                d.copy_(h, non_blocking=True)
+            h = host[i % NBUF]
+            slots[s][0].copy_(h[0], non_blocking=True)          # the raw uint8 stack: the only bulk H2D copy
+            loader.labels(h[1], ext, out=slots[s][1])           # mask / pwl: the crop is gathered from pinned host memory
+            loader.labels(h[2], ext, out=slots[s][2])
             ready[s].record(copy_stream)
 
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()     # D2H landing slots for the step's loss
@@ -400,7 +409,8 @@ def main_ours(args):
                 # eager: per-kernel events need individual launches.  No gradient all-reduce here: only rank 0 profiles
                 # (a collective entered by one rank would dead-lock), and the collective is not one of this library's kernels
                 opt.zero_grad(set_to_none=True)
-                H.cross_entropy(model(resident[i % NBUF][0]), resident[i % NBUF][1], resident[i % NBUF][2], "pixel").backward()
+                H.cross_entropy(model(loader.image(resident[i % NBUF][0])), resident[i % NBUF][1], resident[i % NBUF][2],
+                                "pixel").backward()
                 opt.step()
         roof = prof.roofline(peaks, t_step * min(args.steps, 5))
         # DRAM traffic of the dominant kernel: not measurable live (needs ncu); the committed capture of the same command
@@ -436,12 +446,13 @@ def main_ours(args):
                 "data": "synthetic (seeded), random-init weights",
                 "config": {"workload": WORKLOAD, "patch": [C, X, Y, Z], "batch_per_gpu": B, "global_batch": B * world,
                            "precision": args.precision, "parallelism": f"dp{world}", "optimizer": "Adam(fused) lr 1e-3",
+                           "input": "raw uint8 stack [B,Z,Y,X,C] -> hcunet_b200.StackLoader (hcu_load_stack inside the step)",
                            "launch": "one CUDA graph per step (hcunet_b200.graph.GraphedTrainStep)" if use_graph else "eager",
                            "l2": "256 MB buffer zeroed between iterations, its time measured alone and subtracted",
                            "output_voxels_per_step": B * world * 68 * 68 * (Z - 5)},
                 "e2e": {"value": vox_per_step / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                         "d2h_bytes_per_step": 4, "ms_per_step": t_e2e * 1e3,
-                        "note": "pinned fp16 image/mask/pwl -> H2D on a copy stream one step ahead, straight into the static inputs of one of two alternating CUDA graphs; every step's loss copied D2H into pinned memory and read by the host one step later"},
+                        "note": "host inputs = the raw stack as the reference dataloader reads it (uint8 [B,Z,Y,X,C], pinned) + fp16 mask / pwl [B,Z,Y,X] (pinned); per step, on a copy stream one step ahead: the raw stack H2D straight into the static input of one of two alternating CUDA graphs, and the origin crop of mask / pwl that the loss reads (loss.py:51-56) gathered in place from pinned host memory (hcu_load_labels); the graph starts with hcu_load_stack (to_float / reshape / normalize / to_tensor on the device); every step's loss is copied D2H into pinned memory and read by the host one step later"},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
                 "loss_first_last": [losses[0], losses[-1]] if losses else None}
     if world > 1:

@@ -10,10 +10,11 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 17
+# HCUNET_LIB: an alternative build of the SAME library (A/B experiments: tools/build_variant.py); never a fallback
+LIB_PATH = os.environ.get("HCUNET_LIB") or os.path.join(HERE, "libhcunet_b200.so")
+ABI_VERSION = 18
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, U8, U16, F64 = 0, 1, 2, 3, 4, 5
 BATCH_JOB_BYTES = 256
 STAT_BINS = 4
 
@@ -75,6 +76,8 @@ SIGNATURES = {
     "hcu_launch_count": [],
     "hcu_zero": [P, C.c_size_t, P],
     "hcu_h2d_tile": [P, I64, I64, I64, I64, I64, P, P],
+    "hcu_load_stack": [P, I32, I64, I32, I32, I32, I32, C.POINTER(D), C.POINTER(D), P, I32, P],
+    "hcu_load_labels": [P, I32, I64, I32, I32, I32, I32, I32, I32, P, P],
     "hcu_conv_fwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
     "hcu_conv_tc_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_tc_describe": [C.POINTER(HcuConvDesc), C.c_char_p, I32],

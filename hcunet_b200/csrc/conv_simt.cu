@@ -183,6 +183,10 @@ __global__ void __launch_bounds__(kThreads) conv_simt_kernel(ConvK p, const TI* 
                 v.x = v.x < 0.f ? 0.f : v.x; v.y = v.y < 0.f ? 0.f : v.y;
                 v.z = v.z < 0.f ? 0.f : v.z; v.w = v.w < 0.f ? 0.f : v.w;
               }
+              // the transformed operand has the precision of the storage type (fp16 path: same arithmetic as the
+              // tensor-core kernels, whose operand is the fp16-rounded BatchNorm + ReLU output)
+              v.x = to_f(from_f<TI>(v.x)); v.y = to_f(from_f<TI>(v.y));
+              v.z = to_f(from_f<TI>(v.z)); v.w = to_f(from_f<TI>(v.w));
             }
           }
           areg[(i * 2 + h) * 4 + 0] = v.x; areg[(i * 2 + h) * 4 + 1] = v.y;
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__(kThreads) conv_simt_kernel(ConvK p, const TI* 
             if (in_scale != nullptr) {
               v = fmaf(v, sc, sh);
               if (p.in_relu) v = v < 0.f ? 0.f : v;
+              v = to_f(from_f<TI>(v));
             }
           }
           areg[i * KC + kk] = v;
@@ -470,7 +475,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(ConvK p, const TA* __re
         for (int i = 0; i < 8; ++i) {
           float t = fmaf(av[i], asc[i], ash[i]);
           if (p.in_relu) t = t < 0.f ? 0.f : t;
-          av[i] = (i < na) ? t : 0.f;
+          av[i] = (i < na) ? to_f(from_f<TA>(t)) : 0.f;
         }
       }
       if (VB) {

@@ -391,6 +391,10 @@ class UnetEngine:
                        "conv_tc_fwd")
             return False
         w = self._gather_w(wm, ref, nw)
+        if d.dtype_in == _lib.F16:
+            # fp16 path on the FFMA kernel (channel pitches that are not a multiple of 8): same arithmetic as the tensor-core
+            # kernels -- fp16 operands (the packed weights are fp16 there), fp32 accumulate
+            w = w.half().float()
         _lib.note(layer, nbytes, flops)
         _lib.check(lib.hcu_conv_fwd(C.byref(d), _ptr(x), _ptr(w), _ptr(bias), _ptr(in_scale), _ptr(in_shift),
                                     _ptr(out_scale), _ptr(out_shift), _ptr(out), _ptr(stats), self._stream()),
@@ -465,8 +469,9 @@ class UnetEngine:
     # (the next conv's operand load, the max-pool pass, the weight-gradient's operand load).  Only y tensors, pooled
     # activations and the up-convolution outputs exist in HBM.
     def forward(self, params: Dict[str, torch.Tensor], buffers: Dict[str, torch.Tensor], x: torch.Tensor,
-                training: bool, save: bool, precision: str = "fp32"):
-        """Returns (logits [B, Cout, *spatial] fp32, saved-state or None)."""
+                training: bool, save: bool, precision: str = "fp32", prelaid: bool = False):
+        """Returns (logits [B, Cout, *spatial] fp32, saved-state or None).  ``prelaid``: ``x`` is the channels-last fp16 view
+        ``hcunet_b200.loader.StackLoader.image`` produced (pitch 8, zero padding): the mixed path reads its storage as is."""
         lib, st = self.lib, self._stream()
         plan = self.plan(x.shape)
         dev = x.device
@@ -489,16 +494,21 @@ class UnetEngine:
         adt = _DT[act_dtype]
         esz = 2 if act_dtype == torch.float16 else 4
         B = plan.batch
-        x = x.contiguous()
-        if x.dtype not in _DT:
-            x = x.float()
         S = plan.in_sz[0] * plan.in_sz[1] * plan.in_sz[2]
         # fp16 path: pad the input channels to a multiple of 8 (16-byte pixels) so the first conv is tensor-core too
         cp = -(-plan.in_channels // 8) * 8 if act_dtype == torch.float16 else plan.in_channels
-        cur = torch.empty((B, S, cp), dtype=act_dtype, device=dev)
-        _lib.note("input", x.numel() * x.element_size() + cur.numel() * esz, 0)
-        _lib.check(lib.hcu_nc_to_cl(_ptr(x), _DT[x.dtype], _ptr(cur), adt, B, plan.in_channels, S, cp, None, st),
-                   "nc_to_cl")
+        want = (S * cp, 1) + tuple(s * cp for s in (plan.in_sz[1] * plan.in_sz[2], plan.in_sz[2], 1)[:plan.dims])
+        if prelaid and act_dtype == torch.float16 and x.dtype == torch.float16 and cp == 8 and tuple(x.stride()) == want \
+                and x.data_ptr() % 16 == 0:
+            cur = x.as_strided((B, S, cp), (S * cp, cp, 1))     # the loader's storage, no layout pass
+        else:
+            x = x.contiguous()
+            if x.dtype not in _DT:
+                x = x.float()
+            cur = torch.empty((B, S, cp), dtype=act_dtype, device=dev)
+            _lib.note("input", x.numel() * x.element_size() + cur.numel() * esz, 0)
+            _lib.check(lib.hcu_nc_to_cl(_ptr(x), _DT[x.dtype], _ptr(cur), adt, B, plan.in_channels, S, cp, None, st),
+                       "nc_to_cl")
         self._tap("input", cur, plan.in_channels, plan.in_sz)
         xf = None  # pending (scale, shift) + ReLU to apply when `cur` is read
         saved = [] if save else None
@@ -596,7 +606,10 @@ class UnetEngine:
         if cache is not None:
             cache.fwd_done = True
         self._cache = None
-        return logits, (plan, saved, act_dtype, training, cache)
+        # the packed weights / job tables of the step cache are shared by every forward with the same key: a backward must
+        # run against the parameters its forward saw (autograd's version check, which the detached views bypass)
+        versions = tuple(p._version for p in params.values())
+        return logits, (plan, saved, act_dtype, training, cache, versions)
 
     def _pool(self, y, g: ConvGeom, B, act_dtype, scale, shift, relu, want_argmax=True):
         adt = _DT[act_dtype]
@@ -649,7 +662,10 @@ class UnetEngine:
     def backward(self, params: Dict[str, torch.Tensor], state, dlogits: torch.Tensor, need_dx: bool):
         """Returns ({param name: grad}, dx or None)."""
         lib, st = self.lib, self._stream()
-        plan, saved, act_dtype, training, cache = state
+        plan, saved, act_dtype, training, cache, versions = state
+        if versions != tuple(p._version for p in params.values()):
+            raise RuntimeError("hcunet_b200: a parameter was modified in place (e.g. optimizer.step()) between this forward and "
+                               "its backward; the step's packed weights no longer match what the forward computed with")
         self._cache = cache
         batched = cache is not None and cache.ready and cache.scatter_table is not None
         self._gflat = torch.empty(cache.g_total, dtype=torch.float32, device=dlogits.device) if batched else None
@@ -721,7 +737,7 @@ class UnetEngine:
                 npix = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2]
                 pool_arg, pool_geom = None, None
                 if (argmax is not None and act_dtype == torch.float16 and g.cout_t % 8 == 0 and 256 % (g.cout_t // 8) == 0
-                        and dcur_dt == _lib.F16):
+                        and g.cout_t <= 512 and dcur_dt == _lib.F16):  # the h8 kernels take up to 512 channels
                     # fp16: the max-pool backward is fused into the two BN-backward passes (no full-resolution dA)
                     pool_arg = argmax
                     pool_geom = _lib.HcuPoolGeom(B, g.out_sz[0], g.out_sz[1], g.out_sz[2], g.pool[0], g.pool[1], g.pool[2])

@@ -26,8 +26,13 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, optimizer, loss_fn: Callable, example: Sequence[torch.Tensor],
-                 grad_sync: Optional[Callable] = None, warmup: int = 3):
+                 grad_sync: Optional[Callable] = None, warmup: int = 3, input_fn: Optional[Callable] = None):
+        if warmup < 3:
+            # steps 1-2 record the engine's step cache (per-layer packs, a synchronous table upload): not capturable
+            raise ValueError("GraphedTrainStep needs warmup >= 3 (the first two steps record the engine's step cache)")
         self.model, self.optimizer, self.loss_fn, self.grad_sync = model, optimizer, loss_fn, grad_sync
+        # input_fn(static_in[0]) -> model input, captured with the step (e.g. StackLoader.image on a raw uint8 stack)
+        self.input_fn = input_fn
         self.static_in = [torch.empty_like(t, device=t.device) for t in example]
         for s, t in zip(self.static_in, example):
             s.copy_(t)
@@ -58,7 +63,8 @@ class GraphedTrainStep:
 
     def _fwd_bwd(self):
         self.optimizer.zero_grad(set_to_none=True)
-        logits = self.model(self.static_in[0])
+        x = self.static_in[0] if self.input_fn is None else self.input_fn(self.static_in[0])
+        logits = self.model(x)
         self.loss = self.loss_fn(logits, *self.static_in[1:])
         self.loss.backward()
 

@@ -78,7 +78,7 @@ class _UnetFunction(torch.autograd.Function):
         names = module._param_names
         pd = {n: p.detach() for n, p in zip(names, params)}
         logits, state = module._engine.forward(pd, module._buffer_dict(), x.detach(), training=module.training,
-                                               save=need_grad, precision=module.precision)
+                                               save=need_grad, precision=module.precision, prelaid=module._x_prelaid)
         ctx.module = module
         ctx.state = state
         ctx.pd = pd
@@ -168,6 +168,7 @@ class Unet_Constructor(nn.Module):
         if self.precision not in _PRECISIONS:
             raise ValueError(f"HCUNET_PRECISION must be one of {_PRECISIONS}, not {self.precision}")
         self._engine = UnetEngine(self.model_specification)
+        self._x_prelaid = False
         self._param_names = [n for n, _ in self.named_parameters()]
         self._buffer_names = [n for n, _ in self.named_buffers()]
 
@@ -190,6 +191,7 @@ class Unet_Constructor(nn.Module):
         # reference's RuntimeError semantics before any kernel is launched
         self._engine.plan(tuple(x.shape))
         need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        self._x_prelaid = bool(getattr(x, "_hcu_cl8", False))   # hcunet_b200.loader.StackLoader.image output
         return _UnetFunction.apply(self, need_grad, x, *params)
 
     # ---- unet.py:145-165 --------------------------------------------------------------------

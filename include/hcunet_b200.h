@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 17
+#define HCU_ABI_VERSION 18
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -49,7 +49,8 @@ typedef enum HcuStatus {
 } HcuStatus;
 
 /* activations / gradients are HCU_F32 or HCU_F16; HCU_BF16 is accepted for loss masks / weights only */
-typedef enum HcuDType { HCU_F32 = 0, HCU_BF16 = 1, HCU_F16 = 2 } HcuDType;
+/* HCU_U8 / HCU_U16 / HCU_F64: source types of the input path only (hcu_load_stack / hcu_load_labels) */
+typedef enum HcuDType { HCU_F32 = 0, HCU_BF16 = 1, HCU_F16 = 2, HCU_U8 = 3, HCU_U16 = 4, HCU_F64 = 5 } HcuDType;
 
 /* ---- library ------------------------------------------------------------------------------ */
 int hcu_abi_version(void);
@@ -66,6 +67,22 @@ int hcu_zero(void* ptr, size_t bytes, void* stream);
  * of the tile on the host first. */
 int hcu_h2d_tile(const void* src, int64_t planes, int64_t src_plane_pitch, int64_t rows, int64_t src_row_pitch,
                  int64_t row_bytes, void* dst, void* stream);
+
+/* ---- input path ---------------------------------------------------------------------------------
+ * hcu_load_stack: the RAW stack as skimage.io.imread yields it, src = [b][z][y][x][c] uint8 / uint16 (device memory), ->
+ * dst = fp16 channels-last [b][x][y][z][dst_cpitch = 8] (channels >= c zero), value half((v / 2^bits - mean[c]) / std[c])
+ * computed in float64 and converted like torch does (double -> float -> half): bit-identical to the reference chain.
+ * mean / std: HOST arrays of c doubles.
+ * Replaces: Stack.__getitem__ (dataloader.py:68-92) with to_float (transforms.py:94-113), reshape (transforms.py:139-157),
+ * normalize (transforms.py:257-282), to_tensor (transforms.py:118-136) -- and the engine's own NCDHW -> NDHWC pass.
+ * hcu_load_labels: mask / pwl, src = [b][z][y][x] (uint8 / uint16: to_float's 1/2^bits scaling; fp16 / fp32 / fp64: as is;
+ * device memory OR pinned host memory read in place), -> dst = fp16 [b][1][ox][oy][oz], the ORIGIN CROP of extent
+ * (ox, oy, oz) <= (x, y, z): the only part of them the loss reads (loss.py:51-56).
+ * Replaces: the same chain for mask / pwl + the origin crop of loss.py:51-56. */
+int hcu_load_stack(const void* src, int32_t dtype_src, int64_t b, int32_t z, int32_t y, int32_t x, int32_t c,
+                   const double* mean, const double* stdv, void* dst, int32_t dst_cpitch, void* stream);
+int hcu_load_labels(const void* src, int32_t dtype_src, int64_t b, int32_t z, int32_t y, int32_t x, int32_t ox, int32_t oy,
+                    int32_t oz, void* dst, void* stream);
 
 /* ---- generic gather-convolution descriptor -------------------------------------------------
  * One launch computes, for every output position o = (n, ox, oy, oz) of an OX*OY*OZ grid and

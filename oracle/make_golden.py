@@ -84,6 +84,83 @@ def mint_model_case(name, kwargs, xshape, seed):
           f"bytes {os.path.getsize(os.path.join(OUT, name + '.pt'))}")
 
 
+FULL_CASES = {
+    # BASELINE.json configs at their full sizes.  name: (ctor kwargs, input shape, seed)
+    "full_cfg1": (README_3D, (1, 4, 256, 256, 32), 0),          # configs[0] with the 256 x 256 correction
+    "full_cfg2": (README_3D, (4, 4, 256, 256, 32), 0),          # configs[1]: the benchmarked train step, batch 4
+    "full_cfg3": (dict(image_dimensions=2, in_channels=3, out_channels=2, feature_sizes=[32, 64, 128, 256, 512, 1024],
+                       kernel=(3, 3), upsample_kernel=(2, 2), max_pool_kernel=(2, 2), upsample_stride=2, dilation=1,
+                       groups=1), (2, 3, 572, 572), 0),          # configs[2] at batch 2 (batch 16 needs ~100 GB on the CPU)
+}
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def mint_full_case(name, kwargs, xshape, seed):
+    """Full-size fixture: the UNMODIFIED reference's logits / loss / gradients (sampled where large) + its own fp64
+    reproducibility floor, and the fp16-storage emulation's (oracle/mixed_oracle.py) with its accumulation-order floor --
+    computed here so that the GPU box only loads them."""
+    import time
+
+    from oracle import mixed_oracle as M
+    from oracle import unet_oracle as O
+
+    t0 = time.time()
+    loss_mod = load_reference_loss()
+    model, sd0 = O.seeded_state_dict(build_reference_unet, kwargs, seed)
+    x, mask, pwl = golden_inputs(kwargs, xshape, seed)
+    model.train()
+    logits = model(x)
+    loss = loss_mod.cross_entropy(logits, mask, pwl, "pixel")
+    loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters()}
+    buf1 = {k: v.detach().clone() for k, v in model.state_dict().items() if "running_" in k or "num_batches" in k}
+    print(f"{name}: reference step {time.time() - t0:.1f}s", flush=True)
+    # eval-mode logits with running statistics := this batch's statistics (keeps the network alive)
+    bstats = O.batch_statistics_buffers(sd0, buf1)
+    model.load_state_dict({**sd0, **bstats})
+    model.eval()
+    with torch.no_grad():
+        logits_eval = model(x)
+    # fp32 reproducibility floor: the reference in float64
+    model64, _ = O.seeded_state_dict(build_reference_unet, kwargs, seed)
+    model64 = model64.double().train()
+    l64 = model64(x.double())
+    loss_mod.cross_entropy(l64, mask.double(), pwl.double(), "pixel").backward()
+    floor32 = {k: _rel(grads[k], p.grad) for k, p in model64.named_parameters()}
+    floor32["logits"] = _rel(logits.detach(), l64.detach())
+    del model64, l64
+    print(f"{name}: fp64 floor {time.time() - t0:.1f}s (logits {floor32['logits']:.1e})", flush=True)
+    # fp16-storage emulation + its accumulation-order floor
+    (eloss, elogits, egrads, ebuf), floor16 = M.accumulation_floor(sd0, kwargs, x, mask, pwl)
+    elogits_eval, eval_spread, eval_agree = M.eval_accumulation_floor({**sd0, **bstats}, kwargs, x)
+    print(f"{name}: emulation {time.time() - t0:.1f}s (logits floor {floor16['logits']:.1e})", flush=True)
+    fx = dict(kwargs=kwargs, seed=seed, xshape=tuple(xshape), torch_version=torch.__version__,
+              state_checksum=O.state_checksum(sd0),
+              input_checksum=float(x.double().sum() + mask.double().sum() + pwl.double().sum()),
+              logits_train=logits.detach(), loss=loss.detach(), logits_eval=logits_eval, eval_buffers=bstats,
+              buffers_after=buf1,
+              grad_norm={k: float(g.double().norm()) for k, g in grads.items()},
+              grad_sample={k: O.sample_tensor(g, k) for k, g in grads.items()},
+              floor32=floor32,
+              emu=dict(logits_train=elogits, loss=eloss, logits_eval=elogits_eval, eval_floor=eval_spread,
+                       eval_agree_floor=eval_agree, buffers_after={k: v for k, v in ebuf.items()},
+                       grad_norm={k: float(g.double().norm()) for k, g in egrads.items()},
+                       grad_sample={k: O.sample_tensor(g, k) for k, g in egrads.items()}, floor=floor16,
+                       vs_fp32=dict(logits=_rel(elogits, logits.detach()),
+                                    agree_eval=float(((elogits_eval > 0) == (logits_eval > 0)).float().mean()))))
+    if name == "full_cfg2":  # same patch as full_cfg1, whose eval logits are stored: keep this fixture under 5 MB
+        for d in (fx, fx["emu"]):
+            d.pop("logits_eval")
+    torch.save(fx, os.path.join(OUT, name + ".pt"))
+    print(f"{name}: logits {tuple(logits.shape)} loss {loss.item():.6f} emu-vs-fp32 logits {fx['emu']['vs_fp32']['logits']:.2e} "
+          f"eval agreement {fx['emu']['vs_fp32']['agree_eval']:.5f} bytes {os.path.getsize(os.path.join(OUT, name + '.pt'))}",
+          flush=True)
+
+
 def mint_loss_cases():
     loss_mod = load_reference_loss()
     g = torch.Generator().manual_seed(77)
@@ -124,11 +201,53 @@ def mint_loss_cases():
     print("loss_cases:", len(out["cases"]))
 
 
+def mint_loader_cases():
+    """Input path: seeded raw stacks through the UNMODIFIED reference transforms (`transforms.py`: to_float -> reshape ->
+    normalize -> to_tensor; mask / pwl: to_float -> reshape -> to_tensor), as `Stack.__getitem__` composes them
+    (`dataloader.py:68-92`, `tests/transforms_test.py:22-52`)."""
+    import numpy as np
+
+    from oracle.ref_loader import load_reference_transforms
+
+    t = load_reference_transforms()
+    rng = np.random.default_rng(123)
+    cases = []
+    specs = [  # (shape [Z, Y, X, C] or [Y, X, C], dtype, mean, std)
+        ((6, 10, 12, 4), np.uint8, None, None),
+        ((35, 3, 70, 4), np.uint8, None, None),                      # crosses the 32 x 32 transpose tiles, ragged
+        ((5, 9, 33, 4), np.uint16, [0.4, 0.5, 0.45, 0.55], [0.2, 0.25, 0.3, 0.22]),
+        ((4, 6, 34, 2), np.uint16, [0.1, 0.9], [0.7, 0.3]),          # channel count != 4: scalar loads
+        ((40, 37, 3), np.uint8, [0.5, 0.4, 0.3], [0.5, 0.25, 0.125]),  # 2D
+    ]
+    for shape, dt, mean, std in specs:
+        hi = 256 if dt == np.uint8 else 65536
+        img = rng.integers(0, hi, size=shape, dtype=dt)
+        mask = (rng.random(shape[:-1]) > 0.5).astype(np.uint8) * 255
+        pwl = rng.integers(0, 65536, size=shape[:-1], dtype=np.uint16)
+        image, m, w = t.to_float()([img.copy(), np.expand_dims(mask, mask.ndim), np.expand_dims(pwl, pwl.ndim)])
+        image, m, w = t.reshape()([image, m, w])
+        image = t.normalize(mean, std)(image)
+        image, m, w = t.to_tensor()([image, m, w])
+        cases.append(dict(raw=torch.from_numpy(img.view(np.int16) if dt == np.uint16 else img), raw_dtype=str(np.dtype(dt)),
+                          mask_raw=torch.from_numpy(mask), pwl_raw=torch.from_numpy(pwl.view(np.int16)), mean=mean, std=std,
+                          image=image.contiguous(), mask=m.contiguous(), pwl=w.contiguous()))
+    torch.save({"torch_version": torch.__version__, "numpy_version": np.__version__, "cases": cases},
+               os.path.join(OUT, "loader_cases.pt"))
+    print("loader_cases:", len(cases), os.path.getsize(os.path.join(OUT, "loader_cases.pt")), "bytes")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    for name, (kwargs, xshape, seed) in CASES.items():
-        mint_model_case(name, kwargs, xshape, seed)
-    mint_loss_cases()
+    which = sys.argv[1:] or ["small", "full"]
+    if "small" in which:
+        for name, (kwargs, xshape, seed) in CASES.items():
+            mint_model_case(name, kwargs, xshape, seed)
+        mint_loss_cases()
+    if "small" in which or "loader" in which:
+        mint_loader_cases()
+    for name, (kwargs, xshape, seed) in FULL_CASES.items():
+        if "full" in which or name in which:
+            mint_full_case(name, kwargs, xshape, seed)
 
 
 if __name__ == "__main__":

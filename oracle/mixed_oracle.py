@@ -31,6 +31,15 @@ import torch.nn.functional as F
 
 from .unet_oracle import cross_entropy, normalise_spec
 
+FLOOR_FACTOR = 4.0
+"""A tensor's gate is max(stated tolerance, FLOOR_FACTOR x its measured accumulation-order floor): the floor is the largest of
+three samples of a heavy-tailed spread, the implementation under test is a fourth draw."""
+
+
+def gate(stated: float, floor: float) -> float:
+    return max(stated, FLOOR_FACTOR * floor)
+
+
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 GRAD_SCALE_TARGET = 64.0
@@ -61,10 +70,11 @@ def _cshape(v, ndim):
 
 
 ACCUMULATE = "fp32"
-"""How the fp32 accumulation of the convolutions is carried out: "fp32" (oneDNN's order), "fp64" (accumulate in double,
-round once) or "split" (two half-K partial sums added at the end).  All three are legitimate fp32-accumulate results; the
-spread between them is the ACCUMULATION-ORDER FLOOR of a case (``accumulation_floor``): how far two correct
-implementations of the same fp16-storage arithmetic may differ on it."""
+"""How the fp32 accumulations are carried out: "fp32" (oneDNN's order, BatchNorm statistics reduced in fp64), "fp64"
+(convolutions accumulated in double, rounded once), "split" (two half-K partial sums added at the end) or "stats32"
+(BatchNorm sums and sums of squares reduced in fp32, as the conv epilogues' per-CTA partial sums are: ~1e-6 relative on
+mean / variance).  All are legitimate results of the same fp16-storage arithmetic; the spread between them is the
+ACCUMULATION-ORDER FLOOR of a case (``accumulation_floor``): how far two correct implementations may differ on it."""
 
 
 def _conv_fn(dims, transposed):
@@ -141,9 +151,13 @@ def train_step(sd: Dict[str, torch.Tensor], spec: dict, x, mask, pwl, method="pi
         red = [0] + list(range(2, y32.dim()))
         n = y32.numel() // y32.shape[1]
         if training:
-            yd = y32.double()
-            mu = yd.mean(dim=red)
-            var = ((yd * yd).mean(dim=red) - mu * mu).clamp_min(0.0)
+            if ACCUMULATE == "stats32":
+                mu = y32.sum(dim=red).double() / n
+                var = ((y32 * y32).sum(dim=red).double() / n - mu * mu).clamp_min(0.0)
+            else:
+                yd = y32.double()
+                mu = yd.mean(dim=red)
+                var = ((yd * yd).mean(dim=red) - mu * mu).clamp_min(0.0)
             invstd = (1.0 / torch.sqrt(var + BN_EPS)).float()
             mean = mu.float()
             unbiased = var * n / (n - 1) if n > 1 else var
@@ -316,8 +330,8 @@ def eval_forward(sd: Dict[str, torch.Tensor], spec: dict, x, emulate=True, taps:
 
 def accumulation_floor(sd, spec, x, mask, pwl, base=None, method="pixel"):
     """Per-tensor spread of the emulated step under a change of the fp32 accumulation order (see ``ACCUMULATE``).
-    Returns (base result, {"logits": rel-L2, "agree": fraction, param name: rel-L2}) -- the largest deviation of the "fp64"
-    and "split" variants from the default one."""
+    Returns (base result, {"logits": rel-L2, "agree": fraction, param name: rel-L2}) -- the largest deviation of the "fp64",
+    "split" and "stats32" variants from the default one."""
     global ACCUMULATE
 
     def rel(a, b):
@@ -329,7 +343,7 @@ def accumulation_floor(sd, spec, x, mask, pwl, base=None, method="pixel"):
     floor = {"logits": 0.0, "agree": 1.0}
     saved = ACCUMULATE
     try:
-        for mode in ("fp64", "split"):
+        for mode in ("fp64", "split", "stats32"):
             ACCUMULATE = mode
             _, lg, gr, _ = train_step(sd, spec, x, mask, pwl, method)
             floor["logits"] = max(floor["logits"], rel(lg, base[1]))
@@ -339,3 +353,20 @@ def accumulation_floor(sd, spec, x, mask, pwl, base=None, method="pixel"):
     finally:
         ACCUMULATE = saved
     return base, floor
+
+
+def eval_accumulation_floor(sd, spec, x):
+    """(eval logits of the emulation, their accumulation-order spread as rel-L2, worst thresholded-mask agreement)."""
+    global ACCUMULATE
+    base = eval_forward(sd, spec, x)
+    spread, agree = 0.0, 1.0
+    saved = ACCUMULATE
+    try:
+        for mode in ("fp64", "split"):
+            ACCUMULATE = mode
+            lg = eval_forward(sd, spec, x)
+            spread = max(spread, float((lg.double() - base.double()).norm() / base.double().norm().clamp_min(1e-30)))
+            agree = min(agree, float(((lg > 0) == (base > 0)).float().mean()))
+    finally:
+        ACCUMULATE = saved
+    return base, spread, agree

@@ -119,6 +119,53 @@ def load_reference_loss():
     return _load("loss", os.path.join(REFERENCE_ROOT, "hcat", "loss.py"))
 
 
+def load_reference_transforms():
+    """The reference ``hcat/transforms.py`` (unmodified source, build container only -- it is not staged).  Its imports of
+    skimage / elasticdeform (absent from this image) are satisfied by empty stub modules: the deterministic transforms
+    this project mirrors (``to_float``, ``reshape``, ``normalize``, ``to_tensor``) are numpy / torch only."""
+    path = os.path.join("/root/reference", "hcat", "transforms.py")
+    if not os.path.isfile(path):
+        raise FileNotFoundError("reference transforms not mounted")
+    key = ("transforms", path)
+    if key in _cache:
+        return _cache[key]
+    names = ["skimage", "skimage.exposure", "skimage.transform", "skimage.io", "skimage.morphology", "elasticdeform", "cv2"]
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        for k in names:
+            try:
+                __import__(k)
+            except Exception:
+                m = types.ModuleType(k)
+                m.__path__ = []
+                sys.modules[k] = m
+        for k in names:   # `import skimage.io as io` needs the attribute on the parent stub
+            if "." in k:
+                parent, child = k.rsplit(".", 1)
+                if not hasattr(sys.modules[parent], child):
+                    setattr(sys.modules[parent], child, sys.modules[k])
+        import numpy as np
+
+        had_float = "float" in np.__dict__
+        if not had_float:
+            np.float = float   # the reference's era of numpy still had this alias (annotations at transforms.py:190 ...)
+        try:
+            spec = importlib.util.spec_from_file_location("_hcat_reference.transforms", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        finally:
+            if not had_float:
+                del np.float
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cache[key] = mod
+    return mod
+
+
 def build_reference_unet(**kwargs):
     """Construct the reference Unet_Constructor.
 

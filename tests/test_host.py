@@ -173,3 +173,39 @@ def test_every_conv_of_the_baseline_configs_gets_a_tensor_core_kernel():
     assert describe(d).startswith("ks M=256 Nc=256 nsplit=1 PC=4")
     d.reserved[0], d.reserved[1] = 1, 0
     assert describe(d).startswith(("classic ", "unsupported"))
+
+
+def test_checkpoints_interchange_with_the_reference_both_ways(tmp_path):
+    """`unet.py:145-196`: a file written by the UNMODIFIED reference's save() loads into this implementation (same
+    state_dict bit for bit, same model_specification, eval mode, hyperparameters returned) and vice versa."""
+    from oracle import ref_loader as R
+
+    if not R.reference_available():
+        pytest.skip("reference modules not available (neither /root/reference nor oracle/_ref)")
+    import hcunet_b200 as H
+
+    kwargs = dict(O.README_3D, feature_sizes=[4, 8])
+    cwd = os.getcwd()
+    os.chdir(tmp_path)   # save() snapshots ./**/*.py (unet.py:150-160): keep that small
+    try:
+        torch.manual_seed(3)
+        ref = R.build_reference_unet(**kwargs)
+        assert ref.save("ref.unet", hyperparameters={"lr": 3e-4}) is None
+        mine = H.Unet_Constructor(image_dimensions=3, in_channels=1, out_channels=1, feature_sizes=[2, 4], kernel=(3, 3, 1),
+                                  upsample_kernel=(2, 2, 1), max_pool_kernel=(2, 2, 1), upsample_stride=(2, 2, 1))
+        assert mine.load("ref.unet", to_cuda=False) == {"lr": 3e-4}
+        assert not mine.training and mine.model_specification == ref.model_specification
+        for k, v in ref.state_dict().items():
+            assert torch.equal(mine.state_dict()[k], v), k
+        # and back: this implementation's file into the reference
+        torch.manual_seed(4)
+        src = H.Unet_Constructor(**kwargs)
+        src.save("mine.unet", hyperparameters=[1, 2])
+        back = R.build_reference_unet(**dict(kwargs, feature_sizes=[2, 4]))
+        assert back.load("mine.unet", to_cuda=False) == [1, 2]
+        for k, v in src.state_dict().items():
+            assert torch.equal(back.state_dict()[k], v), k
+        blob = torch.load("mine.unet", weights_only=False)
+        assert set(blob) == {"state_dict", "model_specifications", "hyperparameters", "python_files", "tree_structure"}
+    finally:
+        os.chdir(cwd)
