@@ -287,14 +287,17 @@ class _StepCache:
         if m:
             maps = (HcuWeightMap * m)(*[j[0] for j in self.scatter_jobs.values()])
             nsp = (C.c_int32 * m)(*[j[1] for j in self.scatter_jobs.values()])
-            po, go, pc, gc = [], [], 0, 0
+            p_off, acc = {}, 0   # offsets of every parameter in the step's ONE flat gradient buffer (parameter order)
+            for name, p in params.items():
+                p_off[name] = acc
+                acc += p.numel()
+            po, go, pc = [], [], 0
             for name, j in self.scatter_jobs.items():
-                self.part_off[name], self.g_off[name] = pc, gc
+                self.part_off[name], self.g_off[name] = pc, p_off[name]
                 po.append(pc)
-                go.append(gc)
+                go.append(p_off[name])
                 pc += j[1] * j[2]
-                gc += params[name].numel()
-            self.g_total = gc
+            self.g_total = acc
             host = C.create_string_buffer(m * _lib.BATCH_JOB_BYTES)
             blocks = C.c_int32(0)
             _lib.check(lib.hcu_weight_scatter_batch_build(maps, nsp, (C.c_int64 * m)(*po), (C.c_int64 * m)(*go), m, host,
@@ -324,6 +327,8 @@ class UnetEngine:
         self._side2 = None
         self.n_side = int(os.environ.get("HCUNET_SIDE_STREAMS", "1"))  # 2 was measured: no gain
         self._keep: List[torch.Tensor] = []
+        self.last_grad_flat: Optional[torch.Tensor] = None   # the flat gradient buffer of the latest backward
+        self._goff: Dict[str, tuple] = {}
         # Test instrumentation (tests/test_gpu_teacher.py): ``tap(tag, tensor, channels, spatial)`` is called on the current
         # stream right after every stored tensor of a step has been produced (channels-last [B, S, C pitch]); it may read
         # the tensor or overwrite it in place.  None in normal operation.
@@ -668,7 +673,14 @@ class UnetEngine:
                                "its backward; the step's packed weights no longer match what the forward computed with")
         self._cache = cache
         batched = cache is not None and cache.ready and cache.scatter_table is not None
-        self._gflat = torch.empty(cache.g_total, dtype=torch.float32, device=dlogits.device) if batched else None
+        # ONE flat fp32 buffer holds every parameter gradient of the step, in parameter order; the gradients handed to autograd
+        # are views of it, so a data-parallel all-reduce runs on it in place (hcunet_b200.parallel.GradSync), no gather copies
+        self._goff, acc = {}, 0
+        for name, p in params.items():
+            self._goff[name] = (acc, p.shape)
+            acc += p.numel()
+        self._gflat = torch.empty(acc, dtype=torch.float32, device=dlogits.device)
+        self.last_grad_flat = self._gflat
         side = None
         if batched and self.overlap_wgrad and _lib._ProfState.profiler is None:
             if self._side is None or self._side.device != dlogits.device:
@@ -726,7 +738,8 @@ class UnetEngine:
             if kind == "out":
                 _, g, a_in, a_cp, a_xf = item
                 npix = B * So
-                grads[g.name + ".bias"] = self._colsum(dcur, dcur_dt, npix, co, scratch, cpitch=dcur_cp)
+                grads[g.name + ".bias"] = self._colsum(dcur, dcur_dt, npix, co, scratch, cpitch=dcur_cp,
+                                                       out=self._gview(g.name + ".bias"))
                 grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, a_cp, a_xf, adt, dcur, dcur_dt, B,
                                                              params[g.name + ".weight"], dy_cp=dcur_cp)
                 dcur = self._dgrad_conv(g, dcur, dcur_dt, B, params[g.name + ".weight"], act_dtype, dy_cp=dcur_cp)
@@ -751,9 +764,8 @@ class UnetEngine:
                 sums = zero_ws[zoff:zoff + 2 * g.cout_t * SB]
                 zoff += 2 * g.cout_t * SB
                 _lib.note(g.name, 2 * npix * g.cout_t * esz, 0)
-                dgamma = torch.empty(g.cout_t, dtype=torch.float32, device=dev)
-                dbeta = torch.empty_like(dgamma)
-                dbias = torch.empty_like(dgamma)
+                dgamma, dbeta = self._gview(g.bn + ".weight"), self._gview(g.bn + ".bias")
+                dbias = self._gview(g.name + ".bias")
                 coef = torch.empty((3, g.cout_t), dtype=torch.float32, device=dev)
                 fin = _lib.HcuBnBwdFin(float(npix), params[g.bn + ".weight"].data_ptr(), 1 if training else 0, 1.0,
                                        inv.data_ptr() if inv is not None else None, dgamma.data_ptr(), dbeta.data_ptr(),
@@ -788,7 +800,7 @@ class UnetEngine:
             else:  # "up"
                 _, u, a_in, a_cp, a_xf = item
                 npix_out = B * u.out_sz[0] * u.out_sz[1] * u.out_sz[2]
-                grads[u.name + ".bias"] = self._colsum(dcur, dcur_dt, npix_out, u.cout, scratch)
+                grads[u.name + ".bias"] = self._colsum(dcur, dcur_dt, npix_out, u.cout, scratch, out=self._gview(u.name + ".bias"))
                 T = u.k[0] * u.k[1] * u.k[2]
                 m = B * u.in_sz[0] * u.in_sz[1] * u.in_sz[2]
                 wt = params[u.name + ".weight"]
@@ -849,6 +861,7 @@ class UnetEngine:
             cache.bwd_done = True
         self._keep.clear()
         self._cache, self._gflat, self._wstream = None, None, None
+        self.last_grad_names = list(grads.keys())
         return grads, dx
 
     def _materialise(self, t, cp, xf, npix, c, act_dtype):
@@ -861,10 +874,19 @@ class UnetEngine:
                                               self._stream()), "bn_relu_apply")
         return a
 
-    def _colsum(self, x, dt, npix, c, scratch, cpitch=None):
+    def _gview(self, name):
+        """The slice of the step's flat gradient buffer that belongs to parameter ``name``."""
+        off, shape = self._goff[name]
+        n = 1
+        for s in shape:
+            n *= s
+        return self._gflat[off:off + n].view(shape)
+
+    def _colsum(self, x, dt, npix, c, scratch, cpitch=None, out=None):
         """Per-channel sum (bias gradients of the layers without a BatchNorm behind them).  Only a gradient comes out of
         it, so with a side stream it leaves the data-gradient chain like the weight gradients do."""
-        out = torch.empty(c, dtype=torch.float32, device=x.device)
+        if out is None:
+            out = torch.empty(c, dtype=torch.float32, device=x.device)
         side = getattr(self, "_wstream", None)
         if side is not None:
             ev = torch.cuda.Event()
@@ -908,8 +930,7 @@ class UnetEngine:
         if cache is not None and cache.ready and wname in cache.part_off and cache.scatter_jobs[wname][1:] == (nsplit, total):
             off = cache.part_off[wname]
             part = cache.wacc[off:off + nsplit * total]
-            goff = cache.g_off[wname]
-            gw = self._gflat[goff:goff + wref.numel()].view(wref.shape)
+            gw = self._gview(wname)
             side = self._wstream
             if side is not None:
                 if self.n_side > 1:  # alternate two gradient streams: the small deep-level kernels overlap each other too
@@ -933,7 +954,7 @@ class UnetEngine:
                                                           nsplit, self._stream()), "wgrad")
             return gw
         partial = torch.empty((nsplit, total), dtype=torch.float32, device=wref.device)
-        gw = torch.empty_like(wref)
+        gw = self._gview(wname)
         _lib.note(*note)
         if tc5 or ws:
             partial.zero_()

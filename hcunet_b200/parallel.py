@@ -1,7 +1,7 @@
 """Data-parallel plumbing for the training path: one process per GPU, patches sharded
 across ranks, ONE exchange step per iteration -- the fp32 mean all-reduce of the parameter gradients
-(727 009 floats = 2.9 MB for the README model).  BatchNorm uses per-rank batch statistics (plain DDP
-semantics); buffers and parameters are broadcast from rank 0 at construction.
+(727 009 floats = 2.9 MB for the README model), in place on the engine's flat gradient buffer.  BatchNorm uses per-rank
+batch statistics (plain DDP semantics); buffers and parameters are broadcast from rank 0 at construction.
 
 The reference has no distributed code at all; this is the build's only collective.
 Works on NCCL (GPU) and gloo (CPU tests)."""
@@ -21,20 +21,54 @@ def shard_range(n_items: int, world: int, rank: int):
 
 
 class GradSync:
-    """Flat-bucket gradient all-reduce (mean).  ``allreduce()`` is called after ``loss.backward()``."""
+    """Gradient all-reduce (mean) of one data-parallel step.  ``allreduce()`` is called after ``loss.backward()``.
+
+    The engine writes every parameter gradient of a step into ONE flat fp32 buffer (parameter order) and hands autograd views
+    of it, so the exchange is a single in-place ``all_reduce(AVG)`` on that buffer: no gather / scatter copies, no scaling
+    pass, one collective per step (2.9 MB for the README model).  When the gradients are NOT views of one such buffer (a
+    foreign module, gradient accumulation into existing ``.grad`` tensors) the generic path packs them into a flat bucket
+    first.  gloo (CPU tests) has no AVG: SUM + scale."""
 
     def __init__(self, module: torch.nn.Module, world: int | None = None, broadcast: bool = True):
         self.module = module
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
         self._flat = None
+        self.in_place_steps = 0     # how many exchanges ran on the engine's own buffer (tests / bench report it)
         if self.world > 1 and broadcast:
             with torch.no_grad():
                 for t in list(module.parameters()) + list(module.buffers()):
                     dist.broadcast(t, src=0)
 
+    def _engine_flat(self):
+        """The engine's flat gradient buffer if every ``.grad`` is the view of it the engine returned, else None."""
+        eng = getattr(self.module, "_engine", None)
+        flat = getattr(eng, "last_grad_flat", None) if eng is not None else None
+        if flat is None:
+            return None
+        off = 0
+        base, esz = flat.data_ptr(), flat.element_size()
+        for p in self.module.parameters():
+            g = p.grad
+            if g is None or g.dtype != flat.dtype or not g.is_contiguous() or g.data_ptr() != base + off * esz:
+                return None
+            off += p.numel()
+        return flat if off == flat.numel() else None
+
+    def _reduce_mean(self, flat):
+        if dist.get_backend() == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            flat.mul_(1.0 / self.world)
+
     def allreduce(self):
         if self.world <= 1:
+            return
+        flat = self._engine_flat()
+        if flat is not None:
+            self._reduce_mean(flat)
+            self.in_place_steps += 1
             return
         grads = [p.grad for p in self.params if p.grad is not None]
         if not grads:
@@ -49,6 +83,5 @@ class GradSync:
             views.append(v)
             o += g.numel()
         torch._foreach_copy_(views, grads)
-        dist.all_reduce(self._flat, op=dist.ReduceOp.SUM)
-        self._flat.mul_(1.0 / self.world)
+        self._reduce_mean(self._flat)
         torch._foreach_copy_(grads, views)

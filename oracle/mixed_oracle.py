@@ -73,8 +73,21 @@ ACCUMULATE = "fp32"
 """How the fp32 accumulations are carried out: "fp32" (oneDNN's order, BatchNorm statistics reduced in fp64), "fp64"
 (convolutions accumulated in double, rounded once), "split" (two half-K partial sums added at the end) or "stats32"
 (BatchNorm sums and sums of squares reduced in fp32, as the conv epilogues' per-CTA partial sums are: ~1e-6 relative on
-mean / variance).  All are legitimate results of the same fp16-storage arithmetic; the spread between them is the
-ACCUMULATION-ORDER FLOOR of a case (``accumulation_floor``): how far two correct implementations may differ on it."""
+mean / variance), or ("noise", seed): every fp32 accumulator (conv outputs, BatchNorm forward / backward sums) multiplied
+by 1 + eps * N(0, 1) with eps = one fp32 rounding (6e-8; 3e-7 for the long BatchNorm sums) -- a generic model of "the
+same sum added in another order", of which any number of independent draws can be taken.  All are legitimate results of
+the same fp16-storage arithmetic; the spread between them is the ACCUMULATION-ORDER FLOOR of a case
+(``accumulation_floor``): how far two correct implementations may differ on it."""
+_NOISE = [None]
+
+
+def _noisy(t, eps):
+    """Multiplicative rounding-level noise when ACCUMULATE is ("noise", seed); identity otherwise."""
+    if not (isinstance(ACCUMULATE, tuple) and ACCUMULATE[0] == "noise"):
+        return t
+    if _NOISE[0] is None or _NOISE[0][0] != ACCUMULATE[1]:
+        _NOISE[0] = (ACCUMULATE[1], torch.Generator().manual_seed(7919 * ACCUMULATE[1] + 1))
+    return t * (1 + eps * torch.randn(t.shape, generator=_NOISE[0][1], dtype=t.dtype))
 
 
 def _conv_fn(dims, transposed):
@@ -86,6 +99,10 @@ def _conv_fn(dims, transposed):
         def f64(a, w, b, **kw):
             return f(a.double(), w.double(), None if b is None else b.double(), **kw).float()
         return f64
+    if isinstance(ACCUMULATE, tuple):
+        def fnoise(a, w, b, **kw):
+            return _noisy(f(a, w, b, **kw), 6e-8)
+        return fnoise
     if ACCUMULATE == "split":
         def fsplit(a, w, b, **kw):
             c = a.shape[1]
@@ -157,7 +174,9 @@ def train_step(sd: Dict[str, torch.Tensor], spec: dict, x, mask, pwl, method="pi
             else:
                 yd = y32.double()
                 mu = yd.mean(dim=red)
-                var = ((yd * yd).mean(dim=red) - mu * mu).clamp_min(0.0)
+                ex2 = _noisy((yd * yd).mean(dim=red), 3e-7)
+                mu = _noisy(mu, 3e-7)
+                var = (ex2 - mu * mu).clamp_min(0.0)
             invstd = (1.0 / torch.sqrt(var + BN_EPS)).float()
             mean = mu.float()
             unbiased = var * n / (n - 1) if n > 1 else var
@@ -251,8 +270,12 @@ def train_step(sd: Dict[str, torch.Tensor], spec: dict, x, mask, pwl, method="pi
             y16, n = rec["y16"], rec["n"]
             g0 = torch.where(rec["pos"], d, torch.zeros_like(d))
             red = sum_dims(d)
-            sg = g0.double().sum(dim=red)
-            sgy = (g0.double() * y16.double()).sum(dim=red)
+            if ACCUMULATE == "stats32":   # fp32 partial sums, like the per-thread accumulators of the BN-backward kernels
+                sg = g0.sum(dim=red).double()
+                sgy = (g0 * y16).sum(dim=red).double()
+            else:
+                sg = _noisy(g0.double().sum(dim=red), 3e-7)
+                sgy = _noisy((g0.double() * y16.double()).sum(dim=red), 3e-7)
             mean, invstd = rec["mean"].double(), rec["invstd"].double()
             sgx = invstd * (sgy - mean * sg)
             grads[f"{p}.batch{idx}.weight"] = (sgx * inv).float()
@@ -328,10 +351,11 @@ def eval_forward(sd: Dict[str, torch.Tensor], spec: dict, x, emulate=True, taps:
     return taps["logits"]
 
 
-def accumulation_floor(sd, spec, x, mask, pwl, base=None, method="pixel"):
+def accumulation_floor(sd, spec, x, mask, pwl, base=None, method="pixel", draws=3):
     """Per-tensor spread of the emulated step under a change of the fp32 accumulation order (see ``ACCUMULATE``).
     Returns (base result, {"logits": rel-L2, "agree": fraction, param name: rel-L2}) -- the largest deviation of the "fp64",
-    "split" and "stats32" variants from the default one."""
+    "split" and "stats32" variants (+ ``draws - 3`` ("noise", seed) draws: small cases, where single rounding flips are rare
+    events, need more samples of the spread) from the default one."""
     global ACCUMULATE
 
     def rel(a, b):
@@ -343,8 +367,9 @@ def accumulation_floor(sd, spec, x, mask, pwl, base=None, method="pixel"):
     floor = {"logits": 0.0, "agree": 1.0}
     saved = ACCUMULATE
     try:
-        for mode in ("fp64", "split", "stats32"):
+        for mode in ["fp64", "split", "stats32"] + [("noise", i) for i in range(max(0, draws - 3))]:
             ACCUMULATE = mode
+            _NOISE[0] = None
             _, lg, gr, _ = train_step(sd, spec, x, mask, pwl, method)
             floor["logits"] = max(floor["logits"], rel(lg, base[1]))
             floor["agree"] = min(floor["agree"], float(((lg > 0) == (base[1] > 0)).float().mean()))
@@ -355,15 +380,16 @@ def accumulation_floor(sd, spec, x, mask, pwl, base=None, method="pixel"):
     return base, floor
 
 
-def eval_accumulation_floor(sd, spec, x):
+def eval_accumulation_floor(sd, spec, x, draws=8):
     """(eval logits of the emulation, their accumulation-order spread as rel-L2, worst thresholded-mask agreement)."""
     global ACCUMULATE
     base = eval_forward(sd, spec, x)
     spread, agree = 0.0, 1.0
     saved = ACCUMULATE
     try:
-        for mode in ("fp64", "split"):
+        for mode in ["fp64", "split"] + [("noise", i) for i in range(max(0, draws - 2))]:
             ACCUMULATE = mode
+            _NOISE[0] = None
             lg = eval_forward(sd, spec, x)
             spread = max(spread, float((lg.double() - base.double()).norm() / base.double().norm().clamp_min(1e-30)))
             agree = min(agree, float(((lg > 0) == (base > 0)).float().mean()))

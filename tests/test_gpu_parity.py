@@ -58,7 +58,9 @@ class Want:
             self.agree_min = 0.999
             self.context = ""
         else:
-            (loss, logits, grads, bufs), floor = M.accumulation_floor(sd, kwargs, x, mask, pwl)
+            # 16 draws: on these small cases a single flipped arg-max / ReLU decision can carry several percent of a
+            # gradient (a rare, bimodal event: e.g. g2d_small's up_steps.1.batch1.bias moves 8.7 % in 2 draws of 12)
+            (loss, logits, grads, bufs), floor = M.accumulation_floor(sd, kwargs, x, mask, pwl, draws=16)
             self.agree_min = min(0.999, floor["agree"] - 0.002)
             if ref is not None:
                 self.context = (f" [fp16 storage vs the fp32 reference on this case: logits {rel_l2(logits, ref[1]):.1e}, worst "

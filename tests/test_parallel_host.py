@@ -48,6 +48,11 @@ def test_tile_grid_covers_output_once_across_ranks():
         tile_grid((100, 100), 24, align)
 
 
+def h3(m, lo, hi):
+    # first element of the first three gradients after the GENERIC all-reduce (recomputed: the in-place phase overwrote .grad)
+    return [(3 + 7) / 2 + i for i in range(3)]
+
+
 def _worker(rank, world, port, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -65,7 +70,22 @@ def _worker(rank, world, port, ret):
             p.grad = torch.full_like(p, float(sum(range(lo, hi))) + i)
         sync.allreduce()
         g = torch.cat([p.grad.flatten() for p in m.parameters()])
-        ret[rank] = (w0, g, [float(p.grad.flatten()[0]) for p in m.parameters()][:3])
+        assert sync.in_place_steps == 0          # foreign .grad tensors: the generic (packing) path
+        # the engine's layout: every .grad is a view of ONE flat buffer in parameter order -> reduced in place, no copies
+        n = sum(p.numel() for p in m.parameters())
+        flat = torch.empty(n)
+        off = 0
+        for i, p in enumerate(m.parameters()):
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            p.grad.fill_(float(rank) + i)
+            off += p.numel()
+        m._engine.last_grad_flat = flat
+        ptr = flat.data_ptr()
+        sync.allreduce()
+        assert sync.in_place_steps == 1 and flat.data_ptr() == ptr
+        first = [float(p.grad.flatten()[0]) for p in m.parameters()][:3]
+        assert first == [0.5 + i for i in range(3)], first      # mean over ranks {0, 1} of (rank + i)
+        ret[rank] = (w0, g, [float(v) for v in g[:1]] and [float(x) for x in h3(m, lo, hi)])
     finally:
         dist.destroy_process_group()
 
