@@ -767,6 +767,49 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long npix, int cpitc
   for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&scratch[i], (double)sh[i]);
 }
 
+// fp16, 8-channel aligned: one 16-byte load per thread per step, a thread keeps ONE group of 8 channels (the total thread
+// count is a multiple of c / 8), no division inside the loop; the CTA's partial sums go through shared memory
+__global__ void __launch_bounds__(256) colsum_h8_kernel(const __half* __restrict__ x, long long npix, int cpitch, int c_off,
+                                                        int c, double* __restrict__ scratch) {
+  extern __shared__ float sh[];  // [c]
+  for (int i = threadIdx.x; i < c; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int g = c >> 3;                                   // 8-channel groups per pixel
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long nthr = (long long)gridDim.x * blockDim.x;  // multiple of g
+  const int grp = (int)(tid % g);
+  const long long pstep = nthr / g;
+  float s[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = 0.f;
+  const __half* src = x + c_off + grp * 8;
+  for (long long pix = tid / g; pix < npix; pix += pstep) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + pix * cpitch));
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = __half22float2(h[k]);
+      s[2 * k] += f.x;
+      s[2 * k + 1] += f.y;
+    }
+  }
+  // lanes holding the same group: 32 % g == 0 -> lanes l, l + g, ...; reduce across them with shuffles when g divides 32
+  if (g <= 32 && (32 % g) == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      for (int o = 16; o >= g; o >>= 1) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+    if ((threadIdx.x & 31) < g) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sh[grp * 8 + j], s[j]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh[grp * 8 + j], s[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&scratch[i], (double)sh[i]);
+}
+
 __global__ void colsum_finish_kernel(const double* __restrict__ scratch, int c, float scale,
                                      const float* __restrict__ dscale, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1182,9 +1225,17 @@ extern "C" int hcu_colsum(const void* x, int32_t dtype_x, int64_t npix, int32_t 
   cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * c, st);
   if (e != cudaSuccess) { set_error("colsum: memset: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
   int threads, grid;
-  channel_fixed_geometry(npix * c, c, threads, grid);
-  HCU_DISPATCH_ACT(dtype_x, T,
-      colsum_kernel<T><<<grid, threads, c * sizeof(float), st>>>((const T*)x, npix, cpitch, c_off, c, scratch));
+  const int g8 = c / 8;
+  if (dtype_x == HCU_F16 && c % 8 == 0 && cpitch % 8 == 0 && c_off % 8 == 0 && aligned16(x) && g8 <= 256 &&
+      (g8 & (g8 - 1)) == 0) {  // power-of-two group count: divides the 256 threads (and a warp, up to 32 groups)
+    threads = 256;
+    grid = grid_for(npix * g8, threads * 4, 8);
+    colsum_h8_kernel<<<grid, threads, c * sizeof(float), st>>>((const __half*)x, npix, cpitch, c_off, c, scratch);
+  } else {
+    channel_fixed_geometry(npix * c, c, threads, grid);
+    HCU_DISPATCH_ACT(dtype_x, T,
+        colsum_kernel<T><<<grid, threads, c * sizeof(float), st>>>((const T*)x, npix, cpitch, c_off, c, scratch));
+  }
   HCU_CHECK_LAUNCH("colsum");
   colsum_finish_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, c, scale, dscale, out);
   HCU_CHECK_LAUNCH("colsum_finish");

@@ -436,3 +436,21 @@ def test_input_layout_kernel_pads_channels():
         got = dst.view(2, 6, 5, 3, 8).cpu().float()
         assert torch.equal(got[..., :4], x.half().float().permute(0, 2, 3, 4, 1))
         assert torch.equal(got[..., 4:], torch.zeros(2, 6, 5, 3, 4))
+
+
+@pytest.mark.parametrize("c,cpitch,c_off,npix", [(8, 8, 0, 20000), (16, 16, 0, 9001), (64, 64, 0, 4099), (32, 64, 32, 777),
+                                                 (512, 512, 0, 300), (1, 8, 0, 5000), (24, 24, 0, 1234)])
+def test_colsum_matches_fp64_sum(c, cpitch, c_off, npix):
+    """Bias gradients of the layers without a BatchNorm behind them (`ConvTranspose`, `out_conv`): per-channel sum of a
+    channels-last fp16 tensor, 16-byte vector kernel where the channel slice is 8-aligned, generic kernel otherwise."""
+    from hcunet_b200 import _lib
+
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(c * 131 + npix)
+    x = torch.randn((npix, cpitch), generator=g).half().cuda()
+    scratch = torch.empty(4096, dtype=torch.float64, device="cuda")
+    out = torch.empty(c, dtype=torch.float32, device="cuda")
+    dscale = torch.tensor([0.25], dtype=torch.float32, device="cuda")
+    _lib.check(lib.hcu_colsum(P(x), _lib.F16, npix, cpitch, c_off, c, 2.0, P(dscale), P(scratch), P(out), stream()), "colsum")
+    want = x[:, c_off:c_off + c].double().sum(0) * 0.5
+    assert float((out.double() - want).abs().max()) <= 1e-5 * float(x.double().abs().sum(0).max())
