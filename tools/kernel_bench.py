@@ -85,8 +85,18 @@ def main():
             sc = sh = None
         T = k[0] * k[1] * k[2]
         nin, nout = x.numel(), B * osz[0] * osz[1] * osz[2] * cout
-        if kind == "conv":
-            d = conv_desc(_lib.F16, _lib.F16, B, isz, cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, in_relu=1)
+        if kind in ("conv", "dgrad", "eval"):
+            if kind == "dgrad":   # data gradient of this layer: dy [osz, cout] -> dx [isz, cin], zero padding k - 1, nothing fused
+                pad = tuple(t - 1 for t in k)
+                x = torch.randn((B,) + osz + (cout,), device="cuda").half()
+                d = conv_desc(_lib.F16, _lib.F16, B, osz, cout, 0, cout, cout, isz, isz, cin, 0, cin, 1, k, pad=pad)
+                cin, cout, osz, sc, sh = cout, cin, isz, None, None
+                nin, nout = x.numel(), B * osz[0] * osz[1] * osz[2] * cout
+            elif kind == "eval":
+                sc = sh = None
+                d = conv_desc(_lib.F16, _lib.F16, B, isz, cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, out_relu=1)
+            else:
+                d = conv_desc(_lib.F16, _lib.F16, B, isz, cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, in_relu=1)
             d.reserved[0], d.reserved[1] = hint, tile
             buf = C.create_string_buffer(256)
             lib.hcu_conv_tc_describe(C.byref(d), buf, 256)
@@ -98,8 +108,17 @@ def main():
             _lib.check(lib.hcu_conv_tc_pack(C.byref(d), P(w), P(packed), st))
             y = torch.empty((B,) + osz + (cout,), dtype=torch.float16, device="cuda")
             stats = torch.zeros((_lib.STAT_BINS, 2, cout), dtype=torch.float64, device="cuda")
-            fn = lambda: _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), P(x), P(packed), None, P(sc), P(sh), None, None, P(y),
-                                                        P(stats), st))
+            bias = torch.randn(cout, device="cuda")
+            osc, osh = torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda")
+            if kind == "dgrad":
+                fn = lambda: _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), P(x), P(packed), None, None, None, None, None, P(y),
+                                                            None, st))
+            elif kind == "eval":
+                fn = lambda: _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), P(x), P(packed), None, None, None, P(osc), P(osh), P(y),
+                                                            None, st))
+            else:   # training forward: conv bias + BatchNorm statistics (+ the previous layer's BN + ReLU on load unless --raw)
+                fn = lambda: _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), P(x), P(packed), P(bias), P(sc), P(sh), None, None, P(y),
+                                                            P(stats), st))
         else:
             dy = torch.randn((B,) + osz + (cout,), device="cuda").half()
             d = conv_desc(_lib.F16, _lib.F16, B, isz, cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, in_relu=1)
@@ -134,7 +153,7 @@ def main():
         ms = sorted(ts)[len(ts) // 2]
         byt = (nin + nout) * 2
         fl = 2 * (nout // cout) * T * cin * cout
-        cfg = ("  " + buf.value.decode()) if kind == "conv" else ""
+        cfg = ("  " + buf.value.decode()) if kind in ("conv", "dgrad", "eval") else ""
         print(f"{kind:5s} {name:12s} {ms*1e3:8.1f} us  {byt/ms/1e6:7.1f} GB/s  {fl/ms/1e9:7.2f} TF/s  (min {min(ts)*1e3:.1f} us){cfg}")
 
 
