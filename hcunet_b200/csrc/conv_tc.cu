@@ -604,14 +604,15 @@ static const char* configure_classic(const HcuConvDesc* d, Params& p) {
           // wide: 4 accumulator slots per M-block in TMEM, an MMA spans up to KX slots (N = KX * nc <= 256)
           const bool wide = can_wide && p.KX * nc <= 256 && 4 * MB * nc <= 512 && (!small_wide || 4 * MB * nc <= 256);
           if ((wide ? 4 : 2) * MB * nc > 512) continue;
-          const int wbytes = p.E * nc * 16;
+          // the specialised variants (Nc = 16, wide) keep KX rotated copies of the weights (rotating accumulator window)
+          const int wbytes = p.E * nc * 16 * ((wide && nc == 16 && npad == 16) ? p.KX : 1);
           const int R = (wide ? 1 : span) + want[sweep];  // wide: every input plane is consumed by ONE step
           if (R > kMaxRing) continue;
           const int off_w = 0;
           const int off_a = round_up(wbytes, 128);
           const int off_bar = off_a + R * slot;
           const int off_stat = round_up(off_bar + 8 * (2 * R + 9) + 8, 16);
-          const int total = off_stat + 19 * nc * 4 + 128;
+          const int total = off_stat + (nc == 16 ? 19 : 11) * nc * 4 + 128;  // bulk mode (Nc = 16 only): 8 statistics slots
           if (total > budget) continue;
           p.M = M; p.MB = MB; p.RUN = run; p.PS = ps; p.SLOT = slot; p.R = R; p.wide = wide ? 1 : 0;
           p.D = want[sweep] >= 4 ? 2 : (want[sweep] >= 2 ? 1 : 0);
@@ -1064,6 +1065,10 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
       const bool bulk = bulk_on && p.P == 1 && in_scale == nullptr && p.ips[0] * p.ips[1] * p.ips[2] == 1 && p.in_zs == 8 &&
                         p.in_ys == p.IZ * p.in_zs && p.RUN * 16 <= 32768 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
       vi = 1 + (((p.MB - 1) * 2 + (nch == 8 ? 0 : 1)) * 3 + fi) * 2 + (bulk ? 1 : 0);
+      // rotating accumulator window: KX slots of Nc columns per M-block
+      int cols = p.MB * p.KX * p.Nc, t = 32;
+      while (t < cols) t <<= 1;
+      p.tmem_cols = t;
     }
   }
   {

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   // in a fixed order, so the statistics (hence the whole forward) do not depend on the order warps happen to run in
   float* sstat = reinterpret_cast<float*>(smem + p.off_stat);  // [8 warps][2][Nc] (slots 4..7: bulk mode)
   const int Nc = S ? 16 : p.Nc;
-  float* sbias = sstat + 16 * Nc;                              // [3][Nc]: bias, out_scale, out_shift of this column chunk
+  float* sbias = sstat + (BULK ? 16 : 8) * Nc;                 // [3][Nc]: bias, out_scale, out_shift of this column chunk
   const uint32_t a_base = smem_u32(smem + p.off_a), w_base = smem_u32(smem + p.off_w);
   const int R = p.R, MB = S ? V::kMB : p.MB;
 
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     __syncwarp();
     tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
   }
-  for (int i = threadIdx.x; i < 16 * Nc; i += kThreads) sstat[i] = 0.f;
+  for (int i = threadIdx.x; i < (BULK ? 16 : 8) * Nc; i += kThreads) sstat[i] = 0.f;
   if (BULK) {  // padding positions of the ring are never written by the bulk copies: zero everything once
     uint4* a4 = reinterpret_cast<uint4*>(smem + p.off_a);
     for (int i = threadIdx.x; i < (R * p.SLOT) >> 4; i += kThreads) a4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -285,7 +285,23 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   // ---- everything above touched no global memory: it overlapped the previous kernel's tail (PDL) ----
   pdl_wait();
   pdl_launch_dependents();
-  if (warp == 8 && lane == 0) {
+  if (S) {
+    // rotating accumulator window (see the MMA issuer): KX copies of the weights, copy r = the order of the KX accumulator
+    // slots when the newest output plane sits in slot r: [r][K8 slab][slot s][Nc][8] = packed[slab][KX-1-tx][Nc][8] with
+    // tx = (r - s) mod KX.  A few KB (the specialised variants are the 8/16-channel levels), gathered from L2 by all threads.
+    const int KX = p.KX, per_rot = p.E_tx * KX * Nc;  // 16-byte units
+    const uint4* src = reinterpret_cast<const uint4*>(p.wp);
+    uint4* dst = reinterpret_cast<uint4*>(smem + p.off_w);
+    for (int u = threadIdx.x; u < KX * per_rot; u += kThreads) {
+      const int r = u / per_rot, rem = u - r * per_rot;
+      const int slab = rem / (KX * Nc), rem2 = rem - slab * (KX * Nc);
+      const int sl = rem2 / Nc, c = rem2 - sl * Nc;
+      int tx = r - sl;
+      tx += tx < 0 ? KX : 0;
+      dst[u] = __ldg(src + (slab * KX + (KX - 1 - tx)) * Nc + c);
+    }
+    fence_proxy_async();
+  } else if (warp == 8 && lane == 0) {
     const uint32_t wbytes = (uint32_t)p.E * Nc * 16u;
     fence_barrier_init();
     mbar_expect_tx(bar_w, wbytes);
@@ -455,8 +471,60 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     const uint32_t a_desc0 = a_base >> 4;
     const uint32_t wdesc = (w_base >> 4) | ((((uint32_t)(Nc * 16)) >> 4) << 16);  // B: LBO = next K8 slab
     PROF_DECL;
-    mbar_wait(bar_w, 0);
-    if (wide) {
+    if (S) {
+      // Rotating accumulator window.  Output plane i accumulates in slot i mod KX of its M-block (TMEM columns
+      // (mb * KX + slot) * Nc); input plane j feeds the outputs j-KX+1 .. j = ALL KX slots, so every K16 step is ONE MMA per
+      // M-block with N = KX * Nc against weight copy r = j mod KX (whose slot order matches): no window ever wraps and no
+      // output needs a separate accumulate = 0 MMA -- the epilogue zeroes a slot (tcgen05.st) when it drains it, every MMA
+      // accumulates.  The x-fused schedule below (4 slots, wrap splits + a separate first MMA per output) issued 15 MMAs per
+      // plane on the (3,3,1) 8-channel layers where this one issues 8, and the tensor pipe -- bound by the shared-memory fetch
+      // of the A operand, ~40 clk per MMA shared by the SM's two CTAs -- was the busiest role (profiles/r02_conv_tc_roles.txt).
+      // The first KX-1 planes complete "virtual" outputs (i < 0) the epilogue drains without storing.
+      const int KX = p.KX;
+      const uint32_t wlbo = (((uint32_t)(KX * Nc * 16)) >> 4) << 16;    // next K8 slab
+      const uint32_t idw = (1u << 4) | ((128u >> 4) << 24) | ((((uint32_t)(KX * Nc)) >> 3) << 17);
+      const uint32_t per_rot = (uint32_t)(p.E_tx * KX * Nc);
+      const uint32_t mbcols = (uint32_t)(KX * Nc);
+      int ring = 0, snew = 0;
+      uint32_t rpar = 0;
+      // EVERY plane touches all KX slots.  Plane 0 needs all of them zeroed (the epilogue's initial arrivals: phase 0 of every
+      // tempty barrier); plane j >= 1 needs the slot of its new output, j mod KX, drained: its previous occupant (output j - KX,
+      // virtual while negative) completed with plane j - 1, so that is the slot's NEXT phase every time.
+      for (int sl = 0; sl < KX; ++sl) mbar_wait(bar_tempty + 8 * sl, 0u);
+      uint32_t te_phase = 0xffffffffu;
+      for (int j = 0; j < nplanes; ++j) {
+        PROF_WAIT(pw0, mbar_wait(bar_full + 8 * ring, rpar));
+        if (j > 0) {
+          PROF_WAIT(pw1, mbar_wait(bar_tempty + 8 * snew, (te_phase >> snew) & 1u));
+          te_phase ^= 1u << snew;
+        }
+        tc_fence_after();
+        const uint32_t abase = a_desc0 + (uint32_t)(ring * (p.SLOT >> 4));
+        const uint32_t wb = (w_base >> 4) + (uint32_t)snew * per_rot;
+        for (int e = 0; e < p.npairs; ++e) {
+          const uint2 t = p.tab[e];
+          const uint64_t ad = desc_hi | (uint64_t)(abase + t.x);
+          const uint64_t bd = desc_hi | (uint64_t)((wb + t.y) | wlbo);
+          if (elect_one()) {
+            umma_f16(tmem_base, ad, bd, idw, 1u);
+            if (MB > 1) umma_f16(tmem_base + mbcols, ad + 128u, bd, idw, 1u);
+            if (MB > 2) umma_f16(tmem_base + 2u * mbcols, ad + 256u, bd, idw, 1u);
+            if (MB > 3) umma_f16(tmem_base + 3u * mbcols, ad + 384u, bd, idw, 1u);
+          }
+          __syncwarp();
+        }
+        const int sdone = snew + 1 == KX ? 0 : snew + 1;  // slot of output j - KX + 1, complete with this plane
+        if (elect_one()) {
+          umma_commit(bar_empty + 8 * ring);
+          umma_commit(bar_tfull + 8 * sdone);
+        }
+        __syncwarp();
+        if (++ring == R) { ring = 0; rpar ^= 1; }
+        snew = sdone;
+      }
+      PROF_REPORT("mma", "wait_full", "wait_tempty", nplanes);
+    } else if (wide) {
+      mbar_wait(bar_w, 0);
       // x-fused schedule: input plane j feeds the output planes i = j - tx (tx = 0 .. KX-1) in ONE MMA per K16 step whose
       // N spans their accumulator slots (4 slots per M-block, consecutive outputs in consecutive columns) against the
       // weights laid out [K8 slab][KX-1-tx][Nc]: the A operand is fetched once per input plane instead of once per
@@ -514,6 +582,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         if (++wslot2 == R) { wslot2 = 0; wpar2 ^= 1; }
       }
     } else {
+      mbar_wait(bar_w, 0);
       const int lastoff = (p.KX - 1) * p.dx;
       int next_wait = 0, wslot = 0;
       uint32_t wpar = 0;
@@ -559,7 +628,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         i_mod = i_mod + 1 == R ? 0 : i_mod + 1;
       }
     }
-    PROF_REPORT("mma", "wait_full", "wait_tempty", nout);
+    if (!S) PROF_REPORT("mma", "wait_full", "wait_tempty", nout);
   } else if (warp == 9) {
     // ====================================== BULK-COPY PRODUCER (bulk mode) ===========================
     if (BULK) {
@@ -645,6 +714,28 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     }
     const long long obase0 = p.out_base + n * p.out_sn + p.out_c_off + ns * Nc;
 
+    // Rotating window (specialised variants): zero this warp's share of every accumulator slot once, then hand the slots to
+    // the MMA issuer (its first KX waits on tempty complete with these arrivals).
+    const int KXr = p.KX;
+    if (S) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int mb = half + k * MBSTEP;
+        if (k * MBSTEP < MB && mb < MB)
+          for (int sl = 0; sl < KXr; ++sl) tmem_zero16(tmem_base + lane_base + (uint32_t)((mb * KXr + sl) * Nc));
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        for (int sl = 0; sl < KXr; ++sl) mbar_arrive(bar_tempty + 8 * sl);
+    }
+    // iteration `it` drains: generic -- output it from buffer it mod NB; rotating window -- output it - (KX-1) (virtual, not
+    // stored, while negative) from slot (it + 1) mod KX
+    const int nit = S ? nplanes : nout;
+    int rslot = 1 % KXr;
+    uint32_t tf_phase = 0;
+
     if (S ? V::kEpi == 1 : (p.epi_fast && nch == 8)) {
       // ---- 8 output channels (the HBM-bound first / last levels): every M-block's 8 columns are fetched with ONE wait,
       // the accumulator buffer is released before the arithmetic, statistics stay in registers until the end
@@ -654,9 +745,15 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       float bs[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) bs[j] = sbias[j];
-      for (int i = 0; i < nout; ++i) {
-        const int buf = i & (NB - 1);
-        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i / NB) & 1));
+      for (int it = 0; it < nit; ++it) {
+        const int i = S ? it - (KXr - 1) : it;
+        const int buf = S ? rslot : (it & (NB - 1));
+        const uint32_t par = S ? ((tf_phase >> rslot) & 1u) : (uint32_t)((it / NB) & 1);
+        if (S) {
+          tf_phase ^= 1u << rslot;
+          rslot = rslot + 1 == KXr ? 0 : rslot + 1;
+        }
+        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, par));
         tc_fence_after();
         if (debug & 2) {
           tc_fence_before();
@@ -665,19 +762,30 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
           continue;
         }
         uint32_t r[4][8];
+        if (!S || i >= 0) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int mb = half + k * MBSTEP;
-          if (k * MBSTEP < MB && mb < MB)
-            tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)((wide ? mb * 4 + buf : buf * MB + mb) * Nc), r[k]);
+          for (int k = 0; k < 4; ++k) {
+            const int mb = half + k * MBSTEP;
+            if (k * MBSTEP < MB && mb < MB)
+              tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)((S ? mb * KXr + buf : (wide ? mb * 4 + buf : buf * MB + mb)) * Nc), r[k]);
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k * MBSTEP < MB && half + k * MBSTEP < MB) tmem_pin8(r[k]);
         }
-        tmem_wait_ld();
+        if (S) {  // the slot's next output starts from zero: every MMA accumulates
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (k * MBSTEP < MB && half + k * MBSTEP < MB) tmem_pin8(r[k]);
+          for (int k = 0; k < 4; ++k) {
+            const int mb = half + k * MBSTEP;
+            if (k * MBSTEP < MB && mb < MB) tmem_zero8(tmem_base + lane_base + (uint32_t)((mb * KXr + buf) * Nc));
+          }
+          tmem_wait_st();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+        if (S && i < 0) continue;
         __half* oplane = reinterpret_cast<__half*>(p.out) + obase0 + (long long)(x0 + i) * p.out_sx;
 #pragma unroll
         for (int mb = 0; mb < 4; ++mb) {  // mb: slot index of this warp
@@ -730,19 +838,27 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       float t1[16], t2[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) { t1[j] = 0.f; t2[j] = 0.f; }
-      for (int i = 0; i < nout; ++i) {
-        const int buf = i & (NB - 1);
-        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, (i / NB) & 1));
+      for (int it = 0; it < nit; ++it) {
+        const int i = S ? it - (KXr - 1) : it;
+        const int buf = S ? rslot : (it & (NB - 1));
+        const uint32_t par = S ? ((tf_phase >> rslot) & 1u) : (uint32_t)((it / NB) & 1);
+        if (S) {
+          tf_phase ^= 1u << rslot;
+          rslot = rslot + 1 == KXr ? 0 : rslot + 1;
+        }
+        PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, par));
         tc_fence_after();
         __half* oplane = reinterpret_cast<__half*>(p.out) + obase0 + (long long)(x0 + i) * p.out_sx;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int mb = half + k * MBSTEP;  // warp-uniform
           if (k * MBSTEP >= MB || mb >= MB) break;
-          const bool valid = poff[k] >= 0;
+          const bool valid = poff[k] >= 0 && (!S || i >= 0);
           for (int cc = 0; cc < nch; cc += 16) {
             float v[16];
-            tmem_ld16(tmem_base + lane_base + (uint32_t)((wide ? mb * 4 + buf : buf * MB + mb) * Nc + cc), v);
+            const uint32_t taddr = tmem_base + lane_base + (uint32_t)((S ? mb * KXr + buf : (wide ? mb * 4 + buf : buf * MB + mb)) * Nc + cc);
+            tmem_ld16(taddr, v);
+            if (S) tmem_zero16(taddr);  // ordered behind the load by its wait; completion awaited before the slot is released
             if (has_bias) {
 #pragma unroll
               for (int j = 0; j < 16; j += 4) {
@@ -795,6 +911,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
             }
           }
         }
+        if (S) tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);

@@ -748,7 +748,7 @@ __global__ void bn_bwd_apply_kernel(const TD* __restrict__ da, const TY* __restr
 
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, long long npix, int cpitch, int c_off, int c,
-                              double* __restrict__ scratch) {
+                              double* __restrict__ scratch, int nbins) {
   extern __shared__ float sh[];  // [c]
   for (int i = threadIdx.x; i < c; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
@@ -764,13 +764,14 @@ __global__ void colsum_kernel(const T* __restrict__ x, long long npix, int cpitc
     for (; e < total; e += stride) atomicAdd(&sh[(int)(e % c)], to_f(x[(e / c) * cpitch + c_off + (int)(e % c)]));
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&scratch[i], (double)sh[i]);
+  double* sb = scratch + (size_t)(blockIdx.x % nbins) * c;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&sb[i], (double)sh[i]);
 }
 
 // fp16, 8-channel aligned: one 16-byte load per thread per step, a thread keeps ONE group of 8 channels (the total thread
 // count is a multiple of c / 8), no division inside the loop; the CTA's partial sums go through shared memory
 __global__ void __launch_bounds__(256) colsum_h8_kernel(const __half* __restrict__ x, long long npix, int cpitch, int c_off,
-                                                        int c, double* __restrict__ scratch) {
+                                                        int c, double* __restrict__ scratch, int nbins) {
   extern __shared__ float sh[];  // [c]
   for (int i = threadIdx.x; i < c; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
@@ -807,14 +808,19 @@ __global__ void __launch_bounds__(256) colsum_h8_kernel(const __half* __restrict
     for (int j = 0; j < 8; ++j) atomicAdd(&sh[grp * 8 + j], s[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&scratch[i], (double)sh[i]);
+  double* sb = scratch + (size_t)(blockIdx.x % nbins) * c;  // binned: same-address fp64 atomics of hundreds of CTAs serialise
+  for (int i = threadIdx.x; i < c; i += blockDim.x) atomicAdd(&sb[i], (double)sh[i]);
 }
 
-__global__ void colsum_finish_kernel(const double* __restrict__ scratch, int c, float scale,
+__global__ void colsum_finish_kernel(const double* __restrict__ scratch, int c, int nbins, float scale,
                                      const float* __restrict__ dscale, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (dscale != nullptr) scale *= dscale[0];
-  if (i < c) out[i] = (float)(scratch[i] * scale);
+  if (i < c) {
+    double sum = 0.0;
+    for (int b = 0; b < nbins; ++b) sum += scratch[(size_t)b * c + i];
+    out[i] = (float)(sum * scale);
+  }
 }
 
 // loss scaling for the fp16 backward: scales[0] = S = 2^k with max|g| * S ~ target, scales[1] = 1/S
@@ -1222,22 +1228,23 @@ extern "C" int hcu_colsum(const void* x, int32_t dtype_x, int64_t npix, int32_t 
   HCU_CHECK_ARG(x && scratch && out && npix > 0 && c > 0 && c_off >= 0 && c_off + c <= cpitch && c <= 4096,
                 "colsum: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * c, st);
+  const int nbins = std::max(1, std::min(32, 4096 / c));  // the caller's scratch holds 4096 doubles
+  cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(double) * c * nbins, st);
   if (e != cudaSuccess) { set_error("colsum: memset: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
   int threads, grid;
   const int g8 = c / 8;
   if (dtype_x == HCU_F16 && c % 8 == 0 && cpitch % 8 == 0 && c_off % 8 == 0 && aligned16(x) && g8 <= 256 &&
       (g8 & (g8 - 1)) == 0) {  // power-of-two group count: divides the 256 threads (and a warp, up to 32 groups)
     threads = 256;
-    grid = grid_for(npix * g8, threads * 4, 8);
-    colsum_h8_kernel<<<grid, threads, c * sizeof(float), st>>>((const __half*)x, npix, cpitch, c_off, c, scratch);
+    grid = grid_for(npix * g8, threads * 8, 2);
+    colsum_h8_kernel<<<grid, threads, c * sizeof(float), st>>>((const __half*)x, npix, cpitch, c_off, c, scratch, nbins);
   } else {
     channel_fixed_geometry(npix * c, c, threads, grid);
     HCU_DISPATCH_ACT(dtype_x, T,
-        colsum_kernel<T><<<grid, threads, c * sizeof(float), st>>>((const T*)x, npix, cpitch, c_off, c, scratch));
+        colsum_kernel<T><<<grid, threads, c * sizeof(float), st>>>((const T*)x, npix, cpitch, c_off, c, scratch, nbins));
   }
   HCU_CHECK_LAUNCH("colsum");
-  colsum_finish_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, c, scale, dscale, out);
+  colsum_finish_kernel<<<(c + 127) / 128, 128, 0, st>>>(scratch, c, nbins, scale, dscale, out);
   HCU_CHECK_LAUNCH("colsum_finish");
   return 0;
 }

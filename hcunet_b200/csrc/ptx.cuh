@@ -49,11 +49,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try(bar, parity)) return;
-  // a poll counter instead of a clock64() comparison: the spin loops were ~20 % of all issued warp instructions of conv_tc_kernel
-  // on the 8-channel levels (source-level profile), 6 of the 10 instructions per poll being the 64-bit time check
+  // the spin loops were ~20 % of all issued warp instructions of conv_tc_kernel on the 8-channel levels (source-level profile),
+  // 6 of the 10 instructions per poll being the 64-bit time check: look at the clock every 256th poll only.  A protocol bug
+  // traps after ~1 s (a poll parks the thread for at most HCU_MBAR_HINT_NS).
+  const long long t0 = clock64();
   uint32_t polls = 0;
   while (!mbar_try(bar, parity))
-    if (++polls > (1u << 26)) __trap();
+    if ((++polls & 255u) == 0u && clock64() - t0 > 2000000000ll) __trap();
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -110,6 +112,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 // 8 accumulator columns of this thread's TMEM lane, no wait: pair with tmem_wait_ld() + tmem_pin8()
 __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -117,6 +127,17 @@ __device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
                : "r"(taddr)
                : "memory");
 }
+// zero 8 / 16 accumulator columns of this thread's TMEM lane (no wait: pair with tmem_wait_st())
+__device__ __forceinline__ void tmem_zero8(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+  const uint32_t z = 0u;
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // orders every later use of r[0..7] after the preceding (volatile) wait
 __device__ __forceinline__ void tmem_pin8(uint32_t* r) {

@@ -339,7 +339,8 @@ int hcu_bn_bwd_finalize(const double* sums, int32_t c, double count, const float
 int hcu_bn_bwd_apply(const void* da, int32_t dtype_da, const void* y, int32_t dtype_y, void* dy, int32_t dtype_dy,
                      int64_t npix, int32_t c, const float* scale, const float* shift, int32_t relu,
                      const float* coef, const uint8_t* argmax, const HcuPoolGeom* pool, void* stream);
-/* out[c] (+)= scale * sum over pixels of x[pix][c_off + c]  (bias gradients of convT / out_conv). */
+/* out[c] = scale * dscale[0] * sum over pixels of x[pix][c_off + c]  (bias gradients of convT / out_conv).  scratch: 4096 doubles
+ * (binned partial sums, zeroed by the call); c <= 4096. */
 int hcu_colsum(const void* x, int32_t dtype_x, int64_t npix, int32_t cpitch, int32_t c_off, int32_t c,
                float scale, const float* dscale, double* scratch, float* out, void* stream);
 
