@@ -102,10 +102,25 @@ struct Params {
   if (blockIdx.x == gridDim.x / 2 && lane == 0)                                                            \
     printf("conv_tc prof %-8s warp %d: total %lld cyc, %s %lld, %s %lld, fence %lld, iters %d -> %lld cyc/iter busy\n", role, warp, \
            clock64() - pt0, n0, pw0, n1, pw1, pw2, iters, (clock64() - pt0 - pw0 - pw1) / max(1, iters))
+// CTA timeline: global-timer stamps (ns) at kernel entry, after the prologue and at exit, for a sample of CTAs
+__device__ __forceinline__ unsigned long long prof_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define PROF_CTA_DECL const unsigned long long pg0 = prof_gtime(); unsigned long long pg1 = 0
+#define PROF_CTA_MID pg1 = prof_gtime()
+#define PROF_CTA_END                                                                                                        \
+  if (threadIdx.x == 0 && (blockIdx.x % 37 == 0 || blockIdx.x == gridDim.x - 1))                                             \
+    printf("conv_tc cta %4d/%d: entry %llu ns, prologue %llu ns, roles %llu ns\n", blockIdx.x, gridDim.x, pg0 % 100000000ull,  \
+           pg1 - pg0, prof_gtime() - pg1)
 #else
 #define PROF_DECL
 #define PROF_WAIT(acc, stmt) stmt
 #define PROF_REPORT(role, n0, n1, iters)
+#define PROF_CTA_DECL
+#define PROF_CTA_MID
+#define PROF_CTA_END
 #endif
 
 // ---------------------------------------------------------------------------------------------------
@@ -231,6 +246,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr bool S = V::kSpec, BULK = V::kBulk;
+  PROF_CTA_DECL;
   const bool wide = S ? true : (p.wide != 0);
   const int debug = S ? 0 : p.debug;
 
@@ -319,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  PROF_CTA_MID;
 
   if (!BULK && warp >= 4 && warp < 8) {
     // =========================================== PRODUCERS ===========================================
@@ -1010,6 +1027,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
   // ---- teardown --------------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  PROF_CTA_END;
   if (warp == 8) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
