@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HCUNET_LIB: an alternative build of the SAME library (A/B experiments: tools/build_variant.py); never a fallback
 LIB_PATH = os.environ.get("HCUNET_LIB") or os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 18
+ABI_VERSION = 19
 
 F32, BF16, F16, U8, U16, F64 = 0, 1, 2, 3, 4, 5
 BATCH_JOB_BYTES = 256
@@ -58,6 +58,11 @@ class HcuPoolGeom(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("n", "ix", "iy", "iz", "px", "py", "pz")]
 
 
+class HcuTileGeom(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("size", C.c_int32 * 3), ("pad", C.c_int32 * 3), ("origin", C.c_int32 * 3),
+                ("extent", C.c_int32 * 3), ("stack_origin", C.c_int32 * 3), ("stack_size", C.c_int32 * 3)]
+
+
 class HcuLossDesc(C.Structure):
     _fields_ = [
         ("b", C.c_int32), ("c", C.c_int32), ("x", C.c_int32), ("y", C.c_int32), ("z", C.c_int32),
@@ -76,6 +81,9 @@ SIGNATURES = {
     "hcu_launch_count": [],
     "hcu_zero": [P, C.c_size_t, P],
     "hcu_h2d_tile": [P, I64, I64, I64, I64, I64, P, P],
+    "hcu_tile_gather": [C.POINTER(HcuTileGeom), P, I32, P, I32, I32, I32, P],
+    "hcu_tile_flags": [C.POINTER(HcuTileGeom), P, I32, P, P],
+    "hcu_sigmoid_paste": [P, C.POINTER(I32), C.POINTER(I32), C.POINTER(I32), P, I32, C.POINTER(I32), C.POINTER(I32), F, P, P],
     "hcu_load_stack": [P, I32, I64, I32, I32, I32, I32, C.POINTER(D), C.POINTER(D), P, I32, P],
     "hcu_load_labels": [P, I32, I64, I32, I32, I32, I32, I32, I32, P, P],
     "hcu_conv_fwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],

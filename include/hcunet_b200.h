@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 18
+#define HCU_ABI_VERSION 19
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -67,6 +67,36 @@ int hcu_zero(void* ptr, size_t bytes, void* stream);
  * of the tile on the host first. */
 int hcu_h2d_tile(const void* src, int64_t planes, int64_t src_plane_pitch, int64_t rows, int64_t src_row_pitch,
                  int64_t row_bytes, void* dst, void* stream);
+
+/* ---- overlap-tile inference driver (hcat/segment.py:21-136 `predict_segmentation_mask`) ---------------
+ * The reference pads the WHOLE stack with reflections on the host (utils.py:33-74: numpy flips + torch.cat per dimension),
+ * slices one tile at a time, `.float().to(device)`, runs the net, crops the centre, applies an in-place sigmoid +
+ * threshold and pastes into a host mask.  Here the stack stays resident in HBM and the padded stack never exists:
+ * a tile is described in PADDED coordinates and gathered straight from the original stack. */
+typedef struct HcuTileGeom {
+  int32_t channels;         /* C of the stack [C][X][Y][Z] (one image) */
+  int32_t size[3];          /* original stack extent X, Y, Z */
+  int32_t pad[3];           /* reflection padding per side (utils.py:33: pad_size) */
+  int32_t origin[3];        /* tile origin in padded coordinates (segment.py:86: x[0], y[0], z[0]) */
+  int32_t extent[3];        /* tile extent (x[1]-x[0], ...) */
+  int32_t stack_origin[3];  /* original coordinates of the first voxel of the RESIDENT sub-stack (0,0,0: whole stack) */
+  int32_t stack_size[3];    /* extent of the resident sub-stack [C][sx][sy][sz] that `stack` points at */
+} HcuTileGeom;
+/* tile = scrubbed (NaN -> 0, +-inf -> 1: segment.py:66-67), reflection-padded (utils.py:48-73) slice of the stack.
+ * layout bit 0: 0 = [C][x][y][z] (the reference's tile), 1 = channels-last [x][y][z][cpitch], channels >= C zero (the layout the
+ * first convolution reads: no NCDHW -> NDHWC pass); bit 1: no scrub (plain pad_image_with_reflections).
+ * dtype_stack / dtype_tile: HCU_F32 | HCU_F16. */
+int hcu_tile_gather(const HcuTileGeom* g, const void* stack, int32_t dtype_stack, void* tile, int32_t dtype_tile,
+                    int32_t layout, int32_t cpitch, void* stream);
+/* flag[0] += number of tile values != -1 after the scrub (saturating): 0 <=> the reference skips the tile
+ * (segment.py:89-93 `(padded_image_slice.float() == -1).all()`).  The caller zeroes flag. */
+int hcu_tile_flags(const HcuTileGeom* g, const void* stack, int32_t dtype_stack, uint32_t* flag, void* stream);
+/* mask[morigin + i] = sigmoid(logits[crop + i]) (probability != 0: fp32 mask) or sigmoid(...) > threshold (uint8 mask) for
+ * i < ext: centre crop + in-place sigmoid + threshold + paste of segment.py:99-123 in one pass.  logits: fp32 [lsize] of ONE
+ * channel; written (optional, uint8 [msize]): set to 1 where the mask was written (merging the shares of several ranks). */
+int hcu_sigmoid_paste(const float* logits, const int32_t* lsize, const int32_t* crop, const int32_t* ext, void* mask,
+                      int32_t probability, const int32_t* msize, const int32_t* morigin, float threshold, uint8_t* written,
+                      void* stream);
 
 /* ---- input path ---------------------------------------------------------------------------------
  * hcu_load_stack: the RAW stack as skimage.io.imread yields it, src = [b][z][y][x][c] uint8 / uint16 (device memory), ->

@@ -236,6 +236,60 @@ def mint_loader_cases():
     print("loader_cases:", len(cases), os.path.getsize(os.path.join(OUT, "loader_cases.pt")), "bytes")
 
 
+TILER_KW = dict(image_dimensions=3, in_channels=4, out_channels=1, feature_sizes=[4, 8, 16, 32], kernel=K3,
+                upsample_kernel=(8, 8, 2), max_pool_kernel=(2, 2, 1), upsample_stride=(2, 2, 1), dilation=1, groups=2)
+TILER_CUDA_MEM = 4.2e9     # hcat.__CUDA_MEM__ of a 4 GB GPU: EVAL [128, 128, 6], PAD (128, 128, 10) (segment.py:48-57)
+
+
+def mint_tiler_case():
+    """`predict_segmentation_mask` (hcat/segment.py:21-136) of the UNMODIFIED reference on CPU: the deployed architecture of
+    `main.py:46-55` (`groups=2`, `ConvTranspose3d k=(8,8,2)`) at a quarter of its width, a seeded [1, 4, 140, 150, 12] stack with a
+    NaN, a +inf and a -inf voxel, the 4 GB row of the tile table -> 2 x 2 x 2 overlapping tiles of 383 x 383 x 25.  BatchNorm
+    running statistics come from 25 train-mode forwards (random affine parameters); the output bias is then centred on the median logit of the first
+    tile, so that the mask is about half ones with an intricate boundary (a random-init model otherwise says 1 everywhere).
+    The reference is called with a NUMPY image: with torch 2.11 its NaN scrub (`image[np.isnan(image)] = 0`, segment.py:66)
+    raises on a torch tensor (np.isnan returns a uint8 tensor), as a numpy array it runs unmodified."""
+    from oracle.ref_loader import load_reference_tiler
+
+    torch.manual_seed(5)
+    model = build_reference_unet(**TILER_KW)
+    g = torch.Generator().manual_seed(6)
+    img = torch.randn((1, 4, 140, 150, 12), generator=g)
+    img[0, 1, 3, 4, 5] = float("nan")
+    img[0, 2, 100, 7, 1] = float("inf")
+    img[0, 0, 50, 60, 7] = float("-inf")
+    utils, seg = load_reference_tiler(cuda_mem=TILER_CUDA_MEM)
+    with torch.no_grad():
+        for k, v in model.state_dict().items():   # non-trivial BatchNorm affine parameters, like the other fixtures
+            if "batch" in k and k.endswith("weight"):
+                v.copy_(torch.rand(v.shape, generator=g) + 0.5)
+            elif "batch" in k and k.endswith("bias"):
+                v.copy_(torch.randn(v.shape, generator=g) * 0.3 + 0.2)
+        model.train()
+        for _ in range(25):                       # running statistics close to the batch statistics (momentum 0.1)
+            model(torch.randn((1, 4, 140, 140, 12), generator=g))
+        model.eval()
+        clean = img.clone()
+        clean[torch.isnan(clean)] = 0
+        clean[torch.isinf(clean)] = 1
+        tile = utils.pad_image_with_reflections(clean, pad_size=(128, 128, 10))[:, :, 0:383, 0:383, 0:25]
+        model.out_conv.bias -= model(tile)[:, :, 128:256, 128:256, 10:16].median()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    mask = seg.predict_segmentation_mask(model, img.clone().numpy(), "cpu")
+    prob = seg.predict_segmentation_mask(model, img.clone().numpy(), "cpu", use_probability_map=True)
+    print()
+    assert mask.dtype == torch.uint8 and prob.dtype == torch.float32
+    frac = float(mask.float().mean())
+    assert 0.2 < frac < 0.8, frac
+    import numpy as np
+    torch.save({"torch_version": torch.__version__, "kwargs": TILER_KW, "cuda_mem": TILER_CUDA_MEM, "state_dict": sd, "image": img,
+                "mask_bits": torch.from_numpy(np.packbits(mask.numpy().reshape(-1))), "mask_shape": list(mask.shape),
+                "prob": prob.half(), "ones_fraction": frac,
+                "x_ind": utils.calculate_indexes(128, 128, 140, 396), "z_ind": utils.calculate_indexes(10, 6, 12, 32)},
+               os.path.join(OUT, "tiler_prod.pt"))
+    print("tiler_prod: ones", frac, os.path.getsize(os.path.join(OUT, "tiler_prod.pt")), "bytes")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     which = sys.argv[1:] or ["small", "full"]
@@ -245,6 +299,8 @@ def main():
         mint_loss_cases()
     if "small" in which or "loader" in which:
         mint_loader_cases()
+    if "small" in which or "tiler" in which:
+        mint_tiler_case()
     for name, (kwargs, xshape, seed) in FULL_CASES.items():
         if "full" in which or name in which:
             mint_full_case(name, kwargs, xshape, seed)

@@ -187,3 +187,61 @@ def build_reference_unet(**kwargs):
         finally:
             conv_mod.ConvTranspose3d = saved
     return ref.Unet_Constructor(**kwargs)
+
+
+_TILER_STUBS = ["skimage", "skimage.exposure", "skimage.filters", "skimage.morphology", "skimage.feature", "skimage.segmentation",
+                "skimage.transform", "skimage.io", "GPy", "matplotlib", "matplotlib.pyplot", "torchvision", "torchvision.ops"]
+
+
+def load_reference_tiler(cuda_mem=None):
+    """The reference's overlap-tile driver, UNMODIFIED source (build container only; not staged):
+    ``hcat/utils.py`` (``pad_image_with_reflections``, ``calculate_indexes``) and ``hcat/segment.py``
+    (``predict_segmentation_mask``).  Their module-level imports of skimage / GPy / matplotlib (absent from this image;
+    none of them is touched by the three functions) are satisfied by empty stub modules, ``hcat.haircell`` by a stub class,
+    and the package attribute ``hcat.__CUDA_MEM__`` (`hcat/__init__.py`: the GPU's memory in bytes, or None) is ``cuda_mem``:
+    it selects the tile size table of `segment.py:48-57`.  Returns (utils module, segment module)."""
+    root = "/root/reference/hcat"
+    if not os.path.isfile(os.path.join(root, "segment.py")):
+        raise FileNotFoundError("reference tiler not mounted")
+    key = ("tiler", cuda_mem)
+    if key in _cache:
+        return _cache[key]
+    names = list(_TILER_STUBS) + ["hcat", "hcat.utils", "hcat.haircell"]
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        for k in _TILER_STUBS:
+            try:
+                __import__(k)
+            except Exception:
+                m = types.ModuleType(k)
+                m.__path__ = []
+                sys.modules[k] = m
+        for k in _TILER_STUBS:
+            if "." in k:
+                parent, child = k.rsplit(".", 1)
+                if not hasattr(sys.modules[parent], child):
+                    setattr(sys.modules[parent], child, sys.modules[k])
+        pkg = types.ModuleType("hcat")
+        pkg.__path__ = []
+        pkg.__CUDA_MEM__ = cuda_mem
+        sys.modules["hcat"] = pkg
+        hc = types.ModuleType("hcat.haircell")
+        hc.HairCell = type("HairCell", (), {})
+        sys.modules["hcat.haircell"] = hc
+        spec = importlib.util.spec_from_file_location("hcat.utils", os.path.join(root, "utils.py"))
+        utils = importlib.util.module_from_spec(spec)
+        sys.modules["hcat.utils"] = utils
+        spec.loader.exec_module(utils)
+        pkg.utils = utils
+        spec = importlib.util.spec_from_file_location("_hcat_reference.segment", os.path.join(root, "segment.py"))
+        seg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(seg)
+        seg.hcat = pkg     # keep the stub package (with this cuda_mem) bound to the module after sys.modules is restored
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cache[key] = (utils, seg)
+    return utils, seg

@@ -153,3 +153,75 @@ def test_oracle_matches_live_reference_and_quirks():
     for method in ("pixel", "sigmoid", "worst_z"):
         assert torch.equal(L.cross_entropy(p, m, w, method), O.cross_entropy(p, m, w, method))
     assert torch.equal(L.dice(p, m), O.dice(p, m))
+
+
+# ---- overlap-tile driver (hcat/segment.py:21-136, hcat/utils.py:33-124) --------------------------------------------------
+
+def _tiler_fixture():
+    import numpy as np
+
+    fx = torch.load(__import__("os").path.join(__import__("conftest").GOLDEN, "tiler_prod.pt"), weights_only=False)
+    n = 1
+    for v in fx["mask_shape"]:
+        n *= v
+    fx["mask"] = torch.from_numpy(np.unpackbits(fx["mask_bits"].numpy())[:n].reshape(fx["mask_shape"]))
+    return fx
+
+
+def test_tiler_oracle_matches_golden_mask():
+    """oracle/tiler_oracle.py (restated tile loop) around oracle/unet_oracle.unet_forward (restated network, eval mode) ==
+    the mask the unmodified reference produced, voxel for voxel; probabilities to fp16 storage of the fixture."""
+    from oracle import tiler_oracle as T
+
+    fx = _tiler_fixture()
+
+    def forward(t):
+        return O.unet_forward(fx["state_dict"], fx["kwargs"], t, training=False)[0]
+
+    mask, skipped = T.predict_segmentation_mask(forward, fx["image"].clone(), cuda_mem=fx["cuda_mem"])
+    assert skipped == 0 and mask.dtype == torch.uint8 and list(mask.shape) == fx["mask_shape"]
+    assert torch.equal(mask, fx["mask"])
+    assert 0.3 < float(mask.float().mean()) < 0.7      # a non-trivial mask (about half ones)
+    prob, _ = T.predict_segmentation_mask(forward, fx["image"].clone(), use_probability_map=True, cuda_mem=fx["cuda_mem"])
+    assert torch.equal(prob.half(), fx["prob"])
+
+
+def test_tile_index_arithmetic_matches_the_reference():
+    """`calculate_indexes` of the product (pure integers), of the oracle and -- when mounted -- of the reference agree,
+    including its quirks (tiles eval + 2 pad - 1 wide, the fallback pair for short extents, [[0, n]] for eval > n)."""
+    from hcunet_b200 import segment as S
+    from oracle import tiler_oracle as T
+
+    fx = _tiler_fixture()
+    assert S.calculate_indexes(128, 128, 140, 396) == fx["x_ind"] and S.calculate_indexes(10, 6, 12, 32) == fx["z_ind"]
+    cases = [(128, 128, 140, 396), (128, 300, 330, 586), (10, 6, 8, 28), (10, 15, 18, 38), (128, 300, 2048, 2304),
+             (10, 15, 128, 148), (128, 300, 200, 456), (128, 300, 300, 556), (30, 50, 49, 109), (6, 7, 100, 112)]
+    ref = None
+    from oracle.ref_loader import reference_is_live
+    if reference_is_live():
+        from oracle.ref_loader import load_reference_tiler
+        ref = load_reference_tiler()[0]
+    for c in cases:
+        assert S.calculate_indexes(*c) == T.calculate_indexes(*c), c
+        if ref is not None:
+            assert S.calculate_indexes(*c) == ref.calculate_indexes(*c), c
+    # tile order: z outermost, then x, then y (segment.py:78-80)
+    tl = S.tile_list((140, 150, 12), (128, 128, 10), (128, 128, 6))
+    assert len(tl) == 8 and tl[0] == ([0, 383], [0, 383], [0, 25]) and tl[1][1] == [22, 405] and tl[4][2] == [6, 31]
+
+
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).reference_is_live(), reason="reference not mounted")
+def test_tiler_oracle_matches_live_reference_padding():
+    """utils.py:33-74 on a seeded stack: the oracle's three flips + cats == the reference's numpy flips, bit for bit."""
+    from oracle import tiler_oracle as T
+    from oracle.ref_loader import load_reference_tiler
+
+    utils, _ = load_reference_tiler()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((2, 3, 9, 11, 8), generator=g)
+    # (pad 0 is not compared: the reference's `image[pad-1::-1]` then mirrors the WHOLE extent, utils.py:50; the tiler always
+    # pads by (128, 128, 10), segment.py:53-56)
+    for pad in ((2, 4, 6), (8, 10, 8), (4, 2, 2)):
+        assert torch.equal(T.pad_image_with_reflections(x, pad), utils.pad_image_with_reflections(x, pad))
+    with pytest.raises(ValueError):
+        T.pad_image_with_reflections(x, (3, 2, 2))
