@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--z", type=int, default=SHAPE[3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra legs (BASELINE configs 3 / 4 / 5) of the line")
     return ap.parse_args()
 
 
@@ -207,6 +208,154 @@ def _stage(msg):
     """Progress marker on stderr (multi-GPU hangs are otherwise silent)."""
     if os.environ.get("HCUNET_BENCH_VERBOSE", "0") != "0":
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
+# ---- extra legs: the other BASELINE.json configurations, reported inside the same JSON line ("extra") ---------------
+
+def _timed_region(dist, world, dev, fn, steps):
+    """`steps` calls of fn between barrier + synchronize, CUDA events, max over ranks -> seconds per call."""
+    import torch
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t) / steps
+
+
+def extra_cfg4(H, dist, world, rank, dev, model, opt, sync, precision, steps):
+    """BASELINE configs[3]: the same model and step on 256 x 256 x 64 patches, batch 4 per GPU, data-parallel (NCCL gradient
+    all-reduce at world > 1), inputs resident, one CUDA graph per step."""
+    import torch
+    from hcunet_b200.graph import GraphedTrainStep
+
+    B, C, X, Y, Z = 4, 4, 256, 256, 64
+    loader = H.StackLoader(model)
+    g = torch.Generator().manual_seed(4321 + rank)
+    raw = torch.randint(0, 256, (B, Z, Y, X, C), generator=g, dtype=torch.uint8).to(dev)
+    ext = loader.label_extent((B, Z, Y, X, C))
+    msk = loader.labels((torch.rand((B, Z, Y, X), generator=g) > 0.7).half().pin_memory(), ext)
+    pwl = loader.labels((torch.rand((B, Z, Y, X), generator=g) * 3).half().pin_memory(), ext)
+
+    def eager():
+        opt.zero_grad(set_to_none=True)
+        H.cross_entropy(model(loader.image(raw)), msk, pwl, "pixel").backward()
+        sync.allreduce()
+        opt.step()
+
+    for _ in range(3):   # this shape's step cache
+        eager()
+    gstep = GraphedTrainStep(model, opt, lambda lg, m, w: H.cross_entropy(lg, m, w, "pixel"), (raw, msk, pwl),
+                             grad_sync=sync.allreduce if world > 1 else None, input_fn=loader.image)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step(i):
+        flush.zero_()
+        gstep.run()
+
+    for i in range(3):
+        step(i)
+    t = _timed_region(dist, world, dev, step, steps)
+    t_flush = _timed_region(dist, world, dev, lambda i: flush.zero_(), steps)
+    t = max(1e-9, t - t_flush)
+    del gstep
+    return {"workload": "BASELINE configs[3]: README 3D model, train step on 256x256x64 patches, data-parallel",
+            "patch": [C, X, Y, Z], "batch_per_gpu": B, "global_batch": B * world, "n_gpus": world, "precision": precision,
+            "ms_per_step": t * 1e3, "value": B * X * Y * Z * world / t, "unit": UNIT, "steps": steps,
+            "timing": "CUDA events, max over ranks, inputs resident, L2 flushed between steps (flush time subtracted)"}
+
+
+def extra_cfg5(H, dist, world, rank, dev, precision):
+    """BASELINE configs[4]: overlap-tile inference of a synthetic 4 x 2048 x 2048 x 128 stack (fp16, pinned host memory) with
+    the README model in eval mode, the tile grid sharded over the ranks with NO communication (hcunet_b200.tiling): every
+    rank copies its tiles host -> device and runs them; the time is the max over ranks."""
+    import torch
+    from hcunet_b200 import tiling
+
+    kw = dict(image_dimensions=3, in_channels=4, out_channels=1, feature_sizes=[8, 16, 32, 64, 128],
+              kernel={"conv1": (3, 3, 2), "conv2": (3, 3, 1)}, upsample_kernel=(2, 2, 2), max_pool_kernel=(2, 2, 1),
+              upsample_stride=(2, 2, 1), dilation=1, groups=1)
+    torch.manual_seed(0)
+    model = H.Unet_Constructor(**kw)
+    model.precision = precision
+    model = model.to(dev)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        model.train()
+        model(torch.randn((1, 4, 256, 256, 32), generator=g).half().to(dev))
+        model.eval()
+    X = Y = 2048
+    Z = 128
+    tile_out = 512 if world > 1 else 1024
+    align, margin, mz = tiling.tile_geometry(model.model_specification)
+    ox, oy = tiling.tiled_output_extent(model.model_specification, X), tiling.tiled_output_extent(model.model_specification, Y)
+    all_tiles = tiling.tile_grid((ox, oy), tile_out, align)
+    mine = tiling.shard_tiles(all_tiles, world, rank)
+    # this rank's rows of the stack only (its tiles' input footprint), cheap synthetic content
+    stack = torch.empty((1, 4, X, Y, Z), dtype=torch.float16).pin_memory()
+    xs = sorted({t[0] for t in mine}) or [0]
+    x_lo, x_hi = xs[0], min(X, max(t[1] for t in mine) + margin + align) if mine else 1
+    for c in range(4):
+        stack[0, c, x_lo:x_hi] = torch.randn((x_hi - x_lo, 1, 1), generator=g).half() * torch.randn((1, Y, Z), generator=g).half()
+    out, tiles = tiling.predict_tiled(model, stack, tile_out=tile_out, world=world, rank=rank)     # warm-up (step cache)
+    t = _timed_region(dist, world, dev, lambda i: tiling.predict_tiled(model, stack, tile_out=tile_out, world=world, rank=rank,
+                                                                       out=out), 2)
+    finite = bool(torch.isfinite(out).all())
+    del out, stack
+    return {"workload": "BASELINE configs[4]: README 3D model eval, overlap-tile inference of a 4x2048x2048x128 fp16 stack from "
+                        "pinned host memory, tiles sharded over the ranks (no communication)",
+            "n_gpus": world, "tile_out": tile_out, "tiles_total": len(all_tiles), "tiles_this_rank": len(tiles),
+            "precision": precision, "seconds_whole_stack": t, "input_voxels_per_s": X * Y * Z / t,
+            "output_voxels_per_s": ox * oy * (Z - mz) / t, "finite": finite,
+            "timing": "CUDA events around every rank's share (tile H2D copies inside), max over ranks"}
+
+
+def extra_cfg3(H, dev, precision, steps):
+    """BASELINE configs[2]: classic 2D U-Net (the constructor's defaults: features [32..1024], 3x3, ConvTranspose 2x2 s2), train
+    step on batch 16 of 572 x 572 x 3 tiles, one GPU, inputs resident."""
+    import torch
+    from hcunet_b200.graph import GraphedTrainStep
+
+    B = 16
+    torch.manual_seed(0)
+    model = H.Unet_Constructor()
+    model.precision = precision
+    model = model.to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
+    g = torch.Generator().manual_seed(1)
+    img = torch.randn((B, 3, 572, 572), generator=g).half().to(dev)
+    msk = (torch.rand((B, 2, 572, 572), generator=g) > 0.7).half().to(dev)
+    pwl = (torch.rand((B, 2, 572, 572), generator=g) * 3).half().to(dev)
+    loss_fn = lambda lg, m, w: H.cross_entropy(lg, m, w, "pixel")  # noqa: E731
+    for _ in range(3):
+        opt.zero_grad(set_to_none=True)
+        loss_fn(model(img), msk, pwl).backward()
+        opt.step()
+    gstep = GraphedTrainStep(model, opt, loss_fn, (img, msk, pwl))
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+
+    def step(i):
+        flush.zero_()
+        gstep.run()
+
+    for i in range(2):
+        step(i)
+    t = _timed_region(None, 1, dev, step, steps) - _timed_region(None, 1, dev, lambda i: flush.zero_(), steps)
+    flops = 3 * 169471 * 572 * 572 * B
+    del gstep
+    return {"workload": "BASELINE configs[2]: classic 2D U-Net [32..1024] k(3,3), ConvTranspose2d s2, train step on 572x572x3 tiles",
+            "batch": B, "n_gpus": 1, "precision": precision, "ms_per_step": t * 1e3, "pixels_per_s": B * 572 * 572 / t,
+            "train_tflops": flops / t / 1e12, "of_bf16_sustained_peak": None, "steps": steps}
 
 
 def main_ours(args):
@@ -455,6 +604,30 @@ def main_ours(args):
                         "note": "host inputs = the raw stack as the reference dataloader reads it (uint8 [B,Z,Y,X,C], pinned) + fp16 mask / pwl [B,Z,Y,X] (pinned); per step, on a copy stream one step ahead: the raw stack H2D straight into the static input of one of two alternating CUDA graphs, and the origin crop of mask / pwl that the loss reads (loss.py:51-56) gathered in place from pinned host memory (hcu_load_labels); the graph starts with hcu_load_stack (to_float / reshape / normalize / to_tensor on the device); every step's loss is copied D2H into pinned memory and read by the host one step later"},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
                 "loss_first_last": [losses[0], losses[-1]] if losses else None}
+    # ---- the other BASELINE configurations, inside the same line ----
+    extra = None
+    if not args.no_extra:
+        extra = {}
+        k4 = max(3, min(args.steps, 10))
+        for name, fn in (("cfg4", lambda: extra_cfg4(H, dist if world > 1 else None, world, rank, dev, model, opt, sync, args.precision, k4)),
+                         ("cfg5", lambda: extra_cfg5(H, dist if world > 1 else None, world, rank, dev, args.precision)),
+                         ("cfg3", (lambda: extra_cfg3(H, dev, args.precision, 3)) if world == 1 else None)):
+            if fn is None:
+                continue
+            try:
+                extra[name] = fn()
+            except Exception as e:   # an extra leg must never take the headline line down (all ranks see the same exception path)
+                extra[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            _stage(f"extra {name} done")
+            torch.cuda.empty_cache()
+        if rank == 0 and extra.get("cfg3") and "train_tflops" in extra["cfg3"]:
+            try:
+                pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+                extra["cfg3"]["of_bf16_sustained_peak"] = extra["cfg3"]["train_tflops"] / pk["bf16_tflops_sustained"]
+            except Exception:
+                pass
+        if line is not None:
+            line["extra"] = extra
     if world > 1:
         dist.barrier()
     if rank == 0:
