@@ -382,6 +382,10 @@ def main_ours(args):
     model.precision = args.precision
     model = model.to(dev).train()
     sync = GradSync(model, world)          # broadcast params from rank 0; fp32 mean all-reduce of the gradients
+    overlap_ar = world > 1 and os.environ.get("HCUNET_AR_OVERLAP", "1") != "0"
+    if overlap_ar:
+        # the exchange is launched from inside backward (two buckets, communication stream) and captured with the step
+        sync.attach()
     _stage("parameters broadcast")
     use_graph = os.environ.get("HCUNET_BENCH_GRAPH", "1") != "0"
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
@@ -595,6 +599,10 @@ def main_ours(args):
                 "data": "synthetic (seeded), random-init weights",
                 "config": {"workload": WORKLOAD, "patch": [C, X, Y, Z], "batch_per_gpu": B, "global_batch": B * world,
                            "precision": args.precision, "parallelism": f"dp{world}", "optimizer": "Adam(fused) lr 1e-3",
+                           "gradient_exchange": None if world == 1 else (
+                               "NCCL all-reduce (mean, fp32, in place on the engine's flat gradient buffer) in two buckets launched "
+                               "from inside backward on a communication stream, captured in the step's CUDA graph"
+                               if overlap_ar else "one NCCL all-reduce between the backward graph and the optimiser graph"),
                            "input": "raw uint8 stack [B,Z,Y,X,C] -> hcunet_b200.StackLoader (hcu_load_stack inside the step)",
                            "launch": "one CUDA graph per step (hcunet_b200.graph.GraphedTrainStep)" if use_graph else "eager",
                            "l2": "256 MB buffer zeroed between iterations, its time measured alone and subtracted",
@@ -638,6 +646,14 @@ def main_ours(args):
             line["cpu_baseline"] = None
         emit(line)
     if world > 1:
+        # captured collectives: drop the graphs before the communicator, and never let a teardown problem hold the ranks
+        import gc
+        t_exit = threading.Timer(30.0, lambda: os._exit(0))
+        t_exit.daemon = True
+        t_exit.start()
+        gstep = gstep2 = gsteps = step = None   # noqa: F841
+        gc.collect()
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

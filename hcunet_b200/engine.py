@@ -257,6 +257,9 @@ class _StepCache:
         self.g_total = 0
         self.scatter_table = None
         self.scatter_blocks = 0
+        # data-parallel overlap: the scatter jobs recorded before / after the bucket split (UnetEngine.grad_ready_hook)
+        self.split_at = None            # number of scatter jobs that belong to the EARLY bucket (None: one bucket)
+        self.scatter_tables2 = None     # [(table, njobs, blocks)] for the early and the late part
 
     @staticmethod
     def _sig(params, names):
@@ -305,6 +308,16 @@ class _StepCache:
             self.scatter_blocks = blocks.value
             self.scatter_table = torch.frombuffer(bytearray(host.raw), dtype=torch.uint8).to(device)
             self.wacc = torch.empty(pc, dtype=torch.float32, device=device)
+            if self.split_at is not None and 0 < self.split_at < m:
+                self.scatter_tables2 = []
+                for a, b in ((0, self.split_at), (self.split_at, m)):
+                    k = b - a
+                    host2 = C.create_string_buffer(k * _lib.BATCH_JOB_BYTES)
+                    blk = C.c_int32(0)
+                    _lib.check(lib.hcu_weight_scatter_batch_build((HcuWeightMap * k)(*list(maps)[a:b]), (C.c_int32 * k)(*list(nsp)[a:b]),
+                                                                  (C.c_int64 * k)(*po[a:b]), (C.c_int64 * k)(*go[a:b]), k, host2,
+                                                                  C.byref(blk)), "weight_scatter_batch_build")
+                    self.scatter_tables2.append((torch.frombuffer(bytearray(host2.raw), dtype=torch.uint8).to(device), k, blk.value))
         self.ptr_sig = self._sig(params, [j[2] for j in self.pack_jobs.values()])
         self.ready = True
 
@@ -333,6 +346,12 @@ class UnetEngine:
         # stream right after every stored tensor of a step has been produced (channels-last [B, S, C pitch]); it may read
         # the tensor or overwrite it in place.  None in normal operation.
         self.tap = None
+        # Data-parallel overlap (hcunet_b200.parallel.GradSync.attach): called twice per backward with (flat, lo, hi, events) -- the
+        # range [lo, hi) of the flat gradient buffer `flat` that is final once `events` have completed.  First when the deep levels
+        # and the whole up path are done (most of the parameters: their all-reduce runs while the first levels' backward --
+        # most of the time -- is still computing), then for the rest at the end.  Returns an event the backward's stream
+        # waits for before it returns (or None).
+        self.grad_ready_hook = None
 
     @property
     def lib(self):
@@ -726,6 +745,7 @@ class UnetEngine:
         self._tap("dlogits", dcur, co, plan.out_sz)
         self._inv = inv
         dx = None
+        split_done = False
         SB = _lib.STAT_BINS
         nstat = sum(2 * it[1].cout_t * SB for it in saved if it[0] == "conv")
         nbn = sum(1 for it in saved if it[0] == "conv")
@@ -733,8 +753,48 @@ class UnetEngine:
         zero_ws = torch.zeros(nstat + nbn, dtype=torch.float64, device=dev)
         kbn = 0
         zoff = 0
+        # bucket split of the data-parallel overlap: the down levels below the two deepest are the LATE bucket (the flat
+        # buffer is in parameter order out_conv | down_steps.* | up_steps.*, so late = [0, offset of the first early level))
+        hook = self.grad_ready_hook
+        split_name, split_off, hook_events = None, 0, []
+        if hook is not None:
+            nlev = len(self.spec["feature_sizes"])
+            first_early = f"down_steps.{max(0, nlev - 2)}."
+            offs = [o for n_, (o, _) in self._goff.items() if n_.startswith(first_early)]
+            late_names = [n_ for n_, (o, _) in self._goff.items() if offs and o < min(offs)]
+            if offs and nlev > 2 and all(n_.startswith("out_conv") or n_.startswith("down_steps.") for n_ in late_names):
+                split_off = min(offs)
+                split_name = f"down_steps.{nlev - 3}.conv2"      # the first late layer the backward reaches
         for item in reversed(saved):
             kind = item[0]
+            if split_name is not None and kind == "conv" and item[1].name == split_name:
+                # ---- early bucket complete: up path + the two deepest levels ----
+                if cache is not None and not cache.ready and cache.split_at is None:
+                    cache.split_at = len(cache.scatter_jobs)
+                evs = []
+                if batched and cache.scatter_tables2 is not None:
+                    tab, k, blk = cache.scatter_tables2[0]
+                    with torch.cuda.stream(side) if side is not None else _NullCtx():
+                        _lib.check(lib.hcu_weight_scatter_batch(_ptr(tab), k, blk, _ptr(cache.wacc), 1.0, _ptr(inv),
+                                                                _ptr(self._gflat), self._stream()), "weight_scatter_batch")
+                        if side is not None:
+                            e_s = torch.cuda.Event()
+                            e_s.record()
+                            evs.append(e_s)
+                    e_m = torch.cuda.Event()
+                    e_m.record()
+                    evs.append(e_m)
+                    done = hook(self._gflat, split_off, self._gflat.numel(), evs)
+                    if done is not None:
+                        hook_events.append(done)
+                    split_done = True
+                elif not batched:
+                    e_m = torch.cuda.Event()
+                    e_m.record()
+                    done = hook(self._gflat, split_off, self._gflat.numel(), [e_m])
+                    if done is not None:
+                        hook_events.append(done)
+                    split_done = True
             if kind == "out":
                 _, g, a_in, a_cp, a_xf = item
                 npix = B * So
@@ -852,11 +912,24 @@ class UnetEngine:
             if side is not None and self.n_side > 1:
                 side.wait_stream(self._side2)
             with torch.cuda.stream(side) if side is not None else _NullCtx():
-                _lib.check(lib.hcu_weight_scatter_batch(_ptr(cache.scatter_table), len(cache.scatter_jobs),
-                                                        cache.scatter_blocks, _ptr(cache.wacc), 1.0, _ptr(inv),
-                                                        _ptr(self._gflat), self._stream()), "weight_scatter_batch")
+                if split_done and cache.scatter_tables2 is not None:   # the early part was scattered at the split
+                    tab, k, blk = cache.scatter_tables2[1]
+                    _lib.check(lib.hcu_weight_scatter_batch(_ptr(tab), k, blk, _ptr(cache.wacc), 1.0, _ptr(inv),
+                                                            _ptr(self._gflat), self._stream()), "weight_scatter_batch")
+                else:
+                    _lib.check(lib.hcu_weight_scatter_batch(_ptr(cache.scatter_table), len(cache.scatter_jobs),
+                                                            cache.scatter_blocks, _ptr(cache.wacc), 1.0, _ptr(inv),
+                                                            _ptr(self._gflat), self._stream()), "weight_scatter_batch")
             if side is not None:
                 torch.cuda.current_stream().wait_stream(side)
+        if hook is not None:
+            e_m = torch.cuda.Event()
+            e_m.record()
+            done = hook(self._gflat, 0, split_off if split_done else self._gflat.numel(), [e_m])
+            if done is not None:
+                hook_events.append(done)
+            for ev in hook_events:
+                torch.cuda.current_stream().wait_event(ev)
         if cache is not None:
             cache.bwd_done = True
         self._keep.clear()

@@ -50,6 +50,12 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.g_main = torch.cuda.CUDAGraph()
         self.g_opt = None
+        owner = getattr(grad_sync, "__self__", None)
+        if owner is not None and getattr(owner, "attached", False):
+            # GradSync.attach(): the collectives are launched inside backward on a communication stream and are captured as a
+            # branch of the ONE graph (forward, backward with the all-reduces overlapped, optimiser)
+            grad_sync = None
+            self.grad_sync = None
         if grad_sync is None:
             with torch.cuda.graph(self.g_main):
                 self._fwd_bwd()

@@ -34,11 +34,52 @@ class GradSync:
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         self.params: List[torch.nn.Parameter] = [p for p in module.parameters() if p.requires_grad]
         self._flat = None
+        self.attached = False
         self.in_place_steps = 0     # how many exchanges ran on the engine's own buffer (tests / bench report it)
         if self.world > 1 and broadcast:
             with torch.no_grad():
                 for t in list(module.parameters()) + list(module.buffers()):
                     dist.broadcast(t, src=0)
+
+    # ---- all-reduce overlapped with backward ------------------------------------------------------------------------
+    def attach(self):
+        """Launch the exchange from INSIDE the backward pass: the engine reports when a range of its flat gradient buffer is
+        final (`UnetEngine.grad_ready_hook`) -- first the up path + the two deepest levels (~97 % of the README model's
+        parameters, ready after ~40 % of the backward's time), then the first levels at the end -- and each range is
+        all-reduced (mean) in place on a communication stream while the backward keeps computing.  The backward's stream
+        waits for both collectives before it returns, so `optimizer.step()` may follow directly and `allreduce()` becomes a
+        no-op.  Capturable: inside `torch.cuda.graph` the collectives become nodes of the step's graph on their own branch.
+        Attach BEFORE the first training step (the engine records the bucket split with its step cache)."""
+        eng = getattr(self.module, "_engine", None)
+        if eng is None:
+            raise RuntimeError("GradSync.attach needs a hcunet_b200.Unet_Constructor")
+        self._comm = None
+        self.overlapped_steps = 0
+        self._bucket_calls = 0
+        eng.grad_ready_hook = self._on_grads_ready
+        self.attached = True
+        return self
+
+    def _on_grads_ready(self, flat, lo, hi, events):
+        if self.world <= 1 or hi <= lo:
+            return None
+        if self._comm is None or self._comm.device != flat.device:
+            self._comm = torch.cuda.Stream(device=flat.device) if flat.is_cuda else None
+        part = flat[lo:hi]
+        if self._comm is None:          # CPU tensors (gloo tests): no streams
+            self._reduce_mean(part)
+            self._bucket_calls += 1
+            return None
+        for ev in events:
+            self._comm.wait_event(ev)
+        with torch.cuda.stream(self._comm):
+            self._reduce_mean(part)
+            done = torch.cuda.Event()
+            done.record()
+        self._bucket_calls += 1
+        if lo == 0:
+            self.overlapped_steps += 1
+        return done
 
     def _engine_flat(self):
         """The engine's flat gradient buffer if every ``.grad`` is the view of it the engine returned, else None."""
@@ -63,8 +104,8 @@ class GradSync:
             flat.mul_(1.0 / self.world)
 
     def allreduce(self):
-        if self.world <= 1:
-            return
+        if self.world <= 1 or getattr(self, "attached", False):
+            return      # attached: the exchange already ran inside backward (see attach())
         flat = self._engine_flat()
         if flat is not None:
             self._reduce_mean(flat)

@@ -85,6 +85,14 @@ def _worker(rank, world, port, ret):
         assert sync.in_place_steps == 1 and flat.data_ptr() == ptr
         first = [float(p.grad.flatten()[0]) for p in m.parameters()][:3]
         assert first == [0.5 + i for i in range(3)], first      # mean over ranks {0, 1} of (rank + i)
+        # overlapped exchange (GradSync.attach): the engine reports two ranges of its flat buffer, each is averaged in place
+        sync.attach()
+        flat2 = torch.arange(n, dtype=torch.float32) * (rank + 1)
+        split = n // 3
+        assert sync._on_grads_ready(flat2, split, n, []) is None and sync._on_grads_ready(flat2, 0, split, []) is None
+        assert torch.equal(flat2, torch.arange(n, dtype=torch.float32) * 1.5) and sync.overlapped_steps == 0 and sync._bucket_calls == 2
+        sync.allreduce()                          # attached: a no-op
+        assert torch.equal(flat2, torch.arange(n, dtype=torch.float32) * 1.5)
         ret[rank] = (w0, g, [float(v) for v in g[:1]] and [float(x) for x in h3(m, lo, hi)])
     finally:
         dist.destroy_process_group()
