@@ -233,7 +233,7 @@ def _timed_region(dist, world, dev, fn, steps):
     return float(t) / steps
 
 
-def extra_cfg4(H, dist, world, rank, dev, model, opt, sync, precision, steps):
+def extra_cfg4(H, dist, world, rank, dev, model, opt, sync, precision, steps, flat=None):
     """BASELINE configs[3]: the same model and step on 256 x 256 x 64 patches, batch 4 per GPU, data-parallel (NCCL gradient
     all-reduce at world > 1), inputs resident, one CUDA graph per step."""
     import torch
@@ -248,15 +248,20 @@ def extra_cfg4(H, dist, world, rank, dev, model, opt, sync, precision, steps):
     pwl = loader.labels((torch.rand((B, Z, Y, X), generator=g) * 3).half().pin_memory(), ext)
 
     def eager():
-        opt.zero_grad(set_to_none=True)
+        if flat is not None:
+            flat.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
         H.cross_entropy(model(loader.image(raw)), msk, pwl, "pixel").backward()
+        if flat is not None:
+            flat.sync_grad()
         sync.allreduce()
         opt.step()
 
     for _ in range(3):   # this shape's step cache
         eager()
     gstep = GraphedTrainStep(model, opt, lambda lg, m, w: H.cross_entropy(lg, m, w, "pixel"), (raw, msk, pwl),
-                             grad_sync=sync.allreduce if world > 1 else None, input_fn=loader.image)
+                             grad_sync=sync.allreduce if world > 1 else None, input_fn=loader.image, flat=flat)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
     def step(i):
@@ -388,7 +393,20 @@ def main_ours(args):
         sync.attach()
     _stage("parameters broadcast")
     use_graph = os.environ.get("HCUNET_BENCH_GRAPH", "1") != "0"
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
+    # the optimiser holds ONE flat parameter (every nn.Parameter is a view of it; its gradient is the engine's flat gradient
+    # buffer): one elementwise Adam launch instead of a multi-tensor pass over 136 tensors + 136 step counters (0.10 -> 0.01 ms)
+    flat = H.FlatParameters(model) if os.environ.get("HCUNET_FLAT_ADAM", "1") != "0" else None
+    opt = torch.optim.Adam([flat.flat] if flat is not None else model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
+
+    def zero_grads():
+        if flat is not None:
+            flat.zero_grad()
+        else:
+            opt.zero_grad(set_to_none=True)
+
+    def grads_ready():
+        if flat is not None:
+            flat.sync_grad()
 
     # Synthetic patches as the reference dataloader finds them on disk (dataloader.py:40-58): the RAW stack [Z, Y, X, C] uint8
     # as skimage.io.imread yields it, mask / pwl [Z, Y, X].  hcunet_b200.StackLoader is the input path (to_float -> reshape ->
@@ -411,10 +429,11 @@ def main_ours(args):
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def eager_step(raw, msk, pwl):
-        opt.zero_grad(set_to_none=True)
+        zero_grads()
         logits = model(loader.image(raw))
         loss = H.cross_entropy(logits, msk, pwl, "pixel")
         loss.backward()
+        grads_ready()
         sync.allreduce()
         opt.step()
         return loss
@@ -431,7 +450,7 @@ def main_ours(args):
         from hcunet_b200.graph import GraphedTrainStep
 
         gstep = GraphedTrainStep(model, opt, lambda lg, m, w: H.cross_entropy(lg, m, w, "pixel"), resident[0],
-                                 grad_sync=sync.allreduce if world > 1 else None, input_fn=loader.image)
+                                 grad_sync=sync.allreduce if world > 1 else None, input_fn=loader.image, flat=flat)
         # one CUDA-graph launch per step; the inputs are copied into the graph's static buffers (device->device here,
         # pinned host->device in the e2e leg) inside the timed region
         step = gstep
@@ -483,7 +502,7 @@ def main_ours(args):
         # Two captured graphs of the same step (same model, same optimiser), each with its own static input buffers: the
         # copy stream fills graph B's inputs from pinned host memory while graph A runs -- no device-to-device staging copy.
         gstep2 = GraphedTrainStep(model, opt, lambda lg, m, w: H.cross_entropy(lg, m, w, "pixel"), resident[0],
-                                  grad_sync=sync.allreduce if world > 1 else None, input_fn=loader.image)
+                                  grad_sync=sync.allreduce if world > 1 else None, input_fn=loader.image, flat=flat)
         gsteps = [gstep, gstep2]
         slots = [tuple(g_.static_in) for g_ in gsteps]
         _stage("second graph captured (double-buffered inputs)")
@@ -554,6 +573,7 @@ def main_ours(args):
         except Exception:
             pass
         prof = profiler.KernelProfile()
+        hook_saved, model._engine.grad_ready_hook = model._engine.grad_ready_hook, None   # rank 0 alone: no collective here
         with prof:
             for i in range(min(args.steps, 5)):
                 # Park the GPU behind a ~12 ms spin so the host enqueues the whole step before the first kernel runs:
@@ -561,10 +581,12 @@ def main_ours(args):
                 torch.cuda._sleep(int(12e-3 * 1.9e9))
                 # eager: per-kernel events need individual launches.  No gradient all-reduce here: only rank 0 profiles
                 # (a collective entered by one rank would dead-lock), and the collective is not one of this library's kernels
-                opt.zero_grad(set_to_none=True)
+                zero_grads()
                 H.cross_entropy(model(loader.image(resident[i % NBUF][0])), resident[i % NBUF][1], resident[i % NBUF][2],
                                 "pixel").backward()
+                grads_ready()
                 opt.step()
+        model._engine.grad_ready_hook = hook_saved
         roof = prof.roofline(peaks, t_step * min(args.steps, 5))
         # DRAM traffic of the dominant kernel: not measurable live (needs ncu); the committed capture of the same command
         # (tools/gpu_profile.sh -> profiles/*_traffic.json) is reported per launch, like `achieved`
@@ -598,7 +620,8 @@ def main_ours(args):
                 "vs_baseline": None, "dtype": "fp16 storage, fp32 accumulate" if args.precision == "mixed" else "fp32",
                 "data": "synthetic (seeded), random-init weights",
                 "config": {"workload": WORKLOAD, "patch": [C, X, Y, Z], "batch_per_gpu": B, "global_batch": B * world,
-                           "precision": args.precision, "parallelism": f"dp{world}", "optimizer": "Adam(fused) lr 1e-3",
+                           "precision": args.precision, "parallelism": f"dp{world}",
+                           "optimizer": "Adam(fused) lr 1e-3" + (" on the flat parameter buffer (hcunet_b200.FlatParameters)" if flat is not None else ""),
                            "gradient_exchange": None if world == 1 else (
                                "NCCL all-reduce (mean, fp32, in place on the engine's flat gradient buffer) in two buckets launched "
                                "from inside backward on a communication stream, captured in the step's CUDA graph"
@@ -617,7 +640,7 @@ def main_ours(args):
     if not args.no_extra:
         extra = {}
         k4 = max(3, min(args.steps, 10))
-        for name, fn in (("cfg4", lambda: extra_cfg4(H, dist if world > 1 else None, world, rank, dev, model, opt, sync, args.precision, k4)),
+        for name, fn in (("cfg4", lambda: extra_cfg4(H, dist if world > 1 else None, world, rank, dev, model, opt, sync, args.precision, k4, flat)),
                          ("cfg5", lambda: extra_cfg5(H, dist if world > 1 else None, world, rank, dev, args.precision)),
                          ("cfg3", (lambda: extra_cfg3(H, dev, args.precision, 3)) if world == 1 else None)):
             if fn is None:

@@ -1,0 +1,56 @@
+"""Flat parameter storage for the optimiser step.
+
+The engine already writes every parameter gradient of a step into ONE flat fp32 buffer in parameter order
+(`UnetEngine.last_grad_flat`).  `FlatParameters` gives the parameters the same shape: every `nn.Parameter` of the model
+becomes a view of one fp32 buffer, exposed as ONE `nn.Parameter` (`.flat`) whose `.grad` is the engine's buffer.  An
+optimiser built on `[fp.flat]` then updates the whole model with a single elementwise launch instead of a multi-tensor
+pass over 136 tensors (+ 136 step counters): torch's fused Adam on the README model costs 0.10 ms per step that way,
+3 % of the step.  The arithmetic is the same elementwise update, so the result is bit-identical to
+`torch.optim.Adam(model.parameters())`.
+
+    fp = FlatParameters(model)                       # after model.to(device), before the first step
+    opt = torch.optim.Adam([fp.flat], lr=1e-3, fused=True)
+    loss.backward(); fp.sync_grad(); opt.step(); fp.zero_grad()
+
+`state_dict()` / `load_state_dict()` / `save()` / `load()` of the model keep working (they copy in place); `model.to()`
+afterwards would re-allocate the parameters and break the views (flatten again)."""
+from __future__ import annotations
+
+import torch
+
+
+class FlatParameters:
+    def __init__(self, model: torch.nn.Module):
+        params = [p for p in model.parameters()]
+        if not params:
+            raise ValueError("model has no parameters")
+        dev, dt = params[0].device, params[0].dtype
+        if any(p.device != dev or p.dtype != dt for p in params):
+            raise ValueError("parameters must share one device and dtype")
+        n = sum(p.numel() for p in params)
+        flat = torch.empty(n, dtype=dt, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in params:
+                k = p.numel()
+                flat[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = flat[off:off + k].view(p.shape)
+                off += k
+        self.model = model
+        self.flat = torch.nn.Parameter(flat, requires_grad=True)
+        self.numel = n
+
+    def sync_grad(self):
+        """Point `.flat.grad` at the flat gradient buffer of the latest backward (no copy)."""
+        eng = getattr(self.model, "_engine", None)
+        g = getattr(eng, "last_grad_flat", None) if eng is not None else None
+        if g is None or g.numel() != self.numel:
+            raise RuntimeError("FlatParameters.sync_grad: the engine holds no flat gradient buffer of this model "
+                               "(call it right after loss.backward())")
+        self.flat.grad = g
+
+    def zero_grad(self):
+        """Drop the gradients of the flat parameter AND of the model's parameter views (so that the next backward assigns
+        fresh views instead of accumulating into the old buffer)."""
+        self.flat.grad = None
+        self.model.zero_grad(set_to_none=True)

@@ -26,13 +26,15 @@ class GraphedTrainStep:
     """
 
     def __init__(self, model, optimizer, loss_fn: Callable, example: Sequence[torch.Tensor],
-                 grad_sync: Optional[Callable] = None, warmup: int = 3, input_fn: Optional[Callable] = None):
+                 grad_sync: Optional[Callable] = None, warmup: int = 3, input_fn: Optional[Callable] = None, flat=None):
         if warmup < 3:
             # steps 1-2 record the engine's step cache (per-layer packs, a synchronous table upload): not capturable
             raise ValueError("GraphedTrainStep needs warmup >= 3 (the first two steps record the engine's step cache)")
         self.model, self.optimizer, self.loss_fn, self.grad_sync = model, optimizer, loss_fn, grad_sync
         # input_fn(static_in[0]) -> model input, captured with the step (e.g. StackLoader.image on a raw uint8 stack)
         self.input_fn = input_fn
+        # flat: hcunet_b200.flat.FlatParameters -- the optimiser holds ONE flat parameter whose gradient is the engine's flat buffer
+        self.flat = flat
         self.static_in = [torch.empty_like(t, device=t.device) for t in example]
         for s, t in zip(self.static_in, example):
             s.copy_(t)
@@ -68,11 +70,16 @@ class GraphedTrainStep:
                 optimizer.step()
 
     def _fwd_bwd(self):
-        self.optimizer.zero_grad(set_to_none=True)
+        if self.flat is not None:
+            self.flat.zero_grad()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
         x = self.static_in[0] if self.input_fn is None else self.input_fn(self.static_in[0])
         logits = self.model(x)
         self.loss = self.loss_fn(logits, *self.static_in[1:])
         self.loss.backward()
+        if self.flat is not None:
+            self.flat.sync_grad()
 
     def load(self, *tensors, non_blocking=True):
         """Copy one step's inputs (device or pinned-host tensors) into the static input buffers."""

@@ -242,6 +242,24 @@ class Unet_Constructor(nn.Module):
             return None
 
     def evaluate(self, image: torch.Tensor):
-        """`unet.py:198-233` is unfinished in the reference (returns ``None`` after looping); the tiled
-        inference that callers use lives in `segment.py:21-136` (out of scope this round)."""
-        raise NotImplementedError("Unet_Constructor.evaluate is unfinished in the reference (unet.py:198-233)")
+        """`unet.py:198-233`, as unfinished as in the reference: same argument checks (`ValueError` for a non-tensor,
+        `ImportError` for a channel mismatch -- sic), `eval()`, reflection padding by (100, 100, 8), a forward pass over every
+        200 x 200 XY slice of the padded image whose result is dropped, and `None`.  The tiled inference callers really use
+        is `hcunet_b200.segment.predict_segmentation_mask` (`segment.py:21-136`)."""
+        if not isinstance(image, torch.Tensor):
+            raise ValueError(f'Expected image type of torch.Tensor, not {type(image)}')
+        if image.shape[1] != self.model_specification['in_channels']:
+            raise ImportError(f'Image expected to have {self.model_specification["in_channels"]} not {image.shape[1]}')
+        from .segment import pad_image_with_reflections
+
+        self.eval()
+        pad = (100, 100, 8)
+        skip = 200
+        device = next(self.parameters()).device
+        padded_image = pad_image_with_reflections(image.to(device), pad).float()
+        with torch.no_grad():
+            for x in range(0, padded_image.shape[2], skip):
+                for y in range(0, padded_image.shape[3], skip):
+                    slice_to_eval = padded_image[:, :, x:x + skip, y:y + skip, :]
+                    self.forward(slice_to_eval)      # the reference slices the result into `mask_slice` and drops it
+        return None

@@ -61,3 +61,58 @@ def test_backward_reports_two_final_gradient_ranges():
     # same gradients as the un-hooked model (weight-gradient atomics: ~1e-6)
     live = (want.abs() > 0)
     assert float((got - want).norm() / want.norm()) <= 1e-4 and bool(live.any())
+
+
+def test_flat_parameters_adam_is_bit_identical_and_graphable():
+    """hcunet_b200.FlatParameters: one flat parameter whose gradient is the engine's flat buffer.  Three Adam steps on it ==
+    three steps of torch.optim.Adam(model.parameters()), bit for bit (the same elementwise update), eager and as a CUDA graph."""
+    import hcunet_b200 as H
+    from hcunet_b200.graph import GraphedTrainStep
+
+    kw = dict(O.README_3D, feature_sizes=[8, 16, 32])
+    x, mask, pwl = O.golden_inputs(kw, (2, 4, 60, 60, 8), 3)
+    x, mask, pwl = x.cuda(), mask.cuda(), pwl.cuda()
+    loss_fn = lambda lg, m, w: H.cross_entropy(lg, m, w, "pixel")  # noqa: E731
+
+    def make():
+        torch.manual_seed(0)
+        m = H.Unet_Constructor(**kw)
+        m.precision = "mixed"
+        return m.cuda().train()
+
+    # same gradients -> same update, bit for bit: model `a` (per-tensor Adam) is fed the gradients model `b` (flat Adam) computed
+    a, b = make(), make()
+    opt_a = torch.optim.Adam(a.parameters(), lr=1e-3, fused=True, capturable=True)
+    fp = H.FlatParameters(b)
+    assert all(fp.flat.data_ptr() <= p.data_ptr() < fp.flat.data_ptr() + 4 * fp.numel for p in b.parameters())
+    assert fp.numel == sum(p.numel() for p in b.parameters())
+    opt_b = torch.optim.Adam([fp.flat], lr=1e-3, fused=True, capturable=True)
+    for _ in range(4):
+        fp.zero_grad()
+        loss_fn(b(x), mask, pwl).backward()
+        fp.sync_grad()
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            pa.grad = pb.grad.clone()
+        opt_a.step()
+        opt_b.step()
+        torch.cuda.synchronize()
+        for (k, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+            assert torch.equal(pa, pb), k
+    # as ONE CUDA graph (3 warm-up steps inside + 1 replay = 4 steps): Adam moves every element by <= lr per step whatever the
+    # gradient's size, and the weight gradients' fp32 atomics are reproducible to ~1e-6 only, so two runs agree to a few lr
+    c = make()
+    fc = H.FlatParameters(c)
+    opt_c = torch.optim.Adam([fc.flat], lr=1e-3, fused=True, capturable=True)
+    g = GraphedTrainStep(c, opt_c, loss_fn, (x, mask, pwl), flat=fc)
+    loss = g(x, mask, pwl)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss)
+    moved = 0.0
+    for (k, pb), (_, pc) in zip(b.named_parameters(), c.named_parameters()):
+        assert float((pb - pc).abs().max()) <= 8e-3, k
+        moved = max(moved, float((pc - make().state_dict()[k].cuda()).abs().max())) if k == "out_conv.bias" else moved
+    assert moved > 0.0
+    # state_dict round trip keeps the views
+    sd = {k: v.clone() for k, v in a.state_dict().items()}
+    c.load_state_dict(sd)
+    assert all(p.data_ptr() >= fc.flat.data_ptr() and p.data_ptr() < fc.flat.data_ptr() + 4 * fc.numel for p in c.parameters())

@@ -122,3 +122,18 @@ def test_all_minus_one_tiles_are_skipped_and_errors_match():
     m.train()
     with pytest.raises(RuntimeError):
         S.predict_segmentation_mask(m, fx["image"].clone(), "cuda", cuda_mem=fx["cuda_mem"])
+
+
+def test_evaluate_is_as_unfinished_as_the_reference():
+    """`unet.py:198-233`: checks, eval(), padding, forward over the slices, result dropped -> None."""
+    import hcunet_b200 as H
+    from oracle import unet_oracle as O
+
+    m = H.Unet_Constructor(**dict(O.README_3D, feature_sizes=[4, 8])).cuda().train()
+    with pytest.raises(ValueError):
+        m.evaluate([1, 2, 3])
+    with pytest.raises(ImportError):
+        m.evaluate(torch.zeros((1, 3, 120, 120, 10)))
+    n0 = H._lib.launch_count()
+    assert m.evaluate(torch.randn((1, 4, 120, 104, 10))) is None
+    assert not m.training and H._lib.launch_count() > n0
