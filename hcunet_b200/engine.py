@@ -701,7 +701,7 @@ class UnetEngine:
         self._gflat = torch.empty(acc, dtype=torch.float32, device=dlogits.device)
         self.last_grad_flat = self._gflat
         side = None
-        if batched and self.overlap_wgrad and _lib._ProfState.profiler is None:
+        if batched and self.overlap_wgrad and (_lib._ProfState.profiler is None or os.environ.get("HCUNET_PROFILE_OVERLAP") == "1"):
             if self._side is None or self._side.device != dlogits.device:
                 self._side = torch.cuda.Stream(device=dlogits.device)
                 self._side2 = torch.cuda.Stream(device=dlogits.device)
