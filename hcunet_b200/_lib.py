@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HCUNET_LIB: an alternative build of the SAME library (A/B experiments: tools/build_variant.py); never a fallback
 LIB_PATH = os.environ.get("HCUNET_LIB") or os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 19
+ABI_VERSION = 20
 
 F32, BF16, F16, U8, U16, F64 = 0, 1, 2, 3, 4, 5
 BATCH_JOB_BYTES = 256
@@ -81,6 +81,8 @@ SIGNATURES = {
     "hcu_launch_count": [],
     "hcu_zero": [P, C.c_size_t, P],
     "hcu_h2d_tile": [P, I64, I64, I64, I64, I64, P, P],
+    "hcu_conv_tc_fwd_bnbwd": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, C.POINTER(HcuBnBwdFin), P],
+    "hcu_conv_tc_bnbwd_supported": [C.POINTER(HcuConvDesc)],
     "hcu_tile_gather": [C.POINTER(HcuTileGeom), P, I32, P, I32, I32, I32, P],
     "hcu_tile_flags": [C.POINTER(HcuTileGeom), P, I32, P, P],
     "hcu_sigmoid_paste": [P, C.POINTER(I32), C.POINTER(I32), C.POINTER(I32), P, I32, C.POINTER(I32), C.POINTER(I32), F, P, P],
@@ -193,7 +195,7 @@ def load():
     for name in SIGNATURES:
         raw = getattr(lib, name)
         setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_h2d_tile", "hcu_conv_tc_supported", "hcu_conv_wgrad_tc_supported", "hcu_conv_wgrad_tc5_supported", "hcu_conv_wgrad_ws_supported",
-                                         "hcu_conv_tc_packed_bytes", "hcu_conv_tc_describe", "hcu_conv_tc_pack_batch_build", "hcu_weight_scatter_batch_build") else _wrap(name, raw))
+                                         "hcu_conv_tc_packed_bytes", "hcu_conv_tc_describe", "hcu_conv_tc_bnbwd_supported", "hcu_conv_tc_pack_batch_build", "hcu_weight_scatter_batch_build") else _wrap(name, raw))
     _lib = out
     return out
 

@@ -174,6 +174,37 @@ __device__ __forceinline__ void fdivmod(uint32_t n, const FastDiv& f, uint32_t& 
   r = n - q * f.d;
 }
 
+// BatchNorm(+ReLU) backward, per-channel finalize from the binned fp64 sums (sum g, sum g*xhat): dgamma, dbeta, the conv-bias
+// gradient and the coefficients of dy = c1*g + c2*y + c3.  Shared by bn_bwd_stats' fused tail (elementwise.cu) and by the
+// data-gradient convolution that computes the statistics in its epilogue (conv_tc_kernel.cuh).
+__device__ __forceinline__ void bn_bwd_finalize_one(const double* sums, int c, int i, double count, const float* gamma,
+                                                    const float* mean, const float* invstd, int training, float grad_scale,
+                                                    float* dgamma, float* dbeta, float* dbias, float* coef) {
+  double sg = 0.0, sgx = 0.0;
+  for (int b = 0; b < HCU_STAT_BINS; ++b) {
+    sg += __ldcg(&sums[(size_t)b * 2 * c + i]);
+    sgx += __ldcg(&sums[(size_t)b * 2 * c + c + i]);
+  }
+  if (dgamma != nullptr) dgamma[i] = (float)(sgx * grad_scale);
+  if (dbeta != nullptr) dbeta[i] = (float)(sg * grad_scale);
+  const double s = (double)gamma[i] * (double)invstd[i];
+  double c1, c2, c3;
+  if (training) {
+    const double mg = sg / count, mgx = sgx / count;
+    c1 = s;
+    c2 = -s * (double)invstd[i] * mgx;
+    c3 = s * (double)invstd[i] * mgx * (double)mean[i] - s * mg;
+    // conv bias feeds a batch-stat BN: its gradient sum(dy) is analytically zero
+    if (dbias != nullptr) dbias[i] = (float)((c1 * sg + c2 * count * (double)mean[i] + c3 * count) * grad_scale);
+  } else {
+    c1 = s; c2 = 0.0; c3 = 0.0;
+    if (dbias != nullptr) dbias[i] = (float)(s * sg * grad_scale);
+  }
+  coef[i] = (float)c1;
+  coef[c + i] = (float)c2;
+  coef[2 * c + i] = (float)c3;
+}
+
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------
 // A kernel launched with launch_pdl() may START while its predecessor in the stream is still running: everything it does
 // before pdl_wait() (barrier init, TMEM allocation, index tables built from the kernel parameters -- no global memory) overlaps

@@ -966,7 +966,8 @@ extern "C" int hcu_conv_tc_pack_batch(const void* dev_jobs, int32_t n, int32_t b
 
 static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* packed, const float* bias,
                             const float* in_scale, const float* in_shift, const float* out_scale,
-                            const float* out_shift, void* out, double* stats, const HcuBnFin* fin, void* stream) {
+                            const float* out_shift, void* out, double* stats, const HcuBnFin* fin, void* stream,
+                            const tc::Params::BnBwdFuse* bnb = nullptr, bool query_only = false) {
   HCU_CHECK_ARG(d && in && packed && out, "conv_tc_fwd: null pointer");
   HCU_CHECK_ARG((in_scale == nullptr) == (in_shift == nullptr), "conv_tc_fwd: in_scale/in_shift must come together");
   HCU_CHECK_ARG((out_scale == nullptr) == (out_shift == nullptr), "conv_tc_fwd: out_scale/out_shift must come together");
@@ -1007,6 +1008,10 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
                d->out_c_off % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   HCU_CHECK_ARG(p.ops[0] * p.ops[1] * p.ops[2] == 1 || stats == nullptr, "conv_tc_fwd: no statistics with ophase");
 
+  if (p.ks && bnb != nullptr) {
+    if (!query_only) set_error("conv_tc_fwd_bnbwd: the K-streamed kernel has no fused statistics");
+    return HCU_ERR_UNSUPPORTED;
+  }
   if (p.ks) {
     HCU_CHECK_ARG(d->dtype_out == HCU_F16 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "conv_tc_fwd: K-streamed kernel needs a 16-byte aligned fp16 output");
     if (tc::ks_flat2d(d)) {  // (x, y) of the descriptor are the flat plane's (row, column); no march axis
@@ -1033,17 +1038,17 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
   // ---- kernel variant (see Var): a specialised instantiation when the launch matches one, else the generic kernel ----
   using KernelFn = tc::ConvTcFn;
   struct VariantSlot { KernelFn fn; int regs; bool ready; };
-  static VariantSlot variants[1 + 4 * 2 * 3 * 2] = {};
+  static VariantSlot variants[1 + 4 * 2 * 4 * 2] = {};
   static bool variants_init = false;
   if (!variants_init) {
     variants[0].fn = tc::conv_tc_kernel<tc::VarGeneric>;
     for (int epi = 1; epi <= 2; ++epi)
-      for (int fi = 0; fi < 3; ++fi)
+      for (int fi = 0; fi < 4; ++fi)
         for (int bulk = 0; bulk < 2; ++bulk) {
-          variants[1 + ((0 * 2 + (epi - 1)) * 3 + fi) * 2 + bulk].fn = tc::conv_tc_variant_mb1(epi, fi, bulk);
-          variants[1 + ((1 * 2 + (epi - 1)) * 3 + fi) * 2 + bulk].fn = tc::conv_tc_variant_mb2(epi, fi, bulk);
-          variants[1 + ((2 * 2 + (epi - 1)) * 3 + fi) * 2 + bulk].fn = tc::conv_tc_variant_mb3(epi, fi, bulk);
-          variants[1 + ((3 * 2 + (epi - 1)) * 3 + fi) * 2 + bulk].fn = tc::conv_tc_variant_mb4(epi, fi, bulk);
+          variants[1 + ((0 * 2 + (epi - 1)) * 4 + fi) * 2 + bulk].fn = tc::conv_tc_variant_mb1(epi, fi, bulk);
+          variants[1 + ((1 * 2 + (epi - 1)) * 4 + fi) * 2 + bulk].fn = tc::conv_tc_variant_mb2(epi, fi, bulk);
+          variants[1 + ((2 * 2 + (epi - 1)) * 4 + fi) * 2 + bulk].fn = tc::conv_tc_variant_mb3(epi, fi, bulk);
+          variants[1 + ((3 * 2 + (epi - 1)) * 4 + fi) * 2 + bulk].fn = tc::conv_tc_variant_mb4(epi, fi, bulk);
         }
     variants_init = true;
   }
@@ -1056,6 +1061,7 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
     if (bias != nullptr && stats != nullptr && out_scale == nullptr && !d->out_relu) fi = 0;         // training forward
     else if (bias == nullptr && stats == nullptr && out_scale == nullptr && !d->out_relu) fi = 1;    // data gradient
     else if (bias == nullptr && stats == nullptr && out_scale != nullptr && d->out_relu) fi = 2;     // inference (BN folded)
+    if (bnb != nullptr) fi = fi == 1 ? 3 : -1;   // data gradient + fused BatchNorm-backward statistics of the previous layer
     if (spec_on && p.debug == 0 && p.wide && p.Nc == 16 && p.nsplit == 1 && p.epi_fast && (nch == 8 || nch == 16) && fi >= 0 &&
         p.MB >= 1 && p.MB <= 4)
     {
@@ -1064,7 +1070,7 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
       if (bulk_on < 0) { const char* e = getenv("HCU_TC_BULK"); bulk_on = e ? atoi(e) : 1; }
       const bool bulk = bulk_on && p.P == 1 && in_scale == nullptr && p.ips[0] * p.ips[1] * p.ips[2] == 1 && p.in_zs == 8 &&
                         p.in_ys == p.IZ * p.in_zs && p.RUN * 16 <= 32768 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-      vi = 1 + (((p.MB - 1) * 2 + (nch == 8 ? 0 : 1)) * 3 + fi) * 2 + (bulk ? 1 : 0);
+      vi = 1 + (((p.MB - 1) * 2 + (nch == 8 ? 0 : 1)) * 4 + fi) * 2 + (bulk ? 1 : 0);
       // rotating accumulator window: KX slots of Nc columns per M-block
       int cols = p.MB * p.KX * p.Nc, t = 32;
       while (t < cols) t <<= 1;
@@ -1079,6 +1085,17 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
               p.MB, p.Nc, d->cout, p.wide, p.nsplit, p.epi_fast, p.P, bias != nullptr, stats != nullptr, out_scale != nullptr,
               d->out_relu, in_scale != nullptr);
   }
+  if (bnb != nullptr) {
+    // only the specialised variants carry the fused statistics; the output must be the dense [pixels][cout] tensor y has
+    if (vi == 0 || d->out_cpitch != d->cout || d->out_c_off != 0 || p.ks) {
+      if (!query_only) set_error("conv_tc_fwd_bnbwd: no specialised variant takes this descriptor");
+      return HCU_ERR_UNSUPPORTED;
+    }
+    p.bnb = *bnb;
+  } else {
+    memset(&p.bnb, 0, sizeof(p.bnb));
+  }
+  if (query_only) return 0;
   VariantSlot& var = variants[vi];
   if (!var.ready) {
     cudaError_t e = cudaFuncSetAttribute(var.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemLimit);
@@ -1132,4 +1149,23 @@ extern "C" int hcu_conv_tc_fwd_bn(const HcuConvDesc* d, const void* in, const vo
                                   const float* in_scale, const float* in_shift, const float* out_scale,
                                   const float* out_shift, void* out, double* stats, const HcuBnFin* fin, void* stream) {
   return conv_tc_fwd_impl(d, in, packed, bias, in_scale, in_shift, out_scale, out_shift, out, stats, fin, stream);
+}
+
+extern "C" int hcu_conv_tc_fwd_bnbwd(const HcuConvDesc* d, const void* in, const void* packed, void* out, const void* y,
+                                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                                     double* sums, const HcuBnBwdFin* fin, void* stream) {
+  HCU_CHECK_ARG(y && scale && shift && mean && invstd && sums && fin && fin->gamma && fin->coef && fin->count > 0,
+                "conv_tc_fwd_bnbwd: null pointer");
+  tc::Params::BnBwdFuse f;
+  f.y = (const __half*)y; f.scale = scale; f.shift = shift; f.mean = mean; f.invstd = invstd; f.sums = sums; f.fin = *fin;
+  return conv_tc_fwd_impl(d, in, packed, nullptr, nullptr, nullptr, nullptr, nullptr, out, nullptr, nullptr, stream, &f);
+}
+
+extern "C" int hcu_conv_tc_bnbwd_supported(const HcuConvDesc* d) {
+  if (d == nullptr) return 0;
+  tc::Params::BnBwdFuse f;
+  memset(&f, 0, sizeof(f));
+  alignas(16) static char dummy[16];
+  return conv_tc_fwd_impl(d, dummy, dummy, nullptr, nullptr, nullptr, nullptr, nullptr, dummy, nullptr, nullptr, nullptr, &f,
+                          true) == 0 ? 1 : 0;
 }

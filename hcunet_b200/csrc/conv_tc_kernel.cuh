@@ -36,6 +36,16 @@ struct Params {
   double* stats;
   int stats_pitch;
   HcuBnFin fin;  // optional fused BatchNorm finalize (fin.counter == nullptr: none)
+  // Fused BatchNorm(+ReLU)-backward statistics (data-gradient launches, flag bit 16): this launch's output is the gradient g
+  // with respect to a = relu(bn(y)) of the PREVIOUS layer; its epilogue also reads that layer's raw output y (same shape as
+  // the output) and accumulates sum(g') and sum(g' * y), g' = g where bn(y) > 0 else 0 -- what hcu_bn_bwd_stats would read g
+  // and y again for -- then the per-channel finalize runs in the CTA that takes the last ticket.
+  struct BnBwdFuse {
+    const __half* y;
+    const float* scale; const float* shift; const float* mean; const float* invstd;
+    double* sums;    // binned [HCU_STAT_BINS][2][c]
+    HcuBnBwdFin fin;
+  } bnb;
   int N, IX, IY, IZ, Cp, P;
   int OX, OY, OZ;
   int KX, KY, KZ, dx, dy, dz, px, py, pz;
@@ -219,6 +229,39 @@ __device__ __forceinline__ void stats_tail(const PT& p, float* sstat, int row, i
 }
 
 
+// Fused BatchNorm-backward statistics: per-warp partial sums (same slot layout as the forward statistics) -> the binned fp64
+// accumulators (sum g', invstd * (sum g'y - mean * sum g')), then hcu_bn_bwd_finalize's arithmetic in the last CTA.
+template <typename PT>
+__device__ __forceinline__ void bnb_tail(const PT& p, float* sstat, int row, int Nc, int C, int nthr, bool eight) {
+  named_bar_sync(1, nthr);
+  for (int c = row; c < C; c += nthr) {
+    float q1 = ((sstat[c] + sstat[2 * Nc + c]) + sstat[4 * Nc + c]) + sstat[6 * Nc + c];
+    float q2 = ((sstat[Nc + c] + sstat[3 * Nc + c]) + sstat[5 * Nc + c]) + sstat[7 * Nc + c];
+    if (eight) {
+      q1 += ((sstat[8 * Nc + c] + sstat[10 * Nc + c]) + sstat[12 * Nc + c]) + sstat[14 * Nc + c];
+      q2 += ((sstat[9 * Nc + c] + sstat[11 * Nc + c]) + sstat[13 * Nc + c]) + sstat[15 * Nc + c];
+    }
+    double* sb = p.bnb.sums + (size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * C;
+    const double sg = (double)q1, sgy = (double)q2;
+    atomicAdd(&sb[c], sg);
+    atomicAdd(&sb[C + c], (double)p.bnb.invstd[c] * (sgy - (double)p.bnb.mean[c] * sg));
+  }
+  if (p.bnb.fin.counter != nullptr) {
+    __threadfence();
+    named_bar_sync(1, nthr);
+    if (row == 0) sstat[0] = (atomicAdd(p.bnb.fin.counter, 1u) == gridDim.x - 1) ? 1.f : 0.f;
+    named_bar_sync(1, nthr);
+    if (sstat[0] != 0.f) {
+      __threadfence();
+      float gs = p.bnb.fin.grad_scale;
+      if (p.bnb.fin.dscale != nullptr) gs *= p.bnb.fin.dscale[0];
+      for (int i = row; i < C; i += nthr)
+        bn_bwd_finalize_one(p.bnb.sums, C, i, p.bnb.fin.count, p.bnb.fin.gamma, p.bnb.mean, p.bnb.invstd, p.bnb.fin.training, gs,
+                            p.bnb.fin.dgamma, p.bnb.fin.dbeta, p.bnb.fin.dbias, p.bnb.fin.coef);
+    }
+  }
+}
+
 // Compile-time variants of conv_tc_kernel.  The source-level profile of the generic kernel on the 8-channel levels
 // (profiles/r02_conv_tc_sass_regions.txt) showed 317 warp instructions per epilogue warp per plane of which ~85 did arithmetic:
 // the rest re-tested launch-invariant flags (bias / statistics / affine / ReLU / debug bits / M-block count / wide mode)
@@ -239,7 +282,7 @@ struct Var {
   static constexpr int kMB = MB_, kEpi = EPI_, kFlags = FLAGS_;
 };
 using VarGeneric = Var<false, 0, 0, 0>;
-constexpr int kFlagsTrain = 1 | 2, kFlagsPlain = 0, kFlagsEval = 4 | 8;
+constexpr int kFlagsTrain = 1 | 2, kFlagsPlain = 0, kFlagsEval = 4 | 8, kFlagsPlainBnb = 16;
 
 template <class V>
 __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
@@ -330,6 +373,10 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     sbias[i] = (in && p.bias != nullptr) ? p.bias[ch % p.cpp] : 0.f;
     sbias[Nc + i] = (in && p.out_scale != nullptr) ? p.out_scale[ch] : 1.f;
     sbias[2 * Nc + i] = (in && p.out_shift != nullptr) ? p.out_shift[ch] : 0.f;
+    if (S && (V::kFlags & 16) != 0) {   // fused BN-backward statistics: that layer's scale / shift (for the ReLU mask)
+      sbias[Nc + i] = in ? p.bnb.scale[ch] : 1.f;
+      sbias[2 * Nc + i] = in ? p.bnb.shift[ch] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -718,6 +765,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     const bool affine = S ? (V::kFlags & 4) != 0 : p.out_scale != nullptr;
     const bool has_bias = S ? (V::kFlags & 1) != 0 : p.bias != nullptr;
     const int out_relu = S ? ((V::kFlags & 8) != 0 ? 1 : 0) : p.out_relu, cout = p.cout;
+    constexpr bool BNB = S && (V::kFlags & 16) != 0;   // fused BatchNorm-backward statistics (data-gradient launches)
     const int nch = S ? (V::kEpi == 1 ? 8 : 16) : min(Nc, cout - ns * Nc);  // real output channels of this CTA's column chunk
     // per M-block: element offset of this thread's pixel inside an output x-plane (-1: wrap-around / out of range)
     // (slot k of this warp = M-block half + k * MBSTEP)
@@ -762,6 +810,12 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
       float bs[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) bs[j] = sbias[j];
+      // BNB: t1 = sum g', t2 = sum g' * y; scale / shift of the layer whose backward statistics these are
+      float bsc[8], bsh[8];
+      if (BNB) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { bsc[j] = p.bnb.scale[j]; bsh[j] = p.bnb.shift[j]; }
+      }
       for (int it = 0; it < nit; ++it) {
         const int i = S ? it - (KXr - 1) : it;
         const int buf = S ? rslot : (it & (NB - 1));
@@ -769,6 +823,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         if (S) {
           tf_phase ^= 1u << rslot;
           rslot = rslot + 1 == KXr ? 0 : rslot + 1;
+        }
+        // BNB: this plane's y values, requested before the wait for the accumulators (their latency hides behind it)
+        uint4 yv[4];
+        if (BNB && i >= 0) {
+          const __half* yplane = p.bnb.y + obase0 + (long long)(x0 + i) * p.out_sx;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k * MBSTEP < MB && poff[k] >= 0) yv[k] = ldg_nc16(yplane + poff[k]);
         }
         PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, par));
         tc_fence_after();
@@ -838,10 +900,23 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
             if (!(debug & 16)) *reinterpret_cast<uint4*>(oplane + poff[mb]) = *reinterpret_cast<uint4*>(h);
+            if (BNB) {  // the STORED (fp16) gradient is what the statistics pass would have read
+              const __half2* yh = reinterpret_cast<const __half2*>(&yv[mb]);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 g = __half22float2(h[j]);
+                const float2 yy = __half22float2(yh[j]);
+                if (fmaf(yy.x, bsc[2 * j], bsh[2 * j]) <= 0.f) g.x = 0.f;
+                if (fmaf(yy.y, bsc[2 * j + 1], bsh[2 * j + 1]) <= 0.f) g.y = 0.f;
+                t1[2 * j] += g.x; t1[2 * j + 1] += g.y;
+                t2[2 * j] = fmaf(g.x, yy.x, t2[2 * j]);
+                t2[2 * j + 1] = fmaf(g.y, yy.y, t2[2 * j + 1]);
+              }
+            }
           }
         }
       }
-      if (do_stats) {
+      if (do_stats || BNB) {
         const float r1 = reduce8(t1, lane);
         const float r2 = reduce8(t2, lane);
         if ((lane & 3) == 0) {
@@ -862,6 +937,16 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         if (S) {
           tf_phase ^= 1u << rslot;
           rslot = rslot + 1 == KXr ? 0 : rslot + 1;
+        }
+        uint4 yv[4][2];
+        if (BNB && i >= 0) {
+          const __half* yplane = p.bnb.y + obase0 + (long long)(x0 + i) * p.out_sx;
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k * MBSTEP < MB && poff[k] >= 0) {
+              yv[k][0] = ldg_nc16(yplane + poff[k]);
+              yv[k][1] = ldg_nc16(yplane + poff[k] + 8);
+            }
         }
         PROF_WAIT(pw0, mbar_wait(bar_tfull + 8 * buf, par));
         tc_fence_after();
@@ -925,6 +1010,19 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
               __half* o = oplane + poff[k] + cc;
               *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(&h[0]);
               if (cc + 8 < nch) *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<uint4*>(&h[4]);
+              if (BNB) {  // 16 channels, one chunk (Nc == 16): sums in t1 / t2, scale / shift from shared memory
+                const __half2* yh = reinterpret_cast<const __half2*>(&yv[k][0]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float2 g = __half22float2(h[j]);
+                  const float2 yy = __half22float2(yh[j]);
+                  if (fmaf(yy.x, sbias[Nc + 2 * j], sbias[2 * Nc + 2 * j]) <= 0.f) g.x = 0.f;
+                  if (fmaf(yy.y, sbias[Nc + 2 * j + 1], sbias[2 * Nc + 2 * j + 1]) <= 0.f) g.y = 0.f;
+                  t1[2 * j] += g.x; t1[2 * j + 1] += g.y;
+                  t2[2 * j] = fmaf(g.x, yy.x, t2[2 * j]);
+                  t2[2 * j + 1] = fmaf(g.y, yy.y, t2[2 * j + 1]);
+                }
+              }
             }
           }
         }
@@ -933,7 +1031,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
       }
-      if (local_stats) {
+      if (local_stats || BNB) {
         const float r1 = reduce16(t1, lane);
         const float r2 = reduce16(t2, lane);
         if ((lane & 1) == 0) {
@@ -1021,6 +1119,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     }
     PROF_REPORT("epilogue", "wait_tfull", "-", nout);
     if (do_stats) stats_tail(p, sstat, BULK ? (int)threadIdx.x : row, ns, Nc, BULK ? 256 : 128, BULK);
+    if (BNB) bnb_tail(p, sstat, BULK ? (int)threadIdx.x : row, Nc, nch, BULK ? 256 : 128, BULK);
   }
 
 
@@ -1036,7 +1135,8 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
 
 
 using ConvTcFn = void (*)(const Params);
-// specialised instantiations, one translation unit per M-block count: epi 1 | 2, flag set 0 train | 1 plain | 2 eval, bulk 0 | 1
+// specialised instantiations, one translation unit per M-block count: epi 1 | 2, flag set 0 train | 1 plain | 2 eval |
+// 3 plain + fused BatchNorm-backward statistics, bulk 0 | 1
 ConvTcFn conv_tc_variant_mb1(int epi, int fi, int bulk);
 ConvTcFn conv_tc_variant_mb2(int epi, int fi, int bulk);
 ConvTcFn conv_tc_variant_mb3(int epi, int fi, int bulk);
@@ -1045,6 +1145,7 @@ ConvTcFn conv_tc_variant_mb4(int epi, int fi, int bulk);
 #define HCU_TC_VARIANT_ROW(mb, epi, bulk)                                            \
   if (fi == 0) return conv_tc_kernel<Var<true, mb, epi, kFlagsTrain, bulk>>;         \
   if (fi == 1) return conv_tc_kernel<Var<true, mb, epi, kFlagsPlain, bulk>>;         \
+  if (fi == 3) return conv_tc_kernel<Var<true, mb, epi, kFlagsPlainBnb, bulk>>;      \
   return conv_tc_kernel<Var<true, mb, epi, kFlagsEval, bulk>>;
 #define HCU_TC_DEFINE_VARIANTS(mb)                                                   \
   ConvTcFn conv_tc_variant_mb##mb(int epi, int fi, int bulk) {                       \

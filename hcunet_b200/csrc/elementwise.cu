@@ -483,9 +483,6 @@ __device__ __forceinline__ void load_g8(const __half* __restrict__ da, const uin
   }
 }
 
-__device__ __forceinline__ void bn_bwd_finalize_one(const double* sums, int c, int i, double count, const float* gamma,
-                                                    const float* mean, const float* invstd, int training, float grad_scale,
-                                                    float* dgamma, float* dbeta, float* dbias, float* coef);
 
 __global__ void __launch_bounds__(256, 3) bn_bwd_stats_h8_kernel(const __half* __restrict__ da, const __half* __restrict__ y,
                                                              long long npix, int c, const float* __restrict__ scale,
@@ -666,33 +663,6 @@ __global__ void bn_bwd_stats_kernel(const TD* __restrict__ da, const TY* __restr
     atomicAdd(&sums[(size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * c + i], (double)sh[i]);
 }
 
-__device__ __forceinline__ void bn_bwd_finalize_one(const double* sums, int c, int i, double count, const float* gamma,
-                                                    const float* mean, const float* invstd, int training, float grad_scale,
-                                                    float* dgamma, float* dbeta, float* dbias, float* coef) {
-  double sg = 0.0, sgx = 0.0;
-  for (int b = 0; b < HCU_STAT_BINS; ++b) {
-    sg += __ldcg(&sums[(size_t)b * 2 * c + i]);
-    sgx += __ldcg(&sums[(size_t)b * 2 * c + c + i]);
-  }
-  if (dgamma != nullptr) dgamma[i] = (float)(sgx * grad_scale);
-  if (dbeta != nullptr) dbeta[i] = (float)(sg * grad_scale);
-  const double s = (double)gamma[i] * (double)invstd[i];
-  double c1, c2, c3;
-  if (training) {
-    const double mg = sg / count, mgx = sgx / count;
-    c1 = s;
-    c2 = -s * (double)invstd[i] * mgx;
-    c3 = s * (double)invstd[i] * mgx * (double)mean[i] - s * mg;
-    // conv bias feeds a batch-stat BN: its gradient sum(dy) is analytically zero
-    if (dbias != nullptr) dbias[i] = (float)((c1 * sg + c2 * count * (double)mean[i] + c3 * count) * grad_scale);
-  } else {
-    c1 = s; c2 = 0.0; c3 = 0.0;
-    if (dbias != nullptr) dbias[i] = (float)(s * sg * grad_scale);
-  }
-  coef[i] = (float)c1;
-  coef[c + i] = (float)c2;
-  coef[2 * c + i] = (float)c3;
-}
 
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, int c, double count,
                                        const float* __restrict__ gamma, const float* __restrict__ mean,

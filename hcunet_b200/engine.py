@@ -334,6 +334,8 @@ class UnetEngine:
         self.use_tc5 = os.environ.get("HCUNET_WGRAD5", "1") != "0"      # tcgen05 weight gradient on the channel-rich levels
         self.use_batch = os.environ.get("HCUNET_BATCH", "1") != "0"      # batched packs / scatters (_StepCache)
         self.overlap_wgrad = os.environ.get("HCUNET_OVERLAP", "1") != "0"  # weight gradients on a side stream
+        # BatchNorm-backward statistics of a block's conv1 computed in the epilogue of conv2's data gradient (its producer)
+        self.fuse_bnbwd = os.environ.get("HCUNET_FUSE_BNBWD", "1") != "0"
         self._caches: Dict[tuple, _StepCache] = {}
         self._cache: Optional[_StepCache] = None   # cache of the call in progress
         self._side = None
@@ -765,7 +767,24 @@ class UnetEngine:
             if offs and nlev > 2 and all(n_.startswith("out_conv") or n_.startswith("down_steps.") for n_ in late_names):
                 split_off = min(offs)
                 split_name = f"down_steps.{nlev - 3}.conv2"      # the first late layer the backward reaches
-        for item in reversed(saved):
+        items = list(reversed(saved))
+        prefused: Dict[str, tuple] = {}      # conv name -> BN-backward context whose statistics the producer already computed
+
+        def bn_ctx(g_, npix_):
+            """(sums, coef, fin, dgamma, dbeta, dbias) of one BatchNorm backward; slices of this backward's zeroed workspace."""
+            nonlocal zoff, kbn
+            sums_ = zero_ws[zoff:zoff + 2 * g_.cout_t * SB]
+            zoff += 2 * g_.cout_t * SB
+            dgamma_, dbeta_ = self._gview(g_.bn + ".weight"), self._gview(g_.bn + ".bias")
+            dbias_ = self._gview(g_.name + ".bias")
+            coef_ = torch.empty((3, g_.cout_t), dtype=torch.float32, device=dev)
+            fin_ = _lib.HcuBnBwdFin(float(npix_), params[g_.bn + ".weight"].data_ptr(), 1 if training else 0, 1.0,
+                                    inv.data_ptr() if inv is not None else None, dgamma_.data_ptr(), dbeta_.data_ptr(),
+                                    dbias_.data_ptr(), coef_.data_ptr(), zero_ws.data_ptr() + 8 * (nstat + kbn))
+            kbn += 1
+            return sums_, coef_, fin_, dgamma_, dbeta_, dbias_
+
+        for idx, item in enumerate(items):
             kind = item[0]
             if split_name is not None and kind == "conv" and item[1].name == split_name:
                 # ---- early bucket complete: up path + the two deepest levels ----
@@ -821,20 +840,16 @@ class UnetEngine:
                                                    g.out_sz[1], g.out_sz[2], g.cout_t, g.pool[0], g.pool[1],
                                                    g.pool[2], st), "maxpool_bwd")
                     dcur, dcur_dt = dfull, adt
-                sums = zero_ws[zoff:zoff + 2 * g.cout_t * SB]
-                zoff += 2 * g.cout_t * SB
-                _lib.note(g.name, 2 * npix * g.cout_t * esz, 0)
-                dgamma, dbeta = self._gview(g.bn + ".weight"), self._gview(g.bn + ".bias")
-                dbias = self._gview(g.name + ".bias")
-                coef = torch.empty((3, g.cout_t), dtype=torch.float32, device=dev)
-                fin = _lib.HcuBnBwdFin(float(npix), params[g.bn + ".weight"].data_ptr(), 1 if training else 0, 1.0,
-                                       inv.data_ptr() if inv is not None else None, dgamma.data_ptr(), dbeta.data_ptr(),
-                                       dbias.data_ptr(), coef.data_ptr(), zero_ws.data_ptr() + 8 * (nstat + kbn))
-                kbn += 1
-                _lib.check(lib.hcu_bn_bwd_stats_fin(_ptr(dcur), dcur_dt, _ptr(y), adt, npix, g.cout_t, _ptr(vec[2]),
-                                                    _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(pool_arg),
-                                                    C.byref(pool_geom) if pool_geom is not None else None, _ptr(sums),
-                                                    C.byref(fin), st), "bn_bwd_stats_fin")
+                ctx = prefused.pop(g.name, None)
+                if ctx is None:
+                    sums, coef, fin, dgamma, dbeta, dbias = bn_ctx(g, npix)
+                    _lib.note(g.name, 2 * npix * g.cout_t * esz, 0)
+                    _lib.check(lib.hcu_bn_bwd_stats_fin(_ptr(dcur), dcur_dt, _ptr(y), adt, npix, g.cout_t, _ptr(vec[2]),
+                                                        _ptr(vec[3]), _ptr(vec[0]), _ptr(vec[1]), 1, _ptr(pool_arg),
+                                                        C.byref(pool_geom) if pool_geom is not None else None, _ptr(sums),
+                                                        C.byref(fin), st), "bn_bwd_stats_fin")
+                else:   # the data gradient that produced `dcur` computed these statistics in its epilogue
+                    sums, coef, fin, dgamma, dbeta, dbias = ctx
                 dy = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
                 _lib.note(g.name, 3 * npix * g.cout_t * esz, 0)
                 _lib.check(lib.hcu_bn_bwd_apply(_ptr(dcur), dcur_dt, _ptr(y), adt, _ptr(dy), adt, npix, g.cout_t,
@@ -847,8 +862,17 @@ class UnetEngine:
                 if g.first and not need_dx:
                     dcur = None
                 else:
+                    # the next item is the conv whose output this conv reads (conv1 of the same block, no pool in between):
+                    # its BatchNorm-backward statistics are sums over exactly the tensor this data gradient writes
+                    fuse = None
+                    nxt = items[idx + 1] if idx + 1 < len(items) else None
+                    if (self.fuse_bnbwd and self.tap is None and act_dtype == torch.float16 and nxt is not None and nxt[0] == "conv"
+                            and nxt[5] is a_in and nxt[7] is None and a_xf is not None and not g.first):
+                        g1, y1, vec1 = nxt[1], nxt[5], nxt[6]
+                        npix1 = B * g1.out_sz[0] * g1.out_sz[1] * g1.out_sz[2]
+                        fuse = (g1, y1, vec1, npix1)
                     dcur = self._dgrad_conv(g, dy, adt, B, params[g.name + ".weight"], act_dtype,
-                                            out_cp=a_cp if g.first else None)
+                                            out_cp=a_cp if g.first else None, fuse=fuse, bn_ctx=bn_ctx, prefused=prefused)
                     dcur_dt = adt
                     self._tap(g.name + ".dgrad", dcur, g.cin_t, g.in_sz)
                 if g.first and need_dx:
@@ -1046,7 +1070,8 @@ class UnetEngine:
             cache.scatter_jobs[wname] = (HcuWeightMap.from_buffer_copy(wm), nsplit, total)
         return gw
 
-    def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype, out_cp=None, dy_cp=None):
+    def _dgrad_conv(self, g: ConvGeom, dy, dy_dt, B, wref, act_dtype, out_cp=None, dy_cp=None, fuse=None, bn_ctx=None,
+                    prefused=None):
         adt = _DT[act_dtype]
         T = g.taps[0] * g.taps[1] * g.taps[2]
         eg, ecin, ecout, bd = self._eff(g, dy_dt == _lib.F16 and act_dtype == torch.float16)
@@ -1057,5 +1082,22 @@ class UnetEngine:
         pad = tuple((g.taps[i] - 1) * g.dil[i] for i in range(3))
         d = conv_desc(dy_dt, adt, B, g.out_sz, dy_cp or g.cout_t, 0, ecout, ecout, g.in_sz, g.in_sz, cpo, 0, ecin,
                       eg, g.taps, g.dil, pad=pad)
-        self._conv(d, dy, w, None, dprev, layer=g.name + ".dgrad")
+        lib, cache, key = self.lib, self._cache, g.name + ".dgrad"
+        if (fuse is not None and self.use_tc and cache is not None and cache.ready and key in cache.pack_off
+                and lib.hcu_conv_tc_bnbwd_supported(C.byref(d))):
+            # BatchNorm-backward statistics of the layer `dprev` is the gradient of, computed in this launch's epilogue
+            g1, y1, vec1, npix1 = fuse
+            ctx = bn_ctx(g1, npix1)
+            sums, coef, fin = ctx[0], ctx[1], ctx[2]
+            pk = C.c_void_p(cache.packed.data_ptr() + cache.pack_off[key])
+            esz = 2
+            nin = B * g.out_sz[0] * g.out_sz[1] * g.out_sz[2] * g.cout_t
+            _lib.note(key, (nin + 2 * npix1 * g1.cout_t) * esz, 2 * npix1 * g1.cout_t * T * g.cout_t)
+            _lib.check(lib.hcu_conv_tc_fwd_bnbwd(C.byref(d), _ptr(dy), pk, _ptr(dprev), _ptr(y1), _ptr(vec1[2]), _ptr(vec1[3]),
+                                                 _ptr(vec1[0]), _ptr(vec1[1]), _ptr(sums), C.byref(fin), self._stream()),
+                       "conv_tc_fwd_bnbwd")
+            prefused[g1.name] = ctx
+            self._keep.append(coef)
+            return dprev
+        self._conv(d, dy, w, None, dprev, layer=key)
         return dprev

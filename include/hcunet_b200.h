@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 19
+#define HCU_ABI_VERSION 20
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -229,6 +229,17 @@ int hcu_conv_tc_fwd_bn(const HcuConvDesc* d, const void* in, const void* packed,
                     const float* in_scale, const float* in_shift, const float* out_scale,
                     const float* out_shift, void* out, double* stats, const HcuBnFin* fin,
                        void* stream);
+/* Data gradient of a convolution (hcu_conv_tc_fwd with pad = (k-1)*dil and the flipped packed weights, no bias / statistics /
+ * affine) whose EPILOGUE also computes the BatchNorm(+ReLU)-backward statistics of the layer its output is the gradient of:
+ * out = g [pixels][c] (fp16, dense); y = that layer's raw convolution output, same shape; scale / shift / mean / invstd its
+ * BatchNorm vectors; sums = binned fp64 [HCU_STAT_BINS][2][c], zeroed by the caller; fin as for hcu_bn_bwd_stats_fin (the
+ * finalize runs in the last CTA).  Equivalent to hcu_conv_tc_fwd followed by hcu_bn_bwd_stats_fin(g, y, relu = 1) without
+ * the second pass over g and y.  Only the specialised 8 / 16-channel variants carry it: hcu_conv_tc_bnbwd_supported(). */
+int hcu_conv_tc_fwd_bnbwd(const HcuConvDesc* d, const void* in, const void* packed, void* out, const void* y,
+                          const float* scale, const float* shift, const float* mean, const float* invstd, double* sums,
+                          const HcuBnBwdFin* fin, void* stream);
+int hcu_conv_tc_bnbwd_supported(const HcuConvDesc* d);
+
 
 /* Weight gradient of the same gather-convolution:
  *   R[g][t][ca][cb] = sum_{n,o} A(a[n, o*istep - pad + t*dil, a_c_off + g*a_c_gstep + ca]) * b[n, o, b_c_off + g*cb_n + cb]

@@ -454,3 +454,49 @@ def test_colsum_matches_fp64_sum(c, cpitch, c_off, npix):
     _lib.check(lib.hcu_colsum(P(x), _lib.F16, npix, cpitch, c_off, c, 2.0, P(dscale), P(scratch), P(out), stream()), "colsum")
     want = x[:, c_off:c_off + c].double().sum(0) * 0.5
     assert float((out.double() - want).abs().max()) <= 1e-5 * float(x.double().abs().sum(0).max())
+
+
+@pytest.mark.parametrize("case", [(2, 8, 8, (20, 22, 9), (3, 3, 1)), (1, 8, 8, (40, 36, 15), (3, 3, 2)),
+                                  (2, 16, 16, (20, 22, 9), (3, 3, 1)), (2, 16, 8, (20, 22, 9), (3, 3, 2))])
+def test_data_gradient_with_fused_bn_backward_statistics(case):
+    """`hcu_conv_tc_fwd_bnbwd` == `hcu_conv_tc_fwd` (data gradient) followed by `hcu_bn_bwd_stats_fin`: the same g bit for
+    bit, the same sums / coefficients / dgamma / dbeta to fp32 grouping."""
+    from hcunet_b200 import _lib
+    from hcunet_b200.engine import conv_desc
+
+    lib = _lib.load()
+    B, cdy, cout, osz, k = case
+    isz = tuple(osz[i] + k[i] - 1 for i in range(3))
+    g0 = torch.Generator(device="cuda").manual_seed(sum(osz) + cdy)
+    dy = torch.randn((B,) + osz + (cdy,), device="cuda", generator=g0).half()
+    d = conv_desc(_lib.F16, _lib.F16, B, osz, cdy, 0, cdy, cdy, isz, isz, cout, 0, cout, 1, k, pad=tuple(t - 1 for t in k))
+    assert lib.hcu_conv_tc_bnbwd_supported(C.byref(d)) == 1
+    T = k[0] * k[1] * k[2]
+    w = torch.randn(T * cdy * cout, device="cuda", generator=g0) / (T * cdy) ** 0.5
+    packed = torch.empty(lib.hcu_conv_tc_packed_bytes(C.byref(d)), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.hcu_conv_tc_pack(C.byref(d), P(w), P(packed), stream()))
+    npix = B * isz[0] * isz[1] * isz[2]
+    y = torch.randn((B,) + isz + (cout,), device="cuda", generator=g0).half()
+    scale, shift = torch.rand(cout, device="cuda", generator=g0) + 0.5, torch.randn(cout, device="cuda", generator=g0) * 0.3
+    mean, invstd = torch.randn(cout, device="cuda", generator=g0) * 0.1, torch.rand(cout, device="cuda", generator=g0) + 0.5
+    gamma = torch.rand(cout, device="cuda", generator=g0) + 0.5
+    outs = []
+    for fused in (False, True):
+        g = torch.full((B,) + isz + (cout,), float("nan"), dtype=torch.float16, device="cuda")
+        ws = torch.zeros(2 * cout * _lib.STAT_BINS + 1, dtype=torch.float64, device="cuda")
+        coef, dgamma, dbeta = torch.zeros((3, cout), device="cuda"), torch.zeros(cout, device="cuda"), torch.zeros(cout, device="cuda")
+        fin = _lib.HcuBnBwdFin(float(npix), gamma.data_ptr(), 1, 1.0, None, dgamma.data_ptr(), dbeta.data_ptr(), None,
+                               coef.data_ptr(), ws.data_ptr() + 8 * 2 * cout * _lib.STAT_BINS)
+        if fused:
+            _lib.check(lib.hcu_conv_tc_fwd_bnbwd(C.byref(d), P(dy), P(packed), P(g), P(y), P(scale), P(shift), P(mean), P(invstd),
+                                                 P(ws), C.byref(fin), stream()), "conv_tc_fwd_bnbwd")
+        else:
+            _lib.check(lib.hcu_conv_tc_fwd(C.byref(d), P(dy), P(packed), None, None, None, None, None, P(g), None, stream()))
+            _lib.check(lib.hcu_bn_bwd_stats_fin(P(g), _lib.F16, P(y), _lib.F16, npix, cout, P(scale), P(shift), P(mean), P(invstd),
+                                                1, None, None, P(ws), C.byref(fin), stream()))
+        torch.cuda.synchronize()
+        outs.append((g, coef, dgamma, dbeta))
+    a, b = outs
+    assert not torch.isnan(b[0]).any() and torch.equal(a[0], b[0])
+    for i in (1, 2, 3):
+        assert float((a[i] - b[i]).abs().max()) <= 2e-6 * float(a[i].abs().max()), i

@@ -240,6 +240,9 @@ def test_batched_weight_pack_equals_per_layer_pack(name):
     m = H.Unet_Constructor(**kwargs)
     m.precision = "mixed"
     m = m.cuda().train()
+    # the steady-state step also moves the BatchNorm-backward statistics of every conv1 into the producing data gradient's epilogue
+    # (a different fp32 grouping of the same sums: tests/test_gpu_overlap.py); this test isolates the weight packs
+    m._engine.fuse_bnbwd = False
     g = torch.Generator().manual_seed(7)
     x = torch.randn(xs, generator=g).cuda()
     mask = (torch.rand(ms, generator=g) > 0.5).float().cuda()
