@@ -387,9 +387,12 @@ def main_ours(args):
     model.precision = args.precision
     model = model.to(dev).train()
     sync = GradSync(model, world)          # broadcast params from rank 0; fp32 mean all-reduce of the gradients
-    overlap_ar = world > 1 and os.environ.get("HCUNET_AR_OVERLAP", "1") != "0"
+    # HCUNET_AR_OVERLAP=1: the exchange is launched from inside backward (two buckets, communication stream) and captured with
+    # the step's graph (GradSync.attach).  Measured on 8 B200 (profiles/r02_bench_n8_*.json): 3.01 ms per step against 2.97 ms
+    # for the serial form (graph -> one all-reduce -> optimiser graph): the 2.9 MB collective costs less than the SMs its
+    # kernels take from the backward, so the serial form is the default.
+    overlap_ar = world > 1 and os.environ.get("HCUNET_AR_OVERLAP", "0") != "0"
     if overlap_ar:
-        # the exchange is launched from inside backward (two buckets, communication stream) and captured with the step
         sync.attach()
     _stage("parameters broadcast")
     use_graph = os.environ.get("HCUNET_BENCH_GRAPH", "1") != "0"

@@ -582,6 +582,107 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_stats_h8_kernel(const __half* _
   }
 }
 
+// Statistics pass of a POOLED layer at POOLED resolution.  The gradient of a full-resolution voxel is the pooled gradient if the
+// voxel was its window's argmax, else 0 -- so both sums only need, per pooled voxel and channel, the pooled gradient and the
+// ONE y value at the argmax position: a quarter of the threads of the full-resolution pass (kernel (2,2,1)), no per-voxel
+// window search (bn_bwd_stats_h8_kernel with `argmax` spent ~60 instructions per full-resolution 8-channel group on index
+// arithmetic: d0.conv2 of the bench step 86 us alone, 153 us beside a weight gradient).  The y values are gathered with 2-byte
+// loads (each channel has its own argmax); a window's voxels share 32-byte sectors, so the DRAM traffic stays one pass over y.
+__global__ void __launch_bounds__(256, 3) bn_bwd_stats_pool_h8_kernel(const __half* __restrict__ dpool, const uint8_t* __restrict__ argmax,
+                                                                      const __half* __restrict__ y, long long npool, int c,
+                                                                      const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                      const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                      int relu, PoolGeom pg, FastDiv doz, FastDiv doy, FastDiv dox,
+                                                                      double* __restrict__ sums, HcuBnBwdFin fin) {
+  extern __shared__ float sh[];                       // [8 warps][2][c] partial sums, then the window offset table
+  int* woff = reinterpret_cast<int*>(sh + 16 * c);    // [px * py * pz]: element offset of window position w from the window origin
+  for (int i = threadIdx.x; i < 16 * c; i += blockDim.x) sh[i] = 0.f;
+  const int nwin = pg.px * pg.py * pg.pz;
+  for (int w = threadIdx.x; w < nwin; w += blockDim.x) {
+    const int wz = w % pg.pz, wq = w / pg.pz;
+    const int wy = wq % pg.py, wx = wq / pg.py;
+    woff[w] = ((wx * pg.iy + wy) * pg.iz + wz) * c;
+  }
+  __syncthreads();
+  pdl_wait();
+  pdl_launch_dependents();
+  const int c8 = c >> 3, lc8 = __ffs(c8) - 1;
+  const uint32_t total = (uint32_t)(npool * c8), stride = gridDim.x * blockDim.x;  // stride % c8 == 0
+  uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int cg = (int)(e & (uint32_t)(c8 - 1));
+  float sc[8], sf[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[cg * 8 + j]; sf[j] = shift[cg * 8 + j];
+    s1[j] = 0.f; s2[j] = 0.f;
+  }
+  for (; e < total; e += stride) {
+    const uint32_t q = e >> lc8;                      // pooled voxel
+    uint32_t r, qz, qy, qx, b;
+    fdivmod(q, doz, r, qz);
+    fdivmod(r, doy, r, qy);
+    fdivmod(r, dox, b, qx);
+    const size_t pe = (size_t)q * c + cg * 8;
+    const uint4 graw = *reinterpret_cast<const uint4*>(dpool + pe);
+    const uint2 a = *reinterpret_cast<const uint2*>(argmax + pe);
+    const __half* yb = y + ((((size_t)b * pg.ix + qx * pg.px) * pg.iy + qy * pg.py) * pg.iz + qz * pg.pz) * c + cg * 8;
+    const __half* gh = reinterpret_cast<const __half*>(&graw);
+    float yv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t aj = ((j < 4 ? a.x : a.y) >> (8 * (j & 3))) & 0xffu;
+      yv[j] = __half2float(yb[woff[aj] + j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float g = __half2float(gh[j]);
+      if (relu && fmaf(yv[j], sc[j], sf[j]) <= 0.f) g = 0.f;
+      s1[j] += g;
+      s2[j] = fmaf(g, yv[j], s2[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    for (int off = 16; off >= c8; off >>= 1) {
+      s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], off);
+      s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], off);
+    }
+  }
+  if ((threadIdx.x & 31) < c8 || c8 > 16) {
+    float* sw = sh + (threadIdx.x >> 5) * 2 * c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sw[cg * 8 + j] = s1[j];
+      sw[c + cg * 8 + j] = s2[j];
+    }
+  }
+  __syncthreads();
+  double* sb = sums + (size_t)(blockIdx.x % HCU_STAT_BINS) * 2 * c;
+  for (int i = threadIdx.x; i < c; i += blockDim.x) {
+    float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { q1 += sh[w * 2 * c + i]; q2 += sh[w * 2 * c + c + i]; }
+    const double sg = (double)q1, sgy = (double)q2;
+    atomicAdd(&sb[i], sg);
+    atomicAdd(&sb[c + i], (double)invstd[i] * (sgy - (double)mean[i] * sg));
+  }
+  if (fin.counter != nullptr) {
+    __shared__ int last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(fin.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+      __threadfence();
+      float gs = fin.grad_scale;
+      if (fin.dscale != nullptr) gs *= fin.dscale[0];
+      for (int i = threadIdx.x; i < c; i += blockDim.x)
+        bn_bwd_finalize_one(sums, c, i, fin.count, fin.gamma, mean, invstd, fin.training, gs, fin.dgamma, fin.dbeta,
+                            fin.dbias, fin.coef);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_bwd_apply_h8_kernel(const __half* __restrict__ da, const __half* __restrict__ y,
                                                              __half* __restrict__ dy, long long npix, int c,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
@@ -1114,6 +1215,19 @@ static int bn_bwd_stats_impl(const void* da, int32_t dtype_da, const void* y, in
     HcuBnBwdFin f;
     memset(&f, 0, sizeof(f));
     if (fin != nullptr) f = *fin;
+    static int pooled_on = -1;
+    if (pooled_on < 0) { const char* e = getenv("HCU_BN_POOLED_STATS"); pooled_on = e ? atoi(e) : 1; }
+    if (argmax != nullptr && pooled_on && pg.px * pg.py * pg.pz <= 256 && (((uintptr_t)argmax) & 7) == 0) {
+      // pooled layer: the sums over the full-resolution gradient only need the pooled gradient and y at the argmax positions
+      const long long npool = (long long)pg.n * pg.ox * pg.oy * pg.oz;
+      const int grid = grid_for(npool * (c / 8), 256 * 4, 12);
+      const size_t smem = 16 * c * sizeof(float) + (size_t)pg.px * pg.py * pg.pz * sizeof(int);
+      launch_pdl(2, bn_bwd_stats_pool_h8_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, (const __half*)da, argmax,
+                 (const __half*)y, npool, c, scale, shift, mean, invstd, relu, pg, make_fastdiv((uint32_t)pg.oz),
+                 make_fastdiv((uint32_t)pg.oy), make_fastdiv((uint32_t)pg.ox), sums, f);
+      HCU_CHECK_LAUNCH("bn_bwd_stats_pool_h8");
+      return 0;
+    }
     const int grid = grid_for(npix * (c / 8), 256 * 4, 12);
     launch_pdl(2, bn_bwd_stats_h8_kernel, dim3(grid), dim3(256), 16 * c * sizeof(float), (cudaStream_t)stream,
                (const __half*)da, (const __half*)y, npix, c, scale, shift, mean, invstd, relu, argmax, pg, sums, f);

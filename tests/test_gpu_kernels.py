@@ -500,3 +500,48 @@ def test_data_gradient_with_fused_bn_backward_statistics(case):
     assert not torch.isnan(b[0]).any() and torch.equal(a[0], b[0])
     for i in (1, 2, 3):
         assert float((a[i] - b[i]).abs().max()) <= 2e-6 * float(a[i].abs().max()), i
+
+
+@pytest.mark.parametrize("shape,c,pool", [((2, 11, 12, 7), 8, (2, 2, 1)), ((1, 8, 9, 6), 16, (2, 2, 2)), ((1, 6, 6, 5), 64, (2, 2, 1)),
+                                          ((1, 9, 7, 4), 32, (3, 2, 1))])
+def test_pooled_bn_backward_statistics_match_the_scattered_gradient(shape, c, pool):
+    """BatchNorm-backward statistics of a pooled layer computed at POOLED resolution (`bn_bwd_stats_pool_h8_kernel`: pooled
+    gradient + y gathered at the argmax positions) == the sums over the full-resolution gradient that max-pool backward would
+    scatter (torch, float64), including extents that the pooling floors."""
+    from hcunet_b200 import _lib
+
+    lib = _lib.load()
+    B, X, Y, Z = shape
+    px, py, pz = pool
+    g0 = torch.Generator().manual_seed(X * 100 + c)
+    y = (torch.randn((B, X, Y, Z, c), generator=g0) * 1.5).half().cuda()
+    scale = (torch.rand(c, generator=g0) + 0.5).cuda()
+    shift = (torch.randn(c, generator=g0) * 0.3).cuda()
+    mean = (torch.randn(c, generator=g0) * 0.1).cuda()
+    invstd = (torch.rand(c, generator=g0) + 0.5).cuda()
+    ox, oy, oz = X // px, Y // py, Z // pz
+    pooled = torch.empty((B, ox, oy, oz, c), dtype=torch.float16, device="cuda")
+    argmax = torch.empty((B, ox, oy, oz, c), dtype=torch.uint8, device="cuda")
+    _lib.check(lib.hcu_bn_relu_maxpool(P(y), _lib.F16, P(pooled), _lib.F16, P(argmax), B, X, Y, Z, c, px, py, pz, P(scale), P(shift), 1,
+                                       stream()), "bn_relu_maxpool")
+    dpool = torch.randn((B, ox, oy, oz, c), generator=g0).half().cuda()
+    npix = B * X * Y * Z
+    sums = torch.zeros((_lib.STAT_BINS, 2, c), dtype=torch.float64, device="cuda")
+    geom = _lib.HcuPoolGeom(B, X, Y, Z, px, py, pz)
+    _lib.check(lib.hcu_bn_bwd_stats(P(dpool), _lib.F16, P(y), _lib.F16, npix, c, P(scale), P(shift), P(mean), P(invstd), 1, P(argmax),
+                                    C.byref(geom), P(sums), stream()), "bn_bwd_stats")
+    torch.cuda.synchronize()
+    got = sums.sum(0).cpu()
+    # reference: scatter the pooled gradient to the argmax voxel of every window, then the plain sums
+    yc, dp, am = y.double().cpu(), dpool.double().cpu(), argmax.cpu().long()
+    full = torch.zeros((B, X, Y, Z, c), dtype=torch.float64)
+    wz, wq = am % pz, am // pz
+    wy, wx = wq % py, wq // py
+    bi, qx, qy, qz, ci = torch.meshgrid(torch.arange(B), torch.arange(ox), torch.arange(oy), torch.arange(oz), torch.arange(c), indexing="ij")
+    full[bi, qx * px + wx, qy * py + wy, qz * pz + wz, ci] = dp
+    act = yc * scale.double().cpu() + shift.double().cpu()
+    g = torch.where(act > 0, full, torch.zeros_like(full))
+    want1 = g.sum(dim=(0, 1, 2, 3))
+    want2 = (g * (yc - mean.double().cpu()) * invstd.double().cpu()).sum(dim=(0, 1, 2, 3))
+    den = max(float(want1.abs().max()), float(want2.abs().max()), 1.0)
+    assert float((got[0] - want1).abs().max()) <= 1e-4 * den and float((got[1] - want2).abs().max()) <= 1e-4 * den
