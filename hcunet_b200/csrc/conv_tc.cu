@@ -1087,7 +1087,15 @@ static int conv_tc_fwd_impl(const HcuConvDesc* d, const void* in, const void* pa
   }
   if (bnb != nullptr) {
     // only the specialised variants carry the fused statistics; the output must be the dense [pixels][cout] tensor y has
-    if (vi == 0 || d->out_cpitch != d->cout || d->out_c_off != 0 || p.ks) {
+    // The generic kernel's vector epilogue can do it too (32 / 64-channel levels, every output channel in the CTA), but there
+    // the y loads are not prefetched and the sums need a shuffle reduction per 16-channel chunk and plane: measured SLOWER than
+    // the separate pass (d2.conv2.dgrad 37 -> 63 us, d3.conv2.dgrad 28 -> 60 us for 28 + 19 us of statistics saved; bench step
+    // 2.86 -> 2.93 ms).  Opt-in only (HCU_TC_BNB_GENERIC=1).
+    static int bnb_generic = -1;
+    if (bnb_generic < 0) { const char* e = getenv("HCU_TC_BNB_GENERIC"); bnb_generic = e ? atoi(e) : 0; }
+    const bool generic_ok = bnb_generic && vi == 0 && p.debug == 0 && p.nsplit == 1 && p.epi_fast && d->cout % 16 == 0 &&
+                            d->cout == p.Nc && bias == nullptr && stats == nullptr && out_scale == nullptr && !d->out_relu;
+    if ((vi == 0 && !generic_ok) || d->out_cpitch != d->cout || d->out_c_off != 0 || p.ks) {
       if (!query_only) set_error("conv_tc_fwd_bnbwd: no specialised variant takes this descriptor");
       return HCU_ERR_UNSUPPORTED;
     }

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     sbias[i] = (in && p.bias != nullptr) ? p.bias[ch % p.cpp] : 0.f;
     sbias[Nc + i] = (in && p.out_scale != nullptr) ? p.out_scale[ch] : 1.f;
     sbias[2 * Nc + i] = (in && p.out_shift != nullptr) ? p.out_shift[ch] : 0.f;
-    if (S && (V::kFlags & 16) != 0) {   // fused BN-backward statistics: that layer's scale / shift (for the ReLU mask)
+    if (S ? (V::kFlags & 16) != 0 : p.bnb.y != nullptr) {   // fused BN-backward statistics: that layer's scale / shift (ReLU mask)
       sbias[Nc + i] = in ? p.bnb.scale[ch] : 1.f;
       sbias[2 * Nc + i] = in ? p.bnb.shift[ch] : 0.f;
     }
@@ -766,6 +766,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     const bool has_bias = S ? (V::kFlags & 1) != 0 : p.bias != nullptr;
     const int out_relu = S ? ((V::kFlags & 8) != 0 ? 1 : 0) : p.out_relu, cout = p.cout;
     constexpr bool BNB = S && (V::kFlags & 16) != 0;   // fused BatchNorm-backward statistics (data-gradient launches)
+    const bool bnb_rt = !S && p.bnb.y != nullptr;      // the same in the generic kernel's vector epilogue (32 / 64-channel levels)
     const int nch = S ? (V::kEpi == 1 ? 8 : 16) : min(Nc, cout - ns * Nc);  // real output channels of this CTA's column chunk
     // per M-block: element offset of this thread's pixel inside an output x-plane (-1: wrap-around / out of range)
     // (slot k of this warp = M-block half + k * MBSTEP)
@@ -990,6 +991,11 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
                 sstat[warp * 2 * Nc + Nc + cc + (lane >> 1)] += r2;
               }
             }
+            float b1[16], b2[16];   // generic kernel's fused BN-backward statistics: this row's masked gradient and its product with y
+            if (bnb_rt) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { b1[j] = 0.f; b2[j] = 0.f; }
+            }
             if (valid) {
               if (affine) {
 #pragma unroll
@@ -1010,6 +1016,21 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
               __half* o = oplane + poff[k] + cc;
               *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(&h[0]);
               if (cc + 8 < nch) *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<uint4*>(&h[4]);
+              if (bnb_rt) {  // generic kernel: any multiple of 16 channels, one shuffle reduction per chunk into the warp's slot
+                const __half* yp = p.bnb.y + obase0 + (long long)(x0 + i) * p.out_sx + poff[k] + cc;
+                const uint4 y0 = ldg_nc16(yp), y1 = ldg_nc16(yp + 8);
+                const __half2* ya = reinterpret_cast<const __half2*>(&y0);
+                const __half2* yb = reinterpret_cast<const __half2*>(&y1);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float2 g = __half22float2(h[j]);
+                  const float2 yy = __half22float2(j < 4 ? ya[j] : yb[j - 4]);
+                  if (fmaf(yy.x, sbias[Nc + cc + 2 * j], sbias[2 * Nc + cc + 2 * j]) <= 0.f) g.x = 0.f;
+                  if (fmaf(yy.y, sbias[Nc + cc + 2 * j + 1], sbias[2 * Nc + cc + 2 * j + 1]) <= 0.f) g.y = 0.f;
+                  b1[2 * j] = g.x; b1[2 * j + 1] = g.y;
+                  b2[2 * j] = g.x * yy.x; b2[2 * j + 1] = g.y * yy.y;
+                }
+              }
               if (BNB) {  // 16 channels, one chunk (Nc == 16): sums in t1 / t2, scale / shift from shared memory
                 const __half2* yh = reinterpret_cast<const __half2*>(&yv[k][0]);
 #pragma unroll
@@ -1022,6 +1043,14 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
                   t2[2 * j] = fmaf(g.x, yy.x, t2[2 * j]);
                   t2[2 * j + 1] = fmaf(g.y, yy.y, t2[2 * j + 1]);
                 }
+              }
+            }
+            if (bnb_rt) {   // every lane takes part in the reduction (rows without an output contribute zeros)
+              const float r1 = reduce16(b1, lane);
+              const float r2 = reduce16(b2, lane);
+              if ((lane & 1) == 0) {
+                sstat[warp * 2 * Nc + cc + (lane >> 1)] += r1;
+                sstat[warp * 2 * Nc + Nc + cc + (lane >> 1)] += r2;
               }
             }
           }
@@ -1119,7 +1148,7 @@ __global__ void __launch_bounds__(kThreads, 2) conv_tc_kernel(const Params p) {
     }
     PROF_REPORT("epilogue", "wait_tfull", "-", nout);
     if (do_stats) stats_tail(p, sstat, BULK ? (int)threadIdx.x : row, ns, Nc, BULK ? 256 : 128, BULK);
-    if (BNB) bnb_tail(p, sstat, BULK ? (int)threadIdx.x : row, Nc, nch, BULK ? 256 : 128, BULK);
+    if (BNB || bnb_rt) bnb_tail(p, sstat, BULK ? (int)threadIdx.x : row, Nc, nch, BULK ? 256 : 128, BULK);
   }
 
 

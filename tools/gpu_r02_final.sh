@@ -23,10 +23,12 @@ if [ "$2" == "noncu" ]; then exit 0; fi
 L="d0.conv1 d0.conv2 d1.conv1 d1.conv2 d2.conv2 u3.conv1"
 timeout 120 python tools/kernel_bench.py conv $L --once > $OUT/${TAG}_plain1.log 2>&1 && timeout 120 python tools/kernel_bench.py dgrad $L --once > $OUT/${TAG}_plain2.log 2>&1 && \
 timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-profile --no-extra > $OUT/${TAG}_plain3.log 2>&1 && {
+if [ "$2" != "lite" ]; then   # the two --set full reports are ~25 MB each: gpurun_out/ only travels back below 64 MiB
 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel" -c 6 -f -o $OUT/${TAG}_full_conv_train \
   python tools/kernel_bench.py conv $L --once > $OUT/${TAG}_ncu1.log 2>&1; echo "ncu full conv train rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"conv_tc_kernel" -c 6 -f -o $OUT/${TAG}_full_conv_dgrad \
   python tools/kernel_bench.py dgrad $L --once > $OUT/${TAG}_ncu2.log 2>&1; echo "ncu full conv dgrad rc=$?"
+fi
 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 700 -c 400 --csv --log-file $OUT/${TAG}_launches_bench.csv \
   python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-profile --no-extra > $OUT/${TAG}_ncu3.log 2>&1; echo "ncu list rc=$?"
 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"conv_tc_kernel|conv_ks_kernel" --launch-skip 102 -c 52 --csv \
