@@ -400,6 +400,8 @@ def main_ours(args):
     # buffer): one elementwise Adam launch instead of a multi-tensor pass over 136 tensors + 136 step counters (0.10 -> 0.01 ms)
     flat = H.FlatParameters(model) if os.environ.get("HCUNET_FLAT_ADAM", "1") != "0" else None
     opt = torch.optim.Adam([flat.flat] if flat is not None else model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
+    if flat is not None and os.environ.get("HCUNET_GUARD", "1") != "0":
+        flat.guard(opt)     # skip-step on non-finite gradients (fp16 storage), one pass over the flat gradient per step
 
     def zero_grads():
         if flat is not None:

@@ -39,6 +39,24 @@ class FlatParameters:
         self.model = model
         self.flat = torch.nn.Parameter(flat, requires_grad=True)
         self.numel = n
+        self._found_inf = None
+        self._one = None
+
+    def guard(self, optimizer):
+        """Skip-step safety net of the fp16-storage path (what torch.cuda.amp.GradScaler does for autocast training): after
+        every backward one pass over the flat gradient sets a device flag when any gradient is inf / NaN (an activation or a
+        gradient left fp16's range), and the optimiser -- torch's fused Adam / AdamW / SGD read `optimizer.found_inf` -- then
+        leaves parameters and state untouched for that step.  No host synchronisation, capturable; `skipped_steps()` reads the
+        flag of the latest step.  The backward's own scale is recomputed from max|dlogits| every step, so there is no scale
+        state to back off."""
+        self._found_inf = torch.zeros((), dtype=torch.float32, device=self.flat.device)   # 0-dim like GradScaler's
+        self._one = torch.ones((), dtype=torch.float32, device=self.flat.device)
+        optimizer.found_inf = self._found_inf
+        return self
+
+    def nonfinite(self) -> bool:
+        """True when the latest guarded step found a non-finite gradient (host synchronisation)."""
+        return self._found_inf is not None and bool(self._found_inf.item() != 0)
 
     def sync_grad(self):
         """Point `.flat.grad` at the flat gradient buffer of the latest backward (no copy)."""
@@ -48,6 +66,9 @@ class FlatParameters:
             raise RuntimeError("FlatParameters.sync_grad: the engine holds no flat gradient buffer of this model "
                                "(call it right after loss.backward())")
         self.flat.grad = g
+        if self._found_inf is not None:
+            self._found_inf.zero_()
+            torch._amp_foreach_non_finite_check_and_unscale_([g], self._found_inf, self._one)
 
     def zero_grad(self):
         """Drop the gradients of the flat parameter AND of the model's parameter views (so that the next backward assigns

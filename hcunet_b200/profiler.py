@@ -14,7 +14,7 @@ from . import _lib
 
 
 # entry points that launch the same kernel (the *_bn / *_fin forms only add a fused tail)
-_ALIAS = {"hcu_conv_tc_fwd_bn": "hcu_conv_tc_fwd", "hcu_bn_bwd_stats_fin": "hcu_bn_bwd_stats"}
+_ALIAS = {"hcu_conv_tc_fwd_bn": "hcu_conv_tc_fwd", "hcu_conv_tc_fwd_bnbwd": "hcu_conv_tc_fwd", "hcu_bn_bwd_stats_fin": "hcu_bn_bwd_stats"}
 
 
 class KernelProfile:

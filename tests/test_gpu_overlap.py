@@ -170,3 +170,36 @@ def test_fused_bn_backward_statistics_match_the_separate_pass(feats, shape):
     assert direct > 0.0 or True
     print(f"fused BN-backward statistics: {na} -> {nb} launches per step; fused layers' own dgamma / dbeta deviate {direct:.1e}, "
           f"worst gradient anywhere {worst:.1e} (run-to-run floor of the separate path {wfloor:.1e})")
+
+
+def test_guarded_flat_optimizer_skips_a_step_with_non_finite_gradients():
+    """`FlatParameters.guard`: an input outside fp16's range makes the step's gradients non-finite; the fused Adam leaves the
+    parameters and its state untouched for that step, and trains normally on the next one."""
+    import hcunet_b200 as H
+
+    kw = dict(O.README_3D, feature_sizes=[8, 16, 32])
+    x, mask, pwl = O.golden_inputs(kw, (2, 4, 60, 60, 8), 3)
+    x, mask, pwl = x.cuda(), mask.cuda(), pwl.cuda()
+    torch.manual_seed(0)
+    m = H.Unet_Constructor(**kw)
+    m.precision = "mixed"
+    m = m.cuda().train()
+    fp = H.FlatParameters(m)
+    opt = torch.optim.Adam([fp.flat], lr=1e-3, fused=True, capturable=True)
+    fp.guard(opt)
+
+    def step(inp):
+        fp.zero_grad()
+        H.cross_entropy(m(inp), mask, pwl, "pixel").backward()
+        fp.sync_grad()
+        opt.step()
+
+    step(x)
+    assert not fp.nonfinite()
+    before = fp.flat.detach().clone()
+    bad = x.clone()
+    bad[0, 0, 5, 5, 3] = 1e6           # > 65504: inf once stored as fp16
+    step(bad)
+    assert fp.nonfinite() and torch.equal(fp.flat.detach(), before)
+    step(x)
+    assert not fp.nonfinite() and not torch.equal(fp.flat.detach(), before) and bool(torch.isfinite(fp.flat).all())
