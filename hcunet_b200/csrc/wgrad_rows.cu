@@ -1,0 +1,640 @@
+// Weight gradient of the gather-convolution for the CHANNEL-POOR levels (8 ... 32 channels) on the 5th-generation tensor
+// cores, fed by TMA tensor-map loads: the "row-stacked" formulation.
+//
+//   dW[tap][ci][co] = sum_{n, x, y, z} act(a[n, x + tx, y + ty, z + tz, ci]) * dy[n, x, y, z, co]
+//
+// wgrad_tc5.cu puts the input channels on the M = 128 rows of a tcgen05.mma: with 8 channels 94 % of every MMA is padding, and
+// an MMA costs (A bytes + B bytes) / 128 B per clock whatever it computes (profiles/r01_umma_rate.txt) -- which is why the
+// 8/16-channel levels stayed on mma.sync (wgrad_ws.cu / wgrad_mma.cu, 100 - 160 us per layer for 15 - 40 us of HBM time).
+// Here BOTH operand dimensions carry image rows:
+//   M index = (input row r, 8 input channels)   16 rows x 8 channels = 128
+//   N index = (dy row r', 8 output channels)    up to 14 rows x 8 channels = 112
+//   K index = 16 consecutive z positions of a row
+//   D[(r, ci), (r', co)] += sum_z a[y0 + r, z + tz, ci] * dy[y0 + r', z, co]
+// so ONE MMA multiplies every input row of a tile with every dy row of the tile, and the block (r, r') of the accumulator
+// is the contribution of rows (y0 + r, y0 + r') to the tap ty = r - r': three block diagonals of the 16 x 14 block matrix
+// are the KY = 3 taps, the rest is never read.  19 % of the MACs are useful -- and the layer still needs 4x fewer tensor
+// cycles than the mma.sync kernels need shared-memory cycles, because one 60-clock MMA covers 14 rows x 16 z = 224 pixels
+// of three taps.  A filter tap along z moves the START ADDRESS of the A operand by whole pixels, a tap along x selects
+// another x-plane of the ring: one accumulator (N columns of TMEM) per (tx, tz, input plane, dy plane).
+//
+// Operand layout = memory layout: a row of an x-plane is [z][8 channels] = the canonical no-swizzle MN-major core-matrix
+// layout (8 channels in 16 bytes, the 8 z positions of a K group 16 bytes apart, LBO = 128 B to the next K group, SBO =
+// row pitch to the next 8-row group of M / N).  A tile (rows x z x 8 channels of one x-plane) is ONE TMA tensor-map box;
+// positions outside the tensor (z >= OZ of the last K group, rows >= OY of the last tile) are zero-filled by the TMA
+// unit, which is all the masking the formulation needs: a zero dy element kills whatever its partner is.
+//
+// Roles (448 threads, one CTA per SM -- the accumulators take up to 512 TMEM columns):
+//   warps 0-3   epilogue at the end of a segment: TMEM -> block diagonals summed over the rows -> shared -> red.global
+//   warps 4-11  the previous layer's BatchNorm + ReLU applied in place to a landed input tile (generic proxy, then
+//               fence.proxy.async); idle when the input needs no transform
+//   warp 12     TMA producer: the input tile and the dy tile of a step into one ring slot, one mbarrier complete_tx
+//   warp 13     TMEM allocation + MMA issue (one thread); tcgen05.commit frees ring slots
+// Work: the (image, row tile, x) steps of a layer are cut into equal contiguous ranges, one per CTA; a CTA marches along x
+// inside a row tile (each input plane serves KX output planes) and flushes its accumulators when it leaves the tile.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace hcu {
+namespace wgr {
+using namespace ptx;
+
+constexpr int kThreads = 448;
+constexpr int kXfWarps = 8;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kMaxPer = 64;  // MMAs per x tap and step
+
+struct Params {
+  float* wacc;  // fp32 [taps][cin][cout], zeroed by the caller
+  const float* a_scale;
+  const float* a_shift;
+  long long* prof;         // HCU_ROWS_PROF: clock64 stamps of CTA (0, 0) (timing experiments only)
+  int N, OX, OY, cin, cout;
+  int P, PG;               // input channel planes (all in every CTA), dy channel planes per CTA (kinds = Po / PG on grid.y)
+  int KX, KY, KZ, dx, dy_, dz;
+  int RP, RA, ZC;          // dy rows / input rows per tile, K groups of 16 z positions
+  int ZAP, ZGP;            // row pitch (pixels) of the staged input / dy tiles
+  int NCOL, tmem_cols;
+  int S;                   // ring depth: slot = [P input planes | pad | PG dy planes]
+  int a_plane_bytes, g_plane_bytes, slot_bytes, off_g;   // off_g: the dy tiles inside a slot
+  int a_box_bytes, g_box_bytes;
+  int off_red, off_bar, smem_bytes;
+  int n_ytiles, total_steps, steps_per_cta;
+  int in_relu, zero_fill;
+  int dbg;                 // HCU_ROWS_DEBUG (timing experiments only): 1 = no MMA issue
+  int nper;                // MMAs per x tap and step: (tz, input plane, dy plane, K group), K group fastest
+  // per MMA of an x tap, read through the constant bank with a uniform index (the issuing warp runs on the uniform datapath):
+  uint32_t tab_a[kMaxPer];  // input operand: offset from the slot base, 16-byte units
+  uint32_t tab_b[kMaxPer];  // dy operand: offset from the slot base, 16-byte units
+  uint32_t tab_t[kMaxPer];  // accumulator column offset | (K group != 0) << 31
+};
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3, int c4,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::
+          "r"(dst),
+      "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar)
+      : "memory");
+}
+
+// MN-major, no swizzle: LBO = next 8-position K group, SBO = next 8-element M / N group (here: the next image row)
+__device__ __forceinline__ uint64_t desc_hi_mn(uint32_t sbo_bytes) {
+  return (uint64_t)(((sbo_bytes >> 4) & 0x3FFF) | (1u << 14)) << 32;  // SBO | descriptor version 1 (bit 46)
+}
+
+__device__ __forceinline__ uint4 bn_relu8(uint4 v, const float* sc, const float* sh, int relu) {
+  __half2* h = reinterpret_cast<__half2*>(&v);
+  const __half2 zero = __float2half2_rn(0.f);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 f = __half22float2(h[k]);
+    f.x = fmaf(f.x, sc[2 * k], sh[2 * k]);
+    f.y = fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]);
+    h[k] = __floats2half2_rn(f.x, f.y);
+    if (relu) h[k] = __hmax2_nan(h[k], zero);
+  }
+  return v;
+}
+
+// One contiguous piece of a CTA's step range inside one (image, row tile)
+struct Segment {
+  int n, yt, xb, nout;
+};
+__device__ __forceinline__ bool next_segment(const Params& p, int& f, int f1, Segment& s) {
+  if (f >= f1) return false;
+  const int tile = f / p.OX;
+  s.xb = f - tile * p.OX;
+  s.nout = min(p.OX - s.xb, f1 - f);
+  s.n = tile / p.n_ytiles;
+  s.yt = tile - s.n * p.n_ytiles;
+  f += s.nout;
+  return true;
+}
+
+// The MMA-issuing warp.  It is bound by its own instruction latency, not by the tensor pipe (one warp, dependent uniform-datapath
+// instructions: the first version spent ~1000 clocks of bookkeeping per step beside 6 MMAs of 60): the common shapes get the x
+// taps and the per-tap MMA list unrolled at compile time with the descriptor offsets held in registers.
+struct MmaCtx {
+  uint32_t tmem_base, ring, bar_in, bar_e, bar_accf, bar_acce;
+  int f0, f1, span, lane;
+  bool prof;
+};
+template <int KXT, int NPT>
+__device__ __forceinline__ void mma_role(const Params& p, const MmaCtx& c) {
+  const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NCOL >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t lbo = (128u >> 4) << 16;
+  const uint64_t a_hi = desc_hi_mn((uint32_t)(p.ZAP * 16)) | lbo, b_hi = desc_hi_mn((uint32_t)(p.ZGP * 16)) | lbo;
+  const int S = p.S, span = c.span, dxs = p.dx;
+  const int KX = KXT > 0 ? KXT : p.KX, nper = NPT > 0 ? NPT : p.nper;
+  const uint32_t ring16 = c.ring >> 4, slot16 = (uint32_t)p.slot_bytes >> 4;
+  const uint32_t tx_cols = (uint32_t)(p.KZ * p.P * p.PG * p.NCOL);
+  const bool no_mma = (p.dbg & 1) != 0;
+  constexpr int NP = NPT > 0 ? NPT : 1;
+  uint32_t ta[NP], tb[NP], tt[NP], tp[NP];
+  if (NPT > 0) {
+#pragma unroll
+    for (int m = 0; m < NP; ++m) {
+      ta[m] = p.tab_a[m]; tb[m] = p.tab_b[m];
+      tt[m] = p.tab_t[m] & 0x7fffffffu; tp[m] = p.tab_t[m] >> 31;
+    }
+  }
+  int w_idx = 0, seg = 0, f = c.f0;
+  uint32_t w_par = 0;
+  Segment s;
+  while (next_segment(p, f, c.f1, s)) {
+    if (seg > 0) {
+      mbar_wait(c.bar_acce, (uint32_t)(seg - 1) & 1u);
+      tc_fence_after();
+    }
+    int ring_i = w_idx, have = 0;
+    for (int i = 0; i < s.nout; ++i) {
+      for (; have < i + span; ++have) {  // slot i + span - 1 carries the newest input plane and dy plane i
+        mbar_wait(c.bar_in + 8 * w_idx, w_par);
+        if (++w_idx == S) { w_idx = 0; w_par ^= 1u; }
+      }
+      tc_fence_after();
+      if (c.prof && c.lane == 0 && seg == 0 && i == 0) p.prof[2] = clock64();
+      if (c.prof && c.lane == 0 && seg == 0 && i == 1) p.prof[9] = clock64();
+      int sg = ring_i + span - 1;
+      if (sg >= S) sg -= S;
+      const uint32_t gslot = ring16 + (uint32_t)sg * slot16;
+      const uint32_t acc0 = (uint32_t)i;
+      if (elect_one()) {
+        if (!no_mma) {
+          if (KXT > 0 && NPT > 0) {
+            int sl = ring_i;
+#pragma unroll
+            for (int tx = 0; tx < KXT; ++tx) {
+              const uint32_t aslot = ring16 + (uint32_t)sl * slot16;
+              const uint32_t tbase = c.tmem_base + (uint32_t)tx * tx_cols;
+#pragma unroll
+              for (int m = 0; m < NP; ++m)
+                umma_f16(tbase + tt[m], a_hi | (uint64_t)(aslot + ta[m]), b_hi | (uint64_t)(gslot + tb[m]), idesc, acc0 | tp[m]);
+              sl += dxs;
+              if (sl >= S) sl -= S;
+            }
+          } else {
+            uint32_t tbase = c.tmem_base;
+            int sl = ring_i;
+            for (int tx = 0; tx < KX; ++tx) {
+              const uint32_t aslot = ring16 + (uint32_t)sl * slot16;
+#pragma unroll 2
+              for (int m = 0; m < nper; ++m) {
+                const uint32_t t = p.tab_t[m];
+                umma_f16(tbase + (t & 0x7fffffffu), a_hi | (uint64_t)(aslot + p.tab_a[m]), b_hi | (uint64_t)(gslot + p.tab_b[m]), idesc,
+                         acc0 | (t >> 31));
+              }
+              tbase += tx_cols;
+              sl += dxs;
+              if (sl >= S) sl -= S;
+            }
+          }
+        }
+        umma_commit(c.bar_e + 8 * ring_i);  // slot i: its input plane is not needed by later outputs, its dy plane was used earlier
+        if (i == s.nout - 1) {
+          int r = ring_i;
+          for (int k = 1; k < span; ++k) {
+            if (++r == S) r = 0;
+            umma_commit(c.bar_e + 8 * r);
+          }
+          umma_commit(c.bar_accf);
+        }
+      }
+      __syncwarp();
+      if (++ring_i == S) ring_i = 0;
+    }
+    if (c.prof && c.lane == 0 && seg == 0) { p.prof[3] = clock64(); p.prof[10] = s.nout; }
+    ++seg;
+  }
+  if (c.prof && c.lane == 0) p.prof[4] = clock64();
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.S;
+  const bool prof = p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (prof && tid == 0) p.prof[0] = clock64();
+  // barrier map: full[S] (TMA bytes of the slot), ready[S] (input tile transformed), empty[S], acc_full, acc_empty
+  const uint32_t bar_f = smem_u32(smem + p.off_bar), bar_r = bar_f + 8 * S, bar_e = bar_r + 8 * S, bar_accf = bar_e + 8 * S,
+                 bar_acce = bar_accf + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (3 * S + 2));
+  const uint32_t ring = smem_u32(smem);
+  const bool xf = p.a_scale != nullptr;
+  const int span = (p.KX - 1) * p.dx + 1;
+  const int kind = blockIdx.y;
+  const int f0 = blockIdx.x * p.steps_per_cta, f1 = min(p.total_steps, f0 + p.steps_per_cta);
+  const int red_n = p.KX * p.KY * p.KZ * p.P * 8 * p.PG * 8;
+
+  if (p.zero_fill) {  // merged rows shorter than the z reach of the last tap: the bytes read past a tile must be finite
+    uint4* q = reinterpret_cast<uint4*>(smem);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = tid; i < p.off_red / 16; i += kThreads) q[i] = z;
+  }
+  if (warp == 13) {
+    if (lane == 0) {
+      for (int i = 0; i < S; ++i) { mbar_init(bar_f + 8 * i, 1); mbar_init(bar_r + 8 * i, kXfWarps); mbar_init(bar_e + 8 * i, 1); }
+      mbar_init(bar_accf, 1);
+      mbar_init(bar_acce, 4);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), (uint32_t)p.tmem_cols);
+  }
+  fence_proxy_async();  // the zero fill above (generic proxy) before any TMA write to the same bytes
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (prof && tid == 0) p.prof[1] = clock64();
+
+  // The single-thread roles (TMA issue, MMA issue) are bound by their own instruction latency: the WHOLE warp runs their
+  // loops so that every index stays on the uniform datapath (no R2UR per operand), ring positions and parities are kept
+  // incrementally, and only the issuing instructions sit behind elect_one().
+  if (warp == 12) {
+    // =========================================== TMA PRODUCER ========================================
+    int idx = 0, f = f0;
+    uint32_t par = 1, dst = ring;
+    const uint32_t a_bytes = (uint32_t)(p.P * p.a_box_bytes), ag_bytes = a_bytes + (uint32_t)(p.PG * p.g_box_bytes);
+    const int c0g = 8 * kind * p.PG;
+    Segment s;
+    while (next_segment(p, f, f1, s)) {
+      const int y0 = s.yt * p.RP;
+      const int nplanes = s.nout + span - 1;
+      for (int j = 0; j < nplanes; ++j) {  // slot j: input plane xb + j and (from j = span - 1 on) dy plane xb + j - (span - 1)
+        mbar_wait(bar_e + 8 * idx, par);
+        if (elect_one()) {
+          const uint32_t bar = bar_f + 8 * idx;
+          const bool with_g = j >= span - 1;
+          mbar_expect_tx(bar, with_g ? ag_bytes : a_bytes);
+          for (int pl = 0; pl < p.P; ++pl) tma_load_5d(dst + (uint32_t)(pl * p.a_plane_bytes), &tmA, 8 * pl, 0, y0, s.xb + j, s.n, bar);
+          if (with_g)
+            for (int q = 0; q < p.PG; ++q)
+              tma_load_5d(dst + (uint32_t)(p.off_g + q * p.g_plane_bytes), &tmG, c0g + 8 * q, 0, y0, s.xb + j - (span - 1), s.n, bar);
+        }
+        __syncwarp();
+        dst += (uint32_t)p.slot_bytes;
+        if (++idx == S) { idx = 0; par ^= 1u; dst = ring; }
+      }
+    }
+  } else if (warp == 13) {
+    // =========================================== MMA ISSUER ==========================================
+    const MmaCtx c{tmem_base, ring, xf ? bar_r : bar_f, bar_e, bar_accf, bar_acce, f0, f1, span, lane, prof};
+    if (p.KX == 3 && p.nper == 2) mma_role<3, 2>(p, c);
+    else if (p.KX == 3 && p.nper == 4) mma_role<3, 4>(p, c);
+    else if (p.KX == 3 && p.nper == 8) mma_role<3, 8>(p, c);
+    else mma_role<0, 0>(p, c);
+  } else if (warp >= 4) {
+    // =========================================== INPUT TRANSFORM =====================================
+    if (xf) {
+      const int xt = tid - 128;
+      const int plane = xt % p.P, c0 = xt / p.P, cstep = (32 * kXfWarps) / p.P;
+      const int nchunk = p.RA * p.ZAP;
+      float sc[8], sh[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = p.a_scale[plane * 8 + j]; sh[j] = p.a_shift[plane * 8 + j]; }
+      const int relu = p.in_relu;
+      int sl = 0, f = f0;
+      uint32_t par = 0;
+      Segment s;
+      while (next_segment(p, f, f1, s)) {
+        const int nplanes = s.nout + span - 1;
+        for (int j = 0; j < nplanes; ++j) {
+          mbar_wait(bar_f + 8 * sl, par);
+          uint4* tile = reinterpret_cast<uint4*>(smem + sl * p.slot_bytes + plane * p.a_plane_bytes);
+          for (int c = c0; c < nchunk; c += cstep) tile[c] = bn_relu8(tile[c], sc, sh, relu);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_r + 8 * sl);
+          if (++sl == S) { sl = 0; par ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // =========================================== EPILOGUE ============================================
+    // TMEM lane = 8 * r + ci (input row r of the tile, channel ci of the plane); warp w holds rows 4w .. 4w + 3 and writes
+    // its sums over those rows into its own copy of the [tap][ci][co] block (plain stores: every entry once per segment).
+    const int rj = lane >> 3, ci = lane & 7;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int redw = p.PG * 8;
+    float* red = reinterpret_cast<float*>(smem + p.off_red);
+    float* mine = red + (size_t)warp * red_n;
+    int seg = 0, f = f0;
+    Segment s;
+    while (next_segment(p, f, f1, s)) {
+      mbar_wait(bar_accf, (uint32_t)seg & 1u);
+      tc_fence_after();
+      if (prof && tid == 0 && seg == 0) p.prof[5] = clock64();
+      int comb = 0;
+      for (int tx = 0; tx < p.KX; ++tx)
+        for (int tz = 0; tz < p.KZ; ++tz)
+          for (int pl = 0; pl < p.P; ++pl)
+            for (int q = 0; q < p.PG; ++q, ++comb) {
+              for (int ty = 0; ty < p.KY; ++ty) {
+                // block (r, r' = r - ty * dil) of the accumulator, for the four rows of this warp; the column offset is
+                // warp-uniform per load, every lane keeps the load of its own row
+                uint32_t u[4][8];
+                bool any = false;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int r = 4 * warp + j, rp = r - ty * p.dy_;
+                  if (r < p.RA && rp >= 0 && rp < p.RP) {
+                    tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)(comb * p.NCOL + 8 * rp), u[j]);
+                    any = true;
+                  }
+                }
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = 0.f;
+                if (any) {  // warp-uniform
+                  tmem_wait_ld();
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const int r = 4 * warp + j, rp = r - ty * p.dy_;
+                    if (r < p.RA && rp >= 0 && rp < p.RP) {
+                      tmem_pin8(u[j]);
+                      if (rj == j) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(u[j][k]);
+                      }
+                    }
+                  }
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
+                    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+                  }
+                }
+                if (lane < 8) {
+                  const int tap = (tx * p.KY + ty) * p.KZ + tz;
+                  float4* o = reinterpret_cast<float4*>(mine + ((size_t)(tap * p.P + pl) * 8 + ci) * redw + q * 8);
+                  o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                  o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+              }
+            }
+      // the accumulators are free: the next segment's MMAs may overwrite them while this one is flushed
+      tc_fence_before();
+      __syncwarp();
+      if (prof && tid == 0 && seg == 0) p.prof[6] = clock64();
+      if (lane == 0) mbar_arrive(bar_acce);
+      named_bar_sync(1, 128);
+      const int cin_p = p.P * 8;
+      for (int e = tid; e < red_n; e += 128) {
+        const int col = e % redw, row = e / redw;  // row = tap * (8 P) + input channel
+        const int tap = row / cin_p, cc = row - tap * cin_p;
+        const int co = kind * redw + col;
+        const float val = (red[e] + red[e + red_n]) + (red[e + 2 * red_n] + red[e + 3 * red_n]);
+        if (cc < p.cin && co < p.cout) atomicAdd(&p.wacc[((size_t)tap * p.cin + cc) * p.cout + co], val);
+      }
+      named_bar_sync(1, 128);
+      if (prof && tid == 0 && seg == 0) p.prof[7] = clock64();
+      ++seg;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (prof && tid == 0) p.prof[8] = clock64();
+  if (warp == 13) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+struct Config {
+  Params p;
+  int kinds, gx;
+  bool merged_a, merged_g;
+  int za;  // z extent the taps reach in an input row
+};
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static const char* configure(const HcuConvDesc* d, Config& c) {
+  Params& p = c.p;
+  memset(&p, 0, sizeof(p));
+  if (d->dtype_in != HCU_F16 || d->dtype_out != HCU_F16) return "fp16 only";
+  if (d->groups != 1) return "groups != 1";
+  if (d->iphase || d->ophase) return "stride phases";
+  if (d->in_cpitch % 8 != 0 || d->in_c_off != 0 || d->cin > d->in_cpitch) return "input channel layout";
+  if (d->out_cpitch % 8 != 0 || d->out_c_off != 0 || d->cout > d->out_cpitch) return "dy channel layout";
+  const int P = d->in_cpitch / 8, Po = d->out_cpitch / 8;
+  static const int maxp = env_int("HCU_ROWS_MAXP", 4);
+  if (P != 1 && P != 2 && P != 4) return "input channel pitch above 32";
+  if (Po != 1 && Po != 2 && Po != 4) return "dy channel pitch above 32";
+  if (P > maxp || Po > maxp) return "channel pitch above HCU_ROWS_MAXP";
+  for (int i = 0; i < 3; ++i) {
+    if (d->istep[i] != 1 || d->ostep[i] != 1 || d->ooff[i] != 0 || d->out_tsize[i] != d->out_size[i]) return "strided";
+    if (d->pad[i] != 0) return "padding";  // a transformed zero-filled position would not be zero
+    if (d->in_size[i] != d->out_size[i] + (d->taps[i] - 1) * d->dil[i]) return "not a valid convolution";
+  }
+  p.N = d->batch; p.OX = d->out_size[0]; p.OY = d->out_size[1];
+  const int OZ = d->out_size[2];
+  p.cin = d->cin; p.cout = d->cout; p.P = P;
+  p.KX = d->taps[0]; p.KY = d->taps[1]; p.KZ = d->taps[2];
+  p.dx = d->dil[0]; p.dy_ = d->dil[1]; p.dz = d->dil[2];
+  const int span = (p.KX - 1) * p.dx + 1, halo_y = (p.KY - 1) * p.dy_, halo_z = (p.KZ - 1) * p.dz;
+  if (span > 6) return "x extent";
+  if (halo_y > 12) return "y extent";
+  if (OZ < 8) return "rows too short for a K group";  // K = 16 z positions per MMA: mostly padding
+  p.ZC = (OZ + 15) / 16;
+  const int ZG = 16 * p.ZC;
+  c.za = ZG + halo_z;
+  if (c.za > 256) return "rows too long for one box";
+  // Cp == 8: (z, channel) is one contiguous run -> box rows of up to 256 elements instead of 16-byte pieces
+  c.merged_g = d->out_cpitch == 8 && ZG <= 32;
+  // (a merged input row of 32 positions may be shorter than the z reach of the last tap: what is read past it pairs with
+  // zero-filled dy positions only while the whole input row fits, IZ <= 32)
+  c.merged_a = d->in_cpitch == 8 && ZG <= 32 && d->in_size[2] <= 32 && halo_z <= 8;
+  p.ZGP = ZG;
+  p.ZAP = c.merged_a ? std::min(c.za, 32) : c.za;
+  p.zero_fill = p.ZAP < c.za ? 1 : 0;
+  // dy planes per CTA and rows per tile: all (tx, tz, input plane, dy plane) accumulators of a CTA live in TMEM
+  static const int tmem_max = env_int("HCU_ROWS_TMEM", 512);
+  const int oy_even = round_up(p.OY, 2);
+  double best = 1e30;
+  int best_pg = 0, best_rp = 0;
+  for (int pg = Po; pg >= 1; pg >>= 1) {
+    const int ncomb = p.KX * p.KZ * P * pg;
+    int rp = std::min(16 - halo_y, tmem_max / (8 * ncomb));
+    rp = std::min(rp & ~1, oy_even);
+    if (rp < 2) continue;
+    const int tiles = (p.OY + rp - 1) / rp;
+    const double cost = (double)ncomb * (32 + 2 * rp) / (16.0 * rp) * (Po / pg) * ((double)tiles * rp / p.OY);
+    if (cost < best) { best = cost; best_pg = pg; best_rp = rp; }
+  }
+  if (best_pg == 0) return "accumulators do not fit in TMEM";
+  p.PG = best_pg; p.RP = best_rp; p.RA = best_rp + halo_y;
+  c.kinds = Po / p.PG;
+  p.NCOL = 8 * p.RP;
+  {
+    int cols = p.KX * p.KZ * P * p.PG * p.NCOL, t = 32;
+    while (t < cols) t <<= 1;
+    p.tmem_cols = t;
+  }
+  p.a_box_bytes = p.RA * p.ZAP * 16;
+  p.g_box_bytes = p.RP * p.ZGP * 16;
+  p.a_plane_bytes = round_up(p.a_box_bytes, 128);
+  p.g_plane_bytes = round_up(p.g_box_bytes, 128);
+  p.off_g = P * p.a_plane_bytes + 128;  // + what the last tap reads past a merged row
+  p.slot_bytes = p.off_g + p.PG * p.g_plane_bytes;
+  const int red_bytes = 4 * p.KX * p.KY * p.KZ * P * 8 * p.PG * 8 * 4;  // one copy per epilogue warp
+  p.nper = p.KZ * P * p.PG * p.ZC;
+  if (p.nper > kMaxPer) return "too many MMAs per step";
+  for (int m = 0; m < p.nper; ++m) {
+    int r = m;
+    const int zc = r % p.ZC; r /= p.ZC;
+    const int q = r % p.PG; r /= p.PG;
+    const int pl = r % P;
+    const int tz = r / P;
+    p.tab_a[m] = (uint32_t)(pl * p.a_plane_bytes + tz * p.dz * 16 + zc * 256) >> 4;
+    p.tab_b[m] = (uint32_t)(p.off_g + q * p.g_plane_bytes + zc * 256) >> 4;
+    p.tab_t[m] = (uint32_t)(((tz * P + pl) * p.PG + q) * p.NCOL) | (zc ? 0x80000000u : 0u);
+  }
+  // look-ahead: ~64 KB of loads in flight per SM
+  static const int la_env = env_int("HCU_ROWS_LA", 0);
+  int la = la_env > 0 ? la_env : std::max(2, std::min(8, (64 * 1024 + p.slot_bytes - 1) / p.slot_bytes));
+  for (;; --la) {
+    if (la < 1) return "does not fit in shared memory";
+    p.S = span + la;
+    // an M = 128 tile reads 16 row groups from a plane's base whatever RA is: keep those reads inside the allocation
+    const int a_end = (p.S - 1) * p.slot_bytes + (P - 1) * p.a_plane_bytes + 16 * p.ZAP * 16 + 512;
+    p.off_red = round_up(p.S * p.slot_bytes, 128);
+    p.off_bar = round_up(p.off_red + red_bytes, 128);
+    p.smem_bytes = std::max(p.off_bar + 8 * (3 * p.S + 2) + 16, a_end) + 128;
+    if (p.smem_bytes <= 200 * 1024) break;
+  }
+  if (p.ZAP * 16 / 16 > 0x3FFF) return "row pitch";
+  p.n_ytiles = (p.OY + p.RP - 1) / p.RP;
+  const long long total = (long long)p.N * p.n_ytiles * p.OX;
+  if (total >= 0x7fffffffLL) return "too many steps";
+  p.total_steps = (int)total;
+  // equal contiguous step ranges, one CTA per SM (and kind); no range shorter than 8 planes (pipeline fill + flush)
+  int gx = std::max(1, num_sms() / c.kinds);
+  gx = (int)std::max(1LL, std::min<long long>(gx, total / 8));
+  p.steps_per_cta = (int)((total + gx - 1) / gx);
+  c.gx = (int)((total + p.steps_per_cta - 1) / p.steps_per_cta);
+  return nullptr;
+}
+
+// rank-5 map of a channels-last fp16 tensor [N][X][Y][Z][cpitch]; box = rows x boxz z positions x 8 channels of one x-plane
+static const char* encode_map(CUtensorMap* tm, const void* base, int cpitch, int Z, int Y, int X, int N, bool merged, int boxz,
+                              int rows) {
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
+  const cuuint64_t px = (cuuint64_t)cpitch * 2;
+  if (merged) {
+    gdim[0] = (cuuint64_t)Z * 8; gdim[1] = 1;
+    gstr[0] = (cuuint64_t)Z * px;
+    box[0] = (cuuint32_t)boxz * 8; box[1] = 1;
+  } else {
+    gdim[0] = (cuuint64_t)cpitch; gdim[1] = (cuuint64_t)Z;
+    gstr[0] = px;
+    box[0] = 8; box[1] = (cuuint32_t)boxz;
+  }
+  gdim[2] = (cuuint64_t)Y; gdim[3] = (cuuint64_t)X; gdim[4] = (cuuint64_t)N;
+  gstr[1] = (cuuint64_t)Z * px; gstr[2] = gstr[1] * Y; gstr[3] = gstr[2] * X;
+  box[2] = (cuuint32_t)rows; box[3] = 1; box[4] = 1;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return "tensor not 16-byte aligned";
+  // the driver entry point is looked up through the runtime: the library keeps no link-time dependency on libcuda.so
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+        qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return "cuTensorMapEncodeTiled not available from this driver";
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, estr,
+                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    static char msg[96];
+    snprintf(msg, sizeof(msg), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return msg;
+  }
+  return nullptr;
+}
+
+}  // namespace wgr
+}  // namespace hcu
+
+using namespace hcu;
+
+extern "C" int hcu_conv_wgrad_rows_supported(const HcuConvDesc* d) {
+  if (d == nullptr) return 0;
+  wgr::Config c;
+  return wgr::configure(d, c) == nullptr ? 1 : 0;
+}
+
+extern "C" int hcu_conv_wgrad_rows_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
+                                       const void* dy, float* wacc, void* stream) {
+  HCU_CHECK_ARG(d && a && dy && wacc, "wgrad_rows: null pointer");
+  HCU_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr), "wgrad_rows: a_scale/a_shift must come together");
+  wgr::Config c;
+  const char* why = wgr::configure(d, c);
+  if (why != nullptr) {
+    set_error("wgrad_rows: unsupported descriptor (%s)", why);
+    return HCU_ERR_UNSUPPORTED;
+  }
+  wgr::Params& p = c.p;
+  p.wacc = wacc; p.a_scale = a_scale; p.a_shift = a_shift; p.in_relu = d->in_relu;
+  static const int dbg_env = wgr::env_int("HCU_ROWS_DEBUG", 0);
+  p.dbg = dbg_env;
+  static const int prof_env = wgr::env_int("HCU_ROWS_PROF", 0);
+  static long long* prof_buf = nullptr;
+  if (prof_env && prof_buf == nullptr) cudaMalloc(&prof_buf, 16 * sizeof(long long));
+  p.prof = prof_env ? prof_buf : nullptr;
+  CUtensorMap tmA, tmG;
+  why = wgr::encode_map(&tmA, a, d->in_cpitch, d->in_size[2], d->in_size[1], d->in_size[0], d->batch, c.merged_a, p.ZAP, p.RA);
+  if (why == nullptr)
+    why = wgr::encode_map(&tmG, dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g, p.ZGP, p.RP);
+  if (why != nullptr) {
+    set_error("wgrad_rows: %s", why);
+    return HCU_ERR_CUDA;
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(wgr::wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wgr::kSmemLimit);
+    if (e != cudaSuccess) { set_error("wgrad_rows: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
+    attr = true;
+  }
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("HCU_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
+    if (dbg & 8)
+      fprintf(stderr, "wgrad_rows: P %d PG %d kinds %d RP %d RA %d ZC %d ZAP %d ZGP %d N %d tmem %d S %d smem %d grid %d x %d steps/cta %d merged %d/%d\n",
+              p.P, p.PG, c.kinds, p.RP, p.RA, p.ZC, p.ZAP, p.ZGP, p.NCOL, p.tmem_cols, p.S, p.smem_bytes, c.gx, c.kinds,
+              p.steps_per_cta, (int)c.merged_a, (int)c.merged_g);
+  }
+  wgr::wgrad_rows_kernel<<<dim3((unsigned)c.gx, (unsigned)c.kinds), wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, p);
+  HCU_CHECK_LAUNCH("wgrad_rows");
+  if (prof_env) {  // timing experiments: synchronous read-back of the stamps
+    long long h[16];
+    cudaDeviceSynchronize();
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "wgrad_rows prof (clk from entry): setup %lld | mma first-ready %lld second-ready %lld seg0-issued %lld (%lld steps) role-end %lld | epi accfull %lld tmem-read %lld flushed %lld | end %lld\n",
+            h[1] - h[0], h[2] - h[0], h[9] - h[0], h[3] - h[0], h[10], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0]);
+  }
+  return 0;
+}

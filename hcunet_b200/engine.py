@@ -332,6 +332,9 @@ class UnetEngine:
         self.use_tc = os.environ.get("HCUNET_TC", "1") != "0"
         self.use_ws = os.environ.get("HCUNET_WGRADWS", "1") != "0"      # warp-specialised weight gradient (8/16-channel levels)
         self.use_tc5 = os.environ.get("HCUNET_WGRAD5", "1") != "0"      # tcgen05 weight gradient on the channel-rich levels
+        # row-stacked tcgen05 weight gradient fed by TMA (channel-poor levels); input channel pitch up to ROWS_MAXCP
+        self.use_rows = os.environ.get("HCUNET_WGRADROWS", "1") != "0"
+        self.rows_maxcp = int(os.environ.get("HCUNET_WGRADROWS_MAXCP", "16"))
         self.use_batch = os.environ.get("HCUNET_BATCH", "1") != "0"      # batched packs / scatters (_StepCache)
         self.overlap_wgrad = os.environ.get("HCUNET_OVERLAP", "1") != "0"  # weight gradients on a side stream
         # BatchNorm-backward statistics of a block's conv1 computed in the epilogue of conv2's data gradient (its producer)
@@ -1018,11 +1021,16 @@ class UnetEngine:
         lib, cache = self.lib, self._cache
         f16 = self.use_tc and d.dtype_in == _lib.F16 and d.dtype_out == _lib.F16
         # channel-rich levels: tcgen05 kernel (M = 128 rows of Cin would be mostly padding below 32 input channels)
-        tc5 = bool(f16 and self.use_tc5 and d.in_cpitch >= 32 and
+        # channel-poor levels: rows of the image stacked on both MMA dimensions, TMA-fed (wgrad_rows.cu)
+        rows = bool(f16 and self.use_rows and max(d.in_cpitch, d.out_cpitch) <= self.rows_maxcp and
+                    lib.hcu_conv_wgrad_rows_supported(C.byref(d)))
+        tc5 = bool(f16 and not rows and self.use_tc5 and d.in_cpitch >= 32 and
                    lib.hcu_conv_wgrad_tc5_supported(C.byref(d)))
-        # 8/16-channel levels: warp-specialised mma.sync pipeline
-        ws = bool(f16 and not tc5 and self.use_ws and lib.hcu_conv_wgrad_ws_supported(C.byref(d)))
-        tc = bool(f16 and (tc5 or ws or lib.hcu_conv_wgrad_tc_supported(C.byref(d))))
+        # 8/16-channel levels the row kernel does not take: warp-specialised mma.sync pipeline
+        ws = bool(f16 and not rows and not tc5 and self.use_ws and lib.hcu_conv_wgrad_ws_supported(C.byref(d)))
+        tc = bool(f16 and (rows or tc5 or ws or lib.hcu_conv_wgrad_tc_supported(C.byref(d))))
+        acc_fn, acc_name = ((lib.hcu_conv_wgrad_rows_acc, "wgrad_rows") if rows else
+                            (lib.hcu_conv_wgrad_tc5_acc, "wgrad_tc5") if tc5 else (lib.hcu_conv_wgrad_ws_acc, "wgrad_ws"))
         nsplit = 1 if tc else ns
         if cache is not None and cache.ready and wname in cache.part_off and cache.scatter_jobs[wname][1:] == (nsplit, total):
             off = cache.part_off[wname]
@@ -1039,10 +1047,8 @@ class UnetEngine:
                 self._keep.extend(t for t in (a, b, isc, ish) if t is not None)  # alive until the streams join
             with torch.cuda.stream(side) if side is not None else _NullCtx():
                 _lib.note(*note)
-                if tc5 or ws:
-                    fn = lib.hcu_conv_wgrad_tc5_acc if tc5 else lib.hcu_conv_wgrad_ws_acc
-                    _lib.check(fn(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part), self._stream()),
-                               "wgrad_tc5" if tc5 else "wgrad_ws")
+                if rows or tc5 or ws:
+                    _lib.check(acc_fn(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part), self._stream()), acc_name)
                 elif tc:
                     _lib.check(lib.hcu_conv_wgrad_tc_acc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(part),
                                                          self._stream()), "wgrad_tc")
@@ -1053,11 +1059,9 @@ class UnetEngine:
         partial = torch.empty((nsplit, total), dtype=torch.float32, device=wref.device)
         gw = self._gview(wname)
         _lib.note(*note)
-        if tc5 or ws:
+        if rows or tc5 or ws:
             partial.zero_()
-            fn = lib.hcu_conv_wgrad_tc5_acc if tc5 else lib.hcu_conv_wgrad_ws_acc
-            _lib.check(fn(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial), self._stream()),
-                       "wgrad_tc5" if tc5 else "wgrad_ws")
+            _lib.check(acc_fn(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial), self._stream()), acc_name)
         elif tc:
             _lib.check(lib.hcu_conv_wgrad_tc(C.byref(d), _ptr(a), _ptr(isc), _ptr(ish), _ptr(b), _ptr(partial),
                                              self._stream()), "wgrad_tc")

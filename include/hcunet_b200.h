@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 20
+#define HCU_ABI_VERSION 21
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -270,6 +270,15 @@ int hcu_conv_wgrad_ws_acc(const HcuConvDesc* d, const void* a, const float* a_sc
 int hcu_conv_wgrad_tc5_supported(const HcuConvDesc* d);
 int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
                            float* wacc, void* stream);
+/* hcu_conv_wgrad_rows_*: tcgen05 flavour for the channel-POOR levels (8 ... 32 channels; wgrad_rows.cu), fed by TMA
+ * tensor-map loads: image rows are stacked on BOTH operand dimensions (M = 16 input rows x 8 channels, N = up to 14 dy rows
+ * x 8 channels, K = 16 z positions), so one MMA covers 224 pixels of three taps and the KY taps are block diagonals of the
+ * accumulator.  Valid 3D convolutions with >= 8 output z positions, no stride phases.
+ * Same contract as hcu_conv_wgrad_tc_acc (accumulates into a zeroed fp32 [taps][cin][cout]).
+ * Replaces: the weight-gradient half of autograd's conv backward for unet.py:246-257 on the first levels. */
+int hcu_conv_wgrad_rows_supported(const HcuConvDesc* d);
+int hcu_conv_wgrad_rows_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
+                            float* wacc, void* stream);
 
 /* ---- weight layout transforms -------------------------------------------------------------
  * Generic strided gather between a reference-layout parameter and a packed GEMM-B tensor

@@ -227,7 +227,8 @@ def test_conv_ks_fused_input_bn_relu_and_output_affine_and_classic_agreement():
 
 
 # ---- weight gradient on tensor cores (wgrad_mma.cu) ---------------------------------------------------------
-def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=False, use_tc5=False, use_ws=False):
+def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=False, use_tc5=False, use_ws=False,
+              use_rows=False):
     """x [N,Cin,...] activations (pre-transform), dy [N,Cout,...] -> dW [Cout,Cin,kx,ky,kz] fp32."""
     from hcunet_b200 import _lib
     from hcunet_b200.engine import conv_desc
@@ -254,6 +255,10 @@ def run_wgrad(x, dy, k, *, dil=(1, 1, 1), cpitch=None, in_affine=None, use_simt=
         assert lib.hcu_conv_wgrad_ws_supported(C.byref(d)) == 1
         wacc = torch.zeros((T * cin * cout,), device="cuda")
         _lib.check(lib.hcu_conv_wgrad_ws_acc(C.byref(d), P(xin), P(isc), P(ish), P(dyin), P(wacc), stream()), "wgrad_ws")
+    elif use_rows:
+        assert lib.hcu_conv_wgrad_rows_supported(C.byref(d)) == 1
+        wacc = torch.zeros((T * cin * cout,), device="cuda")
+        _lib.check(lib.hcu_conv_wgrad_rows_acc(C.byref(d), P(xin), P(isc), P(ish), P(dyin), P(wacc), stream()), "wgrad_rows")
     elif use_tc5:
         assert lib.hcu_conv_wgrad_tc5_supported(C.byref(d)) == 1
         wacc = torch.zeros((T * cin * cout,), device="cuda")   # the tcgen05 kernel accumulates into a zeroed buffer
@@ -326,6 +331,64 @@ def test_wgrad_ws_fused_input_bn_relu():
     ref = torch.nn.grad.conv3d_weight(a, (8, 8, 3, 3, 2), dy)
     got = run_wgrad(x, dy, (3, 3, 2), in_affine=(sc, sh), use_ws=True)
     assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)
+
+
+# ---- row-stacked tcgen05 weight gradient fed by TMA (wgrad_rows.cu, channel-poor levels) ---------------------
+WGR_CASES = [
+    (1, 8, 8, (10, 12, 9), (3, 3, 2), (1, 1, 1), None),        # one tile, one K group (8 z positions of 16)
+    (2, 4, 8, (9, 11, 17), (3, 3, 2), (1, 1, 1), 8),           # 4 of 8 input channels live (the first layer)
+    (1, 8, 8, (9, 40, 31), (3, 3, 1), (1, 1, 1), None),        # several row tiles, ragged last tile, z = 31 of 32
+    (2, 8, 8, (40, 60, 33), (3, 3, 2), (1, 1, 1), None),       # two K groups, merged rows shorter than the z reach
+    (2, 8, 8, (12, 37, 50), (3, 3, 2), (1, 1, 1), None),       # four K groups: 16-byte boxes
+    (1, 8, 16, (8, 22, 18), (3, 3, 2), (1, 1, 1), None),       # two dy planes: one per CTA kind
+    (2, 16, 16, (7, 24, 19), (3, 3, 1), (1, 1, 1), None),      # two input planes per CTA
+    (1, 16, 8, (20, 45, 31), (3, 3, 1), (1, 1, 1), None),
+    (1, 16, 32, (7, 19, 18), (3, 3, 2), (1, 1, 1), None),      # four dy planes
+    (1, 32, 32, (6, 21, 19), (3, 3, 1), (1, 1, 1), None),      # four input planes
+    (1, 8, 16, (12, 23, 16), (3, 3, 2), (2, 2, 1), None),      # dilation in x and y
+    (1, 8, 8, (9, 20, 24), (3, 3, 2), (1, 1, 2), None),        # dilation in z
+    (1, 16, 8, (5, 16, 17), (1, 1, 1), (1, 1, 1), None),       # 1x1: 16 rows per tile
+    (4, 8, 8, (30, 33, 20), (3, 3, 1), (1, 1, 1), None),       # CTAs whose step range crosses tiles and images
+]
+
+
+@pytest.mark.parametrize("case", WGR_CASES)
+def test_wgrad_rows_matches_fp32(case):
+    n, cin, cout, isz, k, dil, cp = case
+    g = torch.Generator().manual_seed(hash(case) % 10000 + 7)
+    osz = tuple(isz[i] - (k[i] - 1) * dil[i] for i in range(3))
+    x = h16(torch.randn((n, cin) + isz, generator=g))
+    dy = h16(torch.randn((n, cout) + osz, generator=g))
+    ref = torch.nn.grad.conv3d_weight(x, (cout, cin) + k, dy, dilation=dil)
+    got = run_wgrad(x, dy, k, dil=dil, cpitch=cp, use_rows=True)
+    assert not torch.isnan(got).any()
+    assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)   # exact fp16 products, fp32 accumulate
+
+
+def test_wgrad_rows_fused_input_bn_relu():
+    g = torch.Generator().manual_seed(31)
+    for cin, cout, isz, k in ((8, 8, (12, 19, 17), (3, 3, 2)), (16, 16, (9, 30, 20), (3, 3, 1))):
+        osz = tuple(isz[i] - k[i] + 1 for i in range(3))
+        x = h16(torch.randn((2, cin) + isz, generator=g))
+        dy = h16(torch.randn((2, cout) + osz, generator=g))
+        sc, sh = torch.rand(cin, generator=g) + 0.5, torch.randn(cin, generator=g) * 0.3
+        a = h16(F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1)))
+        ref = torch.nn.grad.conv3d_weight(a, (cout, cin) + k, dy)
+        got = run_wgrad(x, dy, k, in_affine=(sc, sh), use_rows=True)
+        assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)
+
+
+def test_wgrad_rows_refuses_what_it_cannot_take():
+    from hcunet_b200 import _lib
+    from hcunet_b200.engine import conv_desc
+
+    lib = _lib.load()
+    ok = conv_desc(_lib.F16, _lib.F16, 1, (9, 12, 20), 8, 0, 8, 8, (7, 10, 19), (7, 10, 19), 8, 0, 8, 1, (3, 3, 2), (1, 1, 1))
+    assert lib.hcu_conv_wgrad_rows_supported(C.byref(ok)) == 1
+    flat = conv_desc(_lib.F16, _lib.F16, 1, (30, 30, 1), 8, 0, 8, 8, (28, 28, 1), (28, 28, 1), 8, 0, 8, 1, (3, 3, 1), (1, 1, 1))
+    assert lib.hcu_conv_wgrad_rows_supported(C.byref(flat)) == 0      # 2D: no z rows to put on K
+    wide = conv_desc(_lib.F16, _lib.F16, 1, (9, 12, 20), 64, 0, 64, 64, (7, 10, 19), (7, 10, 19), 64, 0, 64, 1, (3, 3, 2), (1, 1, 1))
+    assert lib.hcu_conv_wgrad_rows_supported(C.byref(wide)) == 0      # channel-rich: wgrad_tc5.cu
 
 
 # ---- weight gradient on tcgen05 (wgrad_tc5.cu, channel-rich levels) -----------------------------------------

@@ -123,7 +123,13 @@ def main():
             dy = torch.randn((B,) + osz + (cout,), device="cuda").half()
             d = conv_desc(_lib.F16, _lib.F16, B, isz, cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, in_relu=1)
             wacc = torch.empty(T * cin * cout, device="cuda")
-            if kind == "wgrad5":
+            if kind == "wgradrows":
+                wacc.zero_()
+                if not lib.hcu_conv_wgrad_rows_supported(C.byref(d)):
+                    print(f"{kind:5s} {name:12s} unsupported")
+                    continue
+                fn = lambda: _lib.check(lib.hcu_conv_wgrad_rows_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
+            elif kind == "wgrad5":
                 wacc.zero_()
                 fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
             elif kind == "wgrad_auto":   # what the engine picks: warp-specialised kernel when it takes the shape
