@@ -54,6 +54,11 @@ struct Params {
   float* wacc;  // fp32 [taps][cin][cout], zeroed by the caller
   const float* a_scale;
   const float* a_shift;
+  // dy-side fusion (bnb): the dy operand is BatchNorm(+ReLU) backward applied to (g, y) while the tile is staged:
+  // dy = c1 * (bn(y) > 0 ? g : 0) + c2 * y + c3, rounded to fp16 exactly like hcu_bn_bwd_apply
+  const float* bn_scale;
+  const float* bn_shift;
+  const float* coef;       // [3][coef_c]
   long long* prof;         // HCU_ROWS_PROF: clock64 stamps of CTA (0, 0) (timing experiments only)
   int N, OX, OY, cin, cout;
   int P, PG;               // input channel planes (all in every CTA), dy channel planes per CTA (kinds = Po / PG on grid.y)
@@ -67,6 +72,7 @@ struct Params {
   int off_red, off_bar, smem_bytes;
   int n_ytiles, total_steps, steps_per_cta;
   int in_relu, zero_fill;
+  int bnb, off_y, coef_c, OZ;
   int dbg;                 // HCU_ROWS_DEBUG (timing experiments only): 1 = no MMA issue
   int nper;                // MMAs per x tap and step: (tz, input plane, dy plane, K group), K group fastest
   // per MMA of an x tap, read through the constant bank with a uniform index (the issuing warp runs on the uniform datapath):
@@ -126,14 +132,28 @@ struct MmaCtx {
   int f0, f1, span, lane;
   bool prof;
 };
+// descriptors as 32-bit halves: the high words (SBO, version) are loop invariants, the low words one add per MMA
+__device__ __forceinline__ void umma_f16_split(uint32_t d_tmem, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                               uint32_t accum) {
+  asm volatile(
+      "{\n.reg .pred p;\n.reg .b64 da, db;\n"
+      "setp.ne.b32 p, %6, 0;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}" ::"r"(d_tmem),
+      "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accum)
+      : "memory");
+}
+
 template <int KXT, int NPT>
 __device__ __forceinline__ void mma_role(const Params& p, const MmaCtx& c) {
   const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NCOL >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t lbo = (128u >> 4) << 16;
-  const uint64_t a_hi = desc_hi_mn((uint32_t)(p.ZAP * 16)) | lbo, b_hi = desc_hi_mn((uint32_t)(p.ZGP * 16)) | lbo;
-  const int S = p.S, span = c.span, dxs = p.dx;
+  const uint32_t ahi = (((uint32_t)(p.ZAP * 16) >> 4) & 0x3FFF) | (1u << 14), bhi = (((uint32_t)(p.ZGP * 16) >> 4) & 0x3FFF) | (1u << 14);
+  const int S = p.S, span = c.span;
   const int KX = KXT > 0 ? KXT : p.KX, nper = NPT > 0 ? NPT : p.nper;
-  const uint32_t ring16 = c.ring >> 4, slot16 = (uint32_t)p.slot_bytes >> 4;
+  const uint32_t ring16 = c.ring >> 4, slot16 = (uint32_t)p.slot_bytes >> 4, wrap16 = (uint32_t)S * slot16, dx16 = (uint32_t)p.dx * slot16;
+  const uint32_t end16 = ring16 + wrap16;
   const uint32_t tx_cols = (uint32_t)(p.KZ * p.P * p.PG * p.NCOL);
   const bool no_mma = (p.dbg & 1) != 0;
   constexpr int NP = NPT > 0 ? NPT : 1;
@@ -141,83 +161,91 @@ __device__ __forceinline__ void mma_role(const Params& p, const MmaCtx& c) {
   if (NPT > 0) {
 #pragma unroll
     for (int m = 0; m < NP; ++m) {
-      ta[m] = p.tab_a[m]; tb[m] = p.tab_b[m];
-      tt[m] = p.tab_t[m] & 0x7fffffffu; tp[m] = p.tab_t[m] >> 31;
+      ta[m] = p.tab_a[m] | lbo; tb[m] = p.tab_b[m] | lbo;
+      tt[m] = c.tmem_base + (p.tab_t[m] & 0x7fffffffu); tp[m] = p.tab_t[m] >> 31;
     }
   }
-  int w_idx = 0, seg = 0, f = c.f0;
-  uint32_t w_par = 0;
+  // ring position of the next slot to wait for (w_*) and of output plane i's first input plane (r_*): index + address
+  int w_idx = 0, r_idx = 0, seg = 0, f = c.f0;
+  uint32_t w_par = 0, w16 = ring16, r16 = ring16;
+  long long t_wait = 0, t_issue = 0, t_mark = 0;
   Segment s;
   while (next_segment(p, f, c.f1, s)) {
     if (seg > 0) {
       mbar_wait(c.bar_acce, (uint32_t)(seg - 1) & 1u);
       tc_fence_after();
     }
-    int ring_i = w_idx, have = 0;
+    for (int k = 1; k < span; ++k) {  // the first output needs `span` input planes
+      mbar_wait(c.bar_in + 8 * w_idx, w_par);
+      w16 += slot16;
+      if (++w_idx == S) { w_idx = 0; w_par ^= 1u; w16 = ring16; }
+    }
+    if (c.prof) t_mark = clock64();
     for (int i = 0; i < s.nout; ++i) {
-      for (; have < i + span; ++have) {  // slot i + span - 1 carries the newest input plane and dy plane i
-        mbar_wait(c.bar_in + 8 * w_idx, w_par);
-        if (++w_idx == S) { w_idx = 0; w_par ^= 1u; }
-      }
+      mbar_wait(c.bar_in + 8 * w_idx, w_par);  // slot i + span - 1: the newest input plane and dy plane i
+      const uint32_t gslot = w16;
+      w16 += slot16;
+      if (++w_idx == S) { w_idx = 0; w_par ^= 1u; w16 = ring16; }
       tc_fence_after();
-      if (c.prof && c.lane == 0 && seg == 0 && i == 0) p.prof[2] = clock64();
-      if (c.prof && c.lane == 0 && seg == 0 && i == 1) p.prof[9] = clock64();
-      int sg = ring_i + span - 1;
-      if (sg >= S) sg -= S;
-      const uint32_t gslot = ring16 + (uint32_t)sg * slot16;
+      if (c.prof) { const long long t = clock64(); t_wait += t - t_mark; t_mark = t; }
       const uint32_t acc0 = (uint32_t)i;
       if (elect_one()) {
         if (!no_mma) {
           if (KXT > 0 && NPT > 0) {
-            int sl = ring_i;
+            uint32_t blo[NP], acc[NP];
+#pragma unroll
+            for (int m = 0; m < NP; ++m) { blo[m] = gslot + tb[m]; acc[m] = acc0 | tp[m]; }
+            uint32_t a16 = r16;
 #pragma unroll
             for (int tx = 0; tx < KXT; ++tx) {
-              const uint32_t aslot = ring16 + (uint32_t)sl * slot16;
-              const uint32_t tbase = c.tmem_base + (uint32_t)tx * tx_cols;
 #pragma unroll
-              for (int m = 0; m < NP; ++m)
-                umma_f16(tbase + tt[m], a_hi | (uint64_t)(aslot + ta[m]), b_hi | (uint64_t)(gslot + tb[m]), idesc, acc0 | tp[m]);
-              sl += dxs;
-              if (sl >= S) sl -= S;
+              for (int m = 0; m < NP; ++m) umma_f16_split(tt[m] + (uint32_t)tx * tx_cols, a16 + ta[m], ahi, blo[m], bhi, idesc, acc[m]);
+              a16 += dx16;
+              if (a16 >= end16) a16 -= wrap16;
             }
           } else {
-            uint32_t tbase = c.tmem_base;
-            int sl = ring_i;
+            uint32_t tbase = c.tmem_base, a16 = r16;
             for (int tx = 0; tx < KX; ++tx) {
-              const uint32_t aslot = ring16 + (uint32_t)sl * slot16;
 #pragma unroll 2
               for (int m = 0; m < nper; ++m) {
                 const uint32_t t = p.tab_t[m];
-                umma_f16(tbase + (t & 0x7fffffffu), a_hi | (uint64_t)(aslot + p.tab_a[m]), b_hi | (uint64_t)(gslot + p.tab_b[m]), idesc,
-                         acc0 | (t >> 31));
+                umma_f16_split(tbase + (t & 0x7fffffffu), a16 + (p.tab_a[m] | lbo), ahi, gslot + (p.tab_b[m] | lbo), bhi, idesc, acc0 | (t >> 31));
               }
               tbase += tx_cols;
-              sl += dxs;
-              if (sl >= S) sl -= S;
+              a16 += dx16;
+              if (a16 >= end16) a16 -= wrap16;
             }
           }
         }
-        umma_commit(c.bar_e + 8 * ring_i);  // slot i: its input plane is not needed by later outputs, its dy plane was used earlier
-        if (i == s.nout - 1) {
-          int r = ring_i;
-          for (int k = 1; k < span; ++k) {
-            if (++r == S) r = 0;
-            umma_commit(c.bar_e + 8 * r);
-          }
-          umma_commit(c.bar_accf);
-        }
+        umma_commit(c.bar_e + 8 * r_idx);  // slot i: its input plane is not needed by later outputs, its dy plane was used earlier
       }
       __syncwarp();
-      if (++ring_i == S) ring_i = 0;
+      r16 += slot16;
+      if (++r_idx == S) { r_idx = 0; r16 = ring16; }
+      if (c.prof) { const long long t = clock64(); t_issue += t - t_mark; t_mark = t; }
     }
-    if (c.prof && c.lane == 0 && seg == 0) { p.prof[3] = clock64(); p.prof[10] = s.nout; }
+    // the segment's last span - 1 input planes, and the accumulators
+    if (elect_one()) {
+      for (int k = 1; k < span; ++k) {
+        umma_commit(c.bar_e + 8 * r_idx);
+        if (++r_idx == S) r_idx = 0;
+      }
+      umma_commit(c.bar_accf);
+    }
+    __syncwarp();
+    r_idx = w_idx; r16 = w16;  // (the elected lane's r_idx; every lane continues from the next segment's first slot)
+    if (c.prof && c.lane == 0 && seg == 0) { p.prof[3] = clock64(); p.prof[10] = s.nout; p.prof[2] = t_wait; p.prof[9] = t_issue; }
     ++seg;
   }
   if (c.prof && c.lane == 0) p.prof[4] = clock64();
 }
 
+// MODE: 0 = operands as stored, 1 = BatchNorm + ReLU on the input tiles, 2 = BatchNorm backward applied on the dy tiles
+// (compile-time: the transform warps keep their per-channel vectors in registers, one set per variant)
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ Params p) {
+wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmY,
+                  const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.S;
@@ -228,7 +256,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                  bar_acce = bar_accf + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (3 * S + 2));
   const uint32_t ring = smem_u32(smem);
-  const bool xf = p.a_scale != nullptr;
+  constexpr bool xf = MODE == 1, bnb = MODE == 2;
   const int span = (p.KX - 1) * p.dx + 1;
   const int kind = blockIdx.y;
   const int f0 = blockIdx.x * p.steps_per_cta, f1 = min(p.total_steps, f0 + p.steps_per_cta);
@@ -263,7 +291,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // =========================================== TMA PRODUCER ========================================
     int idx = 0, f = f0;
     uint32_t par = 1, dst = ring;
-    const uint32_t a_bytes = (uint32_t)(p.P * p.a_box_bytes), ag_bytes = a_bytes + (uint32_t)(p.PG * p.g_box_bytes);
+    const uint32_t a_bytes = (uint32_t)(p.P * p.a_box_bytes), ag_bytes = a_bytes + (uint32_t)((bnb ? 2 : 1) * p.PG * p.g_box_bytes);
     const int c0g = 8 * kind * p.PG;
     Segment s;
     while (next_segment(p, f, f1, s)) {
@@ -276,9 +304,13 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const bool with_g = j >= span - 1;
           mbar_expect_tx(bar, with_g ? ag_bytes : a_bytes);
           for (int pl = 0; pl < p.P; ++pl) tma_load_5d(dst + (uint32_t)(pl * p.a_plane_bytes), &tmA, 8 * pl, 0, y0, s.xb + j, s.n, bar);
-          if (with_g)
+          if (with_g) {
             for (int q = 0; q < p.PG; ++q)
               tma_load_5d(dst + (uint32_t)(p.off_g + q * p.g_plane_bytes), &tmG, c0g + 8 * q, 0, y0, s.xb + j - (span - 1), s.n, bar);
+            if (bnb)
+              for (int q = 0; q < p.PG; ++q)
+                tma_load_5d(dst + (uint32_t)(p.off_y + q * p.g_plane_bytes), &tmY, c0g + 8 * q, 0, y0, s.xb + j - (span - 1), s.n, bar);
+          }
         }
         __syncwarp();
         dst += (uint32_t)p.slot_bytes;
@@ -287,30 +319,69 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 13) {
     // =========================================== MMA ISSUER ==========================================
-    const MmaCtx c{tmem_base, ring, xf ? bar_r : bar_f, bar_e, bar_accf, bar_acce, f0, f1, span, lane, prof};
+    const MmaCtx c{tmem_base, ring, (xf || bnb) ? bar_r : bar_f, bar_e, bar_accf, bar_acce, f0, f1, span, lane, prof};
     if (p.KX == 3 && p.nper == 2) mma_role<3, 2>(p, c);
     else if (p.KX == 3 && p.nper == 4) mma_role<3, 4>(p, c);
     else if (p.KX == 3 && p.nper == 8) mma_role<3, 8>(p, c);
     else mma_role<0, 0>(p, c);
   } else if (warp >= 4) {
-    // =========================================== INPUT TRANSFORM =====================================
-    if (xf) {
+    // =========================================== OPERAND TRANSFORMS ===================================
+    if (xf || bnb) {
       const int xt = tid - 128;
-      const int plane = xt % p.P, c0 = xt / p.P, cstep = (32 * kXfWarps) / p.P;
-      const int nchunk = p.RA * p.ZAP;
-      float sc[8], sh[8];
+      // input side: thread -> (channel plane, chunk); dy side: thread -> (dy plane q, chunk)
+      const int pln = xf ? xt % p.P : xt % p.PG, c0 = xf ? xt / p.P : xt / p.PG, cstep = (32 * kXfWarps) / (xf ? p.P : p.PG);
+      const int nchunk = xf ? p.RA * p.ZAP : p.RP * p.ZGP;
+      float sc[8], sh[8], c1[bnb ? 8 : 1], c2[bnb ? 8 : 1], c3[bnb ? 8 : 1];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { sc[j] = p.a_scale[plane * 8 + j]; sh[j] = p.a_shift[plane * 8 + j]; }
+      for (int j = 0; j < 8; ++j) {
+        if (xf) { sc[j] = p.a_scale[pln * 8 + j]; sh[j] = p.a_shift[pln * 8 + j]; }
+        if (bnb) {
+          const int ch = (kind * p.PG + pln) * 8 + j;
+          sc[j] = p.bn_scale[ch]; sh[j] = p.bn_shift[ch];
+          c1[j] = p.coef[ch]; c2[j] = p.coef[p.coef_c + ch]; c3[j] = p.coef[2 * p.coef_c + ch];
+        }
+      }
       const int relu = p.in_relu;
+      const int row0 = c0 / p.ZGP, z0 = c0 - row0 * p.ZGP, rstep = cstep / p.ZGP, zstep = cstep - rstep * p.ZGP;  // dy side walk
       int sl = 0, f = f0;
       uint32_t par = 0;
       Segment s;
       while (next_segment(p, f, f1, s)) {
         const int nplanes = s.nout + span - 1;
+        const int rows_left = p.OY - s.yt * p.RP;  // dy rows of this tile inside the tensor
         for (int j = 0; j < nplanes; ++j) {
           mbar_wait(bar_f + 8 * sl, par);
-          uint4* tile = reinterpret_cast<uint4*>(smem + sl * p.slot_bytes + plane * p.a_plane_bytes);
-          for (int c = c0; c < nchunk; c += cstep) tile[c] = bn_relu8(tile[c], sc, sh, relu);
+          unsigned char* slot = smem + sl * p.slot_bytes;
+          if (xf) {
+            uint4* tile = reinterpret_cast<uint4*>(slot + pln * p.a_plane_bytes);
+            for (int c = c0; c < nchunk; c += cstep) tile[c] = bn_relu8(tile[c], sc, sh, relu);
+          }
+          if (bnb && j >= span - 1) {
+            uint4* gt = reinterpret_cast<uint4*>(slot + p.off_g + pln * p.g_plane_bytes);
+            const uint4* yt = reinterpret_cast<const uint4*>(slot + p.off_y + pln * p.g_plane_bytes);
+            int row = row0, z = z0;
+            for (int c = c0; c < nchunk; c += cstep) {
+              uint4 o = make_uint4(0u, 0u, 0u, 0u);  // positions outside the tensor stay zero (c3 must not leak into them)
+              if (z < p.OZ && row < rows_left) {
+                const uint4 gr = gt[c], yr = yt[c];
+                const __half2* gh = reinterpret_cast<const __half2*>(&gr);
+                const __half2* yh = reinterpret_cast<const __half2*>(&yr);
+                __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float2 yv = __half22float2(yh[k]);
+                  float2 gv = __half22float2(gh[k]);
+                  if (fmaf(yv.x, sc[2 * k], sh[2 * k]) <= 0.f) gv.x = 0.f;
+                  if (fmaf(yv.y, sc[2 * k + 1], sh[2 * k + 1]) <= 0.f) gv.y = 0.f;
+                  oh[k] = __floats2half2_rn(fmaf(c1[bnb ? 2 * k : 0], gv.x, fmaf(c2[bnb ? 2 * k : 0], yv.x, c3[bnb ? 2 * k : 0])),
+                                            fmaf(c1[bnb ? 2 * k + 1 : 0], gv.y, fmaf(c2[bnb ? 2 * k + 1 : 0], yv.y, c3[bnb ? 2 * k + 1 : 0])));
+                }
+              }
+              gt[c] = o;
+              z += zstep; row += rstep;
+              if (z >= p.ZGP) { z -= p.ZGP; ++row; }
+            }
+          }
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_r + 8 * sl);
@@ -424,7 +495,7 @@ static int env_int(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-static const char* configure(const HcuConvDesc* d, Config& c) {
+static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) {
   Params& p = c.p;
   memset(&p, 0, sizeof(p));
   if (d->dtype_in != HCU_F16 || d->dtype_out != HCU_F16) return "fp16 only";
@@ -491,7 +562,11 @@ static const char* configure(const HcuConvDesc* d, Config& c) {
   p.a_plane_bytes = round_up(p.a_box_bytes, 128);
   p.g_plane_bytes = round_up(p.g_box_bytes, 128);
   p.off_g = P * p.a_plane_bytes + 128;  // + what the last tap reads past a merged row
-  p.slot_bytes = p.off_g + p.PG * p.g_plane_bytes;
+  p.off_y = p.off_g + p.PG * p.g_plane_bytes;
+  p.slot_bytes = p.off_y + (bnb ? p.PG * p.g_plane_bytes : 0);
+  p.bnb = bnb ? 1 : 0;
+  p.OZ = OZ;
+  p.coef_c = d->out_cpitch;
   const int red_bytes = 4 * p.KX * p.KY * p.KZ * P * 8 * p.PG * 8 * 4;  // one copy per epilogue warp
   p.nper = p.KZ * P * p.PG * p.ZC;
   if (p.nper > kMaxPer) return "too many MMAs per step";
@@ -587,35 +662,43 @@ extern "C" int hcu_conv_wgrad_rows_supported(const HcuConvDesc* d) {
   return wgr::configure(d, c) == nullptr ? 1 : 0;
 }
 
-extern "C" int hcu_conv_wgrad_rows_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
-                                       const void* dy, float* wacc, void* stream) {
+static int wgrad_rows_launch(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
+                             const void* y, const float* bn_scale, const float* bn_shift, const float* coef, float* wacc, void* stream) {
   HCU_CHECK_ARG(d && a && dy && wacc, "wgrad_rows: null pointer");
   HCU_CHECK_ARG((a_scale == nullptr) == (a_shift == nullptr), "wgrad_rows: a_scale/a_shift must come together");
+  const bool bnb = y != nullptr;
+  HCU_CHECK_ARG(!bnb || (bn_scale && bn_shift && coef), "wgrad_rows: the fused BatchNorm backward needs scale, shift and coef");
+  HCU_CHECK_ARG(!bnb || a_scale == nullptr, "wgrad_rows: the fused BatchNorm backward takes an untransformed input (the first layer)");
   wgr::Config c;
-  const char* why = wgr::configure(d, c);
+  const char* why = wgr::configure(d, c, bnb);
   if (why != nullptr) {
     set_error("wgrad_rows: unsupported descriptor (%s)", why);
     return HCU_ERR_UNSUPPORTED;
   }
   wgr::Params& p = c.p;
   p.wacc = wacc; p.a_scale = a_scale; p.a_shift = a_shift; p.in_relu = d->in_relu;
+  p.bn_scale = bn_scale; p.bn_shift = bn_shift; p.coef = coef;
   static const int dbg_env = wgr::env_int("HCU_ROWS_DEBUG", 0);
   p.dbg = dbg_env;
   static const int prof_env = wgr::env_int("HCU_ROWS_PROF", 0);
   static long long* prof_buf = nullptr;
   if (prof_env && prof_buf == nullptr) cudaMalloc(&prof_buf, 16 * sizeof(long long));
   p.prof = prof_env ? prof_buf : nullptr;
-  CUtensorMap tmA, tmG;
+  CUtensorMap tmA, tmG, tmY;
   why = wgr::encode_map(&tmA, a, d->in_cpitch, d->in_size[2], d->in_size[1], d->in_size[0], d->batch, c.merged_a, p.ZAP, p.RA);
   if (why == nullptr)
     why = wgr::encode_map(&tmG, dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g, p.ZGP, p.RP);
+  if (why == nullptr)
+    why = wgr::encode_map(&tmY, bnb ? y : dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g, p.ZGP, p.RP);
   if (why != nullptr) {
     set_error("wgrad_rows: %s", why);
     return HCU_ERR_CUDA;
   }
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(wgr::wgrad_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wgr::kSmemLimit);
+    cudaError_t e = cudaFuncSetAttribute(wgr::wgrad_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgr::kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgr::wgrad_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgr::kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgr::wgrad_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgr::kSmemLimit);
     if (e != cudaSuccess) { set_error("wgrad_rows: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
     attr = true;
   }
@@ -623,18 +706,33 @@ extern "C" int hcu_conv_wgrad_rows_acc(const HcuConvDesc* d, const void* a, cons
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("HCU_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     if (dbg & 8)
-      fprintf(stderr, "wgrad_rows: P %d PG %d kinds %d RP %d RA %d ZC %d ZAP %d ZGP %d N %d tmem %d S %d smem %d grid %d x %d steps/cta %d merged %d/%d\n",
+      fprintf(stderr, "wgrad_rows: P %d PG %d kinds %d RP %d RA %d ZC %d ZAP %d ZGP %d N %d tmem %d S %d smem %d grid %d x %d steps/cta %d merged %d/%d bnb %d\n",
               p.P, p.PG, c.kinds, p.RP, p.RA, p.ZC, p.ZAP, p.ZGP, p.NCOL, p.tmem_cols, p.S, p.smem_bytes, c.gx, c.kinds,
-              p.steps_per_cta, (int)c.merged_a, (int)c.merged_g);
+              p.steps_per_cta, (int)c.merged_a, (int)c.merged_g, p.bnb);
   }
-  wgr::wgrad_rows_kernel<<<dim3((unsigned)c.gx, (unsigned)c.kinds), wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, p);
+  const dim3 grid((unsigned)c.gx, (unsigned)c.kinds);
+  if (bnb) wgr::wgrad_rows_kernel<2><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
+  else if (a_scale != nullptr) wgr::wgrad_rows_kernel<1><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
+  else wgr::wgrad_rows_kernel<0><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
   HCU_CHECK_LAUNCH("wgrad_rows");
   if (prof_env) {  // timing experiments: synchronous read-back of the stamps
     long long h[16];
     cudaDeviceSynchronize();
     cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "wgrad_rows prof (clk from entry): setup %lld | mma first-ready %lld second-ready %lld seg0-issued %lld (%lld steps) role-end %lld | epi accfull %lld tmem-read %lld flushed %lld | end %lld\n",
-            h[1] - h[0], h[2] - h[0], h[9] - h[0], h[3] - h[0], h[10], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0]);
+    fprintf(stderr, "wgrad_rows prof (clk from entry): setup %lld | mma seg0: waiting %lld issuing %lld, done at %lld (%lld steps) role-end %lld | epi accfull %lld tmem-read %lld flushed %lld | end %lld\n",
+            h[1] - h[0], h[2], h[9], h[3] - h[0], h[10], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0]);
   }
   return 0;
+}
+
+extern "C" int hcu_conv_wgrad_rows_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
+                                       const void* dy, float* wacc, void* stream) {
+  return wgrad_rows_launch(d, a, a_scale, a_shift, dy, nullptr, nullptr, nullptr, nullptr, wacc, stream);
+}
+
+extern "C" int hcu_conv_wgrad_rows_bnb_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift,
+                                           const void* g, const void* y, const float* bn_scale, const float* bn_shift,
+                                           const float* coef, float* wacc, void* stream) {
+  HCU_CHECK_ARG(y != nullptr, "wgrad_rows_bnb: null pointer");
+  return wgrad_rows_launch(d, a, a_scale, a_shift, g, y, bn_scale, bn_shift, coef, wacc, stream);
 }

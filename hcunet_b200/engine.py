@@ -335,6 +335,8 @@ class UnetEngine:
         # row-stacked tcgen05 weight gradient fed by TMA (channel-poor levels); input channel pitch up to ROWS_MAXCP
         self.use_rows = os.environ.get("HCUNET_WGRADROWS", "1") != "0"
         self.rows_maxcp = int(os.environ.get("HCUNET_WGRADROWS_MAXCP", "16"))
+        self.rows_maxcp_out = int(os.environ.get("HCUNET_WGRADROWS_MAXCP_OUT", "16"))
+        self.fuse_apply = os.environ.get("HCUNET_FUSE_APPLY", "1") != "0"   # BN-backward apply inside the first layer's weight gradient
         self.use_batch = os.environ.get("HCUNET_BATCH", "1") != "0"      # batched packs / scatters (_StepCache)
         self.overlap_wgrad = os.environ.get("HCUNET_OVERLAP", "1") != "0"  # weight gradients on a side stream
         # BatchNorm-backward statistics of a block's conv1 computed in the epilogue of conv2's data gradient (its producer)
@@ -853,13 +855,22 @@ class UnetEngine:
                                                         C.byref(fin), st), "bn_bwd_stats_fin")
                 else:   # the data gradient that produced `dcur` computed these statistics in its epilogue
                     sums, coef, fin, dgamma, dbeta, dbias = ctx
+                grads[g.bn + ".weight"], grads[g.bn + ".bias"], grads[g.name + ".bias"] = dgamma, dbeta, dbias
+                if (g.first and not need_dx and argmax is None and self.tap is None and self.fuse_apply
+                        and dcur_dt == _lib.F16 and act_dtype == torch.float16
+                        and self._wgrad_conv(g, a_in, a_cp, a_xf, adt, dcur, adt, B, params[g.name + ".weight"], probe=True)):
+                    # nobody needs this layer's data gradient: BatchNorm backward's apply pass is fused into the staging of
+                    # the weight gradient's dy operand (wgrad_rows.cu), the gradient tensor is never written
+                    grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, a_cp, a_xf, adt, dcur, adt, B, params[g.name + ".weight"],
+                                                                 bnb=(y, vec[2], vec[3], coef))
+                    dcur = None
+                    continue
                 dy = torch.empty((B, npix // B, g.cout_t), dtype=act_dtype, device=dev)
                 _lib.note(g.name, 3 * npix * g.cout_t * esz, 0)
                 _lib.check(lib.hcu_bn_bwd_apply(_ptr(dcur), dcur_dt, _ptr(y), adt, _ptr(dy), adt, npix, g.cout_t,
                                                 _ptr(vec[2]), _ptr(vec[3]), 1, _ptr(coef), _ptr(pool_arg),
                                                 C.byref(pool_geom) if pool_geom is not None else None, st), "bn_bwd_apply")
                 self._tap(g.name + ".dy", dy, g.cout_t, g.out_sz)
-                grads[g.bn + ".weight"], grads[g.bn + ".bias"], grads[g.name + ".bias"] = dgamma, dbeta, dbias
                 grads[g.name + ".weight"] = self._wgrad_conv(g, a_in, a_cp, a_xf, adt, dy, adt, B,
                                                              params[g.name + ".weight"])
                 if g.first and not need_dx:
@@ -998,7 +1009,7 @@ class UnetEngine:
                                            _ptr(out), self._stream()), "colsum")
         return out
 
-    def _wgrad_conv(self, g: ConvGeom, a_in, a_cp, a_xf, a_dt, dy, dy_dt, B, wref, dy_cp=None):
+    def _wgrad_conv(self, g: ConvGeom, a_in, a_cp, a_xf, a_dt, dy, dy_dt, B, wref, dy_cp=None, bnb=None, probe=False):
         T = g.taps[0] * g.taps[1] * g.taps[2]
         eg, ecin, ecout, bd = self._eff(g, a_dt == _lib.F16 and dy_dt == _lib.F16)
         d = conv_desc(a_dt, dy_dt, B, g.in_sz, a_cp, 0, ecin, ecin, g.out_sz, g.out_sz, dy_cp or g.cout_t, 0, ecout,
@@ -1011,9 +1022,19 @@ class UnetEngine:
         nin = B * g.in_sz[0] * g.in_sz[1] * g.in_sz[2] * g.cin_t
         note = (g.name, (nin + m * g.cout_t) * esz, 2 * m * T * g.cin_g * g.cout_g * g.groups)
         isc, ish = (a_xf[0], a_xf[1]) if a_xf is not None else (None, None)
-        return self._wgrad_dispatch(g.name + ".weight", wref, d, a_in, isc, ish, dy, self._wm_conv_fwd(g, bd), total, ns, note)
+        if probe:   # would the row-stacked kernel (the one with the fused BatchNorm-backward apply) take this layer?
+            return self._rows_takes(d)
+        if bnb is not None:  # the fused launch also reads y: the apply pass it replaces read g and y and wrote dy
+            note = (note[0], note[1] + m * g.cout_t * esz, note[2])
+        return self._wgrad_dispatch(g.name + ".weight", wref, d, a_in, isc, ish, dy, self._wm_conv_fwd(g, bd), total, ns, note,
+                                    bnb=bnb)
 
-    def _wgrad_dispatch(self, wname, wref, d, a, isc, ish, b, wm, total, ns, note):
+    def _rows_takes(self, d) -> bool:
+        f16 = self.use_tc and d.dtype_in == _lib.F16 and d.dtype_out == _lib.F16
+        return bool(f16 and self.use_rows and d.in_cpitch <= self.rows_maxcp and d.out_cpitch <= self.rows_maxcp_out and
+                    self.lib.hcu_conv_wgrad_rows_supported(C.byref(d)))
+
+    def _wgrad_dispatch(self, wname, wref, d, a, isc, ish, b, wm, total, ns, note, bnb=None):
         """Weight gradient of one conv: tensor-core kernel when it takes the descriptor, else the FFMA split-K kernel;
         result scattered into the reference layout.  With a ready step cache the kernel runs on the side stream
         (overlapping the data-gradient chain), accumulates into the persistent workspace and the scatter is left to
@@ -1022,8 +1043,8 @@ class UnetEngine:
         f16 = self.use_tc and d.dtype_in == _lib.F16 and d.dtype_out == _lib.F16
         # channel-rich levels: tcgen05 kernel (M = 128 rows of Cin would be mostly padding below 32 input channels)
         # channel-poor levels: rows of the image stacked on both MMA dimensions, TMA-fed (wgrad_rows.cu)
-        rows = bool(f16 and self.use_rows and max(d.in_cpitch, d.out_cpitch) <= self.rows_maxcp and
-                    lib.hcu_conv_wgrad_rows_supported(C.byref(d)))
+        rows = self._rows_takes(d)
+        assert rows or bnb is None
         tc5 = bool(f16 and not rows and self.use_tc5 and d.in_cpitch >= 32 and
                    lib.hcu_conv_wgrad_tc5_supported(C.byref(d)))
         # 8/16-channel levels the row kernel does not take: warp-specialised mma.sync pipeline
@@ -1031,6 +1052,12 @@ class UnetEngine:
         tc = bool(f16 and (rows or tc5 or ws or lib.hcu_conv_wgrad_tc_supported(C.byref(d))))
         acc_fn, acc_name = ((lib.hcu_conv_wgrad_rows_acc, "wgrad_rows") if rows else
                             (lib.hcu_conv_wgrad_tc5_acc, "wgrad_tc5") if tc5 else (lib.hcu_conv_wgrad_ws_acc, "wgrad_ws"))
+        if bnb is not None:
+            by, bsc, bsh, bcoef = bnb
+
+            def acc_fn(dd, pa, psc, psh, pb, pacc, stream):   # noqa: F811 -- same call shape as the plain kernels
+                return lib.hcu_conv_wgrad_rows_bnb_acc(dd, pa, psc, psh, pb, _ptr(by), _ptr(bsc), _ptr(bsh), _ptr(bcoef), pacc, stream)
+            acc_name = "wgrad_rows_bnb"
         nsplit = 1 if tc else ns
         if cache is not None and cache.ready and wname in cache.part_off and cache.scatter_jobs[wname][1:] == (nsplit, total):
             off = cache.part_off[wname]

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 21
+#define HCU_ABI_VERSION 22
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -279,6 +279,15 @@ int hcu_conv_wgrad_tc5_acc(const HcuConvDesc* d, const void* a, const float* a_s
 int hcu_conv_wgrad_rows_supported(const HcuConvDesc* d);
 int hcu_conv_wgrad_rows_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
                             float* wacc, void* stream);
+/* Same kernel with hcu_bn_bwd_apply fused into the staging of its dy operand: dy = c1 * (bn(y) > 0 ? g : 0) + c2 * y + c3 is
+ * computed (fp32, rounded to fp16 like the stand-alone pass) on the landed (g, y) tiles and never written to memory.  For a
+ * layer whose data gradient nobody needs (the FIRST conv of the net) this removes the apply pass: 2 reads + 1 write of the
+ * layer's gradient tensor and the re-read by the weight gradient.  bn_scale / bn_shift: the layer's BatchNorm as scale / shift
+ * (the ReLU mask), coef: hcu_bn_bwd_finalize's [3][out_cpitch].
+ * Replaces: BatchNorm + ReLU backward followed by the conv weight gradient (autograd of unet.py:259-265 / 246-250). */
+int hcu_conv_wgrad_rows_bnb_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* g,
+                                const void* y, const float* bn_scale, const float* bn_shift, const float* coef, float* wacc,
+                                void* stream);
 
 /* ---- weight layout transforms -------------------------------------------------------------
  * Generic strided gather between a reference-layout parameter and a packed GEMM-B tensor

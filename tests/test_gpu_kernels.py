@@ -378,6 +378,39 @@ def test_wgrad_rows_fused_input_bn_relu():
         assert rel_l2(got, ref) <= 1e-5, rel_l2(got, ref)
 
 
+@pytest.mark.parametrize("case", [(2, 4, 8, (9, 27, 20), (3, 3, 2), 8), (1, 8, 8, (8, 33, 31), (3, 3, 1), None),
+                                  (1, 16, 16, (7, 20, 18), (3, 3, 2), None)])
+def test_wgrad_rows_with_fused_bn_backward_apply_equals_the_two_launches(case):
+    """dy = c1 * (bn(y) > 0 ? g : 0) + c2 * y + c3 computed on the staged tiles (hcu_conv_wgrad_rows_bnb_acc) against
+    hcu_bn_bwd_apply followed by hcu_conv_wgrad_rows_acc: the same fp16 dy, the same MMAs -> the same bits."""
+    from hcunet_b200 import _lib
+    from hcunet_b200.engine import conv_desc
+
+    lib = _lib.load()
+    n, cin, cout, isz, k, cp = case
+    gen = torch.Generator().manual_seed(41)
+    osz = tuple(isz[i] - k[i] + 1 for i in range(3))
+    x = to_cl(h16(torch.randn((n, cin) + isz, generator=gen)), cp or cin)
+    g = to_cl(h16(torch.randn((n, cout) + osz, generator=gen)))
+    y = to_cl(h16(torch.randn((n, cout) + osz, generator=gen)))
+    sc = (torch.rand(cout, generator=gen) + 0.5).cuda(); sh = (torch.randn(cout, generator=gen) * 0.3).cuda()
+    coef = torch.randn(3, cout, generator=gen).cuda().contiguous()
+    npix = n * osz[0] * osz[1] * osz[2]
+    d = conv_desc(_lib.F16, _lib.F16, n, isz, cp or cin, 0, cin, cin, osz, osz, cout, 0, cout, 1, k, (1, 1, 1))
+    T = k[0] * k[1] * k[2]
+    dy = torch.empty_like(g)
+    _lib.check(lib.hcu_bn_bwd_apply(P(g), _lib.F16, P(y), _lib.F16, P(dy), _lib.F16, npix, cout, P(sc), P(sh), 1, P(coef), None, None,
+                                    stream()), "bn_bwd_apply")
+    two = torch.zeros(T * cin * cout, device="cuda")
+    _lib.check(lib.hcu_conv_wgrad_rows_acc(C.byref(d), P(x), None, None, P(dy), P(two), stream()), "wgrad_rows")
+    one = torch.zeros(T * cin * cout, device="cuda")
+    _lib.check(lib.hcu_conv_wgrad_rows_bnb_acc(C.byref(d), P(x), None, None, P(g), P(y), P(sc), P(sh), P(coef), P(one), stream()),
+               "wgrad_rows_bnb")
+    torch.cuda.synchronize()
+    assert torch.isfinite(one).all()
+    assert rel_l2(one, two) <= 1e-6, rel_l2(one, two)   # same products; the fp32 atomics land in another order
+
+
 def test_wgrad_rows_refuses_what_it_cannot_take():
     from hcunet_b200 import _lib
     from hcunet_b200.engine import conv_desc

@@ -129,6 +129,13 @@ def main():
                     print(f"{kind:5s} {name:12s} unsupported")
                     continue
                 fn = lambda: _lib.check(lib.hcu_conv_wgrad_rows_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
+            elif kind == "wgradrowsbnb":   # BatchNorm-backward apply fused into the dy staging (first layer: untransformed input)
+                wacc.zero_()
+                yy = torch.randn_like(dy)
+                bsc, bsh = torch.rand(cout, device="cuda") + 0.5, torch.randn(cout, device="cuda") * 0.3
+                coef = torch.randn(3, cout, device="cuda")
+                fn = lambda: _lib.check(lib.hcu_conv_wgrad_rows_bnb_acc(C.byref(d), P(x), None, None, P(dy), P(yy), P(bsc), P(bsh), P(coef),
+                                                                        P(wacc), st))
             elif kind == "wgrad5":
                 wacc.zero_()
                 fn = lambda: _lib.check(lib.hcu_conv_wgrad_tc5_acc(C.byref(d), P(x), P(sc), P(sh), P(dy), P(wacc), st))
