@@ -73,6 +73,10 @@ struct Params {
   int n_ytiles, total_steps, steps_per_cta;
   int in_relu, zero_fill;
   int bnb, off_y, coef_c, OZ;
+  // interleaved mode (il, P > 1): the channel planes of a row are M / N groups of ONE MMA.  The natural [row][z][C] tile lands in
+  // a staging area (one TMA box with a 16 P-byte inner run) and the transform warps re-lay it as [row][plane][z][8 channels]
+  // (+ BatchNorm + ReLU on the input side): M = 128 = (16 / P rows) x P planes x 8 channels, N = RP x PG x 8.
+  int il, sbo_a, sbo_b, off_sa, off_sg, ZOA, ZOG, tx_cols;
   int dbg;                 // HCU_ROWS_DEBUG (timing experiments only): 1 = no MMA issue
   int nper;                // MMAs per x tap and step: (tz, input plane, dy plane, K group), K group fastest
   // per MMA of an x tap, read through the constant bank with a uniform index (the issuing warp runs on the uniform datapath):
@@ -149,12 +153,12 @@ template <int KXT, int NPT>
 __device__ __forceinline__ void mma_role(const Params& p, const MmaCtx& c) {
   const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(p.NCOL >> 3) << 17) | ((128u >> 4) << 24);
   const uint32_t lbo = (128u >> 4) << 16;
-  const uint32_t ahi = (((uint32_t)(p.ZAP * 16) >> 4) & 0x3FFF) | (1u << 14), bhi = (((uint32_t)(p.ZGP * 16) >> 4) & 0x3FFF) | (1u << 14);
+  const uint32_t ahi = (((uint32_t)p.sbo_a >> 4) & 0x3FFF) | (1u << 14), bhi = (((uint32_t)p.sbo_b >> 4) & 0x3FFF) | (1u << 14);
   const int S = p.S, span = c.span;
   const int KX = KXT > 0 ? KXT : p.KX, nper = NPT > 0 ? NPT : p.nper;
   const uint32_t ring16 = c.ring >> 4, slot16 = (uint32_t)p.slot_bytes >> 4, wrap16 = (uint32_t)S * slot16, dx16 = (uint32_t)p.dx * slot16;
   const uint32_t end16 = ring16 + wrap16;
-  const uint32_t tx_cols = (uint32_t)(p.KZ * p.P * p.PG * p.NCOL);
+  const uint32_t tx_cols = (uint32_t)p.tx_cols;
   const bool no_mma = (p.dbg & 1) != 0;
   constexpr int NP = NPT > 0 ? NPT : 1;
   uint32_t ta[NP], tb[NP], tt[NP], tp[NP];
@@ -171,10 +175,6 @@ __device__ __forceinline__ void mma_role(const Params& p, const MmaCtx& c) {
   long long t_wait = 0, t_issue = 0, t_mark = 0;
   Segment s;
   while (next_segment(p, f, c.f1, s)) {
-    if (seg > 0) {
-      mbar_wait(c.bar_acce, (uint32_t)(seg - 1) & 1u);
-      tc_fence_after();
-    }
     for (int k = 1; k < span; ++k) {  // the first output needs `span` input planes
       mbar_wait(c.bar_in + 8 * w_idx, w_par);
       w16 += slot16;
@@ -188,7 +188,7 @@ __device__ __forceinline__ void mma_role(const Params& p, const MmaCtx& c) {
       if (++w_idx == S) { w_idx = 0; w_par ^= 1u; w16 = ring16; }
       tc_fence_after();
       if (c.prof) { const long long t = clock64(); t_wait += t - t_mark; t_mark = t; }
-      const uint32_t acc0 = (uint32_t)i;
+      const uint32_t acc0 = (uint32_t)(i | seg);  // the accumulators run on across row tiles: (r, r') means the same tap everywhere
       if (elect_one()) {
         if (!no_mma) {
           if (KXT > 0 && NPT > 0) {
@@ -224,23 +224,25 @@ __device__ __forceinline__ void mma_role(const Params& p, const MmaCtx& c) {
       if (++r_idx == S) { r_idx = 0; r16 = ring16; }
       if (c.prof) { const long long t = clock64(); t_issue += t - t_mark; t_mark = t; }
     }
-    // the segment's last span - 1 input planes, and the accumulators
+    // the segment's last span - 1 input planes
     if (elect_one()) {
       for (int k = 1; k < span; ++k) {
         umma_commit(c.bar_e + 8 * r_idx);
         if (++r_idx == S) r_idx = 0;
       }
-      umma_commit(c.bar_accf);
     }
     __syncwarp();
     r_idx = w_idx; r16 = w16;  // (the elected lane's r_idx; every lane continues from the next segment's first slot)
     if (c.prof && c.lane == 0 && seg == 0) { p.prof[3] = clock64(); p.prof[10] = s.nout; p.prof[2] = t_wait; p.prof[9] = t_issue; }
     ++seg;
   }
+  if (elect_one()) umma_commit(c.bar_accf);  // every MMA of this CTA: the epilogue runs once
+  __syncwarp();
   if (c.prof && c.lane == 0) p.prof[4] = clock64();
 }
 
-// MODE: 0 = operands as stored, 1 = BatchNorm + ReLU on the input tiles, 2 = BatchNorm backward applied on the dy tiles
+// MODE: 0 = operands as stored, 1 = BatchNorm + ReLU on the input tiles, 2 = BatchNorm backward applied on the dy tiles,
+// 3 = interleaved channel planes (re-layout of both tiles, + BatchNorm + ReLU on the input side when a_scale is given)
 // (compile-time: the transform warps keep their per-channel vectors in registers, one set per variant)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -256,11 +258,12 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                  bar_acce = bar_accf + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + p.off_bar + 8 * (3 * S + 2));
   const uint32_t ring = smem_u32(smem);
-  constexpr bool xf = MODE == 1, bnb = MODE == 2;
+  constexpr bool il = MODE == 3, bnb = MODE == 2;
+  const bool xf = MODE == 1 || (il && p.a_scale != nullptr);
   const int span = (p.KX - 1) * p.dx + 1;
   const int kind = blockIdx.y;
   const int f0 = blockIdx.x * p.steps_per_cta, f1 = min(p.total_steps, f0 + p.steps_per_cta);
-  const int red_n = p.KX * p.KY * p.KZ * p.P * 8 * p.PG * 8;
+  const int red_n = p.KY * (MODE == 3 ? p.P * p.PG : 1) * 64;  // one accumulator's (ty, ci, co) block
 
   if (p.zero_fill) {  // merged rows shorter than the z reach of the last tap: the bytes read past a tile must be finite
     uint4* q = reinterpret_cast<uint4*>(smem);
@@ -291,7 +294,8 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // =========================================== TMA PRODUCER ========================================
     int idx = 0, f = f0;
     uint32_t par = 1, dst = ring;
-    const uint32_t a_bytes = (uint32_t)(p.P * p.a_box_bytes), ag_bytes = a_bytes + (uint32_t)((bnb ? 2 : 1) * p.PG * p.g_box_bytes);
+    const uint32_t a_bytes = il ? (uint32_t)p.a_box_bytes : (uint32_t)(p.P * p.a_box_bytes);
+    const uint32_t ag_bytes = a_bytes + (il ? (uint32_t)p.g_box_bytes : (uint32_t)((bnb ? 2 : 1) * p.PG * p.g_box_bytes));
     const int c0g = 8 * kind * p.PG;
     Segment s;
     while (next_segment(p, f, f1, s)) {
@@ -303,6 +307,10 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t bar = bar_f + 8 * idx;
           const bool with_g = j >= span - 1;
           mbar_expect_tx(bar, with_g ? ag_bytes : a_bytes);
+          if (il) {  // one box per tile: all channel planes of the rows, [row][z][C]
+            tma_load_5d(dst + (uint32_t)p.off_sa, &tmA, 0, 0, y0, s.xb + j, s.n, bar);
+            if (with_g) tma_load_5d(dst + (uint32_t)p.off_sg, &tmG, c0g, 0, y0, s.xb + j - (span - 1), s.n, bar);
+          } else {
           for (int pl = 0; pl < p.P; ++pl) tma_load_5d(dst + (uint32_t)(pl * p.a_plane_bytes), &tmA, 8 * pl, 0, y0, s.xb + j, s.n, bar);
           if (with_g) {
             for (int q = 0; q < p.PG; ++q)
@@ -310,6 +318,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (bnb)
               for (int q = 0; q < p.PG; ++q)
                 tma_load_5d(dst + (uint32_t)(p.off_y + q * p.g_plane_bytes), &tmY, c0g + 8 * q, 0, y0, s.xb + j - (span - 1), s.n, bar);
+          }
           }
         }
         __syncwarp();
@@ -319,14 +328,66 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 13) {
     // =========================================== MMA ISSUER ==========================================
-    const MmaCtx c{tmem_base, ring, (xf || bnb) ? bar_r : bar_f, bar_e, bar_accf, bar_acce, f0, f1, span, lane, prof};
+    const MmaCtx c{tmem_base, ring, (xf || bnb || il) ? bar_r : bar_f, bar_e, bar_accf, bar_acce, f0, f1, span, lane, prof};
     if (p.KX == 3 && p.nper == 2) mma_role<3, 2>(p, c);
     else if (p.KX == 3 && p.nper == 4) mma_role<3, 4>(p, c);
     else if (p.KX == 3 && p.nper == 8) mma_role<3, 8>(p, c);
     else mma_role<0, 0>(p, c);
   } else if (warp >= 4) {
     // =========================================== OPERAND TRANSFORMS ===================================
-    if (xf || bnb) {
+    if (il) {
+      // staging [row][z][plane] (chunk e = (row * Z + z) * planes + plane) -> operand [row][plane][z]: thread t owns the chunks
+      // e = t, t + 256, ...: its plane is fixed (256 % planes == 0), (row, z) walk incrementally
+      const int xt = tid - 128;
+      const int P = p.P, PG = p.PG;
+      const int pla = xt % P, plg = xt % PG;
+      const int na = p.RA * p.ZAP * P, ng = p.RP * p.ZGP * PG;
+      const int sa = 256 / P, sg = 256 / PG;                       // pixels advanced per 256 chunks
+      const int a_r0 = (xt / P) / p.ZAP, a_z0 = (xt / P) - a_r0 * p.ZAP, a_rs = sa / p.ZAP, a_zs = sa - a_rs * p.ZAP;
+      const int g_r0 = (xt / PG) / p.ZGP, g_z0 = (xt / PG) - g_r0 * p.ZGP, g_rs = sg / p.ZGP, g_zs = sg - g_rs * p.ZGP;
+      float sc[8], sh[8];
+      if (xf) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = p.a_scale[pla * 8 + j]; sh[j] = p.a_shift[pla * 8 + j]; }
+      }
+      const int relu = p.in_relu;
+      int sl = 0, f = f0;
+      uint32_t par = 0;
+      Segment s;
+      while (next_segment(p, f, f1, s)) {
+        const int nplanes = s.nout + span - 1;
+        for (int j = 0; j < nplanes; ++j) {
+          mbar_wait(bar_f + 8 * sl, par);
+          unsigned char* slot = smem + sl * p.slot_bytes;
+          {
+            const uint4* src = reinterpret_cast<const uint4*>(slot + p.off_sa);
+            uint4* dst = reinterpret_cast<uint4*>(slot);
+            int row = a_r0, z = a_z0;
+            for (int e = xt; e < na; e += 256) {
+              uint4 v = src[e];
+              if (xf) v = bn_relu8(v, sc, sh, relu);
+              dst[(row * P + pla) * p.ZOA + z] = v;
+              z += a_zs; row += a_rs;
+              if (z >= p.ZAP) { z -= p.ZAP; ++row; }
+            }
+          }
+          if (j >= span - 1) {
+            const uint4* src = reinterpret_cast<const uint4*>(slot + p.off_sg);
+            uint4* dst = reinterpret_cast<uint4*>(slot + p.off_g);
+            int row = g_r0, z = g_z0;
+            for (int e = xt; e < ng; e += 256) {
+              dst[(row * PG + plg) * p.ZOG + z] = src[e];
+              z += g_zs; row += g_rs;
+              if (z >= p.ZGP) { z -= p.ZGP; ++row; }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_r + 8 * sl);
+          if (++sl == S) { sl = 0; par ^= 1u; }
+        }
+      }
+    } else if (xf || bnb) {
       const int xt = tid - 128;
       // input side: thread -> (channel plane, chunk); dy side: thread -> (dy plane q, chunk)
       const int pln = xf ? xt % p.P : xt % p.PG, c0 = xf ? xt / p.P : xt / p.PG, cstep = (32 * kXfWarps) / (xf ? p.P : p.PG);
@@ -391,84 +452,102 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else {
     // =========================================== EPILOGUE ============================================
-    // TMEM lane = 8 * r + ci (input row r of the tile, channel ci of the plane); warp w holds rows 4w .. 4w + 3 and writes
-    // its sums over those rows into its own copy of the [tap][ci][co] block (plain stores: every entry once per segment).
-    const int rj = lane >> 3, ci = lane & 7;
+    // TMEM lane = 8 * g + ci with M group g = r * PL + plane (PL = P planes per row in interleaved mode, else 1: one plane per
+    // MMA); warp w holds the groups 4w .. 4w + 3 and writes its sums over its rows into its own copy of the [tap][ci][co] block
+    // (plain stores: every entry once per segment).  Accumulator columns of one (tx, tz[, plane, dy plane]) combination:
+    // 8 * (r' * QL + q) + co, QL = PG dy planes per row in interleaved mode, else 1.
+    const int ci = lane & 7;
+    const int PL = il ? p.P : 1, QL = il ? p.PG : 1;
+    const int pl_lane = il ? ((4 * warp + (lane >> 3)) % PL) : 0;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    const int redw = p.PG * 8;
     float* red = reinterpret_cast<float*>(smem + p.off_red);
     float* mine = red + (size_t)warp * red_n;
-    int seg = 0, f = f0;
-    Segment s;
-    while (next_segment(p, f, f1, s)) {
-      mbar_wait(bar_accf, (uint32_t)seg & 1u);
+    const int npl = il ? 1 : p.P, nq = il ? 1 : p.PG;
+    const int cin_b = (il ? p.P : 1) * 8, cout_b = (il ? p.PG : 1) * 8;   // channel block of one accumulator
+    const int blk_n = p.KY * cin_b * cout_b;                              // floats of one accumulator's taps
+    const bool vec4 = (p.cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.wacc) & 15) == 0);
+    if (f0 < f1) {
+      mbar_wait(bar_accf, 0u);
       tc_fence_after();
-      if (prof && tid == 0 && seg == 0) p.prof[5] = clock64();
+      if (prof && tid == 0) p.prof[5] = clock64();
       int comb = 0;
       for (int tx = 0; tx < p.KX; ++tx)
         for (int tz = 0; tz < p.KZ; ++tz)
-          for (int pl = 0; pl < p.P; ++pl)
-            for (int q = 0; q < p.PG; ++q, ++comb) {
-              for (int ty = 0; ty < p.KY; ++ty) {
-                // block (r, r' = r - ty * dil) of the accumulator, for the four rows of this warp; the column offset is
-                // warp-uniform per load, every lane keeps the load of its own row
-                uint32_t u[4][8];
-                bool any = false;
+          for (int pl = 0; pl < npl; ++pl)
+            for (int q = 0; q < nq; ++q, ++comb) {
+              // A round = one ty and up to four 8-column loads issued back to back: NR = 4 / PL distinct rows per warp x QC dy
+              // planes (NR * QC <= 4).  The column offset of a load is warp-uniform, every lane keeps the loads of its own row.
+              const int NR = 4 / PL, QC = min(QL, 4 / NR);
+              const int jr_me = (lane >> 3) / PL;
+              for (int ty = 0; ty < p.KY; ++ty)
+                for (int q0 = 0; q0 < QL; q0 += QC) {
+                  uint32_t u[4][8];
+                  bool any = false;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int r = 4 * warp + j, rp = r - ty * p.dy_;
-                  if (r < p.RA && rp >= 0 && rp < p.RP) {
-                    tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)(comb * p.NCOL + 8 * rp), u[j]);
-                    any = true;
-                  }
-                }
-                float v[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = 0.f;
-                if (any) {  // warp-uniform
-                  tmem_wait_ld();
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    const int r = 4 * warp + j, rp = r - ty * p.dy_;
-                    if (r < p.RA && rp >= 0 && rp < p.RP) {
-                      tmem_pin8(u[j]);
-                      if (rj == j) {
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(u[j][k]);
-                      }
+                  for (int sl = 0; sl < 4; ++sl) {
+                    const int jr = sl / QC, qc = sl - jr * QC;
+                    const int r = (4 * warp) / PL + jr, rp = r - ty * p.dy_;
+                    if (jr < NR && r < p.RA && rp >= 0 && rp < p.RP) {
+                      tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)(comb * p.NCOL + 8 * (rp * QL + q0 + qc)), u[sl]);
+                      any = true;
                     }
                   }
+                  if (any) tmem_wait_ld();  // warp-uniform
+                  const int r_me = (4 * warp) / PL + jr_me, rp_me = r_me - ty * p.dy_;
+                  const bool ok_me = r_me < p.RA && rp_me >= 0 && rp_me < p.RP;
+                  for (int qc = 0; qc < QC; ++qc) {
+                    float v[8];
 #pragma unroll
-                  for (int k = 0; k < 8; ++k) {
-                    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 8);
-                    v[k] += __shfl_xor_sync(0xffffffffu, v[k], 16);
+                    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) {
+                      const int jr = sl / QC, qcs = sl - jr * QC;
+                      const int r = (4 * warp) / PL + jr, rp = r - ty * p.dy_;
+                      if (jr < NR && r < p.RA && rp >= 0 && rp < p.RP) {   // the load was issued (warp-uniform)
+                        tmem_pin8(u[sl]);
+                        if (ok_me && jr == jr_me && qcs == qc) {
+#pragma unroll
+                          for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(u[sl][k]);
+                        }
+                      }
+                    }
+                    for (int off = 8 * PL; off < 32; off <<= 1) {  // the rows of this warp that share (plane, channel)
+#pragma unroll
+                      for (int k = 0; k < 8; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+                    }
+                    if (lane < 8 * PL) {
+                      float4* o = reinterpret_cast<float4*>(mine + ((size_t)(ty * cin_b + pl_lane * 8 + ci)) * cout_b + (q0 + qc) * 8);
+                      o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                      o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    }
                   }
                 }
-                if (lane < 8) {
-                  const int tap = (tx * p.KY + ty) * p.KZ + tz;
-                  float4* o = reinterpret_cast<float4*>(mine + ((size_t)(tap * p.P + pl) * 8 + ci) * redw + q * 8);
-                  o[0] = make_float4(v[0], v[1], v[2], v[3]);
-                  o[1] = make_float4(v[4], v[5], v[6], v[7]);
+              // this accumulator's taps: sum of the four warps' copies -> global accumulator
+              named_bar_sync(1, 128);
+              const int ci0 = il ? 0 : pl * 8, co0 = kind * p.PG * 8 + (il ? 0 : q * 8);
+              for (int e = tid * 4; e < blk_n; e += 128 * 4) {
+                const int col = e % cout_b, row = e / cout_b;  // row = ty * cin_b + input channel of the block
+                const int ty = row / cin_b, cc = ci0 + row - ty * cin_b, co = co0 + col;
+                const int tap = (tx * p.KY + ty) * p.KZ + tz;
+                const float4 a0 = *reinterpret_cast<const float4*>(red + e), a1 = *reinterpret_cast<const float4*>(red + red_n + e),
+                             a2 = *reinterpret_cast<const float4*>(red + 2 * red_n + e), a3 = *reinterpret_cast<const float4*>(red + 3 * red_n + e);
+                const float w0 = (a0.x + a1.x) + (a2.x + a3.x), w1 = (a0.y + a1.y) + (a2.y + a3.y), w2 = (a0.z + a1.z) + (a2.z + a3.z),
+                            w3 = (a0.w + a1.w) + (a2.w + a3.w);
+                if (cc < p.cin) {
+                  float* o = p.wacc + ((size_t)tap * p.cin + cc) * p.cout + co;
+                  if (vec4 && co + 3 < p.cout) red_add_v4(o, w0, w1, w2, w3);
+                  else {
+                    if (co < p.cout) atomicAdd(o, w0);
+                    if (co + 1 < p.cout) atomicAdd(o + 1, w1);
+                    if (co + 2 < p.cout) atomicAdd(o + 2, w2);
+                    if (co + 3 < p.cout) atomicAdd(o + 3, w3);
+                  }
                 }
               }
+              named_bar_sync(1, 128);
             }
-      // the accumulators are free: the next segment's MMAs may overwrite them while this one is flushed
       tc_fence_before();
-      __syncwarp();
-      if (prof && tid == 0 && seg == 0) p.prof[6] = clock64();
-      if (lane == 0) mbar_arrive(bar_acce);
-      named_bar_sync(1, 128);
-      const int cin_p = p.P * 8;
-      for (int e = tid; e < red_n; e += 128) {
-        const int col = e % redw, row = e / redw;  // row = tap * (8 P) + input channel
-        const int tap = row / cin_p, cc = row - tap * cin_p;
-        const int co = kind * redw + col;
-        const float val = (red[e] + red[e + red_n]) + (red[e + 2 * red_n] + red[e + 3 * red_n]);
-        if (cc < p.cin && co < p.cout) atomicAdd(&p.wacc[((size_t)tap * p.cin + cc) * p.cout + co], val);
-      }
-      named_bar_sync(1, 128);
-      if (prof && tid == 0 && seg == 0) p.prof[7] = clock64();
-      ++seg;
+      if (prof && tid == 0) p.prof[7] = clock64();
     }
   }
 
@@ -506,8 +585,8 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
   const int P = d->in_cpitch / 8, Po = d->out_cpitch / 8;
   static const int maxp = env_int("HCU_ROWS_MAXP", 4);
   if (P != 1 && P != 2 && P != 4) return "input channel pitch above 32";
-  if (Po != 1 && Po != 2 && Po != 4) return "dy channel pitch above 32";
-  if (P > maxp || Po > maxp) return "channel pitch above HCU_ROWS_MAXP";
+  if (Po != 1 && Po != 2 && Po != 4 && !(Po == 8 && P > 1)) return "dy channel pitch above 32 (64 with interleaved input planes)";
+  if (P > maxp || Po > 2 * maxp) return "channel pitch above HCU_ROWS_MAXP";
   for (int i = 0; i < 3; ++i) {
     if (d->istep[i] != 1 || d->ostep[i] != 1 || d->ooff[i] != 0 || d->out_tsize[i] != d->out_size[i]) return "strided";
     if (d->pad[i] != 0) return "padding";  // a transformed zero-filled position would not be zero
@@ -536,50 +615,96 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
   p.zero_fill = p.ZAP < c.za ? 1 : 0;
   // dy planes per CTA and rows per tile: all (tx, tz, input plane, dy plane) accumulators of a CTA live in TMEM
   static const int tmem_max = env_int("HCU_ROWS_TMEM", 512);
+  static const int il_on = env_int("HCU_ROWS_IL", 1);
   const int oy_even = round_up(p.OY, 2);
+  p.il = (P > 1 && il_on && !bnb) ? 1 : 0;
   double best = 1e30;
   int best_pg = 0, best_rp = 0;
-  for (int pg = Po; pg >= 1; pg >>= 1) {
-    const int ncomb = p.KX * p.KZ * P * pg;
-    int rp = std::min(16 - halo_y, tmem_max / (8 * ncomb));
-    rp = std::min(rp & ~1, oy_even);
-    if (rp < 2) continue;
-    const int tiles = (p.OY + rp - 1) / rp;
-    const double cost = (double)ncomb * (32 + 2 * rp) / (16.0 * rp) * (Po / pg) * ((double)tiles * rp / p.OY);
-    if (cost < best) { best = cost; best_pg = pg; best_rp = rp; }
+  if (p.il) {
+    // interleaved: M = (16 / P rows) x P planes, N = RP rows x PG planes; one accumulator per (tx, tz)
+    const int ra_max = 16 / P, ncomb = p.KX * p.KZ;
+    if (ra_max - halo_y < 1) return "y extent of the taps above the rows of an interleaved tile";
+    for (int pg = Po; pg >= 1; pg >>= 1)
+      for (int rp = std::min(ra_max - halo_y, oy_even); rp >= 1; --rp) {
+        if ((rp * pg) % 2 != 0 || ncomb * 8 * rp * pg > tmem_max || 8 * rp * pg > 256) continue;
+        const int tiles = (p.OY + rp - 1) / rp;
+        const double cost = (double)ncomb * (32 + 2 * rp * pg) / (16.0 * rp) * (Po / pg) * ((double)tiles * rp / p.OY);
+        if (cost < best) { best = cost; best_pg = pg; best_rp = rp; }
+      }
+  } else {
+    for (int pg = Po; pg >= 1; pg >>= 1) {
+      const int ncomb = p.KX * p.KZ * P * pg;
+      int rp = std::min(16 - halo_y, tmem_max / (8 * ncomb));
+      rp = std::min(rp & ~1, oy_even);
+      if (rp < 2) continue;
+      const int tiles = (p.OY + rp - 1) / rp;
+      const double cost = (double)ncomb * (32 + 2 * rp) / (16.0 * rp) * (Po / pg) * ((double)tiles * rp / p.OY);
+      if (cost < best) { best = cost; best_pg = pg; best_rp = rp; }
+    }
   }
   if (best_pg == 0) return "accumulators do not fit in TMEM";
   p.PG = best_pg; p.RP = best_rp; p.RA = best_rp + halo_y;
   c.kinds = Po / p.PG;
-  p.NCOL = 8 * p.RP;
+  p.NCOL = p.il ? 8 * p.RP * p.PG : 8 * p.RP;
+  p.tx_cols = p.il ? p.KZ * p.NCOL : p.KZ * P * p.PG * p.NCOL;
   {
-    int cols = p.KX * p.KZ * P * p.PG * p.NCOL, t = 32;
+    int cols = p.KX * p.tx_cols, t = 32;
     while (t < cols) t <<= 1;
     p.tmem_cols = t;
   }
-  p.a_box_bytes = p.RA * p.ZAP * 16;
-  p.g_box_bytes = p.RP * p.ZGP * 16;
-  p.a_plane_bytes = round_up(p.a_box_bytes, 128);
-  p.g_plane_bytes = round_up(p.g_box_bytes, 128);
-  p.off_g = P * p.a_plane_bytes + 128;  // + what the last tap reads past a merged row
-  p.off_y = p.off_g + p.PG * p.g_plane_bytes;
-  p.slot_bytes = p.off_y + (bnb ? p.PG * p.g_plane_bytes : 0);
-  p.bnb = bnb ? 1 : 0;
+  const int red_bytes = 4 * p.KY * (p.il ? P * p.PG : 1) * 64 * 4;  // one accumulator's (ty, ci, co) block, one copy per epilogue warp
+  int a_reach;  // bytes an M = 128 tile may read from a slot's base (16 row groups whatever RA is)
+  if (p.il) {
+    c.merged_a = c.merged_g = false;
+    p.ZAP = c.za; p.zero_fill = 0;
+    // operand row pitch = 1 (mod 8) positions: the P groups of a row land in different banks for the re-layout's stores
+    p.ZOA = round_up(p.ZAP, 8) + 1; p.ZOG = round_up(p.ZGP, 8) + 1;
+    p.sbo_a = p.ZOA * 16; p.sbo_b = p.ZOG * 16;
+    p.a_box_bytes = p.RA * p.ZAP * 16 * P;       // one box: all planes
+    p.g_box_bytes = p.RP * p.ZGP * 16 * p.PG;
+    const int opa = round_up(16 * p.ZOA * 16, 128);                 // operand: 16 groups
+    const int opg = round_up(p.RP * p.PG * p.ZOG * 16, 128);
+    p.off_g = opa;
+    p.off_sa = p.off_g + opg;
+    p.off_sg = p.off_sa + round_up(p.a_box_bytes, 128);
+    p.slot_bytes = p.off_sg + round_up(p.g_box_bytes, 128);
+    p.off_y = 0; p.bnb = 0;
+    p.a_plane_bytes = 0; p.g_plane_bytes = 0;
+    p.nper = p.KZ * p.ZC;
+    if (p.nper > kMaxPer) return "too many MMAs per step";
+    for (int m = 0; m < p.nper; ++m) {
+      const int zc = m % p.ZC, tz = m / p.ZC;
+      p.tab_a[m] = (uint32_t)(tz * p.dz * 16 + zc * 256) >> 4;
+      p.tab_b[m] = (uint32_t)(p.off_g + zc * 256) >> 4;
+      p.tab_t[m] = (uint32_t)(tz * p.NCOL) | (zc ? 0x80000000u : 0u);
+    }
+    a_reach = opa;
+  } else {
+    p.sbo_a = p.ZAP * 16; p.sbo_b = p.ZGP * 16;
+    p.a_box_bytes = p.RA * p.ZAP * 16;
+    p.g_box_bytes = p.RP * p.ZGP * 16;
+    p.a_plane_bytes = round_up(p.a_box_bytes, 128);
+    p.g_plane_bytes = round_up(p.g_box_bytes, 128);
+    p.off_g = P * p.a_plane_bytes + 128;  // + what the last tap reads past a merged row
+    p.off_y = p.off_g + p.PG * p.g_plane_bytes;
+    p.slot_bytes = p.off_y + (bnb ? p.PG * p.g_plane_bytes : 0);
+    p.bnb = bnb ? 1 : 0;
+    p.nper = p.KZ * P * p.PG * p.ZC;
+    if (p.nper > kMaxPer) return "too many MMAs per step";
+    for (int m = 0; m < p.nper; ++m) {
+      int r = m;
+      const int zc = r % p.ZC; r /= p.ZC;
+      const int q = r % p.PG; r /= p.PG;
+      const int pl = r % P;
+      const int tz = r / P;
+      p.tab_a[m] = (uint32_t)(pl * p.a_plane_bytes + tz * p.dz * 16 + zc * 256) >> 4;
+      p.tab_b[m] = (uint32_t)(p.off_g + q * p.g_plane_bytes + zc * 256) >> 4;
+      p.tab_t[m] = (uint32_t)(((tz * P + pl) * p.PG + q) * p.NCOL) | (zc ? 0x80000000u : 0u);
+    }
+    a_reach = (P - 1) * p.a_plane_bytes + 16 * p.ZAP * 16 + 512;
+  }
   p.OZ = OZ;
   p.coef_c = d->out_cpitch;
-  const int red_bytes = 4 * p.KX * p.KY * p.KZ * P * 8 * p.PG * 8 * 4;  // one copy per epilogue warp
-  p.nper = p.KZ * P * p.PG * p.ZC;
-  if (p.nper > kMaxPer) return "too many MMAs per step";
-  for (int m = 0; m < p.nper; ++m) {
-    int r = m;
-    const int zc = r % p.ZC; r /= p.ZC;
-    const int q = r % p.PG; r /= p.PG;
-    const int pl = r % P;
-    const int tz = r / P;
-    p.tab_a[m] = (uint32_t)(pl * p.a_plane_bytes + tz * p.dz * 16 + zc * 256) >> 4;
-    p.tab_b[m] = (uint32_t)(p.off_g + q * p.g_plane_bytes + zc * 256) >> 4;
-    p.tab_t[m] = (uint32_t)(((tz * P + pl) * p.PG + q) * p.NCOL) | (zc ? 0x80000000u : 0u);
-  }
   // look-ahead: ~64 KB of loads in flight per SM
   static const int la_env = env_int("HCU_ROWS_LA", 0);
   int la = la_env > 0 ? la_env : std::max(2, std::min(8, (64 * 1024 + p.slot_bytes - 1) / p.slot_bytes));
@@ -587,13 +712,12 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
     if (la < 1) return "does not fit in shared memory";
     p.S = span + la;
     // an M = 128 tile reads 16 row groups from a plane's base whatever RA is: keep those reads inside the allocation
-    const int a_end = (p.S - 1) * p.slot_bytes + (P - 1) * p.a_plane_bytes + 16 * p.ZAP * 16 + 512;
+    const int a_end = (p.S - 1) * p.slot_bytes + a_reach;
     p.off_red = round_up(p.S * p.slot_bytes, 128);
     p.off_bar = round_up(p.off_red + red_bytes, 128);
     p.smem_bytes = std::max(p.off_bar + 8 * (3 * p.S + 2) + 16, a_end) + 128;
     if (p.smem_bytes <= 200 * 1024) break;
   }
-  if (p.ZAP * 16 / 16 > 0x3FFF) return "row pitch";
   p.n_ytiles = (p.OY + p.RP - 1) / p.RP;
   const long long total = (long long)p.N * p.n_ytiles * p.OX;
   if (total >= 0x7fffffffLL) return "too many steps";
@@ -608,7 +732,7 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
 
 // rank-5 map of a channels-last fp16 tensor [N][X][Y][Z][cpitch]; box = rows x boxz z positions x 8 channels of one x-plane
 static const char* encode_map(CUtensorMap* tm, const void* base, int cpitch, int Z, int Y, int X, int N, bool merged, int boxz,
-                              int rows) {
+                              int rows, int boxc = 8) {
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t box[5], estr[5] = {1, 1, 1, 1, 1};
   const cuuint64_t px = (cuuint64_t)cpitch * 2;
@@ -619,7 +743,7 @@ static const char* encode_map(CUtensorMap* tm, const void* base, int cpitch, int
   } else {
     gdim[0] = (cuuint64_t)cpitch; gdim[1] = (cuuint64_t)Z;
     gstr[0] = px;
-    box[0] = 8; box[1] = (cuuint32_t)boxz;
+    box[0] = (cuuint32_t)boxc; box[1] = (cuuint32_t)boxz;
   }
   gdim[2] = (cuuint64_t)Y; gdim[3] = (cuuint64_t)X; gdim[4] = (cuuint64_t)N;
   gstr[1] = (cuuint64_t)Z * px; gstr[2] = gstr[1] * Y; gstr[3] = gstr[2] * X;
@@ -659,7 +783,9 @@ using namespace hcu;
 extern "C" int hcu_conv_wgrad_rows_supported(const HcuConvDesc* d) {
   if (d == nullptr) return 0;
   wgr::Config c;
-  return wgr::configure(d, c) == nullptr ? 1 : 0;
+  const char* why = wgr::configure(d, c);
+  if (why != nullptr && (wgr::env_int("HCU_TC_DEBUG", 0) & 8)) fprintf(stderr, "wgrad_rows: not taken (%s)\n", why);
+  return why == nullptr ? 1 : 0;
 }
 
 static int wgrad_rows_launch(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
@@ -685,9 +811,11 @@ static int wgrad_rows_launch(const HcuConvDesc* d, const void* a, const float* a
   if (prof_env && prof_buf == nullptr) cudaMalloc(&prof_buf, 16 * sizeof(long long));
   p.prof = prof_env ? prof_buf : nullptr;
   CUtensorMap tmA, tmG, tmY;
-  why = wgr::encode_map(&tmA, a, d->in_cpitch, d->in_size[2], d->in_size[1], d->in_size[0], d->batch, c.merged_a, p.ZAP, p.RA);
+  why = wgr::encode_map(&tmA, a, d->in_cpitch, d->in_size[2], d->in_size[1], d->in_size[0], d->batch, c.merged_a, p.ZAP, p.RA,
+                        p.il ? 8 * p.P : 8);
   if (why == nullptr)
-    why = wgr::encode_map(&tmG, dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g, p.ZGP, p.RP);
+    why = wgr::encode_map(&tmG, dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g, p.ZGP, p.RP,
+                          p.il ? 8 * p.PG : 8);
   if (why == nullptr)
     why = wgr::encode_map(&tmY, bnb ? y : dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g, p.ZGP, p.RP);
   if (why != nullptr) {
@@ -699,6 +827,7 @@ static int wgrad_rows_launch(const HcuConvDesc* d, const void* a, const float* a
     cudaError_t e = cudaFuncSetAttribute(wgr::wgrad_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgr::kSmemLimit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wgr::wgrad_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgr::kSmemLimit);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(wgr::wgrad_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgr::kSmemLimit);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(wgr::wgrad_rows_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, wgr::kSmemLimit);
     if (e != cudaSuccess) { set_error("wgrad_rows: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return HCU_ERR_CUDA; }
     attr = true;
   }
@@ -706,12 +835,13 @@ static int wgrad_rows_launch(const HcuConvDesc* d, const void* a, const float* a
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("HCU_TC_DEBUG"); dbg = e ? atoi(e) : 0; }
     if (dbg & 8)
-      fprintf(stderr, "wgrad_rows: P %d PG %d kinds %d RP %d RA %d ZC %d ZAP %d ZGP %d N %d tmem %d S %d smem %d grid %d x %d steps/cta %d merged %d/%d bnb %d\n",
+      fprintf(stderr, "wgrad_rows: P %d PG %d kinds %d RP %d RA %d ZC %d ZAP %d ZGP %d N %d tmem %d S %d smem %d grid %d x %d steps/cta %d merged %d/%d bnb %d il %d\n",
               p.P, p.PG, c.kinds, p.RP, p.RA, p.ZC, p.ZAP, p.ZGP, p.NCOL, p.tmem_cols, p.S, p.smem_bytes, c.gx, c.kinds,
-              p.steps_per_cta, (int)c.merged_a, (int)c.merged_g, p.bnb);
+              p.steps_per_cta, (int)c.merged_a, (int)c.merged_g, p.bnb, p.il);
   }
   const dim3 grid((unsigned)c.gx, (unsigned)c.kinds);
-  if (bnb) wgr::wgrad_rows_kernel<2><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
+  if (p.il) wgr::wgrad_rows_kernel<3><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
+  else if (bnb) wgr::wgrad_rows_kernel<2><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
   else if (a_scale != nullptr) wgr::wgrad_rows_kernel<1><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
   else wgr::wgrad_rows_kernel<0><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
   HCU_CHECK_LAUNCH("wgrad_rows");

@@ -349,6 +349,13 @@ WGR_CASES = [
     (1, 8, 8, (9, 20, 24), (3, 3, 2), (1, 1, 2), None),        # dilation in z
     (1, 16, 8, (5, 16, 17), (1, 1, 1), (1, 1, 1), None),       # 1x1: 16 rows per tile
     (4, 8, 8, (30, 33, 20), (3, 3, 1), (1, 1, 1), None),       # CTAs whose step range crosses tiles and images
+    # interleaved channel planes (P > 1): one MMA covers all planes of a row on both sides
+    (2, 16, 16, (9, 41, 30), (3, 3, 1), (1, 1, 1), None),      # 8 rows x 2 planes, ragged last row tile
+    (2, 16, 32, (8, 30, 30), (3, 3, 2), (1, 1, 1), None),      # dy planes split over CTA kinds by TMEM capacity
+    (2, 32, 32, (9, 31, 29), (3, 3, 1), (1, 1, 1), None),      # 4 rows x 4 planes
+    (1, 32, 64, (7, 15, 29), (3, 3, 2), (1, 1, 1), None),      # 64 dy channels
+    (1, 32, 16, (6, 13, 40), (3, 3, 2), (1, 1, 1), None),      # three K groups
+    (1, 24, 16, (6, 13, 20), (3, 3, 2), (1, 1, 1), 32),        # 24 of 32 input channels live
 ]
 
 
@@ -367,7 +374,7 @@ def test_wgrad_rows_matches_fp32(case):
 
 def test_wgrad_rows_fused_input_bn_relu():
     g = torch.Generator().manual_seed(31)
-    for cin, cout, isz, k in ((8, 8, (12, 19, 17), (3, 3, 2)), (16, 16, (9, 30, 20), (3, 3, 1))):
+    for cin, cout, isz, k in ((8, 8, (12, 19, 17), (3, 3, 2)), (16, 16, (9, 30, 20), (3, 3, 1)), (32, 32, (7, 22, 29), (3, 3, 1))):
         osz = tuple(isz[i] - k[i] + 1 for i in range(3))
         x = h16(torch.randn((2, cin) + isz, generator=g))
         dy = h16(torch.randn((2, cout) + osz, generator=g))
