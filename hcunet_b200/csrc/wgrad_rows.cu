@@ -470,11 +470,16 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       mbar_wait(bar_accf, 0u);
       tc_fence_after();
       if (prof && tid == 0) p.prof[5] = clock64();
-      int comb = 0;
-      for (int tx = 0; tx < p.KX; ++tx)
-        for (int tz = 0; tz < p.KZ; ++tz)
-          for (int pl = 0; pl < npl; ++pl)
-            for (int q = 0; q < nq; ++q, ++comb) {
+      // Every CTA adds its accumulators to the same [taps][cin][cout] block: CTA b starts with accumulator b mod ncomb and walks
+      // its flush from a different element, so that at any moment the CTAs' reductions hit different addresses (with all of
+      // them on accumulator 0 at once the same-address atomics serialised in L2: 97 k of 133 k clocks on the 32 -> 64 layer).
+      const int ncomb = p.KX * p.KZ * npl * nq;
+      for (int cidx = 0; cidx < ncomb; ++cidx) {
+              const int comb = (cidx + (int)blockIdx.x) % ncomb;
+              int rem = comb;
+              const int q = rem % nq; rem /= nq;
+              const int pl = rem % npl; rem /= npl;
+              const int tz = rem % p.KZ, tx = rem / p.KZ;
               // A round = one ty and up to four 8-column loads issued back to back: NR = 4 / PL distinct rows per warp x QC dy
               // planes (NR * QC <= 4).  The column offset of a load is warp-uniform, every lane keeps the loads of its own row.
               const int NR = 4 / PL, QC = min(QL, 4 / NR);
@@ -525,7 +530,9 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               // this accumulator's taps: sum of the four warps' copies -> global accumulator
               named_bar_sync(1, 128);
               const int ci0 = il ? 0 : pl * 8, co0 = kind * p.PG * 8 + (il ? 0 : q * 8);
-              for (int e = tid * 4; e < blk_n; e += 128 * 4) {
+              const int rot = (int)((blockIdx.x * 131u) % (unsigned)(blk_n / 4)) * 4;
+              for (int e0 = tid * 4; e0 < blk_n; e0 += 128 * 4) {
+                const int e = e0 + rot < blk_n ? e0 + rot : e0 + rot - blk_n;
                 const int col = e % cout_b, row = e / cout_b;  // row = ty * cin_b + input channel of the block
                 const int ty = row / cin_b, cc = ci0 + row - ty * cin_b, co = co0 + col;
                 const int tap = (tx * p.KY + ty) * p.KZ + tz;
@@ -722,9 +729,9 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
   const long long total = (long long)p.N * p.n_ytiles * p.OX;
   if (total >= 0x7fffffffLL) return "too many steps";
   p.total_steps = (int)total;
-  // equal contiguous step ranges, one CTA per SM (and kind); no range shorter than 8 planes (pipeline fill + flush)
+  // equal contiguous step ranges, one CTA per SM (and kind); no range shorter than 16 planes (pipeline fill + flush)
   int gx = std::max(1, num_sms() / c.kinds);
-  gx = (int)std::max(1LL, std::min<long long>(gx, total / 8));
+  gx = (int)std::max(1LL, std::min<long long>(gx, total / 16));
   p.steps_per_cta = (int)((total + gx - 1) / gx);
   c.gx = (int)((total + p.steps_per_cta - 1) / p.steps_per_cta);
   return nullptr;
