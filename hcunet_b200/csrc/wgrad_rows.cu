@@ -35,6 +35,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 
@@ -450,112 +451,118 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
       }
     }
-  } else {
+  }
+
+  if (warp < 12 && f0 < f1) {
     // =========================================== EPILOGUE ============================================
+    // Once per CTA, by the twelve warps whose roles are over (the four idle ones and the eight transform warps; a warp reads the
+    // TMEM lanes 32 * (warp % 4) ...: three warps share a quadrant and split its rounds).
     // TMEM lane = 8 * g + ci with M group g = r * PL + plane (PL = P planes per row in interleaved mode, else 1: one plane per
-    // MMA); warp w holds the groups 4w .. 4w + 3 and writes its sums over its rows into its own copy of the [tap][ci][co] block
-    // (plain stores: every entry once per segment).  Accumulator columns of one (tx, tz[, plane, dy plane]) combination:
+    // MMA); quadrant w holds the groups 4w .. 4w + 3 and writes its sums over its rows into its own copy of the accumulator's
+    // [ty][ci][co] block (plain stores: every entry once).  Accumulator columns of one (tx, tz[, plane, dy plane]) combination:
     // 8 * (r' * QL + q) + co, QL = PG dy planes per row in interleaved mode, else 1.
+    const int qd = warp & 3, helper = warp >> 2;
+    const int et = tid;                                  // 0 .. 383
     const int ci = lane & 7;
     const int PL = il ? p.P : 1, QL = il ? p.PG : 1;
-    const int pl_lane = il ? ((4 * warp + (lane >> 3)) % PL) : 0;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const int pl_lane = il ? ((4 * qd + (lane >> 3)) % PL) : 0;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
     float* red = reinterpret_cast<float*>(smem + p.off_red);
-    float* mine = red + (size_t)warp * red_n;
+    float* mine = red + (size_t)qd * red_n;
     const int npl = il ? 1 : p.P, nq = il ? 1 : p.PG;
-    const int cin_b = (il ? p.P : 1) * 8, cout_b = (il ? p.PG : 1) * 8;   // channel block of one accumulator
+    const int cin_b = (il ? p.P : 1) * 8, cout_b = (il ? p.PG : 1) * 8;   // channel block of one accumulator (powers of two)
+    const int lg_ci = 31 - __clz(cin_b), lg_co = 31 - __clz(cout_b);
     const int blk_n = p.KY * cin_b * cout_b;                              // floats of one accumulator's taps
     const bool vec4 = (p.cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.wacc) & 15) == 0);
-    if (f0 < f1) {
-      mbar_wait(bar_accf, 0u);
-      tc_fence_after();
-      if (prof && tid == 0) p.prof[5] = clock64();
-      // Every CTA adds its accumulators to the same [taps][cin][cout] block: CTA b starts with accumulator b mod ncomb and walks
-      // its flush from a different element, so that at any moment the CTAs' reductions hit different addresses (with all of
-      // them on accumulator 0 at once the same-address atomics serialised in L2: 97 k of 133 k clocks on the 32 -> 64 layer).
-      const int ncomb = p.KX * p.KZ * npl * nq;
-      for (int cidx = 0; cidx < ncomb; ++cidx) {
-              const int comb = (cidx + (int)blockIdx.x) % ncomb;
-              int rem = comb;
-              const int q = rem % nq; rem /= nq;
-              const int pl = rem % npl; rem /= npl;
-              const int tz = rem % p.KZ, tx = rem / p.KZ;
-              // A round = one ty and up to four 8-column loads issued back to back: NR = 4 / PL distinct rows per warp x QC dy
-              // planes (NR * QC <= 4).  The column offset of a load is warp-uniform, every lane keeps the loads of its own row.
-              const int NR = 4 / PL, QC = min(QL, 4 / NR);
-              const int jr_me = (lane >> 3) / PL;
-              for (int ty = 0; ty < p.KY; ++ty)
-                for (int q0 = 0; q0 < QL; q0 += QC) {
-                  uint32_t u[4][8];
-                  bool any = false;
+    mbar_wait(bar_accf, 0u);
+    tc_fence_after();
+    if (prof && tid == 0) p.prof[5] = clock64();
+    // Every CTA adds its accumulators to the same [taps][cin][cout] block: CTA b starts with accumulator b mod ncomb and walks its
+    // flush from a different element, so that the CTAs' reductions spread over the addresses.
+    const int ncomb = p.KX * p.KZ * npl * nq;
+    const int NR = 4 / PL, QC = min(QL, 4 / NR);
+    const int jr_me = (lane >> 3) / PL;
+    for (int cidx = 0; cidx < ncomb; ++cidx) {
+      const int comb = (cidx + (int)blockIdx.x) % ncomb;
+      int rem = comb;
+      const int q = rem % nq; rem /= nq;
+      const int pl = rem % npl; rem /= npl;
+      const int tz = rem % p.KZ, tx = rem / p.KZ;
+      // A round = one ty and up to four 8-column loads issued back to back: NR = 4 / PL distinct rows per quadrant x QC dy planes
+      // (NR * QC <= 4).  The column offset of a load is warp-uniform, every lane keeps the loads of its own row.
+      int round = 0;
+      for (int ty = 0; ty < p.KY; ++ty)
+        for (int q0 = 0; q0 < QL; q0 += QC, ++round) {
+          if (round % 3 != helper) continue;   // warp-uniform
+          uint32_t u[4][8];
+          bool any = false;
 #pragma unroll
-                  for (int sl = 0; sl < 4; ++sl) {
-                    const int jr = sl / QC, qc = sl - jr * QC;
-                    const int r = (4 * warp) / PL + jr, rp = r - ty * p.dy_;
-                    if (jr < NR && r < p.RA && rp >= 0 && rp < p.RP) {
-                      tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)(comb * p.NCOL + 8 * (rp * QL + q0 + qc)), u[sl]);
-                      any = true;
-                    }
-                  }
-                  if (any) tmem_wait_ld();  // warp-uniform
-                  const int r_me = (4 * warp) / PL + jr_me, rp_me = r_me - ty * p.dy_;
-                  const bool ok_me = r_me < p.RA && rp_me >= 0 && rp_me < p.RP;
-                  for (int qc = 0; qc < QC; ++qc) {
-                    float v[8];
+          for (int sl = 0; sl < 4; ++sl) {
+            const int jr = sl / QC, qc = sl - jr * QC;
+            const int r = (4 * qd) / PL + jr, rp = r - ty * p.dy_;
+            if (jr < NR && r < p.RA && rp >= 0 && rp < p.RP) {
+              tmem_ld8_nowait(tmem_base + lane_base + (uint32_t)(comb * p.NCOL + 8 * (rp * QL + q0 + qc)), u[sl]);
+              any = true;
+            }
+          }
+          if (any) tmem_wait_ld();  // warp-uniform
+          const int r_me = (4 * qd) / PL + jr_me, rp_me = r_me - ty * p.dy_;
+          const bool ok_me = r_me < p.RA && rp_me >= 0 && rp_me < p.RP;
+          for (int qc = 0; qc < QC; ++qc) {
+            float v[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+            for (int k = 0; k < 8; ++k) v[k] = 0.f;
 #pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) {
-                      const int jr = sl / QC, qcs = sl - jr * QC;
-                      const int r = (4 * warp) / PL + jr, rp = r - ty * p.dy_;
-                      if (jr < NR && r < p.RA && rp >= 0 && rp < p.RP) {   // the load was issued (warp-uniform)
-                        tmem_pin8(u[sl]);
-                        if (ok_me && jr == jr_me && qcs == qc) {
+            for (int sl = 0; sl < 4; ++sl) {
+              const int jr = sl / QC, qcs = sl - jr * QC;
+              const int r = (4 * qd) / PL + jr, rp = r - ty * p.dy_;
+              if (jr < NR && r < p.RA && rp >= 0 && rp < p.RP) {   // the load was issued (warp-uniform)
+                tmem_pin8(u[sl]);
+                if (ok_me && jr == jr_me && qcs == qc) {
 #pragma unroll
-                          for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(u[sl][k]);
-                        }
-                      }
-                    }
-                    for (int off = 8 * PL; off < 32; off <<= 1) {  // the rows of this warp that share (plane, channel)
-#pragma unroll
-                      for (int k = 0; k < 8; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
-                    }
-                    if (lane < 8 * PL) {
-                      float4* o = reinterpret_cast<float4*>(mine + ((size_t)(ty * cin_b + pl_lane * 8 + ci)) * cout_b + (q0 + qc) * 8);
-                      o[0] = make_float4(v[0], v[1], v[2], v[3]);
-                      o[1] = make_float4(v[4], v[5], v[6], v[7]);
-                    }
-                  }
-                }
-              // this accumulator's taps: sum of the four warps' copies -> global accumulator
-              named_bar_sync(1, 128);
-              const int ci0 = il ? 0 : pl * 8, co0 = kind * p.PG * 8 + (il ? 0 : q * 8);
-              const int rot = (int)((blockIdx.x * 131u) % (unsigned)(blk_n / 4)) * 4;
-              for (int e0 = tid * 4; e0 < blk_n; e0 += 128 * 4) {
-                const int e = e0 + rot < blk_n ? e0 + rot : e0 + rot - blk_n;
-                const int col = e % cout_b, row = e / cout_b;  // row = ty * cin_b + input channel of the block
-                const int ty = row / cin_b, cc = ci0 + row - ty * cin_b, co = co0 + col;
-                const int tap = (tx * p.KY + ty) * p.KZ + tz;
-                const float4 a0 = *reinterpret_cast<const float4*>(red + e), a1 = *reinterpret_cast<const float4*>(red + red_n + e),
-                             a2 = *reinterpret_cast<const float4*>(red + 2 * red_n + e), a3 = *reinterpret_cast<const float4*>(red + 3 * red_n + e);
-                const float w0 = (a0.x + a1.x) + (a2.x + a3.x), w1 = (a0.y + a1.y) + (a2.y + a3.y), w2 = (a0.z + a1.z) + (a2.z + a3.z),
-                            w3 = (a0.w + a1.w) + (a2.w + a3.w);
-                if (cc < p.cin) {
-                  float* o = p.wacc + ((size_t)tap * p.cin + cc) * p.cout + co;
-                  if (vec4 && co + 3 < p.cout) red_add_v4(o, w0, w1, w2, w3);
-                  else {
-                    if (co < p.cout) atomicAdd(o, w0);
-                    if (co + 1 < p.cout) atomicAdd(o + 1, w1);
-                    if (co + 2 < p.cout) atomicAdd(o + 2, w2);
-                    if (co + 3 < p.cout) atomicAdd(o + 3, w3);
-                  }
+                  for (int k = 0; k < 8; ++k) v[k] = __uint_as_float(u[sl][k]);
                 }
               }
-              named_bar_sync(1, 128);
             }
-      tc_fence_before();
-      if (prof && tid == 0) p.prof[7] = clock64();
+            for (int off = 8 * PL; off < 32; off <<= 1) {  // the rows of this quadrant that share (plane, channel)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+            }
+            if (lane < 8 * PL) {
+              float4* o = reinterpret_cast<float4*>(mine + ((size_t)(ty * cin_b + pl_lane * 8 + ci)) * cout_b + (q0 + qc) * 8);
+              o[0] = make_float4(v[0], v[1], v[2], v[3]);
+              o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+          }
+        }
+      // this accumulator's taps: sum of the four quadrants' copies -> global accumulator
+      named_bar_sync(1, 384);
+      const int ci0 = il ? 0 : pl * 8, co0 = kind * p.PG * 8 + (il ? 0 : q * 8);
+      const int rot = (int)((blockIdx.x * 131u) % (unsigned)(blk_n / 4)) * 4;
+      for (int e0 = et * 4; e0 < blk_n; e0 += 384 * 4) {
+        const int e = e0 + rot < blk_n ? e0 + rot : e0 + rot - blk_n;
+        const int col = e & (cout_b - 1), row = e >> lg_co;  // row = ty * cin_b + input channel of the block
+        const int ty = row >> lg_ci, cc = ci0 + (row & (cin_b - 1)), co = co0 + col;
+        const int tap = (tx * p.KY + ty) * p.KZ + tz;
+        const float4 a0 = *reinterpret_cast<const float4*>(red + e), a1 = *reinterpret_cast<const float4*>(red + red_n + e),
+                     a2 = *reinterpret_cast<const float4*>(red + 2 * red_n + e), a3 = *reinterpret_cast<const float4*>(red + 3 * red_n + e);
+        const float w0 = (a0.x + a1.x) + (a2.x + a3.x), w1 = (a0.y + a1.y) + (a2.y + a3.y), w2 = (a0.z + a1.z) + (a2.z + a3.z),
+                    w3 = (a0.w + a1.w) + (a2.w + a3.w);
+        if (cc < p.cin) {
+          float* o = p.wacc + ((size_t)tap * p.cin + cc) * p.cout + co;
+          if (vec4 && co + 3 < p.cout) red_add_v4(o, w0, w1, w2, w3);
+          else {
+            if (co < p.cout) atomicAdd(o, w0);
+            if (co + 1 < p.cout) atomicAdd(o + 1, w1);
+            if (co + 2 < p.cout) atomicAdd(o + 2, w2);
+            if (co + 3 < p.cout) atomicAdd(o + 3, w3);
+          }
+        }
+      }
+      named_bar_sync(1, 384);
     }
+    tc_fence_before();
+    if (prof && tid == 0) p.prof[7] = clock64();
   }
 
   tc_fence_before();
@@ -732,6 +739,12 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
   // equal contiguous step ranges, one CTA per SM (and kind); no range shorter than 16 planes (pipeline fill + flush)
   int gx = std::max(1, num_sms() / c.kinds);
   gx = (int)std::max(1LL, std::min<long long>(gx, total / 16));
+  {
+    // (fewer, longer CTAs to save end-of-kernel reductions were measured and lose: the epilogue is bound by its own instructions
+    // per CTA, not by the L2's reduction rate -- 32 -> 64 layer 77 us with 143 CTAs, 106 us with 50)
+    static const int gx_env = env_int("HCU_ROWS_GX", 0);
+    if (gx_env > 0) gx = std::min(gx, gx_env);
+  }
   p.steps_per_cta = (int)((total + gx - 1) / gx);
   c.gx = (int)((total + p.steps_per_cta - 1) / p.steps_per_cta);
   return nullptr;

@@ -335,7 +335,7 @@ class UnetEngine:
         # row-stacked tcgen05 weight gradient fed by TMA (channel-poor levels); input channel pitch up to ROWS_MAXCP
         self.use_rows = os.environ.get("HCUNET_WGRADROWS", "1") != "0"
         self.rows_maxcp = int(os.environ.get("HCUNET_WGRADROWS_MAXCP", "32"))
-        self.rows_maxcp_out = int(os.environ.get("HCUNET_WGRADROWS_MAXCP_OUT", "32"))
+        self.rows_maxcp_out = int(os.environ.get("HCUNET_WGRADROWS_MAXCP_OUT", "64"))
         self.fuse_apply = os.environ.get("HCUNET_FUSE_APPLY", "1") != "0"   # BN-backward apply inside the first layer's weight gradient
         self.use_batch = os.environ.get("HCUNET_BATCH", "1") != "0"      # batched packs / scatters (_StepCache)
         self.overlap_wgrad = os.environ.get("HCUNET_OVERLAP", "1") != "0"  # weight gradients on a side stream
