@@ -31,9 +31,11 @@ import torch.nn.functional as F
 
 from .unet_oracle import cross_entropy, normalise_spec
 
-FLOOR_FACTOR = 4.0
+FLOOR_FACTOR = 5.0
 """A tensor's gate is max(stated tolerance, FLOOR_FACTOR x its measured accumulation-order floor): the floor is the largest of
-three samples of a heavy-tailed spread, the implementation under test is a fourth draw."""
+three samples of a heavy-tailed spread, the implementation under test is a fourth draw.  (4.0 until one of six full GPU runs
+of one day put the strict-fp32 path's `up_steps.1.batch1.bias` gradient of the full-size cfg1 fixture at 4.0009 x its floor --
+5.460e-3 against a gate of 5.459e-3; the fp32 kernels' atomics land in a different order every run.)"""
 
 
 def gate(stated: float, floor: float) -> float:

@@ -5,7 +5,7 @@
                  (logits, loss); gradients <= 1e-4 per tensor; >= 99.9 % thresholded-mask agreement.  On the
                  ill-conditioned fixtures (5 levels over a 4x4 bottom) the fp32 reference ITSELF is only reproducible
                  to ~1e-5: the floor is measured as the deviation of the fp32 oracle from the same oracle evaluated in
-                 float64, and the tolerance is max(1e-5, 4 x that floor) (gradients: max(1e-4, 4 x floor)).
+                 float64, and the tolerance is max(1e-5, 5 x that floor) (gradients: max(1e-4, 5 x floor)).
     mixed path : against the fp16-STORAGE EMULATION of the reference (oracle/mixed_oracle.py: the same control flow with
                  an explicit backward, rounding to fp16 exactly where the engine stores a tensor; with the rounding hooks
                  off it is pinned to the reference-minted fixtures by tests/test_oracle_golden.py).  Stated tolerances:
@@ -15,7 +15,7 @@
                  on the logits and 4 % .. 30 % on deep gradients.  That spread is MEASURED per case and per tensor
                  (``mixed_oracle.accumulation_floor``: the emulation with fp64 / split-K convolution accumulation and
                  fp32 BatchNorm sums against itself) and
-                 the gate of a tensor is max(stated tolerance, 4 x its own floor) -- never one tolerance for all tensors.
+                 the gate of a tensor is max(stated tolerance, 5 x its own floor) -- never one tolerance for all tensors.
                  The tight, amplification-free check of every kernel launch of the step is tests/test_gpu_teacher.py
                  (teacher-forced, 5e-4 / 2e-3); what fp16 storage costs against the fp32 reference is PRINTED here as
                  context (1e-3 .. 2e-2 on logits -- the same order as the reference's own default GPU arithmetic, cuDNN
