@@ -166,6 +166,9 @@ def test_every_conv_of_the_baseline_configs_gets_a_tensor_core_kernel():
             wg = lib.hcu_conv_wgrad_tc5_supported(C.byref(d)) or lib.hcu_conv_wgrad_ws_supported(C.byref(d)) or \
                 lib.hcu_conv_wgrad_tc_supported(C.byref(d))
             assert wg, g.name
+            # the channel-poor levels of the 3D model go to the TMA-fed row-stacked tcgen05 kernel, the 2D model has no z rows for it
+            rows = bool(lib.hcu_conv_wgrad_rows_supported(C.byref(d)))
+            assert rows == (spec["image_dimensions"] == 3 and cpi <= 32 and cpo <= 64), (g.name, rows)
     assert kinds == {"classic", "ks"}
     # the kernel hint and the forced tile are honoured
     d = conv_desc(_lib.F16, _lib.F16, 16, (66, 66, 1), 256, 0, 256, 256, (64, 64, 1), (64, 64, 1), 256, 0, 256, 1, (3, 3, 1))

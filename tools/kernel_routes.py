@@ -48,9 +48,10 @@ def main(which="cfg3", hint=0):
         w5 = lib.hcu_conv_wgrad_tc5_supported(C.byref(d))
         ws = lib.hcu_conv_wgrad_ws_supported(C.byref(d))
         wt = lib.hcu_conv_wgrad_tc_supported(C.byref(d))
+        wr = int(bool(lib.hcu_conv_wgrad_rows_supported(C.byref(d))) and cpi <= 32 and cpo <= 64)   # the engine's routing limits
         print(f"{g.name:20s} {g.cin_t:4d}->{g.cout_t:4d} {str(g.in_sz):16s} {gf:6.1f} GF | fwd: {describe(lib, d)}")
         print(f"{'':55s} | dgrad: {describe(lib, dd)}")
-        print(f"{'':55s} | wgrad: tc5={w5} ws={ws} mma={wt}")
+        print(f"{'':55s} | wgrad: rows={wr} tc5={w5} ws={ws} mma={wt}  -> {'rows' if wr else 'tc5' if (w5 and cpi >= 32) else 'ws' if ws else 'mma' if wt else 'simt'}")
 
 
 if __name__ == "__main__":
