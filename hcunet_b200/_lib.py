@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HCUNET_LIB: an alternative build of the SAME library (A/B experiments: tools/build_variant.py); never a fallback
 LIB_PATH = os.environ.get("HCUNET_LIB") or os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 22
+ABI_VERSION = 23
 
 F32, BF16, F16, U8, U16, F64 = 0, 1, 2, 3, 4, 5
 BATCH_JOB_BYTES = 256
@@ -106,6 +106,7 @@ SIGNATURES = {
     "hcu_conv_wgrad_tc5_acc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
     "hcu_conv_wgrad_rows_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_wgrad_rows_acc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
+    "hcu_conv_wgrad_rows_bnb_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_wgrad_rows_bnb_acc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
     "hcu_conv_tc_pack_batch_build": [C.POINTER(HcuConvDesc), C.POINTER(HcuWeightMap), C.POINTER(I64), C.POINTER(I64), I32, P,
                                      C.POINTER(I32)],
@@ -197,7 +198,7 @@ def load():
     out._cdll = lib
     for name in SIGNATURES:
         raw = getattr(lib, name)
-        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_h2d_tile", "hcu_conv_tc_supported", "hcu_conv_wgrad_tc_supported", "hcu_conv_wgrad_tc5_supported", "hcu_conv_wgrad_ws_supported", "hcu_conv_wgrad_rows_supported",
+        setattr(out, name, raw if name in ("hcu_abi_version", "hcu_last_error", "hcu_launch_count", "hcu_h2d_tile", "hcu_conv_tc_supported", "hcu_conv_wgrad_tc_supported", "hcu_conv_wgrad_tc5_supported", "hcu_conv_wgrad_ws_supported", "hcu_conv_wgrad_rows_supported", "hcu_conv_wgrad_rows_bnb_supported",
                                          "hcu_conv_tc_packed_bytes", "hcu_conv_tc_describe", "hcu_conv_tc_bnbwd_supported", "hcu_conv_tc_pack_batch_build", "hcu_weight_scatter_batch_build") else _wrap(name, raw))
     _lib = out
     return out

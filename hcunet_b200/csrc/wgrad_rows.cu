@@ -808,6 +808,12 @@ extern "C" int hcu_conv_wgrad_rows_supported(const HcuConvDesc* d) {
   return why == nullptr ? 1 : 0;
 }
 
+extern "C" int hcu_conv_wgrad_rows_bnb_supported(const HcuConvDesc* d) {
+  if (d == nullptr) return 0;
+  wgr::Config c;
+  return wgr::configure(d, c, true) == nullptr ? 1 : 0;
+}
+
 static int wgrad_rows_launch(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* dy,
                              const void* y, const float* bn_scale, const float* bn_shift, const float* coef, float* wacc, void* stream) {
   HCU_CHECK_ARG(d && a && dy && wacc, "wgrad_rows: null pointer");

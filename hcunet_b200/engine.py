@@ -1022,8 +1022,8 @@ class UnetEngine:
         nin = B * g.in_sz[0] * g.in_sz[1] * g.in_sz[2] * g.cin_t
         note = (g.name, (nin + m * g.cout_t) * esz, 2 * m * T * g.cin_g * g.cout_g * g.groups)
         isc, ish = (a_xf[0], a_xf[1]) if a_xf is not None else (None, None)
-        if probe:   # would the row-stacked kernel (the one with the fused BatchNorm-backward apply) take this layer?
-            return self._rows_takes(d)
+        if probe:   # would the row-stacked kernel with the fused BatchNorm-backward apply take this layer?
+            return self._rows_takes(d) and a_xf is None and bool(self.lib.hcu_conv_wgrad_rows_bnb_supported(C.byref(d)))
         if bnb is not None:  # the fused launch also reads y: the apply pass it replaces read g and y and wrote dy
             note = (note[0], note[1] + m * g.cout_t * esz, note[2])
         return self._wgrad_dispatch(g.name + ".weight", wref, d, a_in, isc, ish, dy, self._wm_conv_fwd(g, bd), total, ns, note,

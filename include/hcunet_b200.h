@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 22
+#define HCU_ABI_VERSION 23
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -285,6 +285,7 @@ int hcu_conv_wgrad_rows_acc(const HcuConvDesc* d, const void* a, const float* a_
  * layer's gradient tensor and the re-read by the weight gradient.  bn_scale / bn_shift: the layer's BatchNorm as scale / shift
  * (the ReLU mask), coef: hcu_bn_bwd_finalize's [3][out_cpitch].
  * Replaces: BatchNorm + ReLU backward followed by the conv weight gradient (autograd of unet.py:259-265 / 246-250). */
+int hcu_conv_wgrad_rows_bnb_supported(const HcuConvDesc* d);
 int hcu_conv_wgrad_rows_bnb_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* g,
                                 const void* y, const float* bn_scale, const float* bn_shift, const float* coef, float* wacc,
                                 void* stream);
