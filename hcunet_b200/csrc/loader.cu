@@ -18,6 +18,7 @@ namespace hcu {
 namespace ld {
 
 constexpr int kTile = 32;
+constexpr int kYG = 8;   // y rows per CTA: the per-CTA lookup table (1024 float64 conversions) cost a quarter of a one-row CTA's work
 
 struct StackParams {
   const void* src;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256) load_stack_kernel(const StackParams p) {
   __shared__ uint4 tile[kTile][kTile + 1];        // [z][x] -> 8 halfs
   __shared__ __half lut[U8LUT ? 8 * 256 : 1];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int x0 = blockIdx.x * kTile, y = blockIdx.y;
+  const int x0 = blockIdx.x * kTile, y_lo = blockIdx.y * kYG, y_hi = min(p.Y, y_lo + kYG);
   const int b = blockIdx.z / p.nzt, z0 = (blockIdx.z - b * p.nzt) * kTile;
   const double inv_range = sizeof(TS) == 1 ? 1.0 / 256.0 : 1.0 / 65536.0;
   if (U8LUT) {
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256) load_stack_kernel(const StackParams p) {
   }
   const TS* src = reinterpret_cast<const TS*>(p.src);
   const int x = x0 + lane;
+  for (int y = y_lo; y < y_hi; ++y) {
   for (int zz = warp; zz < kTile; zz += 8) {
     const int z = z0 + zz;
     __align__(16) __half h[8];
@@ -82,6 +84,8 @@ __global__ void __launch_bounds__(256) load_stack_kernel(const StackParams p) {
       __half* o = p.dst + ((((size_t)b * p.X + xo) * p.Y + y) * p.Z + z) * p.Cp;
       *reinterpret_cast<uint4*>(o) = tile[lane][xx];
     }
+  }
+  __syncthreads();   // the tile is re-used by the next row
   }
 }
 
@@ -126,7 +130,7 @@ extern "C" int hcu_load_stack(const void* src, int32_t dtype_src, int64_t b, int
   HCU_CHECK_ARG(dtype_src == HCU_U8 || dtype_src == HCU_U16, "load_stack: the raw stack must be uint8 or uint16 (to_float, transforms.py:104-112)");
   HCU_CHECK_ARG(b > 0 && z > 0 && y > 0 && x > 0 && c > 0 && c <= 8, "load_stack: bad shape (1..8 channels)");
   HCU_CHECK_ARG(dst_cpitch == 8, "load_stack: the destination channel pitch is 8 (16-byte voxels)");
-  HCU_CHECK_ARG(y <= 65535 && b * ((z + 31) / 32) <= 65535, "load_stack: grid too large");
+  HCU_CHECK_ARG((y + ld::kYG - 1) / ld::kYG <= 65535 && b * ((z + 31) / 32) <= 65535, "load_stack: grid too large");
   HCU_CHECK_ARG((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (reinterpret_cast<uintptr_t>(src) & 7) == 0, "load_stack: unaligned pointer");
   ld::StackParams p;
   memset(&p, 0, sizeof(p));
@@ -136,7 +140,7 @@ extern "C" int hcu_load_stack(const void* src, int32_t dtype_src, int64_t b, int
     HCU_CHECK_ARG(stdv[i] != 0.0, "load_stack: std[%d] == 0", i);
     p.neg_mean[i] = -mean[i]; p.std_[i] = stdv[i];
   }
-  dim3 grid((x + ld::kTile - 1) / ld::kTile, y, (unsigned)(b * p.nzt));
+  dim3 grid((x + ld::kTile - 1) / ld::kTile, (y + ld::kYG - 1) / ld::kYG, (unsigned)(b * p.nzt));
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype_src == HCU_U8) ld::load_stack_kernel<uint8_t, true><<<grid, 256, 0, st>>>(p);
   else ld::load_stack_kernel<uint16_t, false><<<grid, 256, 0, st>>>(p);
