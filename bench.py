@@ -399,9 +399,14 @@ def main_ours(args):
     # the optimiser holds ONE flat parameter (every nn.Parameter is a view of it; its gradient is the engine's flat gradient
     # buffer): one elementwise Adam launch instead of a multi-tensor pass over 136 tensors + 136 step counters (0.10 -> 0.01 ms)
     flat = H.FlatParameters(model) if os.environ.get("HCUNET_FLAT_ADAM", "1") != "0" else None
-    opt = torch.optim.Adam([flat.flat] if flat is not None else model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
-    if flat is not None and os.environ.get("HCUNET_GUARD", "1") != "0":
-        flat.guard(opt)     # skip-step on non-finite gradients (fp16 storage), one pass over the flat gradient per step
+    own_adam = flat is not None and os.environ.get("HCUNET_OWN_ADAM", "1") != "0"
+    if own_adam:
+        # the whole optimiser step (non-finite check of the fp16-storage path + Adam) is ONE launch of the library (hcu_adam_flat)
+        opt = H.FlatAdam(flat, lr=1e-3)
+    else:
+        opt = torch.optim.Adam([flat.flat] if flat is not None else model.parameters(), lr=1e-3, fused=True, capturable=use_graph)
+        if flat is not None and os.environ.get("HCUNET_GUARD", "1") != "0":
+            flat.guard(opt)     # skip-step on non-finite gradients (fp16 storage), one pass over the flat gradient per step
 
     def zero_grads():
         if flat is not None:
@@ -626,7 +631,8 @@ def main_ours(args):
                 "data": "synthetic (seeded), random-init weights",
                 "config": {"workload": WORKLOAD, "patch": [C, X, Y, Z], "batch_per_gpu": B, "global_batch": B * world,
                            "precision": args.precision, "parallelism": f"dp{world}",
-                           "optimizer": "Adam(fused) lr 1e-3" + (" on the flat parameter buffer (hcunet_b200.FlatParameters)" if flat is not None else ""),
+                           "optimizer": ("hcunet_b200.FlatAdam lr 1e-3 (one launch: skip-step check + Adam on the flat parameter buffer)" if own_adam else
+                                         "Adam(fused) lr 1e-3" + (" on the flat parameter buffer (hcunet_b200.FlatParameters)" if flat is not None else "")),
                            "gradient_exchange": None if world == 1 else (
                                "NCCL all-reduce (mean, fp32, in place on the engine's flat gradient buffer) in two buckets launched "
                                "from inside backward on a communication stream, captured in the step's CUDA graph"

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 # HCUNET_LIB: an alternative build of the SAME library (A/B experiments: tools/build_variant.py); never a fallback
 LIB_PATH = os.environ.get("HCUNET_LIB") or os.path.join(HERE, "libhcunet_b200.so")
-ABI_VERSION = 23
+ABI_VERSION = 24
 
 F32, BF16, F16, U8, U16, F64 = 0, 1, 2, 3, 4, 5
 BATCH_JOB_BYTES = 256
@@ -108,6 +108,7 @@ SIGNATURES = {
     "hcu_conv_wgrad_rows_acc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P],
     "hcu_conv_wgrad_rows_bnb_supported": [C.POINTER(HcuConvDesc)],
     "hcu_conv_wgrad_rows_bnb_acc": [C.POINTER(HcuConvDesc), P, P, P, P, P, P, P, P, P, P],
+    "hcu_adam_flat": [P, P, P, P, I64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, P, P, P],
     "hcu_conv_tc_pack_batch_build": [C.POINTER(HcuConvDesc), C.POINTER(HcuWeightMap), C.POINTER(I64), C.POINTER(I64), I32, P,
                                      C.POINTER(I32)],
     "hcu_conv_tc_pack_batch": [P, I32, I32, P, P, P],

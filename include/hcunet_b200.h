@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define HCU_ABI_VERSION 23
+#define HCU_ABI_VERSION 24
 
 /* Per-channel reduction buffers (`stats` of the convolutions, `sums` of hcu_bn_bwd_stats) are fp64 and BINNED:
  * HCU_STAT_BINS consecutive [2][c] blocks; a producing CTA adds its partial sums into ONE bin (same-address L2 atomics
@@ -289,6 +289,16 @@ int hcu_conv_wgrad_rows_bnb_supported(const HcuConvDesc* d);
 int hcu_conv_wgrad_rows_bnb_acc(const HcuConvDesc* d, const void* a, const float* a_scale, const float* a_shift, const void* g,
                                 const void* y, const float* bn_scale, const float* bn_shift, const float* coef, float* wacc,
                                 void* stream);
+
+/* ---- optimiser -------------------------------------------------------------------------------
+ * Adam on ONE flat fp32 parameter buffer (hcunet_b200.FlatParameters: every nn.Parameter is a view of it, its gradient is the
+ * engine's flat gradient buffer), one launch per step, with the skip-step check of fp16-storage training inside: if any gradient
+ * is inf / NaN nothing is touched and `step` is not advanced.  torch.optim.Adam's arithmetic (amsgrad = False, maximize = False),
+ * `weight_decay` as its L2 term.  step: device int32 (steps taken so far); scratch: 2 device words the call zeroes, scratch[0]
+ * reads 1.0f afterwards when the step was skipped.
+ * Replaces: torch.optim.Adam.step() of the reference's training loop (tests/r_unet_test.py:24, hcat/train scripts). */
+int hcu_adam_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float weight_decay, int32_t* step, float* scratch, void* stream);
 
 /* ---- weight layout transforms -------------------------------------------------------------
  * Generic strided gather between a reference-layout parameter and a packed GEMM-B tensor

@@ -648,3 +648,44 @@ def test_pooled_bn_backward_statistics_match_the_scattered_gradient(shape, c, po
     want2 = (g * (yc - mean.double().cpu()) * invstd.double().cpu()).sum(dim=(0, 1, 2, 3))
     den = max(float(want1.abs().max()), float(want2.abs().max()), 1.0)
     assert float((got[0] - want1).abs().max()) <= 1e-4 * den and float((got[1] - want2).abs().max()) <= 1e-4 * den
+
+
+# ---- Adam on the flat parameter buffer (optim.cu) ------------------------------------------------------------------
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_flat_adam_matches_torch_adam_and_skips_non_finite_steps(wd):
+    """hcu_adam_flat against torch.optim.Adam on the same parameters and gradients (5 steps, odd length: scalar tail), then
+    one step with an inf gradient: parameters, moments and the step counter must not move."""
+    import hcunet_b200 as H
+
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Linear(53, 11)).cuda()      # 2 607 parameters, not a multiple of 4
+    ref = torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Linear(53, 11)).cuda()
+    ref.load_state_dict(net.state_dict())
+    fp = H.FlatParameters(net)
+    opt = H.FlatAdam(fp, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    topt = torch.optim.Adam(ref.parameters(), lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    for _ in range(5):
+        g = torch.randn(fp.numel, device="cuda", generator=gen)
+        fp.flat.grad = g
+        off = 0
+        for p in ref.parameters():
+            p.grad = g[off:off + p.numel()].view_as(p).clone()
+            off += p.numel()
+        opt.step()
+        topt.step()
+    assert not opt.skipped() and int(opt.step_count.item()) == 5
+    want = torch.cat([p.detach().reshape(-1) for p in ref.parameters()])
+    assert rel_l2(fp.flat.detach(), want) <= 1e-6, rel_l2(fp.flat.detach(), want)
+    for p, q in zip(net.parameters(), ref.parameters()):      # the model's parameters are views of the flat buffer
+        assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+    before = (fp.flat.detach().clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone())
+    g = torch.randn(fp.numel, device="cuda", generator=gen)
+    g[1234] = float("inf")
+    fp.flat.grad = g
+    opt.step()
+    assert opt.skipped() and int(opt.step_count.item()) == 5
+    assert torch.equal(fp.flat.detach(), before[0]) and torch.equal(opt.exp_avg, before[1]) and torch.equal(opt.exp_avg_sq, before[2])
+    g[1234] = 0.0
+    opt.step()
+    assert not opt.skipped() and int(opt.step_count.item()) == 6
