@@ -722,7 +722,9 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
   // look-ahead: ~128 KB of loads in flight per SM (Little's law at ~2 us of loaded-HBM latency: with 64 KB the HBM-bound first-level
   // layers ran at 17 B per clock and SM; d0.conv2 73.7 -> 65.6 us, the fused first layer 150 -> 131 us with 8 slots ahead)
   static const int la_env = env_int("HCU_ROWS_LA", 0);
-  int la = la_env > 0 ? la_env : std::max(2, std::min(10, (128 * 1024 + p.slot_bytes - 1) / p.slot_bytes));
+  static const int il_kb = env_int("HCU_ROWS_IL_KB", 128);   // in-flight target of the interleaved (16 / 32-channel) layers
+  const int fly = (p.il ? il_kb : 128) * 1024;
+  int la = la_env > 0 ? la_env : std::max(2, std::min(10, (fly + p.slot_bytes - 1) / p.slot_bytes));
   for (;; --la) {
     if (la < 1) return "does not fit in shared memory";
     p.S = span + la;
