@@ -689,3 +689,50 @@ def test_flat_adam_matches_torch_adam_and_skips_non_finite_steps(wd):
     g[1234] = 0.0
     opt.step()
     assert not opt.skipped() and int(opt.step_count.item()) == 6
+
+
+def test_wgrad_rows_randomised_geometry_sweep():
+    """Seeded sweep over the geometry corners of wgrad_rows.cu: ragged last row tile / K group, step ranges that cross tiles and
+    images, merged and 16-byte TMA boxes, one to eight dy planes, plain and interleaved input planes, with and without the fused
+    BatchNorm + ReLU of the input.  (compute-sanitizer is closed on this pool: wide coverage against the fp32 op stands in.)"""
+    import random
+
+    from hcunet_b200 import _lib
+    from hcunet_b200.engine import conv_desc
+
+    lib = _lib.load()
+    rng = random.Random(20261019)
+    g = torch.Generator().manual_seed(77)
+    done = 0
+    for _ in range(60):
+        cin = rng.choice([3, 4, 8, 16, 24, 32])
+        cout = rng.choice([1, 8, 16, 32, 64] if cin > 8 else [1, 8, 16, 32])
+        k = rng.choice([(3, 3, 2), (3, 3, 1), (1, 1, 1), (2, 2, 2), (3, 1, 2)])
+        n = rng.choice([1, 2, 3])
+        isz = (rng.randint(k[0], 9), rng.randint(k[1] + 1, 45), rng.randint(k[2] + 7, 70))
+        osz = tuple(isz[i] - k[i] + 1 for i in range(3))
+        cp = (cin + 7) // 8 * 8
+        cop = (cout + 7) // 8 * 8
+        d = conv_desc(_lib.F16, _lib.F16, n, isz, cp, 0, cin, cin, osz, osz, cop, 0, cout, 1, k, (1, 1, 1), in_relu=1)
+        if not lib.hcu_conv_wgrad_rows_supported(C.byref(d)):
+            continue
+        x = h16(torch.randn((n, cin) + isz, generator=g))
+        dy = h16(torch.randn((n, cout) + osz, generator=g))
+        affine = rng.random() < 0.5
+        sc, sh = torch.rand(cin, generator=g) + 0.5, torch.randn(cin, generator=g) * 0.3
+        a = h16(F.relu(x * sc.view(1, -1, 1, 1, 1) + sh.view(1, -1, 1, 1, 1))) if affine else x
+        ref = torch.nn.grad.conv3d_weight(a, (cout, cin) + k, dy)
+        xin, dyin = to_cl(x, cp), to_cl(dy, cop)
+        isc = ish = None
+        if affine:
+            isc = torch.zeros(cp, device="cuda"); ish = torch.zeros(cp, device="cuda")
+            isc[:cin], ish[:cin] = sc.cuda(), sh.cuda()
+        T = k[0] * k[1] * k[2]
+        wacc = torch.zeros((T * cin * cout,), device="cuda")
+        _lib.check(lib.hcu_conv_wgrad_rows_acc(C.byref(d), P(xin), P(isc), P(ish), P(dyin), P(wacc), stream()), "wgrad_rows")
+        torch.cuda.synchronize()
+        got = wacc.view(k[0], k[1], k[2], cin, cout).permute(4, 3, 0, 1, 2).cpu()
+        assert torch.isfinite(got).all(), (cin, cout, k, n, isz)
+        assert rel_l2(got, ref) <= 1e-5, (rel_l2(got, ref), cin, cout, k, n, isz, affine)
+        done += 1
+    assert done >= 30, done
