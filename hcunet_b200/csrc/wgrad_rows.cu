@@ -78,6 +78,10 @@ struct Params {
   // a staging area (one TMA box with a 16 P-byte inner run) and the transform warps re-lay it as [row][plane][z][8 channels]
   // (+ BatchNorm + ReLU on the input side): M = 128 = (16 / P rows) x P planes x 8 channels, N = RP x PG x 8.
   int il, sbo_a, sbo_b, off_sa, off_sg, ZOA, ZOG, tx_cols;
+  // stride phases of a transposed convolution on the dy side (interleaved mode): dy plane q = phase * PPH + plane of the phase; a
+  // CTA's PG planes arrive as NB boxes of PB planes, one per phase touched (each phase is a strided sub-lattice: its own tensor map);
+  // low-side zero padding of the input (box origin shifted; transformed positions outside the tensor are zeroed by the re-layout)
+  int PPH, NB, PB, pad_x, pad_y, pad_z, IX, IY, IZ;
   int dbg;                 // HCU_ROWS_DEBUG (timing experiments only): 1 = no MMA issue
   int nper;                // MMAs per x tap and step: (tz, input plane, dy plane, K group), K group fastest
   // per MMA of an x tap, read through the constant bank with a uniform index (the issuing warp runs on the uniform datapath):
@@ -115,6 +119,10 @@ __device__ __forceinline__ uint4 bn_relu8(uint4 v, const float* sc, const float*
 }
 
 // One contiguous piece of a CTA's step range inside one (image, row tile)
+struct alignas(64) GMaps {
+  CUtensorMap m[8];   // one per stride phase (m[0] alone without phases)
+};
+
 struct Segment {
   int n, yt, xb, nout;
 };
@@ -247,7 +255,7 @@ __device__ __forceinline__ void mma_role(const Params& p, const MmaCtx& c) {
 // (compile-time: the transform warps keep their per-channel vectors in registers, one set per variant)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
-wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmY,
+wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ GMaps tmGs, const __grid_constant__ CUtensorMap tmY,
                   const __grid_constant__ Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -296,7 +304,7 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int idx = 0, f = f0;
     uint32_t par = 1, dst = ring;
     const uint32_t a_bytes = il ? (uint32_t)p.a_box_bytes : (uint32_t)(p.P * p.a_box_bytes);
-    const uint32_t ag_bytes = a_bytes + (il ? (uint32_t)p.g_box_bytes : (uint32_t)((bnb ? 2 : 1) * p.PG * p.g_box_bytes));
+    const uint32_t ag_bytes = a_bytes + (il ? (uint32_t)(p.NB * p.g_box_bytes) : (uint32_t)((bnb ? 2 : 1) * p.PG * p.g_box_bytes));
     const int c0g = 8 * kind * p.PG;
     Segment s;
     while (next_segment(p, f, f1, s)) {
@@ -309,13 +317,18 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const bool with_g = j >= span - 1;
           mbar_expect_tx(bar, with_g ? ag_bytes : a_bytes);
           if (il) {  // one box per tile: all channel planes of the rows, [row][z][C]
-            tma_load_5d(dst + (uint32_t)p.off_sa, &tmA, 0, 0, y0, s.xb + j, s.n, bar);
-            if (with_g) tma_load_5d(dst + (uint32_t)p.off_sg, &tmG, c0g, 0, y0, s.xb + j - (span - 1), s.n, bar);
+            tma_load_5d(dst + (uint32_t)p.off_sa, &tmA, 0, -p.pad_z, y0 - p.pad_y, s.xb + j - p.pad_x, s.n, bar);
+            if (with_g)
+              for (int bx = 0; bx < p.NB; ++bx) {   // one box per stride phase touched
+                const int q = kind * p.PG + bx * p.PB, ph = q / p.PPH;
+                tma_load_5d(dst + (uint32_t)(p.off_sg + bx * p.g_box_bytes), &tmGs.m[ph], 8 * (q - ph * p.PPH), 0, y0, s.xb + j - (span - 1), s.n,
+                            bar);
+              }
           } else {
           for (int pl = 0; pl < p.P; ++pl) tma_load_5d(dst + (uint32_t)(pl * p.a_plane_bytes), &tmA, 8 * pl, 0, y0, s.xb + j, s.n, bar);
           if (with_g) {
             for (int q = 0; q < p.PG; ++q)
-              tma_load_5d(dst + (uint32_t)(p.off_g + q * p.g_plane_bytes), &tmG, c0g + 8 * q, 0, y0, s.xb + j - (span - 1), s.n, bar);
+              tma_load_5d(dst + (uint32_t)(p.off_g + q * p.g_plane_bytes), &tmGs.m[0], c0g + 8 * q, 0, y0, s.xb + j - (span - 1), s.n, bar);
             if (bnb)
               for (int q = 0; q < p.PG; ++q)
                 tma_load_5d(dst + (uint32_t)(p.off_y + q * p.g_plane_bytes), &tmY, c0g + 8 * q, 0, y0, s.xb + j - (span - 1), s.n, bar);
@@ -341,11 +354,10 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       // e = t, t + 256, ...: its plane is fixed (256 % planes == 0), (row, z) walk incrementally
       const int xt = tid - 128;
       const int P = p.P, PG = p.PG;
-      const int pla = xt % P, plg = xt % PG;
-      const int na = p.RA * p.ZAP * P, ng = p.RP * p.ZGP * PG;
-      const int sa = 256 / P, sg = 256 / PG;                       // pixels advanced per 256 chunks
+      const int pla = xt % P;
+      const int na = p.RA * p.ZAP * P;
+      const int sa = 256 / P;                                      // pixels advanced per 256 chunks
       const int a_r0 = (xt / P) / p.ZAP, a_z0 = (xt / P) - a_r0 * p.ZAP, a_rs = sa / p.ZAP, a_zs = sa - a_rs * p.ZAP;
-      const int g_r0 = (xt / PG) / p.ZGP, g_z0 = (xt / PG) - g_r0 * p.ZGP, g_rs = sg / p.ZGP, g_zs = sg - g_rs * p.ZGP;
       float sc[8], sh[8];
       if (xf) {
 #pragma unroll
@@ -364,9 +376,19 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint4* src = reinterpret_cast<const uint4*>(slot + p.off_sa);
             uint4* dst = reinterpret_cast<uint4*>(slot);
             int row = a_r0, z = a_z0;
+            // transformed positions outside the tensor (zero padding) must stay zero: relu(shift) would leak into the taps
+            const bool padded = xf && (p.pad_x | p.pad_y | p.pad_z) != 0;
+            const int xt_in = s.xb + j - p.pad_x, y_in0 = s.yt * p.RP - p.pad_y;
+            const bool x_in = xt_in >= 0 && xt_in < p.IX;
             for (int e = xt; e < na; e += 256) {
               uint4 v = src[e];
-              if (xf) v = bn_relu8(v, sc, sh, relu);
+              if (xf) {
+                v = bn_relu8(v, sc, sh, relu);
+                if (padded) {
+                  const int zi = z - p.pad_z, yi = y_in0 + row;
+                  if (!x_in || zi < 0 || zi >= p.IZ || yi < 0 || yi >= p.IY) v = make_uint4(0u, 0u, 0u, 0u);
+                }
+              }
               dst[(row * P + pla) * p.ZOA + z] = v;
               z += a_zs; row += a_rs;
               if (z >= p.ZAP) { z -= p.ZAP; ++row; }
@@ -375,11 +397,17 @@ wgrad_rows_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (j >= span - 1) {
             const uint4* src = reinterpret_cast<const uint4*>(slot + p.off_sg);
             uint4* dst = reinterpret_cast<uint4*>(slot + p.off_g);
-            int row = g_r0, z = g_z0;
-            for (int e = xt; e < ng; e += 256) {
-              dst[(row * PG + plg) * p.ZOG + z] = src[e];
-              z += g_zs; row += g_rs;
-              if (z >= p.ZGP) { z -= p.ZGP; ++row; }
+            // staging: NB boxes of [row][z][PB planes]; chunk e of a box -> dy plane bx * PB + (e mod PB)
+            const int PB = p.PB, nb1 = p.RP * p.ZGP * PB;
+            const int plb = xt % PB, sb = 256 / PB;
+            const int b_r0 = (xt / PB) / p.ZGP, b_z0 = (xt / PB) - b_r0 * p.ZGP, b_rs = sb / p.ZGP, b_zs = sb - b_rs * p.ZGP;
+            for (int bx = 0; bx < p.NB; ++bx) {
+              int row = b_r0, z = b_z0;
+              for (int e = xt; e < nb1; e += 256) {
+                dst[(row * PG + bx * PB + plb) * p.ZOG + z] = src[bx * nb1 + e];
+                z += b_zs; row += b_rs;
+                if (z >= p.ZGP) { z -= p.ZGP; ++row; }
+              }
             }
           }
           fence_proxy_async();
@@ -593,7 +621,12 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
   memset(&p, 0, sizeof(p));
   if (d->dtype_in != HCU_F16 || d->dtype_out != HCU_F16) return "fp16 only";
   if (d->groups != 1) return "groups != 1";
-  if (d->iphase || d->ophase) return "stride phases";
+  if (d->iphase) return "input stride phases";
+  int dps[3];
+  for (int i = 0; i < 3; ++i) dps[i] = std::max(1, (d->ophase >> (8 * i)) & 0xff);
+  const int nph = dps[0] * dps[1] * dps[2];
+  if (nph > 8) return "more than 8 stride phases";
+  if (nph > 1 && (d->cout != d->out_cpitch || d->cout % nph || (d->cout / nph) % 8)) return "ophase needs 8-channel aligned phases";
   if (d->in_cpitch % 8 != 0 || d->in_c_off != 0 || d->cin > d->in_cpitch) return "input channel layout";
   if (d->out_cpitch % 8 != 0 || d->out_c_off != 0 || d->cout > d->out_cpitch) return "dy channel layout";
   const int P = d->in_cpitch / 8, Po = d->out_cpitch / 8;
@@ -601,11 +634,15 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
   if (P != 1 && P != 2 && P != 4) return "input channel pitch above 32";
   if (Po != 1 && Po != 2 && Po != 4 && !(Po == 8 && P > 1)) return "dy channel pitch above 32 (64 with interleaved input planes)";
   if (P > maxp || Po > 2 * maxp) return "channel pitch above HCU_ROWS_MAXP";
+  bool padded = false;
   for (int i = 0; i < 3; ++i) {
-    if (d->istep[i] != 1 || d->ostep[i] != 1 || d->ooff[i] != 0 || d->out_tsize[i] != d->out_size[i]) return "strided";
-    if (d->pad[i] != 0) return "padding";  // a transformed zero-filled position would not be zero
-    if (d->in_size[i] != d->out_size[i] + (d->taps[i] - 1) * d->dil[i]) return "not a valid convolution";
+    if (d->istep[i] != 1 || d->ostep[i] != dps[i] || d->ooff[i] != 0 || d->out_tsize[i] != d->out_size[i] * dps[i]) return "strided";
+    if (d->pad[i] < 0 || d->pad[i] > (d->taps[i] - 1) * d->dil[i]) return "padding beyond the taps' reach";
+    padded = padded || d->pad[i] != 0;
+    if (d->pad[i] == 0 && d->in_size[i] != d->out_size[i] + (d->taps[i] - 1) * d->dil[i]) return "not a valid convolution";
   }
+  // padding and stride phases (the transposed convolutions' weight gradients) are handled by the interleaved mode only
+  if ((padded || nph > 1) && (P == 1 || bnb)) return "padding / stride phases need interleaved input planes";
   p.N = d->batch; p.OX = d->out_size[0]; p.OY = d->out_size[1];
   const int OZ = d->out_size[2];
   p.cin = d->cin; p.cout = d->cout; p.P = P;
@@ -632,6 +669,10 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
   static const int il_on = env_int("HCU_ROWS_IL", 1);
   const int oy_even = round_up(p.OY, 2);
   p.il = (P > 1 && il_on && !bnb) ? 1 : 0;
+  if ((padded || nph > 1) && !p.il) return "padding / stride phases need interleaved input planes";
+  p.PPH = Po / nph;   // dy planes per stride phase
+  p.pad_x = d->pad[0]; p.pad_y = d->pad[1]; p.pad_z = d->pad[2];
+  p.IX = d->in_size[0]; p.IY = d->in_size[1]; p.IZ = d->in_size[2];
   double best = 1e30;
   int best_pg = 0, best_rp = 0;
   if (p.il) {
@@ -675,13 +716,15 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
     p.ZOA = round_up(p.ZAP, 8) + 1; p.ZOG = round_up(p.ZGP, 8) + 1;
     p.sbo_a = p.ZOA * 16; p.sbo_b = p.ZOG * 16;
     p.a_box_bytes = p.RA * p.ZAP * 16 * P;       // one box: all planes
-    p.g_box_bytes = p.RP * p.ZGP * 16 * p.PG;
+    p.PB = std::min(p.PG, p.PPH); p.NB = p.PG / p.PB;   // dy boxes: one per stride phase touched by this CTA's planes
+    p.g_box_bytes = p.RP * p.ZGP * 16 * p.PB;
+    if (p.g_box_bytes % 128 != 0) return "dy box not 128-byte aligned";   // (ZGP is a multiple of 16: always true)
     const int opa = round_up(16 * p.ZOA * 16, 128);                 // operand: 16 groups
     const int opg = round_up(p.RP * p.PG * p.ZOG * 16, 128);
     p.off_g = opa;
     p.off_sa = p.off_g + opg;
     p.off_sg = p.off_sa + round_up(p.a_box_bytes, 128);
-    p.slot_bytes = p.off_sg + round_up(p.g_box_bytes, 128);
+    p.slot_bytes = p.off_sg + round_up(p.NB * p.g_box_bytes, 128);
     p.off_y = 0; p.bnb = 0;
     p.a_plane_bytes = 0; p.g_plane_bytes = 0;
     p.nper = p.KZ * p.ZC;
@@ -798,6 +841,33 @@ static const char* encode_map(CUtensorMap* tm, const void* base, int cpitch, int
   return nullptr;
 }
 
+// dy of a transposed convolution: stride phase (fx, fy, fz) is the sub-lattice o * s + f of the full-resolution tensor
+// [N][TX][TY][TZ][cr]; one map per phase, coordinates in coarse positions
+static const char* encode_phase_map(CUtensorMap* tm, const void* base, int cr, const int* tsize, const int* osize, const int* dps,
+                                    const int* f, int N, int boxc, int boxz, int rows) {
+  const long long ez = cr, ey = ez * tsize[2], ex = ey * tsize[1], en = ex * tsize[0];   // element strides of the fine tensor
+  const char* b = reinterpret_cast<const char*>(base) + 2 * (f[0] * ex + f[1] * ey + f[2] * ez);
+  cuuint64_t gdim[5] = {(cuuint64_t)cr, (cuuint64_t)osize[2], (cuuint64_t)osize[1], (cuuint64_t)osize[0], (cuuint64_t)N};
+  cuuint64_t gstr[4] = {(cuuint64_t)(2 * ez * dps[2]), (cuuint64_t)(2 * ey * dps[1]), (cuuint64_t)(2 * ex * dps[0]), (cuuint64_t)(2 * en)};
+  cuuint32_t box[5] = {(cuuint32_t)boxc, (cuuint32_t)boxz, (cuuint32_t)rows, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+  if ((reinterpret_cast<uintptr_t>(b) & 15) != 0) return "dy phase not 16-byte aligned";
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || fn == nullptr ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return "cuTensorMapEncodeTiled not available from this driver";
+  }
+  const CUresult r = reinterpret_cast<EncodeFn>(fn)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<char*>(b), gdim, gstr, box, estr,
+                                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return "cuTensorMapEncodeTiled failed (dy phase)";
+  return nullptr;
+}
+
 }  // namespace wgr
 }  // namespace hcu
 
@@ -839,14 +909,29 @@ static int wgrad_rows_launch(const HcuConvDesc* d, const void* a, const float* a
   static long long* prof_buf = nullptr;
   if (prof_env && prof_buf == nullptr) cudaMalloc(&prof_buf, 16 * sizeof(long long));
   p.prof = prof_env ? prof_buf : nullptr;
-  CUtensorMap tmA, tmG, tmY;
+  CUtensorMap tmA, tmY;
+  wgr::GMaps tmGs;
   why = wgr::encode_map(&tmA, a, d->in_cpitch, d->in_size[2], d->in_size[1], d->in_size[0], d->batch, c.merged_a, p.ZAP, p.RA,
                         p.il ? 8 * p.P : 8);
+  {
+    int dps[3], nph = 1;
+    for (int i = 0; i < 3; ++i) { dps[i] = std::max(1, (d->ophase >> (8 * i)) & 0xff); nph *= dps[i]; }
+    if (why == nullptr && nph == 1) {
+      why = wgr::encode_map(&tmGs.m[0], dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g, p.ZGP, p.RP,
+                            p.il ? 8 * p.PB : 8);
+      for (int i = 1; i < 8; ++i) tmGs.m[i] = tmGs.m[0];
+    } else if (why == nullptr) {
+      for (int ph = 0; ph < 8 && why == nullptr; ++ph) {
+        int r = ph % nph;
+        const int fz = r % dps[2]; r /= dps[2];
+        const int f[3] = {r / dps[1], r % dps[1], fz};
+        why = wgr::encode_phase_map(&tmGs.m[ph], dy, d->out_cpitch / nph, d->out_tsize, d->out_size, dps, f, d->batch, 8 * p.PB, p.ZGP, p.RP);
+      }
+    }
+  }
   if (why == nullptr)
-    why = wgr::encode_map(&tmG, dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g, p.ZGP, p.RP,
-                          p.il ? 8 * p.PG : 8);
-  if (why == nullptr)
-    why = wgr::encode_map(&tmY, bnb ? y : dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g, p.ZGP, p.RP);
+    why = wgr::encode_map(&tmY, bnb ? y : dy, d->out_cpitch, d->out_size[2], d->out_size[1], d->out_size[0], d->batch, c.merged_g && !d->ophase,
+                          p.ZGP, p.RP);
   if (why != nullptr) {
     set_error("wgrad_rows: %s", why);
     return HCU_ERR_CUDA;
@@ -869,10 +954,10 @@ static int wgrad_rows_launch(const HcuConvDesc* d, const void* a, const float* a
               p.steps_per_cta, (int)c.merged_a, (int)c.merged_g, p.bnb, p.il);
   }
   const dim3 grid((unsigned)c.gx, (unsigned)c.kinds);
-  if (p.il) wgr::wgrad_rows_kernel<3><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
-  else if (bnb) wgr::wgrad_rows_kernel<2><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
-  else if (a_scale != nullptr) wgr::wgrad_rows_kernel<1><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
-  else wgr::wgrad_rows_kernel<0><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmG, tmY, p);
+  if (p.il) wgr::wgrad_rows_kernel<3><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmGs, tmY, p);
+  else if (bnb) wgr::wgrad_rows_kernel<2><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmGs, tmY, p);
+  else if (a_scale != nullptr) wgr::wgrad_rows_kernel<1><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmGs, tmY, p);
+  else wgr::wgrad_rows_kernel<0><<<grid, wgr::kThreads, p.smem_bytes, (cudaStream_t)stream>>>(tmA, tmGs, tmY, p);
   HCU_CHECK_LAUNCH("wgrad_rows");
   if (prof_env) {  // timing experiments: synchronous read-back of the stamps
     long long h[16];

@@ -736,3 +736,40 @@ def test_wgrad_rows_randomised_geometry_sweep():
         assert rel_l2(got, ref) <= 1e-5, (rel_l2(got, ref), cin, cout, k, n, isz, affine)
         done += 1
     assert done >= 30, done
+
+
+@pytest.mark.parametrize("case", [(2, 16, 8, (9, 21, 17), (2, 2, 2), (2, 2, 1), True),      # up_steps.3.up_conv shape class
+                                  (1, 32, 16, (7, 13, 19), (2, 2, 2), (2, 2, 1), True),     # 64 virtual dy channels, two CTA kinds
+                                  (2, 16, 8, (6, 14, 12), (2, 2, 2), (2, 2, 2), False),     # eight phases, no taps left
+                                  (1, 32, 8, (5, 11, 16), (4, 4, 2), (2, 2, 1), False)])    # (2,2,2) taps per phase, padding in x and y
+def test_wgrad_rows_transposed_conv_phases_agree_with_the_mma_kernel(case):
+    """Weight gradient of a ConvTranspose with its stride phases folded into the dy channels (HcuConvDesc.ophase) and the low-side
+    padding its taps need: the TMA-fed row-stacked kernel (one tensor map per phase, padded positions zeroed after the fused
+    BatchNorm + ReLU) against wgrad_mma.cu on the same descriptor."""
+    from hcunet_b200 import _lib
+    from hcunet_b200.engine import conv_desc
+
+    lib = _lib.load()
+    n, cin, cout, isz, k, s, affine = case
+    gen = torch.Generator().manual_seed(91)
+    nph = s[0] * s[1] * s[2]
+    J = tuple(k[i] // s[i] for i in range(3))
+    osz = tuple((isz[i] - 1) * s[i] + k[i] for i in range(3))
+    Q = tuple(osz[i] // s[i] for i in range(3))
+    x = to_cl(h16(torch.randn((n, cin) + isz, generator=gen)))
+    dy = to_cl(h16(torch.randn((n, cout) + osz, generator=gen)))
+    d = conv_desc(_lib.F16, _lib.F16, n, isz, cin, 0, cin, cin, Q, osz, nph * cout, 0, nph * cout, 1, J,
+                  pad=tuple(j - 1 for j in J), ostep=s, in_relu=int(affine))
+    d.ophase = s[0] | (s[1] << 8) | (s[2] << 16)
+    isc = ish = None
+    if affine:
+        isc = (torch.rand(cin, generator=gen) + 0.5).cuda(); ish = (torch.randn(cin, generator=gen) * 0.3).cuda()
+    assert lib.hcu_conv_wgrad_rows_supported(C.byref(d)) == 1 and lib.hcu_conv_wgrad_tc_supported(C.byref(d)) == 1
+    T = J[0] * J[1] * J[2]
+    want = torch.zeros(T * cin * nph * cout, device="cuda")
+    _lib.check(lib.hcu_conv_wgrad_tc_acc(C.byref(d), P(x), P(isc), P(ish), P(dy), P(want), stream()), "wgrad_tc")
+    got = torch.zeros_like(want)
+    _lib.check(lib.hcu_conv_wgrad_rows_acc(C.byref(d), P(x), P(isc), P(ish), P(dy), P(got), stream()), "wgrad_rows")
+    torch.cuda.synchronize()
+    assert torch.isfinite(got).all() and float(want.abs().max()) > 0
+    assert rel_l2(got, want) <= 1e-5, rel_l2(got, want)
