@@ -52,7 +52,12 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(const AdamParams a) {
     if (blockIdx.x == 0) atomicAdd(a.step, 1);   // every CTA reads t after the barrier; taken back below when the step is skipped
     __threadfence();
     atomicAdd(a.barrier, 1u);
-    while (*reinterpret_cast<volatile unsigned*>(a.barrier) < gridDim.x) __nanosleep(32);
+    // bounded: a grid that is not fully resident (it always is: at most one 256-thread CTA per SM) traps instead of hanging the GPU
+    const long long t0 = clock64();
+    while (*reinterpret_cast<volatile unsigned*>(a.barrier) < gridDim.x) {
+      __nanosleep(32);
+      if (clock64() - t0 > 4000000000ll) __trap();
+    }
     __threadfence();
   }
   __syncthreads();
