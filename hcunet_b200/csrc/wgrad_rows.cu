@@ -24,14 +24,26 @@
 // positions outside the tensor (z >= OZ of the last K group, rows >= OY of the last tile) are zero-filled by the TMA
 // unit, which is all the masking the formulation needs: a zero dy element kills whatever its partner is.
 //
+// Interleaved mode (16 / 32 input channels): M groups must be ONE stride apart, so the channel planes of a row become groups
+// [row][plane][z][8]: the natural [row][z][C] tile lands in a staging area (one box with a 16 P-byte inner run) and the transform
+// warps re-lay it -- M = (16 / P rows) x P planes, N = RP rows x PG planes, one accumulator per (tx, tz).  The same mode takes the
+// transposed convolutions' weight gradients: the stride phases folded into the dy channels (HcuConvDesc.ophase) are one tensor map
+// per phase, low-side zero padding is a shifted box origin (transformed positions outside the tensor are zeroed by the re-layout).
+//
 // Roles (448 threads, one CTA per SM -- the accumulators take up to 512 TMEM columns):
-//   warps 0-3   epilogue at the end of a segment: TMEM -> block diagonals summed over the rows -> shared -> red.global
-//   warps 4-11  the previous layer's BatchNorm + ReLU applied in place to a landed input tile (generic proxy, then
-//               fence.proxy.async); idle when the input needs no transform
-//   warp 12     TMA producer: the input tile and the dy tile of a step into one ring slot, one mbarrier complete_tx
-//   warp 13     TMEM allocation + MMA issue (one thread); tcgen05.commit frees ring slots
-// Work: the (image, row tile, x) steps of a layer are cut into equal contiguous ranges, one per CTA; a CTA marches along x
-// inside a row tile (each input plane serves KX output planes) and flushes its accumulators when it leaves the tile.
+//   warps 4-11  operand transforms on a landed tile (generic proxy, then fence.proxy.async): the previous layer's BatchNorm + ReLU
+//               on the input (MODE 1), BatchNorm backward's apply pass on (g, y) -> dy (MODE 2, the first layer), the re-layout of
+//               interleaved mode (MODE 3, + BatchNorm + ReLU); idle in MODE 0
+//   warp 12     TMA producer: the input tile and the dy tile(s) of a step into one ring slot, one mbarrier complete_tx; ~128 KB
+//               of loads in flight per SM
+//   warp 13     TMEM allocation + MMA issue; the whole warp runs the loop (uniform datapath), x taps and the per-tap MMA list are
+//               compile-time for the common shapes; one wait and one tcgen05.commit per step
+//   warps 0-11  epilogue, ONCE per CTA (the accumulators run on across row tiles: block (r, r') means the same tap everywhere):
+//               three warps per TMEM lane quadrant read the block diagonals, sum them over the rows, and the CTA adds its
+//               [tap][ci][co] block to the global accumulator with vector reductions
+// Work: the (image, row tile, x) steps of a layer are cut into equal contiguous ranges, one per CTA; a CTA marches along x inside a
+// row tile (each input plane serves KX output planes) and re-fills its ring when it crosses into the next tile.  dy planes whose
+// accumulators do not fit in TMEM beside each other go to CTA "kinds" on grid.y.
 #include <cuda.h>
 
 #include <algorithm>
