@@ -796,7 +796,8 @@ static const char* configure(const HcuConvDesc* d, Config& c, bool bnb = false) 
   p.total_steps = (int)total;
   // equal contiguous step ranges, one CTA per SM (and kind); no range shorter than 16 planes (pipeline fill + flush)
   int gx = std::max(1, num_sms() / c.kinds);
-  gx = (int)std::max(1LL, std::min<long long>(gx, total / 16));
+  static const int min_steps = std::max(1, env_int("HCU_ROWS_MINSTEPS", 16));
+  gx = (int)std::max(1LL, std::min<long long>(gx, total / min_steps));
   {
     // (fewer, longer CTAs to save end-of-kernel reductions were measured and lose: the epilogue is bound by its own instructions
     // per CTA, not by the L2's reduction rate -- 32 -> 64 layer 77 us with 143 CTAs, 106 us with 50)
